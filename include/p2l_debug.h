@@ -1,0 +1,58 @@
+/* Kernel-level C-ABI used by the parity tests (tests/test_conv_gemm_gpu.py): one launch of the
+ * tcgen05 implicit-GEMM convolution with an explicit epilogue description. Not part of the
+ * drop-in boundary (that is include/p2l.h); exported so that every kernel can be checked against
+ * the oracle in isolation. All pointers are device pointers owned by the caller. */
+#ifndef P2L_DEBUG_H
+#define P2L_DEBUG_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct p2l_conv_args {
+    /* A: bf16 NHWC */
+    const void* A;
+    int A_N, A_H, A_W, A_C, a_c0, Cin;
+    /* B: bf16 [batch][Cout][kh*kw*Cin] */
+    const void* B;
+    int Cout, B_batch, kh, kw, pad_h, pad_w;
+    /* output pixel grid, tile N, mode (0 fwd, 1 bwd) */
+    int NI, H, W, BN, mode;
+    /* forward epilogue */
+    float alpha;
+    const float* alpha_ptr;
+    const float* bias;
+    const void* resid;
+    int resid_C, resid_shift;
+    void* raw;
+    int raw_C;
+    float* raw_f32;
+    int raw_f32_C;
+    const float* aff_a;
+    const float* aff_s;
+    int aff_stride, relu;
+    void* act;
+    int act_C, act_up;
+    void* act_lo;
+    float* img_nchw;
+    /* backward epilogue */
+    const void* saved;
+    int saved_C;
+    float* stat0;
+    float* stat1;
+    int stat_stride;
+    const void* addin;
+    int addin_C, addin_climit, addin_pool;
+    void* dx;
+    int dx_C;
+    float* dx_f32;
+    int dx_f32_C;
+} p2l_conv_args;
+
+/* returns 0 on success, <0 on error (see p2l_last_error) */
+int p2l_debug_conv(const p2l_conv_args* args, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

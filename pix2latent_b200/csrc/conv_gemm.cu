@@ -1,0 +1,168 @@
+// Host side of the tcgen05 implicit-GEMM: TMA descriptor construction, tile-shape choice,
+// template dispatch. The kernel itself is in conv_gemm.cuh.
+#include "conv_gemm.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace p2l {
+
+// ----------------------------------------------------------------------------- errors
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ----------------------------------------------------------------------------- TMA maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess || !p) {
+            set_error("cuTensorMapEncodeTiled not available from the driver");
+            return nullptr;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims,
+                       const cuuint64_t* strides_bytes /*rank-1*/, const cuuint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return -1;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims,
+                    strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]",
+                  (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                  (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                  box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+        return -1;
+    }
+    return 0;
+}
+
+static int pow2_ceil(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// ----------------------------------------------------------------------------- build
+int conv_op_build(ConvOp* op, const ConvDesc& d) {
+    if (d.Cin <= 0 || d.Cin % kBK != 0) {
+        set_error("conv_op_build: Cin=%d must be a positive multiple of %d", d.Cin, kBK);
+        return -1;
+    }
+    if (d.A_C % 8 != 0 || (reinterpret_cast<uintptr_t>(d.A) & 15) || (reinterpret_cast<uintptr_t>(d.B) & 15)) {
+        set_error("conv_op_build: A/B must be 16-byte aligned with channel count %% 8 == 0");
+        return -1;
+    }
+    if (d.BN != 16 && d.BN != 64 && d.BN != 128 && d.BN != 256) {
+        set_error("conv_op_build: unsupported BN=%d", d.BN);
+        return -1;
+    }
+    std::memset(op, 0, sizeof(*op));
+    ConvGemmParams p = d.epi;
+    p.NI = d.NI; p.H = d.H; p.W = d.W;
+    // tile box: up to 16 wide, up to 8 high, rest over images
+    int tw = pow2_ceil(d.W); if (tw > 16) tw = 16;
+    int th = pow2_ceil(d.H); if (th > kBM / tw) th = kBM / tw;
+    int nb = kBM / (tw * th);
+    if (d.B_batch > 0 && nb != 1) {
+        set_error("conv_op_build: batched B needs >=128 pixels per image (got %dx%d)", d.H, d.W);
+        return -1;
+    }
+    p.tw = tw; p.th = th; p.nb = nb;
+    p.tiles_w = (d.W + tw - 1) / tw;
+    p.tiles_h = (d.H + th - 1) / th;
+    p.tiles_n = (d.NI + nb - 1) / nb;
+    p.Cout = d.Cout;
+    p.n_tiles = (d.Cout + d.BN - 1) / d.BN;
+    p.taps_h = d.kh; p.taps_w = d.kw; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
+    p.cin_chunks = d.Cin / kBK;
+    p.a_c0 = d.a_c0;
+    p.b_batched = d.B_batch > 0 ? 1 : 0;
+    if (p.alpha == 0.f) p.alpha = 1.f;
+
+    {   // A: {C, W, H, N}
+        cuuint64_t dims[4] = {(cuuint64_t)d.A_C, (cuuint64_t)d.A_W, (cuuint64_t)d.A_H, (cuuint64_t)d.A_N};
+        cuuint64_t str[3] = {(cuuint64_t)d.A_C * 2, (cuuint64_t)d.A_W * d.A_C * 2, (cuuint64_t)d.A_H * d.A_W * d.A_C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+        if (encode_bf16(&op->tmA, d.A, 4, dims, str, box)) return -1;
+    }
+    {   // B: {K, Cout, batch}
+        const cuuint64_t K = (cuuint64_t)d.kh * d.kw * d.Cin;
+        cuuint64_t dims[3] = {K, (cuuint64_t)d.Cout, (cuuint64_t)(d.B_batch > 0 ? d.B_batch : 1)};
+        cuuint64_t str[2] = {K * 2, K * 2 * (cuuint64_t)d.Cout};
+        cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)d.BN, 1};
+        if (encode_bf16(&op->tmB, d.B, 3, dims, str, box)) return -1;
+    }
+    op->p = p;
+    op->BN = d.BN;
+    op->mode = d.mode;
+    const long total = (long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+    op->grid = (int)(total < num_sms() ? total : num_sms());
+    op->flops = 2.0 * d.NI * d.H * d.W * (double)d.Cout * d.kh * d.kw * d.Cin;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- launch
+template <int BN, int MODE>
+static int launch_t(const ConvOp& op, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        P2L_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    conv_gemm_kernel<BN, MODE><<<op.grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(op.tmA, op.tmB, op.p);
+    P2L_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int conv_op_launch(const ConvOp& op, cudaStream_t stream) {
+#define P2L_DISPATCH(bn)                                                          \
+    case bn:                                                                      \
+        return op.mode == EPI_FWD ? launch_t<bn, EPI_FWD>(op, stream)             \
+                                  : launch_t<bn, EPI_BWD>(op, stream);
+    switch (op.BN) {
+        P2L_DISPATCH(16)
+        P2L_DISPATCH(64)
+        P2L_DISPATCH(128)
+        P2L_DISPATCH(256)
+    }
+#undef P2L_DISPATCH
+    set_error("conv_op_launch: unsupported BN=%d", op.BN);
+    return -1;
+}
+
+}  // namespace p2l

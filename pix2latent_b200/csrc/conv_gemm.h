@@ -1,0 +1,53 @@
+// Host-side description of one tcgen05 implicit-GEMM launch (see conv_gemm.cuh).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "conv_gemm.cuh"
+
+namespace p2l {
+
+struct ConvDesc {
+    // A: bf16 NHWC tensor read by TMA
+    const void* A = nullptr;
+    int A_N = 0, A_H = 0, A_W = 0, A_C = 0;
+    int a_c0 = 0;  // first channel used
+    int Cin = 0;   // channels used per tap (multiple of 64)
+    // B: bf16 [batch][Cout][kh*kw*Cin]
+    const void* B = nullptr;
+    int Cout = 0;
+    int B_batch = 0;  // 0: shared weights; >0: one matrix per image
+    int kh = 1, kw = 1, pad_h = 0, pad_w = 0;
+    // output pixel grid
+    int NI = 0, H = 0, W = 0;
+    int BN = 128;
+    int mode = EPI_FWD;
+    ConvGemmParams epi{};  // only the epilogue fields are read from here
+};
+
+struct ConvOp {
+    CUtensorMap tmA, tmB;
+    ConvGemmParams p;
+    int BN, mode, grid;
+    double flops;  // algorithmic 2*M*N*K of this launch
+};
+
+// returns 0 on success; on failure sets the thread-local error string
+int conv_op_build(ConvOp* op, const ConvDesc& d);
+int conv_op_launch(const ConvOp& op, cudaStream_t stream);
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+int num_sms();
+
+#define P2L_CUDA_CHECK(expr)                                                             \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ::p2l::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                             __FILE__, __LINE__);                                        \
+            return -1;                                                                   \
+        }                                                                                \
+    } while (0)
+
+}  // namespace p2l

@@ -1,0 +1,173 @@
+"""Parity of the tcgen05 implicit-GEMM convolution (pix2latent_b200/csrc/conv_gemm.cuh) against
+plain PyTorch fp32 ops on the same bf16-rounded inputs. Every epilogue feature the BigGAN /
+LPIPS path uses is exercised here in isolation (per-kernel parity)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from pix2latent_b200 import _lib
+    return _lib
+
+
+def pack_w(w):
+    """torch conv weight [Cout, Cin, kh, kw] -> bf16 [Cout, kh*kw*Cin] (tap-major, channel-minor)."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous().to(torch.bfloat16)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def run_conv(**kw):
+    L = _lib()
+    a = L.ConvArgs()
+    keep = []
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            keep.append(v)
+            setattr(a, k, v.data_ptr())
+        else:
+            setattr(a, k, v)
+    if a.alpha == 0:
+        a.alpha = 1.0
+    L.check(L.lib().p2l_debug_conv(a, L.current_stream()))
+    torch.cuda.synchronize()
+
+
+def rel_err(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+CASES_FWD = [
+    # N, H, W, Cin, Cout, k, BN
+    (2, 16, 16, 64, 64, 1, 64),
+    (3, 32, 32, 128, 128, 3, 128),
+    (1, 256, 256, 64, 64, 3, 64),
+    (18, 4, 4, 256, 128, 3, 128),
+    (5, 8, 8, 128, 256, 3, 256),
+    (2, 15, 15, 192, 128, 3, 64),
+    (2, 31, 31, 64, 192, 5, 64),
+    (2, 64, 64, 512, 128, 3, 128),
+    (3, 64, 64, 64, 256, 1, 256),
+]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,BN", CASES_FWD)
+def test_conv_fwd_raw(N, H, W, Cin, Cout, k, BN):
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = torch.randn(N, Cin, H, W, device=dev).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(Cout, device=dev)
+    ref = F.conv2d(x.float(), w.float(), bias, padding=k // 2)
+    xa = nhwc(x)
+    out = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    out32 = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.float32)
+    run_conv(A=xa, A_N=N, A_H=H, A_W=W, A_C=Cin, a_c0=0, Cin=Cin, B=pack_w(w), Cout=Cout, kh=k, kw=k,
+             pad_h=k // 2, pad_w=k // 2, NI=N, H=H, W=W, BN=BN, mode=0, bias=bias,
+             raw=out, raw_C=Cout, raw_f32=out32, raw_f32_C=Cout)
+    assert rel_err(out32.permute(0, 3, 1, 2), ref) < 2e-3
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < 6e-3
+
+
+def test_conv_fwd_affine_relu_resid_up():
+    """conv_0/conv_3-style epilogue: bias, skip add (channel-sliced, nearest-upsampled), raw write,
+    per-sample affine + relu, 2x replicated activated write."""
+    torch.manual_seed(1)
+    dev = "cuda"
+    N, H, W, Cin, Cout = 3, 16, 16, 128, 64
+    x = torch.randn(N, Cin, H, W, device=dev).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, 1, 1, device=dev) / Cin ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(Cout, device=dev)
+    skip = torch.randn(N, 2 * Cout, H // 2, W // 2, device=dev).to(torch.bfloat16)  # first Cout channels used
+    a = torch.randn(N, Cout, device=dev)
+    s = torch.randn(N, Cout, device=dev)
+    v = F.conv2d(x.float(), w.float(), bias) + F.interpolate(skip[:, :Cout].float(), scale_factor=2, mode="nearest")
+    y = torch.relu(a[:, :, None, None] * v + s[:, :, None, None])
+    y_up = F.interpolate(y, scale_factor=2, mode="nearest")
+    raw = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    act = torch.zeros(N, 2 * H, 2 * W, Cout, device=dev, dtype=torch.bfloat16)
+    act_lo = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    run_conv(A=nhwc(x), A_N=N, A_H=H, A_W=W, A_C=Cin, Cin=Cin, B=pack_w(w), Cout=Cout, kh=1, kw=1,
+             NI=N, H=H, W=W, BN=64, mode=0, bias=bias, resid=nhwc(skip), resid_C=2 * Cout, resid_shift=1,
+             raw=raw, raw_C=Cout, aff_a=a, aff_s=s, aff_stride=Cout, relu=1,
+             act=act, act_C=Cout, act_up=1, act_lo=act_lo)
+    assert rel_err(raw.permute(0, 3, 1, 2), v) < 6e-3
+    assert rel_err(act_lo.permute(0, 3, 1, 2), y) < 8e-3
+    assert rel_err(act.permute(0, 3, 1, 2), y_up) < 8e-3
+
+
+def test_conv_fwd_rgb_tanh():
+    torch.manual_seed(2)
+    dev = "cuda"
+    N, H, W, Cin = 2, 64, 64, 128
+    x = torch.randn(N, Cin, H, W, device=dev).to(torch.bfloat16)
+    w = (torch.randn(3, Cin, 3, 3, device=dev) / (Cin * 9) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(3, device=dev) * 0.1
+    ref = torch.tanh(F.conv2d(x.float(), w.float(), bias, padding=1))
+    img = torch.zeros(N, 3, H, W, device=dev)
+    run_conv(A=nhwc(x), A_N=N, A_H=H, A_W=W, A_C=Cin, Cin=Cin, B=pack_w(w), Cout=3, kh=3, kw=3, pad_h=1, pad_w=1,
+             NI=N, H=H, W=W, BN=16, mode=0, bias=bias, img_nchw=img)
+    assert (img - ref).abs().max().item() < 5e-3
+
+
+def test_gemm_batched_b_fp32_out():
+    """attention logits: S[b] = theta[b] (4096x64) @ phi[b]^T (1024x64)."""
+    torch.manual_seed(3)
+    dev = "cuda"
+    b, H, W, d, nk = 3, 64, 64, 64, 1024
+    theta = torch.randn(b, H, W, d, device=dev).to(torch.bfloat16)
+    phi = torch.randn(b, nk, d, device=dev).to(torch.bfloat16)
+    ref = torch.einsum("bqd,bkd->bqk", theta.float().reshape(b, H * W, d), phi.float())
+    S = torch.zeros(b, H * W, nk, device=dev)
+    run_conv(A=theta, A_N=b, A_H=H, A_W=W, A_C=d, Cin=d, B=phi, Cout=nk, B_batch=b, kh=1, kw=1,
+             NI=b, H=H, W=W, BN=128, mode=0, raw_f32=S, raw_f32_C=nk)
+    assert rel_err(S, ref) < 2e-3
+
+
+@pytest.mark.parametrize("N,H,W,C,Cout,k,BN,pool", [
+    (3, 16, 16, 128, 128, 3, 128, 0),
+    (2, 32, 32, 64, 256, 1, 128, 1),
+    (18, 4, 4, 128, 64, 3, 64, 0),
+    (5, 8, 8, 64, 128, 1, 128, 0),
+    (1, 128, 128, 64, 64, 3, 64, 0),
+])
+def test_conv_bwd(N, H, W, C, Cout, k, BN, pool):
+    """dgrad-style launch: A = upstream gradient [N,H,W,C], B = transposed/flipped weights
+    [Cout(=forward Cin), k*k*C]; epilogue = relu mask from the saved activation, BN-affine
+    gradient sums, multiply by the affine gain, add the skip gradient."""
+    torch.manual_seed(4)
+    dev = "cuda"
+    g = torch.randn(N, C, H, W, device=dev).to(torch.bfloat16)
+    w = (torch.randn(Cout, C, k, k, device=dev) / (C * k * k) ** 0.5).to(torch.bfloat16)
+    saved = torch.relu(torch.randn(N, Cout, H, W, device=dev)).to(torch.bfloat16)
+    a = torch.randn(N, Cout, device=dev)
+    if pool:
+        addin = torch.randn(N, Cout // 2, 2 * H, 2 * W, device=dev).to(torch.bfloat16)
+        add_ref = F.avg_pool2d(addin.float(), 2) * 4
+    else:
+        addin = torch.randn(N, Cout // 2, H, W, device=dev).to(torch.bfloat16)
+        add_ref = addin.float()
+    acc = F.conv2d(g.float(), w.float(), padding=k // 2)
+    dpre = acc * (saved.float() > 0)
+    s0 = dpre.sum((2, 3))
+    s1 = (dpre * saved.float()).sum((2, 3))
+    dx = dpre * a[:, :, None, None]
+    dx[:, :Cout // 2] += add_ref
+    st0 = torch.zeros(N, Cout, device=dev)
+    st1 = torch.zeros(N, Cout, device=dev)
+    out = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    out32 = torch.zeros(N, H, W, Cout, device=dev)
+    run_conv(A=nhwc(g), A_N=N, A_H=H, A_W=W, A_C=C, Cin=C, B=pack_w(w), Cout=Cout, kh=k, kw=k,
+             pad_h=k // 2, pad_w=k // 2, NI=N, H=H, W=W, BN=BN, mode=1,
+             saved=nhwc(saved), saved_C=Cout, stat0=st0, stat1=st1, stat_stride=Cout,
+             aff_a=a, aff_stride=Cout, addin=nhwc(addin), addin_C=Cout // 2, addin_climit=Cout // 2,
+             addin_pool=pool, dx=out, dx_C=Cout, dx_f32=out32, dx_f32_C=Cout)
+    assert rel_err(out32.permute(0, 3, 1, 2), dx) < 2e-3
+    assert rel_err(out.permute(0, 3, 1, 2), dx) < 6e-3
+    assert rel_err(st0, s0) < 2e-3
+    assert rel_err(st1, s1) < 2e-3
