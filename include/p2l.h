@@ -1,0 +1,124 @@
+/* libp2l — C-ABI of the B200-native latent-inversion inner step.
+ *
+ * Drop-in boundary: in the reference the only caller of the generator and of the
+ * loss is pix2latent/optimizer/closure.py:
+ *     out  = model(**input_args)                              closure.py:51
+ *     loss = loss_fn(out, **target_args).view(b,-1).mean(1)   closure.py:55
+ *     loss.mean().backward()                                  closure.py:58
+ * Every entry point below replaces one of those calls (cited per function). The reference has no
+ * FFI of its own (it is pure Python on torch); the binding a maintainer adds is the ctypes stub
+ * shown in INTEGRATION.md (pix2latent_b200/native.py is that stub).
+ *
+ * Conventions: plain C types; every pointer argument named *_dev is a DEVICE pointer owned by
+ * the caller (torch); `stream` is a cudaStream_t passed as void*; every call is asynchronous and
+ * stream-ordered (no hidden synchronisation); return 0 = ok, <0 = error with the message in
+ * p2l_last_error() (thread-local). A handle is bound to one device and is not thread-safe.
+ * There is no CPU fallback: p2l_create fails on anything that is not an sm_100 GPU.
+ */
+#ifndef P2L_H
+#define P2L_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct p2l_ctx p2l_ctx;
+typedef struct p2l_biggan p2l_biggan;
+typedef struct p2l_lpips p2l_lpips;
+typedef struct p2l_target p2l_target;
+
+#define P2L_MAX_LAYERS 16
+
+/* pytorch_pretrained_biggan/config.py (BigGANConfig) as used by pix2latent/model/biggan.py:26 */
+typedef struct p2l_biggan_config {
+    int n_layers;
+    int up[P2L_MAX_LAYERS], in_mult[P2L_MAX_LAYERS], out_mult[P2L_MAX_LAYERS];
+    int channel_width;      /* ch (128) */
+    int z_dim;              /* 128 */
+    int class_embed_dim;    /* 128 */
+    int attention_pos;      /* SelfAttn inserted before block index attention_pos; <0: none */
+    int n_stats;            /* 51 */
+    float eps;              /* BN eps, 1e-4 */
+    float truncation;       /* selects / interpolates the BN statistics row (biggan.py:50: 1.0) */
+} p2l_biggan_config;
+
+const char* p2l_last_error(void);
+int p2l_version(void);
+/* cumulative number of CUDA kernels this library has launched in this process */
+long p2l_launch_count(void);
+
+/* Bind to a CUDA device. Fails (-1) if the device is not compute capability 10.x. */
+int p2l_create(int device, p2l_ctx** out);
+void p2l_destroy(p2l_ctx* ctx);
+
+/* ---- generator: replaces BigGAN.__init__ / forward (pix2latent/model/biggan.py:23-34, 50-58) */
+int p2l_biggan_create(p2l_ctx* ctx, const p2l_biggan_config* cfg, p2l_biggan** out);
+/* name = state-dict key of pix2latent's BigGAN module after remove_spectral_norm
+ * (e.g. "generator.layers.0.conv_0.weight"); data = fp32, host or device, torch layout. */
+int p2l_biggan_set_tensor(p2l_biggan* m, const char* name, const float* data, long numel);
+/* Pack weights into the bf16 GEMM layouts the kernels read; frees the staging copies. */
+int p2l_biggan_finalize(p2l_biggan* m);
+void p2l_biggan_destroy(p2l_biggan* m);
+/* img_dev[b,3,R,R] fp32 NCHW in (-1,1) = generator(cat(z,c), truncation). Keeps the activations
+ * needed by p2l_biggan_backward for this batch size.                       biggan.py:58 */
+int p2l_biggan_forward(p2l_biggan* m, int b, const float* z_dev, const float* c_dev, float* img_dev,
+                       void* stream);
+/* Given dL/dimg [b,3,R,R] of the LAST forward with this b: dz[b,z_dim], dc[b,class_embed_dim].
+ * dgrad only — no weight gradients.                         closure.py:58 */
+int p2l_biggan_backward(p2l_biggan* m, int b, const float* dimg_dev, float* dz_dev, float* dc_dev,
+                        void* stream);
+/* bytes of device memory held (weights + all cached per-batch plans) */
+long p2l_biggan_device_bytes(p2l_biggan* m);
+/* algorithmic FLOPs (MAC=2) of one forward for batch b through the tensor-core launches, and the
+ * number of kernels launched by forward / backward (for bench.py's gpu_launches) */
+double p2l_biggan_flops(p2l_biggan* m, int b, int backward);
+int p2l_biggan_launches(p2l_biggan* m, int b, int backward);
+
+/* ---- perceptual loss: replaces lpips.LPIPS(net, spatial=True) + ProjectionLoss
+ *      (pix2latent/loss_functions.py:86-148) */
+#define P2L_LPIPS_ALEX 0
+#define P2L_LPIPS_VGG 1
+int p2l_lpips_create(p2l_ctx* ctx, int net, p2l_lpips** out);
+/* names: "net.slice{k}.{idx}.weight|bias" (torchvision feature indices) and "lin{k}.weight" */
+int p2l_lpips_set_tensor(p2l_lpips* m, const char* name, const float* data, long numel);
+int p2l_lpips_finalize(p2l_lpips* m);
+void p2l_lpips_destroy(p2l_lpips* m);
+
+/* Cache everything that depends only on the target: unit-normalised backbone features of
+ * target[3,H,W], the adjoint-upsampled weight maps and sum(W). weight/mask may be NULL (ones).
+ * rec_type 1 = l1, 2 = l2 (ReconstructionLoss); beta = LPIPS weight (ProjectionLoss: 10);
+ * rec_weight = weight of the pixel term (1 for ProjectionLoss, 0 for PerceptualLoss alone),
+ * per_weight likewise (0 for ReconstructionLoss alone).          loss_functions.py:97-100 */
+int p2l_target_create(p2l_lpips* m, const float* target_dev, const float* weight_dev,
+                      const float* mask_dev, int H, int W, int rec_type, float rec_weight,
+                      float per_weight, p2l_target** out, void* stream);
+void p2l_target_destroy(p2l_target* t);
+
+/* loss_dev[b] = rec_weight*rec + per_weight*per for img_dev[b,3,H,W]. With want_grad, also
+ * prepares d loss_i / d img_i (unit upstream) for p2l_loss_backward.    loss_functions.py:97 */
+int p2l_loss_forward(p2l_lpips* m, p2l_target* t, int b, const float* img_dev, float* loss_dev,
+                     int want_grad, void* stream);
+/* dimg_dev[b,3,H,W] = dloss_dev[b] * d loss_b / d img_b  (of the last p2l_loss_forward) */
+int p2l_loss_backward(p2l_lpips* m, p2l_target* t, int b, const float* dloss_dev, float* dimg_dev,
+                      void* stream);
+double p2l_lpips_flops(p2l_lpips* m, int b, int H, int W, int backward);
+int p2l_lpips_launches(p2l_lpips* m, int backward);
+
+/* ---- fused step: generator fwd + loss (+ backward to the latent) in one stream-ordered launch
+ * sequence — what closure.py:51-58 does per mini-batch. The upstream gradient of sample i is
+ * grad_scale * (dloss_dev ? dloss_dev[i] : 1); closure.py:58 (`loss.mean().backward()`) is
+ * grad_scale = 1/b_chunk. loss_dev[b]; dz/dc/img may be NULL when not wanted. */
+int p2l_biggan_step(p2l_biggan* g, p2l_lpips* l, p2l_target* t, int b, const float* z_dev,
+                    const float* c_dev, int want_grad, float grad_scale, const float* dloss_dev,
+                    float* loss_dev, float* dz_dev, float* dc_dev, float* img_dev, void* stream);
+
+/* ---- measurement hooks (bench.py): while enabled, every tensor-core launch is bracketed by
+ * CUDA events on its stream; p2l_profile_read synchronises and returns the summed duration
+ * (ms), the number of launches and their algorithmic FLOPs since the last enable. */
+void p2l_profile_enable(int on);
+int p2l_profile_read(double* conv_ms, long* conv_launches, double* conv_flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

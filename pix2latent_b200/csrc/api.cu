@@ -1,0 +1,187 @@
+// C-ABI entry points (include/p2l.h). Thin: argument checks, handle casts, error strings.
+#include "p2l.h"
+
+#include "biggan.h"
+#include "lpips.h"
+
+#define P2L_EXPORT extern "C" __attribute__((visibility("default")))
+
+using namespace p2l;
+
+struct p2l_ctx { Ctx c; };
+struct p2l_biggan { BigGAN g; };
+struct p2l_lpips { Lpips l; };
+struct p2l_target { Target* t; };
+
+#define P2L_TRY_BEGIN try {
+#define P2L_TRY_END                                             \
+    }                                                           \
+    catch (const std::exception& e) {                           \
+        set_error("exception: %s", e.what());                   \
+        return -1;                                              \
+    }
+
+P2L_EXPORT int p2l_version(void) { return 1; }
+P2L_EXPORT long p2l_launch_count(void) { return launch_count(); }
+
+P2L_EXPORT int p2l_create(int device, p2l_ctx** out) {
+    if (!out) { set_error("p2l_create: out is NULL"); return -1; }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        set_error("p2l_create: no CUDA device visible (this library has no CPU fallback)");
+        return -1;
+    }
+    if (device < 0 || device >= n) { set_error("p2l_create: device %d out of range (%d devices)", device, n); return -1; }
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+    if (major != 10) {
+        set_error("p2l_create: device %d is sm_%d%d; this library is built for sm_100a only", device, major, minor);
+        return -1;
+    }
+    P2L_CUDA_CHECK(cudaSetDevice(device));
+    p2l_ctx* c = new p2l_ctx();
+    c->c.device = device;
+    cudaDeviceGetAttribute(&c->c.sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return 0;
+}
+P2L_EXPORT void p2l_destroy(p2l_ctx* ctx) { delete ctx; }
+
+// ----------------------------------------------------------------------------- BigGAN
+P2L_EXPORT int p2l_biggan_create(p2l_ctx* ctx, const p2l_biggan_config* cfg, p2l_biggan** out) {
+    if (!ctx || !cfg || !out) { set_error("p2l_biggan_create: NULL argument"); return -1; }
+    P2L_TRY_BEGIN
+    p2l_biggan* m = new p2l_biggan();
+    m->g.ctx = &ctx->c;
+    m->g.cfg = *cfg;
+    *out = m;
+    return 0;
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_biggan_set_tensor(p2l_biggan* m, const char* name, const float* data, long numel) {
+    if (!m || !name || !data) { set_error("p2l_biggan_set_tensor: NULL argument"); return -1; }
+    if (m->g.finalized) { set_error("p2l_biggan_set_tensor after finalize"); return -1; }
+    P2L_TRY_BEGIN
+    return m->g.stage.set(name, data, numel);
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_biggan_finalize(p2l_biggan* m) {
+    if (!m) { set_error("p2l_biggan_finalize: NULL"); return -1; }
+    P2L_TRY_BEGIN
+    return m->g.finalize();
+    P2L_TRY_END
+}
+P2L_EXPORT void p2l_biggan_destroy(p2l_biggan* m) { delete m; }
+P2L_EXPORT int p2l_biggan_forward(p2l_biggan* m, int b, const float* z, const float* c, float* img, void* stream) {
+    if (!m || b <= 0 || !z || !c) { set_error("p2l_biggan_forward: bad argument"); return -1; }
+    P2L_TRY_BEGIN
+    return m->g.forward(b, z, c, img, static_cast<cudaStream_t>(stream));
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_biggan_backward(p2l_biggan* m, int b, const float* dimg, float* dz, float* dc, void* stream) {
+    if (!m || b <= 0 || !dimg || !dz || !dc) { set_error("p2l_biggan_backward: bad argument"); return -1; }
+    P2L_TRY_BEGIN
+    return m->g.backward(b, dimg, dz, dc, static_cast<cudaStream_t>(stream));
+    P2L_TRY_END
+}
+P2L_EXPORT long p2l_biggan_device_bytes(p2l_biggan* m) {
+    if (!m) return 0;
+    return (long)m->g.device_bytes();
+}
+P2L_EXPORT double p2l_biggan_flops(p2l_biggan* m, int b, int backward) {
+    if (!m) return 0;
+    return m->g.flops(b, backward);
+}
+P2L_EXPORT int p2l_biggan_launches(p2l_biggan* m, int b, int backward) {
+    (void)m; (void)b; (void)backward;
+    return 0;  // superseded by p2l_launch_count(); kept for ABI stability
+}
+
+// ----------------------------------------------------------------------------- LPIPS
+P2L_EXPORT int p2l_lpips_create(p2l_ctx* ctx, int net, p2l_lpips** out) {
+    if (!ctx || !out) { set_error("p2l_lpips_create: NULL argument"); return -1; }
+    if (net != P2L_LPIPS_ALEX && net != P2L_LPIPS_VGG) { set_error("p2l_lpips_create: unknown net %d", net); return -1; }
+    P2L_TRY_BEGIN
+    p2l_lpips* m = new p2l_lpips();
+    m->l.ctx = &ctx->c;
+    m->l.net = net;
+    *out = m;
+    return 0;
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_lpips_set_tensor(p2l_lpips* m, const char* name, const float* data, long numel) {
+    if (!m || !name || !data) { set_error("p2l_lpips_set_tensor: NULL argument"); return -1; }
+    if (m->l.finalized) { set_error("p2l_lpips_set_tensor after finalize"); return -1; }
+    P2L_TRY_BEGIN
+    return m->l.stage.set(name, data, numel);
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_lpips_finalize(p2l_lpips* m) {
+    if (!m) { set_error("p2l_lpips_finalize: NULL"); return -1; }
+    P2L_TRY_BEGIN
+    return m->l.finalize();
+    P2L_TRY_END
+}
+P2L_EXPORT void p2l_lpips_destroy(p2l_lpips* m) { delete m; }
+
+P2L_EXPORT int p2l_target_create(p2l_lpips* m, const float* target, const float* weight, const float* mask, int H, int W,
+                                 int rec_type, float rec_weight, float per_weight, p2l_target** out, void* stream) {
+    if (!m || !target || !out || H <= 0 || W <= 0) { set_error("p2l_target_create: bad argument"); return -1; }
+    if (rec_type != 1 && rec_type != 2) { set_error("p2l_target_create: rec_type must be 1 (l1) or 2 (l2)"); return -1; }
+    P2L_TRY_BEGIN
+    Target* t = m->l.make_target(target, weight, mask, H, W, rec_type, rec_weight, per_weight, static_cast<cudaStream_t>(stream));
+    if (!t) return -1;
+    p2l_target* h = new p2l_target();
+    h->t = t;
+    *out = h;
+    return 0;
+    P2L_TRY_END
+}
+P2L_EXPORT void p2l_target_destroy(p2l_target* t) {
+    if (t) { delete t->t; delete t; }
+}
+P2L_EXPORT int p2l_loss_forward(p2l_lpips* m, p2l_target* t, int b, const float* img, float* loss, int want_grad, void* stream) {
+    if (!m || !t || b <= 0 || !img || !loss) { set_error("p2l_loss_forward: bad argument"); return -1; }
+    P2L_TRY_BEGIN
+    return m->l.loss_forward(*t->t, b, img, loss, want_grad, static_cast<cudaStream_t>(stream));
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_loss_backward(p2l_lpips* m, p2l_target* t, int b, const float* dloss, float* dimg, void* stream) {
+    if (!m || !t || b <= 0 || !dloss || !dimg) { set_error("p2l_loss_backward: bad argument"); return -1; }
+    P2L_TRY_BEGIN
+    return m->l.loss_backward(*t->t, b, dloss, dimg, static_cast<cudaStream_t>(stream));
+    P2L_TRY_END
+}
+P2L_EXPORT double p2l_lpips_flops(p2l_lpips* m, int b, int H, int W, int backward) {
+    if (!m) return 0;
+    return m->l.flops(b, H, W, backward);
+}
+P2L_EXPORT int p2l_lpips_launches(p2l_lpips* m, int backward) {
+    (void)m; (void)backward;
+    return 0;
+}
+
+P2L_EXPORT void p2l_profile_enable(int on) { profile_enable(on); }
+P2L_EXPORT int p2l_profile_read(double* conv_ms, long* conv_launches, double* conv_flops) {
+    return profile_read(conv_ms, conv_launches, conv_flops);
+}
+
+// ----------------------------------------------------------------------------- fused step
+P2L_EXPORT int p2l_biggan_step(p2l_biggan* g, p2l_lpips* l, p2l_target* t, int b, const float* z, const float* c,
+                               int want_grad, float grad_scale, const float* dloss, float* loss, float* dz, float* dc,
+                               float* img, void* stream) {
+    if (!g || !l || !t || b <= 0 || !z || !c || !loss) { set_error("p2l_biggan_step: bad argument"); return -1; }
+    if (want_grad && (!dz || !dc)) { set_error("p2l_biggan_step: want_grad needs dz and dc"); return -1; }
+    P2L_TRY_BEGIN
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g->g.forward(b, z, c, img, st)) return -1;
+    const float* im = img ? img : g->g.last_image(b);
+    if (l->l.loss_forward(*t->t, b, im, loss, want_grad, st)) return -1;
+    if (!want_grad) return 0;
+    float* dimg = l->l.unit_grad(*t->t, b);
+    if (!dimg) return -1;
+    if (g->g.backward(b, dimg, dz, dc, st, grad_scale, dloss)) return -1;
+    return 0;
+    P2L_TRY_END
+}

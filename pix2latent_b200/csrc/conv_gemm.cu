@@ -5,6 +5,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <utility>
+#include <vector>
 
 namespace p2l {
 
@@ -17,6 +19,36 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+static long g_launches = 0;
+void count_launch() { ++g_launches; }
+long launch_count() { return g_launches; }
+
+// ---- optional per-launch event timing of the tensor-core kernel (bench.py roofline leg)
+static bool g_prof = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static size_t g_prof_used = 0;
+static double g_prof_flops = 0;
+void profile_enable(int on) {
+    g_prof = on != 0;
+    g_prof_used = 0;
+    g_prof_flops = 0;
+}
+int profile_read(double* conv_ms, long* conv_launches, double* conv_flops) {
+    double ms = 0;
+    for (size_t i = 0; i < g_prof_used; ++i) {
+        if (cudaEventSynchronize(g_prof_events[i].second) != cudaSuccess) { set_error("profile_read: event sync failed"); return -1; }
+        float t = 0;
+        cudaEventElapsedTime(&t, g_prof_events[i].first, g_prof_events[i].second);
+        ms += t;
+    }
+    if (conv_ms) *conv_ms = ms;
+    if (conv_launches) *conv_launches = (long)g_prof_used;
+    if (conv_flops) *conv_flops = g_prof_flops;
+    g_prof_used = 0;
+    g_prof_flops = 0;
+    return 0;
+}
 
 int num_sms() {
     static int n = 0;
@@ -144,7 +176,22 @@ static int launch_t(const ConvOp& op, cudaStream_t stream) {
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_prof) {
+        if (g_prof_used == g_prof_events.size()) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            g_prof_events.emplace_back(e0, e1);
+        }
+        e0 = g_prof_events[g_prof_used].first;
+        e1 = g_prof_events[g_prof_used].second;
+        ++g_prof_used;
+        g_prof_flops += op.flops;
+        cudaEventRecord(e0, stream);
+    }
     conv_gemm_kernel<BN, MODE><<<op.grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(op.tmA, op.tmB, op.p);
+    if (g_prof) cudaEventRecord(e1, stream);
+    count_launch();
     P2L_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -48,7 +48,7 @@ struct ConvGemmParams {
     int b_batched;   // B tensor map's 3rd coordinate = image index
     // ---- epilogue, forward
     float alpha;             // scale on the accumulator
-    const float* alpha_ptr;  // optional device scalar multiplied into alpha (attention gamma)
+    const float* alpha_ptr;  // optional device scalar multiplied into alpha (attention gamma); both modes
     const float* bias;       // [Cout] or null
     const __nv_bfloat16* resid;  // skip input, NHWC [NI, H>>resid_shift, W>>resid_shift, resid_C]
     int resid_C, resid_shift;
@@ -225,7 +225,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int ni = row / (p.tw * p.th);
         const int rows_per_img = p.tw * p.th;
         float alpha = p.alpha;
-        if (MODE == EPI_FWD && p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
+        if (p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
@@ -355,7 +355,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     // ---------------------------------------------------------- backward
                     float y[CH];
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) y[j] = 0.f;
+                    for (int j = 0; j < CH; ++j) { y[j] = 0.f; v[j] *= alpha; }
                     if (p.saved) {
                         if (valid) {
                             const uint4* src = reinterpret_cast<const uint4*>(p.saved + pix * p.saved_C + cbase);

@@ -39,6 +39,10 @@ int conv_op_launch(const ConvOp& op, cudaStream_t stream);
 void set_error(const char* fmt, ...);
 const char* get_error();
 int num_sms();
+void count_launch();  // every kernel launch of the library is counted (bench.py gpu_launches)
+long launch_count();
+void profile_enable(int on);
+int profile_read(double* conv_ms, long* conv_launches, double* conv_flops);
 
 #define P2L_CUDA_CHECK(expr)                                                             \
     do {                                                                                 \

@@ -1,0 +1,715 @@
+// Non-contraction kernels of the inversion step (see kernels.h). These are the HBM-bound glue
+// between the tcgen05 convolutions: latent-side GEMVs, pooling, softmax, the LPIPS distance and
+// the loss reductions (warp-shuffle + one atomic per block).
+#include "kernels.h"
+#include "conv_gemm.h"
+
+#include <cstdint>
+
+namespace p2l {
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float b2f(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ bf16 f2b(float x) { return __float2bfloat16_rn(x); }
+
+// ============================================================================= latent side
+__global__ void concat_cond_kernel(const float* z, const float* c, float* cond, int b, int zd, int cd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int D = zd + cd;
+    if (i >= b * D) return;
+    const int bi = i / D, k = i % D;
+    cond[i] = k < zd ? z[bi * zd + k] : c[bi * cd + (k - zd)];
+}
+void k_concat_cond(const float* z, const float* c, float* cond, int b, int zd, int cd, cudaStream_t st) {
+    concat_cond_kernel<<<cdiv((long)b * (zd + cd), 256), 256, 0, st>>>(z, c, cond, b, zd, cd); count_launch();
+}
+
+// one warp per channel; cond staged in shared memory
+__global__ void cond_affine_kernel(const float* __restrict__ cond, const float* __restrict__ Ws,
+                                   const float* __restrict__ Wo, const float* __restrict__ mean,
+                                   const float* __restrict__ inv_std, float* a, float* s, int b,
+                                   int cdim, int C, int stride) {
+    extern __shared__ float sc[];  // [b, cdim]
+    for (int i = threadIdx.x; i < b * cdim; i += blockDim.x) sc[i] = cond[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ch = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (ch >= C) return;
+    const float* ws = Ws + (long)ch * cdim;
+    const float* wo = Wo + (long)ch * cdim;
+    const float m = mean[ch], is = inv_std[ch];
+    for (int bi = 0; bi < b; ++bi) {
+        float ds = 0.f, dof = 0.f;
+        for (int k = lane; k < cdim; k += 32) {
+            const float cv = sc[bi * cdim + k];
+            ds = fmaf(cv, ws[k], ds);
+            dof = fmaf(cv, wo[k], dof);
+        }
+        ds = warp_sum(ds);
+        dof = warp_sum(dof);
+        if (lane == 0) {
+            const float av = (1.f + ds) * is;
+            a[(long)bi * stride + ch] = av;
+            s[(long)bi * stride + ch] = dof - m * av;
+        }
+    }
+}
+void k_cond_affine(const float* cond, const float* Ws, const float* Wo, const float* mean,
+                   const float* inv_std, float* a, float* s, int b, int cdim, int C_cond, int stride,
+                   cudaStream_t st) {
+    const int warps = 8;
+    cond_affine_kernel<<<cdiv(C_cond, warps), warps * 32, (size_t)b * cdim * sizeof(float), st>>>(
+        cond, Ws, Wo, mean, inv_std, a, s, b, cdim, C_cond, stride); count_launch();
+}
+
+__global__ void uncond_affine_kernel(const float* weight, const float* bias, const float* mean,
+                                     const float* inv_std, float* a, float* s, int b, int C_cond,
+                                     int C_unc, int stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b * C_unc) return;
+    const int bi = i / C_unc, ch = i % C_unc;
+    const float av = weight[ch] * inv_std[C_cond + ch];
+    a[(long)bi * stride + C_cond + ch] = av;
+    s[(long)bi * stride + C_cond + ch] = bias[ch] - mean[C_cond + ch] * av;
+}
+void k_uncond_affine(const float* weight, const float* bias, const float* mean, const float* inv_std,
+                     float* a, float* s, int b, int C_cond, int C_unc, int stride, cudaStream_t st) {
+    uncond_affine_kernel<<<cdiv((long)b * C_unc, 256), 256, 0, st>>>(weight, bias, mean, inv_std, a, s, b,
+                                                                     C_cond, C_unc, stride); count_launch();
+}
+
+__global__ void gen_z_kernel(const float* __restrict__ cond, const float* __restrict__ W,
+                             const float* __restrict__ bias, const float* __restrict__ a,
+                             const float* __restrict__ s, int aff_stride, bf16* raw, bf16* act, int b,
+                             int cdim, int J, int C) {
+    extern __shared__ float sc[];
+    for (int i = threadIdx.x; i < b * cdim; i += blockDim.x) sc[i] = cond[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (j >= J) return;
+    const float* w = W + (long)j * cdim;
+    const int ch = j % C;
+    const float bj = bias[j];
+    for (int bi = 0; bi < b; ++bi) {
+        float d = 0.f;
+        for (int k = lane; k < cdim; k += 32) d = fmaf(sc[bi * cdim + k], w[k], d);
+        d = warp_sum(d);
+        if (lane == 0) {
+            const float h = d + bj;
+            raw[(long)bi * J + j] = f2b(h);
+            const float y = fmaf(a[(long)bi * aff_stride + ch], h, s[(long)bi * aff_stride + ch]);
+            act[(long)bi * J + j] = f2b(fmaxf(y, 0.f));
+        }
+    }
+}
+void k_gen_z(const float* cond, const float* W, const float* bias, const float* a, const float* s,
+             int aff_stride, bf16* raw, bf16* act, int b, int cdim, int J, int C, cudaStream_t st) {
+    const int warps = 8;
+    gen_z_kernel<<<cdiv(J, warps), warps * 32, (size_t)b * cdim * sizeof(float), st>>>(
+        cond, W, bias, a, s, aff_stride, raw, act, b, cdim, J, C); count_launch();
+}
+
+__global__ void bn_grad_finalize_kernel(const float* S0, const float* S1, const float* a, const float* s,
+                                        const float* mean, const float* inv_std, float* G, int b, int C,
+                                        int stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b * C) return;
+    const int bi = i / C, ch = i % C;
+    const long o = (long)bi * stride + ch;
+    const float av = a[o], sv = s[o];
+    const float ds = S0[o];
+    const float da = fabsf(av) > 1e-20f ? (S1[o] - sv * ds) / av : 0.f;
+    G[(long)bi * 2 * C + ch] = inv_std[ch] * (da - mean[ch] * ds);
+    G[(long)bi * 2 * C + C + ch] = ds;
+}
+void k_bn_grad_finalize(const float* S0, const float* S1, const float* a, const float* s,
+                        const float* mean, const float* inv_std, float* G, int b, int C_cond,
+                        int stride, cudaStream_t st) {
+    bn_grad_finalize_kernel<<<cdiv((long)b * C_cond, 256), 256, 0, st>>>(S0, S1, a, s, mean, inv_std, G, b,
+                                                                         C_cond, stride); count_launch();
+}
+
+// dcond[b,k] += sum_j G[b,j] W[j,k]; block = cdim threads (one per k), 128 rows of W per block
+constexpr int kDcRows = 128;
+__global__ void dcond_accum_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ W,
+                                   float* dcond, int b, int J, int cdim) {
+    extern __shared__ float sg[];  // [b][kDcRows]
+    const int j0 = blockIdx.x * kDcRows;
+    const int nj = min(kDcRows, J - j0);
+    for (int i = threadIdx.x; i < b * kDcRows; i += blockDim.x) {
+        const int bi = i / kDcRows, jj = i % kDcRows;
+        sg[i] = jj < nj ? G[(long)bi * ldg + j0 + jj] : 0.f;
+    }
+    __syncthreads();
+    const int k = threadIdx.x;
+    if (k >= cdim) return;
+    for (int b0 = 0; b0 < b; b0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int jj = 0; jj < nj; ++jj) {
+            const float w = W[(long)(j0 + jj) * cdim + k];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (b0 + i < b) acc[i] = fmaf(sg[(b0 + i) * kDcRows + jj], w, acc[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (b0 + i < b) atomicAdd(dcond + (long)(b0 + i) * cdim + k, acc[i]);
+        }
+    }
+}
+void k_dcond_accum(const float* G, int ldg, const float* W, float* dcond, int b, int J, int cdim,
+                   cudaStream_t st) {
+    dcond_accum_kernel<<<cdiv(J, kDcRows), cdim, (size_t)b * kDcRows * sizeof(float), st>>>(G, ldg, W, dcond, b, J,
+                                                                                          cdim); count_launch();
+}
+
+__global__ void bf16_to_f32_kernel(const bf16* src, float* dst, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = b2f(src[i]);
+}
+void k_bf16_to_f32(const bf16* src, float* dst, long n, cudaStream_t st) {
+    bf16_to_f32_kernel<<<cdiv(n, 256), 256, 0, st>>>(src, dst, n); count_launch();
+}
+
+__global__ void split_dcond_kernel(const float* dcond, float* dz, float* dc, int b, int zd, int cd, float scale,
+                                   const float* row_scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int D = zd + cd;
+    if (i >= b * D) return;
+    const int bi = i / D, k = i % D;
+    const float sc = row_scale ? scale * row_scale[bi] : scale;
+    if (k < zd) dz[bi * zd + k] = dcond[i] * sc;
+    else dc[bi * cd + k - zd] = dcond[i] * sc;
+}
+void k_split_dcond(const float* dcond, float* dz, float* dc, int b, int zd, int cd, float scale,
+                   const float* row_scale, cudaStream_t st) {
+    split_dcond_kernel<<<cdiv((long)b * (zd + cd), 256), 256, 0, st>>>(dcond, dz, dc, b, zd, cd, scale, row_scale); count_launch();
+}
+
+__global__ void fill_kernel(float* p, float v, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+void k_fill_f32(float* p, float v, long n, cudaStream_t st) { fill_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, v, n); count_launch(); }
+
+// ============================================================================= BigGAN glue
+// block: 64 channels x 4 pixel lanes; each block covers 64 low-res pixels of one image
+__global__ void pool_bnrelu_bwd_kernel(const bf16* __restrict__ g_up, const bf16* __restrict__ y_lo,
+                                       const float* __restrict__ a, int aff_stride, float* S0, float* S1,
+                                       int stat_stride, bf16* dx, int H, int W, int C) {
+    __shared__ float r0[4][64], r1[4][64];
+    const int cx = threadIdx.x, py = threadIdx.y;
+    const int c = blockIdx.y * 64 + cx;
+    const int bi = blockIdx.z;
+    const int HW = H * W;
+    const int p0 = blockIdx.x * 64;
+    const float av = a[(long)bi * aff_stride + c];
+    float s0 = 0.f, s1 = 0.f;
+    const int W2 = 2 * W;
+    for (int pp = py; pp < 64; pp += 4) {
+        const int p = p0 + pp;
+        if (p >= HW) break;
+        const int y = p / W, x = p % W;
+        const long base = (((long)bi * 2 * H + 2 * y) * W2 + 2 * x) * C + c;
+        const float g = b2f(g_up[base]) + b2f(g_up[base + C]) + b2f(g_up[base + (long)W2 * C]) +
+                        b2f(g_up[base + (long)W2 * C + C]);
+        const long o = ((long)bi * HW + p) * C + c;
+        const float yv = b2f(y_lo[o]);
+        const float dpre = yv > 0.f ? g : 0.f;
+        s0 += dpre;
+        s1 += dpre * yv;
+        dx[o] = f2b(av * dpre);
+    }
+    r0[py][cx] = s0;
+    r1[py][cx] = s1;
+    __syncthreads();
+    if (py == 0) {
+        s0 = r0[0][cx] + r0[1][cx] + r0[2][cx] + r0[3][cx];
+        s1 = r1[0][cx] + r1[1][cx] + r1[2][cx] + r1[3][cx];
+        atomicAdd(S0 + (long)bi * stat_stride + c, s0);
+        atomicAdd(S1 + (long)bi * stat_stride + c, s1);
+    }
+}
+void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int aff_stride, float* S0,
+                       float* S1, int stat_stride, bf16* dx, int b, int H, int W, int C, cudaStream_t st) {
+    dim3 grid(cdiv((long)H * W, 64), C / 64, b), block(64, 4);
+    pool_bnrelu_bwd_kernel<<<grid, block, 0, st>>>(g_up, y_lo, a, aff_stride, S0, S1, stat_stride, dx, H, W, C); count_launch();
+}
+
+// ============================================================================= attention glue
+__global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, int xC, int c0, int C, bf16* out, bf16* outT,
+                                    unsigned char* idx, int b, int H, int W) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int Ho = H / 2, Wo = W / 2;
+    const long total = (long)b * Ho * Wo * C;
+    if (i >= total) return;
+    const int c = i % C;
+    const long q = i / C;
+    const int ox = q % Wo, oy = (q / Wo) % Ho, bi = q / ((long)Wo * Ho);
+    float best = 0.f;
+    int bidx = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int y = 2 * oy + (k >> 1), xx = 2 * ox + (k & 1);
+        const float v = b2f(x[(((long)bi * H + y) * W + xx) * xC + c0 + c]);
+        if (k == 0 || v > best) { best = v; bidx = k; }
+    }
+    const int nk = Ho * Wo, kk = oy * Wo + ox;
+    if (out) out[((long)bi * nk + kk) * C + c] = f2b(best);
+    if (outT) outT[((long)bi * C + c) * nk + kk] = f2b(best);
+    idx[i] = (unsigned char)bidx;
+}
+void k_maxpool2_fwd(const bf16* x, int xC, int c0, int C, bf16* out, bf16* outT, unsigned char* idx, int b,
+                    int H, int W, cudaStream_t st) {
+    const long total = (long)b * (H / 2) * (W / 2) * C;
+    maxpool2_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, xC, c0, C, out, outT, idx, b, H, W); count_launch();
+}
+
+__global__ void maxpool2_bwd_kernel(const bf16* __restrict__ d_out, const unsigned char* __restrict__ idx,
+                                    bf16* dx, int xC, int c0, int C, int b, int H, int W) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int Ho = H / 2, Wo = W / 2;
+    const long total = (long)b * Ho * Wo * C;
+    if (i >= total) return;
+    const int c = i % C;
+    const long q = i / C;
+    const int ox = q % Wo, oy = (q / Wo) % Ho, bi = q / ((long)Wo * Ho);
+    const bf16 g = d_out[i];
+    const int bidx = idx[i];
+    const bf16 zero = f2b(0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int y = 2 * oy + (k >> 1), xx = 2 * ox + (k & 1);
+        dx[(((long)bi * H + y) * W + xx) * xC + c0 + c] = (k == bidx) ? g : zero;
+    }
+}
+void k_maxpool2_bwd(const bf16* d_out, const unsigned char* idx, bf16* dx, int xC, int c0, int C, int b, int H,
+                    int W, cudaStream_t st) {
+    const long total = (long)b * (H / 2) * (W / 2) * C;
+    maxpool2_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(d_out, idx, dx, xC, c0, C, b, H, W); count_launch();
+}
+
+// one warp per row
+__global__ void softmax_fwd_kernel(const float* __restrict__ S, bf16* __restrict__ P, long rows, int n) {
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* s = S + row * n;
+    float m = -INFINITY;
+    for (int k = lane; k < n; k += 32) m = fmaxf(m, s[k]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int k = lane; k < n; k += 32) sum += __expf(s[k] - m);
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    bf16* p = P + row * n;
+    for (int k = lane; k < n; k += 32) p[k] = f2b(__expf(s[k] - m) * inv);
+}
+void k_softmax_fwd(const float* S, bf16* P, long rows, int n, cudaStream_t st) {
+    softmax_fwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(S, P, rows, n); count_launch();
+}
+
+__global__ void softmax_bwd_kernel(const bf16* __restrict__ P, const float* __restrict__ dP, bf16* __restrict__ dS,
+                                   long rows, int n) {
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const bf16* p = P + row * n;
+    const float* dp = dP + row * n;
+    float dot = 0.f;
+    for (int k = lane; k < n; k += 32) dot = fmaf(dp[k], b2f(p[k]), dot);
+    dot = warp_sum(dot);
+    bf16* ds = dS + row * n;
+    for (int k = lane; k < n; k += 32) ds[k] = f2b(b2f(p[k]) * (dp[k] - dot));
+}
+void k_softmax_bwd(const bf16* P, const float* dP, bf16* dS, long rows, int n, cudaStream_t st) {
+    softmax_bwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(P, dP, dS, rows, n); count_launch();
+}
+
+__global__ void transpose_kernel(const bf16* __restrict__ in, int ldin, int in_c0, bf16* __restrict__ out, int R, int C) {
+    __shared__ bf16 tile[32][33];
+    const int bi = blockIdx.z;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const bf16* src = in + (long)bi * R * ldin + in_c0;
+    bf16* dst = out + (long)bi * C * R;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < R && c < C) tile[i][threadIdx.x] = src[(long)r * ldin + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < C) dst[(long)c * R + r] = tile[threadIdx.x][i];
+    }
+}
+void k_transpose(const bf16* in, int ldin, int in_c0, bf16* out, int b, int R, int C, cudaStream_t st) {
+    dim3 grid(cdiv(C, 32), cdiv(R, 32), b), block(32, 8);
+    transpose_kernel<<<grid, block, 0, st>>>(in, ldin, in_c0, out, R, C); count_launch();
+}
+
+// ============================================================================= image / loss glue
+__constant__ float kLpipsShift[3] = {-.030f, -.088f, -.188f};
+__constant__ float kLpipsScale[3] = {.458f, .448f, .450f};
+
+__global__ void im2col_alex1_kernel(const float* __restrict__ img, bf16* __restrict__ col, int b, int H, int W,
+                                    int Ho, int Wo, int Kp) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)b * Ho * Wo * Kp;
+    if (i >= total) return;
+    const int k = i % Kp;
+    const long q = i / Kp;
+    const int ox = q % Wo, oy = (q / Wo) % Ho, bi = q / ((long)Wo * Ho);
+    float v = 0.f;
+    if (k < 363) {
+        const int c = k / 121, r = (k / 11) % 11, s = k % 11;
+        const int y = 4 * oy - 2 + r, x = 4 * ox - 2 + s;
+        if (y >= 0 && y < H && x >= 0 && x < W)
+            v = (img[(((long)bi * 3 + c) * H + y) * W + x] - kLpipsShift[c]) / kLpipsScale[c];
+    }
+    col[i] = f2b(v);
+}
+void k_im2col_alex1(const float* img, bf16* col, int b, int H, int W, int Ho, int Wo, int Kp, cudaStream_t st) {
+    const long total = (long)b * Ho * Wo * Kp;
+    im2col_alex1_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, col, b, H, W, Ho, Wo, Kp); count_launch();
+}
+
+__global__ void col2im_alex1_kernel(const bf16* __restrict__ dcol, float* __restrict__ dimg, int b, int H, int W,
+                                    int Ho, int Wo, int Kp, int accumulate) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)b * 3 * H * W;
+    if (i >= total) return;
+    const int x = i % W, y = (i / W) % H, c = (i / ((long)W * H)) % 3, bi = i / ((long)3 * W * H);
+    float acc = 0.f;
+    const int oy_lo = max(0, (y + 2 - 10 + 3) / 4), oy_hi = min(Ho - 1, (y + 2) / 4);
+    const int ox_lo = max(0, (x + 2 - 10 + 3) / 4), ox_hi = min(Wo - 1, (x + 2) / 4);
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        const int r = y + 2 - 4 * oy;
+        if (r < 0 || r > 10) continue;
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+            const int s = x + 2 - 4 * ox;
+            if (s < 0 || s > 10) continue;
+            acc += b2f(dcol[(((long)bi * Ho + oy) * Wo + ox) * Kp + (c * 11 + r) * 11 + s]);
+        }
+    }
+    acc /= kLpipsScale[c];
+    dimg[i] = accumulate ? dimg[i] + acc : acc;
+}
+void k_col2im_alex1(const bf16* dcol, float* dimg, int b, int H, int W, int Ho, int Wo, int Kp, int accumulate,
+                    cudaStream_t st) {
+    const long total = (long)b * 3 * H * W;
+    col2im_alex1_kernel<<<cdiv(total, 256), 256, 0, st>>>(dcol, dimg, b, H, W, Ho, Wo, Kp, accumulate); count_launch();
+}
+
+__global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, unsigned char* __restrict__ idx,
+                                   int b, int H, int W, int C, int Ho, int Wo, int k, int s) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)b * Ho * Wo * C;
+    if (i >= total) return;
+    const int c = i % C;
+    const long q = i / C;
+    const int ox = q % Wo, oy = (q / Wo) % Ho, bi = q / ((long)Wo * Ho);
+    float best = 0.f;
+    int bidx = 0;
+    for (int r = 0; r < k; ++r) {
+        for (int t = 0; t < k; ++t) {
+            const float v = b2f(x[(((long)bi * H + oy * s + r) * W + ox * s + t) * C + c]);
+            if ((r == 0 && t == 0) || v > best) { best = v; bidx = r * k + t; }
+        }
+    }
+    out[i] = f2b(best);
+    idx[i] = (unsigned char)bidx;
+}
+void k_maxpool_fwd(const bf16* x, bf16* out, unsigned char* idx, int b, int H, int W, int C, int Ho, int Wo, int k,
+                   int s, cudaStream_t st) {
+    const long total = (long)b * Ho * Wo * C;
+    maxpool_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, out, idx, b, H, W, C, Ho, Wo, k, s); count_launch();
+}
+
+__global__ void maxpool_bwd_kernel(const bf16* __restrict__ dout, const unsigned char* __restrict__ idx,
+                                   const bf16* __restrict__ x, const bf16* __restrict__ addin, bf16* __restrict__ dx,
+                                   int b, int H, int W, int C, int Ho, int Wo, int k, int s) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)b * H * W * C;
+    if (i >= total) return;
+    const int c = i % C;
+    const long q = i / C;
+    const int xx = q % W, y = (q / W) % H, bi = q / ((long)W * H);
+    float acc = 0.f;
+    // windows (oy, ox) with oy*s <= y < oy*s + k
+    const int oy_lo = max(0, (y - k + s) / s), oy_hi = min(Ho - 1, y / s);
+    const int ox_lo = max(0, (xx - k + s) / s), ox_hi = min(Wo - 1, xx / s);
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        const int r = y - oy * s;
+        if (r < 0 || r >= k) continue;
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+            const int t = xx - ox * s;
+            if (t < 0 || t >= k) continue;
+            const long o = (((long)bi * Ho + oy) * Wo + ox) * C + c;
+            if (idx[o] == r * k + t) acc += b2f(dout[o]);
+        }
+    }
+    if (x && !(b2f(x[i]) > 0.f)) acc = 0.f;
+    if (addin) acc += b2f(addin[i]);
+    dx[i] = f2b(acc);
+}
+void k_maxpool_bwd(const bf16* dout, const unsigned char* idx, const bf16* x, const bf16* addin, bf16* dx, int b,
+                   int H, int W, int C, int Ho, int Wo, int k, int s, cudaStream_t st) {
+    const long total = (long)b * H * W * C;
+    maxpool_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(dout, idx, x, addin, dx, b, H, W, C, Ho, Wo, k, s); count_launch();
+}
+
+// one warp per feature pixel; block = 8 warps; one atomic per block for the loss
+__global__ void lpips_dist_kernel(const bf16* __restrict__ f, const float* __restrict__ t,
+                                  const float* __restrict__ lin, const float* __restrict__ wadj, float* loss,
+                                  bf16* __restrict__ g, int HW, int C) {
+    __shared__ float part[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bi = blockIdx.y;
+    const int p = blockIdx.x * 8 + warp;
+    float contrib = 0.f;
+    if (p < HW) {
+        const bf16* fp = f + ((long)bi * HW + p) * C;
+        const float* tp = t + (long)p * C;
+        float ss = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float v = b2f(fp[c]);
+            ss = fmaf(v, v, ss);
+        }
+        ss = warp_sum(ss);
+        const float r = sqrtf(ss);
+        const float inv = 1.f / (r + 1e-10f);
+        float d = 0.f, q = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float v = b2f(fp[c]);
+            const float diff = v * inv - tp[c];
+            const float l = lin[c];
+            d = fmaf(l * diff, diff, d);
+            q = fmaf(2.f * l * diff, v, q);
+        }
+        d = warp_sum(d);
+        q = warp_sum(q);
+        const float wv = wadj[p];
+        contrib = wv * d;
+        if (g) {
+            bf16* gp = g + ((long)bi * HW + p) * C;
+            const float k2 = r > 0.f ? q * inv * inv / r : 0.f;
+            for (int c = lane; c < C; c += 32) {
+                const float v = b2f(fp[c]);
+                const float diff = v * inv - tp[c];
+                const float e = 2.f * lin[c] * diff;
+                const float df = e * inv - k2 * v;
+                gp[c] = f2b(v > 0.f ? wv * df : 0.f);
+            }
+        }
+    }
+    if (lane == 0) part[warp] = contrib;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += part[i];
+        atomicAdd(loss + bi, s);
+    }
+}
+void k_lpips_dist(const bf16* f, const float* t, const float* lin, const float* wadj, float* loss, bf16* g, int b,
+                  int HW, int C, cudaStream_t st) {
+    dim3 grid(cdiv(HW, 8), b);
+    lpips_dist_kernel<<<grid, 256, 0, st>>>(f, t, lin, wadj, loss, g, HW, C); count_launch();
+}
+
+__global__ void lpips_normalize_kernel(const bf16* __restrict__ f, float* __restrict__ t, int HW, int C) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * 8 + warp;
+    if (p >= HW) return;
+    const bf16* fp = f + (long)p * C;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float v = b2f(fp[c]);
+        ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.f / (sqrtf(ss) + 1e-10f);
+    for (int c = lane; c < C; c += 32) t[(long)p * C + c] = b2f(fp[c]) * inv;
+}
+void k_lpips_normalize(const bf16* f, float* t, int HW, int C, cudaStream_t st) {
+    lpips_normalize_kernel<<<cdiv(HW, 8), 256, 0, st>>>(f, t, HW, C); count_launch();
+}
+
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+    float src = scale * (dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 < in_size - 1 ? i0 + 1 : i0;
+    l1 = src - i0;
+}
+__global__ void upsample_adjoint_kernel(const float* __restrict__ wsum, float* wadj, int H, int W, int h, int w,
+                                        float coef) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * W) return;
+    const int Y = i / W, X = i % W;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(Y, (float)h / H, h, y0, y1, ly);
+    bilinear_src(X, (float)w / W, w, x0, x1, lx);
+    const float v = wsum[i] * coef;
+    atomicAdd(wadj + y0 * w + x0, v * (1.f - ly) * (1.f - lx));
+    atomicAdd(wadj + y0 * w + x1, v * (1.f - ly) * lx);
+    atomicAdd(wadj + y1 * w + x0, v * ly * (1.f - lx));
+    atomicAdd(wadj + y1 * w + x1, v * ly * lx);
+}
+void k_upsample_adjoint(const float* wsum, float* wadj, int H, int W, int h, int w, float coef, cudaStream_t st) {
+    cudaMemsetAsync(wadj, 0, (size_t)h * w * sizeof(float), st);
+    upsample_adjoint_kernel<<<cdiv((long)H * W, 256), 256, 0, st>>>(wsum, wadj, H, W, h, w, coef); count_launch();
+}
+
+__global__ void weight_sum_kernel(const float* __restrict__ weight, const float* __restrict__ mask, float* wsum,
+                                  float* total, int HW) {
+    __shared__ float part[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float v = 0.f;
+    if (i < HW) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float wv = weight ? weight[c * HW + i] : 1.f;
+            if (mask) wv *= mask[c * HW + i];
+            v += wv;
+        }
+        wsum[i] = v;
+    }
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int k = 0; k < (blockDim.x >> 5); ++k) s += part[k];
+        atomicAdd(total, s);
+    }
+}
+void k_weight_sum(const float* weight, const float* mask, float* wsum, float* total, int HW, cudaStream_t st) {
+    cudaMemsetAsync(total, 0, sizeof(float), st);
+    weight_sum_kernel<<<cdiv(HW, 256), 256, 0, st>>>(weight, mask, wsum, total, HW); count_launch();
+}
+
+__global__ void l1_loss_kernel(const float* __restrict__ img, const float* __restrict__ target,
+                               const float* __restrict__ weight, const float* __restrict__ mask,
+                               const float* __restrict__ total, float* loss, float* __restrict__ dimg, int HW3,
+                               int l2) {
+    __shared__ float part[8];
+    const int bi = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float inv_total = 1.f / total[0];
+    float v = 0.f;
+    if (i < HW3) {
+        float wv = weight ? weight[i] : 1.f;
+        if (mask) wv *= mask[i];
+        wv *= inv_total;
+        const float d = target[i] - img[(long)bi * HW3 + i];
+        float gi;
+        if (l2) {
+            v = d * d * wv;
+            gi = -2.f * d * wv;
+        } else {
+            v = fabsf(d) * wv;
+            gi = d > 0.f ? -wv : (d < 0.f ? wv : 0.f);
+        }
+        if (dimg) dimg[(long)bi * HW3 + i] = gi;
+    }
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int k = 0; k < (blockDim.x >> 5); ++k) s += part[k];
+        atomicAdd(loss + bi, s);
+    }
+}
+void k_l1_loss(const float* img, const float* target, const float* weight, const float* mask, const float* total,
+               float* loss, float* dimg, int b, int HW3, int HW, int l2, cudaStream_t st) {
+    (void)HW;
+    dim3 grid(cdiv(HW3, 256), b);
+    l1_loss_kernel<<<grid, 256, 0, st>>>(img, target, weight, mask, total, loss, dimg, HW3, l2); count_launch();
+}
+
+__global__ void scale_rows_kernel(float* x, const float* scale, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[(long)blockIdx.y * n + i] *= scale[blockIdx.y];
+}
+void k_scale_rows(float* x, const float* scale, int b, long n, cudaStream_t st) {
+    dim3 grid(cdiv(n, 256), b);
+    scale_rows_kernel<<<grid, 256, 0, st>>>(x, scale, n); count_launch();
+}
+
+__global__ void im2col_rgb_bwd_kernel(const float* __restrict__ dimg, const float* __restrict__ img,
+                                      bf16* __restrict__ col, int b, int H, int W, int Kp) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)b * H * W * Kp;
+    if (i >= total) return;
+    const int k = i % Kp;
+    const long q = i / Kp;
+    const int x = q % W, y = (q / W) % H, bi = q / ((long)W * H);
+    float v = 0.f;
+    if (k < 27) {
+        const int o = k % 3, s = (k / 3) % 3, r = k / 9;
+        // dx[q] = sum_{r,s,o} dv[q - (r-1, s-1), o] * W[o, c, r, s]
+        const int yy = y - (r - 1), xx = x - (s - 1);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const long o_i = (((long)bi * 3 + o) * H + yy) * W + xx;
+            const float im = img[o_i];
+            v = dimg[o_i] * (1.f - im * im);
+        }
+    }
+    col[i] = f2b(v);
+}
+void k_im2col_rgb_bwd(const float* dimg, const float* img, bf16* col, int b, int H, int W, int Kp, cudaStream_t st) {
+    const long total = (long)b * H * W * Kp;
+    im2col_rgb_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(dimg, img, col, b, H, W, Kp); count_launch();
+}
+
+// ---- VGG first layer helpers (3 input channels padded to Cp) --------------------------------
+__global__ void img_to_nhwc_scaled_kernel(const float* __restrict__ img, bf16* __restrict__ out, int b, int H, int W,
+                                          int Cp) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)b * H * W * Cp;
+    if (i >= total) return;
+    const int c = i % Cp;
+    const long q = i / Cp;
+    const int x = q % W, y = (q / W) % H, bi = q / ((long)W * H);
+    float v = 0.f;
+    if (c < 3) v = (img[(((long)bi * 3 + c) * H + y) * W + x] - kLpipsShift[c]) / kLpipsScale[c];
+    out[i] = f2b(v);
+}
+void k_img_to_nhwc_scaled(const float* img, bf16* out, int b, int H, int W, int Cp, cudaStream_t st) {
+    const long total = (long)b * H * W * Cp;
+    img_to_nhwc_scaled_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, out, b, H, W, Cp); count_launch();
+}
+__global__ void nhwc_to_dimg_scaled_kernel(const bf16* __restrict__ dx, int Cp, float* __restrict__ dimg, int b, int H,
+                                           int W, int accumulate) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)b * 3 * H * W;
+    if (i >= total) return;
+    const int x = i % W, y = (i / W) % H, c = (i / ((long)W * H)) % 3, bi = i / ((long)3 * W * H);
+    const float v = b2f(dx[(((long)bi * H + y) * W + x) * Cp + c]) / kLpipsScale[c];
+    dimg[i] = accumulate ? dimg[i] + v : v;
+}
+void k_nhwc_to_dimg_scaled(const bf16* dx, int Cp, float* dimg, int b, int H, int W, int accumulate, cudaStream_t st) {
+    const long total = (long)b * 3 * H * W;
+    nhwc_to_dimg_scaled_kernel<<<cdiv(total, 256), 256, 0, st>>>(dx, Cp, dimg, b, H, W, accumulate); count_launch();
+}
+
+}  // namespace p2l

@@ -1,0 +1,97 @@
+// Launchers for the non-contraction kernels of the inversion step (memory-bound glue around
+// the tcgen05 convolutions). All pointers are device pointers; all launches are asynchronous
+// on `st`. bf16 tensors are NHWC.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace p2l {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- latent side ---------------------------------------------------------------------------
+// cond[b,256] = cat(z[b,zd], c[b,cd])
+void k_concat_cond(const float* z, const float* c, float* cond, int b, int zd, int cd, cudaStream_t st);
+// a[b, off+ch] = (1 + cond.Ws[ch]) * inv_std[ch] ; s = cond.Wo[ch] - mean[ch]*a   (conditional BNs)
+void k_cond_affine(const float* cond, const float* Ws, const float* Wo, const float* mean,
+                   const float* inv_std, float* a, float* s, int b, int cdim, int C_cond, int stride,
+                   cudaStream_t st);
+// rows [C_cond, C_cond+C_unc): a = weight*inv_std, s = bias - mean*a (same for every sample)
+void k_uncond_affine(const float* weight, const float* bias, const float* mean, const float* inv_std,
+                     float* a, float* s, int b, int C_cond, int C_unc, int stride, cudaStream_t st);
+// h[b, j] = cond[b].W[j] + bias[j] ; raw = bf16(h) ; act = relu(a[b, j%C]*h + s[b, j%C])
+void k_gen_z(const float* cond, const float* W, const float* bias, const float* a, const float* s,
+             int aff_stride, bf16* raw, bf16* act, int b, int cdim, int J, int C, cudaStream_t st);
+// BN-affine gradient finalisation: from S0 = sum dpre, S1 = sum dpre*y to
+//   G[b, ch] = dgamma = inv_std*(da - mean*ds),  G[b, C+ch] = dbeta = ds,
+//   with da = (S1 - s*S0)/a, ds = S0.
+void k_bn_grad_finalize(const float* S0, const float* S1, const float* a, const float* s,
+                        const float* mean, const float* inv_std, float* G, int b, int C_cond,
+                        int stride, cudaStream_t st);
+// dcond[b, k] += sum_j G[b, j] * W[j, k]   (W row-major [J, cdim], G row stride ldg)
+void k_dcond_accum(const float* G, int ldg, const float* W, float* dcond, int b, int J, int cdim,
+                   cudaStream_t st);
+// G32[b, j] = float(g_bf16[b, j])
+void k_bf16_to_f32(const bf16* src, float* dst, long n, cudaStream_t st);
+// dz/dc = dcond halves * scale * (row_scale ? row_scale[b] : 1)
+void k_split_dcond(const float* dcond, float* dz, float* dc, int b, int zd, int cd, float scale,
+                   const float* row_scale, cudaStream_t st);
+
+// ---- BigGAN glue ---------------------------------------------------------------------------
+// backward through nearest-x2 + relu + BN affine of an up block's conv_0 output:
+//   g = sum2x2(g_up) ; dpre = g*[y>0] ; S0 += dpre ; S1 += dpre*y ; dx = a*dpre
+void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int aff_stride,
+                       float* S0, float* S1, int stat_stride, bf16* dx, int b, int H, int W, int C,
+                       cudaStream_t st);
+
+// ---- attention glue ------------------------------------------------------------------------
+// 2x2 max-pool of channels [c0, c0+C) of x[b,H,W,xC] -> out[b,(H/2)*(W/2),C], outT[b,C,(H/2)*(W/2)]
+// (either may be null), argmax (0..3) -> idx
+void k_maxpool2_fwd(const bf16* x, int xC, int c0, int C, bf16* out, bf16* outT, unsigned char* idx,
+                    int b, int H, int W, cudaStream_t st);
+// dx[b,H,W,xC] channels [c0,c0+C) = routed d_out[b,(H/2)(W/2),C]
+void k_maxpool2_bwd(const bf16* d_out, const unsigned char* idx, bf16* dx, int xC, int c0, int C,
+                    int b, int H, int W, cudaStream_t st);
+// P = softmax(S) row-wise, S fp32 [rows, n] -> P bf16
+void k_softmax_fwd(const float* S, bf16* P, long rows, int n, cudaStream_t st);
+// dS = P * (dP - sum_k dP*P)
+void k_softmax_bwd(const bf16* P, const float* dP, bf16* dS, long rows, int n, cudaStream_t st);
+// out[b, c, r] = in[b, r, in_c0 + c], in row stride ldin
+void k_transpose(const bf16* in, int ldin, int in_c0, bf16* out, int b, int R, int C, cudaStream_t st);
+
+// ---- image / loss glue ---------------------------------------------------------------------
+// AlexNet conv1 (11x11 s4 p2) im2col of the scaled image: col[b,Ho,Wo,Kp] (k = (c*11+r)*11+s, zero pad)
+void k_im2col_alex1(const float* img, bf16* col, int b, int H, int W, int Ho, int Wo, int Kp, cudaStream_t st);
+// gradient back to the (unscaled) image: dimg[b,3,H,W] (+)= col2im(dcol) / scale_c
+void k_col2im_alex1(const bf16* dcol, float* dimg, int b, int H, int W, int Ho, int Wo, int Kp, int accumulate, cudaStream_t st);
+// VGG first layer: img fp32 NCHW -> scaled bf16 NHWC padded to Cp channels
+void k_img_to_nhwc_scaled(const float* img, bf16* out, int b, int H, int W, int Cp, cudaStream_t st);
+void k_nhwc_to_dimg_scaled(const bf16* dx, int Cp, float* dimg, int b, int H, int W, int accumulate, cudaStream_t st);
+// max-pool k x k stride s (no padding), with argmax byte
+void k_maxpool_fwd(const bf16* x, bf16* out, unsigned char* idx, int b, int H, int W, int C, int Ho, int Wo,
+                   int k, int s, cudaStream_t st);
+// dx = [x>0]*(sum over windows whose argmax is this pixel of dout) + addin
+void k_maxpool_bwd(const bf16* dout, const unsigned char* idx, const bf16* x, const bf16* addin, bf16* dx,
+                   int b, int H, int W, int C, int Ho, int Wo, int k, int s, cudaStream_t st);
+// LPIPS layer distance + its gradient: f[b,HW,C] bf16 (post-relu), t[HW,C] fp32 (unit-normalised
+// target features), lin[C], wadj[HW] (adjoint-upsampled weight map / sumW * beta).
+//   loss[b] += sum_p wadj[p] * sum_c lin_c (f_c/(|f|+eps) - t_c)^2 ; g = d/df (masked by f>0), or null
+void k_lpips_dist(const bf16* f, const float* t, const float* lin, const float* wadj, float* loss,
+                  bf16* g, int b, int HW, int C, cudaStream_t st);
+// t[p, c] = f_c/(|f|+eps)  (target features, b = 1)
+void k_lpips_normalize(const bf16* f, float* t, int HW, int C, cudaStream_t st);
+// wadj_k = U_k^T (sum_c W[c]) * coef   for a feature map h x w (bilinear, align_corners=False)
+void k_upsample_adjoint(const float* wsum, float* wadj, int H, int W, int h, int w, float coef, cudaStream_t st);
+// wsum[p] = sum_c W[c,p] (* mask) ; total = sum
+void k_weight_sum(const float* weight, const float* mask, float* wsum, float* total, int HW, cudaStream_t st);
+// L1 term: loss[b] += sum |t-o| * W / sumW ; dimg[b,c,p] = -sign(t-o) * W / sumW   (dimg overwritten)
+void k_l1_loss(const float* img, const float* target, const float* weight, const float* mask,
+               const float* total, float* loss, float* dimg, int b, int HW3, int HW, int l2, cudaStream_t st);
+// dimg[b] *= dloss[b]
+void k_scale_rows(float* x, const float* scale, int b, long n, cudaStream_t st);
+// rgb conv backward input: A[b,H,W,Kp] bf16 with k = (r*3+s)*3 + c of dpre = dimg*(1-img^2)
+void k_im2col_rgb_bwd(const float* dimg, const float* img, bf16* col, int b, int H, int W, int Kp, cudaStream_t st);
+
+void k_fill_f32(float* p, float v, long n, cudaStream_t st);
+
+}  // namespace p2l

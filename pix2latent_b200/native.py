@@ -1,5 +1,258 @@
-"""Opaque-handle part of the C-ABI (include/p2l.h): declared here, used by model/ and loss."""
+"""ctypes stub over the opaque-handle C-ABI (include/p2l.h).
+
+This file is the "reference-side binding" of INTEGRATION.md: everything pix2latent's
+``closure.step`` needs from the GPU goes through these ~10 C entry points with raw device
+pointers and a CUDA stream. torch is used for memory, streams and autograd plumbing only.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+P2L_MAX_LAYERS = 16
+LPIPS_NETS = {"alex": 0, "alexnet": 0, "vgg": 1, "vgg16": 1}
+
+
+class BigGANConfigC(C.Structure):
+    """Mirror of ``p2l_biggan_config``."""
+    _fields_ = [
+        ("n_layers", C.c_int),
+        ("up", C.c_int * P2L_MAX_LAYERS), ("in_mult", C.c_int * P2L_MAX_LAYERS),
+        ("out_mult", C.c_int * P2L_MAX_LAYERS),
+        ("channel_width", C.c_int), ("z_dim", C.c_int), ("class_embed_dim", C.c_int),
+        ("attention_pos", C.c_int), ("n_stats", C.c_int),
+        ("eps", C.c_float), ("truncation", C.c_float),
+    ]
 
 
 def declare(L):
-    pass
+    vp, ci, cf, cl = C.c_void_p, C.c_int, C.c_float, C.c_long
+    pp = C.POINTER(C.c_void_p)
+    sig = {
+        "p2l_version": (ci, []),
+        "p2l_launch_count": (cl, []),
+        "p2l_create": (ci, [ci, pp]),
+        "p2l_destroy": (None, [vp]),
+        "p2l_biggan_create": (ci, [vp, C.POINTER(BigGANConfigC), pp]),
+        "p2l_biggan_set_tensor": (ci, [vp, C.c_char_p, vp, cl]),
+        "p2l_biggan_finalize": (ci, [vp]),
+        "p2l_biggan_destroy": (None, [vp]),
+        "p2l_biggan_forward": (ci, [vp, ci, vp, vp, vp, vp]),
+        "p2l_biggan_backward": (ci, [vp, ci, vp, vp, vp, vp]),
+        "p2l_biggan_device_bytes": (cl, [vp]),
+        "p2l_biggan_flops": (C.c_double, [vp, ci, ci]),
+        "p2l_biggan_launches": (ci, [vp, ci, ci]),
+        "p2l_lpips_create": (ci, [vp, ci, pp]),
+        "p2l_lpips_set_tensor": (ci, [vp, C.c_char_p, vp, cl]),
+        "p2l_lpips_finalize": (ci, [vp]),
+        "p2l_lpips_destroy": (None, [vp]),
+        "p2l_target_create": (ci, [vp, vp, vp, vp, ci, ci, ci, cf, cf, pp, vp]),
+        "p2l_target_destroy": (None, [vp]),
+        "p2l_loss_forward": (ci, [vp, vp, ci, vp, vp, ci, vp]),
+        "p2l_loss_backward": (ci, [vp, vp, ci, vp, vp, vp]),
+        "p2l_lpips_flops": (C.c_double, [vp, ci, ci, ci, ci]),
+        "p2l_lpips_launches": (ci, [vp, ci]),
+        "p2l_biggan_step": (ci, [vp, vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]),
+        "p2l_profile_enable": (None, [ci]),
+        "p2l_profile_read": (ci, [C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_double)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+EXPORTED_SYMBOLS = [
+    "p2l_last_error", "p2l_version", "p2l_launch_count", "p2l_create", "p2l_destroy",
+    "p2l_biggan_create", "p2l_biggan_set_tensor", "p2l_biggan_finalize", "p2l_biggan_destroy",
+    "p2l_biggan_forward", "p2l_biggan_backward", "p2l_biggan_device_bytes", "p2l_biggan_flops",
+    "p2l_biggan_launches", "p2l_lpips_create", "p2l_lpips_set_tensor", "p2l_lpips_finalize",
+    "p2l_lpips_destroy", "p2l_target_create", "p2l_target_destroy", "p2l_loss_forward",
+    "p2l_loss_backward", "p2l_lpips_flops", "p2l_lpips_launches", "p2l_biggan_step",
+    "p2l_profile_enable", "p2l_profile_read",
+    "p2l_debug_conv",
+]
+
+_ctx = {}
+
+
+def _f32c(t):
+    assert t.is_cuda, "pix2latent_b200 runs on a CUDA (sm_100a) device only; got a CPU tensor"
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return t
+
+
+def context(device=None):
+    """One p2l_ctx per CUDA device (created lazily; fails loudly off sm_100)."""
+    if not torch.cuda.is_available():
+        raise _lib.P2LError("pix2latent_b200 needs a CUDA device (sm_100a); none is visible and "
+                            "there is no CPU fallback.")
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    if dev not in _ctx:
+        h = C.c_void_p()
+        _lib.check(_lib.lib().p2l_create(dev, C.byref(h)))
+        _ctx[dev] = h
+    return _ctx[dev], dev
+
+
+def launch_count():
+    return int(_lib.lib().p2l_launch_count())
+
+
+class NativeBigGAN:
+    """Owns a ``p2l_biggan`` handle. ``state_dict`` uses pix2latent's BigGAN module keys."""
+
+    def __init__(self, config, state_dict, truncation=1.0, device=None):
+        L = _lib.lib()
+        self.ctx, self.device = context(device)
+        cfg = BigGANConfigC()
+        layers = list(config.layers)
+        assert len(layers) <= P2L_MAX_LAYERS
+        cfg.n_layers = len(layers)
+        for i, (up, cin, cout) in enumerate(layers):
+            cfg.up[i], cfg.in_mult[i], cfg.out_mult[i] = int(bool(up)), int(cin), int(cout)
+        cfg.channel_width = config.channel_width
+        cfg.z_dim = config.z_dim
+        cfg.class_embed_dim = config.class_embed_dim
+        cfg.attention_pos = config.attention_layer_position
+        cfg.n_stats = config.n_stats
+        cfg.eps = config.eps
+        cfg.truncation = truncation
+        self.config = config
+        self.truncation = truncation
+        self.out_res = config.output_dim
+        self.h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(L.p2l_biggan_create(self.ctx, C.byref(cfg), C.byref(self.h)))
+            for k, v in state_dict.items():
+                if not k.startswith("generator."):
+                    continue
+                t = v.detach().float().contiguous()
+                _lib.check(L.p2l_biggan_set_tensor(self.h, k.encode(), C.c_void_p(t.data_ptr()), t.numel()))
+            _lib.check(L.p2l_biggan_finalize(self.h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.lib().p2l_biggan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def forward(self, z, c):
+        z, c = _f32c(z), _f32c(c)
+        b = z.shape[0]
+        img = torch.empty(b, 3, self.out_res, self.out_res, device=z.device, dtype=torch.float32)
+        _lib.check(_lib.lib().p2l_biggan_forward(self.h, b, _lib.ptr(z), _lib.ptr(c), _lib.ptr(img),
+                                                 _lib.current_stream()))
+        return img
+
+    def backward(self, b, dimg):
+        dimg = _f32c(dimg)
+        dz = torch.empty(b, self.config.z_dim, device=dimg.device, dtype=torch.float32)
+        dc = torch.empty(b, self.config.class_embed_dim, device=dimg.device, dtype=torch.float32)
+        _lib.check(_lib.lib().p2l_biggan_backward(self.h, b, _lib.ptr(dimg), _lib.ptr(dz), _lib.ptr(dc),
+                                                  _lib.current_stream()))
+        return dz, dc
+
+    def flops(self, b, backward=False):
+        return float(_lib.lib().p2l_biggan_flops(self.h, b, int(backward)))
+
+    def device_bytes(self):
+        return int(_lib.lib().p2l_biggan_device_bytes(self.h))
+
+
+class NativeLPIPS:
+    def __init__(self, net, state_dict, device=None):
+        L = _lib.lib()
+        self.ctx, self.device = context(device)
+        self.net = net
+        self.h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(L.p2l_lpips_create(self.ctx, LPIPS_NETS[net], C.byref(self.h)))
+            for k, v in state_dict.items():
+                t = v.detach().float().contiguous()
+                _lib.check(L.p2l_lpips_set_tensor(self.h, k.encode(), C.c_void_p(t.data_ptr()), t.numel()))
+            _lib.check(L.p2l_lpips_finalize(self.h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.lib().p2l_lpips_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def make_target(self, target, weight=None, mask=None, rec_type=1, rec_weight=1.0, per_weight=10.0):
+        return NativeTarget(self, target, weight, mask, rec_type, rec_weight, per_weight)
+
+    def flops(self, b, H, W, backward=False):
+        return float(_lib.lib().p2l_lpips_flops(self.h, b, H, W, int(backward)))
+
+
+class NativeTarget:
+    """Everything that depends only on (target, weight, mask): cached once."""
+
+    def __init__(self, lp, target, weight, mask, rec_type, rec_weight, per_weight):
+        self.lp = lp
+        t = _f32c(target)
+        assert t.dim() == 3 and t.shape[0] == 3, "target must be [3,H,W]"
+        self.H, self.W = int(t.shape[1]), int(t.shape[2])
+        w = None if weight is None else _f32c(weight.expand_as(t) if weight.shape != t.shape else weight)
+        m = None if mask is None else _f32c(mask.expand_as(t) if mask.shape != t.shape else mask)
+        self.h = C.c_void_p()
+        _lib.check(_lib.lib().p2l_target_create(lp.h, _lib.ptr(t), _lib.ptr(w), _lib.ptr(m), self.H, self.W,
+                                                int(rec_type), float(rec_weight), float(per_weight),
+                                                C.byref(self.h), _lib.current_stream()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.lib().p2l_target_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def loss_forward(self, img, want_grad):
+        img = _f32c(img)
+        b = img.shape[0]
+        loss = torch.empty(b, device=img.device, dtype=torch.float32)
+        _lib.check(_lib.lib().p2l_loss_forward(self.lp.h, self.h, b, _lib.ptr(img), _lib.ptr(loss),
+                                               int(want_grad), _lib.current_stream()))
+        return loss
+
+    def loss_backward(self, b, dloss):
+        dloss = _f32c(dloss)
+        dimg = torch.empty(b, 3, self.H, self.W, device=dloss.device, dtype=torch.float32)
+        _lib.check(_lib.lib().p2l_loss_backward(self.lp.h, self.h, b, _lib.ptr(dloss), _lib.ptr(dimg),
+                                                _lib.current_stream()))
+        return dimg
+
+
+def profile_enable(on):
+    _lib.lib().p2l_profile_enable(int(on))
+
+
+def profile_read():
+    ms, n, fl = C.c_double(), C.c_long(), C.c_double()
+    _lib.check(_lib.lib().p2l_profile_read(C.byref(ms), C.byref(n), C.byref(fl)))
+    return ms.value, n.value, fl.value
+
+
+def biggan_step(gen, lp, tgt, z, c, want_grad, grad_scale, want_img=True, dloss=None):
+    """One fused inner step (closure.py:51-58) for a mini-batch: returns (loss[b], dz, dc, img).
+    Upstream gradient of sample i = grad_scale * (dloss[i] if dloss is given else 1)."""
+    z, c = _f32c(z), _f32c(c)
+    b = z.shape[0]
+    dev = z.device
+    loss = torch.empty(b, device=dev, dtype=torch.float32)
+    dz = torch.empty_like(z) if want_grad else None
+    dc = torch.empty_like(c) if want_grad else None
+    img = torch.empty(b, 3, gen.out_res, gen.out_res, device=dev, dtype=torch.float32) if want_img else None
+    _lib.check(_lib.lib().p2l_biggan_step(gen.h, lp.h, tgt.h, b, _lib.ptr(z), _lib.ptr(c), int(want_grad),
+                                          float(grad_scale), _lib.ptr(None if dloss is None else _f32c(dloss)),
+                                          _lib.ptr(loss), _lib.ptr(dz), _lib.ptr(dc),
+                                          _lib.ptr(img), _lib.current_stream()))
+    return loss, dz, dc, img

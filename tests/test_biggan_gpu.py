@@ -1,0 +1,144 @@
+"""Parity of the native (sm_100a) BigGAN generator + ProjectionLoss against the oracle
+(oracle/biggan.py, oracle/lpips.py) on the same seeded weights and latents.
+
+Tolerances (bf16 tensor-core operands, fp32 accumulation, ~40 layers): stated per assertion.
+The oracle runs in fp32 with TF32 disabled."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def lpips_native_state(lp):
+    sd = {}
+    for k, sl in enumerate(lp.net.slices):
+        for name, mod in sl.named_children():
+            if hasattr(mod, "weight"):
+                sd["net.slice%d.%s.weight" % (k + 1, name)] = mod.weight
+                sd["net.slice%d.%s.bias" % (k + 1, name)] = mod.bias
+    for k, l in enumerate(lp.lins):
+        sd["lin%d.weight" % k] = l
+    return sd
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+def cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    _setup()
+    from oracle.biggan import BigGANConfig, make_biggan
+    from pix2latent_b200.native import NativeBigGAN
+    cfg = BigGANConfig.tiny128()
+    orc = make_biggan(cfg, seed=0).cuda()
+    nat = NativeBigGAN(cfg, orc.state_dict())
+    return cfg, orc, nat
+
+
+def test_generator_forward_backward(tiny):
+    cfg, orc, nat = tiny
+    torch.manual_seed(2)
+    b = 5
+    z = torch.fmod(torch.randn(b, 128), 2.0).cuda().requires_grad_(True)
+    c = orc.get_class_embedding(3).repeat(b, 1).clone().requires_grad_(True)
+    ref = orc(z=z, c=c)
+    img = nat.forward(z.detach(), c.detach())
+    torch.cuda.synchronize()
+    err = (img - ref).abs().max().item()
+    print("image max abs err", err, "rel", rel(img, ref))
+    assert err < 4e-2 and rel(img, ref) < 2e-2  # bf16 mode, image in (-1,1)
+    torch.manual_seed(3)
+    dimg = torch.randn_like(ref) * 1e-3
+    ref.backward(dimg)
+    dz, dc = nat.backward(b, dimg)
+    torch.cuda.synchronize()
+    print("dz rel", rel(dz, z.grad), "cos", cos(dz, z.grad), "dc rel", rel(dc, c.grad), "cos", cos(dc, c.grad))
+    assert cos(dz, z.grad) > 0.995 and cos(dc, c.grad) > 0.995
+    assert rel(dz, z.grad) < 8e-2 and rel(dc, c.grad) < 8e-2
+
+
+@pytest.mark.parametrize("net", ["alex", "vgg"])
+def test_projection_loss(net):
+    _setup()
+    from oracle.lpips import ProjectionLoss, make_lpips
+    from pix2latent_b200.native import NativeLPIPS
+    torch.manual_seed(5)
+    H = W = 128
+    b = 3
+    lp = make_lpips(net, seed=0).cuda()
+    ref_fn = ProjectionLoss(lpips_net=net, lpips_module=lp)
+    nat = NativeLPIPS(net, lpips_native_state(lp))
+    target = torch.tanh(torch.randn(3, H, W, device="cuda"))
+    weight = torch.full((3, H, W), 0.3, device="cuda")
+    weight[:, 32:96, 32:96] = 1.0
+    img = torch.tanh(torch.randn(b, 3, H, W, device="cuda") * 0.7).requires_grad_(True)
+    ref = ref_fn(img, target[None].expand(b, -1, -1, -1), weight[None].expand(b, -1, -1, -1))
+    dloss = torch.tensor([1.0, 0.5, 0.25], device="cuda")
+    ref.backward(dloss)
+    tgt = nat.make_target(target, weight)
+    loss = tgt.loss_forward(img.detach(), want_grad=True)
+    dimg = tgt.loss_backward(b, dloss)
+    torch.cuda.synchronize()
+    print(net, "loss", loss.tolist(), ref.tolist(), "dimg rel", rel(dimg, img.grad), cos(dimg, img.grad))
+    assert torch.allclose(loss, ref.detach(), rtol=2e-2, atol=1e-3)
+    assert cos(dimg, img.grad) > 0.99 and rel(dimg, img.grad) < 0.1
+
+
+def test_projection_loss_no_weight_and_mask():
+    _setup()
+    from oracle.lpips import ProjectionLoss, make_lpips
+    from pix2latent_b200.native import NativeLPIPS
+    torch.manual_seed(6)
+    H = W = 64
+    b = 2
+    lp = make_lpips("alex", seed=1).cuda()
+    ref_fn = ProjectionLoss(lpips_module=lp)
+    nat = NativeLPIPS("alex", lpips_native_state(lp))
+    target = torch.tanh(torch.randn(3, H, W, device="cuda"))
+    img = torch.tanh(torch.randn(b, 3, H, W, device="cuda"))
+    # weight=None: the reference returns the un-reduced map and closure.py:55 means it
+    ref = ref_fn(img, target[None].expand(b, -1, -1, -1)).view(b, -1).mean(1)
+    loss = nat.make_target(target).loss_forward(img, want_grad=False)
+    assert torch.allclose(loss, ref, rtol=2e-2, atol=1e-3)
+    weight = torch.rand(3, H, W, device="cuda") + 0.1
+    mask = torch.zeros(3, H, W, device="cuda")
+    mask[:, 8:-8, :] = 1
+    ref = ref_fn(img, target[None].expand(b, -1, -1, -1), weight[None].expand(b, -1, -1, -1),
+                 mask[None].expand(b, -1, -1, -1))
+    loss = nat.make_target(target, weight, mask).loss_forward(img, want_grad=False)
+    assert torch.allclose(loss, ref, rtol=2e-2, atol=1e-3)
+
+
+def test_fused_step_matches_separate(tiny):
+    cfg, orc, nat = tiny
+    _setup()
+    from oracle.lpips import make_lpips
+    from pix2latent_b200.native import NativeLPIPS, biggan_step
+    torch.manual_seed(7)
+    b = 4
+    lp = make_lpips("alex", seed=0).cuda()
+    nl = NativeLPIPS("alex", lpips_native_state(lp))
+    target = torch.tanh(torch.randn(3, 128, 128, device="cuda"))
+    tgt = nl.make_target(target)
+    z = torch.fmod(torch.randn(b, 128), 2.0).cuda()
+    c = orc.get_class_embedding(1).repeat(b, 1)
+    loss, dz, dc, img = biggan_step(nat, nl, tgt, z, c, True, 1.0 / b)
+    img2 = nat.forward(z, c)
+    loss2 = tgt.loss_forward(img2, want_grad=True)
+    dimg = tgt.loss_backward(b, torch.full((b,), 1.0 / b, device="cuda"))
+    dz2, dc2 = nat.backward(b, dimg)
+    torch.cuda.synchronize()
+    assert torch.equal(img, img2)
+    assert torch.allclose(loss, loss2, rtol=1e-5, atol=1e-7)
+    assert rel(dz, dz2) < 1e-3 and rel(dc, dc2) < 1e-3
