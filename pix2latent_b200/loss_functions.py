@@ -139,14 +139,15 @@ def _same_rows(t):
 class _NativeLoss(nn.Module):
     """Common machinery: rec_weight * pixel term + per_weight * LPIPS term, natively."""
 
-    def __init__(self, net, rec_type, rec_weight, per_weight):
+    def __init__(self, net, rec_type, rec_weight, per_weight, lpips_state_dict=None):
         super().__init__()
         self._net, self._rec_type = net, rec_type
         self._rec_weight, self._per_weight = rec_weight, per_weight
+        self._lpips_state = lpips_state_dict
         self._cache = None
 
     def native_lpips(self):
-        return get_native_lpips(self._net)
+        return get_native_lpips(self._net, self._lpips_state)
 
     def target_cache(self):
         if self._cache is None:
@@ -206,13 +207,13 @@ class ReconstructionLoss(_NativeLoss):
 class PerceptualLoss(_NativeLoss):
     """LPIPS(net, spatial=True) with spatial weighting: sum(map * W) / sum(W) per sample."""
 
-    def __init__(self, net="vgg", use_gpu=True):
-        super().__init__(net, 1, 0.0, 1.0)
+    def __init__(self, net="vgg", use_gpu=True, lpips_state_dict=None):
+        super().__init__(net, 1, 0.0, 1.0, lpips_state_dict)
 
 
 class ProjectionLoss(_NativeLoss):
     """The paper's default: weighted L1 + beta * weighted LPIPS."""
 
-    def __init__(self, lpips_net="alex", beta=10):
-        super().__init__(lpips_net, 1, 1.0, float(beta))
+    def __init__(self, lpips_net="alex", beta=10, lpips_state_dict=None):
+        super().__init__(lpips_net, 1, 1.0, float(beta), lpips_state_dict)
         self.beta = beta

@@ -11,6 +11,7 @@ gradient-refined) variables with an eval-only step but tells CMA the ORIGINAL sa
 import numpy as np
 import torch
 
+from .. import parallel
 from ..utils.image import binarize
 from ..utils.misc import HiddenPrints, cprint
 
@@ -91,8 +92,11 @@ class _BaseCMAOptimizer():
     @torch.no_grad()
     def cma_init(self, var_manager):
         variables = var_manager.initialize(num_samples=self.num_samples)
+        rank, size = parallel.world()
         for (var_type, name), opt in self.cma_optimizers.items():
-            asked = opt.ask()
+            asked = opt.ask() if rank == 0 else None
+            if size > 1:
+                asked = parallel.broadcast_array(asked)  # rank 0 owns the search state
             slots = variables[var_type][name].data
             for i, d in enumerate(asked):
                 slots[i].data = torch.Tensor(d).data.type_as(slots[i].data)
@@ -105,6 +109,7 @@ class _BaseCMAOptimizer():
             asked = self._sampled[key]
             if loss is None:
                 out, loss, _ = self.step(variables, optimize=False)
+                loss = self.gathered_loss()  # the one data-path collective: N scalar losses
             if inverted_loss and hasattr(variables, "transform"):
                 info = self.var_manager.variable_info
                 target = info["target"]["default"].unsqueeze(0).type_as(out)
@@ -112,5 +117,6 @@ class _BaseCMAOptimizer():
                 t_fn = self.transform_fns["target"]["fn"]
                 out = t_fn(out, torch.stack(variables.transform.t.data), invert=True)
                 loss = self.loss_fn(out, target, binarize(weight)).cpu().detach().numpy()
-            opt.tell(asked, loss)
+            if parallel.world()[0] == 0:
+                opt.tell(asked, loss)
         return loss

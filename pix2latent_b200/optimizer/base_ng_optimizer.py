@@ -8,6 +8,7 @@ meta-iteration, one ``tell`` per candidate with its (refined) loss."""
 import numpy as np
 import torch
 
+from .. import parallel
 from ..utils.image import binarize
 from ..utils.misc import cprint
 
@@ -55,9 +56,12 @@ class _BaseNevergradOptimizer():
         if self.is_sequential:
             num_samples = 1
         variables = var_manager.initialize(num_samples=num_samples)
+        rank, size = parallel.world()
         for (var_type, name), opt in self.ng_optimizers.items():
-            asked = [opt.ask() for _ in range(num_samples)]
-            values = np.concatenate([np.asarray(x.args[0])[None] for x in asked])
+            asked = [opt.ask() for _ in range(num_samples)] if rank == 0 else None
+            values = np.concatenate([np.asarray(x.args[0])[None] for x in asked]) if rank == 0 else None
+            if size > 1:
+                values = parallel.broadcast_array(values)
             slots = variables[var_type][name].data
             for i, d in enumerate(values):
                 slots[i].data = torch.Tensor(d).data.type_as(slots[i].data)
@@ -70,6 +74,7 @@ class _BaseNevergradOptimizer():
             asked = self._sampled[key]
             if loss is None:
                 out, loss, _ = self.step(variables, optimize=False)
+                loss = self.gathered_loss()
             if inverted_loss and hasattr(variables, "transform"):
                 info = self.var_manager.variable_info
                 target = info["target"]["default"].unsqueeze(0).type_as(out)
@@ -77,5 +82,6 @@ class _BaseNevergradOptimizer():
                 t_fn = self.transform_fns["target"]["fn"]
                 out = t_fn(out, torch.stack(variables.transform.t.data), invert=True)
                 loss = self.loss_fn(out, target, binarize(weight)).cpu().detach().numpy()
-            for cand, l in zip(asked, loss):
-                opt.tell(cand, float(l))
+            if parallel.world()[0] == 0:
+                for cand, l in zip(asked, loss):
+                    opt.tell(cand, float(l))

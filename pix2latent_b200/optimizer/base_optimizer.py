@@ -6,6 +6,7 @@ import time
 import numpy as np
 import torch
 
+from .. import parallel
 from ..utils.image import to_grid, to_image
 from ..utils.misc import progress_print
 from .closure import step
@@ -57,9 +58,17 @@ class _BaseOptimizer():
                 self.apply_transform(variables, td)
         if self.track_variables:
             self.track(variables)
+        rank, size = parallel.world()
+        # one process per GPU: evaluate this rank's candidates only; nothing is communicated here
+        local = parallel.shard_vars(variables, rank, size) if size > 1 else variables
         self.out, self.loss, self.other = step(
-            self.model, variables, loss_fn=self.loss_fn, optimize=optimize, max_batch_size=self.max_batch_size)
+            self.model, local, loss_fn=self.loss_fn, optimize=optimize, max_batch_size=self.max_batch_size)
+        self._n_total = variables.num_samples
         return self.out, self.loss, self.other
+
+    def gathered_loss(self):
+        """Per-candidate losses of the whole population (one all_gather of scalars when sharded)."""
+        return parallel.allgather_losses(self.loss, self._n_total)
 
     def track(self, variables):
         for name, var in variables.input.items():
@@ -73,7 +82,7 @@ class _BaseOptimizer():
             res = self.bm.evaluate(self.out, variables.output.target.data[0].unsqueeze(0),
                                    variables.output.weight.data[0].unsqueeze(0))
         else:
-            res = {"loss": np.array(self.loss)}
+            res = {"loss": np.array(self.gathered_loss())}
         self.losses.append([step_iter, res])
         collage = to_image(to_grid(self.out.cpu()), cv2_format=False)
         if self.log_resize_factor is not None:
@@ -104,6 +113,18 @@ class _BaseOptimizer():
         self._progress(i, total_steps, log_at, pbar)
 
     def _finish(self, variables, total_steps):
+        rank, size = parallel.world()
+        if size > 1:
+            # final state of every shard to every rank: latents (KBs), losses, images
+            n = variables.num_samples
+            lo, hi = parallel.shard_bounds(n, rank, size)
+            with torch.no_grad():
+                for var in variables.input.values():
+                    full = parallel.allgather_rows(torch.stack(var.data[lo:hi]), n)
+                    for i, t in enumerate(var.data):
+                        t.data.copy_(full[i])
+            self.loss = self.gathered_loss()
+            self.out = parallel.allgather_rows(self.out, n)
         if self.log:
             return variables, self.outs, self.losses
         grid = to_grid(torch.stack(list(self.out.cpu().detach())))

@@ -1,0 +1,41 @@
+"""Worker for tests/test_parallel_cpu.py: world_size-2 gloo run of BasinCMAOptimizer with the
+oracle model on CPU; rank 0 writes the results."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+
+def main():
+    out_path = sys.argv[1]
+    dist.init_process_group("gloo")
+    torch.set_num_threads(4)
+    import make_golden as mg
+    from oracle import lpips as olp
+    from pix2latent_b200 import VariableManager
+    from pix2latent_b200.optimizer import BasinCMAOptimizer
+    import pix2latent_b200.distribution as dst
+    import pix2latent_b200.utils.function_hooks as hook
+    cfg, model, target, weight = mg.problem()
+    loss_fn = olp.ProjectionLoss(lpips_module=olp.make_lpips("alex", seed=0))
+    torch.manual_seed(23)
+    vm = VariableManager(device="cpu")
+    mg.register(vm, hook, dst, model, target, weight, True)
+    opt = BasinCMAOptimizer(model, vm, loss_fn, max_batch_size=9)
+    opt.cma_seed = mg.CMA_SEED
+    variables, outs, loss = opt.optimize(meta_steps=2, grad_steps=2, last_grad_steps=2)
+    if dist.get_rank() == 0:
+        np.savez(out_path, loss=np.array(loss[0][1]["loss"]), z=torch.stack(variables.input.z.data).detach().numpy(),
+                 mean=np.array(list(opt.cma_optimizers.values())[0].mean()), grid=np.array(outs[0].shape))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,34 @@
+"""N>1 host path on CPU: 2 gloo ranks shard the BasinCMA population (9 + 9 candidates), rank 0
+owns CMA, one broadcast of the asked z and one all_gather of the losses per meta-iteration. The
+result must equal the single-process golden run of the REAL reference code (candidates are
+independent; chunk size 9 keeps the 1/9 gradient scale)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "reference_cpu.npz"))
+
+
+def test_shard_bounds():
+    from pix2latent_b200.parallel import shard_bounds
+    assert [shard_bounds(18, r, 2) for r in range(2)] == [(0, 9), (9, 18)]
+    assert [shard_bounds(22, r, 4) for r in range(4)] == [(0, 6), (6, 12), (12, 17), (17, 22)]
+    assert [shard_bounds(3, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 3), (3, 3)]
+
+
+def test_basincma_two_ranks_equals_reference(tmp_path):
+    out = str(tmp_path / "res.npz")
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29613", os.path.join(HERE, "_dist_worker.py"), out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = np.load(out)
+    np.testing.assert_allclose(res["loss"], GOLD["basin_loss"], rtol=2e-4, atol=2e-5)
+    # z: a different OpenMP thread count (4 per rank vs 8 in the golden run) reorders fp32 sums in
+    # the CPU convolutions; Adam's normalised first updates amplify that to ~1e-3 on a few elements
+    np.testing.assert_allclose(res["z"], GOLD["basin_z"], rtol=1e-2, atol=5e-3)
+    np.testing.assert_allclose(res["mean"], GOLD["basin_cma_mean"], rtol=1e-2, atol=5e-3)

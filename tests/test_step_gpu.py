@@ -1,0 +1,131 @@
+"""Replay parity of the product's inner step (SURVEY.md §8d "parity run", F6): the oracle
+(oracle/closure.py + oracle generator/LPIPS, fp32 on the GPU, TF32 off) produces a trajectory of
+(z_k, c_k); the native fused step is evaluated at the SAME (z_k, c_k) and compared step by step;
+then a short free-running run through the product API is compared at its end.
+
+Tolerances (bf16 operands, fp32 accumulation): per-step |dloss| <= 3e-3*(1+|loss|); gradient
+cosine >= 0.9; free-running 5-step final loss within 2e-2 and final LPIPS within 1e-3-level."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _lpips_state(lp):
+    sd = {}
+    for k, sl in enumerate(lp.net.slices):
+        for name, mod in sl.named_children():
+            if hasattr(mod, "weight"):
+                sd["net.slice%d.%s.weight" % (k + 1, name)] = mod.weight
+                sd["net.slice%d.%s.bias" % (k + 1, name)] = mod.bias
+    for k, l in enumerate(lp.lins):
+        sd["lin%d.weight" % k] = l
+    return sd
+
+
+@pytest.fixture(scope="module")
+def world():
+    _setup()
+    import make_golden as mg
+    from oracle import lpips as olp
+    from pix2latent_b200.loss_functions import ProjectionLoss
+    from pix2latent_b200.model import BigGAN
+    cfg, orc, target, weight = mg.problem()
+    orc = orc.cuda()
+    lp = olp.make_lpips("alex", seed=0).cuda()
+    ref_loss = olp.ProjectionLoss(lpips_module=lp)
+    model = BigGAN(config=_product_cfg(cfg), state_dict=orc.state_dict())
+    loss = ProjectionLoss(lpips_state_dict=_lpips_state(lp))
+    return cfg, orc, ref_loss, model, loss, target.cuda(), weight.cuda()
+
+
+def _product_cfg(cfg):
+    from pix2latent_b200.model import synth
+    return synth.BigGANConfig(output_dim=cfg.output_dim, num_classes=cfg.num_classes, layers=list(cfg.layers),
+                              attention_layer_position=cfg.attention_layer_position)
+
+
+def _vm(model, target, weight, device):
+    import make_golden as mg
+    from pix2latent_b200 import VariableManager
+    import pix2latent_b200.distribution as dist
+    import pix2latent_b200.utils.function_hooks as hook
+    vm = VariableManager(device=device)
+    mg.register(vm, hook, dist, model, target, weight, False)
+    return vm
+
+
+def test_replay_step_parity(world):
+    from oracle import closure as oc
+    from pix2latent_b200 import native
+    cfg, orc, ref_loss, model, loss, target, weight = world
+    torch.manual_seed(21)
+    vm = _vm(orc, target, weight, "cuda")
+    variables = vm.initialize(6)
+    tgt = loss.prepared_target(target, weight)
+    worst = 0.0
+    for k in range(4):
+        z = torch.stack(variables.input.z.data).detach().clamp(-2, 2)  # the Clamp hook runs first in the step
+        c = torch.stack(variables.input.c.data).detach()
+        l_nat, dz, dc, img = native.biggan_step(model.native, loss.native_lpips(), tgt, z, c, True, 1.0 / 3)
+        zz = z.clone().requires_grad_(True)
+        cc = c.clone().requires_grad_(True)
+        out = orc(z=zz, c=cc)
+        l_ref = ref_loss(out, target[None].expand(6, -1, -1, -1), weight[None].expand(6, -1, -1, -1))
+        (l_ref.sum() / 3).backward()
+        err = ((l_nat - l_ref).abs() / (1 + l_ref.abs())).max().item()
+        worst = max(worst, err)
+        cz = torch.nn.functional.cosine_similarity(dz.flatten(), zz.grad.flatten(), dim=0).item()
+        cc_ = torch.nn.functional.cosine_similarity(dc.flatten(), cc.grad.flatten(), dim=0).item()
+        print("step %d: loss err %.2e cos dz %.4f cos dc %.4f" % (k, err, cz, cc_))
+        assert err < 3e-3 and cz > 0.9 and cc_ > 0.9
+        oc.step(orc, variables, ref_loss, optimize=True, max_batch_size=3)  # advance the ORACLE trajectory
+
+
+def test_free_running_gradient_optimizer(world):
+    from pix2latent_b200.optimizer import GradientOptimizer
+    from pix2latent_b200.optimizer.closure import _native_pair
+    cfg, orc, ref_loss, model, loss, target, weight = world
+    torch.manual_seed(22)
+    opt_ref = GradientOptimizer(orc, _vm(orc, target, weight, "cuda"), ref_loss, max_batch_size=2)
+    v_ref, _, l_ref = opt_ref.optimize(num_samples=4, grad_steps=5)
+    torch.manual_seed(22)
+    opt_nat = GradientOptimizer(model, _vm(model, target, weight, "cuda"), loss, max_batch_size=2)
+    v_nat, outs, l_nat = opt_nat.optimize(num_samples=4, grad_steps=5)
+    assert _native_pair(model, v_nat, loss)
+    lr, ln = np.array(l_ref[0][1]["loss"]), np.array(l_nat[0][1]["loss"])
+    print("final loss oracle", lr, "native", ln)
+    assert np.abs(lr - ln).max() < 2e-2
+    zr, zn = torch.stack(v_ref.input.z.data), torch.stack(v_nat.input.z.data)
+    assert (zr - zn).abs().mean().item() < 0.03  # Adam's sign-like first steps: a few elements flip
+    assert outs[0].shape[0] == 3
+
+
+def test_autograd_path_uses_native_functions(world):
+    """model(...) / loss(...) as separate differentiable calls (closure.py:51-58 as written)."""
+    cfg, orc, ref_loss, model, loss, target, weight = world
+    torch.manual_seed(5)
+    z = torch.fmod(torch.randn(3, 128), 2.0).cuda().requires_grad_(True)
+    c = orc.get_class_embedding(3).repeat(3, 1).clone().requires_grad_(True)
+    out = model(z=z, c=c)
+    l = loss(out, target[None].expand(3, -1, -1, -1), weight[None].expand(3, -1, -1, -1)).view(3, -1).mean(1)
+    l.mean().backward()
+    z2 = z.detach().clone().requires_grad_(True)
+    c2 = c.detach().clone().requires_grad_(True)
+    o2 = orc(z=z2, c=c2)
+    l2 = ref_loss(o2, target[None].expand(3, -1, -1, -1), weight[None].expand(3, -1, -1, -1))
+    l2.mean().backward()
+    assert torch.allclose(l, l2, rtol=5e-3, atol=2e-3)
+    cs = torch.nn.functional.cosine_similarity(z.grad.flatten(), z2.grad.flatten(), dim=0).item()
+    assert cs > 0.9
