@@ -52,6 +52,14 @@ typedef struct p2l_conv_args {
 /* returns 0 on success, <0 on error (see p2l_last_error) */
 int p2l_debug_conv(const p2l_conv_args* args, void* cuda_stream);
 
+/* experiment switches of the kernel library: "halo" (0 = per-tap A loads, 10 / 16 = halo-patch
+ * kernel with that patch row pitch), "halo_bo" (descriptor base-offset mode) */
+void p2l_debug_set_option(const char* key, int value);
+int p2l_debug_get_option(const char* key);
+/* i-th tensor-core launch recorded since p2l_profile_enable(1): duration (ms), algorithmic FLOPs,
+ * info[7] = {BN, mode, halo, grid, M, N, K}; call before p2l_profile_read (which resets) */
+int p2l_debug_profile_get(int i, float* ms, double* flops, int* info);
+
 #ifdef __cplusplus
 }
 #endif

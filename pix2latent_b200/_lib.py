@@ -67,9 +67,35 @@ def _declare(L):
     L.p2l_last_error.argtypes = []
     L.p2l_debug_conv.restype = C.c_int
     L.p2l_debug_conv.argtypes = [C.POINTER(ConvArgs), C.c_void_p]
+    L.p2l_debug_set_option.restype = None
+    L.p2l_debug_set_option.argtypes = [C.c_char_p, C.c_int]
+    L.p2l_debug_get_option.restype = C.c_int
+    L.p2l_debug_get_option.argtypes = [C.c_char_p]
+    L.p2l_debug_profile_get.restype = C.c_int
+    L.p2l_debug_profile_get.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int * 7)]
     # the rest of the API is declared by pix2latent_b200.native (it needs the opaque handles)
     from . import native
     native.declare(L)
+
+
+def set_option(key, value):
+    lib().p2l_debug_set_option(key.encode(), int(value))
+
+
+def get_option(key):
+    return int(lib().p2l_debug_get_option(key.encode()))
+
+
+def profile_records():
+    """[(ms, flops, BN, mode, halo, grid, M, N, K)] of the launches recorded since profile_enable(1)."""
+    out, i = [], 0
+    while True:
+        ms, fl, info = C.c_float(), C.c_double(), (C.c_int * 7)()
+        if lib().p2l_debug_profile_get(i, C.byref(ms), C.byref(fl), C.byref(info)) != 0:
+            break
+        out.append((ms.value, fl.value) + tuple(info))
+        i += 1
+    return out
 
 
 def ptr(t):

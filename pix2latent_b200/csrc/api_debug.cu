@@ -34,3 +34,7 @@ P2L_EXPORT int p2l_debug_conv(const p2l_conv_args* a, void* cuda_stream) {
 }
 
 P2L_EXPORT const char* p2l_last_error(void) { return get_error(); }
+P2L_EXPORT void p2l_debug_set_option(const char* key, int value) { set_option(key, value); }
+P2L_EXPORT int p2l_debug_get_option(const char* key) { return get_option(key); }
+
+P2L_EXPORT int p2l_debug_profile_get(int i, float* ms, double* flops, int* info) { return profile_get(i, ms, flops, info); }

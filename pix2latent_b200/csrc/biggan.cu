@@ -130,8 +130,15 @@ int BigGAN::finalize() {
     if (fill_stats("generator.bn", C_last, C_cond)) return -1;
     mean = upload(weights, h_mean);
     inv_std = upload(weights, h_istd);
-    Ws = upload(weights, h_ws);
-    Wo = upload(weights, h_wo);
+    {   // cond -> (gain, offset): transposed [cdim][C_cond] so a warp of channels reads contiguous rows
+        std::vector<float> t((size_t)C_cond * cdim);
+        for (int c = 0; c < C_cond; ++c)
+            for (int k = 0; k < cdim; ++k) t[(size_t)k * C_cond + c] = h_ws[(size_t)c * cdim + k];
+        Ws = upload(weights, t);
+        for (int c = 0; c < C_cond; ++c)
+            for (int k = 0; k < cdim; ++k) t[(size_t)k * C_cond + c] = h_wo[(size_t)c * cdim + k];
+        Wo = upload(weights, t);
+    }
     {
         std::vector<float> cat((size_t)2 * C_cond * cdim);
         std::memcpy(cat.data(), h_ws.data(), h_ws.size() * sizeof(float));
@@ -149,7 +156,11 @@ int BigGAN::finalize() {
         const auto* w = stage.get("generator.gen_z.weight", (long)genz_J * cdim);
         const auto* bsv = stage.get("generator.gen_z.bias", genz_J);
         if (!w || !bsv) return -1;
-        genz_W = upload(weights, *w);
+        genz_W = upload(weights, *w);  // row-major [J][cdim] for the backward (dcond) pass
+        std::vector<float> t(w->size());
+        for (int j = 0; j < genz_J; ++j)
+            for (int k = 0; k < cdim; ++k) t[(size_t)k * genz_J + j] = (*w)[(size_t)j * cdim + k];
+        genz_WT = upload(weights, t);
         genz_b = upload(weights, *bsv);
     }
     // ---- conv weights
@@ -222,10 +233,12 @@ int BigGAN::finalize() {
 }
 
 // ----------------------------------------------------------------------------- plan
-static int pick_bn_for(int Cout, long m_tiles) {
+static int pick_bn_for(int Cout, long m_tiles, long K) {
     if (Cout <= 16) return 16;
     const int cands[3] = {256, 128, 64};
-    for (int k = 0; k < 3; ++k)
+    // small-K launches are epilogue-bound: N <= 128 tiles run two CTAs per SM and (K <= 512) store
+    // through TMA; N = 256 tiles only pay off when the main loop is long
+    for (int k = (K <= 1024 ? 1 : 0); k < 3; ++k)
         if (Cout % cands[k] == 0 && m_tiles * (Cout / cands[k]) >= num_sms()) return cands[k];
     for (int k = 2; k >= 0; --k)
         if (Cout % cands[k] == 0) return cands[k];
@@ -244,7 +257,7 @@ struct OpB {  // small builder
         d.A = A; d.A_N = N; d.A_H = H; d.A_W = W; d.A_C = C; d.a_c0 = c0; d.Cin = Cin;
         d.B = B; d.Cout = Cout; d.kh = d.kw = k; d.pad_h = d.pad_w = k / 2;
         d.NI = N; d.H = H; d.W = W; d.mode = mode;
-        d.BN = pick_bn_for(Cout, m_tiles_for(N, H, W));
+        d.BN = pick_bn_for(Cout, m_tiles_for(N, H, W), (long)k * k * Cin);
     }
 };
 
@@ -532,7 +545,7 @@ int BigGAN::forward(int b, const float* z, const float* c, float* img, cudaStrea
     k_uncond_affine(unc_weight, unc_bias, mean, inv_std, P.a, P.s, b, C_cond, C_last, C_all, st);
     const int bn00 = blocks[0].bn[0];
     // gen_z output is already NHWC: view(b, 4, 4, C0)
-    k_gen_z(P.cond, genz_W, genz_b, P.a + bns[bn00].off, P.s + bns[bn00].off, C_all, P.bb[0].in_raw, P.bb[0].in_act,
+    k_gen_z(P.cond, genz_WT, genz_b, P.a + bns[bn00].off, P.s + bns[bn00].off, C_all, P.bb[0].in_raw, P.bb[0].in_act,
             b, cdim, genz_J, C0, st);
     const int nL = (int)blocks.size();
     for (int i = 0; i < nL; ++i) {

@@ -21,10 +21,11 @@ struct BigGAN {
     struct BN { int C, off; bool cond; };
     std::vector<BN> bns;  // conditional ones first (concatenated tables), the final unconditional last
     int C_cond = 0, C_all = 0, cdim = 0;
-    float *Ws = nullptr, *Wo = nullptr, *mean = nullptr, *inv_std = nullptr;  // [C_cond(+unc)]
+    float *Ws = nullptr, *Wo = nullptr;  // cond linears, transposed [cdim][C_cond]
+    float *mean = nullptr, *inv_std = nullptr;  // [C_all]
     float *unc_weight = nullptr, *unc_bias = nullptr;
     float *Wcat = nullptr;  // [2*C_cond, cdim] rows: Ws then Wo (for dcond)
-    float *genz_W = nullptr, *genz_b = nullptr;
+    float *genz_W = nullptr, *genz_WT = nullptr, *genz_b = nullptr;
     int genz_J = 0, C0 = 0;
 
     struct Block {

@@ -24,15 +24,41 @@ static long g_launches = 0;
 void count_launch() { ++g_launches; }
 long launch_count() { return g_launches; }
 
+static int g_tma_out = 1;
+static int g_halo = 0, g_halo_bo = 0;  // halo patches: correct but no gain at these shapes (profiles/r1_notes.md)
+void set_option(const char* key, int value) {
+    if (!std::strcmp(key, "halo")) g_halo = value;
+    else if (!std::strcmp(key, "halo_bo")) g_halo_bo = value;
+    else if (!std::strcmp(key, "tma_out")) g_tma_out = value;
+}
+int get_option(const char* key) {
+    if (!std::strcmp(key, "halo")) return g_halo;
+    if (!std::strcmp(key, "halo_bo")) return g_halo_bo;
+    if (!std::strcmp(key, "tma_out")) return g_tma_out;
+    return -1;
+}
+
 // ---- optional per-launch event timing of the tensor-core kernel (bench.py roofline leg)
 static bool g_prof = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static size_t g_prof_used = 0;
 static double g_prof_flops = 0;
+struct ProfRec { double flops; int BN, mode, halo, grid, M, N, K; };
+static std::vector<ProfRec> g_prof_recs;
 void profile_enable(int on) {
     g_prof = on != 0;
     g_prof_used = 0;
     g_prof_flops = 0;
+    g_prof_recs.clear();
+}
+int profile_get(int i, float* ms, double* flops, int* info /*7 ints*/) {
+    if (i < 0 || (size_t)i >= g_prof_used || (size_t)i >= g_prof_recs.size()) return -1;
+    if (cudaEventSynchronize(g_prof_events[i].second) != cudaSuccess) return -1;
+    cudaEventElapsedTime(ms, g_prof_events[i].first, g_prof_events[i].second);
+    const ProfRec& r = g_prof_recs[i];
+    *flops = r.flops;
+    info[0] = r.BN; info[1] = r.mode; info[2] = r.halo; info[3] = r.grid; info[4] = r.M; info[5] = r.N; info[6] = r.K;
+    return 0;
 }
 int profile_read(double* conv_ms, long* conv_launches, double* conv_flops) {
     double ms = 0;
@@ -128,11 +154,19 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     int tw = pow2_ceil(d.W); if (tw > 16) tw = 16;
     int th = pow2_ceil(d.H); if (th > kBM / tw) th = kBM / tw;
     int nb = kBM / (tw * th);
+    // halo patches: always for the 3-channel rgb head (N = 16 tile: the layer is pure A traffic),
+    // optional ("halo" option) elsewhere — measured neutral for N >= 64 (profiles/)
+    const int halo_p = (d.BN == 16) ? 10 : g_halo;
+    const bool halo = halo_p != 0 && d.kh == 3 && d.kw == 3 && d.pad_h == 1 && d.pad_w == 1 && d.B_batch == 0 &&
+                      d.H >= 12 && d.W >= 8;
+    if (halo) { tw = 8; th = 16; nb = 1; }
     if (d.B_batch > 0 && nb != 1) {
         set_error("conv_op_build: batched B needs >=128 pixels per image (got %dx%d)", d.H, d.W);
         return -1;
     }
     p.tw = tw; p.th = th; p.nb = nb;
+    p.ltw = 0; while ((1 << p.ltw) < tw) ++p.ltw;
+    p.lth = 0; while ((1 << p.lth) < th) ++p.lth;
     p.tiles_w = (d.W + tw - 1) / tw;
     p.tiles_h = (d.H + th - 1) / th;
     p.tiles_n = (d.NI + nb - 1) / nb;
@@ -142,12 +176,14 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     p.cin_chunks = d.Cin / kBK;
     p.a_c0 = d.a_c0;
     p.b_batched = d.B_batch > 0 ? 1 : 0;
+    p.halo_bo = g_halo_bo;
     if (p.alpha == 0.f) p.alpha = 1.f;
 
     {   // A: {C, W, H, N}
         cuuint64_t dims[4] = {(cuuint64_t)d.A_C, (cuuint64_t)d.A_W, (cuuint64_t)d.A_H, (cuuint64_t)d.A_N};
         cuuint64_t str[3] = {(cuuint64_t)d.A_C * 2, (cuuint64_t)d.A_W * d.A_C * 2, (cuuint64_t)d.A_H * d.A_W * d.A_C * 2};
         cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+        if (halo) { box[1] = (cuuint32_t)halo_p; box[2] = (cuuint32_t)(th + 2); box[3] = 1; }
         if (encode_bf16(&op->tmA, d.A, 4, dims, str, box)) return -1;
     }
     {   // B: {K, Cout, batch}
@@ -157,22 +193,54 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
         cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)d.BN, 1};
         if (encode_bf16(&op->tmB, d.B, 3, dims, str, box)) return -1;
     }
+    // ---- epilogue outputs by TMA bulk store: worthwhile where the epilogue dominates (small K)
+    const long Ktot = (long)d.kh * d.kw * d.Cin;
+    const bool any_out = d.epi.raw || d.epi.act || d.epi.dx;
+    op->tma_out = (g_tma_out && !halo && any_out && (d.BN == 64 || d.BN == 128) && d.Cout % 64 == 0 && Ktot <= 512 &&
+                   !d.epi.img_nchw) ? 1 : 0;
+    if (op->tma_out) {
+        auto map4 = [&](CUtensorMap* m, const void* ptr, int C, int Hh, int Ww) -> int {
+            cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)Ww, (cuuint64_t)Hh, (cuuint64_t)d.NI};
+            cuuint64_t str[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ww * C * 2, (cuuint64_t)Hh * Ww * C * 2};
+            cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+            return encode_bf16(m, ptr, 4, dims, str, box);
+        };
+        const void* o0 = d.mode == EPI_FWD ? (const void*)d.epi.raw : (const void*)d.epi.dx;
+        const int o0C = d.mode == EPI_FWD ? d.epi.raw_C : d.epi.dx_C;
+        if (o0 && map4(&op->tmO.m[0], o0, o0C, d.H, d.W)) return -1;
+        if (d.mode == EPI_FWD && d.epi.act) {
+            if (!d.epi.act_up) {
+                if (map4(&op->tmO.m[1], d.epi.act, d.epi.act_C, d.H, d.W)) return -1;
+            } else {
+                // [NI, 2H, 2W, C] viewed as {C, dx(2), W, dy(2), NI*H}
+                const cuuint64_t C = (cuuint64_t)d.epi.act_C;
+                cuuint64_t dims[5] = {(cuuint64_t)d.Cout, 2, (cuuint64_t)d.W, 2, (cuuint64_t)d.NI * d.H};
+                cuuint64_t str[4] = {C * 2, 2 * C * 2, 2 * (cuuint64_t)d.W * C * 2, 4 * (cuuint64_t)d.W * C * 2};
+                cuuint32_t box[5] = {(cuuint32_t)kBK, 1, (cuuint32_t)tw, 1, (cuuint32_t)(th * nb)};
+                if (nb > 1 && th != d.H) { set_error("conv_op_build: act_up tile spans images with th != H"); return -1; }
+                if (encode_bf16(&op->tmO.m[2], d.epi.act, 5, dims, str, box)) return -1;
+                if (d.epi.act_lo && map4(&op->tmO.m[3], d.epi.act_lo, d.epi.act_C, d.H, d.W)) return -1;
+            }
+        }
+    }
     op->p = p;
     op->BN = d.BN;
     op->mode = d.mode;
+    op->halo = halo ? halo_p : 0;
     const long total = (long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
-    op->grid = (int)(total < num_sms() ? total : num_sms());
+    const long slots = (long)num_sms() * ((halo || d.BN > 128) ? 1 : P2L_OCC);  // same occupancy with or without TMA_OUT
+    op->grid = (int)(total < slots ? total : slots);
     op->flops = 2.0 * d.NI * d.H * d.W * (double)d.Cout * d.kh * d.kw * d.Cin;
     return 0;
 }
 
 // ----------------------------------------------------------------------------- launch
-template <int BN, int MODE>
+template <int BN, int MODE, bool TMA_OUT>
 static int launch_t(const ConvOp& op, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, TMA_OUT>;
     static bool attr_set = false;
     if (!attr_set) {
-        P2L_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE>,
+        P2L_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE, TMA_OUT>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
@@ -187,9 +255,42 @@ static int launch_t(const ConvOp& op, cudaStream_t stream) {
         e1 = g_prof_events[g_prof_used].second;
         ++g_prof_used;
         g_prof_flops += op.flops;
+        g_prof_recs.push_back({op.flops, op.BN, op.mode, op.halo, op.grid, op.p.NI * op.p.H * op.p.W, op.p.Cout,
+                               op.p.taps_h * op.p.taps_w * op.p.cin_chunks * kBK});
         cudaEventRecord(e0, stream);
     }
-    conv_gemm_kernel<BN, MODE><<<op.grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(op.tmA, op.tmB, op.p);
+    conv_gemm_kernel<BN, MODE, TMA_OUT><<<op.grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(op.tmA, op.tmB, op.tmO, op.p);
+    if (g_prof) cudaEventRecord(e1, stream);
+    count_launch();
+    P2L_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+template <int BN, int MODE, int P>
+static int launch_halo_t(const ConvOp& op, cudaStream_t stream) {
+    using Cfg = HaloCfg<BN, P>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        P2L_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, MODE, P>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_prof) {
+        if (g_prof_used == g_prof_events.size()) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            g_prof_events.emplace_back(e0, e1);
+        }
+        e0 = g_prof_events[g_prof_used].first;
+        e1 = g_prof_events[g_prof_used].second;
+        ++g_prof_used;
+        g_prof_flops += op.flops;
+        g_prof_recs.push_back({op.flops, op.BN, op.mode, op.halo, op.grid, op.p.NI * op.p.H * op.p.W, op.p.Cout,
+                               op.p.taps_h * op.p.taps_w * op.p.cin_chunks * kBK});
+        cudaEventRecord(e0, stream);
+    }
+    conv3x3_halo_kernel<BN, MODE, P><<<op.grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(op.tmA, op.tmB, op.p);
     if (g_prof) cudaEventRecord(e1, stream);
     count_launch();
     P2L_CUDA_CHECK(cudaGetLastError());
@@ -197,10 +298,25 @@ static int launch_t(const ConvOp& op, cudaStream_t stream) {
 }
 
 int conv_op_launch(const ConvOp& op, cudaStream_t stream) {
+    if (op.halo) {
+#define P2L_HALO(bn, pp)                                                                   \
+    if (op.BN == bn && op.halo == pp)                                                      \
+        return op.mode == EPI_FWD ? launch_halo_t<bn, EPI_FWD, pp>(op, stream)             \
+                                  : launch_halo_t<bn, EPI_BWD, pp>(op, stream);
+        P2L_HALO(16, 10) P2L_HALO(64, 10) P2L_HALO(128, 10) P2L_HALO(256, 10)
+        P2L_HALO(64, 16) P2L_HALO(128, 16) P2L_HALO(256, 16)
+#undef P2L_HALO
+        set_error("conv_op_launch: unsupported halo config BN=%d P=%d", op.BN, op.halo);
+        return -1;
+    }
+    if (op.tma_out) {
+        if (op.BN == 64) return op.mode == EPI_FWD ? launch_t<64, EPI_FWD, true>(op, stream) : launch_t<64, EPI_BWD, true>(op, stream);
+        if (op.BN == 128) return op.mode == EPI_FWD ? launch_t<128, EPI_FWD, true>(op, stream) : launch_t<128, EPI_BWD, true>(op, stream);
+    }
 #define P2L_DISPATCH(bn)                                                          \
     case bn:                                                                      \
-        return op.mode == EPI_FWD ? launch_t<bn, EPI_FWD>(op, stream)             \
-                                  : launch_t<bn, EPI_BWD>(op, stream);
+        return op.mode == EPI_FWD ? launch_t<bn, EPI_FWD, false>(op, stream)      \
+                                  : launch_t<bn, EPI_BWD, false>(op, stream);
     switch (op.BN) {
         P2L_DISPATCH(16)
         P2L_DISPATCH(64)

@@ -30,13 +30,20 @@ constexpr int kBM = 128;  // pixels per tile
 constexpr int kBK = 64;   // bf16 per K chunk = one 128-byte swizzle row
 constexpr int kGemmThreads = 192;
 constexpr int kATileBytes = kBM * kBK * 2;
+#ifndef P2L_OCC
+#define P2L_OCC 2
+#endif
+#ifndef P2L_EPI_STAGED
+#define P2L_EPI_STAGED 0  // 1: per-warp swizzled smem staging (measured slower: the epilogue is latency-bound)
+#endif
 
 enum { EPI_FWD = 0, EPI_BWD = 1 };
 
 struct ConvGemmParams {
     // ---- M: output pixel grid [NI, H, W], tile box (nb, th, tw), tw*th*nb == 128
     int NI, H, W;
-    int tw, th, nb;
+    int tw, th, nb;   // powers of two
+    int ltw, lth;     // log2(tw), log2(th)
     int tiles_w, tiles_h, tiles_n;
     // ---- N
     int Cout;     // logical output channels
@@ -46,6 +53,7 @@ struct ConvGemmParams {
     int cin_chunks;  // Cin / 64
     int a_c0;        // channel offset into the A tensor
     int b_batched;   // B tensor map's 3rd coordinate = image index
+    int halo_bo;     // halo kernel: fill the descriptor's base-offset field from the start address
     // ---- epilogue, forward
     float alpha;             // scale on the accumulator
     const float* alpha_ptr;  // optional device scalar multiplied into alpha (attention gamma); both modes
@@ -79,14 +87,21 @@ struct ConvGemmParams {
     int dx_f32_C;
 };
 
-template <int BN>
+template <int BN, bool TMA_OUT = false>
 struct GemmCfg {
     static constexpr int kBTileBytes = BN * kBK * 2;
     static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-    static constexpr int kMaxStages = (200 * 1024) / kStageBytes;
+    // Two co-resident CTAs per SM for BN <= 128: the epilogue (global loads/stores issued by only
+    // four warps) is latency-bound, a second CTA doubles the bytes in flight and lets one CTA's
+    // epilogue overlap the other's main loop even on single-tile launches.
+    static constexpr int kOcc = (BN <= 128) ? P2L_OCC : 1;
+    // TMA_OUT: epilogue outputs leave through two 16 KB swizzled slabs (128 rows x 64 channels) and
+    // cp.async.bulk.tensor stores instead of per-thread st.global
+    static constexpr int kOutBytes = TMA_OUT ? 2 * kATileBytes : 0;
+    static constexpr int kMaxStages = ((kOcc == 2 ? 104 : 208) * 1024 - kOutBytes) / kStageBytes;
     static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
     static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/ + (P2L_EPI_STAGED ? 4 * 4096 : 0);
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
 };
 
@@ -106,17 +121,650 @@ __device__ __forceinline__ float colsum_group(float (&v)[G], int lane) {
     return v[0];
 }
 
-template <int BN, int MODE>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// ----------------------------------------------------------------------------- epilogue I/O
+constexpr int kStageSlabBytes = 4096;  // per epilogue warp: 32 rows x 128 B
+
+// tile-local row (0..127) -> pixel of the output grid
+struct TileMap {
+    int w0, h0, n0, tw_mask, th_mask, ltw, lthw, W, H, NI;
+    __device__ __forceinline__ bool pix(int r, int& n, int& h, int& w) const {
+        w = w0 + (r & tw_mask);
+        h = h0 + ((r >> ltw) & th_mask);
+        n = n0 + (r >> lthw);
+        return (w < W) && (h < H) && (n < NI);
+    }
+};
+// where a row lives in the tensor being read/written:
+//   plain: (n,h,w) on an Hs x Ws grid; shift: (h>>shift, w>>shift); up: (2h+dy, 2w+dx) on (2H,2W)
+struct SrcMap {
+    int Hs, Ws, shift, up, dy, dx;
+    __device__ __forceinline__ long index(int n, int h, int w) const {
+        const int hh = up ? 2 * h + dy : (h >> shift);
+        const int ww = up ? 2 * w + dx : (w >> shift);
+        return (static_cast<long>(n) * Hs + hh) * Ws + ww;
+    }
+};
+
+// bf16 slab: 32 rows x 64 B, 16-byte chunk j of row r stored at slot j ^ ((r >> 1) & 3)
+__device__ __forceinline__ uint32_t slab64_off(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
+// fp32 slab: 32 rows x 128 B, chunk j of row r at slot j ^ (r & 7)
+__device__ __forceinline__ uint32_t slab128_off(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
+
+// v[32] += bf16 tensor rows (coalesced global read through the slab)
+__device__ __forceinline__ void coop_load_add(uint8_t* stg, int quad, int lane, const TileMap& tm, const SrcMap& sm,
+                                              const __nv_bfloat16* src, int C, int cbase, float (&v)[32]) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2), j = lane & 3;
+        int n, h, w;
+        uint4 t = make_uint4(0, 0, 0, 0);
+        if (tm.pix(quad * 32 + r, n, h, w)) t = __ldg(reinterpret_cast<const uint4*>(src + sm.index(n, h, w) * C + cbase) + j);
+        *reinterpret_cast<uint4*>(stg + slab64_off(r, j)) = t;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 t = *reinterpret_cast<const uint4*>(stg + slab64_off(lane, q));
+        v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
+        v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
+        v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
+        v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void slab_put_bf16(uint8_t* stg, int lane, const float (&v)[32]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        *reinterpret_cast<uint4*>(stg + slab64_off(lane, q)) =
+            make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                       pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+    }
+    __syncwarp();
+}
+
+// bf16(v) rows -> dst (coalesced global write through the slab)
+__device__ __forceinline__ void coop_store_bf16(uint8_t* stg, int quad, int lane, const TileMap& tm, const SrcMap& dm,
+                                                __nv_bfloat16* dst, int C, int cbase, const float (&v)[32]) {
+    slab_put_bf16(stg, lane, v);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2), j = lane & 3;
+        int n, h, w;
+        if (tm.pix(quad * 32 + r, n, h, w)) {
+            const uint4 t = *reinterpret_cast<const uint4*>(stg + slab64_off(r, j));
+            *(reinterpret_cast<uint4*>(dst + dm.index(n, h, w) * C + cbase) + j) = t;
+        }
+    }
+    __syncwarp();
+}
+
+// nearest x2: every row is written to its 2x2 block of the (2H, 2W) map, plus the low-res copy
+__device__ __forceinline__ void coop_store_bf16_up(uint8_t* stg, int quad, int lane, const TileMap& tm,
+                                                   __nv_bfloat16* dst_up, __nv_bfloat16* dst_lo, int C, int cbase,
+                                                   const float (&v)[32]) {
+    slab_put_bf16(stg, lane, v);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2), j = lane & 3;
+        int n, h, w;
+        if (tm.pix(quad * 32 + r, n, h, w)) {
+            const uint4 t = *reinterpret_cast<const uint4*>(stg + slab64_off(r, j));
+            const long W2 = 2L * tm.W;
+            const long base = (static_cast<long>(n) * 2 * tm.H + 2 * h) * W2 + 2 * w;
+            *(reinterpret_cast<uint4*>(dst_up + base * C + cbase) + j) = t;
+            *(reinterpret_cast<uint4*>(dst_up + (base + 1) * C + cbase) + j) = t;
+            *(reinterpret_cast<uint4*>(dst_up + (base + W2) * C + cbase) + j) = t;
+            *(reinterpret_cast<uint4*>(dst_up + (base + W2 + 1) * C + cbase) + j) = t;
+            if (dst_lo) *(reinterpret_cast<uint4*>(dst_lo + ((static_cast<long>(n) * tm.H + h) * tm.W + w) * C + cbase) + j) = t;
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void coop_store_f32(uint8_t* stg, int quad, int lane, const TileMap& tm, float* dst, int C,
+                                               int cbase, const float (&v)[32]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        *reinterpret_cast<float4*>(stg + slab128_off(lane, q)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), j = lane & 7;
+        int n, h, w;
+        if (tm.pix(quad * 32 + r, n, h, w)) {
+            const float4 t = *reinterpret_cast<const float4*>(stg + slab128_off(r, j));
+            *(reinterpret_cast<float4*>(dst + ((static_cast<long>(n) * tm.H + h) * tm.W + w) * C + cbase) + j) = t;
+        }
+    }
+    __syncwarp();
+}
+
+// Row `row` (0..127) of a 128-row x 128-byte slab in the TMA 128B-swizzle layout: write 32 bf16
+// (pieces piece0 .. piece0+3 of the row's eight 16-byte pieces).
+__device__ __forceinline__ void slab_put_row(uint8_t* buf, int row, int piece0, const float (&v)[32]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        *reinterpret_cast<uint4*>(buf + row * 128 + (((piece0 + q) ^ (row & 7)) << 4)) =
+            make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                       pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+    }
+}
+__device__ __forceinline__ void slab_put_row(uint8_t*, int, int, const float (&)[16]) {}
+
+// Direct epilogue: every thread reads / writes the global rows of its own accumulator row.
+template <int BN, int MODE, int CH, bool TMA_OUT>
+__device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, const CUtensorMap* tmo, uint8_t* obuf,
+                                                     uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
+                                                     int total_tiles, int warp, int lane) {
+    // TMA_OUT: tmo[0] = raw / dx, tmo[1] = act, tmo[2] = act on the 2x grid (5-D view), tmo[3] = act_lo
+    const bool storer = TMA_OUT && (warp & 3) == 0 && lane == 0;
+    // ------------------------------------------------------------------ epilogue warps
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    const int wi = row % p.tw;
+    const int hi = (row / p.tw) % p.th;
+    const int ni = row / (p.tw * p.th);
+    const int rows_per_img = p.tw * p.th;
+    float alpha = p.alpha;
+    if (p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const int twi = m_tile % p.tiles_w;
+        const int thi = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tni = m_tile / (p.tiles_w * p.tiles_h);
+        const int w = twi * p.tw + wi, h = thi * p.th + hi, n = tni * p.nb + ni;
+        const bool valid = (w < p.W) && (h < p.H) && (n < p.NI);
+        const long pix = (static_cast<long>(n) * p.H + h) * p.W + w;
+
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+
+#pragma unroll 1
+        for (int c = 0; c < BN; c += CH) {
+            const int cbase = n_tile * BN + c;
+            if (cbase >= p.Cout) break;  // warp-uniform
+            if constexpr (TMA_OUT) {
+                if ((c & 63) == 0) {
+                    // both output slabs are about to be overwritten: their previous stores must have
+                    // finished READING shared memory
+                    if (storer) bulk_wait_read0();
+                    bar_epilogue();
+                }
+            }
+            float v[CH];
+            {
+                uint32_t u[CH];
+                if constexpr (CH == 32) tmem_ld32(t_addr + c, u);
+                else tmem_ld16(t_addr + c, u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(u[j]);
+            }
+            const bool full_chunk = (cbase + CH <= p.Cout);
+
+            if constexpr (MODE == EPI_FWD) {
+                // ---- v = alpha*acc + bias (+ skip)
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    float b = 0.f;
+                    if (p.bias && (full_chunk || cbase + j < p.Cout)) b = __ldg(p.bias + cbase + j);
+                    v[j] = alpha * v[j] + b;
+                }
+                if (p.resid && valid) {
+                    const int Hs = p.H >> p.resid_shift, Ws = p.W >> p.resid_shift;
+                    const long rp = (static_cast<long>(n) * Hs + (h >> p.resid_shift)) * Ws + (w >> p.resid_shift);
+                    const uint4* src = reinterpret_cast<const uint4*>(p.resid + rp * p.resid_C + cbase);
+#pragma unroll
+                    for (int q = 0; q < CH / 8; ++q) {
+                        const uint4 t = __ldg(src + q);
+                        v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
+                        v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
+                        v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
+                        v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
+                    }
+                }
+                if (p.img_nchw) {
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            if (cbase + j < p.Cout) {
+                                p.img_nchw[((static_cast<long>(n) * p.Cout + cbase + j) * p.H + h) * p.W + w] = tanhf(v[j]);
+                            }
+                        }
+                    }
+                }
+                if (p.raw_f32 && valid) {
+                    float4* dst = reinterpret_cast<float4*>(p.raw_f32 + pix * p.raw_f32_C + cbase);
+#pragma unroll
+                    for (int q = 0; q < CH / 4; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                }
+                if constexpr (TMA_OUT) {
+                    if (p.raw) slab_put_row(obuf, row, (c & 32) >> 3, v);
+                } else if (p.raw && valid) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.raw + pix * p.raw_C + cbase);
+#pragma unroll
+                    for (int q = 0; q < CH / 8; ++q) {
+                        dst[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                                            pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+                    }
+                }
+                if (p.act) {
+                    if (p.aff_a) {
+                        const int nn = valid ? n : 0;
+                        const float* pa = p.aff_a + static_cast<long>(nn) * p.aff_stride + cbase;
+                        const float* ps = p.aff_s + static_cast<long>(nn) * p.aff_stride + cbase;
+#pragma unroll
+                        for (int q = 0; q < CH / 4; ++q) {
+                            const float4 a4 = __ldg(reinterpret_cast<const float4*>(pa) + q);
+                            const float4 s4 = __ldg(reinterpret_cast<const float4*>(ps) + q);
+                            v[q * 4 + 0] = fmaf(a4.x, v[q * 4 + 0], s4.x);
+                            v[q * 4 + 1] = fmaf(a4.y, v[q * 4 + 1], s4.y);
+                            v[q * 4 + 2] = fmaf(a4.z, v[q * 4 + 2], s4.z);
+                            v[q * 4 + 3] = fmaf(a4.w, v[q * 4 + 3], s4.w);
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if constexpr (TMA_OUT) {
+                        slab_put_row(obuf + kATileBytes, row, (c & 32) >> 3, v);
+                    } else if (valid) {
+                        uint4 o[CH / 8];
+#pragma unroll
+                        for (int q = 0; q < CH / 8; ++q) {
+                            o[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                                              pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+                        }
+                        if (!p.act_up) {
+                            uint4* dst = reinterpret_cast<uint4*>(p.act + pix * p.act_C + cbase);
+#pragma unroll
+                            for (int q = 0; q < CH / 8; ++q) dst[q] = o[q];
+                        } else {
+                            const int W2 = p.W * 2, H2 = p.H * 2;
+#pragma unroll
+                            for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+                                for (int dxx = 0; dxx < 2; ++dxx) {
+                                    const long hp = (static_cast<long>(n) * H2 + 2 * h + dy) * W2 + 2 * w + dxx;
+                                    uint4* dst = reinterpret_cast<uint4*>(p.act + hp * p.act_C + cbase);
+#pragma unroll
+                                    for (int q = 0; q < CH / 8; ++q) dst[q] = o[q];
+                                }
+                            }
+                            if (p.act_lo) {
+                                uint4* dst = reinterpret_cast<uint4*>(p.act_lo + pix * p.act_C + cbase);
+#pragma unroll
+                                for (int q = 0; q < CH / 8; ++q) dst[q] = o[q];
+                            }
+                        }
+                    }
+                }
+            } else {
+                // ---------------------------------------------------------- backward
+                float y[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) { y[j] = 0.f; v[j] *= alpha; }
+                if (p.saved) {
+                    if (valid) {
+                        const uint4* src = reinterpret_cast<const uint4*>(p.saved + pix * p.saved_C + cbase);
+#pragma unroll
+                        for (int q = 0; q < CH / 8; ++q) {
+                            const uint4 t = __ldg(src + q);
+                            y[q * 8 + 0] = bf16_lo(t.x); y[q * 8 + 1] = bf16_hi(t.x);
+                            y[q * 8 + 2] = bf16_lo(t.y); y[q * 8 + 3] = bf16_hi(t.y);
+                            y[q * 8 + 4] = bf16_lo(t.z); y[q * 8 + 5] = bf16_hi(t.z);
+                            y[q * 8 + 6] = bf16_lo(t.w); y[q * 8 + 7] = bf16_hi(t.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) y[j] = 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) v[j] = (y[j] > 0.f) ? v[j] : 0.f;
+                } else if (!valid) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) v[j] = 0.f;
+                }
+                if (p.stat0) {
+                    // BN-affine gradients: reduce over the pixels (lanes) of one image.
+                    if (rows_per_img >= 32) {
+                        float t0[32], t1[32];
+                        static_assert(CH == 32 || CH == 16, "chunk");
+                        if constexpr (CH == 32) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { t0[j] = v[j]; t1[j] = v[j] * y[j]; }
+                            const float s0 = colsum_group<32>(t0, lane);
+                            const float s1 = colsum_group<32>(t1, lane);
+                            const int nn = tni * p.nb + (quad * 32) / rows_per_img;
+                            if (nn < p.NI) {
+                                atomicAdd(p.stat0 + static_cast<long>(nn) * p.stat_stride + cbase + lane, s0);
+                                atomicAdd(p.stat1 + static_cast<long>(nn) * p.stat_stride + cbase + lane, s1);
+                            }
+                        }
+                    } else {
+                        // 16 pixels per image (4x4 maps): half-warp groups.
+                        if constexpr (CH == 32) {
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                float t0[16], t1[16];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) { t0[j] = v[half * 16 + j]; t1[j] = v[half * 16 + j] * y[half * 16 + j]; }
+                                const float s0 = colsum_group<16>(t0, lane);
+                                const float s1 = colsum_group<16>(t1, lane);
+                                const int nn = tni * p.nb + (quad * 32 + (lane & 16)) / rows_per_img;
+                                if (nn < p.NI) {
+                                    atomicAdd(p.stat0 + static_cast<long>(nn) * p.stat_stride + cbase + half * 16 + (lane & 15), s0);
+                                    atomicAdd(p.stat1 + static_cast<long>(nn) * p.stat_stride + cbase + half * 16 + (lane & 15), s1);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (p.aff_a) {
+                    const int nn = valid ? n : 0;
+                    const float* pa = p.aff_a + static_cast<long>(nn) * p.aff_stride + cbase;
+#pragma unroll
+                    for (int q = 0; q < CH / 4; ++q) {
+                        const float4 a4 = __ldg(reinterpret_cast<const float4*>(pa) + q);
+                        v[q * 4 + 0] *= a4.x; v[q * 4 + 1] *= a4.y; v[q * 4 + 2] *= a4.z; v[q * 4 + 3] *= a4.w;
+                    }
+                }
+                if (p.addin && valid && cbase < p.addin_climit) {
+                    if (!p.addin_pool) {
+                        const uint4* src = reinterpret_cast<const uint4*>(p.addin + pix * p.addin_C + cbase);
+#pragma unroll
+                        for (int q = 0; q < CH / 8; ++q) {
+                            const uint4 t = __ldg(src + q);
+                            v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
+                            v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
+                            v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
+                            v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
+                        }
+                    } else {
+                        const int W2 = p.W * 2, H2 = p.H * 2;
+#pragma unroll
+                        for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+                            for (int dxx = 0; dxx < 2; ++dxx) {
+                                const long hp = (static_cast<long>(n) * H2 + 2 * h + dy) * W2 + 2 * w + dxx;
+                                const uint4* src = reinterpret_cast<const uint4*>(p.addin + hp * p.addin_C + cbase);
+#pragma unroll
+                                for (int q = 0; q < CH / 8; ++q) {
+                                    const uint4 t = __ldg(src + q);
+                                    v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
+                                    v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
+                                    v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
+                                    v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
+                                }
+                            }
+                        }
+                    }
+                }
+                if constexpr (TMA_OUT) {
+                    if (p.dx) slab_put_row(obuf, row, (c & 32) >> 3, v);
+                }
+                if (valid) {
+                    if (!TMA_OUT && p.dx) {
+                        uint4* dst = reinterpret_cast<uint4*>(p.dx + pix * p.dx_C + cbase);
+#pragma unroll
+                        for (int q = 0; q < CH / 8; ++q) {
+                            dst[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                                                pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+                        }
+                    }
+                    if (p.dx_f32) {
+                        float4* dst = reinterpret_cast<float4*>(p.dx_f32 + pix * p.dx_f32_C + cbase);
+#pragma unroll
+                        for (int q = 0; q < CH / 4; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                    }
+                }
+            }
+            if constexpr (TMA_OUT) {
+                if (c & 32) {  // a 64-channel slab is complete: hand it to the TMA store engine
+                    fence_async_smem();
+                    bar_epilogue();
+                    if (storer) {
+                        const int cs = n_tile * BN + (c & ~63);
+                        const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.nb;
+                        if constexpr (MODE == EPI_FWD) {
+                            if (p.raw) tma_store_4d(&tmo[0], obuf, cs, w0, h0, n0);
+                            if (p.act) {
+                                if (!p.act_up) {
+                                    tma_store_4d(&tmo[1], obuf + kATileBytes, cs, w0, h0, n0);
+                                } else {
+                                    // nearest x2: the same slab goes to the four (dy, dx) phases of the 2x grid
+                                    for (int d = 0; d < 4; ++d)
+                                        tma_store_5d(&tmo[2], obuf + kATileBytes, cs, d & 1, w0, d >> 1, n0 * p.H + h0);
+                                    if (p.act_lo) tma_store_4d(&tmo[3], obuf + kATileBytes, cs, w0, h0, n0);
+                                }
+                            }
+                        } else {
+                            if (p.dx) tma_store_4d(&tmo[0], obuf, cs, w0, h0, n0);
+                        }
+                        bulk_commit();
+                    }
+                }
+            }
+        }
+        // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+    if (storer) bulk_wait0();  // shared memory must outlive the last bulk store's reads
+}
+
+// Epilogue of both kernels: runs on the 4 epilogue warps (warp & 3 = TMEM lane quadrant).
+template <int BN, int MODE, int CH>
+__device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* stg_base, uint64_t* tfull_bar,
+                                              uint64_t* tempty_bar, uint32_t tmem_base, int total_tiles, int warp,
+                                              int lane) {
+    // ------------------------------------------------------------------ epilogue warps
+    // TMEM hands every thread one accumulator ROW (pixel). Writing rows straight to global
+    // memory makes each warp-wide 16-byte store touch 32 different 128-byte lines. All bulk
+    // epilogue traffic therefore goes through a per-warp, XOR-swizzled shared-memory slab
+    // (32 rows x 64 B for bf16, x 128 B for fp32): threads exchange so that every warp-wide
+    // access covers 8 (or 4) full 64-byte (128-byte) row segments.
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    const int rows_per_img = p.tw * p.th;
+    uint8_t* stg = stg_base + quad * kStageSlabBytes;
+    float alpha = p.alpha;
+    if (p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        TileMap tm;
+        tm.w0 = (m_tile % p.tiles_w) * p.tw;
+        tm.h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+        const int tni = m_tile / (p.tiles_w * p.tiles_h);
+        tm.n0 = tni * p.nb;
+        tm.tw_mask = p.tw - 1; tm.th_mask = p.th - 1; tm.ltw = p.ltw; tm.lthw = p.ltw + p.lth;
+        tm.W = p.W; tm.H = p.H; tm.NI = p.NI;
+        int n, h, w;
+        const bool valid = tm.pix(row, n, h, w);
+        const long pix = (static_cast<long>(n) * p.H + h) * p.W + w;
+
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+
+#pragma unroll 1
+        for (int c = 0; c < BN; c += CH) {
+            const int cbase = n_tile * BN + c;
+            if (cbase >= p.Cout) break;  // warp-uniform
+            float v[CH];
+            {
+                uint32_t u[CH];
+                if constexpr (CH == 32) tmem_ld32(t_addr + c, u);
+                else tmem_ld16(t_addr + c, u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < CH; ++j) v[j] = alpha * __uint_as_float(u[j]);
+            }
+            const bool full_chunk = (cbase + CH <= p.Cout);
+
+            if constexpr (MODE == EPI_FWD) {
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        if (full_chunk || cbase + j < p.Cout) v[j] += __ldg(p.bias + cbase + j);
+                    }
+                }
+                if constexpr (CH == 32) {
+                    if (p.resid) {
+                        SrcMap sm{p.H >> p.resid_shift, p.W >> p.resid_shift, p.resid_shift, 0, 0, 0};
+                        coop_load_add(stg, quad, lane, tm, sm, p.resid, p.resid_C, cbase, v);
+                    }
+                }
+                if (p.img_nchw) {
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            if (cbase + j < p.Cout) {
+                                p.img_nchw[((static_cast<long>(n) * p.Cout + cbase + j) * p.H + h) * p.W + w] = tanhf(v[j]);
+                            }
+                        }
+                    }
+                }
+                if constexpr (CH == 32) {
+                    if (p.raw_f32) coop_store_f32(stg, quad, lane, tm, p.raw_f32, p.raw_f32_C, cbase, v);
+                    if (p.raw) {
+                        SrcMap dm{p.H, p.W, 0, 0, 0, 0};
+                        coop_store_bf16(stg, quad, lane, tm, dm, p.raw, p.raw_C, cbase, v);
+                    }
+                    if (p.act) {
+                        if (p.aff_a) {
+                            const int nn = valid ? n : 0;
+                            const float* pa = p.aff_a + static_cast<long>(nn) * p.aff_stride + cbase;
+                            const float* ps = p.aff_s + static_cast<long>(nn) * p.aff_stride + cbase;
+#pragma unroll
+                            for (int q = 0; q < CH / 4; ++q) {
+                                const float4 a4 = __ldg(reinterpret_cast<const float4*>(pa) + q);
+                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(ps) + q);
+                                v[q * 4 + 0] = fmaf(a4.x, v[q * 4 + 0], s4.x);
+                                v[q * 4 + 1] = fmaf(a4.y, v[q * 4 + 1], s4.y);
+                                v[q * 4 + 2] = fmaf(a4.z, v[q * 4 + 2], s4.z);
+                                v[q * 4 + 3] = fmaf(a4.w, v[q * 4 + 3], s4.w);
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+                        }
+                        if (!p.act_up) {
+                            SrcMap dm{p.H, p.W, 0, 0, 0, 0};
+                            coop_store_bf16(stg, quad, lane, tm, dm, p.act, p.act_C, cbase, v);
+                        } else {
+                            coop_store_bf16_up(stg, quad, lane, tm, p.act, p.act_lo, p.act_C, cbase, v);
+                        }
+                    }
+                }
+            } else {
+                // ---------------------------------------------------------- backward
+                if constexpr (CH == 32) {
+                    float y[CH];
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) y[j] = 0.f;
+                    if (p.saved) {
+                        SrcMap sm{p.H, p.W, 0, 0, 0, 0};
+                        coop_load_add(stg, quad, lane, tm, sm, p.saved, p.saved_C, cbase, y);
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = (y[j] > 0.f) ? v[j] : 0.f;
+                    }
+                    if (!valid) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = 0.f;
+                    }
+                    if (p.stat0) {
+                        // BN-affine gradients: reduce over the pixels (lanes) of one image.
+                        if (rows_per_img >= 32) {
+                            float t0[32], t1[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { t0[j] = v[j]; t1[j] = v[j] * y[j]; }
+                            const float s0 = colsum_group<32>(t0, lane);
+                            const float s1 = colsum_group<32>(t1, lane);
+                            const int nn = tni * p.nb + (quad * 32) / rows_per_img;
+                            if (nn < p.NI) {
+                                atomicAdd(p.stat0 + static_cast<long>(nn) * p.stat_stride + cbase + lane, s0);
+                                atomicAdd(p.stat1 + static_cast<long>(nn) * p.stat_stride + cbase + lane, s1);
+                            }
+                        } else {
+                            // 16 pixels per image (4x4 maps): half-warp groups.
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                float t0[16], t1[16];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) { t0[j] = v[half * 16 + j]; t1[j] = v[half * 16 + j] * y[half * 16 + j]; }
+                                const float s0 = colsum_group<16>(t0, lane);
+                                const float s1 = colsum_group<16>(t1, lane);
+                                const int nn = tni * p.nb + (quad * 32 + (lane & 16)) / rows_per_img;
+                                if (nn < p.NI) {
+                                    atomicAdd(p.stat0 + static_cast<long>(nn) * p.stat_stride + cbase + half * 16 + (lane & 15), s0);
+                                    atomicAdd(p.stat1 + static_cast<long>(nn) * p.stat_stride + cbase + half * 16 + (lane & 15), s1);
+                                }
+                            }
+                        }
+                    }
+                    if (p.aff_a) {
+                        const int nn = valid ? n : 0;
+                        const float* pa = p.aff_a + static_cast<long>(nn) * p.aff_stride + cbase;
+#pragma unroll
+                        for (int q = 0; q < CH / 4; ++q) {
+                            const float4 a4 = __ldg(reinterpret_cast<const float4*>(pa) + q);
+                            v[q * 4 + 0] *= a4.x; v[q * 4 + 1] *= a4.y; v[q * 4 + 2] *= a4.z; v[q * 4 + 3] *= a4.w;
+                        }
+                    }
+                    if (p.addin && cbase < p.addin_climit) {
+                        if (!p.addin_pool) {
+                            SrcMap sm{p.H, p.W, 0, 0, 0, 0};
+                            coop_load_add(stg, quad, lane, tm, sm, p.addin, p.addin_C, cbase, v);
+                        } else {
+#pragma unroll 1
+                            for (int d = 0; d < 4; ++d) {
+                                SrcMap sm{2 * p.H, 2 * p.W, 0, 1, d >> 1, d & 1};
+                                coop_load_add(stg, quad, lane, tm, sm, p.addin, p.addin_C, cbase, v);
+                            }
+                        }
+                    }
+                    if (p.dx) {
+                        SrcMap dm{p.H, p.W, 0, 0, 0, 0};
+                        coop_store_bf16(stg, quad, lane, tm, dm, p.dx, p.dx_C, cbase, v);
+                    }
+                    if (p.dx_f32) coop_store_f32(stg, quad, lane, tm, p.dx_f32, p.dx_f32_C, cbase, v);
+                }
+            }
+        }
+        // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+}
+
+struct OutMaps { CUtensorMap m[4]; };
+
+template <int BN, int MODE, bool TMA_OUT>
+__global__ void __launch_bounds__(kGemmThreads, GemmCfg<BN, TMA_OUT>::kOcc)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvGemmParams p) {
-    using Cfg = GemmCfg<BN>;
+                 const __grid_constant__ OutMaps tmO, const ConvGemmParams p) {
+    using Cfg = GemmCfg<BN, TMA_OUT>;
     constexpr int S = Cfg::kStages;
     constexpr int CH = (BN >= 32) ? 32 : 16;  // epilogue column chunk
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+    uint8_t* obuf = smem + S * Cfg::kStageBytes;  // TMA_OUT: two 16 KB output slabs (1024-aligned)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + Cfg::kOutBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + S;
     uint64_t* tfull_bar = bars + 2 * S;
@@ -217,265 +865,149 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue warps
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-        const int row = quad * 32 + lane;
-        const int wi = row % p.tw;
-        const int hi = (row / p.tw) % p.th;
-        const int ni = row / (p.tw * p.th);
-        const int rows_per_img = p.tw * p.th;
-        float alpha = p.alpha;
-        if (p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-            const int twi = m_tile % p.tiles_w;
-            const int thi = (m_tile / p.tiles_w) % p.tiles_h;
-            const int tni = m_tile / (p.tiles_w * p.tiles_h);
-            const int w = twi * p.tw + wi, h = thi * p.th + hi, n = tni * p.nb + ni;
-            const bool valid = (w < p.W) && (h < p.H) && (n < p.NI);
-            const long pix = (static_cast<long>(n) * p.H + h) * p.W + w;
+#if P2L_EPI_STAGED
+        epilogue_loop<BN, MODE, CH>(p, smem + S * Cfg::kStageBytes + Cfg::kOutBytes + 256, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
+#else
+        epilogue_loop_direct<BN, MODE, CH, TMA_OUT>(p, tmO.m, obuf, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
+#endif
+    }
 
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after();
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
 
-#pragma unroll 1
-            for (int c = 0; c < BN; c += CH) {
-                const int cbase = n_tile * BN + c;
-                if (cbase >= p.Cout) break;  // warp-uniform
-                float v[CH];
-                {
-                    uint32_t u[CH];
-                    if constexpr (CH == 32) tmem_ld32(t_addr + c, u);
-                    else tmem_ld16(t_addr + c, u);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(u[j]);
-                }
-                const bool full_chunk = (cbase + CH <= p.Cout);
+// ============================================================================= 3x3, halo patches
+// For 3x3 / pad 1 convolutions the plain kernel above fetches the A tile once per filter tap:
+// nine 16 KB loads of almost the same pixels, and with small N (64..128 output channels) the
+// layer is bound by L2 -> SM bandwidth, not by the tensor pipe. Here the producer loads ONE
+// (16+2) x (8+2) pixel patch per 64-channel chunk (box {64, P, 18, 1}, P = patch row pitch in
+// pixels) and the nine taps are nine views of that patch: tap (r, s) starts (r*P + s) rows in,
+// 8-row groups (one output row of the 8-wide tile) are P*128 bytes apart (the descriptor's SBO).
+// TMA and tcgen05 both apply the 128-byte swizzle on absolute shared-memory address bits, so a
+// row-shifted start address addresses the same bytes TMA wrote.
+// Two rings: A patches (consumed once per 9 taps) and B weight tiles (one per tap).
+template <int BN, int P>
+struct HaloCfg {
+    static constexpr int kTw = 8, kTh = 16;
+    static constexpr int kPatchTx = P * (kTh + 2) * 128;
+    static constexpr int kPatchBytes = ((kPatchTx + 1023) / 1024) * 1024;
+    static constexpr int kBTileBytes = BN * kBK * 2;
+    static constexpr int kAStages = (P == 16 && BN == 256) ? 2 : 3;
+    static constexpr int kBStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int kRingBytes = kAStages * kPatchBytes + kBStages * kBTileBytes;
+    static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int kSmemBytes = kRingBytes + 1024 + 256 + 4 * kStageSlabBytes;
+};
 
-                if constexpr (MODE == EPI_FWD) {
-                    // ---- v = alpha*acc + bias (+ skip)
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) {
-                        float b = 0.f;
-                        if (p.bias && (full_chunk || cbase + j < p.Cout)) b = __ldg(p.bias + cbase + j);
-                        v[j] = alpha * v[j] + b;
-                    }
-                    if (p.resid && valid) {
-                        const int Hs = p.H >> p.resid_shift, Ws = p.W >> p.resid_shift;
-                        const long rp = (static_cast<long>(n) * Hs + (h >> p.resid_shift)) * Ws + (w >> p.resid_shift);
-                        const uint4* src = reinterpret_cast<const uint4*>(p.resid + rp * p.resid_C + cbase);
-#pragma unroll
-                        for (int q = 0; q < CH / 8; ++q) {
-                            const uint4 t = __ldg(src + q);
-                            v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
-                            v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
-                            v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
-                            v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
-                        }
-                    }
-                    if (p.img_nchw) {
-                        if (valid) {
-#pragma unroll
-                            for (int j = 0; j < CH; ++j) {
-                                if (cbase + j < p.Cout) {
-                                    p.img_nchw[((static_cast<long>(n) * p.Cout + cbase + j) * p.H + h) * p.W + w] = tanhf(v[j]);
-                                }
-                            }
-                        }
-                    }
-                    if (p.raw_f32 && valid) {
-                        float4* dst = reinterpret_cast<float4*>(p.raw_f32 + pix * p.raw_f32_C + cbase);
-#pragma unroll
-                        for (int q = 0; q < CH / 4; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                    }
-                    if (p.raw && valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.raw + pix * p.raw_C + cbase);
-#pragma unroll
-                        for (int q = 0; q < CH / 8; ++q) {
-                            dst[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                                                pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
-                        }
-                    }
-                    if (p.act) {
-                        if (p.aff_a) {
-                            const int nn = valid ? n : 0;
-                            const float* pa = p.aff_a + static_cast<long>(nn) * p.aff_stride + cbase;
-                            const float* ps = p.aff_s + static_cast<long>(nn) * p.aff_stride + cbase;
-#pragma unroll
-                            for (int q = 0; q < CH / 4; ++q) {
-                                const float4 a4 = __ldg(reinterpret_cast<const float4*>(pa) + q);
-                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(ps) + q);
-                                v[q * 4 + 0] = fmaf(a4.x, v[q * 4 + 0], s4.x);
-                                v[q * 4 + 1] = fmaf(a4.y, v[q * 4 + 1], s4.y);
-                                v[q * 4 + 2] = fmaf(a4.z, v[q * 4 + 2], s4.z);
-                                v[q * 4 + 3] = fmaf(a4.w, v[q * 4 + 3], s4.w);
-                            }
-                        }
-                        if (p.relu) {
-#pragma unroll
-                            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
-                        }
-                        if (valid) {
-                            uint4 o[CH / 8];
-#pragma unroll
-                            for (int q = 0; q < CH / 8; ++q) {
-                                o[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                                                  pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
-                            }
-                            if (!p.act_up) {
-                                uint4* dst = reinterpret_cast<uint4*>(p.act + pix * p.act_C + cbase);
-#pragma unroll
-                                for (int q = 0; q < CH / 8; ++q) dst[q] = o[q];
-                            } else {
-                                const int W2 = p.W * 2, H2 = p.H * 2;
-#pragma unroll
-                                for (int dy = 0; dy < 2; ++dy) {
-#pragma unroll
-                                    for (int dxx = 0; dxx < 2; ++dxx) {
-                                        const long hp = (static_cast<long>(n) * H2 + 2 * h + dy) * W2 + 2 * w + dxx;
-                                        uint4* dst = reinterpret_cast<uint4*>(p.act + hp * p.act_C + cbase);
-#pragma unroll
-                                        for (int q = 0; q < CH / 8; ++q) dst[q] = o[q];
-                                    }
-                                }
-                                if (p.act_lo) {
-                                    uint4* dst = reinterpret_cast<uint4*>(p.act_lo + pix * p.act_C + cbase);
-#pragma unroll
-                                    for (int q = 0; q < CH / 8; ++q) dst[q] = o[q];
-                                }
-                            }
-                        }
-                    }
-                } else {
-                    // ---------------------------------------------------------- backward
-                    float y[CH];
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) { y[j] = 0.f; v[j] *= alpha; }
-                    if (p.saved) {
-                        if (valid) {
-                            const uint4* src = reinterpret_cast<const uint4*>(p.saved + pix * p.saved_C + cbase);
-#pragma unroll
-                            for (int q = 0; q < CH / 8; ++q) {
-                                const uint4 t = __ldg(src + q);
-                                y[q * 8 + 0] = bf16_lo(t.x); y[q * 8 + 1] = bf16_hi(t.x);
-                                y[q * 8 + 2] = bf16_lo(t.y); y[q * 8 + 3] = bf16_hi(t.y);
-                                y[q * 8 + 4] = bf16_lo(t.z); y[q * 8 + 5] = bf16_hi(t.z);
-                                y[q * 8 + 6] = bf16_lo(t.w); y[q * 8 + 7] = bf16_hi(t.w);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < CH; ++j) y[j] = 0.f;
-                        }
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) v[j] = (y[j] > 0.f) ? v[j] : 0.f;
-                    } else if (!valid) {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) v[j] = 0.f;
-                    }
-                    if (p.stat0) {
-                        // BN-affine gradients: reduce over the pixels (lanes) of one image.
-                        if (rows_per_img >= 32) {
-                            float t0[32], t1[32];
-                            static_assert(CH == 32 || CH == 16, "chunk");
-                            if constexpr (CH == 32) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) { t0[j] = v[j]; t1[j] = v[j] * y[j]; }
-                                const float s0 = colsum_group<32>(t0, lane);
-                                const float s1 = colsum_group<32>(t1, lane);
-                                const int nn = tni * p.nb + (quad * 32) / rows_per_img;
-                                if (nn < p.NI) {
-                                    atomicAdd(p.stat0 + static_cast<long>(nn) * p.stat_stride + cbase + lane, s0);
-                                    atomicAdd(p.stat1 + static_cast<long>(nn) * p.stat_stride + cbase + lane, s1);
-                                }
-                            }
-                        } else {
-                            // 16 pixels per image (4x4 maps): half-warp groups.
-                            if constexpr (CH == 32) {
-#pragma unroll
-                                for (int half = 0; half < 2; ++half) {
-                                    float t0[16], t1[16];
-#pragma unroll
-                                    for (int j = 0; j < 16; ++j) { t0[j] = v[half * 16 + j]; t1[j] = v[half * 16 + j] * y[half * 16 + j]; }
-                                    const float s0 = colsum_group<16>(t0, lane);
-                                    const float s1 = colsum_group<16>(t1, lane);
-                                    const int nn = tni * p.nb + (quad * 32 + (lane & 16)) / rows_per_img;
-                                    if (nn < p.NI) {
-                                        atomicAdd(p.stat0 + static_cast<long>(nn) * p.stat_stride + cbase + half * 16 + (lane & 15), s0);
-                                        atomicAdd(p.stat1 + static_cast<long>(nn) * p.stat_stride + cbase + half * 16 + (lane & 15), s1);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    if (p.aff_a) {
-                        const int nn = valid ? n : 0;
-                        const float* pa = p.aff_a + static_cast<long>(nn) * p.aff_stride + cbase;
-#pragma unroll
-                        for (int q = 0; q < CH / 4; ++q) {
-                            const float4 a4 = __ldg(reinterpret_cast<const float4*>(pa) + q);
-                            v[q * 4 + 0] *= a4.x; v[q * 4 + 1] *= a4.y; v[q * 4 + 2] *= a4.z; v[q * 4 + 3] *= a4.w;
-                        }
-                    }
-                    if (p.addin && valid && cbase < p.addin_climit) {
-                        if (!p.addin_pool) {
-                            const uint4* src = reinterpret_cast<const uint4*>(p.addin + pix * p.addin_C + cbase);
-#pragma unroll
-                            for (int q = 0; q < CH / 8; ++q) {
-                                const uint4 t = __ldg(src + q);
-                                v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
-                                v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
-                                v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
-                                v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
-                            }
-                        } else {
-                            const int W2 = p.W * 2, H2 = p.H * 2;
-#pragma unroll
-                            for (int dy = 0; dy < 2; ++dy) {
-#pragma unroll
-                                for (int dxx = 0; dxx < 2; ++dxx) {
-                                    const long hp = (static_cast<long>(n) * H2 + 2 * h + dy) * W2 + 2 * w + dxx;
-                                    const uint4* src = reinterpret_cast<const uint4*>(p.addin + hp * p.addin_C + cbase);
-#pragma unroll
-                                    for (int q = 0; q < CH / 8; ++q) {
-                                        const uint4 t = __ldg(src + q);
-                                        v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
-                                        v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
-                                        v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
-                                        v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    if (valid) {
-                        if (p.dx) {
-                            uint4* dst = reinterpret_cast<uint4*>(p.dx + pix * p.dx_C + cbase);
-#pragma unroll
-                            for (int q = 0; q < CH / 8; ++q) {
-                                dst[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                                                    pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
-                            }
-                        }
-                        if (p.dx_f32) {
-                            float4* dst = reinterpret_cast<float4*>(p.dx_f32 + pix * p.dx_f32_C + cbase);
-#pragma unroll
-                            for (int q = 0; q < CH / 4; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                        }
+template <int BN, int MODE, int P>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const ConvGemmParams p) {
+    using Cfg = HaloCfg<BN, P>;
+    constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
+    constexpr int CH = (BN >= 32) ? 32 : 16;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smemB = smem + SA * Cfg::kPatchBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kRingBytes);
+    uint64_t* afull = bars;
+    uint64_t* aempty = bars + SA;
+    uint64_t* bfull = bars + 2 * SA;
+    uint64_t* bempty = bars + 2 * SA + SB;
+    uint64_t* tfull_bar = bars + 2 * SA + 2 * SB;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < SA; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+        mbar_init(&tfull_bar[0], 1);
+        mbar_init(&tfull_bar[1], 1);
+        mbar_init(&tempty_bar[0], 4);
+        mbar_init(&tempty_bar[1], 4);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int total_tiles = m_tiles * p.n_tiles;
+    const int Cin = p.cin_chunks * kBK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+                const int w0 = (m_tile % p.tiles_w) * Cfg::kTw;
+                const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * Cfg::kTh;
+                const int n0 = m_tile / (p.tiles_w * p.tiles_h);
+                for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                    mbar_wait(&aempty[sa], pa ^ 1);
+                    mbar_expect_tx(&afull[sa], Cfg::kPatchTx);
+                    tma_load_4d(smem + sa * Cfg::kPatchBytes, &tmA, &afull[sa], p.a_c0 + cc * kBK, w0 - 1, h0 - 1, n0);
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&bempty[sb], pb ^ 1);
+                        mbar_expect_tx(&bfull[sb], Cfg::kBTileBytes);
+                        tma_load_3d(smemB + sb * Cfg::kBTileBytes, &tmB, &bfull[sb], tap * Cin + cc * kBK, n_tile * BN, 0);
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
                     }
                 }
             }
-            // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BN);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                    mbar_wait(&afull[sa], pa);
+                    const uint32_t a_base = smem_u32(smem + sa * Cfg::kPatchBytes);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&bfull[sb], pb);
+                        tc_fence_after();
+                        const int r = tap / 3, s = tap - 3 * r;
+                        const uint32_t a_addr = a_base + (r * P + s) * 128;
+                        const uint64_t adesc = umma_desc_sw128(a_addr, P * 128, p.halo_bo ? (a_addr >> 7) : 0);
+                        const uint64_t bdesc = umma_desc_k128(smem_u32(smemB + sb * Cfg::kBTileBytes));
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k) {
+                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cc | tap | k) != 0);
+                        }
+                        umma_commit(&bempty[sb]);
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                    }
+                    umma_commit(&aempty[sa]);
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);
+            }
+        }
+    } else {
+#if P2L_EPI_STAGED
+        epilogue_loop<BN, MODE, CH>(p, smem + Cfg::kRingBytes + 256, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
+#else
+        epilogue_loop_direct<BN, MODE, CH, false>(p, nullptr, nullptr, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
+#endif
     }
-
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);

@@ -27,8 +27,11 @@ struct ConvDesc {
 
 struct ConvOp {
     CUtensorMap tmA, tmB;
+    OutMaps tmO;
+    int tma_out;  // epilogue outputs through TMA bulk stores
     ConvGemmParams p;
     int BN, mode, grid;
+    int halo;  // 0: per-tap A loads; 10 / 16: halo-patch kernel with that patch row pitch
     double flops;  // algorithmic 2*M*N*K of this launch
 };
 
@@ -41,8 +44,12 @@ const char* get_error();
 int num_sms();
 void count_launch();  // every kernel launch of the library is counted (bench.py gpu_launches)
 long launch_count();
+// tuning / experiment switches: "halo" (0 off, 10, 16), "halo_bo" (0/1)
+void set_option(const char* key, int value);
+int get_option(const char* key);
 void profile_enable(int on);
 int profile_read(double* conv_ms, long* conv_launches, double* conv_flops);
+int profile_get(int i, float* ms, double* flops, int* info);
 
 #define P2L_CUDA_CHECK(expr)                                                             \
     do {                                                                                 \

@@ -35,42 +35,46 @@ void k_concat_cond(const float* z, const float* c, float* cond, int b, int zd, i
     concat_cond_kernel<<<cdiv((long)b * (zd + cd), 256), 256, 0, st>>>(z, c, cond, b, zd, cd); count_launch();
 }
 
-// one warp per channel; cond staged in shared memory
-__global__ void cond_affine_kernel(const float* __restrict__ cond, const float* __restrict__ Ws,
-                                   const float* __restrict__ Wo, const float* __restrict__ mean,
+// thread per channel; weights stored transposed ([cdim][C]) so that a warp reads 128 contiguous
+// bytes per k; cond staged in shared memory (broadcast reads); 8 samples per register pass
+__global__ void cond_affine_kernel(const float* __restrict__ cond, const float* __restrict__ WsT,
+                                   const float* __restrict__ WoT, const float* __restrict__ mean,
                                    const float* __restrict__ inv_std, float* a, float* s, int b,
                                    int cdim, int C, int stride) {
     extern __shared__ float sc[];  // [b, cdim]
     for (int i = threadIdx.x; i < b * cdim; i += blockDim.x) sc[i] = cond[i];
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ch = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= C) return;
-    const float* ws = Ws + (long)ch * cdim;
-    const float* wo = Wo + (long)ch * cdim;
     const float m = mean[ch], is = inv_std[ch];
-    for (int bi = 0; bi < b; ++bi) {
-        float ds = 0.f, dof = 0.f;
-        for (int k = lane; k < cdim; k += 32) {
-            const float cv = sc[bi * cdim + k];
-            ds = fmaf(cv, ws[k], ds);
-            dof = fmaf(cv, wo[k], dof);
+    for (int b0 = 0; b0 < b; b0 += 8) {
+        float as[8], ao[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { as[i] = 0.f; ao[i] = 0.f; }
+        for (int k = 0; k < cdim; ++k) {
+            const float ws = WsT[(long)k * C + ch], wo = WoT[(long)k * C + ch];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float cv = sc[min(b0 + i, b - 1) * cdim + k];
+                as[i] = fmaf(cv, ws, as[i]);
+                ao[i] = fmaf(cv, wo, ao[i]);
+            }
         }
-        ds = warp_sum(ds);
-        dof = warp_sum(dof);
-        if (lane == 0) {
-            const float av = (1.f + ds) * is;
-            a[(long)bi * stride + ch] = av;
-            s[(long)bi * stride + ch] = dof - m * av;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (b0 + i < b) {
+                const float av = (1.f + as[i]) * is;
+                a[(long)(b0 + i) * stride + ch] = av;
+                s[(long)(b0 + i) * stride + ch] = ao[i] - m * av;
+            }
         }
     }
 }
-void k_cond_affine(const float* cond, const float* Ws, const float* Wo, const float* mean,
+void k_cond_affine(const float* cond, const float* WsT, const float* WoT, const float* mean,
                    const float* inv_std, float* a, float* s, int b, int cdim, int C_cond, int stride,
                    cudaStream_t st) {
-    const int warps = 8;
-    cond_affine_kernel<<<cdiv(C_cond, warps), warps * 32, (size_t)b * cdim * sizeof(float), st>>>(
-        cond, Ws, Wo, mean, inv_std, a, s, b, cdim, C_cond, stride); count_launch();
+    cond_affine_kernel<<<cdiv(C_cond, 128), 128, (size_t)b * cdim * sizeof(float), st>>>(
+        cond, WsT, WoT, mean, inv_std, a, s, b, cdim, C_cond, stride); count_launch();
 }
 
 __global__ void uncond_affine_kernel(const float* weight, const float* bias, const float* mean,
@@ -89,36 +93,42 @@ void k_uncond_affine(const float* weight, const float* bias, const float* mean, 
                                                                      C_cond, C_unc, stride); count_launch();
 }
 
-__global__ void gen_z_kernel(const float* __restrict__ cond, const float* __restrict__ W,
+__global__ void gen_z_kernel(const float* __restrict__ cond, const float* __restrict__ WT,
                              const float* __restrict__ bias, const float* __restrict__ a,
                              const float* __restrict__ s, int aff_stride, bf16* raw, bf16* act, int b,
                              int cdim, int J, int C) {
     extern __shared__ float sc[];
     for (int i = threadIdx.x; i < b * cdim; i += blockDim.x) sc[i] = cond[i];
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int j = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= J) return;
-    const float* w = W + (long)j * cdim;
     const int ch = j % C;
     const float bj = bias[j];
-    for (int bi = 0; bi < b; ++bi) {
-        float d = 0.f;
-        for (int k = lane; k < cdim; k += 32) d = fmaf(sc[bi * cdim + k], w[k], d);
-        d = warp_sum(d);
-        if (lane == 0) {
-            const float h = d + bj;
-            raw[(long)bi * J + j] = f2b(h);
-            const float y = fmaf(a[(long)bi * aff_stride + ch], h, s[(long)bi * aff_stride + ch]);
-            act[(long)bi * J + j] = f2b(fmaxf(y, 0.f));
+    for (int b0 = 0; b0 < b; b0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int k = 0; k < cdim; ++k) {
+            const float w = WT[(long)k * J + j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(sc[min(b0 + i, b - 1) * cdim + k], w, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int bi = b0 + i;
+            if (bi < b) {
+                const float h = acc[i] + bj;
+                raw[(long)bi * J + j] = f2b(h);
+                const float y = fmaf(a[(long)bi * aff_stride + ch], h, s[(long)bi * aff_stride + ch]);
+                act[(long)bi * J + j] = f2b(fmaxf(y, 0.f));
+            }
         }
     }
 }
-void k_gen_z(const float* cond, const float* W, const float* bias, const float* a, const float* s,
+void k_gen_z(const float* cond, const float* WT, const float* bias, const float* a, const float* s,
              int aff_stride, bf16* raw, bf16* act, int b, int cdim, int J, int C, cudaStream_t st) {
-    const int warps = 8;
-    gen_z_kernel<<<cdiv(J, warps), warps * 32, (size_t)b * cdim * sizeof(float), st>>>(
-        cond, W, bias, a, s, aff_stride, raw, act, b, cdim, J, C); count_launch();
+    gen_z_kernel<<<cdiv(J, 128), 128, (size_t)b * cdim * sizeof(float), st>>>(
+        cond, WT, bias, a, s, aff_stride, raw, act, b, cdim, J, C); count_launch();
 }
 
 __global__ void bn_grad_finalize_kernel(const float* S0, const float* S1, const float* a, const float* s,
@@ -142,7 +152,7 @@ void k_bn_grad_finalize(const float* S0, const float* S1, const float* a, const 
 }
 
 // dcond[b,k] += sum_j G[b,j] W[j,k]; block = cdim threads (one per k), 128 rows of W per block
-constexpr int kDcRows = 128;
+constexpr int kDcRows = 256;
 __global__ void dcond_accum_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ W,
                                    float* dcond, int b, int J, int cdim) {
     extern __shared__ float sg[];  // [b][kDcRows]
@@ -155,19 +165,17 @@ __global__ void dcond_accum_kernel(const float* __restrict__ G, int ldg, const f
     __syncthreads();
     const int k = threadIdx.x;
     if (k >= cdim) return;
-    for (int b0 = 0; b0 < b; b0 += 8) {
-        float acc[8];
+    for (int b0 = 0; b0 < b; b0 += 24) {
+        float acc[24];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int i = 0; i < 24; ++i) acc[i] = 0.f;
         for (int jj = 0; jj < nj; ++jj) {
             const float w = W[(long)(j0 + jj) * cdim + k];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (b0 + i < b) acc[i] = fmaf(sg[(b0 + i) * kDcRows + jj], w, acc[i]);
-            }
+            for (int i = 0; i < 24; ++i) acc[i] = fmaf(sg[min(b0 + i, b - 1) * kDcRows + jj], w, acc[i]);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 24; ++i) {
             if (b0 + i < b) atomicAdd(dcond + (long)(b0 + i) * cdim + k, acc[i]);
         }
     }
@@ -208,46 +216,73 @@ __global__ void fill_kernel(float* p, float v, long n) {
 void k_fill_f32(float* p, float v, long n, cudaStream_t st) { fill_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, v, n); count_launch(); }
 
 // ============================================================================= BigGAN glue
-// block: 64 channels x 4 pixel lanes; each block covers 64 low-res pixels of one image
+// thread = 8 channels (one uint4) of one low-res pixel; block = 8 channel-groups x 32 pixels
+__device__ __forceinline__ void unpack8(const uint4 t, float (&f)[8]) {
+    f[0] = __uint_as_float(t.x << 16); f[1] = __uint_as_float(t.x & 0xFFFF0000u);
+    f[2] = __uint_as_float(t.y << 16); f[3] = __uint_as_float(t.y & 0xFFFF0000u);
+    f[4] = __uint_as_float(t.z << 16); f[5] = __uint_as_float(t.z & 0xFFFF0000u);
+    f[6] = __uint_as_float(t.w << 16); f[7] = __uint_as_float(t.w & 0xFFFF0000u);
+}
+__device__ __forceinline__ uint32_t pk2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pk2(f[0], f[1]), pk2(f[2], f[3]), pk2(f[4], f[5]), pk2(f[6], f[7]));
+}
 __global__ void pool_bnrelu_bwd_kernel(const bf16* __restrict__ g_up, const bf16* __restrict__ y_lo,
                                        const float* __restrict__ a, int aff_stride, float* S0, float* S1,
                                        int stat_stride, bf16* dx, int H, int W, int C) {
-    __shared__ float r0[4][64], r1[4][64];
-    const int cx = threadIdx.x, py = threadIdx.y;
-    const int c = blockIdx.y * 64 + cx;
+    __shared__ float r0[32][65], r1[32][65];
+    const int cg = threadIdx.x, py = threadIdx.y;  // 8 x 32
+    const int c = blockIdx.y * 64 + cg * 8;
     const int bi = blockIdx.z;
     const int HW = H * W;
-    const int p0 = blockIdx.x * 64;
-    const float av = a[(long)bi * aff_stride + c];
-    float s0 = 0.f, s1 = 0.f;
     const int W2 = 2 * W;
-    for (int pp = py; pp < 64; pp += 4) {
-        const int p = p0 + pp;
-        if (p >= HW) break;
+    float av[8], s0[8], s1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { av[i] = a[(long)bi * aff_stride + c + i]; s0[i] = 0.f; s1[i] = 0.f; }
+    for (int p = blockIdx.x * 256 + py; p < min(HW, (int)(blockIdx.x + 1) * 256); p += 32) {
         const int y = p / W, x = p % W;
         const long base = (((long)bi * 2 * H + 2 * y) * W2 + 2 * x) * C + c;
-        const float g = b2f(g_up[base]) + b2f(g_up[base + C]) + b2f(g_up[base + (long)W2 * C]) +
-                        b2f(g_up[base + (long)W2 * C + C]);
+        float g[8], t[8], yv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(g_up + base)), g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(g_up + base + C)), t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] += t[i];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(g_up + base + (long)W2 * C)), t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] += t[i];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(g_up + base + (long)W2 * C + C)), t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] += t[i];
         const long o = ((long)bi * HW + p) * C + c;
-        const float yv = b2f(y_lo[o]);
-        const float dpre = yv > 0.f ? g : 0.f;
-        s0 += dpre;
-        s1 += dpre * yv;
-        dx[o] = f2b(av * dpre);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(y_lo + o)), yv);
+        float d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float dpre = yv[i] > 0.f ? g[i] : 0.f;
+            s0[i] += dpre;
+            s1[i] += dpre * yv[i];
+            d[i] = av[i] * dpre;
+        }
+        *reinterpret_cast<uint4*>(dx + o) = pack8(d);
     }
-    r0[py][cx] = s0;
-    r1[py][cx] = s1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r0[py][cg * 8 + i] = s0[i]; r1[py][cg * 8 + i] = s1[i]; }
     __syncthreads();
-    if (py == 0) {
-        s0 = r0[0][cx] + r0[1][cx] + r0[2][cx] + r0[3][cx];
-        s1 = r1[0][cx] + r1[1][cx] + r1[2][cx] + r1[3][cx];
-        atomicAdd(S0 + (long)bi * stat_stride + c, s0);
-        atomicAdd(S1 + (long)bi * stat_stride + c, s1);
+    const int tid = py * 8 + cg;
+    if (tid < 64) {
+        float t0 = 0.f, t1 = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) { t0 += r0[k][tid]; t1 += r1[k][tid]; }
+        atomicAdd(S0 + (long)bi * stat_stride + blockIdx.y * 64 + tid, t0);
+        atomicAdd(S1 + (long)bi * stat_stride + blockIdx.y * 64 + tid, t1);
     }
 }
 void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int aff_stride, float* S0,
                        float* S1, int stat_stride, bf16* dx, int b, int H, int W, int C, cudaStream_t st) {
-    dim3 grid(cdiv((long)H * W, 64), C / 64, b), block(64, 4);
+    dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
     pool_bnrelu_bwd_kernel<<<grid, block, 0, st>>>(g_up, y_lo, a, aff_stride, S0, S1, stat_stride, dx, H, W, C); count_launch();
 }
 
@@ -342,24 +377,38 @@ void k_softmax_bwd(const bf16* P, const float* dP, bf16* dS, long rows, int n, c
 }
 
 __global__ void transpose_kernel(const bf16* __restrict__ in, int ldin, int in_c0, bf16* __restrict__ out, int R, int C) {
-    __shared__ bf16 tile[32][33];
+    // 64 x 64 tile; rows padded to 72 elements so column reads spread over the banks
+    __shared__ __align__(16) bf16 tile[64][72];
     const int bi = blockIdx.z;
-    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
     const bf16* src = in + (long)bi * R * ldin + in_c0;
     bf16* dst = out + (long)bi * C * R;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int r = r0 + i, c = c0 + threadIdx.x;
-        if (r < R && c < C) tile[i][threadIdx.x] = src[(long)r * ldin + c];
+    const int t = threadIdx.x;  // 256 threads
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = t + i * 256;       // 512 pieces of 8 elements
+        const int r = idx >> 3, cp = (idx & 7) * 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r0 + r < R && c0 + cp < C) v = __ldg(reinterpret_cast<const uint4*>(src + (long)(r0 + r) * ldin + c0 + cp));
+        *reinterpret_cast<uint4*>(&tile[r][cp]) = v;
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int c = c0 + i, r = r0 + threadIdx.x;
-        if (r < R && c < C) dst[(long)c * R + r] = tile[threadIdx.x][i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = t + i * 256;
+        const int c = idx >> 3, rp = (idx & 7) * 8;
+        if (c0 + c < C && r0 + rp < R) {
+            __align__(16) bf16 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = tile[rp + k][c];
+            *reinterpret_cast<uint4*>(dst + (long)(c0 + c) * R + r0 + rp) = *reinterpret_cast<const uint4*>(v);
+        }
     }
 }
 void k_transpose(const bf16* in, int ldin, int in_c0, bf16* out, int b, int R, int C, cudaStream_t st) {
-    dim3 grid(cdiv(C, 32), cdiv(R, 32), b), block(32, 8);
-    transpose_kernel<<<grid, block, 0, st>>>(in, ldin, in_c0, out, R, C); count_launch();
+    // requires R % 8 == 0, C % 8 == 0, 16-byte aligned rows (true for every caller)
+    dim3 grid(cdiv(C, 64), cdiv(R, 64), b);
+    transpose_kernel<<<grid, 256, 0, st>>>(in, ldin, in_c0, out, R, C); count_launch();
 }
 
 // ============================================================================= image / loss glue
@@ -368,23 +417,31 @@ __constant__ float kLpipsScale[3] = {.458f, .448f, .450f};
 
 __global__ void im2col_alex1_kernel(const float* __restrict__ img, bf16* __restrict__ col, int b, int H, int W,
                                     int Ho, int Wo, int Kp) {
+    // thread = 8 consecutive k of one output pixel -> one 16-byte store
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long total = (long)b * Ho * Wo * Kp;
+    const int groups = Kp / 8;
+    const long total = (long)b * Ho * Wo * groups;
     if (i >= total) return;
-    const int k = i % Kp;
-    const long q = i / Kp;
+    const int kg = i % groups;
+    const long q = i / groups;
     const int ox = q % Wo, oy = (q / Wo) % Ho, bi = q / ((long)Wo * Ho);
-    float v = 0.f;
-    if (k < 363) {
-        const int c = k / 121, r = (k / 11) % 11, s = k % 11;
-        const int y = 4 * oy - 2 + r, x = 4 * ox - 2 + s;
-        if (y >= 0 && y < H && x >= 0 && x < W)
-            v = (img[(((long)bi * 3 + c) * H + y) * W + x] - kLpipsShift[c]) / kLpipsScale[c];
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = kg * 8 + e;
+        float val = 0.f;
+        if (k < 363) {
+            const int c = k / 121, rem = k - c * 121, r = rem / 11, s = rem - r * 11;
+            const int y = 4 * oy - 2 + r, x = 4 * ox - 2 + s;
+            if (y >= 0 && y < H && x >= 0 && x < W)
+                val = (__ldg(img + (((long)bi * 3 + c) * H + y) * W + x) - kLpipsShift[c]) / kLpipsScale[c];
+        }
+        v[e] = val;
     }
-    col[i] = f2b(v);
+    *reinterpret_cast<uint4*>(col + q * Kp + kg * 8) = pack8(v);
 }
 void k_im2col_alex1(const float* img, bf16* col, int b, int H, int W, int Ho, int Wo, int Kp, cudaStream_t st) {
-    const long total = (long)b * Ho * Wo * Kp;
+    const long total = (long)b * Ho * Wo * (Kp / 8);
     im2col_alex1_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, col, b, H, W, Ho, Wo, Kp); count_launch();
 }
 
@@ -418,25 +475,33 @@ void k_col2im_alex1(const bf16* dcol, float* dimg, int b, int H, int W, int Ho, 
 __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, unsigned char* __restrict__ idx,
                                    int b, int H, int W, int C, int Ho, int Wo, int k, int s) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long total = (long)b * Ho * Wo * C;
+    const int CG = C / 8;
+    const long total = (long)b * Ho * Wo * CG;
     if (i >= total) return;
-    const int c = i % C;
-    const long q = i / C;
+    const int cg = i % CG;
+    const long q = i / CG;
     const int ox = q % Wo, oy = (q / Wo) % Ho, bi = q / ((long)Wo * Ho);
-    float best = 0.f;
-    int bidx = 0;
+    float best[8];
+    int bidx[8];
     for (int r = 0; r < k; ++r) {
         for (int t = 0; t < k; ++t) {
-            const float v = b2f(x[(((long)bi * H + oy * s + r) * W + ox * s + t) * C + c]);
-            if ((r == 0 && t == 0) || v > best) { best = v; bidx = r * k + t; }
+            float v[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long)bi * H + oy * s + r) * W + ox * s + t) * C + cg * 8)), v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if ((r == 0 && t == 0) || v[e] > best[e]) { best[e] = v[e]; bidx[e] = r * k + t; }
+            }
         }
     }
-    out[i] = f2b(best);
-    idx[i] = (unsigned char)bidx;
+    *reinterpret_cast<uint4*>(out + q * C + cg * 8) = pack8(best);
+    uint2 pk;
+    pk.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+    pk.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+    *reinterpret_cast<uint2*>(idx + q * C + cg * 8) = pk;
 }
 void k_maxpool_fwd(const bf16* x, bf16* out, unsigned char* idx, int b, int H, int W, int C, int Ho, int Wo, int k,
                    int s, cudaStream_t st) {
-    const long total = (long)b * Ho * Wo * C;
+    const long total = (long)b * Ho * Wo * (C / 8);
     maxpool_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, out, idx, b, H, W, C, Ho, Wo, k, s); count_launch();
 }
 
@@ -444,12 +509,15 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dout, const unsigned
                                    const bf16* __restrict__ x, const bf16* __restrict__ addin, bf16* __restrict__ dx,
                                    int b, int H, int W, int C, int Ho, int Wo, int k, int s) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long total = (long)b * H * W * C;
+    const int CG = C / 8;
+    const long total = (long)b * H * W * CG;
     if (i >= total) return;
-    const int c = i % C;
-    const long q = i / C;
+    const int cg = i % CG;
+    const long q = i / CG;
     const int xx = q % W, y = (q / W) % H, bi = q / ((long)W * H);
-    float acc = 0.f;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     // windows (oy, ox) with oy*s <= y < oy*s + k
     const int oy_lo = max(0, (y - k + s) / s), oy_hi = min(Ho - 1, y / s);
     const int ox_lo = max(0, (xx - k + s) / s), ox_hi = min(Wo - 1, xx / s);
@@ -459,17 +527,36 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dout, const unsigned
         for (int ox = ox_lo; ox <= ox_hi; ++ox) {
             const int t = xx - ox * s;
             if (t < 0 || t >= k) continue;
-            const long o = (((long)bi * Ho + oy) * Wo + ox) * C + c;
-            if (idx[o] == r * k + t) acc += b2f(dout[o]);
+            const long o = (((long)bi * Ho + oy) * Wo + ox) * C + cg * 8;
+            const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx + o));
+            float g[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dout + o)), g);
+            const int me = r * k + t;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int id = ((e < 4 ? pk.x : pk.y) >> ((e & 3) * 8)) & 0xFF;
+                if (id == me) acc[e] += g[e];
+            }
         }
     }
-    if (x && !(b2f(x[i]) > 0.f)) acc = 0.f;
-    if (addin) acc += b2f(addin[i]);
-    dx[i] = f2b(acc);
+    const long o = q * C + cg * 8;
+    if (x) {
+        float xv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + o)), xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (!(xv[e] > 0.f)) acc[e] = 0.f;
+    }
+    if (addin) {
+        float av[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(addin + o)), av);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += av[e];
+    }
+    *reinterpret_cast<uint4*>(dx + o) = pack8(acc);
 }
 void k_maxpool_bwd(const bf16* dout, const unsigned char* idx, const bf16* x, const bf16* addin, bf16* dx, int b,
                    int H, int W, int C, int Ho, int Wo, int k, int s, cudaStream_t st) {
-    const long total = (long)b * H * W * C;
+    const long total = (long)b * H * W * (C / 8);
     maxpool_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(dout, idx, x, addin, dx, b, H, W, C, Ho, Wo, k, s); count_launch();
 }
 
@@ -657,28 +744,41 @@ void k_scale_rows(float* x, const float* scale, int b, long n, cudaStream_t st) 
 
 __global__ void im2col_rgb_bwd_kernel(const float* __restrict__ dimg, const float* __restrict__ img,
                                       bf16* __restrict__ col, int b, int H, int W, int Kp) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long total = (long)b * H * W * Kp;
-    if (i >= total) return;
-    const int k = i % Kp;
-    const long q = i / Kp;
+    // thread = one pixel: 27 live values (k = (r*3+s)*3 + o), one full 128-byte row written
+    const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)b * H * W;
+    if (q >= total) return;
     const int x = q % W, y = (q / W) % H, bi = q / ((long)W * H);
-    float v = 0.f;
-    if (k < 27) {
-        const int o = k % 3, s = (k / 3) % 3, r = k / 9;
-        // dx[q] = sum_{r,s,o} dv[q - (r-1, s-1), o] * W[o, c, r, s]
-        const int yy = y - (r - 1), xx = x - (s - 1);
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-            const long o_i = (((long)bi * 3 + o) * H + yy) * W + xx;
-            const float im = img[o_i];
-            v = dimg[o_i] * (1.f - im * im);
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            // dx[q] = sum_{r,s,o} dv[q - (r-1, s-1), o] * W[o, c, r, s]
+            const int yy = y - (r - 1), xx = x - (s - 1);
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+#pragma unroll
+                for (int o = 0; o < 3; ++o) {
+                    const long oi = (((long)bi * 3 + o) * H + yy) * W + xx;
+                    const float im = __ldg(img + oi);
+                    v[(r * 3 + s) * 3 + o] = __ldg(dimg + oi) * (1.f - im * im);
+                }
+            }
         }
     }
-    col[i] = f2b(v);
+    uint4* dst = reinterpret_cast<uint4*>(col + q * Kp);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        dst[j] = make_uint4(pk2(v[j * 8], v[j * 8 + 1]), pk2(v[j * 8 + 2], v[j * 8 + 3]), pk2(v[j * 8 + 4], v[j * 8 + 5]),
+                            pk2(v[j * 8 + 6], v[j * 8 + 7]));
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int j = 4; j < Kp / 8; ++j) dst[j] = z;
 }
 void k_im2col_rgb_bwd(const float* dimg, const float* img, bf16* col, int b, int H, int W, int Kp, cudaStream_t st) {
-    const long total = (long)b * H * W * Kp;
-    im2col_rgb_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(dimg, img, col, b, H, W, Kp); count_launch();
+    const long total = (long)b * H * W;
+    im2col_rgb_bwd_kernel<<<cdiv(total, 128), 128, 0, st>>>(dimg, img, col, b, H, W, Kp); count_launch();
 }
 
 // ---- VGG first layer helpers (3 input channels padded to Cp) --------------------------------

@@ -13,6 +13,7 @@ typedef __nv_bfloat16 bf16;
 // cond[b,256] = cat(z[b,zd], c[b,cd])
 void k_concat_cond(const float* z, const float* c, float* cond, int b, int zd, int cd, cudaStream_t st);
 // a[b, off+ch] = (1 + cond.Ws[ch]) * inv_std[ch] ; s = cond.Wo[ch] - mean[ch]*a   (conditional BNs)
+// Ws / Wo are stored TRANSPOSED: [cdim][C_cond]
 void k_cond_affine(const float* cond, const float* Ws, const float* Wo, const float* mean,
                    const float* inv_std, float* a, float* s, int b, int cdim, int C_cond, int stride,
                    cudaStream_t st);
@@ -20,6 +21,7 @@ void k_cond_affine(const float* cond, const float* Ws, const float* Wo, const fl
 void k_uncond_affine(const float* weight, const float* bias, const float* mean, const float* inv_std,
                      float* a, float* s, int b, int C_cond, int C_unc, int stride, cudaStream_t st);
 // h[b, j] = cond[b].W[j] + bias[j] ; raw = bf16(h) ; act = relu(a[b, j%C]*h + s[b, j%C])
+// W is stored TRANSPOSED: [cdim][J]
 void k_gen_z(const float* cond, const float* W, const float* bias, const float* a, const float* s,
              int aff_stride, bf16* raw, bf16* act, int b, int cdim, int J, int C, cudaStream_t st);
 // BN-affine gradient finalisation: from S0 = sum dpre, S1 = sum dpre*y to

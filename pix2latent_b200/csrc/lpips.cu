@@ -130,9 +130,9 @@ int Lpips::feature_dims(int H, int W, int* fh, int* fw) const {
     return 0;
 }
 
-static int pick_bn_l(int Cout, long m_tiles) {
+static int pick_bn_l(int Cout, long m_tiles, long K = 1 << 20) {
     const int cands[3] = {256, 128, 64};
-    for (int k = 0; k < 3; ++k)
+    for (int k = (K <= 1024 ? 1 : 0); k < 3; ++k)
         if (Cout % cands[k] == 0 && m_tiles * (Cout / cands[k]) >= num_sms()) return cands[k];
     for (int k = 2; k >= 0; --k)
         if (Cout % cands[k] == 0) return cands[k];

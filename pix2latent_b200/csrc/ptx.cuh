@@ -82,6 +82,27 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, ui
         : "memory");
 }
 
+// TMA stores (shared -> global), bulk-group completion
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// named barrier over the 128 epilogue threads (id 1; id 0 is __syncthreads)
+__device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- tcgen05
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
@@ -160,6 +181,19 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(1024 >> 4) << 32;             // stride byte offset = 1024 B
     d |= static_cast<uint64_t>(1) << 46;                     // descriptor version (sm_100)
     d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
+    return d;
+}
+
+// Same layout family with an arbitrary 8-row-group stride (SBO) and an optional base offset:
+// used by the halo kernel, whose operand rows live inside a larger swizzled patch.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(base_offset & 7) << 49;
+    d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
 

@@ -71,7 +71,7 @@ EXPORTED_SYMBOLS = [
     "p2l_lpips_destroy", "p2l_target_create", "p2l_target_destroy", "p2l_loss_forward",
     "p2l_loss_backward", "p2l_lpips_flops", "p2l_lpips_launches", "p2l_biggan_step",
     "p2l_profile_enable", "p2l_profile_read",
-    "p2l_debug_conv",
+    "p2l_debug_conv", "p2l_debug_set_option", "p2l_debug_get_option", "p2l_debug_profile_get",
 ]
 
 _ctx = {}
