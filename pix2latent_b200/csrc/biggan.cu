@@ -40,7 +40,7 @@ struct BigGANPlan {
     __nv_bfloat16* col_rgb = nullptr;
     float* img = nullptr;  // internal copy target when the caller passes none
     // gradient ping-pong
-    __nv_bfloat16 *dhA = nullptr, *dhB = nullptr, *g1 = nullptr, *g2 = nullptr, *g3 = nullptr;
+    __nv_bfloat16 *dhA = nullptr, *dhB = nullptr, *g1 = nullptr, *g2 = nullptr, *g3 = nullptr, *dh_pool = nullptr;
     double flops_fwd = 0, flops_bwd = 0;
     int launches_fwd = 0, launches_bwd = 0;
     bool forward_done = false;
@@ -312,6 +312,7 @@ BigGANPlan* BigGAN::plan(int b) {
     P.g1 = ar.alloc<bf>(max_g);
     P.g2 = ar.alloc<bf>(max_g);
     P.g3 = ar.alloc<bf>(max_g);
+    P.dh_pool = ar.alloc<bf>(max_dh / 4 + 64);  // 2x2-pooled skip gradient of up blocks
     const int R = H_out;
     P.col_rgb = ar.alloc<bf>((size_t)b * R * R * 64);
     P.img = ar.alloc<float>((size_t)b * 3 * R * R);
@@ -359,7 +360,9 @@ BigGANPlan* BigGAN::plan(int b) {
             ConvGemmParams& e = o.d.epi;
             e.bias = bl.bias[3];
             e.resid = B.in_raw; e.resid_C = bl.in; e.resid_shift = bl.up ? 1 : 0;
-            e.raw = B.out_raw; e.raw_C = bl.out;
+            // the raw (pre-BN) output feeds the next block's skip / the attention; after the last block
+            // nothing reads it
+            if (i + 1 < nL) { e.raw = B.out_raw; e.raw_C = bl.out; }
             if (!attn_next) {
                 e.aff_a = P.a + bns[next_bn].off; e.aff_s = P.s + bns[next_bn].off; e.aff_stride = C_all; e.relu = 1;
                 e.act = B.out_act; e.act_C = bl.out;
@@ -407,7 +410,8 @@ BigGANPlan* BigGAN::plan(int b) {
             e.saved = B.in_act; e.saved_C = bl.in;
             e.stat0 = P.S0 + bns[bl.bn[0]].off; e.stat1 = P.S1 + bns[bl.bn[0]].off; e.stat_stride = C_all;
             e.aff_a = P.a + bns[bl.bn[0]].off; e.aff_stride = C_all;
-            e.addin = dh_out; e.addin_C = bl.out; e.addin_climit = bl.out; e.addin_pool = bl.up ? 1 : 0;
+            // skip gradient: dh_out itself, or (up block) its 2x2-pooled copy written by k_pool2x2_sum
+            e.addin = bl.up ? P.dh_pool : dh_out; e.addin_C = bl.out; e.addin_climit = bl.out; e.addin_pool = 0;
             e.dx = dh_in; e.dx_C = bl.in;
             if (i == 0) { e.dx_f32 = P.dh0; e.dx_f32_C = bl.in; }
             if (build(&B.d[0], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
@@ -601,6 +605,10 @@ int BigGAN::backward(int b, const float* dimg, float* dz, float* dc, cudaStream_
             const BN& bn1 = bns[bl.bn[1]];
             k_pool_bnrelu_bwd(P.g3, B.t1_lo, P.a + bn1.off, C_all, P.S0 + bn1.off, P.S1 + bn1.off, C_all, P.g1, b, bl.Hin,
                               bl.Hin, bl.mid, st);
+        }
+        if (bl.up) {
+            __nv_bfloat16* dh_out = ((nL - 1 - i) % 2 == 0) ? P.dhA : P.dhB;
+            k_pool2x2_sum(dh_out, bl.out, P.dh_pool, b, bl.Hin, bl.Hin, bl.out, st);
         }
         if (conv_op_launch(B.d[0], st)) return -1;
         if (attn.C && i == cfg.attention_pos) {

@@ -156,7 +156,7 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     int nb = kBM / (tw * th);
     // halo patches: always for the 3-channel rgb head (N = 16 tile: the layer is pure A traffic),
     // optional ("halo" option) elsewhere — measured neutral for N >= 64 (profiles/)
-    const int halo_p = (d.BN == 16) ? 10 : g_halo;
+    const int halo_p = (d.BN == 16) ? 0 : g_halo;  // rgb head: N=16 MMAs are issue-bound; per-tap path + 2 CTAs/SM is faster
     const bool halo = halo_p != 0 && d.kh == 3 && d.kw == 3 && d.pad_h == 1 && d.pad_w == 1 && d.B_batch == 0 &&
                       d.H >= 12 && d.W >= 8;
     if (halo) { tw = 8; th = 16; nb = 1; }
@@ -197,7 +197,8 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     const long Ktot = (long)d.kh * d.kw * d.Cin;
     const bool any_out = d.epi.raw || d.epi.act || d.epi.dx;
     op->tma_out = (g_tma_out && !halo && any_out && (d.BN == 64 || d.BN == 128) && d.Cout % 64 == 0 && Ktot <= 512 &&
-                   !d.epi.img_nchw) ? 1 : 0;
+                   !d.epi.img_nchw && !(d.epi.addin && d.epi.addin_pool) && (d.epi.resid_shift == 0 || (tw >= 2 && th >= 2)) &&
+                   (!d.epi.addin || d.epi.addin_climit % 64 == 0)) ? 1 : 0;
     if (op->tma_out) {
         auto map4 = [&](CUtensorMap* m, const void* ptr, int C, int Hh, int Ww) -> int {
             cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)Ww, (cuuint64_t)Hh, (cuuint64_t)d.NI};
@@ -205,6 +206,17 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
             cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
             return encode_bf16(m, ptr, 4, dims, str, box);
         };
+        // epilogue inputs: [4] = saved activation (bwd) / residual skip (fwd), [5] = skip gradient (bwd)
+        auto map_in = [&](CUtensorMap* m, const void* ptr, int C, int Cext, int sh) -> int {
+            const int Hh = d.H >> sh, Ww = d.W >> sh;
+            cuuint64_t dims[4] = {(cuuint64_t)Cext, (cuuint64_t)Ww, (cuuint64_t)Hh, (cuuint64_t)d.NI};
+            cuuint64_t str[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ww * C * 2, (cuuint64_t)Hh * Ww * C * 2};
+            cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(tw >> sh), (cuuint32_t)(th >> sh), (cuuint32_t)nb};
+            return encode_bf16(m, ptr, 4, dims, str, box);
+        };
+        if (d.mode == EPI_FWD && d.epi.resid && map_in(&op->tmO.m[4], d.epi.resid, d.epi.resid_C, d.Cout, d.epi.resid_shift)) return -1;
+        if (d.mode == EPI_BWD && d.epi.saved && map_in(&op->tmO.m[4], d.epi.saved, d.epi.saved_C, d.Cout, 0)) return -1;
+        if (d.mode == EPI_BWD && d.epi.addin && map_in(&op->tmO.m[5], d.epi.addin, d.epi.addin_C, d.epi.addin_climit, 0)) return -1;
         const void* o0 = d.mode == EPI_FWD ? (const void*)d.epi.raw : (const void*)d.epi.dx;
         const int o0C = d.mode == EPI_FWD ? d.epi.raw_C : d.epi.dx_C;
         if (o0 && map4(&op->tmO.m[0], o0, o0C, d.H, d.W)) return -1;
@@ -228,7 +240,7 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     op->mode = d.mode;
     op->halo = halo ? halo_p : 0;
     const long total = (long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
-    const long slots = (long)num_sms() * ((halo || d.BN > 128) ? 1 : P2L_OCC);  // same occupancy with or without TMA_OUT
+    const long slots = (long)num_sms() * ((halo || d.BN > 128 || op->tma_out) ? 1 : P2L_OCC);
     op->grid = (int)(total < slots ? total : slots);
     op->flops = 2.0 * d.NI * d.H * d.W * (double)d.Cout * d.kh * d.kw * d.Cin;
     return 0;
@@ -259,7 +271,7 @@ static int launch_t(const ConvOp& op, cudaStream_t stream) {
                                op.p.taps_h * op.p.taps_w * op.p.cin_chunks * kBK});
         cudaEventRecord(e0, stream);
     }
-    conv_gemm_kernel<BN, MODE, TMA_OUT><<<op.grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(op.tmA, op.tmB, op.tmO, op.p);
+    conv_gemm_kernel<BN, MODE, TMA_OUT><<<op.grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(op.tmA, op.tmB, op.tmO, op.p);
     if (g_prof) cudaEventRecord(e1, stream);
     count_launch();
     P2L_CUDA_CHECK(cudaGetLastError());

@@ -33,9 +33,6 @@ constexpr int kATileBytes = kBM * kBK * 2;
 #ifndef P2L_OCC
 #define P2L_OCC 2
 #endif
-#ifndef P2L_EPI_STAGED
-#define P2L_EPI_STAGED 0  // 1: per-warp swizzled smem staging (measured slower: the epilogue is latency-bound)
-#endif
 
 enum { EPI_FWD = 0, EPI_BWD = 1 };
 
@@ -94,14 +91,19 @@ struct GemmCfg {
     // Two co-resident CTAs per SM for BN <= 128: the epilogue (global loads/stores issued by only
     // four warps) is latency-bound, a second CTA doubles the bytes in flight and lets one CTA's
     // epilogue overlap the other's main loop even on single-tile launches.
-    static constexpr int kOcc = (BN <= 128) ? P2L_OCC : 1;
-    // TMA_OUT: epilogue outputs leave through two 16 KB swizzled slabs (128 rows x 64 channels) and
-    // cp.async.bulk.tensor stores instead of per-thread st.global
-    static constexpr int kOutBytes = TMA_OUT ? 2 * kATileBytes : 0;
+    // TMA_OUT ("TMA I/O" variant, used where the epilogue dominates): one CTA per SM with a fifth
+    // role, the epilogue-input loader. Outputs leave through two 16 KB swizzled slabs (128 rows x 64
+    // channels) and cp.async.bulk.tensor stores; the per-pixel epilogue inputs (saved activation,
+    // residual skip, skip gradient) are prefetched by TMA into a ring of kInSlots slabs, so no
+    // thread ever waits on a global load.
+    static constexpr int kOcc = TMA_OUT ? 1 : ((BN <= 128) ? P2L_OCC : 1);
+    static constexpr int kInSlots = TMA_OUT ? 4 : 0;
+    static constexpr int kOutBytes = TMA_OUT ? (4 + kInSlots) * kATileBytes : 0;  // 2 x {raw, act} + inputs
+    static constexpr int kThreads = TMA_OUT ? kGemmThreads + 32 : kGemmThreads;
     static constexpr int kMaxStages = ((kOcc == 2 ? 104 : 208) * 1024 - kOutBytes) / kStageBytes;
     static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
     static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/ + (P2L_EPI_STAGED ? 4 * 4096 : 0);
+    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 6 * BN * 4 /*coefficient tables*/;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
 };
 
@@ -121,126 +123,6 @@ __device__ __forceinline__ float colsum_group(float (&v)[G], int lane) {
     return v[0];
 }
 
-// ----------------------------------------------------------------------------- epilogue I/O
-constexpr int kStageSlabBytes = 4096;  // per epilogue warp: 32 rows x 128 B
-
-// tile-local row (0..127) -> pixel of the output grid
-struct TileMap {
-    int w0, h0, n0, tw_mask, th_mask, ltw, lthw, W, H, NI;
-    __device__ __forceinline__ bool pix(int r, int& n, int& h, int& w) const {
-        w = w0 + (r & tw_mask);
-        h = h0 + ((r >> ltw) & th_mask);
-        n = n0 + (r >> lthw);
-        return (w < W) && (h < H) && (n < NI);
-    }
-};
-// where a row lives in the tensor being read/written:
-//   plain: (n,h,w) on an Hs x Ws grid; shift: (h>>shift, w>>shift); up: (2h+dy, 2w+dx) on (2H,2W)
-struct SrcMap {
-    int Hs, Ws, shift, up, dy, dx;
-    __device__ __forceinline__ long index(int n, int h, int w) const {
-        const int hh = up ? 2 * h + dy : (h >> shift);
-        const int ww = up ? 2 * w + dx : (w >> shift);
-        return (static_cast<long>(n) * Hs + hh) * Ws + ww;
-    }
-};
-
-// bf16 slab: 32 rows x 64 B, 16-byte chunk j of row r stored at slot j ^ ((r >> 1) & 3)
-__device__ __forceinline__ uint32_t slab64_off(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
-// fp32 slab: 32 rows x 128 B, chunk j of row r at slot j ^ (r & 7)
-__device__ __forceinline__ uint32_t slab128_off(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
-
-// v[32] += bf16 tensor rows (coalesced global read through the slab)
-__device__ __forceinline__ void coop_load_add(uint8_t* stg, int quad, int lane, const TileMap& tm, const SrcMap& sm,
-                                              const __nv_bfloat16* src, int C, int cbase, float (&v)[32]) {
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int r = it * 8 + (lane >> 2), j = lane & 3;
-        int n, h, w;
-        uint4 t = make_uint4(0, 0, 0, 0);
-        if (tm.pix(quad * 32 + r, n, h, w)) t = __ldg(reinterpret_cast<const uint4*>(src + sm.index(n, h, w) * C + cbase) + j);
-        *reinterpret_cast<uint4*>(stg + slab64_off(r, j)) = t;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const uint4 t = *reinterpret_cast<const uint4*>(stg + slab64_off(lane, q));
-        v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
-        v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
-        v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
-        v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
-    }
-    __syncwarp();
-}
-
-__device__ __forceinline__ void slab_put_bf16(uint8_t* stg, int lane, const float (&v)[32]) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        *reinterpret_cast<uint4*>(stg + slab64_off(lane, q)) =
-            make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                       pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
-    }
-    __syncwarp();
-}
-
-// bf16(v) rows -> dst (coalesced global write through the slab)
-__device__ __forceinline__ void coop_store_bf16(uint8_t* stg, int quad, int lane, const TileMap& tm, const SrcMap& dm,
-                                                __nv_bfloat16* dst, int C, int cbase, const float (&v)[32]) {
-    slab_put_bf16(stg, lane, v);
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int r = it * 8 + (lane >> 2), j = lane & 3;
-        int n, h, w;
-        if (tm.pix(quad * 32 + r, n, h, w)) {
-            const uint4 t = *reinterpret_cast<const uint4*>(stg + slab64_off(r, j));
-            *(reinterpret_cast<uint4*>(dst + dm.index(n, h, w) * C + cbase) + j) = t;
-        }
-    }
-    __syncwarp();
-}
-
-// nearest x2: every row is written to its 2x2 block of the (2H, 2W) map, plus the low-res copy
-__device__ __forceinline__ void coop_store_bf16_up(uint8_t* stg, int quad, int lane, const TileMap& tm,
-                                                   __nv_bfloat16* dst_up, __nv_bfloat16* dst_lo, int C, int cbase,
-                                                   const float (&v)[32]) {
-    slab_put_bf16(stg, lane, v);
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int r = it * 8 + (lane >> 2), j = lane & 3;
-        int n, h, w;
-        if (tm.pix(quad * 32 + r, n, h, w)) {
-            const uint4 t = *reinterpret_cast<const uint4*>(stg + slab64_off(r, j));
-            const long W2 = 2L * tm.W;
-            const long base = (static_cast<long>(n) * 2 * tm.H + 2 * h) * W2 + 2 * w;
-            *(reinterpret_cast<uint4*>(dst_up + base * C + cbase) + j) = t;
-            *(reinterpret_cast<uint4*>(dst_up + (base + 1) * C + cbase) + j) = t;
-            *(reinterpret_cast<uint4*>(dst_up + (base + W2) * C + cbase) + j) = t;
-            *(reinterpret_cast<uint4*>(dst_up + (base + W2 + 1) * C + cbase) + j) = t;
-            if (dst_lo) *(reinterpret_cast<uint4*>(dst_lo + ((static_cast<long>(n) * tm.H + h) * tm.W + w) * C + cbase) + j) = t;
-        }
-    }
-    __syncwarp();
-}
-
-__device__ __forceinline__ void coop_store_f32(uint8_t* stg, int quad, int lane, const TileMap& tm, float* dst, int C,
-                                               int cbase, const float (&v)[32]) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        *reinterpret_cast<float4*>(stg + slab128_off(lane, q)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + (lane >> 3), j = lane & 7;
-        int n, h, w;
-        if (tm.pix(quad * 32 + r, n, h, w)) {
-            const float4 t = *reinterpret_cast<const float4*>(stg + slab128_off(r, j));
-            *(reinterpret_cast<float4*>(dst + ((static_cast<long>(n) * tm.H + h) * tm.W + w) * C + cbase) + j) = t;
-        }
-    }
-    __syncwarp();
-}
-
 // Row `row` (0..127) of a 128-row x 128-byte slab in the TMA 128B-swizzle layout: write 32 bf16
 // (pieces piece0 .. piece0+3 of the row's eight 16-byte pieces).
 __device__ __forceinline__ void slab_put_row(uint8_t* buf, int row, int piece0, const float (&v)[32]) {
@@ -252,14 +134,39 @@ __device__ __forceinline__ void slab_put_row(uint8_t* buf, int row, int piece0, 
     }
 }
 __device__ __forceinline__ void slab_put_row(uint8_t*, int, int, const float (&)[16]) {}
+// v[32] += the 32 bf16 of row `row`, pieces piece0 .. piece0+3, of a swizzled 128-byte-row slab
+__device__ __forceinline__ void slab_add_row(const uint8_t* buf, int row, int piece0, float (&v)[32]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 t = *reinterpret_cast<const uint4*>(buf + row * 128 + (((piece0 + q) ^ (row & 7)) << 4));
+        v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
+        v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
+        v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
+        v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
+    }
+}
+__device__ __forceinline__ void slab_add_row(const uint8_t*, int, int, float (&)[16]) {}
 
 // Direct epilogue: every thread reads / writes the global rows of its own accumulator row.
 template <int BN, int MODE, int CH, bool TMA_OUT>
 __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, const CUtensorMap* tmo, uint8_t* obuf,
-                                                     uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
-                                                     int total_tiles, int warp, int lane) {
-    // TMA_OUT: tmo[0] = raw / dx, tmo[1] = act, tmo[2] = act on the 2x grid (5-D view), tmo[3] = act_lo
+                                                     uint64_t* in_full, uint64_t* in_empty, uint64_t* tfull_bar,
+                                                     uint64_t* tempty_bar, uint32_t tmem_base, int total_tiles, int warp,
+                                                     int lane, float* ctab) {
+    // ctab: 2 x 3 x BN floats in shared memory — per-tile copies of bias / affine gain / affine offset
+    // (they depend on (image, channel) only; staging them once per tile, before the accumulator is
+    // ready, takes their global-load latency off the per-chunk critical path)
+    const bool use_tab = (p.nb == 1);
+    // TMA_OUT: tmo[0] = raw / dx, tmo[1] = act, tmo[2] = act on the 2x grid (5-D view), tmo[3] = act_lo;
+    // obuf = [2 output slabs][kInSlots input slabs]; input slabs arrive through in_full / in_empty
     const bool storer = TMA_OUT && (warp & 3) == 0 && lane == 0;
+    constexpr int NIN = GemmCfg<BN, TMA_OUT>::kInSlots;
+    uint8_t* inbuf = obuf + 4 * kATileBytes;
+    uint8_t* obase = obuf;        // output slab pair in use (two pairs alternate per 64-channel slab)
+    int slab_no = 0;
+    int in_cnt = 0;               // consumed input slabs (same order as the loader warp issues them)
+    int slot0 = 0, slot1 = 0;     // slots of the current 64-channel slab
+    bool has0 = false, has1 = false;
     // ------------------------------------------------------------------ epilogue warps
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
@@ -281,6 +188,19 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
         const bool valid = (w < p.W) && (h < p.H) && (n < p.NI);
         const long pix = (static_cast<long>(n) * p.H + h) * p.W + w;
 
+        float* tab = ctab + (it & 1) * 3 * BN;
+        if (use_tab) {
+            const int et = (warp & 3) * 32 + lane;  // 0..127
+            const int nn = min(tni * p.nb, p.NI - 1);
+            for (int j = et; j < BN; j += 128) {
+                const int ch = n_tile * BN + j;
+                const bool in = ch < p.Cout;
+                tab[j] = (MODE == EPI_FWD && p.bias && in) ? __ldg(p.bias + ch) : 0.f;
+                tab[BN + j] = (p.aff_a && in) ? __ldg(p.aff_a + static_cast<long>(nn) * p.aff_stride + ch) : 1.f;
+                tab[2 * BN + j] = (MODE == EPI_FWD && p.aff_s && in) ? __ldg(p.aff_s + static_cast<long>(nn) * p.aff_stride + ch) : 0.f;
+            }
+            bar_epilogue();  // table[it & 1] was last read two tiles ago: every warp has passed the previous barrier since
+        }
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
@@ -293,8 +213,23 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 if ((c & 63) == 0) {
                     // both output slabs are about to be overwritten: their previous stores must have
                     // finished READING shared memory
-                    if (storer) bulk_wait_read0();
+                    // the pair written two slabs ago must have been READ by its bulk stores
+                    obuf = obase + (slab_no & 1) * 2 * kATileBytes;
+                    ++slab_no;
+                    if (storer) bulk_wait_read1();
                     bar_epilogue();
+                    has0 = (MODE == EPI_FWD) ? (p.resid != nullptr) : (p.saved != nullptr);
+                    has1 = (MODE == EPI_BWD) && p.addin != nullptr && cbase < p.addin_climit;
+                    if (has0) {
+                        slot0 = in_cnt % NIN;
+                        mbar_wait(&in_full[slot0], (in_cnt / NIN) & 1);
+                        ++in_cnt;
+                    }
+                    if (has1) {
+                        slot1 = in_cnt % NIN;
+                        mbar_wait(&in_full[slot1], (in_cnt / NIN) & 1);
+                        ++in_cnt;
+                    }
                 }
             }
             float v[CH];
@@ -310,13 +245,36 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 
             if constexpr (MODE == EPI_FWD) {
                 // ---- v = alpha*acc + bias (+ skip)
+                if (use_tab) {
 #pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    float b = 0.f;
-                    if (p.bias && (full_chunk || cbase + j < p.Cout)) b = __ldg(p.bias + cbase + j);
-                    v[j] = alpha * v[j] + b;
+                    for (int q = 0; q < CH / 4; ++q) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(tab + c + q * 4);
+                        v[q * 4 + 0] = fmaf(alpha, v[q * 4 + 0], b4.x); v[q * 4 + 1] = fmaf(alpha, v[q * 4 + 1], b4.y);
+                        v[q * 4 + 2] = fmaf(alpha, v[q * 4 + 2], b4.z); v[q * 4 + 3] = fmaf(alpha, v[q * 4 + 3], b4.w);
+                    }
+                } else if (p.bias && full_chunk) {
+#pragma unroll
+                    for (int q = 0; q < CH / 4; ++q) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase) + q);
+                        v[q * 4 + 0] = fmaf(alpha, v[q * 4 + 0], b4.x); v[q * 4 + 1] = fmaf(alpha, v[q * 4 + 1], b4.y);
+                        v[q * 4 + 2] = fmaf(alpha, v[q * 4 + 2], b4.z); v[q * 4 + 3] = fmaf(alpha, v[q * 4 + 3], b4.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        float b = 0.f;
+                        if (p.bias && cbase + j < p.Cout) b = __ldg(p.bias + cbase + j);
+                        v[j] = alpha * v[j] + b;
+                    }
                 }
-                if (p.resid && valid) {
+                if constexpr (TMA_OUT) {
+                    if (has0) {
+                        // residual skip from its prefetched slab (low-res box when the skip is upsampled)
+                        const int sh = p.resid_shift;
+                        const int rr = ((ni * (p.th >> sh)) + (hi >> sh)) * (p.tw >> sh) + (wi >> sh);
+                        slab_add_row(inbuf + slot0 * kATileBytes, rr, (c & 32) >> 3, v);
+                    }
+                } else if (p.resid && valid) {
                     const int Hs = p.H >> p.resid_shift, Ws = p.W >> p.resid_shift;
                     const long rp = (static_cast<long>(n) * Hs + (h >> p.resid_shift)) * Ws + (w >> p.resid_shift);
                     const uint4* src = reinterpret_cast<const uint4*>(p.resid + rp * p.resid_C + cbase);
@@ -355,7 +313,17 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     }
                 }
                 if (p.act) {
-                    if (p.aff_a) {
+                    if (p.aff_a && use_tab) {
+#pragma unroll
+                        for (int q = 0; q < CH / 4; ++q) {
+                            const float4 a4 = *reinterpret_cast<const float4*>(tab + BN + c + q * 4);
+                            const float4 s4 = *reinterpret_cast<const float4*>(tab + 2 * BN + c + q * 4);
+                            v[q * 4 + 0] = fmaf(a4.x, v[q * 4 + 0], s4.x);
+                            v[q * 4 + 1] = fmaf(a4.y, v[q * 4 + 1], s4.y);
+                            v[q * 4 + 2] = fmaf(a4.z, v[q * 4 + 2], s4.z);
+                            v[q * 4 + 3] = fmaf(a4.w, v[q * 4 + 3], s4.w);
+                        }
+                    } else if (p.aff_a) {
                         const int nn = valid ? n : 0;
                         const float* pa = p.aff_a + static_cast<long>(nn) * p.aff_stride + cbase;
                         const float* ps = p.aff_s + static_cast<long>(nn) * p.aff_stride + cbase;
@@ -411,7 +379,11 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 float y[CH];
 #pragma unroll
                 for (int j = 0; j < CH; ++j) { y[j] = 0.f; v[j] *= alpha; }
-                if (p.saved) {
+                if (TMA_OUT && p.saved) {
+                    slab_add_row(inbuf + slot0 * kATileBytes, row, (c & 32) >> 3, y);  // y starts at 0
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) v[j] = (valid && y[j] > 0.f) ? v[j] : 0.f;
+                } else if (p.saved) {
                     if (valid) {
                         const uint4* src = reinterpret_cast<const uint4*>(p.saved + pix * p.saved_C + cbase);
 #pragma unroll
@@ -467,7 +439,13 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                         }
                     }
                 }
-                if (p.aff_a) {
+                if (p.aff_a && use_tab) {
+#pragma unroll
+                    for (int q = 0; q < CH / 4; ++q) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(tab + BN + c + q * 4);
+                        v[q * 4 + 0] *= a4.x; v[q * 4 + 1] *= a4.y; v[q * 4 + 2] *= a4.z; v[q * 4 + 3] *= a4.w;
+                    }
+                } else if (p.aff_a) {
                     const int nn = valid ? n : 0;
                     const float* pa = p.aff_a + static_cast<long>(nn) * p.aff_stride + cbase;
 #pragma unroll
@@ -476,7 +454,9 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                         v[q * 4 + 0] *= a4.x; v[q * 4 + 1] *= a4.y; v[q * 4 + 2] *= a4.z; v[q * 4 + 3] *= a4.w;
                     }
                 }
-                if (p.addin && valid && cbase < p.addin_climit) {
+                if constexpr (TMA_OUT) {
+                    if (has1) slab_add_row(inbuf + slot1 * kATileBytes, row, (c & 32) >> 3, v);
+                } else if (p.addin && valid && cbase < p.addin_climit) {
                     if (!p.addin_pool) {
                         const uint4* src = reinterpret_cast<const uint4*>(p.addin + pix * p.addin_C + cbase);
 #pragma unroll
@@ -528,6 +508,13 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
             }
             if constexpr (TMA_OUT) {
                 if (c & 32) {  // a 64-channel slab is complete: hand it to the TMA store engine
+                    if (has0 || has1) {
+                        __syncwarp();  // every lane of this warp has read its rows of the input slabs
+                        if (lane == 0) {
+                            if (has0) mbar_arrive(&in_empty[slot0]);
+                            if (has1) mbar_arrive(&in_empty[slot1]);
+                        }
+                    }
                     fence_async_smem();
                     bar_epilogue();
                     if (storer) {
@@ -561,200 +548,10 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
     if (storer) bulk_wait0();  // shared memory must outlive the last bulk store's reads
 }
 
-// Epilogue of both kernels: runs on the 4 epilogue warps (warp & 3 = TMEM lane quadrant).
-template <int BN, int MODE, int CH>
-__device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* stg_base, uint64_t* tfull_bar,
-                                              uint64_t* tempty_bar, uint32_t tmem_base, int total_tiles, int warp,
-                                              int lane) {
-    // ------------------------------------------------------------------ epilogue warps
-    // TMEM hands every thread one accumulator ROW (pixel). Writing rows straight to global
-    // memory makes each warp-wide 16-byte store touch 32 different 128-byte lines. All bulk
-    // epilogue traffic therefore goes through a per-warp, XOR-swizzled shared-memory slab
-    // (32 rows x 64 B for bf16, x 128 B for fp32): threads exchange so that every warp-wide
-    // access covers 8 (or 4) full 64-byte (128-byte) row segments.
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;
-    const int rows_per_img = p.tw * p.th;
-    uint8_t* stg = stg_base + quad * kStageSlabBytes;
-    float alpha = p.alpha;
-    if (p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-        TileMap tm;
-        tm.w0 = (m_tile % p.tiles_w) * p.tw;
-        tm.h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
-        const int tni = m_tile / (p.tiles_w * p.tiles_h);
-        tm.n0 = tni * p.nb;
-        tm.tw_mask = p.tw - 1; tm.th_mask = p.th - 1; tm.ltw = p.ltw; tm.lthw = p.ltw + p.lth;
-        tm.W = p.W; tm.H = p.H; tm.NI = p.NI;
-        int n, h, w;
-        const bool valid = tm.pix(row, n, h, w);
-        const long pix = (static_cast<long>(n) * p.H + h) * p.W + w;
-
-        mbar_wait(&tfull_bar[as], aphase);
-        tc_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-
-#pragma unroll 1
-        for (int c = 0; c < BN; c += CH) {
-            const int cbase = n_tile * BN + c;
-            if (cbase >= p.Cout) break;  // warp-uniform
-            float v[CH];
-            {
-                uint32_t u[CH];
-                if constexpr (CH == 32) tmem_ld32(t_addr + c, u);
-                else tmem_ld16(t_addr + c, u);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < CH; ++j) v[j] = alpha * __uint_as_float(u[j]);
-            }
-            const bool full_chunk = (cbase + CH <= p.Cout);
-
-            if constexpr (MODE == EPI_FWD) {
-                if (p.bias) {
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) {
-                        if (full_chunk || cbase + j < p.Cout) v[j] += __ldg(p.bias + cbase + j);
-                    }
-                }
-                if constexpr (CH == 32) {
-                    if (p.resid) {
-                        SrcMap sm{p.H >> p.resid_shift, p.W >> p.resid_shift, p.resid_shift, 0, 0, 0};
-                        coop_load_add(stg, quad, lane, tm, sm, p.resid, p.resid_C, cbase, v);
-                    }
-                }
-                if (p.img_nchw) {
-                    if (valid) {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) {
-                            if (cbase + j < p.Cout) {
-                                p.img_nchw[((static_cast<long>(n) * p.Cout + cbase + j) * p.H + h) * p.W + w] = tanhf(v[j]);
-                            }
-                        }
-                    }
-                }
-                if constexpr (CH == 32) {
-                    if (p.raw_f32) coop_store_f32(stg, quad, lane, tm, p.raw_f32, p.raw_f32_C, cbase, v);
-                    if (p.raw) {
-                        SrcMap dm{p.H, p.W, 0, 0, 0, 0};
-                        coop_store_bf16(stg, quad, lane, tm, dm, p.raw, p.raw_C, cbase, v);
-                    }
-                    if (p.act) {
-                        if (p.aff_a) {
-                            const int nn = valid ? n : 0;
-                            const float* pa = p.aff_a + static_cast<long>(nn) * p.aff_stride + cbase;
-                            const float* ps = p.aff_s + static_cast<long>(nn) * p.aff_stride + cbase;
-#pragma unroll
-                            for (int q = 0; q < CH / 4; ++q) {
-                                const float4 a4 = __ldg(reinterpret_cast<const float4*>(pa) + q);
-                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(ps) + q);
-                                v[q * 4 + 0] = fmaf(a4.x, v[q * 4 + 0], s4.x);
-                                v[q * 4 + 1] = fmaf(a4.y, v[q * 4 + 1], s4.y);
-                                v[q * 4 + 2] = fmaf(a4.z, v[q * 4 + 2], s4.z);
-                                v[q * 4 + 3] = fmaf(a4.w, v[q * 4 + 3], s4.w);
-                            }
-                        }
-                        if (p.relu) {
-#pragma unroll
-                            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
-                        }
-                        if (!p.act_up) {
-                            SrcMap dm{p.H, p.W, 0, 0, 0, 0};
-                            coop_store_bf16(stg, quad, lane, tm, dm, p.act, p.act_C, cbase, v);
-                        } else {
-                            coop_store_bf16_up(stg, quad, lane, tm, p.act, p.act_lo, p.act_C, cbase, v);
-                        }
-                    }
-                }
-            } else {
-                // ---------------------------------------------------------- backward
-                if constexpr (CH == 32) {
-                    float y[CH];
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) y[j] = 0.f;
-                    if (p.saved) {
-                        SrcMap sm{p.H, p.W, 0, 0, 0, 0};
-                        coop_load_add(stg, quad, lane, tm, sm, p.saved, p.saved_C, cbase, y);
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) v[j] = (y[j] > 0.f) ? v[j] : 0.f;
-                    }
-                    if (!valid) {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) v[j] = 0.f;
-                    }
-                    if (p.stat0) {
-                        // BN-affine gradients: reduce over the pixels (lanes) of one image.
-                        if (rows_per_img >= 32) {
-                            float t0[32], t1[32];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) { t0[j] = v[j]; t1[j] = v[j] * y[j]; }
-                            const float s0 = colsum_group<32>(t0, lane);
-                            const float s1 = colsum_group<32>(t1, lane);
-                            const int nn = tni * p.nb + (quad * 32) / rows_per_img;
-                            if (nn < p.NI) {
-                                atomicAdd(p.stat0 + static_cast<long>(nn) * p.stat_stride + cbase + lane, s0);
-                                atomicAdd(p.stat1 + static_cast<long>(nn) * p.stat_stride + cbase + lane, s1);
-                            }
-                        } else {
-                            // 16 pixels per image (4x4 maps): half-warp groups.
-#pragma unroll
-                            for (int half = 0; half < 2; ++half) {
-                                float t0[16], t1[16];
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) { t0[j] = v[half * 16 + j]; t1[j] = v[half * 16 + j] * y[half * 16 + j]; }
-                                const float s0 = colsum_group<16>(t0, lane);
-                                const float s1 = colsum_group<16>(t1, lane);
-                                const int nn = tni * p.nb + (quad * 32 + (lane & 16)) / rows_per_img;
-                                if (nn < p.NI) {
-                                    atomicAdd(p.stat0 + static_cast<long>(nn) * p.stat_stride + cbase + half * 16 + (lane & 15), s0);
-                                    atomicAdd(p.stat1 + static_cast<long>(nn) * p.stat_stride + cbase + half * 16 + (lane & 15), s1);
-                                }
-                            }
-                        }
-                    }
-                    if (p.aff_a) {
-                        const int nn = valid ? n : 0;
-                        const float* pa = p.aff_a + static_cast<long>(nn) * p.aff_stride + cbase;
-#pragma unroll
-                        for (int q = 0; q < CH / 4; ++q) {
-                            const float4 a4 = __ldg(reinterpret_cast<const float4*>(pa) + q);
-                            v[q * 4 + 0] *= a4.x; v[q * 4 + 1] *= a4.y; v[q * 4 + 2] *= a4.z; v[q * 4 + 3] *= a4.w;
-                        }
-                    }
-                    if (p.addin && cbase < p.addin_climit) {
-                        if (!p.addin_pool) {
-                            SrcMap sm{p.H, p.W, 0, 0, 0, 0};
-                            coop_load_add(stg, quad, lane, tm, sm, p.addin, p.addin_C, cbase, v);
-                        } else {
-#pragma unroll 1
-                            for (int d = 0; d < 4; ++d) {
-                                SrcMap sm{2 * p.H, 2 * p.W, 0, 1, d >> 1, d & 1};
-                                coop_load_add(stg, quad, lane, tm, sm, p.addin, p.addin_C, cbase, v);
-                            }
-                        }
-                    }
-                    if (p.dx) {
-                        SrcMap dm{p.H, p.W, 0, 0, 0, 0};
-                        coop_store_bf16(stg, quad, lane, tm, dm, p.dx, p.dx_C, cbase, v);
-                    }
-                    if (p.dx_f32) coop_store_f32(stg, quad, lane, tm, p.dx_f32, p.dx_f32_C, cbase, v);
-                }
-            }
-        }
-        // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
-    }
-}
-
-struct OutMaps { CUtensorMap m[4]; };
+struct OutMaps { CUtensorMap m[6]; };  // [0..3] epilogue outputs, [4..5] epilogue inputs
 
 template <int BN, int MODE, bool TMA_OUT>
-__global__ void __launch_bounds__(kGemmThreads, GemmCfg<BN, TMA_OUT>::kOcc)
+__global__ void __launch_bounds__(GemmCfg<BN, TMA_OUT>::kThreads, GemmCfg<BN, TMA_OUT>::kOcc)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ OutMaps tmO, const ConvGemmParams p) {
     using Cfg = GemmCfg<BN, TMA_OUT>;
@@ -769,7 +566,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* empty_bar = bars + S;
     uint64_t* tfull_bar = bars + 2 * S;
     uint64_t* tempty_bar = bars + 2 * S + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    constexpr int NIN = Cfg::kInSlots;
+    uint64_t* in_full = bars + 2 * S + 4;
+    uint64_t* in_empty = in_full + NIN;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + 2 * NIN);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -781,6 +581,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < NIN; ++s) {
+            mbar_init(&in_full[s], 1);
+            mbar_init(&in_empty[s], 4);
         }
         mbar_init(&tfull_bar[0], 1);
         mbar_init(&tfull_bar[1], 1);
@@ -864,12 +668,44 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_commit(&tfull_bar[as]);
             }
         }
+    } else if (warp == 6) {
+        // ------------------------------------------------------------------ epilogue-input loader
+        if constexpr (TMA_OUT) {
+            if (lane == 0) {
+                uint8_t* inbuf = obuf + 4 * kATileBytes;
+                const bool has0 = (MODE == EPI_FWD) ? (p.resid != nullptr) : (p.saved != nullptr);
+                const int sh = (MODE == EPI_FWD) ? p.resid_shift : 0;
+                const uint32_t bytes0 = kATileBytes >> (2 * sh);
+                int cnt = 0;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+                    const int w0 = (m_tile % p.tiles_w) * p.tw;
+                    const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+                    const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
+                    for (int c = 0; c < BN; c += 64) {
+                        const int cs = n_tile * BN + c;
+                        if (cs >= p.Cout) break;
+                        if (has0) {
+                            const int slot = cnt % NIN;
+                            mbar_wait(&in_empty[slot], ((cnt / NIN) & 1) ^ 1);
+                            mbar_expect_tx(&in_full[slot], bytes0);
+                            tma_load_4d(inbuf + slot * kATileBytes, &tmO.m[4], &in_full[slot], cs, w0 >> sh, h0 >> sh, n0);
+                            ++cnt;
+                        }
+                        if (MODE == EPI_BWD && p.addin != nullptr && cs < p.addin_climit) {
+                            const int slot = cnt % NIN;
+                            mbar_wait(&in_empty[slot], ((cnt / NIN) & 1) ^ 1);
+                            mbar_expect_tx(&in_full[slot], kATileBytes);
+                            tma_load_4d(inbuf + slot * kATileBytes, &tmO.m[5], &in_full[slot], cs, w0, h0, n0);
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+        }
     } else {
-#if P2L_EPI_STAGED
-        epilogue_loop<BN, MODE, CH>(p, smem + S * Cfg::kStageBytes + Cfg::kOutBytes + 256, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
-#else
-        epilogue_loop_direct<BN, MODE, CH, TMA_OUT>(p, tmO.m, obuf, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
-#endif
+        epilogue_loop_direct<BN, MODE, CH, TMA_OUT>(p, tmO.m, obuf, in_full, in_empty, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane,
+                                                    reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + Cfg::kOutBytes + 256));
     }
 
     tc_fence_before();
@@ -897,7 +733,7 @@ struct HaloCfg {
     static constexpr int kBStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int kRingBytes = kAStages * kPatchBytes + kBStages * kBTileBytes;
     static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = kRingBytes + 1024 + 256 + 4 * kStageSlabBytes;
+    static constexpr int kSmemBytes = kRingBytes + 1024 + 256 + 6 * BN * 4;
 };
 
 template <int BN, int MODE, int P>
@@ -1002,11 +838,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {
-#if P2L_EPI_STAGED
-        epilogue_loop<BN, MODE, CH>(p, smem + Cfg::kRingBytes + 256, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
-#else
-        epilogue_loop_direct<BN, MODE, CH, false>(p, nullptr, nullptr, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane);
-#endif
+        epilogue_loop_direct<BN, MODE, CH, false>(p, nullptr, nullptr, nullptr, nullptr, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane,
+                                                  reinterpret_cast<float*>(smem + Cfg::kRingBytes + 256));
     }
     tc_fence_before();
     __syncthreads();

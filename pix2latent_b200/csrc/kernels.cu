@@ -286,6 +286,34 @@ void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int a
     pool_bnrelu_bwd_kernel<<<grid, block, 0, st>>>(g_up, y_lo, a, aff_stride, S0, S1, stat_stride, dx, H, W, C); count_launch();
 }
 
+__global__ void pool2x2_sum_kernel(const bf16* __restrict__ in, int inC, bf16* __restrict__ out, int b, int H, int W, int C) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int CG = C / 8;
+    const long total = (long)b * H * W * CG;
+    if (i >= total) return;
+    const int cg = i % CG;
+    const long q = i / CG;
+    const int x = q % W, y = (q / W) % H, bi = q / ((long)W * H);
+    const long W2 = 2L * W;
+    const long base = (((long)bi * 2 * H + 2 * y) * W2 + 2 * x) * inC + cg * 8;
+    float a[8], t[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(in + base)), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(in + base + inC)), t);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] += t[e];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(in + base + W2 * inC)), t);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] += t[e];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(in + base + W2 * inC + inC)), t);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] += t[e];
+    *reinterpret_cast<uint4*>(out + q * C + cg * 8) = pack8(a);
+}
+void k_pool2x2_sum(const bf16* in, int inC, bf16* out, int b, int H, int W, int C, cudaStream_t st) {
+    const long total = (long)b * H * W * (C / 8);
+    pool2x2_sum_kernel<<<cdiv(total, 256), 256, 0, st>>>(in, inC, out, b, H, W, C); count_launch();
+}
+
 // ============================================================================= attention glue
 __global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, int xC, int c0, int C, bf16* out, bf16* outT,
                                     unsigned char* idx, int b, int H, int W) {

@@ -46,6 +46,10 @@ void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int a
                        float* S0, float* S1, int stat_stride, bf16* dx, int b, int H, int W, int C,
                        cudaStream_t st);
 
+// out[b,H,W,C] = sum of the 2x2 block of in[b,2H,2W,inC] (first C channels): the skip gradient of an
+// up block at the block's input resolution
+void k_pool2x2_sum(const bf16* in, int inC, bf16* out, int b, int H, int W, int C, cudaStream_t st);
+
 // ---- attention glue ------------------------------------------------------------------------
 // 2x2 max-pool of channels [c0, c0+C) of x[b,H,W,xC] -> out[b,(H/2)*(W/2),C], outT[b,C,(H/2)*(W/2)]
 // (either may be null), argmax (0..3) -> idx
