@@ -47,21 +47,29 @@ __global__ void cond_affine_kernel(const float* __restrict__ cond, const float* 
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= C) return;
     const float m = mean[ch], is = inv_std[ch];
-    for (int b0 = 0; b0 < b; b0 += 8) {
-        float as[8], ao[8];
+    for (int b0 = 0; b0 < b; b0 += 12) {
+        float as[12], ao[12];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { as[i] = 0.f; ao[i] = 0.f; }
-        for (int k = 0; k < cdim; ++k) {
-            const float ws = WsT[(long)k * C + ch], wo = WoT[(long)k * C + ch];
+        for (int i = 0; i < 12; ++i) { as[i] = 0.f; ao[i] = 0.f; }
+        for (int k0 = 0; k0 < cdim; k0 += 8) {
+            float ws[8], wo[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float cv = sc[min(b0 + i, b - 1) * cdim + k];
-                as[i] = fmaf(cv, ws, as[i]);
-                ao[i] = fmaf(cv, wo, ao[i]);
+            for (int u = 0; u < 8; ++u) {  // 16 independent loads in flight per thread
+                ws[u] = __ldg(WsT + (long)(k0 + u) * C + ch);
+                wo[u] = __ldg(WoT + (long)(k0 + u) * C + ch);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                    const float cv = sc[min(b0 + i, b - 1) * cdim + k0 + u];
+                    as[i] = fmaf(cv, ws[u], as[i]);
+                    ao[i] = fmaf(cv, wo[u], ao[i]);
+                }
             }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 12; ++i) {
             if (b0 + i < b) {
                 const float av = (1.f + as[i]) * is;
                 a[(long)(b0 + i) * stride + ch] = av;
@@ -73,7 +81,7 @@ __global__ void cond_affine_kernel(const float* __restrict__ cond, const float* 
 void k_cond_affine(const float* cond, const float* WsT, const float* WoT, const float* mean,
                    const float* inv_std, float* a, float* s, int b, int cdim, int C_cond, int stride,
                    cudaStream_t st) {
-    cond_affine_kernel<<<cdiv(C_cond, 128), 128, (size_t)b * cdim * sizeof(float), st>>>(
+    cond_affine_kernel<<<cdiv(C_cond, 64), 64, (size_t)b * cdim * sizeof(float), st>>>(
         cond, WsT, WoT, mean, inv_std, a, s, b, cdim, C_cond, stride); count_launch();
 }
 
@@ -104,17 +112,22 @@ __global__ void gen_z_kernel(const float* __restrict__ cond, const float* __rest
     if (j >= J) return;
     const int ch = j % C;
     const float bj = bias[j];
-    for (int b0 = 0; b0 < b; b0 += 8) {
-        float acc[8];
+    for (int b0 = 0; b0 < b; b0 += 24) {
+        float acc[24];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int k = 0; k < cdim; ++k) {
-            const float w = WT[(long)k * J + j];
+        for (int i = 0; i < 24; ++i) acc[i] = 0.f;
+        for (int k0 = 0; k0 < cdim; k0 += 8) {
+            float w[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(sc[min(b0 + i, b - 1) * cdim + k], w, acc[i]);
+            for (int u = 0; u < 8; ++u) w[u] = __ldg(WT + (long)(k0 + u) * J + j);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int i = 0; i < 24; ++i) acc[i] = fmaf(sc[min(b0 + i, b - 1) * cdim + k0 + u], w[u], acc[i]);
+            }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 24; ++i) {
             const int bi = b0 + i;
             if (bi < b) {
                 const float h = acc[i] + bj;
@@ -127,7 +140,7 @@ __global__ void gen_z_kernel(const float* __restrict__ cond, const float* __rest
 }
 void k_gen_z(const float* cond, const float* WT, const float* bias, const float* a, const float* s,
              int aff_stride, bf16* raw, bf16* act, int b, int cdim, int J, int C, cudaStream_t st) {
-    gen_z_kernel<<<cdiv(J, 128), 128, (size_t)b * cdim * sizeof(float), st>>>(
+    gen_z_kernel<<<cdiv(J, 64), 64, (size_t)b * cdim * sizeof(float), st>>>(
         cond, WT, bias, a, s, aff_stride, raw, act, b, cdim, J, C); count_launch();
 }
 
@@ -152,7 +165,7 @@ void k_bn_grad_finalize(const float* S0, const float* S1, const float* a, const 
 }
 
 // dcond[b,k] += sum_j G[b,j] W[j,k]; block = cdim threads (one per k), 128 rows of W per block
-constexpr int kDcRows = 256;
+constexpr int kDcRows = 64;
 __global__ void dcond_accum_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ W,
                                    float* dcond, int b, int J, int cdim) {
     extern __shared__ float sg[];  // [b][kDcRows]
@@ -169,10 +182,15 @@ __global__ void dcond_accum_kernel(const float* __restrict__ G, int ldg, const f
         float acc[24];
 #pragma unroll
         for (int i = 0; i < 24; ++i) acc[i] = 0.f;
-        for (int jj = 0; jj < nj; ++jj) {
-            const float w = W[(long)(j0 + jj) * cdim + k];
+        for (int jj0 = 0; jj0 < nj; jj0 += 8) {
+            float w[8];
 #pragma unroll
-            for (int i = 0; i < 24; ++i) acc[i] = fmaf(sg[min(b0 + i, b - 1) * kDcRows + jj], w, acc[i]);
+            for (int u = 0; u < 8; ++u) w[u] = (jj0 + u < nj) ? __ldg(W + (long)(j0 + jj0 + u) * cdim + k) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int i = 0; i < 24; ++i) acc[i] = fmaf(sg[min(b0 + i, b - 1) * kDcRows + jj0 + u], w[u], acc[i]);
+            }
         }
 #pragma unroll
         for (int i = 0; i < 24; ++i) {
