@@ -26,6 +26,7 @@ typedef struct p2l_ctx p2l_ctx;
 typedef struct p2l_biggan p2l_biggan;
 typedef struct p2l_lpips p2l_lpips;
 typedef struct p2l_target p2l_target;
+typedef struct p2l_sg2 p2l_sg2;
 
 #define P2L_MAX_LAYERS 16
 
@@ -111,6 +112,31 @@ int p2l_lpips_launches(p2l_lpips* m, int backward);
 int p2l_biggan_step(p2l_biggan* g, p2l_lpips* l, p2l_target* t, int b, const float* z_dev,
                     const float* c_dev, int want_grad, float grad_scale, const float* dloss_dev,
                     float* loss_dev, float* dz_dev, float* dc_dev, float* img_dev, void* stream);
+
+/* ---- StyleGAN2 generator: replaces StyleGAN2.__init__ / forward_z
+ *      (pix2latent/model/stylegan2.py:66-119: rosinality Generator(size, 512, 8, channel_multiplier=2),
+ *      `model([z], truncation=1.0)[0].clamp_(-1, 1)`) */
+typedef struct p2l_sg2_config {
+    int size;            /* output resolution (power of two, 8..1024) */
+    int style_dim;       /* 512 */
+    int n_mlp;           /* 8 */
+    int channels[9];     /* feature channels at resolution 4, 8, ..., 1024 (multiples of 64) */
+} p2l_sg2_config;
+int p2l_sg2_create(p2l_ctx* ctx, const p2l_sg2_config* cfg, p2l_sg2** out);
+/* name = key of rosinality's g_ema state dict ("style.1.weight", "conv1.conv.weight", "to_rgbs.0.bias", ...) */
+int p2l_sg2_set_tensor(p2l_sg2* m, const char* name, const float* data, long numel);
+int p2l_sg2_finalize(p2l_sg2* m);
+void p2l_sg2_destroy(p2l_sg2* m);
+int p2l_sg2_num_noise_layers(p2l_sg2* m);
+/* img_dev[b,3,R,R] = clamp(G(z), -1, 1). noise_dev: HOST array of num_noise_layers DEVICE pointers to
+ * the per-layer noise images [b,1,r,r] (r = 4,8,8,16,16,...); NULL = no noise. The caller draws the
+ * noise (torch RNG), so reference runs can be replayed.      stylegan2.py:117-119 */
+int p2l_sg2_forward(p2l_sg2* m, int b, const float* z_dev, const float* const* noise_dev, float* img_dev, void* stream);
+int p2l_sg2_backward(p2l_sg2* m, int b, const float* dimg_dev, float* dz_dev, void* stream);
+/* fused step, as p2l_biggan_step */
+int p2l_sg2_step(p2l_sg2* g, p2l_lpips* l, p2l_target* t, int b, const float* z_dev, const float* const* noise_dev,
+                 int want_grad, float grad_scale, const float* dloss_dev, float* loss_dev, float* dz_dev, float* img_dev,
+                 void* stream);
 
 /* ---- measurement hooks (bench.py): while enabled, every tensor-core launch is bracketed by
  * CUDA events on its stream; p2l_profile_read synchronises and returns the summed duration

@@ -10,7 +10,7 @@ from pix2latent_b200 import VariableManager, distribution, save_variables  # noq
 __version__ = _impl.__version__
 _ALIASES = ["distribution", "variable_manager", "loss_functions", "optimizer", "optimizer.closure",
             "optimizer.base_optimizer", "optimizer.gradient_optimizer", "optimizer.base_cma_optimizer",
-            "optimizer.cma_optimizer", "optimizer.basincma_optimizer", "model", "model.biggan", "utils",
+            "optimizer.cma_optimizer", "optimizer.basincma_optimizer", "model", "model.biggan", "model.stylegan2", "utils",
             "utils.function_hooks", "utils.misc", "utils.image"]
 for _name in _ALIASES:
     sys.modules["pix2latent." + _name] = importlib.import_module("pix2latent_b200." + _name)

@@ -3,6 +3,7 @@
 
 #include "biggan.h"
 #include "lpips.h"
+#include "sg2.h"
 
 #define P2L_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -12,6 +13,7 @@ struct p2l_ctx { Ctx c; };
 struct p2l_biggan { BigGAN g; };
 struct p2l_lpips { Lpips l; };
 struct p2l_target { Target* t; };
+struct p2l_sg2 { SG2 g; };
 
 #define P2L_TRY_BEGIN try {
 #define P2L_TRY_END                                             \
@@ -183,5 +185,59 @@ P2L_EXPORT int p2l_biggan_step(p2l_biggan* g, p2l_lpips* l, p2l_target* t, int b
     if (!dimg) return -1;
     if (g->g.backward(b, dimg, dz, dc, st, grad_scale, dloss)) return -1;
     return 0;
+    P2L_TRY_END
+}
+
+// ----------------------------------------------------------------------------- StyleGAN2
+P2L_EXPORT int p2l_sg2_create(p2l_ctx* ctx, const p2l_sg2_config* cfg, p2l_sg2** out) {
+    if (!ctx || !cfg || !out) { set_error("p2l_sg2_create: NULL argument"); return -1; }
+    P2L_TRY_BEGIN
+    p2l_sg2* m = new p2l_sg2();
+    m->g.ctx = &ctx->c;
+    m->g.cfg = *cfg;
+    *out = m;
+    return 0;
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_sg2_set_tensor(p2l_sg2* m, const char* name, const float* data, long numel) {
+    if (!m || !name || !data) { set_error("p2l_sg2_set_tensor: NULL argument"); return -1; }
+    if (m->g.finalized) { set_error("p2l_sg2_set_tensor after finalize"); return -1; }
+    P2L_TRY_BEGIN
+    return m->g.stage.set(name, data, numel);
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_sg2_finalize(p2l_sg2* m) {
+    if (!m) { set_error("p2l_sg2_finalize: NULL"); return -1; }
+    P2L_TRY_BEGIN
+    return m->g.finalize();
+    P2L_TRY_END
+}
+P2L_EXPORT void p2l_sg2_destroy(p2l_sg2* m) { delete m; }
+P2L_EXPORT int p2l_sg2_num_noise_layers(p2l_sg2* m) { return m ? m->g.num_layers : 0; }
+P2L_EXPORT int p2l_sg2_forward(p2l_sg2* m, int b, const float* z, const float* const* noise, float* img, void* stream) {
+    if (!m || b <= 0 || !z) { set_error("p2l_sg2_forward: bad argument"); return -1; }
+    P2L_TRY_BEGIN
+    return m->g.forward(b, z, noise, img, static_cast<cudaStream_t>(stream));
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_sg2_backward(p2l_sg2* m, int b, const float* dimg, float* dz, void* stream) {
+    if (!m || b <= 0 || !dimg || !dz) { set_error("p2l_sg2_backward: bad argument"); return -1; }
+    P2L_TRY_BEGIN
+    return m->g.backward(b, dimg, dz, static_cast<cudaStream_t>(stream));
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_sg2_step(p2l_sg2* g, p2l_lpips* l, p2l_target* t, int b, const float* z, const float* const* noise,
+                            int want_grad, float grad_scale, const float* dloss, float* loss, float* dz, float* img, void* stream) {
+    if (!g || !l || !t || b <= 0 || !z || !loss) { set_error("p2l_sg2_step: bad argument"); return -1; }
+    if (want_grad && !dz) { set_error("p2l_sg2_step: want_grad needs dz"); return -1; }
+    P2L_TRY_BEGIN
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g->g.forward(b, z, noise, img, st)) return -1;
+    const float* im = img ? img : g->g.last_image(b);
+    if (l->l.loss_forward(*t->t, b, im, loss, want_grad, st)) return -1;
+    if (!want_grad) return 0;
+    float* dimg = l->l.unit_grad(*t->t, b);
+    if (!dimg) return -1;
+    return g->g.backward(b, dimg, dz, st, grad_scale, dloss);
     P2L_TRY_END
 }

@@ -1,0 +1,350 @@
+// Native StyleGAN2 generator (see sg2.h). Layer algebra follows oracle/stylegan2.py, which restates
+// rosinality/stylegan2-pytorch model.py as reached via pix2latent/model/stylegan2.py:116-119.
+//
+// Execution map (reference op -> here):
+//   ModulatedConv2d (grouped conv with b*Cout per-sample filters)
+//        -> k_sg_modulate (x * s[b,cin]) -> conv_gemm_kernel with SHARED weights -> dm[b,cout] in k_sg_post_fwd
+//   conv_transpose2d(stride 2) + Blur (upfirdn2d)
+//        -> the same 3x3 kernel (taps flipped) on the zero-inserted (2H+1)^2 grid, 4x4 FIR in k_sg_post_fwd
+//   NoiseInjection + FusedLeakyReLU (rosinality's fused_bias_act CUDA op) -> k_sg_post_fwd
+//   ToRGB (1x1 modulated conv, no demod) + Upsample skip (upfirdn2d CUDA op) -> k_sg_torgb_fwd
+// This round's StyleGAN2 path is correctness-first (separate elementwise passes, 4x zero-work in the
+// up-sampling convs); DESIGN.md lists the fusion / polyphase work that remains.
+#include "sg2.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace p2l {
+
+struct SG2Plan {
+    int b = 0;
+    Arena ar;
+    float *z = nullptr, *h[9] = {nullptr}, *g0 = nullptr, *g1 = nullptr;
+    float *s_all = nullptr, *ds_all = nullptr, *dm_all = nullptr, *ddm_all = nullptr, *dw = nullptr;
+    struct Lay {
+        __nv_bfloat16 *A = nullptr, *x = nullptr;
+        float* D = nullptr;
+        int Ha = 0;  // grid the convolution runs on (2*Hin+1 for up layers)
+        ConvOp f, d;
+    };
+    std::vector<Lay> L;
+    std::vector<float*> rgb, weff, dweff;
+    float *drgbA = nullptr, *drgbB = nullptr, *img = nullptr;
+    __nv_bfloat16 *dx[2] = {nullptr, nullptr}, *G = nullptr, *dDp = nullptr, *dA = nullptr;
+    bool forward_done = false;
+};
+
+SG2::~SG2() {}
+
+static int pick_bn_sg(int Cout, long m_tiles, long K) {
+    const int cands[3] = {256, 128, 64};
+    for (int k = (K <= 1024 ? 1 : 0); k < 3; ++k)
+        if (Cout % cands[k] == 0 && m_tiles * (Cout / cands[k]) >= num_sms()) return cands[k];
+    for (int k = 2; k >= 0; --k)
+        if (Cout % cands[k] == 0) return cands[k];
+    return 64;
+}
+
+int SG2::finalize() {
+    if (finalized) return 0;
+    sdim = cfg.style_dim;
+    n_mlp = cfg.n_mlp;
+    log_size = 0;
+    while ((1 << log_size) < cfg.size) ++log_size;
+    if ((1 << log_size) != cfg.size || log_size < 3 || log_size > 10 || n_mlp != 8) { set_error("sg2: unsupported size %d / n_mlp %d", cfg.size, n_mlp); return -1; }
+    num_layers = (log_size - 2) * 2 + 1;
+    // ---- mapping network: EqualLinear(512, 512, lr_mul=0.01, fused_lrelu)
+    const float lr = 0.01f;
+    map_scale = (1.f / std::sqrt((float)sdim)) * lr;
+    for (int k = 1; k <= n_mlp; ++k) {
+        const auto* w = stage.get("style." + std::to_string(k) + ".weight", (long)sdim * sdim);
+        const auto* bsv = stage.get("style." + std::to_string(k) + ".bias", sdim);
+        if (!w || !bsv) return -1;
+        std::vector<float> t((size_t)sdim * sdim), bb(sdim);
+        for (int o = 0; o < sdim; ++o)
+            for (int i = 0; i < sdim; ++i) t[(size_t)i * sdim + o] = (*w)[(size_t)o * sdim + i];
+        for (int o = 0; o < sdim; ++o) bb[o] = (*bsv)[o] * lr;
+        map_WT.push_back(upload(weights, t));
+        map_W.push_back(upload(weights, *w));
+        map_b.push_back(upload(weights, bb));
+    }
+    // ---- layer table
+    auto ch = [&](int res_log) { return cfg.channels[res_log - 2]; };
+    convs.clear();
+    rgbs.clear();
+    int s_off = 0, dm_off = 0;
+    std::vector<std::string> conv_names, rgb_names;
+    {
+        Conv c{}; c.Cin = ch(2); c.Cout = ch(2); c.Hin = 4; c.Hout = 4; c.up = 0;
+        convs.push_back(c); conv_names.push_back("conv1");
+        Rgb r{}; r.Cin = ch(2); r.H = 4; rgbs.push_back(r); rgb_names.push_back("to_rgb1");
+    }
+    int in_c = ch(2);
+    for (int i = 3; i <= log_size; ++i) {
+        const int out_c = ch(i), res = 1 << i;
+        Conv a{}; a.Cin = in_c; a.Cout = out_c; a.Hin = res / 2; a.Hout = res; a.up = 1;
+        Conv bq{}; bq.Cin = out_c; bq.Cout = out_c; bq.Hin = res; bq.Hout = res; bq.up = 0;
+        convs.push_back(a); conv_names.push_back("convs." + std::to_string(2 * (i - 3)));
+        convs.push_back(bq); conv_names.push_back("convs." + std::to_string(2 * (i - 3) + 1));
+        Rgb r{}; r.Cin = out_c; r.H = res; rgbs.push_back(r); rgb_names.push_back("to_rgbs." + std::to_string(i - 3));
+        in_c = out_c;
+    }
+    for (auto& c : convs) {
+        if (c.Cin % 64 || c.Cout % 64) { set_error("sg2: channel counts must be multiples of 64 (got %d -> %d)", c.Cin, c.Cout); return -1; }
+        c.s_off = s_off; s_off += c.Cin;
+        c.dm_off = dm_off; dm_off += c.Cout;
+    }
+    for (auto& r : rgbs) { r.s_off = s_off; s_off += r.Cin; }
+    S = s_off;
+    DM = dm_off;
+    // ---- modulation affines (EqualLinear(512, Cin, bias_init=1), lr_mul 1)
+    std::vector<float> h_aff((size_t)S * sdim), h_affT((size_t)S * sdim), h_affb(S);
+    auto put_aff = [&](const std::string& pre, int Cin, int off) -> int {
+        const auto* w = stage.get(pre + ".conv.modulation.weight", (long)Cin * sdim);
+        const auto* bsv = stage.get(pre + ".conv.modulation.bias", Cin);
+        if (!w || !bsv) return -1;
+        for (int i = 0; i < Cin; ++i) {
+            h_affb[off + i] = (*bsv)[i];
+            for (int k = 0; k < sdim; ++k) {
+                h_aff[(size_t)(off + i) * sdim + k] = (*w)[(size_t)i * sdim + k];
+                h_affT[(size_t)k * S + off + i] = (*w)[(size_t)i * sdim + k];
+            }
+        }
+        return 0;
+    };
+    for (size_t l = 0; l < convs.size(); ++l) {
+        Conv& c = convs[l];
+        const std::string& pre = conv_names[l];
+        if (put_aff(pre, c.Cin, c.s_off)) return -1;
+        const auto* w = stage.get(pre + ".conv.weight", (long)c.Cout * c.Cin * 9);
+        const auto* nw = stage.get(pre + ".noise.weight", 1);
+        const auto* bsv = stage.get(pre + ".activate.bias", c.Cout);
+        if (!w || !nw || !bsv) return -1;
+        const float scale = 1.f / std::sqrt((float)c.Cin * 9.f);
+        std::vector<float> ws(w->size()), wsq((size_t)c.Cout * c.Cin), wsqT((size_t)c.Cout * c.Cin);
+        for (int o = 0; o < c.Cout; ++o)
+            for (int i = 0; i < c.Cin; ++i) {
+                double q = 0;
+                for (int r = 0; r < 3; ++r)
+                    for (int s2 = 0; s2 < 3; ++s2) {
+                        const float v = (*w)[(((size_t)o * c.Cin + i) * 3 + r) * 3 + s2] * scale;
+                        q += (double)v * v;
+                        // up layers: conv_transpose == same-conv with flipped taps on the zero-inserted grid
+                        const int rr = c.up ? 2 - r : r, ss = c.up ? 2 - s2 : s2;
+                        ws[(((size_t)o * c.Cin + i) * 3 + rr) * 3 + ss] = v;
+                    }
+                wsq[(size_t)o * c.Cin + i] = (float)q;
+                wsqT[(size_t)i * c.Cout + o] = (float)q;
+            }
+        c.w = upload(weights, pack_conv_fwd(ws, c.Cout, c.Cin, 3, 3));
+        c.wt = upload(weights, pack_conv_dgrad(ws, c.Cout, c.Cin, 3, 3));
+        c.wsq = upload(weights, wsq);
+        c.wsqT = upload(weights, wsqT);
+        c.noise_w = upload(weights, *nw);
+        c.bias = upload(weights, *bsv);
+    }
+    for (size_t t = 0; t < rgbs.size(); ++t) {
+        Rgb& r = rgbs[t];
+        const std::string& pre = rgb_names[t];
+        if (put_aff(pre, r.Cin, r.s_off)) return -1;
+        const auto* w = stage.get(pre + ".conv.weight", (long)3 * r.Cin);
+        const auto* bsv = stage.get(pre + ".bias", 3);
+        if (!w || !bsv) return -1;
+        r.Wr = upload(weights, *w);
+        r.bias = upload(weights, *bsv);
+        r.scale = 1.f / std::sqrt((float)r.Cin);
+    }
+    aff = upload(weights, h_aff);
+    affT = upload(weights, h_affT);
+    aff_b = upload(weights, h_affb);
+    {   // constant input [1, C0, 4, 4] -> NHWC bf16
+        const int C0 = convs[0].Cin;
+        const auto* w = stage.get("input.input", (long)C0 * 16);
+        if (!w) return -1;
+        std::vector<__nv_bfloat16> t((size_t)16 * C0);
+        for (int c = 0; c < C0; ++c)
+            for (int p = 0; p < 16; ++p) t[(size_t)p * C0 + c] = host_f2bf((*w)[(size_t)c * 16 + p]);
+        const_in = upload(weights, t);
+    }
+    if (weights.failed) return -1;
+    stage.t.clear();
+    finalized = true;
+    return 0;
+}
+
+SG2Plan* SG2::plan(int b) {
+    auto it = plans.find(b);
+    if (it != plans.end()) return it->second.get();
+    std::shared_ptr<SG2Plan> pp(new SG2Plan());
+    SG2Plan& P = *pp;
+    P.b = b;
+    Arena& ar = P.ar;
+    typedef __nv_bfloat16 bf;
+    P.z = ar.alloc<float>((size_t)b * sdim);
+    for (int k = 0; k <= n_mlp; ++k) P.h[k] = ar.alloc<float>((size_t)b * sdim);
+    P.g0 = ar.alloc<float>((size_t)b * sdim);
+    P.g1 = ar.alloc<float>((size_t)b * sdim);
+    P.s_all = ar.alloc<float>((size_t)b * S);
+    P.ds_all = ar.alloc<float>((size_t)b * S);
+    P.dm_all = ar.alloc<float>((size_t)b * DM);
+    P.ddm_all = ar.alloc<float>((size_t)b * DM);
+    P.dw = ar.alloc<float>((size_t)b * sdim);
+    const int nL = (int)convs.size();
+    P.L.resize(nL);
+    size_t max_x = 0, max_a = 0;
+    for (int l = 0; l < nL; ++l) {
+        const Conv& c = convs[l];
+        SG2Plan::Lay& q = P.L[l];
+        q.Ha = c.up ? 2 * c.Hin + 1 : c.Hin;
+        const size_t pa = (size_t)b * q.Ha * q.Ha;
+        q.A = ar.alloc<bf>(pa * c.Cin, /*zero=*/true);  // up layers: even rows / columns stay zero forever
+        q.D = ar.alloc<float>(pa * c.Cout);
+        q.x = ar.alloc<bf>((size_t)b * c.Hout * c.Hout * c.Cout);
+        max_x = std::max(max_x, (size_t)b * c.Hout * c.Hout * c.Cout);
+        max_a = std::max(max_a, std::max(pa * c.Cin, pa * c.Cout));
+    }
+    P.dx[0] = ar.alloc<bf>(max_x);
+    P.dx[1] = ar.alloc<bf>(max_x);
+    P.G = ar.alloc<bf>(max_x);
+    P.dDp = ar.alloc<bf>(max_a);
+    P.dA = ar.alloc<bf>(max_a);
+    const int R = cfg.size;
+    for (size_t t = 0; t < rgbs.size(); ++t) {
+        P.rgb.push_back(ar.alloc<float>((size_t)b * 3 * rgbs[t].H * rgbs[t].H));
+        P.weff.push_back(ar.alloc<float>((size_t)b * 3 * rgbs[t].Cin));
+        P.dweff.push_back(ar.alloc<float>((size_t)b * 3 * rgbs[t].Cin));
+    }
+    P.drgbA = ar.alloc<float>((size_t)b * 3 * R * R);
+    P.drgbB = ar.alloc<float>((size_t)b * 3 * R * R);
+    P.img = ar.alloc<float>((size_t)b * 3 * R * R);
+    if (ar.failed) return nullptr;
+    auto m_tiles = [&](int hh) {
+        int tw = 1; while (tw < hh) tw <<= 1; if (tw > 16) tw = 16;
+        int th = 1; while (th < hh) th <<= 1; if (th > 128 / tw) th = 128 / tw;
+        const int nb = 128 / (tw * th);
+        return (long)((hh + tw - 1) / tw) * ((hh + th - 1) / th) * ((b + nb - 1) / nb);
+    };
+    for (int l = 0; l < nL; ++l) {
+        const Conv& c = convs[l];
+        SG2Plan::Lay& q = P.L[l];
+        {   // D = conv(A, W')   (fp32 out)
+            ConvDesc d;
+            d.A = q.A; d.A_N = b; d.A_H = q.Ha; d.A_W = q.Ha; d.A_C = c.Cin; d.Cin = c.Cin;
+            d.B = c.w; d.Cout = c.Cout; d.kh = d.kw = 3; d.pad_h = d.pad_w = 1;
+            d.NI = b; d.H = q.Ha; d.W = q.Ha; d.mode = EPI_FWD;
+            d.BN = pick_bn_sg(c.Cout, m_tiles(q.Ha), 9L * c.Cin);
+            d.epi.raw_f32 = q.D; d.epi.raw_f32_C = c.Cout;
+            if (conv_op_build(&q.f, d)) return nullptr;
+        }
+        {   // dA = conv^T(dD, W')
+            ConvDesc d;
+            d.A = c.up ? P.dDp : P.G; d.A_N = b; d.A_H = q.Ha; d.A_W = q.Ha; d.A_C = c.Cout; d.Cin = c.Cout;
+            d.B = c.wt; d.Cout = c.Cin; d.kh = d.kw = 3; d.pad_h = d.pad_w = 1;
+            d.NI = b; d.H = q.Ha; d.W = q.Ha; d.mode = EPI_BWD;
+            d.BN = pick_bn_sg(c.Cin, m_tiles(q.Ha), 9L * c.Cout);
+            d.epi.dx = P.dA; d.epi.dx_C = c.Cin;
+            if (conv_op_build(&q.d, d)) return nullptr;
+        }
+    }
+    SG2Plan* raw = pp.get();
+    plans[b] = pp;
+    return raw;
+}
+
+int SG2::forward(int b, const float* z, const float* const* noise, float* img, cudaStream_t st) {
+    if (!finalized) { set_error("sg2: forward before finalize"); return -1; }
+    SG2Plan* Pp = plan(b);
+    if (!Pp) return -1;
+    SG2Plan& P = *Pp;
+    const int nL = (int)convs.size();
+    P2L_CUDA_CHECK(cudaMemcpyAsync(P.z, z, (size_t)b * sdim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // mapping network
+    k_pixelnorm_fwd(P.z, P.h[0], b, sdim, st);
+    for (int k = 0; k < n_mlp; ++k)
+        k_fc_fwd(P.h[k], sdim, map_WT[k], map_b[k], map_scale, P.h[k + 1], sdim, b, sdim, sdim, 1, 0, st);
+    const float* w = P.h[n_mlp];
+    // styles of every modulated conv / ToRGB (the same w feeds all of them in z search)
+    k_fc_fwd(w, sdim, affT, aff_b, 1.f / std::sqrt((float)sdim), P.s_all, S, b, sdim, S, 0, 0, st);
+    for (int l = 0; l < nL; ++l) {
+        const Conv& c = convs[l];
+        k_fc_fwd(P.s_all + c.s_off, S, c.wsqT, nullptr, 1.f, P.dm_all + c.dm_off, DM, b, c.Cin, c.Cout, 2, 1, st);
+    }
+    const __nv_bfloat16* xprev = const_in;
+    long xprev_bs = 0;
+    int t = 0;
+    for (int l = 0; l < nL; ++l) {
+        const Conv& c = convs[l];
+        SG2Plan::Lay& q = P.L[l];
+        k_sg_modulate(xprev, xprev_bs, P.s_all + c.s_off, S, q.A, b, c.Hin, c.Hin, c.Cin, c.up, st);
+        if (conv_op_launch(q.f, st)) return -1;
+        k_sg_post_fwd(q.D, P.dm_all + c.dm_off, DM, noise ? noise[l] : nullptr, c.noise_w, c.bias, q.x, b, c.Hout, c.Hout, c.Cout,
+                      c.up, st);
+        xprev = q.x;
+        xprev_bs = (long)c.Hout * c.Hout * c.Cout;
+        if (l == 0 || (l % 2 == 0)) {
+            const Rgb& r = rgbs[t];
+            k_sg_weff(r.Wr, P.s_all + r.s_off, S, r.scale, P.weff[t], b, r.Cin, st);
+            k_sg_torgb_fwd(q.x, P.weff[t], r.bias, t > 0 ? P.rgb[t - 1] : nullptr, P.rgb[t], b, r.H, r.H, r.Cin, st);
+            ++t;
+        }
+    }
+    const long n = (long)b * 3 * cfg.size * cfg.size;
+    k_sg_clamp(P.rgb.back(), P.img, n, st);
+    if (img && img != P.img) P2L_CUDA_CHECK(cudaMemcpyAsync(img, P.img, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    P.forward_done = true;
+    return 0;
+}
+
+int SG2::backward(int b, const float* dimg, float* dz, cudaStream_t st, float scale, const float* row_scale) {
+    auto it = plans.find(b);
+    if (it == plans.end() || !it->second->forward_done) { set_error("sg2: backward(b=%d) without a matching forward", b); return -1; }
+    SG2Plan& P = *it->second;
+    const int T = (int)rgbs.size();
+    P2L_CUDA_CHECK(cudaMemsetAsync(P.ds_all, 0, (size_t)b * S * sizeof(float), st));
+    P2L_CUDA_CHECK(cudaMemsetAsync(P.ddm_all, 0, (size_t)b * DM * sizeof(float), st));
+    for (int t = 0; t < T; ++t) P2L_CUDA_CHECK(cudaMemsetAsync(P.dweff[t], 0, (size_t)b * 3 * rgbs[t].Cin * sizeof(float), st));
+    float *dcur = P.drgbA, *dprev = P.drgbB;
+    k_sg_clamp_bwd(P.rgb.back(), dimg, dcur, (long)b * 3 * cfg.size * cfg.size, st);
+    auto layer_bwd = [&](int l) -> int {
+        const Conv& c = convs[l];
+        SG2Plan::Lay& q = P.L[l];
+        k_sg_post_bwd(P.dx[l & 1], q.x, q.D, P.dm_all + c.dm_off, DM, P.G, P.ddm_all + c.dm_off, b, c.Hout, c.Hout, c.Cout, c.up, st);
+        if (c.up) k_sg_blur_adjoint(P.G, P.dDp, b, c.Hout, c.Hout, c.Cout, st);
+        if (conv_op_launch(q.d, st)) return -1;
+        const __nv_bfloat16* xp = l == 0 ? const_in : P.L[l - 1].x;
+        const long xbs = l == 0 ? 0 : (long)c.Hin * c.Hin * c.Cin;
+        k_sg_modulate_bwd(P.dA, xp, xbs, P.s_all + c.s_off, S, l == 0 ? nullptr : P.dx[(l - 1) & 1], P.ds_all + c.s_off, S, b, c.Hin,
+                          c.Hin, c.Cin, c.up, st);
+        k_demod_bwd(P.ddm_all + c.dm_off, P.dm_all + c.dm_off, DM, P.s_all + c.s_off, S, c.wsq, P.ds_all + c.s_off, S, b, c.Cin,
+                    c.Cout, st);
+        return 0;
+    };
+    for (int t = T - 1; t >= 0; --t) {
+        const Rgb& r = rgbs[t];
+        const int l = (t == 0) ? 0 : 2 * t;
+        k_sg_torgb_bwd(dcur, P.L[l].x, P.weff[t], P.dx[l & 1], P.dweff[t], b, r.H, r.H, r.Cin, t < T - 1 ? 1 : 0, st);
+        k_sg_weff_bwd(P.dweff[t], r.Wr, r.scale, P.ds_all + r.s_off, S, b, r.Cin, st);
+        if (t > 0) k_sg_rgb_up_adjoint(dcur, dprev, b, r.H / 2, r.H / 2, st);
+        if (layer_bwd(l)) return -1;
+        if (t > 0 && layer_bwd(l - 1)) return -1;
+        std::swap(dcur, dprev);
+    }
+    // styles -> w -> mapping network -> z
+    k_fc_bwd(P.ds_all, S, nullptr, 0, aff, 1.f / std::sqrt((float)sdim), P.dw, sdim, b, sdim, S, 0, 0, st);
+    float *g = P.dw, *gn = P.g0;
+    for (int k = n_mlp - 1; k >= 0; --k) {
+        k_fc_bwd(g, sdim, P.h[k + 1], sdim, map_W[k], map_scale, gn, sdim, b, sdim, sdim, 1, 0, st);
+        g = gn;
+        gn = (gn == P.g0) ? P.g1 : P.g0;
+    }
+    k_pixelnorm_bwd(P.z, g, dz, b, sdim, scale, row_scale, st);
+    return 0;
+}
+
+const float* SG2::last_image(int b) {
+    auto it = plans.find(b);
+    return it == plans.end() ? nullptr : it->second->img;
+}
+
+}  // namespace p2l

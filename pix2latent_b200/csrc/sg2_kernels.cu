@@ -1,0 +1,569 @@
+// StyleGAN2 glue kernels (everything of rosinality's Generator that is not a dense contraction):
+// mapping-network GEMVs, style modulation / demodulation, noise + bias + leaky-ReLU, the 4-tap FIR
+// blur / up-sampling (upfirdn2d) and the 3-channel ToRGB path, forward and backward.
+// The dense 3x3 contractions run on conv_gemm_kernel with SHARED weights: the per-sample weight
+// modulation of the reference (ModulatedConv2d: grouped conv with b*Cout filters) is an input-channel
+// scale before and an output-channel scale after the convolution.
+#include "sg2_kernels.h"
+
+#include "conv_gemm.h"
+
+namespace p2l {
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+__device__ __forceinline__ float b2f(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ bf16 f2b(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ void unpack8(const uint4 t, float (&f)[8]) {
+    f[0] = __uint_as_float(t.x << 16); f[1] = __uint_as_float(t.x & 0xFFFF0000u);
+    f[2] = __uint_as_float(t.y << 16); f[3] = __uint_as_float(t.y & 0xFFFF0000u);
+    f[4] = __uint_as_float(t.z << 16); f[5] = __uint_as_float(t.z & 0xFFFF0000u);
+    f[6] = __uint_as_float(t.w << 16); f[7] = __uint_as_float(t.w & 0xFFFF0000u);
+}
+__device__ __forceinline__ uint32_t pk2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pk2(f[0], f[1]), pk2(f[2], f[3]), pk2(f[4], f[5]), pk2(f[6], f[7]));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __constant__ float kFir[4] = {0.25f, 0.75f, 0.75f, 0.25f};  // [1,3,3,1]/8 * 2 (per axis)
+constexpr float kSqrt2 = 1.41421356237309515f;
+
+// ----------------------------------------------------------------------------- dense latent-side layers
+// y[b, j] = act(wscale * sum_k x[b,k] * WT[k][j] + bias[j]); thread per j, <= 24 samples per pass
+__global__ void fc_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ WT, const float* __restrict__ bias,
+                              float wscale, float* y, int ldy, int b, int in, int out, int act, int square_in) {
+    extern __shared__ float sx[];  // [b][in]
+    for (int i = threadIdx.x; i < b * in; i += blockDim.x) {
+        const float v = x[(long)(i / in) * ldx + (i % in)];
+        sx[i] = square_in ? v * v : v;
+    }
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= out) return;
+    for (int b0 = 0; b0 < b; b0 += 24) {
+        float acc[24];
+#pragma unroll
+        for (int i = 0; i < 24; ++i) acc[i] = 0.f;
+        for (int k0 = 0; k0 < in; k0 += 8) {
+            float w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w[u] = (k0 + u < in) ? __ldg(WT + (long)(k0 + u) * out + j) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = min(k0 + u, in - 1);
+#pragma unroll
+                for (int i = 0; i < 24; ++i) acc[i] = fmaf(sx[min(b0 + i, b - 1) * in + k], w[u], acc[i]);
+            }
+        }
+        const float bj = bias ? bias[j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 24; ++i) {
+            if (b0 + i < b) {
+                float v = acc[i] * wscale + bj;
+                if (act == 1) v = (v > 0.f ? v : 0.2f * v) * kSqrt2;      // fused_leaky_relu
+                else if (act == 2) v = rsqrtf(v + 1e-8f);                   // demodulation (bias = 0)
+                y[(long)(b0 + i) * ldy + j] = v;
+            }
+        }
+    }
+}
+void k_fc_fwd(const float* x, int ldx, const float* WT, const float* bias, float wscale, float* y, int ldy, int b, int in,
+              int out, int act, int square_in, cudaStream_t st) {
+    for (int b0 = 0; b0 < b; b0 += 16) {  // <= 16 samples per launch keeps the staged inputs under 48 KB
+        const int nb = b - b0 < 16 ? b - b0 : 16;
+        fc_fwd_kernel<<<cdiv(out, 64), 64, (size_t)nb * in * sizeof(float), st>>>(x + (long)b0 * ldx, ldx, WT, bias, wscale,
+                                                                                  y + (long)b0 * ldy, ldy, nb, in, out, act, square_in);
+        count_launch();
+    }
+}
+
+// dx[b, k] (+)= wscale * sum_j g[b,j] * W[j][k], g = dy * act'(y); thread per k
+__global__ void fc_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+                              const float* __restrict__ W, float wscale, float* dx, int lddx, int b, int in, int out, int act,
+                              int accumulate) {
+    constexpr int JC = 256;          // rows of W per shared-memory chunk
+    extern __shared__ float sg[];    // [b <= 16][JC]
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int jc = 0; jc < out; jc += JC) {
+        const int nj = min(JC, out - jc);
+        __syncthreads();
+        for (int i = threadIdx.x; i < b * JC; i += blockDim.x) {
+            const int bi = i / JC, jj = i % JC;
+            float g = 0.f;
+            if (jj < nj) {
+                g = dy[(long)bi * lddy + jc + jj];
+                if (act == 1) g *= (y[(long)bi * ldy + jc + jj] > 0.f ? 1.f : 0.2f) * kSqrt2;
+            }
+            sg[i] = g;
+        }
+        __syncthreads();
+        if (k < in) {
+            for (int j0 = 0; j0 < nj; j0 += 8) {
+                float w[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w[u] = (j0 + u < nj) ? __ldg(W + (long)(jc + j0 + u) * in + k) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = fmaf(sg[min(i, b - 1) * JC + min(j0 + u, JC - 1)], w[u], acc[i]);
+                }
+            }
+        }
+    }
+    if (k >= in) return;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (i < b) {
+            float* d = dx + (long)i * lddx + k;
+            *d = (accumulate ? *d : 0.f) + acc[i] * wscale;
+        }
+    }
+}
+void k_fc_bwd(const float* dy, int lddy, const float* y, int ldy, const float* W, float wscale, float* dx, int lddx, int b,
+              int in, int out, int act, int accumulate, cudaStream_t st) {
+    for (int b0 = 0; b0 < b; b0 += 16) {
+        const int nb = b - b0 < 16 ? b - b0 : 16;
+        fc_bwd_kernel<<<cdiv(in, 64), 64, (size_t)nb * 256 * sizeof(float), st>>>(
+            dy + (long)b0 * lddy, lddy, y ? y + (long)b0 * ldy : nullptr, ldy, W, wscale, dx + (long)b0 * lddx, lddx, nb, in, out, act, accumulate);
+        count_launch();
+    }
+}
+
+// PixelNorm: y = x * rsqrt(mean(x^2) + 1e-8); one warp per sample
+__global__ void pixelnorm_fwd_kernel(const float* x, float* y, int n) {
+    const int bi = blockIdx.x, lane = threadIdx.x;
+    float ss = 0.f;
+    for (int k = lane; k < n; k += 32) ss += x[bi * n + k] * x[bi * n + k];
+    ss = warp_sum(ss);
+    const float r = rsqrtf(ss / n + 1e-8f);
+    for (int k = lane; k < n; k += 32) y[bi * n + k] = x[bi * n + k] * r;
+}
+__global__ void pixelnorm_bwd_kernel(const float* x, const float* dy, float* dx, int n, float scale, const float* row_scale) {
+    const int bi = blockIdx.x, lane = threadIdx.x;
+    float ss = 0.f, dot = 0.f;
+    for (int k = lane; k < n; k += 32) {
+        ss += x[bi * n + k] * x[bi * n + k];
+        dot += x[bi * n + k] * dy[bi * n + k];
+    }
+    ss = warp_sum(ss);
+    dot = warp_sum(dot);
+    const float r = rsqrtf(ss / n + 1e-8f);
+    const float sc = scale * (row_scale ? row_scale[bi] : 1.f);
+    // d/dx_k [x_j r] = r delta_jk - x_j x_k r^3 / n
+    for (int k = lane; k < n; k += 32) dx[bi * n + k] = sc * (r * dy[bi * n + k] - x[bi * n + k] * dot * r * r * r / n);
+}
+void k_pixelnorm_fwd(const float* x, float* y, int b, int n, cudaStream_t st) {
+    pixelnorm_fwd_kernel<<<b, 32, 0, st>>>(x, y, n); count_launch();
+}
+void k_pixelnorm_bwd(const float* x, const float* dy, float* dx, int b, int n, float scale, const float* row_scale, cudaStream_t st) {
+    pixelnorm_bwd_kernel<<<b, 32, 0, st>>>(x, dy, dx, n, scale, row_scale); count_launch();
+}
+
+// ds[b,i] += -s[b,i] * sum_o (ddm*dm^3)[b,o] * Wsq[o][i]   (gradient through the demodulation)
+__global__ void demod_bwd_kernel(const float* __restrict__ ddm, const float* __restrict__ dm, int lddm,
+                                 const float* __restrict__ s, int lds, const float* __restrict__ Wsq, float* ds, int ldds,
+                                 int b, int Cin, int Cout) {
+    extern __shared__ float sg[];  // [b][Cout]
+    for (int i = threadIdx.x; i < b * Cout; i += blockDim.x) {
+        const int bi = i / Cout, o = i % Cout;
+        const float d = dm[(long)bi * lddm + o];
+        sg[i] = ddm[(long)bi * lddm + o] * d * d * d;
+    }
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Cin) return;
+    for (int bi = 0; bi < b; ++bi) {
+        float acc = 0.f;
+        for (int o = 0; o < Cout; ++o) acc = fmaf(sg[bi * Cout + o], __ldg(Wsq + (long)o * Cin + k), acc);
+        ds[(long)bi * ldds + k] -= s[(long)bi * lds + k] * acc;
+    }
+}
+void k_demod_bwd(const float* ddm, const float* dm, int lddm, const float* s, int lds, const float* Wsq, float* ds, int ldds,
+                 int b, int Cin, int Cout, cudaStream_t st) {
+    for (int b0 = 0; b0 < b; b0 += 16) {
+        const int nb = b - b0 < 16 ? b - b0 : 16;
+        demod_bwd_kernel<<<cdiv(Cin, 64), 64, (size_t)nb * Cout * sizeof(float), st>>>(
+            ddm + (long)b0 * lddm, dm + (long)b0 * lddm, lddm, s + (long)b0 * lds, lds, Wsq, ds + (long)b0 * ldds, ldds, nb, Cin, Cout);
+        count_launch();
+    }
+}
+
+// ----------------------------------------------------------------------------- modulation
+// A[b, p, c] = x[b or 0, p, c] * s[b, c]; up: written at (2y+1, 2x+1) of a zero-filled [2H+1, 2W+1] grid
+__global__ void modulate_kernel(const bf16* __restrict__ x, long x_bstride, const float* __restrict__ s, int lds, bf16* __restrict__ A,
+                                int b, int H, int W, int C, int up) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int CG = C / 8;
+    const long total = (long)b * H * W * CG;
+    if (i >= total) return;
+    const int cg = i % CG;
+    const long q = i / CG;
+    const int xx = q % W, y = (q / W) % H, bi = q / ((long)W * H);
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + bi * x_bstride + ((long)y * W + xx) * C + cg * 8)), v);
+    const float4 s0 = *reinterpret_cast<const float4*>(s + (long)bi * lds + cg * 8);
+    const float4 s1 = *reinterpret_cast<const float4*>(s + (long)bi * lds + cg * 8 + 4);
+    v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+    long o;
+    if (up) o = (((long)bi * (2 * H + 1) + 2 * y + 1) * (2 * W + 1) + 2 * xx + 1) * C + cg * 8;
+    else o = q * C + cg * 8;
+    *reinterpret_cast<uint4*>(A + o) = pack8(v);
+}
+void k_sg_modulate(const bf16* x, long x_bstride, const float* s, int lds, bf16* A, int b, int H, int W, int C, int up, cudaStream_t st) {
+    const long total = (long)b * H * W * (C / 8);
+    modulate_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, x_bstride, s, lds, A, b, H, W, C, up); count_launch();
+}
+
+// backward: dA (sampled at odd positions when up) -> ds[b,c] += sum_p dA*x ; dx = s*dA
+// block = 8 channel groups x 32 pixels, one image; 64 channels per blockIdx.y
+__global__ void modulate_bwd_kernel(const bf16* __restrict__ dA, const bf16* __restrict__ x, long x_bstride, const float* __restrict__ s,
+                                    int lds, bf16* __restrict__ dx, float* ds, int ldds, int H, int W, int C, int up) {
+    __shared__ float red[32][65];
+    const int cg = threadIdx.x, py = threadIdx.y;
+    const int c = blockIdx.y * 64 + cg * 8;
+    const int bi = blockIdx.z;
+    const int HW = H * W;
+    float sv[8], acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sv[e] = s[(long)bi * lds + c + e]; acc[e] = 0.f; }
+    for (int p = blockIdx.x * 256 + py; p < min(HW, (int)(blockIdx.x + 1) * 256); p += 32) {
+        const int y = p / W, xx = p % W;
+        long ia;
+        if (up) ia = (((long)bi * (2 * H + 1) + 2 * y + 1) * (2 * W + 1) + 2 * xx + 1) * C + c;
+        else ia = ((long)bi * HW + p) * C + c;
+        float g[8], xv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dA + ia)), g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + bi * x_bstride + (long)p * C + c)), xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { acc[e] += g[e] * xv[e]; g[e] *= sv[e]; }
+        if (dx) *reinterpret_cast<uint4*>(dx + ((long)bi * HW + p) * C + c) = pack8(g);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[py][cg * 8 + e] = acc[e];
+    __syncthreads();
+    const int tid = py * 8 + cg;
+    if (tid < 64) {
+        float t = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) t += red[k][tid];
+        atomicAdd(ds + (long)bi * ldds + blockIdx.y * 64 + tid, t);
+    }
+}
+void k_sg_modulate_bwd(const bf16* dA, const bf16* x, long x_bstride, const float* s, int lds, bf16* dx, float* ds, int ldds,
+                       int b, int H, int W, int C, int up, cudaStream_t st) {
+    dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
+    modulate_bwd_kernel<<<grid, block, 0, st>>>(dA, x, x_bstride, s, lds, dx, ds, ldds, H, W, C, up); count_launch();
+}
+
+// ----------------------------------------------------------------------------- demod + noise + bias + lrelu (+ blur)
+// x = lrelu(dm * [blur](D) + nw * noise + bias) * sqrt2. up: D is [b, H+1, W+1, C] (conv_transpose grid),
+// blur = 4x4 FIR with pad (1,1): out[y] = sum_t D[y + t - 1] k[t]
+__device__ __forceinline__ void blur_gather(const float* __restrict__ D, int bi, int y, int xx, int H, int W, int C, int c, float (&u)[8]) {
+    const int Hd = H + 1, Wd = W + 1;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) u[e] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int yy = y + t - 1;
+        if (yy < 0 || yy >= Hd) continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int xv = xx + v - 1;
+            if (xv < 0 || xv >= Wd) continue;
+            const float kw = kFir[t] * kFir[v];
+            const float* src = D + (((long)bi * Hd + yy) * Wd + xv) * C + c;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            u[0] = fmaf(kw, a.x, u[0]); u[1] = fmaf(kw, a.y, u[1]); u[2] = fmaf(kw, a.z, u[2]); u[3] = fmaf(kw, a.w, u[3]);
+            u[4] = fmaf(kw, bq.x, u[4]); u[5] = fmaf(kw, bq.y, u[5]); u[6] = fmaf(kw, bq.z, u[6]); u[7] = fmaf(kw, bq.w, u[7]);
+        }
+    }
+}
+__global__ void post_fwd_kernel(const float* __restrict__ D, const float* __restrict__ dm, int lddm, const float* __restrict__ noise,
+                                const float* __restrict__ nw, const float* __restrict__ bias, bf16* __restrict__ x, int b, int H, int W,
+                                int C, int up) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int CG = C / 8;
+    const long total = (long)b * H * W * CG;
+    if (i >= total) return;
+    const int cg = i % CG, c = cg * 8;
+    const long q = i / CG;
+    const int xx = q % W, y = (q / W) % H, bi = q / ((long)W * H);
+    float u[8];
+    if (up) {
+        blur_gather(D, bi, y, xx, H, W, C, c, u);
+    } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(D + q * C + c));
+        const float4 bq = __ldg(reinterpret_cast<const float4*>(D + q * C + c) + 1);
+        u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = bq.x; u[5] = bq.y; u[6] = bq.z; u[7] = bq.w;
+    }
+    const float nz = noise ? nw[0] * noise[q] : 0.f;
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float pre = dm[(long)bi * lddm + c + e] * u[e] + nz + bias[c + e];
+        o[e] = (pre > 0.f ? pre : 0.2f * pre) * kSqrt2;
+    }
+    *reinterpret_cast<uint4*>(x + q * C + c) = pack8(o);
+}
+void k_sg_post_fwd(const float* D, const float* dm, int lddm, const float* noise, const float* nw, const float* bias, bf16* x,
+                   int b, int H, int W, int C, int up, cudaStream_t st) {
+    const long total = (long)b * H * W * (C / 8);
+    post_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(D, dm, lddm, noise, nw, bias, x, b, H, W, C, up); count_launch();
+}
+
+// backward pass 1: g = dx * sqrt2 * lrelu'(x) ; ddm[b,c] += sum_p g * u (u = [blurred] D) ; G = dm * g (bf16)
+__global__ void post_bwd_kernel(const bf16* __restrict__ dx, const bf16* __restrict__ x, const float* __restrict__ D,
+                                const float* __restrict__ dm, int lddm, bf16* __restrict__ G, float* ddm, int H, int W, int C, int up) {
+    __shared__ float red[32][65];
+    const int cg = threadIdx.x, py = threadIdx.y;
+    const int c = blockIdx.y * 64 + cg * 8;
+    const int bi = blockIdx.z;
+    const int HW = H * W;
+    float dmv[8], acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { dmv[e] = dm[(long)bi * lddm + c + e]; acc[e] = 0.f; }
+    for (int p = blockIdx.x * 256 + py; p < min(HW, (int)(blockIdx.x + 1) * 256); p += 32) {
+        const int y = p / W, xx = p % W;
+        const long o = ((long)bi * HW + p) * C + c;
+        float g[8], xv[8], u[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dx + o)), g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + o)), xv);
+        if (up) {
+            blur_gather(D, bi, y, xx, H, W, C, c, u);
+        } else {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(D + o));
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(D + o) + 1);
+            u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = bq.x; u[5] = bq.y; u[6] = bq.z; u[7] = bq.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            g[e] *= (xv[e] > 0.f ? 1.f : 0.2f) * kSqrt2;
+            acc[e] += g[e] * u[e];
+            g[e] *= dmv[e];
+        }
+        *reinterpret_cast<uint4*>(G + o) = pack8(g);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[py][cg * 8 + e] = acc[e];
+    __syncthreads();
+    const int tid = py * 8 + cg;
+    if (tid < 64) {
+        float t = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) t += red[k][tid];
+        atomicAdd(ddm + (long)bi * lddm + blockIdx.y * 64 + tid, t);
+    }
+}
+void k_sg_post_bwd(const bf16* dx, const bf16* x, const float* D, const float* dm, int lddm, bf16* G, float* ddm, int b, int H,
+                   int W, int C, int up, cudaStream_t st) {
+    dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
+    post_bwd_kernel<<<grid, block, 0, st>>>(dx, x, D, dm, lddm, G, ddm, H, W, C, up); count_launch();
+}
+
+// backward pass 2 (up layers): adjoint of the blur: dD'[m, n] = sum_{t,v} G[m - t + 1, n - v + 1] k[t] k[v]
+__global__ void blur_adjoint_kernel(const bf16* __restrict__ G, bf16* __restrict__ dD, int b, int H, int W, int C) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int CG = C / 8, Hd = H + 1, Wd = W + 1;
+    const long total = (long)b * Hd * Wd * CG;
+    if (i >= total) return;
+    const int cg = i % CG, c = cg * 8;
+    const long q = i / CG;
+    const int n = q % Wd, m = (q / Wd) % Hd, bi = q / ((long)Wd * Hd);
+    float u[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) u[e] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int y = m - t + 1;
+        if (y < 0 || y >= H) continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int xx = n - v + 1;
+            if (xx < 0 || xx >= W) continue;
+            float g[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(G + (((long)bi * H + y) * W + xx) * C + c)), g);
+            const float kw = kFir[t] * kFir[v];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) u[e] = fmaf(kw, g[e], u[e]);
+        }
+    }
+    *reinterpret_cast<uint4*>(dD + q * C + c) = pack8(u);
+}
+void k_sg_blur_adjoint(const bf16* G, bf16* dD, int b, int H, int W, int C, cudaStream_t st) {
+    const long total = (long)b * (H + 1) * (W + 1) * (C / 8);
+    blur_adjoint_kernel<<<cdiv(total, 256), 256, 0, st>>>(G, dD, b, H, W, C); count_launch();
+}
+
+// ----------------------------------------------------------------------------- ToRGB
+// weff[b, c, i] = Wr[c, i] * s[b, i] * scale
+__global__ void weff_kernel(const float* Wr, const float* s, int lds, float scale, float* weff, int b, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b * 3 * C) return;
+    const int k = i % C, c = (i / C) % 3, bi = i / (3 * C);
+    weff[i] = Wr[c * C + k] * s[(long)bi * lds + k] * scale;
+}
+void k_sg_weff(const float* Wr, const float* s, int lds, float scale, float* weff, int b, int C, cudaStream_t st) {
+    weff_kernel<<<cdiv((long)b * 3 * C, 256), 256, 0, st>>>(Wr, s, lds, scale, weff, b, C); count_launch();
+}
+// FIR x2 up-sampling of the previous rgb (upfirdn2d up=2, pad (2,1)): out[y] = sum_{t: (y+t) even} prev[(y+t-2)/2] k[t]
+__device__ __forceinline__ float up_gather(const float* __restrict__ prev, int h, int w, int y, int xx) {
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if ((y + t) & 1) continue;
+        const int i = (y + t - 2) / 2;
+        if (y + t - 2 < 0 || i >= h) continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            if ((xx + v) & 1) continue;
+            const int j = (xx + v - 2) / 2;
+            if (xx + v - 2 < 0 || j >= w) continue;
+            acc = fmaf(kFir[t] * kFir[v], prev[i * w + j], acc);
+        }
+    }
+    return acc;
+}
+// rgb[b,c,p] = sum_i weff[b,c,i] x[b,p,i] + bias[c] (+ upsampled previous rgb); one warp per pixel
+__global__ void torgb_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ weff, const float* __restrict__ bias,
+                                 const float* __restrict__ prev, float* __restrict__ rgb, int H, int W, int C) {
+    extern __shared__ float sw[];  // [3][C]
+    const int bi = blockIdx.y;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sw[i] = weff[(long)bi * 3 * C + i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (p >= H * W) return;
+    const bf16* xp = x + ((long)bi * H * W + p) * C;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int k = lane * 2; k < C; k += 64) {
+        const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(xp + k);
+        const float v0 = __low2float(v2), v1 = __high2float(v2);
+        a0 = fmaf(v0, sw[k], a0); a0 = fmaf(v1, sw[k + 1], a0);
+        a1 = fmaf(v0, sw[C + k], a1); a1 = fmaf(v1, sw[C + k + 1], a1);
+        a2 = fmaf(v0, sw[2 * C + k], a2); a2 = fmaf(v1, sw[2 * C + k + 1], a2);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane < 3) {
+        const int y = p / W, xx = p % W;
+        float v = (lane == 0 ? a0 : lane == 1 ? a1 : a2) + bias[lane];
+        if (prev) v += up_gather(prev + ((long)bi * 3 + lane) * (H / 2) * (W / 2), H / 2, W / 2, y, xx);
+        rgb[((long)bi * 3 + lane) * H * W + p] = v;
+    }
+}
+void k_sg_torgb_fwd(const bf16* x, const float* weff, const float* bias, const float* prev, float* rgb, int b, int H, int W, int C,
+                    cudaStream_t st) {
+    dim3 grid(cdiv((long)H * W, 8), b);
+    torgb_fwd_kernel<<<grid, 256, (size_t)3 * C * sizeof(float), st>>>(x, weff, bias, prev, rgb, H, W, C); count_launch();
+}
+// backward: dx[b,p,i] (+)= sum_c drgb[b,c,p] weff[b,c,i] ; dweff[b,c,i] += sum_p drgb[b,c,p] x[b,p,i]
+// block = 8 channel groups x 32 pixels
+__global__ void torgb_bwd_kernel(const float* __restrict__ drgb, const bf16* __restrict__ x, const float* __restrict__ weff,
+                                 bf16* __restrict__ dx, float* dweff, int H, int W, int C, int accumulate) {
+    __shared__ float red[3][32][65];
+    const int cg = threadIdx.x, py = threadIdx.y;
+    const int c = blockIdx.y * 64 + cg * 8;
+    const int bi = blockIdx.z;
+    const int HW = H * W;
+    float w0[8], w1[8], w2[8], a0[8], a1[8], a2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        w0[e] = weff[((long)bi * 3 + 0) * C + c + e]; w1[e] = weff[((long)bi * 3 + 1) * C + c + e]; w2[e] = weff[((long)bi * 3 + 2) * C + c + e];
+        a0[e] = a1[e] = a2[e] = 0.f;
+    }
+    for (int p = blockIdx.x * 256 + py; p < min(HW, (int)(blockIdx.x + 1) * 256); p += 32) {
+        const float g0 = drgb[((long)bi * 3 + 0) * HW + p], g1 = drgb[((long)bi * 3 + 1) * HW + p], g2 = drgb[((long)bi * 3 + 2) * HW + p];
+        const long o = ((long)bi * HW + p) * C + c;
+        float xv[8], d[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + o)), xv);
+        if (accumulate) unpack8(*reinterpret_cast<const uint4*>(dx + o), d);
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            d[e] += g0 * w0[e] + g1 * w1[e] + g2 * w2[e];
+            a0[e] = fmaf(g0, xv[e], a0[e]); a1[e] = fmaf(g1, xv[e], a1[e]); a2[e] = fmaf(g2, xv[e], a2[e]);
+        }
+        *reinterpret_cast<uint4*>(dx + o) = pack8(d);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { red[0][py][cg * 8 + e] = a0[e]; red[1][py][cg * 8 + e] = a1[e]; red[2][py][cg * 8 + e] = a2[e]; }
+    __syncthreads();
+    const int tid = py * 8 + cg;
+    if (tid < 192) {
+        const int cc = tid / 64, k = tid % 64;
+        float t = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) t += red[cc][j][k];
+        atomicAdd(dweff + ((long)bi * 3 + cc) * C + blockIdx.y * 64 + k, t);
+    }
+}
+void k_sg_torgb_bwd(const float* drgb, const bf16* x, const float* weff, bf16* dx, float* dweff, int b, int H, int W, int C,
+                    int accumulate, cudaStream_t st) {
+    dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
+    torgb_bwd_kernel<<<grid, block, 0, st>>>(drgb, x, weff, dx, dweff, H, W, C, accumulate); count_launch();
+}
+// ds[b, i] += scale * sum_c dweff[b,c,i] * Wr[c,i]
+__global__ void weff_bwd_kernel(const float* dweff, const float* Wr, float scale, float* ds, int ldds, int b, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b * C) return;
+    const int k = i % C, bi = i / C;
+    float t = 0.f;
+    for (int c = 0; c < 3; ++c) t += dweff[((long)bi * 3 + c) * C + k] * Wr[c * C + k];
+    ds[(long)bi * ldds + k] += t * scale;
+}
+void k_sg_weff_bwd(const float* dweff, const float* Wr, float scale, float* ds, int ldds, int b, int C, cudaStream_t st) {
+    weff_bwd_kernel<<<cdiv((long)b * C, 256), 256, 0, st>>>(dweff, Wr, scale, ds, ldds, b, C); count_launch();
+}
+// adjoint of the rgb up-sampling: dprev[i, j] = sum_{t,v} drgb[2i + 2 - t, 2j + 2 - v] k[t] k[v]
+__global__ void rgb_up_adjoint_kernel(const float* __restrict__ drgb, float* __restrict__ dprev, int b3, int h, int w) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)b3 * h * w) return;
+    const int j = idx % w, i = (idx / w) % h;
+    const long pl = idx / ((long)w * h);
+    const int H = 2 * h, W = 2 * w;
+    const float* src = drgb + pl * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int y = 2 * i + 2 - t;
+        if (y < 0 || y >= H) continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int xx = 2 * j + 2 - v;
+            if (xx < 0 || xx >= W) continue;
+            acc = fmaf(kFir[t] * kFir[v], src[(long)y * W + xx], acc);
+        }
+    }
+    dprev[idx] = acc;
+}
+void k_sg_rgb_up_adjoint(const float* drgb, float* dprev, int b, int h, int w, cudaStream_t st) {
+    rgb_up_adjoint_kernel<<<cdiv((long)b * 3 * h * w, 256), 256, 0, st>>>(drgb, dprev, b * 3, h, w); count_launch();
+}
+// img = clamp(rgb, -1, 1)
+__global__ void clamp_kernel(const float* rgb, float* img, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) img[i] = fminf(fmaxf(rgb[i], -1.f), 1.f);
+}
+void k_sg_clamp(const float* rgb, float* img, long n, cudaStream_t st) { clamp_kernel<<<cdiv(n, 256), 256, 0, st>>>(rgb, img, n); count_launch(); }
+// drgb = dimg where -1 <= rgb <= 1 else 0
+__global__ void clamp_bwd_kernel(const float* rgb, const float* dimg, float* drgb, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) drgb[i] = (rgb[i] >= -1.f && rgb[i] <= 1.f) ? dimg[i] : 0.f;
+}
+void k_sg_clamp_bwd(const float* rgb, const float* dimg, float* drgb, long n, cudaStream_t st) {
+    clamp_bwd_kernel<<<cdiv(n, 256), 256, 0, st>>>(rgb, dimg, drgb, n); count_launch();
+}
+
+}  // namespace p2l

@@ -1,0 +1,37 @@
+// Launchers of the StyleGAN2 glue kernels (sg2_kernels.cu). Device pointers, asynchronous on `st`.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace p2l {
+typedef __nv_bfloat16 bf16;
+
+// y = act(wscale * x W^T + bias): WT is [in][out]; act 0 none, 1 leaky-relu(0.2)*sqrt2, 2 rsqrt(.+1e-8);
+// square_in squares x first (demodulation)
+void k_fc_fwd(const float* x, int ldx, const float* WT, const float* bias, float wscale, float* y, int ldy, int b, int in,
+              int out, int act, int square_in, cudaStream_t st);
+// dx (+)= wscale * (dy * act'(y)) W, W is [out][in]
+void k_fc_bwd(const float* dy, int lddy, const float* y, int ldy, const float* W, float wscale, float* dx, int lddx, int b,
+              int in, int out, int act, int accumulate, cudaStream_t st);
+void k_pixelnorm_fwd(const float* x, float* y, int b, int n, cudaStream_t st);
+void k_pixelnorm_bwd(const float* x, const float* dy, float* dx, int b, int n, float scale, const float* row_scale, cudaStream_t st);
+void k_demod_bwd(const float* ddm, const float* dm, int lddm, const float* s, int lds, const float* Wsq, float* ds, int ldds,
+                 int b, int Cin, int Cout, cudaStream_t st);
+void k_sg_modulate(const bf16* x, long x_bstride, const float* s, int lds, bf16* A, int b, int H, int W, int C, int up, cudaStream_t st);
+void k_sg_modulate_bwd(const bf16* dA, const bf16* x, long x_bstride, const float* s, int lds, bf16* dx, float* ds, int ldds,
+                       int b, int H, int W, int C, int up, cudaStream_t st);
+void k_sg_post_fwd(const float* D, const float* dm, int lddm, const float* noise, const float* nw, const float* bias, bf16* x,
+                   int b, int H, int W, int C, int up, cudaStream_t st);
+void k_sg_post_bwd(const bf16* dx, const bf16* x, const float* D, const float* dm, int lddm, bf16* G, float* ddm, int b, int H,
+                   int W, int C, int up, cudaStream_t st);
+void k_sg_blur_adjoint(const bf16* G, bf16* dD, int b, int H, int W, int C, cudaStream_t st);
+void k_sg_weff(const float* Wr, const float* s, int lds, float scale, float* weff, int b, int C, cudaStream_t st);
+void k_sg_torgb_fwd(const bf16* x, const float* weff, const float* bias, const float* prev, float* rgb, int b, int H, int W, int C,
+                    cudaStream_t st);
+void k_sg_torgb_bwd(const float* drgb, const bf16* x, const float* weff, bf16* dx, float* dweff, int b, int H, int W, int C,
+                    int accumulate, cudaStream_t st);
+void k_sg_weff_bwd(const float* dweff, const float* Wr, float scale, float* ds, int ldds, int b, int C, cudaStream_t st);
+void k_sg_rgb_up_adjoint(const float* drgb, float* dprev, int b, int h, int w, cudaStream_t st);
+void k_sg_clamp(const float* rgb, float* img, long n, cudaStream_t st);
+void k_sg_clamp_bwd(const float* rgb, const float* dimg, float* drgb, long n, cudaStream_t st);
+}  // namespace p2l

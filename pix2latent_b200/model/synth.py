@@ -131,3 +131,45 @@ def lpips_state_from_package(sd):
         elif k.startswith("net.slice"):
             out[k] = v
     return out
+
+
+def stylegan2_state_dict(size=512, channels=None, seed=0):
+    """Random-init rosinality ``g_ema`` state dict (keys 'style.k.*', 'input.input', 'conv1.*',
+    'to_rgb1.*', 'convs.i.*', 'to_rgbs.i.*'); N(0,1) weights under equalised-lr scaling, non-zero
+    noise strengths / biases, ToRGB weights scaled down so the summed skip image stays in range."""
+    ch = channels or {4: 512, 8: 512, 16: 512, 32: 512, 64: 512, 128: 256, 256: 128, 512: 64, 1024: 32}
+    g = torch.Generator().manual_seed(2000 + seed)
+    sd = {}
+
+    def randn(*s):
+        return torch.randn(*s, generator=g)
+
+    for k in range(1, 9):
+        sd["style.%d.weight" % k] = randn(512, 512) / 0.01
+        sd["style.%d.bias" % k] = randn(512)
+    sd["input.input"] = randn(1, ch[4], 4, 4)
+
+    def styled(pre, cin, cout):
+        sd[pre + ".conv.weight"] = randn(1, cout, cin, 3, 3)
+        sd[pre + ".conv.modulation.weight"] = randn(cin, 512)
+        sd[pre + ".conv.modulation.bias"] = torch.ones(cin)
+        sd[pre + ".noise.weight"] = 0.1 * randn(1)
+        sd[pre + ".activate.bias"] = 0.1 * randn(cout)
+
+    def torgb(pre, cin):
+        sd[pre + ".conv.weight"] = 0.25 * randn(1, 3, cin, 1, 1)
+        sd[pre + ".conv.modulation.weight"] = randn(cin, 512)
+        sd[pre + ".conv.modulation.bias"] = torch.ones(cin)
+        sd[pre + ".bias"] = 0.1 * randn(1, 3, 1, 1)
+
+    styled("conv1", ch[4], ch[4])
+    torgb("to_rgb1", ch[4])
+    log_size = size.bit_length() - 1
+    cin = ch[4]
+    for i in range(3, log_size + 1):
+        cout = ch[2 ** i]
+        styled("convs.%d" % (2 * (i - 3)), cin, cout)
+        styled("convs.%d" % (2 * (i - 3) + 1), cout, cout)
+        torgb("to_rgbs.%d" % (i - 3), cout)
+        cin = cout
+    return sd

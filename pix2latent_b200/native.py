@@ -26,6 +26,11 @@ class BigGANConfigC(C.Structure):
     ]
 
 
+class SG2ConfigC(C.Structure):
+    """Mirror of ``p2l_sg2_config``."""
+    _fields_ = [("size", C.c_int), ("style_dim", C.c_int), ("n_mlp", C.c_int), ("channels", C.c_int * 9)]
+
+
 def declare(L):
     vp, ci, cf, cl = C.c_void_p, C.c_int, C.c_float, C.c_long
     pp = C.POINTER(C.c_void_p)
@@ -54,6 +59,14 @@ def declare(L):
         "p2l_lpips_flops": (C.c_double, [vp, ci, ci, ci, ci]),
         "p2l_lpips_launches": (ci, [vp, ci]),
         "p2l_biggan_step": (ci, [vp, vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]),
+        "p2l_sg2_create": (ci, [vp, C.POINTER(SG2ConfigC), pp]),
+        "p2l_sg2_set_tensor": (ci, [vp, C.c_char_p, vp, cl]),
+        "p2l_sg2_finalize": (ci, [vp]),
+        "p2l_sg2_destroy": (None, [vp]),
+        "p2l_sg2_num_noise_layers": (ci, [vp]),
+        "p2l_sg2_forward": (ci, [vp, ci, vp, vp, vp, vp]),
+        "p2l_sg2_backward": (ci, [vp, ci, vp, vp, vp]),
+        "p2l_sg2_step": (ci, [vp, vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp]),
         "p2l_profile_enable": (None, [ci]),
         "p2l_profile_read": (ci, [C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_double)]),
     }
@@ -70,7 +83,8 @@ EXPORTED_SYMBOLS = [
     "p2l_biggan_launches", "p2l_lpips_create", "p2l_lpips_set_tensor", "p2l_lpips_finalize",
     "p2l_lpips_destroy", "p2l_target_create", "p2l_target_destroy", "p2l_loss_forward",
     "p2l_loss_backward", "p2l_lpips_flops", "p2l_lpips_launches", "p2l_biggan_step",
-    "p2l_profile_enable", "p2l_profile_read",
+    "p2l_profile_enable", "p2l_profile_read", "p2l_sg2_create", "p2l_sg2_set_tensor", "p2l_sg2_finalize",
+    "p2l_sg2_destroy", "p2l_sg2_num_noise_layers", "p2l_sg2_forward", "p2l_sg2_backward", "p2l_sg2_step",
     "p2l_debug_conv", "p2l_debug_set_option", "p2l_debug_get_option", "p2l_debug_profile_get",
 ]
 
@@ -162,6 +176,78 @@ class NativeBigGAN:
 
     def device_bytes(self):
         return int(_lib.lib().p2l_biggan_device_bytes(self.h))
+
+
+class NativeStyleGAN2:
+    """Owns a ``p2l_sg2`` handle. ``state_dict`` uses rosinality's ``g_ema`` keys."""
+
+    def __init__(self, size, channels, state_dict, device=None):
+        L = _lib.lib()
+        self.ctx, self.device = context(device)
+        cfg = SG2ConfigC()
+        cfg.size, cfg.style_dim, cfg.n_mlp = int(size), 512, 8
+        for i in range(9):
+            cfg.channels[i] = int(channels.get(2 ** (i + 2), 0))
+        self.size = int(size)
+        self.h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(L.p2l_sg2_create(self.ctx, C.byref(cfg), C.byref(self.h)))
+            for k, v in state_dict.items():
+                if k.startswith("noises.") or k.endswith("blur.kernel") or k.endswith("upsample.kernel"):
+                    continue
+                t = v.detach().float().contiguous()
+                _lib.check(L.p2l_sg2_set_tensor(self.h, k.encode(), C.c_void_p(t.data_ptr()), t.numel()))
+            _lib.check(L.p2l_sg2_finalize(self.h))
+        self.num_layers = int(L.p2l_sg2_num_noise_layers(self.h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.lib().p2l_sg2_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def noise_shapes(self, b):
+        return [(b, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2)) for i in range(self.num_layers)]
+
+    def _noise_ptrs(self, noises, b):
+        if noises is None:
+            return None, None
+        assert len(noises) == self.num_layers, "expected %d noise tensors" % self.num_layers
+        keep = [_f32c(n) for n in noises]
+        for n, shp in zip(keep, self.noise_shapes(b)):
+            assert tuple(n.shape) == shp, "noise shape %s != %s" % (tuple(n.shape), shp)
+        arr = (C.c_void_p * self.num_layers)(*[n.data_ptr() for n in keep])
+        return arr, keep
+
+    def forward(self, z, noises=None):
+        z = _f32c(z)
+        b = z.shape[0]
+        img = torch.empty(b, 3, self.size, self.size, device=z.device, dtype=torch.float32)
+        arr, keep = self._noise_ptrs(noises, b)
+        _lib.check(_lib.lib().p2l_sg2_forward(self.h, b, _lib.ptr(z), arr, _lib.ptr(img), _lib.current_stream()))
+        return img
+
+    def backward(self, b, dimg):
+        dimg = _f32c(dimg)
+        dz = torch.empty(b, 512, device=dimg.device, dtype=torch.float32)
+        _lib.check(_lib.lib().p2l_sg2_backward(self.h, b, _lib.ptr(dimg), _lib.ptr(dz), _lib.current_stream()))
+        return dz
+
+
+def sg2_step(gen, lp, tgt, z, noises, want_grad, grad_scale, want_img=True, dloss=None):
+    """Fused StyleGAN2 inner step: returns (loss[b], dz, img)."""
+    z = _f32c(z)
+    b = z.shape[0]
+    loss = torch.empty(b, device=z.device, dtype=torch.float32)
+    dz = torch.empty_like(z) if want_grad else None
+    img = torch.empty(b, 3, gen.size, gen.size, device=z.device, dtype=torch.float32) if want_img else None
+    arr, keep = gen._noise_ptrs(noises, b)
+    _lib.check(_lib.lib().p2l_sg2_step(gen.h, lp.h, tgt.h, b, _lib.ptr(z), arr, int(want_grad), float(grad_scale),
+                                       _lib.ptr(None if dloss is None else _f32c(dloss)), _lib.ptr(loss), _lib.ptr(dz),
+                                       _lib.ptr(img), _lib.current_stream()))
+    return loss, dz, img
 
 
 class NativeLPIPS:

@@ -108,10 +108,55 @@ def _step_native(model, vars, loss_fn, optimize, max_batch_size):
     return img, list(loss.cpu().numpy()), {}
 
 
+def _native_sg2_pair(model, vars, loss_fn):
+    from ..loss_functions import _NativeLoss
+    from ..model.stylegan2 import StyleGAN2
+    m = _unwrap(model)
+    if not (isinstance(m, StyleGAN2) and isinstance(loss_fn, _NativeLoss) and m.native is not None):
+        return False
+    if any(k not in ("input", "output", "opt", "num_samples") for k in vars.keys()):
+        return False
+    if set(vars.input.keys()) != {"z"}:
+        return False
+    outs = set(vars.output.keys()) if "output" in vars else set()
+    return "target" in outs and outs <= {"target", "weight", "loss_mask"}
+
+
+def _step_native_sg2(model, vars, loss_fn, optimize, max_batch_size):
+    """StyleGAN2 (z search): chunk by chunk as the reference does, because hooks (NormalPerturb) and the
+    per-layer noise both draw from torch's RNG between chunks — the draw ORDER is part of the behaviour."""
+    from .. import native
+    m = _unwrap(model)
+    first = {k: v.data[0] for k, v in vars.output.items()}
+    tgt = loss_fn.prepared_target(first["target"], first.get("weight"), first.get("loss_mask"))
+    outs, losses = [], []
+    for chunk in split_vars(vars, size=max_batch_size):
+        if optimize:
+            chunk.opt.zero_grad()
+        _run_hooks(chunk.input)
+        z_list = chunk.input.z.data
+        with torch.no_grad():
+            z = torch.stack(z_list)
+        noises = m.draw_noise(z.shape[0], z.device)
+        loss, dz, img = native.sg2_step(m.native, loss_fn.native_lpips(), tgt, z, noises, want_grad=optimize,
+                                        grad_scale=1.0 / chunk.num_samples)
+        if optimize:
+            for i, t in enumerate(z_list):
+                if t.requires_grad:
+                    t.grad = dz[i]
+            chunk.opt.step()
+            chunk.opt.zero_grad()
+        outs.extend(img)
+        losses.extend(loss.cpu().numpy())
+    return torch.stack(outs), losses, {}
+
+
 def step(model, vars, loss_fn, optimize=True, max_batch_size=9):
     """One evaluation (and, with ``optimize``, one gradient update) of every sample in ``vars``.
 
     Returns ``(outs [N,3,H,W], indiv_losses list[N], {})`` as the reference does."""
     if _native_pair(model, vars, loss_fn):
         return _step_native(model, vars, loss_fn, optimize, max_batch_size)
+    if _native_sg2_pair(model, vars, loss_fn):
+        return _step_native_sg2(model, vars, loss_fn, optimize, max_batch_size)
     return _step_autograd(model, vars, loss_fn, optimize, max_batch_size)
