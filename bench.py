@@ -74,7 +74,7 @@ class ClockSampler:
                     self.rows.append(p)
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1)
 
     def __enter__(self):
         self.t.start()
@@ -264,7 +264,7 @@ def run_native(args, rank, world, local_rank):
     alg_flops = FLOP_PER_UNIT * n * args.steps
     achieved = alg_flops / (conv_ms / 1e3) / 1e12
     roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "conv_gemm_kernel (tcgen05.mma kind::f16, bf16 operands, fp32 accumulate)",
+            "traffic": None, "kernel": "conv_gemm_kernel (tcgen05.mma kind::f16, 16-bit operands, fp32 accumulate)",
             "launches_per_step": conv_n / args.steps, "kernel_ms_per_step": conv_ms / args.steps,
             "kernel_share_of_step": (conv_ms / args.steps) / (ms / args.steps),
             "flops_per_launch_algorithmic": alg_flops / conv_n, "avg_launch_ms": conv_ms / conv_n,
@@ -284,7 +284,7 @@ def run_native(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": "fp16" if native.act_dtype() == torch.float16 else "bf16", "data": "synthetic",
         "config": {"workload": "BigGAN-deep-256 BasinCMA inner step (generator fwd + L1+10*LPIPS-alex + bwd to z,c), "
                                "population 18 per GPU, 256x256, grad scale 1/9 (BASELINE.json configs[1]; configs[3] at N=8)",
                    "population_per_gpu": n, "global_population": n * world, "resolution": 256, "lpips_net": "alex",
@@ -307,7 +307,7 @@ def run_native(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

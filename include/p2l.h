@@ -45,6 +45,8 @@ typedef struct p2l_biggan_config {
 
 const char* p2l_last_error(void);
 int p2l_version(void);
+/* 16-bit storage / tensor-core operand type the library was built with: 0 = bfloat16, 1 = fp16 */
+int p2l_act_dtype(void);
 /* cumulative number of CUDA kernels this library has launched in this process */
 long p2l_launch_count(void);
 

@@ -24,6 +24,7 @@ struct p2l_sg2 { SG2 g; };
     }
 
 P2L_EXPORT int p2l_version(void) { return 1; }
+P2L_EXPORT int p2l_act_dtype(void) { return P2L_ACT_FP16 ? 1 : 0; }
 P2L_EXPORT long p2l_launch_count(void) { return launch_count(); }
 
 P2L_EXPORT int p2l_create(int device, p2l_ctx** out) {

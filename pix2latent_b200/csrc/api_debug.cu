@@ -16,17 +16,17 @@ P2L_EXPORT int p2l_debug_conv(const p2l_conv_args* a, void* cuda_stream) {
     d.NI = a->NI; d.H = a->H; d.W = a->W; d.BN = a->BN; d.mode = a->mode;
     ConvGemmParams& e = d.epi;
     e.alpha = a->alpha; e.alpha_ptr = a->alpha_ptr; e.bias = a->bias;
-    e.resid = static_cast<const __nv_bfloat16*>(a->resid); e.resid_C = a->resid_C; e.resid_shift = a->resid_shift;
-    e.raw = static_cast<__nv_bfloat16*>(a->raw); e.raw_C = a->raw_C;
+    e.resid = static_cast<const act_t*>(a->resid); e.resid_C = a->resid_C; e.resid_shift = a->resid_shift;
+    e.raw = static_cast<act_t*>(a->raw); e.raw_C = a->raw_C;
     e.raw_f32 = a->raw_f32; e.raw_f32_C = a->raw_f32_C;
     e.aff_a = a->aff_a; e.aff_s = a->aff_s; e.aff_stride = a->aff_stride; e.relu = a->relu;
-    e.act = static_cast<__nv_bfloat16*>(a->act); e.act_C = a->act_C; e.act_up = a->act_up;
-    e.act_lo = static_cast<__nv_bfloat16*>(a->act_lo); e.img_nchw = a->img_nchw;
-    e.saved = static_cast<const __nv_bfloat16*>(a->saved); e.saved_C = a->saved_C;
+    e.act = static_cast<act_t*>(a->act); e.act_C = a->act_C; e.act_up = a->act_up;
+    e.act_lo = static_cast<act_t*>(a->act_lo); e.img_nchw = a->img_nchw;
+    e.saved = static_cast<const act_t*>(a->saved); e.saved_C = a->saved_C;
     e.stat0 = a->stat0; e.stat1 = a->stat1; e.stat_stride = a->stat_stride;
-    e.addin = static_cast<const __nv_bfloat16*>(a->addin); e.addin_C = a->addin_C;
+    e.addin = static_cast<const act_t*>(a->addin); e.addin_C = a->addin_C;
     e.addin_climit = a->addin_climit; e.addin_pool = a->addin_pool;
-    e.dx = static_cast<__nv_bfloat16*>(a->dx); e.dx_C = a->dx_C;
+    e.dx = static_cast<act_t*>(a->dx); e.dx_C = a->dx_C;
     e.dx_f32 = a->dx_f32; e.dx_f32_C = a->dx_f32_C;
     ConvOp op;
     if (conv_op_build(&op, d)) return -1;

@@ -23,24 +23,24 @@ struct BigGANPlan {
     float *cond = nullptr, *a = nullptr, *s = nullptr, *S0 = nullptr, *S1 = nullptr, *G = nullptr, *dcond = nullptr,
           *dh0 = nullptr, *ones = nullptr;
     struct BB {
-        __nv_bfloat16 *in_raw, *in_act, *t1_lo, *t1, *t2, *t3, *out_raw, *out_act;
+        act_t *in_raw, *in_act, *t1_lo, *t1, *t2, *t3, *out_raw, *out_act;
         ConvOp f[4], d[4];
     };
     std::vector<BB> bb;
     // attention
-    __nv_bfloat16 *qkv = nullptr, *phi_p = nullptr, *phiT = nullptr, *g_p = nullptr, *gT = nullptr, *P = nullptr,
+    act_t *qkv = nullptr, *phi_p = nullptr, *phiT = nullptr, *g_p = nullptr, *gT = nullptr, *P = nullptr,
                   *O = nullptr, *attn_raw = nullptr, *attn_act = nullptr;
     unsigned char *idx_phi = nullptr, *idx_g = nullptr;
     float* S = nullptr;
-    __nv_bfloat16 *dO = nullptr, *dOT = nullptr, *dS = nullptr, *dST = nullptr, *PT = nullptr, *thetaT = nullptr,
+    act_t *dO = nullptr, *dOT = nullptr, *dS = nullptr, *dST = nullptr, *PT = nullptr, *thetaT = nullptr,
                   *dqkv = nullptr, *dphi_p = nullptr, *dg_p = nullptr;
     ConvOp a_qkv, a_s, a_o, a_out, ad_out, ad_p, ad_theta, ad_phi, ad_g, ad_qkv;
     // image
     ConvOp f_rgb, d_rgb;
-    __nv_bfloat16* col_rgb = nullptr;
+    act_t* col_rgb = nullptr;
     float* img = nullptr;  // internal copy target when the caller passes none
     // gradient ping-pong
-    __nv_bfloat16 *dhA = nullptr, *dhB = nullptr, *g1 = nullptr, *g2 = nullptr, *g3 = nullptr, *dh_pool = nullptr;
+    act_t *dhA = nullptr, *dhB = nullptr, *g1 = nullptr, *g2 = nullptr, *g3 = nullptr, *dh_pool = nullptr;
     double flops_fwd = 0, flops_bwd = 0;
     int launches_fwd = 0, launches_bwd = 0;
     bool forward_done = false;
@@ -218,7 +218,7 @@ int BigGAN::finalize() {
         std::vector<float> b3(bsv->begin(), bsv->begin() + 3);
         brgb = upload(weights, b3);
         // dgrad operand for the im2col'd gradient: [C_last][64], k = (r*3+s)*3 + o -> W[o, c, r, s]
-        std::vector<__nv_bfloat16> t((size_t)C_last * 64, host_f2bf(0.f));
+        std::vector<act_t> t((size_t)C_last * 64, host_f2bf(0.f));
         for (int c = 0; c < C_last; ++c)
             for (int r = 0; r < 3; ++r)
                 for (int s2 = 0; s2 < 3; ++s2)
@@ -268,7 +268,7 @@ BigGANPlan* BigGAN::plan(int b) {
     BigGANPlan& P = *pp;
     P.b = b;
     Arena& ar = P.ar;
-    typedef __nv_bfloat16 bf;
+    typedef act_t bf;
     P.cond = ar.alloc<float>((size_t)b * cdim);
     P.a = ar.alloc<float>((size_t)b * C_all);
     P.s = ar.alloc<float>((size_t)b * C_all);
@@ -281,7 +281,7 @@ BigGANPlan* BigGAN::plan(int b) {
     P.bb.resize(nL);
     size_t max_dh = 0, max_g = 0;
     // activations
-    __nv_bfloat16 *cur_raw = ar.alloc<bf>((size_t)b * genz_J), *cur_act = ar.alloc<bf>((size_t)b * genz_J);
+    act_t *cur_raw = ar.alloc<bf>((size_t)b * genz_J), *cur_act = ar.alloc<bf>((size_t)b * genz_J);
     for (int i = 0; i < nL; ++i) {
         const Block& bl = blocks[i];
         BigGANPlan::BB& B = P.bb[i];
@@ -370,8 +370,8 @@ BigGANPlan* BigGAN::plan(int b) {
             if (build(&B.f[3], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
         }
         // ---- backward ops (dh_out lives in dhA when (nL-1-i) is even, dh_in goes to the other)
-        __nv_bfloat16* dh_out = ((nL - 1 - i) % 2 == 0) ? P.dhA : P.dhB;
-        __nv_bfloat16* dh_in = ((nL - 1 - i) % 2 == 0) ? P.dhB : P.dhA;
+        act_t* dh_out = ((nL - 1 - i) % 2 == 0) ? P.dhA : P.dhB;
+        act_t* dh_in = ((nL - 1 - i) % 2 == 0) ? P.dhB : P.dhA;
         {   // d3: dh_out -> g3 (through bn_3/relu)
             OpB o(dh_out, b, Ho, Ho, bl.out, 0, bl.out, bl.wt[3], bl.mid, 1, EPI_BWD);
             ConvGemmParams& e = o.d.epi;
@@ -443,7 +443,7 @@ BigGANPlan* BigGAN::plan(int b) {
         P.dphi_p = ar.alloc<bf>((size_t)b * Nk * dq);
         P.dg_p = ar.alloc<bf>((size_t)b * Nk * dv);
         if (ar.failed) return nullptr;
-        const __nv_bfloat16* x_raw = P.bb[ap - 1].out_raw;  // attention input (previous block's raw output)
+        const act_t* x_raw = P.bb[ap - 1].out_raw;  // attention input (previous block's raw output)
         const int Hk = H / 2;
         P.launches_fwd += 3;  // 2 pools + softmax
         P.launches_bwd += 8;  // transposes x4, softmax bwd, pool bwd x2 ... (counted below as launched)
@@ -474,11 +474,11 @@ BigGANPlan* BigGAN::plan(int b) {
             if (build(&P.a_out, o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
         }
         // backward: gradient wrt attention output arrives in the buffer block `ap` wrote as dh_in
-        __nv_bfloat16* dh_attn_out = ((nL - 1 - ap) % 2 == 0) ? P.dhB : P.dhA;
+        act_t* dh_attn_out = ((nL - 1 - ap) % 2 == 0) ? P.dhB : P.dhA;
         // block ap-1 reads its dh_out from the same ping-pong buffer block ap wrote dh_in to, so the
         // attention input gradient is produced in place (each thread reads its addin elements
         // before overwriting exactly those elements).
-        __nv_bfloat16* dh_attn_in = dh_attn_out;
+        act_t* dh_attn_in = dh_attn_out;
         {   // dO = gamma * dh W_o
             OpB o(dh_attn_out, b, H, H, C, 0, C, attn.wo_t, dv, 1, EPI_BWD);
             o.d.epi.alpha_ptr = attn.gamma; o.d.epi.dx = P.dO; o.d.epi.dx_C = dv;
@@ -593,7 +593,7 @@ int BigGAN::backward(int b, const float* dimg, float* dz, float* dc, cudaStream_
     P2L_CUDA_CHECK(cudaMemsetAsync(P.S1, 0, (size_t)b * C_all * sizeof(float), st));
     P2L_CUDA_CHECK(cudaMemsetAsync(P.dcond, 0, (size_t)b * cdim * sizeof(float), st));
     // image -> last block output
-    k_im2col_rgb_bwd(dimg, P.img, P.col_rgb, b, R, R, 64, st);
+    k_im2col_rgb_bwd(dimg, P.img, P.col_rgb, b, R, R, 64, grad_scale(), st);  // 16-bit gradients carry grad_scale() from here ...
     if (conv_op_launch(P.d_rgb, st)) return -1;
     for (int i = nL - 1; i >= 0; --i) {
         const Block& bl = blocks[i];
@@ -607,7 +607,7 @@ int BigGAN::backward(int b, const float* dimg, float* dz, float* dc, cudaStream_
                               bl.Hin, bl.mid, st);
         }
         if (bl.up) {
-            __nv_bfloat16* dh_out = ((nL - 1 - i) % 2 == 0) ? P.dhA : P.dhB;
+            act_t* dh_out = ((nL - 1 - i) % 2 == 0) ? P.dhA : P.dhB;
             k_pool2x2_sum(dh_out, bl.out, P.dh_pool, b, bl.Hin, bl.Hin, bl.out, st);
         }
         if (conv_op_launch(B.d[0], st)) return -1;
@@ -633,7 +633,7 @@ int BigGAN::backward(int b, const float* dimg, float* dz, float* dc, cudaStream_
     k_bn_grad_finalize(P.S0, P.S1, P.a, P.s, mean, inv_std, P.G, b, C_cond, C_all, st);
     k_dcond_accum(P.G, 2 * C_cond, Wcat, P.dcond, b, 2 * C_cond, cdim, st);
     k_dcond_accum(P.dh0, genz_J, genz_W, P.dcond, b, genz_J, cdim, st);
-    k_split_dcond(P.dcond, dz, dc, b, cfg.z_dim, cfg.class_embed_dim, scale, row_scale, st);
+    k_split_dcond(P.dcond, dz, dc, b, cfg.z_dim, cfg.class_embed_dim, scale / grad_scale(), row_scale, st);  // ... to here
     return 0;
 }
 

@@ -32,18 +32,18 @@ struct BigGAN {
         int in, out, mid, Hin, Hout;
         bool up;
         int bn[4];
-        __nv_bfloat16 *w[4], *wt[4];
+        act_t *w[4], *wt[4];
         float* bias[4];
     };
     std::vector<Block> blocks;
     struct Attn {
         int C = 0, H = 0, dq = 0, dv = 0;
-        __nv_bfloat16 *wqkv = nullptr, *wqkv_t = nullptr, *wo = nullptr, *wo_t = nullptr;
+        act_t *wqkv = nullptr, *wqkv_t = nullptr, *wo = nullptr, *wo_t = nullptr;
         float* gamma = nullptr;
     } attn;
     int final_bn = -1;
     int C_last = 0, H_out = 0;
-    __nv_bfloat16 *wrgb = nullptr, *wrgb_t = nullptr;
+    act_t *wrgb = nullptr, *wrgb_t = nullptr;
     float* brgb = nullptr;
 
     std::map<int, std::shared_ptr<BigGANPlan>> plans;

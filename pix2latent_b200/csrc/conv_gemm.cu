@@ -25,14 +25,18 @@ void count_launch() { ++g_launches; }
 long launch_count() { return g_launches; }
 
 static int g_tma_out = 1;
+static int g_grad_scale = (int)kGradScale;
+float grad_scale() { return (float)g_grad_scale; }
 static int g_halo = 0, g_halo_bo = 0;  // halo patches: correct but no gain at these shapes (profiles/r1_notes.md)
 void set_option(const char* key, int value) {
     if (!std::strcmp(key, "halo")) g_halo = value;
+    else if (!std::strcmp(key, "grad_scale")) g_grad_scale = value > 0 ? value : 1;
     else if (!std::strcmp(key, "halo_bo")) g_halo_bo = value;
     else if (!std::strcmp(key, "tma_out")) g_tma_out = value;
 }
 int get_option(const char* key) {
     if (!std::strcmp(key, "halo")) return g_halo;
+    if (!std::strcmp(key, "grad_scale")) return g_grad_scale;
     if (!std::strcmp(key, "halo_bo")) return g_halo_bo;
     if (!std::strcmp(key, "tma_out")) return g_tma_out;
     return -1;
@@ -113,7 +117,7 @@ static int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuint64
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return -1;
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims,
+    CUresult r = fn(m, P2L_TMAP_DTYPE, rank, const_cast<void*>(ptr), dims,
                     strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

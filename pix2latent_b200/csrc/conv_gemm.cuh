@@ -55,9 +55,9 @@ struct ConvGemmParams {
     float alpha;             // scale on the accumulator
     const float* alpha_ptr;  // optional device scalar multiplied into alpha (attention gamma); both modes
     const float* bias;       // [Cout] or null
-    const __nv_bfloat16* resid;  // skip input, NHWC [NI, H>>resid_shift, W>>resid_shift, resid_C]
+    const act_t* resid;  // skip input, NHWC [NI, H>>resid_shift, W>>resid_shift, resid_C]
     int resid_C, resid_shift;
-    __nv_bfloat16* raw;  // raw (pre-affine) output, NHWC, channel stride raw_C
+    act_t* raw;  // raw (pre-affine) output, NHWC, channel stride raw_C
     int raw_C;
     float* raw_f32;  // same, fp32 (attention logits)
     int raw_f32_C;
@@ -65,20 +65,20 @@ struct ConvGemmParams {
     const float* aff_s;
     int aff_stride;
     int relu;
-    __nv_bfloat16* act;  // activated output, NHWC, channel stride act_C
+    act_t* act;  // activated output, NHWC, channel stride act_C
     int act_C;
     int act_up;             // write act to the 2x nearest-upsampled grid [NI, 2H, 2W, act_C]
-    __nv_bfloat16* act_lo;  // with act_up: also keep the low-res copy (needed by backward)
+    act_t* act_lo;  // with act_up: also keep the low-res copy (needed by backward)
     float* img_nchw;        // tanh(v) for c < Cout written as fp32 NCHW [NI, Cout, H, W]
     // ---- epilogue, backward
-    const __nv_bfloat16* saved;  // forward activation of the layer being differentiated
+    const act_t* saved;  // forward activation of the layer being differentiated
     int saved_C;
     float* stat0;  // += sum_pix dpre          [NI, stat_stride]
     float* stat1;  // += sum_pix dpre * saved  [NI, stat_stride]
     int stat_stride;
-    const __nv_bfloat16* addin;  // gradient arriving through the skip connection
+    const act_t* addin;  // gradient arriving through the skip connection
     int addin_C, addin_climit, addin_pool;  // pool: sum the 2x2 block of a [NI,2H,2W,addin_C] map
-    __nv_bfloat16* dx;
+    act_t* dx;
     int dx_C;
     float* dx_f32;  // optional fp32 copy (used for the latent-side tensors)
     int dx_f32_C;

@@ -45,6 +45,8 @@ int num_sms();
 void count_launch();  // every kernel launch of the library is counted (bench.py gpu_launches)
 long launch_count();
 // tuning / experiment switches: "halo" (0 off, 10, 16), "halo_bo" (0/1)
+// Static loss scale carried by 16-bit gradients (act_type.h); default kGradScale, option "grad_scale".
+float grad_scale();
 void set_option(const char* key, int value);
 int get_option(const char* key);
 void profile_enable(int on);

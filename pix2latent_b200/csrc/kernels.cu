@@ -20,8 +20,8 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ float b2f(bf16 x) { return __bfloat162float(x); }
-__device__ __forceinline__ bf16 f2b(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ float b2f(bf16 x) { return a2f(x); }
+__device__ __forceinline__ bf16 f2b(float x) { return f2a(x); }
 
 // ============================================================================= latent side
 __global__ void concat_cond_kernel(const float* z, const float* c, float* cond, int b, int zd, int cd) {
@@ -236,15 +236,10 @@ void k_fill_f32(float* p, float v, long n, cudaStream_t st) { fill_kernel<<<cdiv
 // ============================================================================= BigGAN glue
 // thread = 8 channels (one uint4) of one low-res pixel; block = 8 channel-groups x 32 pixels
 __device__ __forceinline__ void unpack8(const uint4 t, float (&f)[8]) {
-    f[0] = __uint_as_float(t.x << 16); f[1] = __uint_as_float(t.x & 0xFFFF0000u);
-    f[2] = __uint_as_float(t.y << 16); f[3] = __uint_as_float(t.y & 0xFFFF0000u);
-    f[4] = __uint_as_float(t.z << 16); f[5] = __uint_as_float(t.z & 0xFFFF0000u);
-    f[6] = __uint_as_float(t.w << 16); f[7] = __uint_as_float(t.w & 0xFFFF0000u);
+    f[0] = act_lo(t.x); f[1] = act_hi(t.x); f[2] = act_lo(t.y); f[3] = act_hi(t.y);
+    f[4] = act_lo(t.z); f[5] = act_hi(t.z); f[6] = act_lo(t.w); f[7] = act_hi(t.w);
 }
-__device__ __forceinline__ uint32_t pk2(float a, float b) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&t);
-}
+__device__ __forceinline__ uint32_t pk2(float a, float b) { return pack_act(a, b); }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return make_uint4(pk2(f[0], f[1]), pk2(f[2], f[3]), pk2(f[4], f[5]), pk2(f[6], f[7]));
 }
@@ -492,7 +487,7 @@ void k_im2col_alex1(const float* img, bf16* col, int b, int H, int W, int Ho, in
 }
 
 __global__ void col2im_alex1_kernel(const bf16* __restrict__ dcol, float* __restrict__ dimg, int b, int H, int W,
-                                    int Ho, int Wo, int Kp, int accumulate) {
+                                    int Ho, int Wo, int Kp, int accumulate, float unscale) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long total = (long)b * 3 * H * W;
     if (i >= total) return;
@@ -509,13 +504,13 @@ __global__ void col2im_alex1_kernel(const bf16* __restrict__ dcol, float* __rest
             acc += b2f(dcol[(((long)bi * Ho + oy) * Wo + ox) * Kp + (c * 11 + r) * 11 + s]);
         }
     }
-    acc /= kLpipsScale[c];
+    acc *= unscale / kLpipsScale[c];
     dimg[i] = accumulate ? dimg[i] + acc : acc;
 }
 void k_col2im_alex1(const bf16* dcol, float* dimg, int b, int H, int W, int Ho, int Wo, int Kp, int accumulate,
-                    cudaStream_t st) {
+                    float unscale, cudaStream_t st) {
     const long total = (long)b * 3 * H * W;
-    col2im_alex1_kernel<<<cdiv(total, 256), 256, 0, st>>>(dcol, dimg, b, H, W, Ho, Wo, Kp, accumulate); count_launch();
+    col2im_alex1_kernel<<<cdiv(total, 256), 256, 0, st>>>(dcol, dimg, b, H, W, Ho, Wo, Kp, accumulate, unscale); count_launch();
 }
 
 __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, unsigned char* __restrict__ idx,
@@ -609,7 +604,7 @@ void k_maxpool_bwd(const bf16* dout, const unsigned char* idx, const bf16* x, co
 // one warp per feature pixel; block = 8 warps; one atomic per block for the loss
 __global__ void lpips_dist_kernel(const bf16* __restrict__ f, const float* __restrict__ t,
                                   const float* __restrict__ lin, const float* __restrict__ wadj, float* loss,
-                                  bf16* __restrict__ g, int HW, int C) {
+                                  bf16* __restrict__ g, int HW, int C, float gscale) {
     __shared__ float part[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bi = blockIdx.y;
@@ -646,7 +641,7 @@ __global__ void lpips_dist_kernel(const bf16* __restrict__ f, const float* __res
                 const float diff = v * inv - tp[c];
                 const float e = 2.f * lin[c] * diff;
                 const float df = e * inv - k2 * v;
-                gp[c] = f2b(v > 0.f ? wv * df : 0.f);
+                gp[c] = f2b(v > 0.f ? wv * gscale * df : 0.f);
             }
         }
     }
@@ -660,9 +655,9 @@ __global__ void lpips_dist_kernel(const bf16* __restrict__ f, const float* __res
     }
 }
 void k_lpips_dist(const bf16* f, const float* t, const float* lin, const float* wadj, float* loss, bf16* g, int b,
-                  int HW, int C, cudaStream_t st) {
+                  int HW, int C, float gscale, cudaStream_t st) {
     dim3 grid(cdiv(HW, 8), b);
-    lpips_dist_kernel<<<grid, 256, 0, st>>>(f, t, lin, wadj, loss, g, HW, C); count_launch();
+    lpips_dist_kernel<<<grid, 256, 0, st>>>(f, t, lin, wadj, loss, g, HW, C, gscale); count_launch();
 }
 
 __global__ void lpips_normalize_kernel(const bf16* __restrict__ f, float* __restrict__ t, int HW, int C) {
@@ -789,7 +784,7 @@ void k_scale_rows(float* x, const float* scale, int b, long n, cudaStream_t st) 
 }
 
 __global__ void im2col_rgb_bwd_kernel(const float* __restrict__ dimg, const float* __restrict__ img,
-                                      bf16* __restrict__ col, int b, int H, int W, int Kp) {
+                                      bf16* __restrict__ col, int b, int H, int W, int Kp, float scale) {
     // thread = one pixel: 27 live values (k = (r*3+s)*3 + o), one full 128-byte row written
     const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long total = (long)b * H * W;
@@ -809,7 +804,7 @@ __global__ void im2col_rgb_bwd_kernel(const float* __restrict__ dimg, const floa
                 for (int o = 0; o < 3; ++o) {
                     const long oi = (((long)bi * 3 + o) * H + yy) * W + xx;
                     const float im = __ldg(img + oi);
-                    v[(r * 3 + s) * 3 + o] = __ldg(dimg + oi) * (1.f - im * im);
+                    v[(r * 3 + s) * 3 + o] = __ldg(dimg + oi) * (1.f - im * im) * scale;
                 }
             }
         }
@@ -822,9 +817,9 @@ __global__ void im2col_rgb_bwd_kernel(const float* __restrict__ dimg, const floa
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (int j = 4; j < Kp / 8; ++j) dst[j] = z;
 }
-void k_im2col_rgb_bwd(const float* dimg, const float* img, bf16* col, int b, int H, int W, int Kp, cudaStream_t st) {
+void k_im2col_rgb_bwd(const float* dimg, const float* img, bf16* col, int b, int H, int W, int Kp, float scale, cudaStream_t st) {
     const long total = (long)b * H * W;
-    im2col_rgb_bwd_kernel<<<cdiv(total, 128), 128, 0, st>>>(dimg, img, col, b, H, W, Kp); count_launch();
+    im2col_rgb_bwd_kernel<<<cdiv(total, 128), 128, 0, st>>>(dimg, img, col, b, H, W, Kp, scale); count_launch();
 }
 
 // ---- VGG first layer helpers (3 input channels padded to Cp) --------------------------------
@@ -845,17 +840,17 @@ void k_img_to_nhwc_scaled(const float* img, bf16* out, int b, int H, int W, int 
     img_to_nhwc_scaled_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, out, b, H, W, Cp); count_launch();
 }
 __global__ void nhwc_to_dimg_scaled_kernel(const bf16* __restrict__ dx, int Cp, float* __restrict__ dimg, int b, int H,
-                                           int W, int accumulate) {
+                                           int W, int accumulate, float unscale) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long total = (long)b * 3 * H * W;
     if (i >= total) return;
     const int x = i % W, y = (i / W) % H, c = (i / ((long)W * H)) % 3, bi = i / ((long)3 * W * H);
-    const float v = b2f(dx[(((long)bi * H + y) * W + x) * Cp + c]) / kLpipsScale[c];
+    const float v = b2f(dx[(((long)bi * H + y) * W + x) * Cp + c]) * unscale / kLpipsScale[c];
     dimg[i] = accumulate ? dimg[i] + v : v;
 }
-void k_nhwc_to_dimg_scaled(const bf16* dx, int Cp, float* dimg, int b, int H, int W, int accumulate, cudaStream_t st) {
+void k_nhwc_to_dimg_scaled(const bf16* dx, int Cp, float* dimg, int b, int H, int W, int accumulate, float unscale, cudaStream_t st) {
     const long total = (long)b * 3 * H * W;
-    nhwc_to_dimg_scaled_kernel<<<cdiv(total, 256), 256, 0, st>>>(dx, Cp, dimg, b, H, W, accumulate); count_launch();
+    nhwc_to_dimg_scaled_kernel<<<cdiv(total, 256), 256, 0, st>>>(dx, Cp, dimg, b, H, W, accumulate, unscale); count_launch();
 }
 
 }  // namespace p2l

@@ -2,12 +2,12 @@
 // the tcgen05 convolutions). All pointers are device pointers; all launches are asynchronous
 // on `st`. bf16 tensors are NHWC.
 #pragma once
-#include <cuda_bf16.h>
+#include "act_type.h"
 #include <cuda_runtime.h>
 
 namespace p2l {
 
-typedef __nv_bfloat16 bf16;
+typedef act_t bf16;  // historical alias: the 16-bit activation type (fp16 by default, act_type.h)
 
 // ---- latent side ---------------------------------------------------------------------------
 // cond[b,256] = cat(z[b,zd], c[b,cd])
@@ -69,10 +69,10 @@ void k_transpose(const bf16* in, int ldin, int in_c0, bf16* out, int b, int R, i
 // AlexNet conv1 (11x11 s4 p2) im2col of the scaled image: col[b,Ho,Wo,Kp] (k = (c*11+r)*11+s, zero pad)
 void k_im2col_alex1(const float* img, bf16* col, int b, int H, int W, int Ho, int Wo, int Kp, cudaStream_t st);
 // gradient back to the (unscaled) image: dimg[b,3,H,W] (+)= col2im(dcol) / scale_c
-void k_col2im_alex1(const bf16* dcol, float* dimg, int b, int H, int W, int Ho, int Wo, int Kp, int accumulate, cudaStream_t st);
+void k_col2im_alex1(const bf16* dcol, float* dimg, int b, int H, int W, int Ho, int Wo, int Kp, int accumulate, float unscale, cudaStream_t st);
 // VGG first layer: img fp32 NCHW -> scaled bf16 NHWC padded to Cp channels
 void k_img_to_nhwc_scaled(const float* img, bf16* out, int b, int H, int W, int Cp, cudaStream_t st);
-void k_nhwc_to_dimg_scaled(const bf16* dx, int Cp, float* dimg, int b, int H, int W, int accumulate, cudaStream_t st);
+void k_nhwc_to_dimg_scaled(const bf16* dx, int Cp, float* dimg, int b, int H, int W, int accumulate, float unscale, cudaStream_t st);
 // max-pool k x k stride s (no padding), with argmax byte
 void k_maxpool_fwd(const bf16* x, bf16* out, unsigned char* idx, int b, int H, int W, int C, int Ho, int Wo,
                    int k, int s, cudaStream_t st);
@@ -83,7 +83,7 @@ void k_maxpool_bwd(const bf16* dout, const unsigned char* idx, const bf16* x, co
 // target features), lin[C], wadj[HW] (adjoint-upsampled weight map / sumW * beta).
 //   loss[b] += sum_p wadj[p] * sum_c lin_c (f_c/(|f|+eps) - t_c)^2 ; g = d/df (masked by f>0), or null
 void k_lpips_dist(const bf16* f, const float* t, const float* lin, const float* wadj, float* loss,
-                  bf16* g, int b, int HW, int C, cudaStream_t st);
+                  bf16* g, int b, int HW, int C, float gscale, cudaStream_t st);
 // t[p, c] = f_c/(|f|+eps)  (target features, b = 1)
 void k_lpips_normalize(const bf16* f, float* t, int HW, int C, cudaStream_t st);
 // wadj_k = U_k^T (sum_c W[c]) * coef   for a feature map h x w (bilinear, align_corners=False)
@@ -96,7 +96,8 @@ void k_l1_loss(const float* img, const float* target, const float* weight, const
 // dimg[b] *= dloss[b]
 void k_scale_rows(float* x, const float* scale, int b, long n, cudaStream_t st);
 // rgb conv backward input: A[b,H,W,Kp] bf16 with k = (r*3+s)*3 + c of dpre = dimg*(1-img^2)
-void k_im2col_rgb_bwd(const float* dimg, const float* img, bf16* col, int b, int H, int W, int Kp, cudaStream_t st);
+// `scale` = gradient scale applied on entry to 16-bit storage (act_type.h kGradScale)
+void k_im2col_rgb_bwd(const float* dimg, const float* img, bf16* col, int b, int H, int W, int Kp, float scale, cudaStream_t st);
 
 void k_fill_f32(float* p, float v, long n, cudaStream_t st);
 

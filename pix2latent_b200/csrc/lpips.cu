@@ -21,12 +21,12 @@ struct LpipsPlan {
     struct Lay {
         int Hin, Win, Hout, Wout;        // conv input / output spatial size
         int Hpre, Wpre;                  // size before the optional pool
-        __nv_bfloat16 *x = nullptr;      // conv input (pooled tensor, im2col buffer or previous F)
-        __nv_bfloat16 *F = nullptr;      // relu(conv) output
+        act_t *x = nullptr;      // conv input (pooled tensor, im2col buffer or previous F)
+        act_t *F = nullptr;      // relu(conv) output
         unsigned char* idx = nullptr;    // pool argmax
-        __nv_bfloat16 *g = nullptr;      // distance gradient (feature layers)
-        __nv_bfloat16 *D = nullptr;      // gradient wrt pre-relu conv output
-        __nv_bfloat16 *dX = nullptr;     // gradient wrt conv input (when a pool or the image follows)
+        act_t *g = nullptr;      // distance gradient (feature layers)
+        act_t *D = nullptr;      // gradient wrt pre-relu conv output
+        act_t *dX = nullptr;     // gradient wrt conv input (when a pool or the image follows)
         ConvOp f, d;
     };
     std::vector<Lay> L;
@@ -82,7 +82,7 @@ int Lpips::finalize() {
         if (j == 0 && net == P2L_LPIPS_ALEX) {
             // im2col GEMM: K = 3*11*11 = 363 -> 384, k = (c*11 + r)*11 + s  (torch weight flatten order)
             c.Kp = 384;
-            std::vector<__nv_bfloat16> f((size_t)c.Cout * c.Kp, host_f2bf(0.f)), t((size_t)c.Kp * c.Cout, host_f2bf(0.f));
+            std::vector<act_t> f((size_t)c.Cout * c.Kp, host_f2bf(0.f)), t((size_t)c.Kp * c.Cout, host_f2bf(0.f));
             for (int o = 0; o < c.Cout; ++o)
                 for (int k = 0; k < 363; ++k) {
                     f[(size_t)o * c.Kp + k] = host_f2bf((*w)[(size_t)o * 363 + k]);
@@ -147,7 +147,7 @@ LpipsPlan* Lpips::plan(int b, int H, int W) {
     LpipsPlan& P = *pp;
     P.b = b; P.H = H; P.W = W;
     Arena& ar = P.ar;
-    typedef __nv_bfloat16 bf;
+    typedef act_t bf;
     const int n = (int)convs.size();
     P.L.resize(n);
     P.dimg = ar.alloc<float>((size_t)b * 3 * H * W);
@@ -325,7 +325,7 @@ int Lpips::loss_forward(Target& T, int b, const float* img, float* loss, int wan
         const int f = convs[j].feat;
         if (f < 0) continue;
         k_lpips_dist(P.L[j].F, T.tfeat[f], lin[f], T.wadj[f], loss, want_grad ? P.L[j].g : nullptr, b, T.fh[f] * T.fw[f],
-                     chns[f], st);
+                     chns[f], grad_scale(), st);
     }
     if (!want_grad) return 0;
     // ---- backward through the backbone (dgrad only)
@@ -335,8 +335,8 @@ int Lpips::loss_forward(Target& T, int b, const float* img, float* loss, int wan
         LpipsPlan::Lay& l = P.L[j];
         if (conv_op_launch(l.d, st)) return -1;
         if (j == 0) {
-            if (net == P2L_LPIPS_ALEX) k_col2im_alex1(l.dX, P.dimg, b, T.H, T.W, l.Hout, l.Wout, c.Kp, 1, st);
-            else k_nhwc_to_dimg_scaled(l.dX, c.Kp, P.dimg, b, T.H, T.W, 1, st);
+            if (net == P2L_LPIPS_ALEX) k_col2im_alex1(l.dX, P.dimg, b, T.H, T.W, l.Hout, l.Wout, c.Kp, 1, 1.f / grad_scale(), st);
+            else k_nhwc_to_dimg_scaled(l.dX, c.Kp, P.dimg, b, T.H, T.W, 1, 1.f / grad_scale(), st);
         } else if (c.pool_before) {
             const LpipsPlan::Lay& pl = P.L[j - 1];
             k_maxpool_bwd(l.dX, l.idx, pl.F, convs[j - 1].feat >= 0 ? pl.g : nullptr, pl.D, b, l.Hpre, l.Wpre, c.Cin, l.Hin,

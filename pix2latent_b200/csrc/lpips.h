@@ -33,7 +33,7 @@ struct Lpips {
         int feat;  // feature index if this conv's relu output is an LPIPS layer, else -1
         int Kp;    // padded K of the first layer
         std::string name;
-        __nv_bfloat16 *w, *wt;
+        act_t *w, *wt;
         float* bias;
     };
     std::vector<LConv> convs;

@@ -44,7 +44,7 @@ struct Arena {
     ~Arena() { release(); }
 };
 
-inline __nv_bfloat16 host_f2bf(float f) { return __float2bfloat16_rn(f); }
+inline act_t host_f2bf(float f) { return f2a(f); }
 
 template <typename T>
 inline T* upload(Arena& ar, const std::vector<T>& h) {
@@ -79,10 +79,10 @@ struct TensorStage {
 };
 
 // conv weight [Cout, Cin, kh, kw] fp32 -> forward GEMM operand [Cout][(r*kw+s)*Cin + c] bf16
-inline std::vector<__nv_bfloat16> pack_conv_fwd(const std::vector<float>& w, int Cout, int Cin, int kh, int kw,
+inline std::vector<act_t> pack_conv_fwd(const std::vector<float>& w, int Cout, int Cin, int kh, int kw,
                                                 int Cout_keep = -1) {
     if (Cout_keep < 0) Cout_keep = Cout;
-    std::vector<__nv_bfloat16> o((size_t)Cout_keep * kh * kw * Cin);
+    std::vector<act_t> o((size_t)Cout_keep * kh * kw * Cin);
     for (int oc = 0; oc < Cout_keep; ++oc)
         for (int r = 0; r < kh; ++r)
             for (int s = 0; s < kw; ++s)
@@ -92,8 +92,8 @@ inline std::vector<__nv_bfloat16> pack_conv_fwd(const std::vector<float>& w, int
     return o;
 }
 // dgrad operand [Cin][(r'*kw+s')*Cout + o] = W[o, c, kh-1-r', kw-1-s'] bf16
-inline std::vector<__nv_bfloat16> pack_conv_dgrad(const std::vector<float>& w, int Cout, int Cin, int kh, int kw) {
-    std::vector<__nv_bfloat16> o((size_t)Cin * kh * kw * Cout);
+inline std::vector<act_t> pack_conv_dgrad(const std::vector<float>& w, int Cout, int Cin, int kh, int kw) {
+    std::vector<act_t> o((size_t)Cin * kh * kw * Cout);
     for (int c = 0; c < Cin; ++c)
         for (int r = 0; r < kh; ++r)
             for (int s = 0; s < kw; ++s)

@@ -6,6 +6,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include "act_type.h"
+
 namespace p2l {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -198,18 +200,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
     return d;
 }
 
-// Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M=128, N=n.
+// Instruction descriptor: act_t x act_t (fp16 or bf16, act_type.h) -> fp32, both operands K-major, M=128, N=n.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+    return (1u << 4) | (kUmmaFmt << 7) | (kUmmaFmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
 // ----------------------------------------------------------------------------- misc
-__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&t);
-}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return act_lo(u); }  // (names kept; the type is act_t)
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return act_hi(u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) { return pack_act(a, b); }
 
 }  // namespace p2l

@@ -23,7 +23,7 @@ struct SG2Plan {
     float *z = nullptr, *h[9] = {nullptr}, *g0 = nullptr, *g1 = nullptr;
     float *s_all = nullptr, *ds_all = nullptr, *dm_all = nullptr, *ddm_all = nullptr, *dw = nullptr;
     struct Lay {
-        __nv_bfloat16 *A = nullptr, *x = nullptr;
+        act_t *A = nullptr, *x = nullptr;
         float* D = nullptr;
         int Ha = 0;  // grid the convolution runs on (2*Hin+1 for up layers)
         ConvOp f, d;
@@ -31,7 +31,7 @@ struct SG2Plan {
     std::vector<Lay> L;
     std::vector<float*> rgb, weff, dweff;
     float *drgbA = nullptr, *drgbB = nullptr, *img = nullptr;
-    __nv_bfloat16 *dx[2] = {nullptr, nullptr}, *G = nullptr, *dDp = nullptr, *dA = nullptr;
+    act_t *dx[2] = {nullptr, nullptr}, *G = nullptr, *dDp = nullptr, *dA = nullptr;
     bool forward_done = false;
 };
 
@@ -162,7 +162,7 @@ int SG2::finalize() {
         const int C0 = convs[0].Cin;
         const auto* w = stage.get("input.input", (long)C0 * 16);
         if (!w) return -1;
-        std::vector<__nv_bfloat16> t((size_t)16 * C0);
+        std::vector<act_t> t((size_t)16 * C0);
         for (int c = 0; c < C0; ++c)
             for (int p = 0; p < 16; ++p) t[(size_t)p * C0 + c] = host_f2bf((*w)[(size_t)c * 16 + p]);
         const_in = upload(weights, t);
@@ -180,7 +180,7 @@ SG2Plan* SG2::plan(int b) {
     SG2Plan& P = *pp;
     P.b = b;
     Arena& ar = P.ar;
-    typedef __nv_bfloat16 bf;
+    typedef act_t bf;
     P.z = ar.alloc<float>((size_t)b * sdim);
     for (int k = 0; k <= n_mlp; ++k) P.h[k] = ar.alloc<float>((size_t)b * sdim);
     P.g0 = ar.alloc<float>((size_t)b * sdim);
@@ -270,7 +270,7 @@ int SG2::forward(int b, const float* z, const float* const* noise, float* img, c
         const Conv& c = convs[l];
         k_fc_fwd(P.s_all + c.s_off, S, c.wsqT, nullptr, 1.f, P.dm_all + c.dm_off, DM, b, c.Cin, c.Cout, 2, 1, st);
     }
-    const __nv_bfloat16* xprev = const_in;
+    const act_t* xprev = const_in;
     long xprev_bs = 0;
     int t = 0;
     for (int l = 0; l < nL; ++l) {
@@ -305,14 +305,14 @@ int SG2::backward(int b, const float* dimg, float* dz, cudaStream_t st, float sc
     P2L_CUDA_CHECK(cudaMemsetAsync(P.ddm_all, 0, (size_t)b * DM * sizeof(float), st));
     for (int t = 0; t < T; ++t) P2L_CUDA_CHECK(cudaMemsetAsync(P.dweff[t], 0, (size_t)b * 3 * rgbs[t].Cin * sizeof(float), st));
     float *dcur = P.drgbA, *dprev = P.drgbB;
-    k_sg_clamp_bwd(P.rgb.back(), dimg, dcur, (long)b * 3 * cfg.size * cfg.size, st);
+    k_sg_clamp_bwd(P.rgb.back(), dimg, dcur, (long)b * 3 * cfg.size * cfg.size, grad_scale(), st);
     auto layer_bwd = [&](int l) -> int {
         const Conv& c = convs[l];
         SG2Plan::Lay& q = P.L[l];
         k_sg_post_bwd(P.dx[l & 1], q.x, q.D, P.dm_all + c.dm_off, DM, P.G, P.ddm_all + c.dm_off, b, c.Hout, c.Hout, c.Cout, c.up, st);
         if (c.up) k_sg_blur_adjoint(P.G, P.dDp, b, c.Hout, c.Hout, c.Cout, st);
         if (conv_op_launch(q.d, st)) return -1;
-        const __nv_bfloat16* xp = l == 0 ? const_in : P.L[l - 1].x;
+        const act_t* xp = l == 0 ? const_in : P.L[l - 1].x;
         const long xbs = l == 0 ? 0 : (long)c.Hin * c.Hin * c.Cin;
         k_sg_modulate_bwd(P.dA, xp, xbs, P.s_all + c.s_off, S, l == 0 ? nullptr : P.dx[(l - 1) & 1], P.ds_all + c.s_off, S, b, c.Hin,
                           c.Hin, c.Cin, c.up, st);
@@ -338,7 +338,7 @@ int SG2::backward(int b, const float* dimg, float* dz, cudaStream_t st, float sc
         g = gn;
         gn = (gn == P.g0) ? P.g1 : P.g0;
     }
-    k_pixelnorm_bwd(P.z, g, dz, b, sdim, scale, row_scale, st);
+    k_pixelnorm_bwd(P.z, g, dz, b, sdim, scale / grad_scale(), row_scale, st);
     return 0;
 }
 

@@ -29,7 +29,7 @@ struct SG2 {
     struct Conv {   // StyledConv
         int Cin, Cout, Hin, Hout, up;
         int s_off, dm_off;
-        __nv_bfloat16 *w, *wt;      // shared weights (scale folded in), forward / dgrad GEMM operands
+        act_t *w, *wt;      // shared weights (scale folded in), forward / dgrad GEMM operands
         float *wsqT, *wsq;          // [Cin][Cout], [Cout][Cin]: sum_k (scale W)^2
         float *noise_w, *bias;
     };
@@ -37,7 +37,7 @@ struct SG2 {
     std::vector<Conv> convs;
     std::vector<Rgb> rgbs;
     int DM = 0;  // sum of Cout over StyledConvs
-    __nv_bfloat16* const_in = nullptr;  // [4,4,C0] NHWC
+    act_t* const_in = nullptr;  // [4,4,C0] NHWC
     std::map<int, std::shared_ptr<SG2Plan>> plans;
 
     int finalize();

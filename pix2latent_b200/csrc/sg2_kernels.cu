@@ -11,18 +11,13 @@
 namespace p2l {
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
-__device__ __forceinline__ float b2f(bf16 x) { return __bfloat162float(x); }
-__device__ __forceinline__ bf16 f2b(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ float b2f(bf16 x) { return a2f(x); }
+__device__ __forceinline__ bf16 f2b(float x) { return f2a(x); }
 __device__ __forceinline__ void unpack8(const uint4 t, float (&f)[8]) {
-    f[0] = __uint_as_float(t.x << 16); f[1] = __uint_as_float(t.x & 0xFFFF0000u);
-    f[2] = __uint_as_float(t.y << 16); f[3] = __uint_as_float(t.y & 0xFFFF0000u);
-    f[4] = __uint_as_float(t.z << 16); f[5] = __uint_as_float(t.z & 0xFFFF0000u);
-    f[6] = __uint_as_float(t.w << 16); f[7] = __uint_as_float(t.w & 0xFFFF0000u);
+    f[0] = act_lo(t.x); f[1] = act_hi(t.x); f[2] = act_lo(t.y); f[3] = act_hi(t.y);
+    f[4] = act_lo(t.z); f[5] = act_hi(t.z); f[6] = act_lo(t.w); f[7] = act_hi(t.w);
 }
-__device__ __forceinline__ uint32_t pk2(float a, float b) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&t);
-}
+__device__ __forceinline__ uint32_t pk2(float a, float b) { return pack_act(a, b); }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return make_uint4(pk2(f[0], f[1]), pk2(f[2], f[3]), pk2(f[4], f[5]), pk2(f[6], f[7]));
 }
@@ -446,8 +441,8 @@ __global__ void torgb_fwd_kernel(const bf16* __restrict__ x, const float* __rest
     const bf16* xp = x + ((long)bi * H * W + p) * C;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     for (int k = lane * 2; k < C; k += 64) {
-        const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(xp + k);
-        const float v0 = __low2float(v2), v1 = __high2float(v2);
+        const uint32_t v2 = *reinterpret_cast<const uint32_t*>(xp + k);
+        const float v0 = act_lo(v2), v1 = act_hi(v2);
         a0 = fmaf(v0, sw[k], a0); a0 = fmaf(v1, sw[k + 1], a0);
         a1 = fmaf(v0, sw[C + k], a1); a1 = fmaf(v1, sw[C + k + 1], a1);
         a2 = fmaf(v0, sw[2 * C + k], a2); a2 = fmaf(v1, sw[2 * C + k + 1], a2);
@@ -558,12 +553,12 @@ __global__ void clamp_kernel(const float* rgb, float* img, long n) {
 }
 void k_sg_clamp(const float* rgb, float* img, long n, cudaStream_t st) { clamp_kernel<<<cdiv(n, 256), 256, 0, st>>>(rgb, img, n); count_launch(); }
 // drgb = dimg where -1 <= rgb <= 1 else 0
-__global__ void clamp_bwd_kernel(const float* rgb, const float* dimg, float* drgb, long n) {
+__global__ void clamp_bwd_kernel(const float* rgb, const float* dimg, float* drgb, long n, float scale) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) drgb[i] = (rgb[i] >= -1.f && rgb[i] <= 1.f) ? dimg[i] : 0.f;
+    if (i < n) drgb[i] = (rgb[i] >= -1.f && rgb[i] <= 1.f) ? dimg[i] * scale : 0.f;
 }
-void k_sg_clamp_bwd(const float* rgb, const float* dimg, float* drgb, long n, cudaStream_t st) {
-    clamp_bwd_kernel<<<cdiv(n, 256), 256, 0, st>>>(rgb, dimg, drgb, n); count_launch();
+void k_sg_clamp_bwd(const float* rgb, const float* dimg, float* drgb, long n, float scale, cudaStream_t st) {
+    clamp_bwd_kernel<<<cdiv(n, 256), 256, 0, st>>>(rgb, dimg, drgb, n, scale); count_launch();
 }
 
 }  // namespace p2l

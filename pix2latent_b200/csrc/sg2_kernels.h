@@ -1,10 +1,10 @@
 // Launchers of the StyleGAN2 glue kernels (sg2_kernels.cu). Device pointers, asynchronous on `st`.
 #pragma once
-#include <cuda_bf16.h>
+#include "act_type.h"
 #include <cuda_runtime.h>
 
 namespace p2l {
-typedef __nv_bfloat16 bf16;
+typedef act_t bf16;
 
 // y = act(wscale * x W^T + bias): WT is [in][out]; act 0 none, 1 leaky-relu(0.2)*sqrt2, 2 rsqrt(.+1e-8);
 // square_in squares x first (demodulation)
@@ -33,5 +33,5 @@ void k_sg_torgb_bwd(const float* drgb, const bf16* x, const float* weff, bf16* d
 void k_sg_weff_bwd(const float* dweff, const float* Wr, float scale, float* ds, int ldds, int b, int C, cudaStream_t st);
 void k_sg_rgb_up_adjoint(const float* drgb, float* dprev, int b, int h, int w, cudaStream_t st);
 void k_sg_clamp(const float* rgb, float* img, long n, cudaStream_t st);
-void k_sg_clamp_bwd(const float* rgb, const float* dimg, float* drgb, long n, cudaStream_t st);
+void k_sg_clamp_bwd(const float* rgb, const float* dimg, float* drgb, long n, float scale, cudaStream_t st);
 }  // namespace p2l

@@ -23,6 +23,50 @@ CHANNELS = {4: 512, 8: 512, 16: 512, 32: 512, 64: 512, 128: 256, 256: 128, 512: 
 IM_DIM = {"cars": 512, "ffhq": 1024}
 
 
+def pad_channels_to_64(sd, size, channels):
+    """Zero-pad every level whose width is not a multiple of 64 (rosinality key layout)."""
+    ch = dict(channels)
+    log_size = size.bit_length() - 1
+    need = {r: ch[r] for r in (2 ** i for i in range(2, log_size + 1)) if ch[r] % 64}
+    if not need:
+        return sd, ch
+    sd = {k: v.clone() for k, v in sd.items()}
+    newc = {r: ((c + 63) // 64) * 64 for r, c in need.items()}
+
+    def pad(t, dim, n):
+        shape = list(t.shape)
+        shape[dim] = n - t.shape[dim]
+        return torch.cat([t, torch.zeros(shape, dtype=t.dtype, device=t.device)], dim)
+
+    def fix_styled(pre, cin_res, cout_res):
+        if cout_res in newc:
+            sd[pre + ".conv.weight"] = pad(sd[pre + ".conv.weight"], 1, newc[cout_res])
+            sd[pre + ".activate.bias"] = pad(sd[pre + ".activate.bias"], 0, newc[cout_res])
+        if cin_res in newc:
+            # the equalised-lr scale is 1/sqrt(fan_in): keep scale*W unchanged under the wider fan-in
+            sd[pre + ".conv.weight"] = pad(sd[pre + ".conv.weight"], 2, newc[cin_res]) * (newc[cin_res] / need[cin_res]) ** 0.5
+            sd[pre + ".conv.modulation.weight"] = pad(sd[pre + ".conv.modulation.weight"], 0, newc[cin_res])
+            sd[pre + ".conv.modulation.bias"] = pad(sd[pre + ".conv.modulation.bias"], 0, newc[cin_res])
+
+    def fix_rgb(pre, res):
+        if res in newc:
+            sd[pre + ".conv.weight"] = pad(sd[pre + ".conv.weight"], 2, newc[res]) * (newc[res] / need[res]) ** 0.5
+            sd[pre + ".conv.modulation.weight"] = pad(sd[pre + ".conv.modulation.weight"], 0, newc[res])
+            sd[pre + ".conv.modulation.bias"] = pad(sd[pre + ".conv.modulation.bias"], 0, newc[res])
+
+    if 4 in newc:
+        sd["input.input"] = pad(sd["input.input"], 1, newc[4])
+    fix_styled("conv1", 4, 4)
+    fix_rgb("to_rgb1", 4)
+    for i in range(3, log_size + 1):
+        r, rp = 2 ** i, 2 ** (i - 1)
+        fix_styled("convs.%d" % (2 * (i - 3)), rp, r)
+        fix_styled("convs.%d" % (2 * (i - 3) + 1), r, r)
+        fix_rgb("to_rgbs.%d" % (i - 3), r)
+    ch.update(newc)
+    return sd, ch
+
+
 class _SG2Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, model, noises):
@@ -41,12 +85,12 @@ class StyleGAN2(nn.Module):
             raise NotImplementedError("StyleGAN2(search=%r): only the z search of the reference examples is built" % search)
         self.im_res = int(size or IM_DIM[model])
         self.channels = dict(channels or CHANNELS)
-        if any(self.channels[2 ** i] % 64 for i in range(2, self.im_res.bit_length())):
-            raise NotImplementedError("feature widths must be multiples of 64 (ffhq-1024's 32-channel top level is not built yet)")
         if state_dict is None:
             warnings.warn("StyleGAN2: no checkpoint reachable offline; using seeded random-init weights (seed=%d)" % seed)
             state_dict = synth.stylegan2_state_dict(self.im_res, self.channels, seed)
-        self._state = state_dict
+        # the tcgen05 path tiles channels by 64: narrower levels (ffhq-1024's 32-channel top level) are
+        # zero-padded to 64 — functionally exact, the padded channels have zero weights on both sides
+        self._state, self.channels = pad_channels_to_64(state_dict, self.im_res, self.channels)
         self.search = search
         self.native = None
         log_size = self.im_res.bit_length() - 1

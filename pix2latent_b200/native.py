@@ -36,6 +36,7 @@ def declare(L):
     pp = C.POINTER(C.c_void_p)
     sig = {
         "p2l_version": (ci, []),
+        "p2l_act_dtype": (ci, []),
         "p2l_launch_count": (cl, []),
         "p2l_create": (ci, [ci, pp]),
         "p2l_destroy": (None, [vp]),
@@ -77,7 +78,7 @@ def declare(L):
 
 
 EXPORTED_SYMBOLS = [
-    "p2l_last_error", "p2l_version", "p2l_launch_count", "p2l_create", "p2l_destroy",
+    "p2l_last_error", "p2l_version", "p2l_act_dtype", "p2l_launch_count", "p2l_create", "p2l_destroy",
     "p2l_biggan_create", "p2l_biggan_set_tensor", "p2l_biggan_finalize", "p2l_biggan_destroy",
     "p2l_biggan_forward", "p2l_biggan_backward", "p2l_biggan_device_bytes", "p2l_biggan_flops",
     "p2l_biggan_launches", "p2l_lpips_create", "p2l_lpips_set_tensor", "p2l_lpips_finalize",
@@ -109,6 +110,11 @@ def context(device=None):
         _lib.check(_lib.lib().p2l_create(dev, C.byref(h)))
         _ctx[dev] = h
     return _ctx[dev], dev
+
+
+def act_dtype():
+    """torch dtype of the library's 16-bit activations / packed weights."""
+    return torch.float16 if _lib.lib().p2l_act_dtype() == 1 else torch.bfloat16
 
 
 def launch_count():

@@ -34,3 +34,9 @@ torch.cuda.synchronize()
 print("native vs fp32 oracle:               img max", (img-ref).abs().max().item(), "rel", rel(img, ref),
       "dz rel", rel(dz, gz), "cos", cos(dz, gz), "dc rel", rel(dc, gc), "cos", cos(dc, gc))
 print("native vs autocast oracle: img rel", rel(img, ab.float()))
+from pix2latent_b200 import _lib
+for gs in (1, 64, 1024, 4096, 65536, 1 << 20, 1 << 24):
+    _lib.set_option("grad_scale", gs)
+    dz, dc = nat.backward(b, dimg)
+    torch.cuda.synchronize()
+    print("grad_scale %8d: dz rel %.4f cos %.5f  dc rel %.4f" % (gs, rel(dz, gz), cos(dz, gz), rel(dc, gc)))

@@ -3,6 +3,11 @@ import sys, time
 sys.path.insert(0, ".")
 sys.path.insert(0, "tests")
 import torch
+
+
+def ACT():
+    from pix2latent_b200 import native
+    return native.act_dtype()
 import torch.nn.functional as F
 from pix2latent_b200 import _lib
 from test_conv_gemm_gpu import run_conv, pack_w, nhwc, rel_err
@@ -10,11 +15,11 @@ from test_conv_gemm_gpu import run_conv, pack_w, nhwc, rel_err
 def conv_case(N, H, W, Cin, Cout, BN, k=3, time_it=False, extra=None):
     torch.manual_seed(0)
     dev = "cuda"
-    x = torch.randn(N, Cin, H, W, device=dev).to(torch.bfloat16)
-    w = (torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+    x = torch.randn(N, Cin, H, W, device=dev).to(ACT())
+    w = (torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5).to(ACT())
     bias = torch.randn(Cout, device=dev)
     xa = nhwc(x); wp = pack_w(w)
-    out = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    out = torch.zeros(N, H, W, Cout, device=dev, dtype=ACT())
     kw = dict(A=xa, A_N=N, A_H=H, A_W=W, A_C=Cin, a_c0=0, Cin=Cin, B=wp, Cout=Cout, kh=k, kw=k, pad_h=k // 2, pad_w=k // 2,
               NI=N, H=H, W=W, BN=BN, mode=0, bias=bias, raw=out, raw_C=Cout)
     if extra: kw.update(extra(N, H, W, Cout, dev))
@@ -58,9 +63,9 @@ for halo, bo in [(0, 0), (10, 0), (16, 0)]:
 
 # epilogue-heavy 1x1 (conv_3 of block 11): resid + raw + affine act
 def extra(N, H, W, Cout, dev):
-    skip = torch.randn(N, H // 2, W // 2, 2 * Cout, device=dev).to(torch.bfloat16)
+    skip = torch.randn(N, H // 2, W // 2, 2 * Cout, device=dev).to(ACT())
     a = torch.randn(N, Cout, device=dev); s = torch.randn(N, Cout, device=dev)
-    act = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    act = torch.zeros(N, H, W, Cout, device=dev, dtype=ACT())
     return dict(resid=skip, resid_C=2 * Cout, resid_shift=1, aff_a=a, aff_s=s, aff_stride=Cout, relu=1, act=act, act_C=Cout)
 _lib.set_option("halo", 0)
 e, t = conv_case(18, 256, 256, 64, 128, 128, 1, time_it=True, extra=extra)

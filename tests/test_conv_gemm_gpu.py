@@ -8,6 +8,11 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
+def ACT():
+    from pix2latent_b200 import native
+    return native.act_dtype()
+
+
 def _lib():
     from pix2latent_b200 import _lib
     return _lib
@@ -15,7 +20,7 @@ def _lib():
 
 def pack_w(w):
     """torch conv weight [Cout, Cin, kh, kw] -> bf16 [Cout, kh*kw*Cin] (tap-major, channel-minor)."""
-    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous().to(torch.bfloat16)
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous().to(ACT())
 
 
 def nhwc(x):
@@ -60,12 +65,12 @@ CASES_FWD = [
 def test_conv_fwd_raw(N, H, W, Cin, Cout, k, BN):
     torch.manual_seed(0)
     dev = "cuda"
-    x = torch.randn(N, Cin, H, W, device=dev).to(torch.bfloat16)
-    w = (torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+    x = torch.randn(N, Cin, H, W, device=dev).to(ACT())
+    w = (torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5).to(ACT())
     bias = torch.randn(Cout, device=dev)
     ref = F.conv2d(x.float(), w.float(), bias, padding=k // 2)
     xa = nhwc(x)
-    out = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    out = torch.zeros(N, H, W, Cout, device=dev, dtype=ACT())
     out32 = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.float32)
     run_conv(A=xa, A_N=N, A_H=H, A_W=W, A_C=Cin, a_c0=0, Cin=Cin, B=pack_w(w), Cout=Cout, kh=k, kw=k,
              pad_h=k // 2, pad_w=k // 2, NI=N, H=H, W=W, BN=BN, mode=0, bias=bias,
@@ -80,18 +85,18 @@ def test_conv_fwd_affine_relu_resid_up():
     torch.manual_seed(1)
     dev = "cuda"
     N, H, W, Cin, Cout = 3, 16, 16, 128, 64
-    x = torch.randn(N, Cin, H, W, device=dev).to(torch.bfloat16)
-    w = (torch.randn(Cout, Cin, 1, 1, device=dev) / Cin ** 0.5).to(torch.bfloat16)
+    x = torch.randn(N, Cin, H, W, device=dev).to(ACT())
+    w = (torch.randn(Cout, Cin, 1, 1, device=dev) / Cin ** 0.5).to(ACT())
     bias = torch.randn(Cout, device=dev)
-    skip = torch.randn(N, 2 * Cout, H // 2, W // 2, device=dev).to(torch.bfloat16)  # first Cout channels used
+    skip = torch.randn(N, 2 * Cout, H // 2, W // 2, device=dev).to(ACT())  # first Cout channels used
     a = torch.randn(N, Cout, device=dev)
     s = torch.randn(N, Cout, device=dev)
     v = F.conv2d(x.float(), w.float(), bias) + F.interpolate(skip[:, :Cout].float(), scale_factor=2, mode="nearest")
     y = torch.relu(a[:, :, None, None] * v + s[:, :, None, None])
     y_up = F.interpolate(y, scale_factor=2, mode="nearest")
-    raw = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
-    act = torch.zeros(N, 2 * H, 2 * W, Cout, device=dev, dtype=torch.bfloat16)
-    act_lo = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    raw = torch.zeros(N, H, W, Cout, device=dev, dtype=ACT())
+    act = torch.zeros(N, 2 * H, 2 * W, Cout, device=dev, dtype=ACT())
+    act_lo = torch.zeros(N, H, W, Cout, device=dev, dtype=ACT())
     run_conv(A=nhwc(x), A_N=N, A_H=H, A_W=W, A_C=Cin, Cin=Cin, B=pack_w(w), Cout=Cout, kh=1, kw=1,
              NI=N, H=H, W=W, BN=64, mode=0, bias=bias, resid=nhwc(skip), resid_C=2 * Cout, resid_shift=1,
              raw=raw, raw_C=Cout, aff_a=a, aff_s=s, aff_stride=Cout, relu=1,
@@ -105,8 +110,8 @@ def test_conv_fwd_rgb_tanh():
     torch.manual_seed(2)
     dev = "cuda"
     N, H, W, Cin = 2, 64, 64, 128
-    x = torch.randn(N, Cin, H, W, device=dev).to(torch.bfloat16)
-    w = (torch.randn(3, Cin, 3, 3, device=dev) / (Cin * 9) ** 0.5).to(torch.bfloat16)
+    x = torch.randn(N, Cin, H, W, device=dev).to(ACT())
+    w = (torch.randn(3, Cin, 3, 3, device=dev) / (Cin * 9) ** 0.5).to(ACT())
     bias = torch.randn(3, device=dev) * 0.1
     ref = torch.tanh(F.conv2d(x.float(), w.float(), bias, padding=1))
     img = torch.zeros(N, 3, H, W, device=dev)
@@ -120,8 +125,8 @@ def test_gemm_batched_b_fp32_out():
     torch.manual_seed(3)
     dev = "cuda"
     b, H, W, d, nk = 3, 64, 64, 64, 1024
-    theta = torch.randn(b, H, W, d, device=dev).to(torch.bfloat16)
-    phi = torch.randn(b, nk, d, device=dev).to(torch.bfloat16)
+    theta = torch.randn(b, H, W, d, device=dev).to(ACT())
+    phi = torch.randn(b, nk, d, device=dev).to(ACT())
     ref = torch.einsum("bqd,bkd->bqk", theta.float().reshape(b, H * W, d), phi.float())
     S = torch.zeros(b, H * W, nk, device=dev)
     run_conv(A=theta, A_N=b, A_H=H, A_W=W, A_C=d, Cin=d, B=phi, Cout=nk, B_batch=b, kh=1, kw=1,
@@ -142,15 +147,15 @@ def test_conv_bwd(N, H, W, C, Cout, k, BN, pool):
     gradient sums, multiply by the affine gain, add the skip gradient."""
     torch.manual_seed(4)
     dev = "cuda"
-    g = torch.randn(N, C, H, W, device=dev).to(torch.bfloat16)
-    w = (torch.randn(Cout, C, k, k, device=dev) / (C * k * k) ** 0.5).to(torch.bfloat16)
-    saved = torch.relu(torch.randn(N, Cout, H, W, device=dev)).to(torch.bfloat16)
+    g = torch.randn(N, C, H, W, device=dev).to(ACT())
+    w = (torch.randn(Cout, C, k, k, device=dev) / (C * k * k) ** 0.5).to(ACT())
+    saved = torch.relu(torch.randn(N, Cout, H, W, device=dev)).to(ACT())
     a = torch.randn(N, Cout, device=dev)
     if pool:
-        addin = torch.randn(N, Cout // 2, 2 * H, 2 * W, device=dev).to(torch.bfloat16)
+        addin = torch.randn(N, Cout // 2, 2 * H, 2 * W, device=dev).to(ACT())
         add_ref = F.avg_pool2d(addin.float(), 2) * 4
     else:
-        addin = torch.randn(N, Cout // 2, H, W, device=dev).to(torch.bfloat16)
+        addin = torch.randn(N, Cout // 2, H, W, device=dev).to(ACT())
         add_ref = addin.float()
     acc = F.conv2d(g.float(), w.float(), padding=k // 2)
     dpre = acc * (saved.float() > 0)
@@ -160,7 +165,7 @@ def test_conv_bwd(N, H, W, C, Cout, k, BN, pool):
     dx[:, :Cout // 2] += add_ref
     st0 = torch.zeros(N, Cout, device=dev)
     st1 = torch.zeros(N, Cout, device=dev)
-    out = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    out = torch.zeros(N, H, W, Cout, device=dev, dtype=ACT())
     out32 = torch.zeros(N, H, W, Cout, device=dev)
     run_conv(A=nhwc(g), A_N=N, A_H=H, A_W=W, A_C=C, Cin=C, B=pack_w(w), Cout=Cout, kh=k, kw=k,
              pad_h=k // 2, pad_w=k // 2, NI=N, H=H, W=W, BN=BN, mode=1,

@@ -71,3 +71,28 @@ def test_no_noise_and_fused_step(tiny):
     print("loss", loss.tolist(), ref_loss.tolist(), "cos", cos(dz, z.grad))
     assert torch.allclose(loss, ref_loss, rtol=3e-2, atol=3e-3)
     assert cos(dz, z.grad) > 0.95
+
+
+def test_narrow_level_is_zero_padded_exactly():
+    """ffhq-1024's top level has 32 channels; the wrapper pads such levels to 64 (zero weights, fan-in
+    scale compensated). Reduced config with a 32-channel level, through the product model class."""
+    import warnings
+    from oracle import stylegan2 as osg
+    from pix2latent_b200.model.stylegan2 import StyleGAN2
+    ch = {4: 128, 8: 64, 16: 32}
+    orc = osg.make_stylegan2(16, ch, seed=1).cuda()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = StyleGAN2(state_dict=orc.model.state_dict(), size=16, channels=ch)
+    assert model.channels[16] == 64
+    torch.manual_seed(4)
+    z = torch.randn(2, 512, device="cuda", requires_grad=True)
+    noise = [torch.randn(s, device="cuda") for s in orc.model.noise_shapes(2)]
+    ref = orc(z, noise)
+    z2 = z.detach().clone().requires_grad_(True)
+    out = model(z2, noise)
+    assert rel(out, ref) < 3e-2
+    g = torch.randn_like(ref) * 1e-2
+    ref.backward(g)
+    out.backward(g)
+    assert cos(z2.grad, z.grad) > 0.98
