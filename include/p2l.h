@@ -59,7 +59,7 @@ int p2l_biggan_create(p2l_ctx* ctx, const p2l_biggan_config* cfg, p2l_biggan** o
 /* name = state-dict key of pix2latent's BigGAN module after remove_spectral_norm
  * (e.g. "generator.layers.0.conv_0.weight"); data = fp32, host or device, torch layout. */
 int p2l_biggan_set_tensor(p2l_biggan* m, const char* name, const float* data, long numel);
-/* Pack weights into the bf16 GEMM layouts the kernels read; frees the staging copies. */
+/* Pack weights into the 16-bit (p2l_act_dtype) GEMM layouts the kernels read; frees the staging copies. */
 int p2l_biggan_finalize(p2l_biggan* m);
 void p2l_biggan_destroy(p2l_biggan* m);
 /* img_dev[b,3,R,R] fp32 NCHW in (-1,1) = generator(cat(z,c), truncation). Keeps the activations

@@ -10,10 +10,10 @@ extern "C" {
 #endif
 
 typedef struct p2l_conv_args {
-    /* A: bf16 NHWC */
+    /* A: 16-bit (p2l_act_dtype) NHWC */
     const void* A;
     int A_N, A_H, A_W, A_C, a_c0, Cin;
-    /* B: bf16 [batch][Cout][kh*kw*Cin] */
+    /* B: 16-bit [batch][Cout][kh*kw*Cin] */
     const void* B;
     int Cout, B_batch, kh, kw, pad_h, pad_w;
     /* output pixel grid, tile N, mode (0 fwd, 1 bwd) */

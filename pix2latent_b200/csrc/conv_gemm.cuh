@@ -92,14 +92,18 @@ struct GemmCfg {
     // four warps) is latency-bound, a second CTA doubles the bytes in flight and lets one CTA's
     // epilogue overlap the other's main loop even on single-tile launches.
     // TMA_OUT ("TMA I/O" variant, used where the epilogue dominates): one CTA per SM with a fifth
-    // role, the epilogue-input loader. Outputs leave through two 16 KB swizzled slabs (128 rows x 64
-    // channels) and cp.async.bulk.tensor stores; the per-pixel epilogue inputs (saved activation,
-    // residual skip, skip gradient) are prefetched by TMA into a ring of kInSlots slabs, so no
-    // thread ever waits on a global load.
+    // role, the epilogue-input loader, and TWO epilogue groups of four warps: group g drains TMEM
+    // accumulator stage g (tiles alternate between the groups), so two tiles' epilogues run
+    // concurrently and each scheduler has two epilogue warps to hide latency with. Outputs leave
+    // through 16 KB swizzled slabs (128 rows x 64 channels, one {raw, act} pair per group) and
+    // cp.async.bulk.tensor stores; the per-pixel epilogue inputs (saved activation, residual skip,
+    // skip gradient) are prefetched by TMA into a ring of kInSlots slabs shared by both groups, so
+    // no thread ever waits on a global load.
     static constexpr int kOcc = TMA_OUT ? 1 : ((BN <= 128) ? P2L_OCC : 1);
     static constexpr int kInSlots = TMA_OUT ? 4 : 0;
     static constexpr int kOutBytes = TMA_OUT ? (4 + kInSlots) * kATileBytes : 0;  // 2 x {raw, act} + inputs
-    static constexpr int kThreads = TMA_OUT ? kGemmThreads + 32 : kGemmThreads;
+    static constexpr int kEpiGroups = TMA_OUT ? 2 : 1;
+    static constexpr int kThreads = 64 + 128 * kEpiGroups + (TMA_OUT ? 32 : 0);
     static constexpr int kMaxStages = ((kOcc == 2 ? 104 : 208) * 1024 - kOutBytes) / kStageBytes;
     static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
     static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -159,12 +163,23 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
     const bool use_tab = (p.nb == 1);
     // TMA_OUT: tmo[0] = raw / dx, tmo[1] = act, tmo[2] = act on the 2x grid (5-D view), tmo[3] = act_lo;
     // obuf = [2 output slabs][kInSlots input slabs]; input slabs arrive through in_full / in_empty
-    const bool storer = TMA_OUT && (warp & 3) == 0 && lane == 0;
     constexpr int NIN = GemmCfg<BN, TMA_OUT>::kInSlots;
+    constexpr int NG = GemmCfg<BN, TMA_OUT>::kEpiGroups;
+    const int grp = (NG == 2) ? ((warp - 2) >> 2) : 0;  // epilogue group = TMEM accumulator stage it drains
+    const bool storer = TMA_OUT && ((warp - 2) & 3) == 0 && lane == 0;
     uint8_t* inbuf = obuf + 4 * kATileBytes;
-    uint8_t* obase = obuf;        // output slab pair in use (two pairs alternate per 64-channel slab)
+    obuf += grp * 2 * kATileBytes;  // this group's {raw | dx, act} slab pair
+    // one output tensor only (dgrad, or act without raw): the two slabs of the pair double-buffer it
+    const bool single_out = (MODE == EPI_BWD) || (p.raw == nullptr);
     int slab_no = 0;
-    int in_cnt = 0;               // consumed input slabs (same order as the loader warp issues them)
+    uint8_t *s_raw = obuf, *s_act = obuf;
+    // each group has its own ring of RING input slots, filled by the loader warp in this group's
+    // consumption order (an mbarrier parity wait is only safe for an in-order consumer)
+    constexpr int RING = (NIN >= NG) ? NIN / NG : 1;
+    inbuf += grp * RING * kATileBytes;
+    in_full += grp * RING;
+    in_empty += grp * RING;
+    int in_cnt = 0;               // input slabs this group has consumed
     int slot0 = 0, slot1 = 0;     // slots of the current 64-channel slab
     bool has0 = false, has1 = false;
     // ------------------------------------------------------------------ epilogue warps
@@ -176,8 +191,8 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
     const int rows_per_img = p.tw * p.th;
     float alpha = p.alpha;
     if (p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    int it = grp;  // index of the tile in this CTA's sequence
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += NG * gridDim.x, it += NG) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
@@ -190,7 +205,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 
         float* tab = ctab + (it & 1) * 3 * BN;
         if (use_tab) {
-            const int et = (warp & 3) * 32 + lane;  // 0..127
+            const int et = ((warp - 2) & 3) * 32 + lane;  // 0..127 within the group
             const int nn = min(tni * p.nb, p.NI - 1);
             for (int j = et; j < BN; j += 128) {
                 const int ch = n_tile * BN + j;
@@ -199,7 +214,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 tab[BN + j] = (p.aff_a && in) ? __ldg(p.aff_a + static_cast<long>(nn) * p.aff_stride + ch) : 1.f;
                 tab[2 * BN + j] = (MODE == EPI_FWD && p.aff_s && in) ? __ldg(p.aff_s + static_cast<long>(nn) * p.aff_stride + ch) : 0.f;
             }
-            bar_epilogue();  // table[it & 1] was last read two tiles ago: every warp has passed the previous barrier since
+            bar_epilogue(grp);  // table[it & 1] was last read by this group's previous tile (or two tiles ago): every warp has passed a barrier since
         }
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
@@ -214,20 +229,24 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     // both output slabs are about to be overwritten: their previous stores must have
                     // finished READING shared memory
                     // the pair written two slabs ago must have been READ by its bulk stores
-                    obuf = obase + (slab_no & 1) * 2 * kATileBytes;
+                    if (storer) {
+                        if (single_out) bulk_wait_read1();
+                        else bulk_wait_read0();
+                    }
+                    s_raw = single_out ? obuf + (slab_no & 1) * kATileBytes : obuf;
+                    s_act = single_out ? s_raw : obuf + kATileBytes;
                     ++slab_no;
-                    if (storer) bulk_wait_read1();
-                    bar_epilogue();
+                    bar_epilogue(grp);
                     has0 = (MODE == EPI_FWD) ? (p.resid != nullptr) : (p.saved != nullptr);
                     has1 = (MODE == EPI_BWD) && p.addin != nullptr && cbase < p.addin_climit;
                     if (has0) {
-                        slot0 = in_cnt % NIN;
-                        mbar_wait(&in_full[slot0], (in_cnt / NIN) & 1);
+                        slot0 = in_cnt % RING;
+                        mbar_wait(&in_full[slot0], (in_cnt / RING) & 1);
                         ++in_cnt;
                     }
                     if (has1) {
-                        slot1 = in_cnt % NIN;
-                        mbar_wait(&in_full[slot1], (in_cnt / NIN) & 1);
+                        slot1 = in_cnt % RING;
+                        mbar_wait(&in_full[slot1], (in_cnt / RING) & 1);
                         ++in_cnt;
                     }
                 }
@@ -303,7 +322,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     for (int q = 0; q < CH / 4; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
                 }
                 if constexpr (TMA_OUT) {
-                    if (p.raw) slab_put_row(obuf, row, (c & 32) >> 3, v);
+                    if (p.raw) slab_put_row(s_raw, row, (c & 32) >> 3, v);
                 } else if (p.raw && valid) {
                     uint4* dst = reinterpret_cast<uint4*>(p.raw + pix * p.raw_C + cbase);
 #pragma unroll
@@ -342,7 +361,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                         for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
                     if constexpr (TMA_OUT) {
-                        slab_put_row(obuf + kATileBytes, row, (c & 32) >> 3, v);
+                        slab_put_row(s_act, row, (c & 32) >> 3, v);
                     } else if (valid) {
                         uint4 o[CH / 8];
 #pragma unroll
@@ -488,7 +507,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     }
                 }
                 if constexpr (TMA_OUT) {
-                    if (p.dx) slab_put_row(obuf, row, (c & 32) >> 3, v);
+                    if (p.dx) slab_put_row(s_raw, row, (c & 32) >> 3, v);
                 }
                 if (valid) {
                     if (!TMA_OUT && p.dx) {
@@ -516,24 +535,24 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                         }
                     }
                     fence_async_smem();
-                    bar_epilogue();
+                    bar_epilogue(grp);
                     if (storer) {
                         const int cs = n_tile * BN + (c & ~63);
                         const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.nb;
                         if constexpr (MODE == EPI_FWD) {
-                            if (p.raw) tma_store_4d(&tmo[0], obuf, cs, w0, h0, n0);
+                            if (p.raw) tma_store_4d(&tmo[0], s_raw, cs, w0, h0, n0);
                             if (p.act) {
                                 if (!p.act_up) {
-                                    tma_store_4d(&tmo[1], obuf + kATileBytes, cs, w0, h0, n0);
+                                    tma_store_4d(&tmo[1], s_act, cs, w0, h0, n0);
                                 } else {
                                     // nearest x2: the same slab goes to the four (dy, dx) phases of the 2x grid
                                     for (int d = 0; d < 4; ++d)
-                                        tma_store_5d(&tmo[2], obuf + kATileBytes, cs, d & 1, w0, d >> 1, n0 * p.H + h0);
-                                    if (p.act_lo) tma_store_4d(&tmo[3], obuf + kATileBytes, cs, w0, h0, n0);
+                                        tma_store_5d(&tmo[2], s_act, cs, d & 1, w0, d >> 1, n0 * p.H + h0);
+                                    if (p.act_lo) tma_store_4d(&tmo[3], s_act, cs, w0, h0, n0);
                                 }
                             }
                         } else {
-                            if (p.dx) tma_store_4d(&tmo[0], obuf, cs, w0, h0, n0);
+                            if (p.dx) tma_store_4d(&tmo[0], s_raw, cs, w0, h0, n0);
                         }
                         bulk_commit();
                     }
@@ -668,7 +687,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_commit(&tfull_bar[as]);
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 2 + 4 * Cfg::kEpiGroups) {
         // ------------------------------------------------------------------ epilogue-input loader
         if constexpr (TMA_OUT) {
             if (lane == 0) {
@@ -676,8 +695,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const bool has0 = (MODE == EPI_FWD) ? (p.resid != nullptr) : (p.saved != nullptr);
                 const int sh = (MODE == EPI_FWD) ? p.resid_shift : 0;
                 const uint32_t bytes0 = kATileBytes >> (2 * sh);
-                int cnt = 0;
-                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                constexpr int RING = NIN / Cfg::kEpiGroups;  // one ring per epilogue group
+                int cnts[2] = {0, 0};
+                int it = 0;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                    const int g = it & 1;
+                    int& cnt = cnts[g];
                     const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
                     const int w0 = (m_tile % p.tiles_w) * p.tw;
                     const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
@@ -686,15 +709,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int cs = n_tile * BN + c;
                         if (cs >= p.Cout) break;
                         if (has0) {
-                            const int slot = cnt % NIN;
-                            mbar_wait(&in_empty[slot], ((cnt / NIN) & 1) ^ 1);
+                            const int slot = g * RING + cnt % RING;
+                            mbar_wait(&in_empty[slot], ((cnt / RING) & 1) ^ 1);
                             mbar_expect_tx(&in_full[slot], bytes0);
                             tma_load_4d(inbuf + slot * kATileBytes, &tmO.m[4], &in_full[slot], cs, w0 >> sh, h0 >> sh, n0);
                             ++cnt;
                         }
                         if (MODE == EPI_BWD && p.addin != nullptr && cs < p.addin_climit) {
-                            const int slot = cnt % NIN;
-                            mbar_wait(&in_empty[slot], ((cnt / NIN) & 1) ^ 1);
+                            const int slot = g * RING + cnt % RING;
+                            mbar_wait(&in_empty[slot], ((cnt / RING) & 1) ^ 1);
                             mbar_expect_tx(&in_full[slot], kATileBytes);
                             tma_load_4d(inbuf + slot * kATileBytes, &tmO.m[5], &in_full[slot], cs, w0, h0, n0);
                             ++cnt;

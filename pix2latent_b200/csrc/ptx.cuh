@@ -103,8 +103,8 @@ __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (TMA)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// named barrier over the 128 epilogue threads (id 1; id 0 is __syncthreads)
-__device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barrier over the 128 threads of epilogue group `grp` (ids 1, 2; id 0 is __syncthreads)
+__device__ __forceinline__ void bar_epilogue(int grp = 0) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
 // ----------------------------------------------------------------------------- tcgen05
 template <uint32_t kCols>

@@ -79,12 +79,16 @@ def test_conv_fwd_raw(N, H, W, Cin, Cout, k, BN):
     assert rel_err(out.permute(0, 3, 1, 2), ref) < 6e-3
 
 
-def test_conv_fwd_affine_relu_resid_up():
+@pytest.mark.parametrize("N,H,W,Cin,Cout,BN", [
+    (3, 16, 16, 128, 64, 64),
+    (18, 64, 64, 64, 128, 128),    # 576 tiles: several per persistent CTA, both epilogue groups, slab rings wrap
+    (9, 64, 64, 256, 192, 64),     # 3 column tiles of 64
+])
+def test_conv_fwd_affine_relu_resid_up(N, H, W, Cin, Cout, BN):
     """conv_0/conv_3-style epilogue: bias, skip add (channel-sliced, nearest-upsampled), raw write,
     per-sample affine + relu, 2x replicated activated write."""
     torch.manual_seed(1)
     dev = "cuda"
-    N, H, W, Cin, Cout = 3, 16, 16, 128, 64
     x = torch.randn(N, Cin, H, W, device=dev).to(ACT())
     w = (torch.randn(Cout, Cin, 1, 1, device=dev) / Cin ** 0.5).to(ACT())
     bias = torch.randn(Cout, device=dev)
@@ -98,7 +102,7 @@ def test_conv_fwd_affine_relu_resid_up():
     act = torch.zeros(N, 2 * H, 2 * W, Cout, device=dev, dtype=ACT())
     act_lo = torch.zeros(N, H, W, Cout, device=dev, dtype=ACT())
     run_conv(A=nhwc(x), A_N=N, A_H=H, A_W=W, A_C=Cin, Cin=Cin, B=pack_w(w), Cout=Cout, kh=1, kw=1,
-             NI=N, H=H, W=W, BN=64, mode=0, bias=bias, resid=nhwc(skip), resid_C=2 * Cout, resid_shift=1,
+             NI=N, H=H, W=W, BN=BN, mode=0, bias=bias, resid=nhwc(skip), resid_C=2 * Cout, resid_shift=1,
              raw=raw, raw_C=Cout, aff_a=a, aff_s=s, aff_stride=Cout, relu=1,
              act=act, act_C=Cout, act_up=1, act_lo=act_lo)
     assert rel_err(raw.permute(0, 3, 1, 2), v) < 6e-3
@@ -140,6 +144,9 @@ def test_gemm_batched_b_fp32_out():
     (18, 4, 4, 128, 64, 3, 64, 0),
     (5, 8, 8, 64, 128, 1, 128, 0),
     (1, 128, 128, 64, 64, 3, 64, 0),
+    (18, 64, 64, 64, 256, 1, 128, 0),   # 1152 tiles, saved + skip-gradient slabs through the input rings
+    (9, 64, 64, 128, 128, 1, 64, 0),
+    (7, 32, 32, 512, 128, 1, 128, 0),
 ])
 def test_conv_bwd(N, H, W, C, Cout, k, BN, pool):
     """dgrad-style launch: A = upstream gradient [N,H,W,C], B = transposed/flipped weights
