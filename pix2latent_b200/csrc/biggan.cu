@@ -130,14 +130,24 @@ int BigGAN::finalize() {
     if (fill_stats("generator.bn", C_last, C_cond)) return -1;
     mean = upload(weights, h_mean);
     inv_std = upload(weights, h_istd);
-    {   // cond -> (gain, offset): transposed [cdim][C_cond] so a warp of channels reads contiguous rows
-        std::vector<float> t((size_t)C_cond * cdim);
-        for (int c = 0; c < C_cond; ++c)
-            for (int k = 0; k < cdim; ++k) t[(size_t)k * C_cond + c] = h_ws[(size_t)c * cdim + k];
-        Ws = upload(weights, t);
-        for (int c = 0; c < C_cond; ++c)
-            for (int k = 0; k < cdim; ++k) t[(size_t)k * C_cond + c] = h_wo[(size_t)c * cdim + k];
-        Wo = upload(weights, t);
+    {   // cond -> (gain, offset) as ONE GEMV + bias with the BN statistics folded in:
+        //   a = (1 + cond.Ws) * istd            = istd          + cond . (Ws * istd)
+        //   s = cond.Wo - mean * a              = -mean * istd  + cond . (Wo - mean * istd * Ws)
+        // transposed [cdim][2*C_cond] so a warp of channels reads contiguous rows
+        if (cdim % 128) { set_error("biggan: z_dim + class_embed_dim must be a multiple of 128"); return -1; }
+        std::vector<float> t((size_t)2 * C_cond * cdim), bias((size_t)2 * C_cond);
+        for (int c = 0; c < C_cond; ++c) {
+            const double is = h_istd[c], m = h_mean[c];
+            bias[c] = (float)is;
+            bias[(size_t)C_cond + c] = (float)(-m * is);
+            for (int k = 0; k < cdim; ++k) {
+                const double ws = h_ws[(size_t)c * cdim + k], wo = h_wo[(size_t)c * cdim + k];
+                t[(size_t)k * 2 * C_cond + c] = (float)(ws * is);
+                t[(size_t)k * 2 * C_cond + C_cond + c] = (float)(wo - m * is * ws);
+            }
+        }
+        WT_as = upload(weights, t);
+        bias_as = upload(weights, bias);
     }
     {
         std::vector<float> cat((size_t)2 * C_cond * cdim);
@@ -275,7 +285,7 @@ BigGANPlan* BigGAN::plan(int b) {
     P.S0 = ar.alloc<float>((size_t)b * C_all, true);
     P.S1 = ar.alloc<float>((size_t)b * C_all, true);
     P.G = ar.alloc<float>((size_t)b * 2 * C_cond);
-    P.dcond = ar.alloc<float>((size_t)b * cdim);
+    P.dcond = ar.alloc<float>((size_t)(k_dcond_blocks(2 * C_cond) + k_dcond_blocks(genz_J)) * b * cdim);  // partial sums per row block
     P.dh0 = ar.alloc<float>((size_t)b * genz_J);
     const int nL = (int)blocks.size();
     P.bb.resize(nL);
@@ -545,7 +555,7 @@ int BigGAN::forward(int b, const float* z, const float* c, float* img, cudaStrea
     BigGANPlan& P = *Pp;
     last_plan = Pp;
     k_concat_cond(z, c, P.cond, b, cfg.z_dim, cfg.class_embed_dim, st);
-    k_cond_affine(P.cond, Ws, Wo, mean, inv_std, P.a, P.s, b, cdim, C_cond, C_all, st);
+    k_cond_affine(P.cond, WT_as, bias_as, P.a, P.s, b, cdim, C_cond, C_all, st);
     k_uncond_affine(unc_weight, unc_bias, mean, inv_std, P.a, P.s, b, C_cond, C_last, C_all, st);
     const int bn00 = blocks[0].bn[0];
     // gen_z output is already NHWC: view(b, 4, 4, C0)
@@ -591,7 +601,6 @@ int BigGAN::backward(int b, const float* dimg, float* dz, float* dc, cudaStream_
     const int R = H_out;
     P2L_CUDA_CHECK(cudaMemsetAsync(P.S0, 0, (size_t)b * C_all * sizeof(float), st));
     P2L_CUDA_CHECK(cudaMemsetAsync(P.S1, 0, (size_t)b * C_all * sizeof(float), st));
-    P2L_CUDA_CHECK(cudaMemsetAsync(P.dcond, 0, (size_t)b * cdim * sizeof(float), st));
     // image -> last block output
     k_im2col_rgb_bwd(dimg, P.img, P.col_rgb, b, R, R, 64, grad_scale(), st);  // 16-bit gradients carry grad_scale() from here ...
     if (conv_op_launch(P.d_rgb, st)) return -1;
@@ -631,9 +640,10 @@ int BigGAN::backward(int b, const float* dimg, float* dz, float* dc, cudaStream_
     }
     // BN-affine gradients -> d cond
     k_bn_grad_finalize(P.S0, P.S1, P.a, P.s, mean, inv_std, P.G, b, C_cond, C_all, st);
-    k_dcond_accum(P.G, 2 * C_cond, Wcat, P.dcond, b, 2 * C_cond, cdim, st);
-    k_dcond_accum(P.dh0, genz_J, genz_W, P.dcond, b, genz_J, cdim, st);
-    k_split_dcond(P.dcond, dz, dc, b, cfg.z_dim, cfg.class_embed_dim, scale / grad_scale(), row_scale, st);  // ... to here
+    const int nb_g = k_dcond_blocks(2 * C_cond), nb_z = k_dcond_blocks(genz_J);
+    k_dcond_partial(P.G, 2 * C_cond, Wcat, P.dcond, b, 2 * C_cond, cdim, st);
+    k_dcond_partial(P.dh0, genz_J, genz_W, P.dcond + (size_t)nb_g * b * cdim, b, genz_J, cdim, st);
+    k_dcond_reduce_split(P.dcond, nb_g + nb_z, dz, dc, b, cfg.z_dim, cfg.class_embed_dim, scale / grad_scale(), row_scale, st);  // ... to here
     return 0;
 }
 

@@ -21,7 +21,7 @@ struct BigGAN {
     struct BN { int C, off; bool cond; };
     std::vector<BN> bns;  // conditional ones first (concatenated tables), the final unconditional last
     int C_cond = 0, C_all = 0, cdim = 0;
-    float *Ws = nullptr, *Wo = nullptr;  // cond linears, transposed [cdim][C_cond]
+    float *WT_as = nullptr, *bias_as = nullptr;  // cond -> BN (gain | offset) GEMV with the statistics folded in: [cdim][2*C_cond], [2*C_cond]
     float *mean = nullptr, *inv_std = nullptr;  // [C_all]
     float *unc_weight = nullptr, *unc_bias = nullptr;
     float *Wcat = nullptr;  // [2*C_cond, cdim] rows: Ws then Wo (for dcond)

@@ -24,21 +24,28 @@ static long g_launches = 0;
 void count_launch() { ++g_launches; }
 long launch_count() { return g_launches; }
 
-static int g_tma_out = 1;
+static int g_tma_out = 1, g_tma_kmax = 512;
 static int g_grad_scale = (int)kGradScale;
 float grad_scale() { return (float)g_grad_scale; }
-static int g_halo = 0, g_halo_bo = 0;  // halo patches: correct but no gain at these shapes (profiles/r1_notes.md)
+// halo patches for 3x3 convs: "halo" = patch pitch in pixels (10 | 16), "halo_mode" = 0 off, 1 only where the
+// weight matrix stays resident in shared memory (the 64-channel layers, L2-bandwidth-bound otherwise), 2 every
+// eligible 3x3 conv
+static int g_halo = 10, g_halo_mode = 0, g_halo_bo = 0;  // measured: the per-tap path with 2 CTAs/SM is faster at every BigGAN shape (profiles/)
 void set_option(const char* key, int value) {
     if (!std::strcmp(key, "halo")) g_halo = value;
     else if (!std::strcmp(key, "grad_scale")) g_grad_scale = value > 0 ? value : 1;
     else if (!std::strcmp(key, "halo_bo")) g_halo_bo = value;
+    else if (!std::strcmp(key, "halo_mode")) g_halo_mode = value;
     else if (!std::strcmp(key, "tma_out")) g_tma_out = value;
+    else if (!std::strcmp(key, "tma_kmax")) g_tma_kmax = value;
 }
 int get_option(const char* key) {
     if (!std::strcmp(key, "halo")) return g_halo;
     if (!std::strcmp(key, "grad_scale")) return g_grad_scale;
     if (!std::strcmp(key, "halo_bo")) return g_halo_bo;
+    if (!std::strcmp(key, "halo_mode")) return g_halo_mode;
     if (!std::strcmp(key, "tma_out")) return g_tma_out;
+    if (!std::strcmp(key, "tma_kmax")) return g_tma_kmax;
     return -1;
 }
 
@@ -161,8 +168,10 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     // halo patches: always for the 3-channel rgb head (N = 16 tile: the layer is pure A traffic),
     // optional ("halo" option) elsewhere — measured neutral for N >= 64 (profiles/)
     const int halo_p = (d.BN == 16) ? 0 : g_halo;  // rgb head: N=16 MMAs are issue-bound; per-tap path + 2 CTAs/SM is faster
-    const bool halo = halo_p != 0 && d.kh == 3 && d.kw == 3 && d.pad_h == 1 && d.pad_w == 1 && d.B_batch == 0 &&
-                      d.H >= 12 && d.W >= 8;
+    const long resb_bytes = 9L * d.Cin * d.BN * 2;
+    const bool resb = d.Cout <= d.BN && resb_bytes <= 80 * 1024;
+    const bool halo = halo_p != 0 && g_halo_mode != 0 && (g_halo_mode == 2 || resb) && d.kh == 3 && d.kw == 3 &&
+                      d.pad_h == 1 && d.pad_w == 1 && d.B_batch == 0 && d.H >= 12 && d.W >= 8;
     if (halo) { tw = 8; th = 16; nb = 1; }
     if (d.B_batch > 0 && nb != 1) {
         set_error("conv_op_build: batched B needs >=128 pixels per image (got %dx%d)", d.H, d.W);
@@ -181,6 +190,22 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     p.a_c0 = d.a_c0;
     p.b_batched = d.B_batch > 0 ? 1 : 0;
     p.halo_bo = g_halo_bo;
+    p.halo_resb = (halo && resb) ? 1 : 0;
+    p.halo_sa = 0; p.halo_sb = 0;
+    if (halo) {
+        // shared-memory plan: [patch ring][B tiles (resident matrix | ring)][barriers][coefficient tables]
+        const long patch = (((long)halo_p * 18 * 128 + 1023) / 1024) * 1024, btile = (long)d.BN * kBK * 2;
+        const long fixed = 1024 + 64 * 8 + 6L * d.BN * 4, budget = 227 * 1024 - fixed;
+        if (p.halo_resb) {
+            p.halo_sa = (int)((budget - resb_bytes) / patch);
+        } else {
+            p.halo_sb = d.BN == 256 ? 4 : (d.BN == 128 ? 6 : 8);
+            p.halo_sa = (int)((budget - p.halo_sb * btile) / patch);
+        }
+        if (p.halo_sa > 6) p.halo_sa = 6;
+        if (p.halo_sa < 2) { set_error("conv_op_build: halo plan does not fit shared memory"); return -1; }
+        op->halo_smem = (int)(p.halo_sa * patch + (p.halo_resb ? resb_bytes : p.halo_sb * btile) + fixed);
+    }
     if (p.alpha == 0.f) p.alpha = 1.f;
 
     {   // A: {C, W, H, N}
@@ -200,7 +225,7 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     // ---- epilogue outputs by TMA bulk store: worthwhile where the epilogue dominates (small K)
     const long Ktot = (long)d.kh * d.kw * d.Cin;
     const bool any_out = d.epi.raw || d.epi.act || d.epi.dx;
-    op->tma_out = (g_tma_out && !halo && any_out && (d.BN == 64 || d.BN == 128) && d.Cout % 64 == 0 && Ktot <= 512 &&
+    op->tma_out = (g_tma_out && !halo && any_out && (d.BN == 64 || d.BN == 128) && d.Cout % 64 == 0 && Ktot <= g_tma_kmax &&
                    !d.epi.img_nchw && !(d.epi.addin && d.epi.addin_pool) && (d.epi.resid_shift == 0 || (tw >= 2 && th >= 2)) &&
                    (!d.epi.addin || d.epi.addin_climit % 64 == 0)) ? 1 : 0;
     if (op->tma_out) {
@@ -288,7 +313,7 @@ static int launch_halo_t(const ConvOp& op, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         P2L_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, MODE, P>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
         attr_set = true;
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -306,7 +331,7 @@ static int launch_halo_t(const ConvOp& op, cudaStream_t stream) {
                                op.p.taps_h * op.p.taps_w * op.p.cin_chunks * kBK});
         cudaEventRecord(e0, stream);
     }
-    conv3x3_halo_kernel<BN, MODE, P><<<op.grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(op.tmA, op.tmB, op.p);
+    conv3x3_halo_kernel<BN, MODE, P><<<op.grid, Cfg::kThreads, op.halo_smem, stream>>>(op.tmA, op.tmB, op.p);
     if (g_prof) cudaEventRecord(e1, stream);
     count_launch();
     P2L_CUDA_CHECK(cudaGetLastError());

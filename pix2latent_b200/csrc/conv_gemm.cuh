@@ -51,6 +51,9 @@ struct ConvGemmParams {
     int a_c0;        // channel offset into the A tensor
     int b_batched;   // B tensor map's 3rd coordinate = image index
     int halo_bo;     // halo kernel: fill the descriptor's base-offset field from the start address
+    int halo_resb;   // halo kernel: the whole weight matrix (9 * cin_chunks tiles) stays resident in shared memory
+    int halo_sa;     // halo kernel: A patch ring depth
+    int halo_sb;     // halo kernel: B tile ring depth (non-resident)
     // ---- epilogue, forward
     float alpha;             // scale on the accumulator
     const float* alpha_ptr;  // optional device scalar multiplied into alpha (attention gamma); both modes
@@ -151,8 +154,69 @@ __device__ __forceinline__ void slab_add_row(const uint8_t* buf, int row, int pi
 }
 __device__ __forceinline__ void slab_add_row(const uint8_t*, int, int, float (&)[16]) {}
 
+// Row-per-thread global access helpers: CH 16-bit values (CH*2 bytes) of one pixel row. `wide`: the row
+// pitch keeps every chunk 32-byte aligned, so 256-bit accesses are legal.
+__device__ __forceinline__ bool wide_ok(const void* base, int row_pitch_bytes) {
+    return ((reinterpret_cast<uintptr_t>(base) | static_cast<uintptr_t>(row_pitch_bytes)) & 31) == 0;
+}
+__device__ __forceinline__ uint4 pack8_act(const float* v) {
+    return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+__device__ __forceinline__ void acc8_act(const uint4 t, float* v) {
+    v[0] += bf16_lo(t.x); v[1] += bf16_hi(t.x); v[2] += bf16_lo(t.y); v[3] += bf16_hi(t.y);
+    v[4] += bf16_lo(t.z); v[5] += bf16_hi(t.z); v[6] += bf16_lo(t.w); v[7] += bf16_hi(t.w);
+}
+template <int CH>
+__device__ __forceinline__ void row_store(act_t* dst, const float (&v)[CH], bool wide) {
+    if (CH == 32 && wide) {
+#pragma unroll
+        for (int q = 0; q < CH / 16; ++q) stg256(dst + q * 16, pack8_act(v + q * 16), pack8_act(v + q * 16 + 8));
+    } else {
+#pragma unroll
+        for (int q = 0; q < CH / 8; ++q) reinterpret_cast<uint4*>(dst)[q] = pack8_act(v + q * 8);
+    }
+}
+template <int CH>
+__device__ __forceinline__ void row_store_packed(act_t* dst, const uint4 (&o)[CH / 8], bool wide) {
+    if (CH == 32 && wide) {
+#pragma unroll
+        for (int q = 0; q < CH / 16; ++q) stg256(dst + q * 16, o[2 * q], o[2 * q + 1]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < CH / 8; ++q) reinterpret_cast<uint4*>(dst)[q] = o[q];
+    }
+}
+// v[0..CH) += row
+template <int CH>
+__device__ __forceinline__ void row_load_add(const act_t* src, float (&v)[CH], bool wide) {
+    if (CH == 32 && wide) {
+#pragma unroll
+        for (int q = 0; q < CH / 16; ++q) {
+            uint4 a, b;
+            ldg256(src + q * 16, a, b);
+            acc8_act(a, v + q * 16);
+            acc8_act(b, v + q * 16 + 8);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < CH / 8; ++q) acc8_act(__ldg(reinterpret_cast<const uint4*>(src) + q), v + q * 8);
+    }
+}
+template <int CH>
+__device__ __forceinline__ void row_store_f32(float* dst, const float (&v)[CH], bool wide) {
+    if (wide) {
+#pragma unroll
+        for (int q = 0; q < CH / 8; ++q)
+            stg256(dst + q * 8, make_uint4(__float_as_uint(v[q * 8]), __float_as_uint(v[q * 8 + 1]), __float_as_uint(v[q * 8 + 2]), __float_as_uint(v[q * 8 + 3])),
+                   make_uint4(__float_as_uint(v[q * 8 + 4]), __float_as_uint(v[q * 8 + 5]), __float_as_uint(v[q * 8 + 6]), __float_as_uint(v[q * 8 + 7])));
+    } else {
+#pragma unroll
+        for (int q = 0; q < CH / 4; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    }
+}
+
 // Direct epilogue: every thread reads / writes the global rows of its own accumulator row.
-template <int BN, int MODE, int CH, bool TMA_OUT>
+template <int BN, int MODE, int CH, bool TMA_OUT, int NG>
 __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, const CUtensorMap* tmo, uint8_t* obuf,
                                                      uint64_t* in_full, uint64_t* in_empty, uint64_t* tfull_bar,
                                                      uint64_t* tempty_bar, uint32_t tmem_base, int total_tiles, int warp,
@@ -164,21 +228,22 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
     // TMA_OUT: tmo[0] = raw / dx, tmo[1] = act, tmo[2] = act on the 2x grid (5-D view), tmo[3] = act_lo;
     // obuf = [2 output slabs][kInSlots input slabs]; input slabs arrive through in_full / in_empty
     constexpr int NIN = GemmCfg<BN, TMA_OUT>::kInSlots;
-    constexpr int NG = GemmCfg<BN, TMA_OUT>::kEpiGroups;
     const int grp = (NG == 2) ? ((warp - 2) >> 2) : 0;  // epilogue group = TMEM accumulator stage it drains
     const bool storer = TMA_OUT && ((warp - 2) & 3) == 0 && lane == 0;
-    uint8_t* inbuf = obuf + 4 * kATileBytes;
-    obuf += grp * 2 * kATileBytes;  // this group's {raw | dx, act} slab pair
+    uint8_t* inbuf = nullptr;
+    constexpr int RING = (NIN >= NG) ? NIN / NG : 1;
+    if constexpr (TMA_OUT) {
+        // each group has its own ring of RING input slots, filled by the loader warp in this group's
+        // consumption order (an mbarrier parity wait is only safe for an in-order consumer)
+        inbuf = obuf + (4 + grp * RING) * kATileBytes;
+        in_full += grp * RING;
+        in_empty += grp * RING;
+        obuf += grp * 2 * kATileBytes;  // this group's {raw | dx, act} slab pair
+    }
     // one output tensor only (dgrad, or act without raw): the two slabs of the pair double-buffer it
     const bool single_out = (MODE == EPI_BWD) || (p.raw == nullptr);
     int slab_no = 0;
     uint8_t *s_raw = obuf, *s_act = obuf;
-    // each group has its own ring of RING input slots, filled by the loader warp in this group's
-    // consumption order (an mbarrier parity wait is only safe for an in-order consumer)
-    constexpr int RING = (NIN >= NG) ? NIN / NG : 1;
-    inbuf += grp * RING * kATileBytes;
-    in_full += grp * RING;
-    in_empty += grp * RING;
     int in_cnt = 0;               // input slabs this group has consumed
     int slot0 = 0, slot1 = 0;     // slots of the current 64-channel slab
     bool has0 = false, has1 = false;
@@ -205,6 +270,9 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 
         float* tab = ctab + (it & 1) * 3 * BN;
         if (use_tab) {
+            // two groups without the slab barriers of the TMA path: this group's previous tile used the
+            // same table half, so every warp must have finished reading it
+            if constexpr (NG == 2 && !TMA_OUT) bar_epilogue(grp);
             const int et = ((warp - 2) & 3) * 32 + lane;  // 0..127 within the group
             const int nn = min(tni * p.nb, p.NI - 1);
             for (int j = et; j < BN; j += 128) {
@@ -296,15 +364,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 } else if (p.resid && valid) {
                     const int Hs = p.H >> p.resid_shift, Ws = p.W >> p.resid_shift;
                     const long rp = (static_cast<long>(n) * Hs + (h >> p.resid_shift)) * Ws + (w >> p.resid_shift);
-                    const uint4* src = reinterpret_cast<const uint4*>(p.resid + rp * p.resid_C + cbase);
-#pragma unroll
-                    for (int q = 0; q < CH / 8; ++q) {
-                        const uint4 t = __ldg(src + q);
-                        v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
-                        v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
-                        v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
-                        v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
-                    }
+                    row_load_add<CH>(p.resid + rp * p.resid_C + cbase, v, wide_ok(p.resid, p.resid_C * 2));
                 }
                 if (p.img_nchw) {
                     if (valid) {
@@ -317,19 +377,12 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     }
                 }
                 if (p.raw_f32 && valid) {
-                    float4* dst = reinterpret_cast<float4*>(p.raw_f32 + pix * p.raw_f32_C + cbase);
-#pragma unroll
-                    for (int q = 0; q < CH / 4; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                    row_store_f32<CH>(p.raw_f32 + pix * p.raw_f32_C + cbase, v, wide_ok(p.raw_f32, p.raw_f32_C * 4));
                 }
                 if constexpr (TMA_OUT) {
                     if (p.raw) slab_put_row(s_raw, row, (c & 32) >> 3, v);
                 } else if (p.raw && valid) {
-                    uint4* dst = reinterpret_cast<uint4*>(p.raw + pix * p.raw_C + cbase);
-#pragma unroll
-                    for (int q = 0; q < CH / 8; ++q) {
-                        dst[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                                            pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
-                    }
+                    row_store<CH>(p.raw + pix * p.raw_C + cbase, v, wide_ok(p.raw, p.raw_C * 2));
                 }
                 if (p.act) {
                     if (p.aff_a && use_tab) {
@@ -369,10 +422,9 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                             o[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
                                               pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
                         }
+                        const bool wide = wide_ok(p.act, p.act_C * 2) && (!p.act_lo || wide_ok(p.act_lo, 32));
                         if (!p.act_up) {
-                            uint4* dst = reinterpret_cast<uint4*>(p.act + pix * p.act_C + cbase);
-#pragma unroll
-                            for (int q = 0; q < CH / 8; ++q) dst[q] = o[q];
+                            row_store_packed<CH>(p.act + pix * p.act_C + cbase, o, wide);
                         } else {
                             const int W2 = p.W * 2, H2 = p.H * 2;
 #pragma unroll
@@ -380,16 +432,10 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 #pragma unroll
                                 for (int dxx = 0; dxx < 2; ++dxx) {
                                     const long hp = (static_cast<long>(n) * H2 + 2 * h + dy) * W2 + 2 * w + dxx;
-                                    uint4* dst = reinterpret_cast<uint4*>(p.act + hp * p.act_C + cbase);
-#pragma unroll
-                                    for (int q = 0; q < CH / 8; ++q) dst[q] = o[q];
+                                    row_store_packed<CH>(p.act + hp * p.act_C + cbase, o, wide);
                                 }
                             }
-                            if (p.act_lo) {
-                                uint4* dst = reinterpret_cast<uint4*>(p.act_lo + pix * p.act_C + cbase);
-#pragma unroll
-                                for (int q = 0; q < CH / 8; ++q) dst[q] = o[q];
-                            }
+                            if (p.act_lo) row_store_packed<CH>(p.act_lo + pix * p.act_C + cbase, o, wide);
                         }
                     }
                 }
@@ -404,15 +450,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     for (int j = 0; j < CH; ++j) v[j] = (valid && y[j] > 0.f) ? v[j] : 0.f;
                 } else if (p.saved) {
                     if (valid) {
-                        const uint4* src = reinterpret_cast<const uint4*>(p.saved + pix * p.saved_C + cbase);
-#pragma unroll
-                        for (int q = 0; q < CH / 8; ++q) {
-                            const uint4 t = __ldg(src + q);
-                            y[q * 8 + 0] = bf16_lo(t.x); y[q * 8 + 1] = bf16_hi(t.x);
-                            y[q * 8 + 2] = bf16_lo(t.y); y[q * 8 + 3] = bf16_hi(t.y);
-                            y[q * 8 + 4] = bf16_lo(t.z); y[q * 8 + 5] = bf16_hi(t.z);
-                            y[q * 8 + 6] = bf16_lo(t.w); y[q * 8 + 7] = bf16_hi(t.w);
-                        }
+                        row_load_add<CH>(p.saved + pix * p.saved_C + cbase, y, wide_ok(p.saved, p.saved_C * 2));  // y starts at 0
                     } else {
 #pragma unroll
                         for (int j = 0; j < CH; ++j) y[j] = 0.f;
@@ -477,15 +515,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     if (has1) slab_add_row(inbuf + slot1 * kATileBytes, row, (c & 32) >> 3, v);
                 } else if (p.addin && valid && cbase < p.addin_climit) {
                     if (!p.addin_pool) {
-                        const uint4* src = reinterpret_cast<const uint4*>(p.addin + pix * p.addin_C + cbase);
-#pragma unroll
-                        for (int q = 0; q < CH / 8; ++q) {
-                            const uint4 t = __ldg(src + q);
-                            v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
-                            v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
-                            v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
-                            v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
-                        }
+                        row_load_add<CH>(p.addin + pix * p.addin_C + cbase, v, wide_ok(p.addin, p.addin_C * 2));
                     } else {
                         const int W2 = p.W * 2, H2 = p.H * 2;
 #pragma unroll
@@ -493,15 +523,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 #pragma unroll
                             for (int dxx = 0; dxx < 2; ++dxx) {
                                 const long hp = (static_cast<long>(n) * H2 + 2 * h + dy) * W2 + 2 * w + dxx;
-                                const uint4* src = reinterpret_cast<const uint4*>(p.addin + hp * p.addin_C + cbase);
-#pragma unroll
-                                for (int q = 0; q < CH / 8; ++q) {
-                                    const uint4 t = __ldg(src + q);
-                                    v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
-                                    v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
-                                    v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
-                                    v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
-                                }
+                                row_load_add<CH>(p.addin + hp * p.addin_C + cbase, v, wide_ok(p.addin, p.addin_C * 2));
                             }
                         }
                     }
@@ -511,17 +533,10 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 }
                 if (valid) {
                     if (!TMA_OUT && p.dx) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.dx + pix * p.dx_C + cbase);
-#pragma unroll
-                        for (int q = 0; q < CH / 8; ++q) {
-                            dst[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                                                pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
-                        }
+                        row_store<CH>(p.dx + pix * p.dx_C + cbase, v, wide_ok(p.dx, p.dx_C * 2));
                     }
                     if (p.dx_f32) {
-                        float4* dst = reinterpret_cast<float4*>(p.dx_f32 + pix * p.dx_f32_C + cbase);
-#pragma unroll
-                        for (int q = 0; q < CH / 4; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                        row_store_f32<CH>(p.dx_f32 + pix * p.dx_f32_C + cbase, v, wide_ok(p.dx_f32, p.dx_f32_C * 4));
                     }
                 }
             }
@@ -727,7 +742,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        epilogue_loop_direct<BN, MODE, CH, TMA_OUT>(p, tmO.m, obuf, in_full, in_empty, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane,
+        epilogue_loop_direct<BN, MODE, CH, TMA_OUT, Cfg::kEpiGroups>(p, tmO.m, obuf, in_full, in_empty, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane,
                                                     reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + Cfg::kOutBytes + 256));
     }
 
@@ -752,24 +767,30 @@ struct HaloCfg {
     static constexpr int kPatchTx = P * (kTh + 2) * 128;
     static constexpr int kPatchBytes = ((kPatchTx + 1023) / 1024) * 1024;
     static constexpr int kBTileBytes = BN * kBK * 2;
-    static constexpr int kAStages = (P == 16 && BN == 256) ? 2 : 3;
-    static constexpr int kBStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int kRingBytes = kAStages * kPatchBytes + kBStages * kBTileBytes;
+    static constexpr int kThreads = 64 + 2 * 128;   // TMA, MMA, two epilogue groups (one per TMEM stage)
+    static constexpr int kMaxBars = 64;             // 8-byte slots reserved for barriers
     static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = kRingBytes + 1024 + 256 + 6 * BN * 4;
+    static constexpr int kFixedBytes = 1024 /*align slack*/ + kMaxBars * 8 + 6 * BN * 4 /*coefficient tables*/;
+    static constexpr int kMaxSmem = 227 * 1024;
 };
 
+// Weights: when the whole [BN x 9*Cin] matrix fits next to the patch ring (p.halo_resb; the 64-channel
+// layers), it is loaded ONCE per persistent CTA and stays resident — per tile only the patch moves.
 template <int BN, int MODE, int P>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(HaloCfg<BN, P>::kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const ConvGemmParams p) {
     using Cfg = HaloCfg<BN, P>;
-    constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
     constexpr int CH = (BN >= 32) ? 32 : 16;
+    const int SA = p.halo_sa;
+    const bool resb = p.halo_resb != 0;
+    const int SB = resb ? 1 : p.halo_sb;                       // barrier pairs of the B ring
+    const int nB = resb ? 9 * p.cin_chunks : p.halo_sb;        // B tiles held in shared memory
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smemB = smem + SA * Cfg::kPatchBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kRingBytes);
+    uint8_t* tail = smemB + nB * Cfg::kBTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
     uint64_t* afull = bars;
     uint64_t* aempty = bars + SA;
     uint64_t* bfull = bars + 2 * SA;
@@ -805,6 +826,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) {
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
+            if (resb && static_cast<int>(blockIdx.x) < total_tiles) {
+                mbar_expect_tx(&bfull[0], nB * Cfg::kBTileBytes);
+                for (int tap = 0; tap < 9; ++tap)
+                    for (int cc = 0; cc < p.cin_chunks; ++cc)
+                        tma_load_3d(smemB + (tap * p.cin_chunks + cc) * Cfg::kBTileBytes, &tmB, &bfull[0], tap * Cin + cc * kBK, 0, 0);
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
                 const int w0 = (m_tile % p.tiles_w) * Cfg::kTw;
@@ -815,6 +842,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_expect_tx(&afull[sa], Cfg::kPatchTx);
                     tma_load_4d(smem + sa * Cfg::kPatchBytes, &tmA, &afull[sa], p.a_c0 + cc * kBK, w0 - 1, h0 - 1, n0);
                     if (++sa == SA) { sa = 0; pa ^= 1; }
+                    if (resb) continue;
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait(&bempty[sb], pb ^ 1);
                         mbar_expect_tx(&bfull[sb], Cfg::kBTileBytes);
@@ -830,6 +858,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             int it = 0;
+            if (resb && static_cast<int>(blockIdx.x) < total_tiles) mbar_wait(&bfull[0], 0);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
@@ -838,21 +867,30 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t d_tmem = tmem_base + as * BN;
                 for (int cc = 0; cc < p.cin_chunks; ++cc) {
                     mbar_wait(&afull[sa], pa);
+                    tc_fence_after();
                     const uint32_t a_base = smem_u32(smem + sa * Cfg::kPatchBytes);
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(&bfull[sb], pb);
-                        tc_fence_after();
+                        uint32_t b_addr;
+                        if (resb) {
+                            b_addr = smem_u32(smemB + (tap * p.cin_chunks + cc) * Cfg::kBTileBytes);
+                        } else {
+                            mbar_wait(&bfull[sb], pb);
+                            tc_fence_after();
+                            b_addr = smem_u32(smemB + sb * Cfg::kBTileBytes);
+                        }
                         const int r = tap / 3, s = tap - 3 * r;
                         const uint32_t a_addr = a_base + (r * P + s) * 128;
                         const uint64_t adesc = umma_desc_sw128(a_addr, P * 128, p.halo_bo ? (a_addr >> 7) : 0);
-                        const uint64_t bdesc = umma_desc_k128(smem_u32(smemB + sb * Cfg::kBTileBytes));
+                        const uint64_t bdesc = umma_desc_k128(b_addr);
 #pragma unroll
                         for (int k = 0; k < kBK / 16; ++k) {
                             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cc | tap | k) != 0);
                         }
-                        umma_commit(&bempty[sb]);
-                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                        if (!resb) {
+                            umma_commit(&bempty[sb]);
+                            if (++sb == SB) { sb = 0; pb ^= 1; }
+                        }
                     }
                     umma_commit(&aempty[sa]);
                     if (++sa == SA) { sa = 0; pa ^= 1; }
@@ -861,8 +899,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {
-        epilogue_loop_direct<BN, MODE, CH, false>(p, nullptr, nullptr, nullptr, nullptr, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane,
-                                                  reinterpret_cast<float*>(smem + Cfg::kRingBytes + 256));
+        epilogue_loop_direct<BN, MODE, CH, false, 2>(p, nullptr, nullptr, nullptr, nullptr, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane,
+                                                     reinterpret_cast<float*>(tail + Cfg::kMaxBars * 8));
     }
     tc_fence_before();
     __syncthreads();

@@ -32,6 +32,7 @@ struct ConvOp {
     ConvGemmParams p;
     int BN, mode, grid;
     int halo;  // 0: per-tap A loads; 10 / 16: halo-patch kernel with that patch row pitch
+    int halo_smem;  // dynamic shared memory of the halo kernel for this plan
     double flops;  // algorithmic 2*M*N*K of this launch
 };
 
@@ -44,7 +45,7 @@ const char* get_error();
 int num_sms();
 void count_launch();  // every kernel launch of the library is counted (bench.py gpu_launches)
 long launch_count();
-// tuning / experiment switches: "halo" (0 off, 10, 16), "halo_bo" (0/1)
+// tuning / experiment switches: "halo" (patch pitch 10 | 16), "halo_mode" (0 off, 1 resident-weight layers, 2 all 3x3), "halo_bo" (0/1), "tma_out", "tma_kmax", "grad_scale"
 // Static loss scale carried by 16-bit gradients (act_type.h); default kGradScale, option "grad_scale".
 float grad_scale();
 void set_option(const char* key, int value);

@@ -37,52 +37,113 @@ void k_concat_cond(const float* z, const float* c, float* cond, int b, int zd, i
 
 // thread per channel; weights stored transposed ([cdim][C]) so that a warp reads 128 contiguous
 // bytes per k; cond staged in shared memory (broadcast reads); 8 samples per register pass
-__global__ void cond_affine_kernel(const float* __restrict__ cond, const float* __restrict__ WsT,
-                                   const float* __restrict__ WoT, const float* __restrict__ mean,
-                                   const float* __restrict__ inv_std, float* a, float* s, int b,
-                                   int cdim, int C, int stride) {
-    extern __shared__ float sc[];  // [b, cdim]
-    for (int i = threadIdx.x; i < b * cdim; i += blockDim.x) sc[i] = cond[i];
-    __syncthreads();
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= C) return;
-    const float m = mean[ch], is = inv_std[ch];
-    for (int b0 = 0; b0 < b; b0 += 12) {
-        float as[12], ao[12];
+// ---- small-batch GEMV family: y[bi][j] = bias[j] + sum_k x[bi][k] * WT[k][j]
+// (cond -> BN gains/offsets, cond -> gen_z). Batches of <= 24 rows ride along a single pass over
+// the fp32 weights: one thread owns 4 consecutive outputs j (one 16-byte weight load per k) for a
+// quarter of the k range and 24 x 4 accumulators; x is staged transposed and zero-padded in shared
+// memory so 24 rows of one k come back in six broadcast LDS.128 — 96 FMAs per 7 memory
+// instructions. The four k-quarters sit in one warp and meet through two xor-shuffles.
+constexpr int kGvB = 24;
+constexpr int kGvU = 8;   // weight loads in flight per thread
+
+__device__ __forceinline__ void gv_stage_x(const float* __restrict__ x, int ldx, int b0, int b, int K, int k0, float* xs) {
+    // xs[k][24] = x[b0 + i][k0 + k], zero beyond row b
+    for (int i = threadIdx.x; i < K * kGvB; i += blockDim.x) {
+        const int k = i / kGvB, bi = i - k * kGvB;
+        xs[i] = (b0 + bi < b) ? x[(long)(b0 + bi) * ldx + k0 + k] : 0.f;
+    }
+}
+__device__ __forceinline__ void gv_fma(float (&acc)[kGvB][4], const float4* xs4, int k, const float4 w) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) { as[i] = 0.f; ao[i] = 0.f; }
-        for (int k0 = 0; k0 < cdim; k0 += 8) {
-            float ws[8], wo[8];
+    for (int q = 0; q < kGvB / 4; ++q) {
+        const float4 xv = xs4[k * (kGvB / 4) + q];
+        const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {  // 16 independent loads in flight per thread
-                ws[u] = __ldg(WsT + (long)(k0 + u) * C + ch);
-                wo[u] = __ldg(WoT + (long)(k0 + u) * C + ch);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-#pragma unroll
-                for (int i = 0; i < 12; ++i) {
-                    const float cv = sc[min(b0 + i, b - 1) * cdim + k0 + u];
-                    as[i] = fmaf(cv, ws[u], as[i]);
-                    ao[i] = fmaf(cv, wo[u], ao[i]);
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            if (b0 + i < b) {
-                const float av = (1.f + as[i]) * is;
-                a[(long)(b0 + i) * stride + ch] = av;
-                s[(long)(b0 + i) * stride + ch] = ao[i] - m * av;
-            }
+        for (int r = 0; r < 4; ++r) {
+            acc[q * 4 + r][0] = fmaf(xr[r], w.x, acc[q * 4 + r][0]);
+            acc[q * 4 + r][1] = fmaf(xr[r], w.y, acc[q * 4 + r][1]);
+            acc[q * 4 + r][2] = fmaf(xr[r], w.z, acc[q * 4 + r][2]);
+            acc[q * 4 + r][3] = fmaf(xr[r], w.w, acc[q * 4 + r][3]);
         }
     }
 }
-void k_cond_affine(const float* cond, const float* WsT, const float* WoT, const float* mean,
-                   const float* inv_std, float* a, float* s, int b, int cdim, int C_cond, int stride,
-                   cudaStream_t st) {
-    cond_affine_kernel<<<cdiv(C_cond, 64), 64, (size_t)b * cdim * sizeof(float), st>>>(
-        cond, WsT, WoT, mean, inv_std, a, s, b, cdim, C_cond, stride); count_launch();
+
+struct GvEpi {
+    // EPI 0: fp32 outputs, columns [0, split) -> out0, [split, J) -> out1, row stride `stride`
+    float *out0, *out1;
+    int split, stride;
+    // EPI 1 (gen_z): 16-bit raw = y and act = relu(a[bi][j % C] * y + s[bi][j % C]), row length J
+    const float *a, *s;
+    int aff_stride, C;
+    bf16 *raw, *act;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(128) gemv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ WT,
+                                                       const float* __restrict__ bias, int b, int cdim, int J,
+                                                       const GvEpi e) {
+    extern __shared__ float4 gv_smem[];
+    float* xs = reinterpret_cast<float*>(gv_smem);
+    const int b0 = blockIdx.y * kGvB;
+    gv_stage_x(x, cdim, b0, b, cdim, 0, xs);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kq = lane >> 3;
+    const int j = (blockIdx.x * 4 + warp) * 32 + (lane & 7) * 4;
+    const bool live = j < J;  // J % 4 == 0
+    float acc[kGvB][4];
+#pragma unroll
+    for (int i = 0; i < kGvB; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    if (live) {
+        const float* wp = WT + j;
+        for (int k = kq; k < cdim; k += 4 * kGvU) {
+            float4 w[kGvU];
+#pragma unroll
+            for (int u = 0; u < kGvU; ++u)
+                w[u] = (k + 4 * u < cdim) ? __ldg(reinterpret_cast<const float4*>(wp + (long)(k + 4 * u) * J)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < kGvU; ++u)
+                if (k + 4 * u < cdim) gv_fma(acc, gv_smem, k + 4 * u, w[u]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kGvB; ++i) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            acc[i][c] += __shfl_xor_sync(0xffffffffu, acc[i][c], 8);
+            acc[i][c] += __shfl_xor_sync(0xffffffffu, acc[i][c], 16);
+        }
+    }
+    if (!live) return;
+    const float4 bj = bias ? __ldg(reinterpret_cast<const float4*>(bias + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kGvB; ++i) {
+        if ((i & 3) != kq || b0 + i >= b) continue;   // the four k-quarter lanes share the rows
+        const int bi = b0 + i;
+        const float4 y = make_float4(acc[i][0] + bj.x, acc[i][1] + bj.y, acc[i][2] + bj.z, acc[i][3] + bj.w);
+        if constexpr (EPI == 0) {
+            float* dst = (j < e.split) ? e.out0 + (long)bi * e.stride + j : e.out1 + (long)bi * e.stride + (j - e.split);
+            *reinterpret_cast<float4*>(dst) = y;
+        } else {
+            const int ch = j % e.C;
+            const float4 av = __ldg(reinterpret_cast<const float4*>(e.a + (long)bi * e.aff_stride + ch));
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(e.s + (long)bi * e.aff_stride + ch));
+            *reinterpret_cast<uint2*>(e.raw + (long)bi * J + j) = make_uint2(pack_act(y.x, y.y), pack_act(y.z, y.w));
+            *reinterpret_cast<uint2*>(e.act + (long)bi * J + j) =
+                make_uint2(pack_act(fmaxf(fmaf(av.x, y.x, sv.x), 0.f), fmaxf(fmaf(av.y, y.y, sv.y), 0.f)),
+                           pack_act(fmaxf(fmaf(av.z, y.z, sv.z), 0.f), fmaxf(fmaf(av.w, y.w, sv.w), 0.f)));
+        }
+    }
+}
+// BN affine tables: [a | s][bi][ch] = bias_as[ch] + cond[bi] . WT_as[:, ch]; the BN statistics are folded
+// into WT_as / bias_as when the weights are packed (biggan.cu finalize)
+void k_cond_affine(const float* cond, const float* WT_as, const float* bias_as, float* a, float* s, int b, int cdim,
+                   int C_cond, int stride, cudaStream_t st) {
+    GvEpi e{};
+    e.out0 = a; e.out1 = s; e.split = C_cond; e.stride = stride;
+    const dim3 grid(cdiv(2 * C_cond, 128), cdiv(b, kGvB));
+    gemv_fwd_kernel<0><<<grid, 128, (size_t)cdim * kGvB * sizeof(float), st>>>(cond, WT_as, bias_as, b, cdim, 2 * C_cond, e);
+    count_launch();
 }
 
 __global__ void uncond_affine_kernel(const float* weight, const float* bias, const float* mean,
@@ -101,47 +162,13 @@ void k_uncond_affine(const float* weight, const float* bias, const float* mean, 
                                                                      C_cond, C_unc, stride); count_launch();
 }
 
-__global__ void gen_z_kernel(const float* __restrict__ cond, const float* __restrict__ WT,
-                             const float* __restrict__ bias, const float* __restrict__ a,
-                             const float* __restrict__ s, int aff_stride, bf16* raw, bf16* act, int b,
-                             int cdim, int J, int C) {
-    extern __shared__ float sc[];
-    for (int i = threadIdx.x; i < b * cdim; i += blockDim.x) sc[i] = cond[i];
-    __syncthreads();
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= J) return;
-    const int ch = j % C;
-    const float bj = bias[j];
-    for (int b0 = 0; b0 < b; b0 += 24) {
-        float acc[24];
-#pragma unroll
-        for (int i = 0; i < 24; ++i) acc[i] = 0.f;
-        for (int k0 = 0; k0 < cdim; k0 += 8) {
-            float w[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) w[u] = __ldg(WT + (long)(k0 + u) * J + j);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-#pragma unroll
-                for (int i = 0; i < 24; ++i) acc[i] = fmaf(sc[min(b0 + i, b - 1) * cdim + k0 + u], w[u], acc[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 24; ++i) {
-            const int bi = b0 + i;
-            if (bi < b) {
-                const float h = acc[i] + bj;
-                raw[(long)bi * J + j] = f2b(h);
-                const float y = fmaf(a[(long)bi * aff_stride + ch], h, s[(long)bi * aff_stride + ch]);
-                act[(long)bi * J + j] = f2b(fmaxf(y, 0.f));
-            }
-        }
-    }
-}
 void k_gen_z(const float* cond, const float* WT, const float* bias, const float* a, const float* s,
              int aff_stride, bf16* raw, bf16* act, int b, int cdim, int J, int C, cudaStream_t st) {
-    gen_z_kernel<<<cdiv(J, 64), 64, (size_t)b * cdim * sizeof(float), st>>>(
-        cond, WT, bias, a, s, aff_stride, raw, act, b, cdim, J, C); count_launch();
+    GvEpi e{};
+    e.a = a; e.s = s; e.aff_stride = aff_stride; e.C = C; e.raw = raw; e.act = act;
+    const dim3 grid(cdiv(J, 128), cdiv(b, kGvB));
+    gemv_fwd_kernel<1><<<grid, 128, (size_t)cdim * kGvB * sizeof(float), st>>>(cond, WT, bias, b, cdim, J, e);
+    count_launch();
 }
 
 __global__ void bn_grad_finalize_kernel(const float* S0, const float* S1, const float* a, const float* s,
@@ -164,44 +191,71 @@ void k_bn_grad_finalize(const float* S0, const float* S1, const float* a, const 
                                                                          C_cond, stride); count_launch();
 }
 
-// dcond[b,k] += sum_j G[b,j] W[j,k]; block = cdim threads (one per k), 128 rows of W per block
-constexpr int kDcRows = 64;
-__global__ void dcond_accum_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ W,
-                                   float* dcond, int b, int J, int cdim) {
-    extern __shared__ float sg[];  // [b][kDcRows]
+// ---- transposed GEMV: dcond[bi][k] = sum_j G[bi][j] * W[j][k] (J ~ 10^4..10^5 rows, cdim = 256 columns).
+// Pass 1: block = kDcRows rows of W, thread = 4 consecutive k (one 16-byte load per row), 24 x 4
+// accumulators, G slice staged transposed in shared memory (same inner loop as gemv_fwd_kernel);
+// partial sums go to partial[block][bi][k] — no atomics. Pass 2 (dcond_reduce_split_kernel) sums the
+// partials of both operands and writes dz / dc.
+constexpr int kDcRows = 128;
+__global__ void __launch_bounds__(64) dcond_partial_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ W,
+                                                          float* __restrict__ partial, int b, int J, int cdim) {
+    extern __shared__ float4 gv_smem[];
+    float* gs = reinterpret_cast<float*>(gv_smem);
     const int j0 = blockIdx.x * kDcRows;
     const int nj = min(kDcRows, J - j0);
-    for (int i = threadIdx.x; i < b * kDcRows; i += blockDim.x) {
-        const int bi = i / kDcRows, jj = i % kDcRows;
-        sg[i] = jj < nj ? G[(long)bi * ldg + j0 + jj] : 0.f;
+    const int b0 = blockIdx.y * kGvB;
+    for (int i = threadIdx.x; i < kDcRows * kGvB; i += blockDim.x) {
+        const int bi = i / kDcRows, jj = i - bi * kDcRows;   // coalesced along j
+        gs[jj * kGvB + bi] = (jj < nj && b0 + bi < b) ? G[(long)(b0 + bi) * ldg + j0 + jj] : 0.f;
     }
     __syncthreads();
-    const int k = threadIdx.x;
-    if (k >= cdim) return;
-    for (int b0 = 0; b0 < b; b0 += 24) {
-        float acc[24];
+    const int k = threadIdx.x * 4;
+    float acc[kGvB][4];
 #pragma unroll
-        for (int i = 0; i < 24; ++i) acc[i] = 0.f;
-        for (int jj0 = 0; jj0 < nj; jj0 += 8) {
-            float w[8];
+    for (int i = 0; i < kGvB; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    const float* wp = W + (long)j0 * cdim + k;
+    for (int jj = 0; jj < nj; jj += kGvU) {
+        float4 w[kGvU];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) w[u] = (jj0 + u < nj) ? __ldg(W + (long)(j0 + jj0 + u) * cdim + k) : 0.f;
+        for (int u = 0; u < kGvU; ++u)
+            w[u] = (jj + u < nj) ? __ldg(reinterpret_cast<const float4*>(wp + (long)(jj + u) * cdim)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-#pragma unroll
-                for (int i = 0; i < 24; ++i) acc[i] = fmaf(sg[min(b0 + i, b - 1) * kDcRows + jj0 + u], w[u], acc[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 24; ++i) {
-            if (b0 + i < b) atomicAdd(dcond + (long)(b0 + i) * cdim + k, acc[i]);
-        }
+        for (int u = 0; u < kGvU; ++u) gv_fma(acc, gv_smem, jj + u, w[u]);   // rows beyond nj are zero in gs
     }
+    float* dst = partial + ((long)blockIdx.x * b + b0) * cdim + k;
+#pragma unroll
+    for (int i = 0; i < kGvB; ++i)
+        if (b0 + i < b) *reinterpret_cast<float4*>(dst + (long)i * cdim) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
 }
-void k_dcond_accum(const float* G, int ldg, const float* W, float* dcond, int b, int J, int cdim,
-                   cudaStream_t st) {
-    dcond_accum_kernel<<<cdiv(J, kDcRows), cdim, (size_t)b * kDcRows * sizeof(float), st>>>(G, ldg, W, dcond, b, J,
-                                                                                          cdim); count_launch();
+int k_dcond_blocks(int J) { return cdiv(J, kDcRows); }
+void k_dcond_partial(const float* G, int ldg, const float* W, float* partial, int b, int J, int cdim, cudaStream_t st) {
+    const dim3 grid(cdiv(J, kDcRows), cdiv(b, kGvB));
+    dcond_partial_kernel<<<grid, cdim / 4, (size_t)kDcRows * kGvB * sizeof(float), st>>>(G, ldg, W, partial, b, J, cdim);
+    count_launch();
+}
+// dcond = sum over nblk partial blocks; split into dz | dc with the step's gradient scale. block = (64 k, 8 slices)
+__global__ void dcond_reduce_split_kernel(const float* __restrict__ partial, int nblk, float* dz, float* dc, int b, int zd,
+                                          int cd, float scale, const float* row_scale) {
+    __shared__ float red[8][64];
+    const int D = zd + cd;
+    const int i = blockIdx.x * 64 + threadIdx.x;   // flat (bi, k)
+    float acc = 0.f;
+    if (i < b * D)
+        for (int blk = threadIdx.y; blk < nblk; blk += 8) acc += __ldg(partial + (long)blk * b * D + i);
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y != 0 || i >= b * D) return;
+#pragma unroll
+    for (int y = 1; y < 8; ++y) acc += red[y][threadIdx.x];
+    const int bi = i / D, k = i - bi * D;
+    const float sc = row_scale ? scale * row_scale[bi] : scale;
+    if (k < zd) dz[bi * zd + k] = acc * sc;
+    else dc[bi * cd + k - zd] = acc * sc;
+}
+void k_dcond_reduce_split(const float* partial, int nblk, float* dz, float* dc, int b, int zd, int cd, float scale,
+                          const float* row_scale, cudaStream_t st) {
+    dcond_reduce_split_kernel<<<cdiv(b * (zd + cd), 64), dim3(64, 8), 0, st>>>(partial, nblk, dz, dc, b, zd, cd, scale, row_scale);
+    count_launch();
 }
 
 __global__ void bf16_to_f32_kernel(const bf16* src, float* dst, long n) {

@@ -12,11 +12,11 @@ typedef act_t bf16;  // historical alias: the 16-bit activation type (fp16 by de
 // ---- latent side ---------------------------------------------------------------------------
 // cond[b,256] = cat(z[b,zd], c[b,cd])
 void k_concat_cond(const float* z, const float* c, float* cond, int b, int zd, int cd, cudaStream_t st);
-// a[b, off+ch] = (1 + cond.Ws[ch]) * inv_std[ch] ; s = cond.Wo[ch] - mean[ch]*a   (conditional BNs)
-// Ws / Wo are stored TRANSPOSED: [cdim][C_cond]
-void k_cond_affine(const float* cond, const float* Ws, const float* Wo, const float* mean,
-                   const float* inv_std, float* a, float* s, int b, int cdim, int C_cond, int stride,
-                   cudaStream_t st);
+// a[b, ch] = (1 + cond.Ws[ch]) * inv_std[ch] ; s[b, ch] = cond.Wo[ch] - mean[ch]*a   (conditional BNs), as one
+// GEMV + bias: WT_as = [cdim][2*C_cond] = [Ws*inv_std | Wo - mean*inv_std*Ws] (transposed), bias_as =
+// [inv_std | -mean*inv_std] — the BN statistics are folded in when the weights are packed
+void k_cond_affine(const float* cond, const float* WT_as, const float* bias_as, float* a, float* s, int b, int cdim,
+                   int C_cond, int stride, cudaStream_t st);
 // rows [C_cond, C_cond+C_unc): a = weight*inv_std, s = bias - mean*a (same for every sample)
 void k_uncond_affine(const float* weight, const float* bias, const float* mean, const float* inv_std,
                      float* a, float* s, int b, int C_cond, int C_unc, int stride, cudaStream_t st);
@@ -30,9 +30,13 @@ void k_gen_z(const float* cond, const float* W, const float* bias, const float* 
 void k_bn_grad_finalize(const float* S0, const float* S1, const float* a, const float* s,
                         const float* mean, const float* inv_std, float* G, int b, int C_cond,
                         int stride, cudaStream_t st);
-// dcond[b, k] += sum_j G[b, j] * W[j, k]   (W row-major [J, cdim], G row stride ldg)
-void k_dcond_accum(const float* G, int ldg, const float* W, float* dcond, int b, int J, int cdim,
-                   cudaStream_t st);
+// partial[blk, b, k] = sum_{j in block blk} G[b, j] * W[j, k]   (W row-major [J, cdim], G row stride ldg;
+// k_dcond_blocks(J) blocks; cdim % 128 == 0)
+int k_dcond_blocks(int J);
+void k_dcond_partial(const float* G, int ldg, const float* W, float* partial, int b, int J, int cdim, cudaStream_t st);
+// dcond = sum of nblk partial blocks; dz/dc = its halves * scale * (row_scale ? row_scale[b] : 1)
+void k_dcond_reduce_split(const float* partial, int nblk, float* dz, float* dc, int b, int zd, int cd, float scale,
+                          const float* row_scale, cudaStream_t st);
 // G32[b, j] = float(g_bf16[b, j])
 void k_bf16_to_f32(const bf16* src, float* dst, long n, cudaStream_t st);
 // dz/dc = dcond halves * scale * (row_scale ? row_scale[b] : 1)

@@ -106,6 +106,19 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // named barrier over the 128 threads of epilogue group `grp` (ids 1, 2; id 0 is __syncthreads)
 __device__ __forceinline__ void bar_epilogue(int grp = 0) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one 32-byte sector per lane and instruction —
+// half the LSU transactions of 128-bit accesses for the row-per-thread epilogue pattern
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4 a, const uint4 b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
 // ----------------------------------------------------------------------------- tcgen05
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {

@@ -9,12 +9,14 @@ from pix2latent_b200.loss_functions import ProjectionLoss
 from pix2latent_b200.model import BigGAN
 from bench import synthetic_target
 
-halos = [int(x) for x in sys.argv[1:]] or [0, 10]
+halos = [int(x) for x in sys.argv[1:]] or [0, 1]  # halo_mode values (0 off, 1 resident-weight layers, 2 all 3x3); values > 100 set the TMA-I/O K limit instead
 n = 18
 target, weight = synthetic_target(256, "cuda")
 z = torch.fmod(torch.randn(n, 128), 2.0).cuda()
 for halo in halos:
-    _lib.set_option("halo", halo)
+    if halo > 100:
+        _lib.set_option("tma_kmax", halo); halo = 0
+    _lib.set_option("halo_mode", halo)
     model = BigGAN(seed=0).cuda()          # plans are built lazily with the current options
     loss_fn = ProjectionLoss()
     tgt = loss_fn.prepared_target(target, weight)

@@ -110,6 +110,47 @@ def test_conv_fwd_affine_relu_resid_up(N, H, W, Cin, Cout, BN):
     assert rel_err(act.permute(0, 3, 1, 2), y_up) < 8e-3
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("N,H,W,C,BN", [(2, 256, 256, 64, 64), (3, 64, 64, 128, 128), (5, 40, 24, 64, 64)])
+def test_conv3x3_paths_agree(mode, N, H, W, C, BN):
+    """The three 3x3 main loops — per-tap A loads (halo_mode 0), halo patches with the weight matrix
+    resident in shared memory (1, 64-channel layers) and halo patches with a weight ring (2) — against
+    torch, forward (bias + affine + relu, raw and act) and backward (mask, statistics, gain)."""
+    from pix2latent_b200 import _lib as L
+    torch.manual_seed(7)
+    dev = "cuda"
+    x = torch.randn(N, C, H, W, device=dev).to(ACT())
+    w = (torch.randn(C, C, 3, 3, device=dev) / (C * 9) ** 0.5).to(ACT())
+    bias = torch.randn(C, device=dev)
+    a = torch.randn(N, C, device=dev)
+    s = torch.randn(N, C, device=dev)
+    v = F.conv2d(x.float(), w.float(), bias, padding=1)
+    y = torch.relu(a[:, :, None, None] * v + s[:, :, None, None])
+    saved = y.to(ACT())
+    acc = F.conv2d(x.float(), w.float(), padding=1)
+    dpre = acc * (saved.float() > 0)
+    L.set_option("halo_mode", mode)
+    try:
+        raw = torch.zeros(N, H, W, C, device=dev, dtype=ACT())
+        act = torch.zeros(N, H, W, C, device=dev, dtype=ACT())
+        run_conv(A=nhwc(x), A_N=N, A_H=H, A_W=W, A_C=C, Cin=C, B=pack_w(w), Cout=C, kh=3, kw=3, pad_h=1, pad_w=1,
+                 NI=N, H=H, W=W, BN=BN, mode=0, bias=bias, raw=raw, raw_C=C, aff_a=a, aff_s=s, aff_stride=C, relu=1,
+                 act=act, act_C=C)
+        st0 = torch.zeros(N, C, device=dev)
+        st1 = torch.zeros(N, C, device=dev)
+        dx = torch.zeros(N, H, W, C, device=dev, dtype=ACT())
+        run_conv(A=nhwc(x), A_N=N, A_H=H, A_W=W, A_C=C, Cin=C, B=pack_w(w), Cout=C, kh=3, kw=3, pad_h=1, pad_w=1,
+                 NI=N, H=H, W=W, BN=BN, mode=1, saved=nhwc(saved), saved_C=C, stat0=st0, stat1=st1, stat_stride=C,
+                 aff_a=a, aff_stride=C, dx=dx, dx_C=C)
+    finally:
+        L.set_option("halo_mode", 0)
+    assert rel_err(raw.permute(0, 3, 1, 2), v) < 6e-3
+    assert rel_err(act.permute(0, 3, 1, 2), y) < 8e-3
+    assert rel_err(dx.permute(0, 3, 1, 2), dpre * a[:, :, None, None]) < 6e-3
+    assert rel_err(st0, dpre.sum((2, 3))) < 2e-3
+    assert rel_err(st1, (dpre * saved.float()).sum((2, 3))) < 2e-3
+
+
 def test_conv_fwd_rgb_tanh():
     torch.manual_seed(2)
     dev = "cuda"
