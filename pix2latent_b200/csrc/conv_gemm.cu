@@ -30,12 +30,14 @@ float grad_scale() { return (float)g_grad_scale; }
 // halo patches for 3x3 convs: "halo" = patch pitch in pixels (10 | 16), "halo_mode" = 0 off, 1 only where the
 // weight matrix stays resident in shared memory (the 64-channel layers, L2-bandwidth-bound otherwise), 2 every
 // eligible 3x3 conv
+static int g_halo_rgb = 0;
 static int g_halo = 10, g_halo_mode = 0, g_halo_bo = 0;  // measured: the per-tap path with 2 CTAs/SM is faster at every BigGAN shape (profiles/)
 void set_option(const char* key, int value) {
     if (!std::strcmp(key, "halo")) g_halo = value;
     else if (!std::strcmp(key, "grad_scale")) g_grad_scale = value > 0 ? value : 1;
     else if (!std::strcmp(key, "halo_bo")) g_halo_bo = value;
     else if (!std::strcmp(key, "halo_mode")) g_halo_mode = value;
+    else if (!std::strcmp(key, "halo_rgb")) g_halo_rgb = value;
     else if (!std::strcmp(key, "tma_out")) g_tma_out = value;
     else if (!std::strcmp(key, "tma_kmax")) g_tma_kmax = value;
 }
@@ -167,10 +169,11 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     int nb = kBM / (tw * th);
     // halo patches: always for the 3-channel rgb head (N = 16 tile: the layer is pure A traffic),
     // optional ("halo" option) elsewhere — measured neutral for N >= 64 (profiles/)
-    const int halo_p = (d.BN == 16) ? 0 : g_halo;  // rgb head: N=16 MMAs are issue-bound; per-tap path + 2 CTAs/SM is faster
+    const int halo_p = g_halo;
     const long resb_bytes = 9L * d.Cin * d.BN * 2;
     const bool resb = d.Cout <= d.BN && resb_bytes <= 80 * 1024;
-    const bool halo = halo_p != 0 && g_halo_mode != 0 && (g_halo_mode == 2 || resb) && d.kh == 3 && d.kw == 3 &&
+    const bool halo_on = (d.BN == 16) ? (g_halo_rgb != 0) : (g_halo_mode != 0 && (g_halo_mode == 2 || resb));
+    const bool halo = halo_p != 0 && halo_on && d.kh == 3 && d.kw == 3 &&
                       d.pad_h == 1 && d.pad_w == 1 && d.B_batch == 0 && d.H >= 12 && d.W >= 8;
     if (halo) { tw = 8; th = 16; nb = 1; }
     if (d.B_batch > 0 && nb != 1) {

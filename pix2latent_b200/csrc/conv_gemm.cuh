@@ -133,19 +133,21 @@ __device__ __forceinline__ float colsum_group(float (&v)[G], int lane) {
 // Row `row` (0..127) of a 128-row x 128-byte slab in the TMA 128B-swizzle layout: write 32 bf16
 // (pieces piece0 .. piece0+3 of the row's eight 16-byte pieces).
 __device__ __forceinline__ void slab_put_row(uint8_t* buf, int row, int piece0, const float (&v)[32]) {
+    const uint32_t base = smem_u32(buf) + row * 128;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        *reinterpret_cast<uint4*>(buf + row * 128 + (((piece0 + q) ^ (row & 7)) << 4)) =
-            make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                       pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+        sts128(base + (((piece0 + q) ^ (row & 7)) << 4),
+               make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                          pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7])));
     }
 }
 __device__ __forceinline__ void slab_put_row(uint8_t*, int, int, const float (&)[16]) {}
 // v[32] += the 32 bf16 of row `row`, pieces piece0 .. piece0+3, of a swizzled 128-byte-row slab
 __device__ __forceinline__ void slab_add_row(const uint8_t* buf, int row, int piece0, float (&v)[32]) {
+    const uint32_t base = smem_u32(buf) + row * 128;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const uint4 t = *reinterpret_cast<const uint4*>(buf + row * 128 + (((piece0 + q) ^ (row & 7)) << 4));
+        const uint4 t = lds128(base + (((piece0 + q) ^ (row & 7)) << 4));
         v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x);
         v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
         v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z);
@@ -268,7 +270,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
         const bool valid = (w < p.W) && (h < p.H) && (n < p.NI);
         const long pix = (static_cast<long>(n) * p.H + h) * p.W + w;
 
-        float* tab = ctab + (it & 1) * 3 * BN;
+        const uint32_t tab = smem_u32(ctab) + (it & 1) * 3 * BN * 4;  // shared-space byte address
         if (use_tab) {
             // two groups without the slab barriers of the TMA path: this group's previous tile used the
             // same table half, so every warp must have finished reading it
@@ -278,9 +280,9 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
             for (int j = et; j < BN; j += 128) {
                 const int ch = n_tile * BN + j;
                 const bool in = ch < p.Cout;
-                tab[j] = (MODE == EPI_FWD && p.bias && in) ? __ldg(p.bias + ch) : 0.f;
-                tab[BN + j] = (p.aff_a && in) ? __ldg(p.aff_a + static_cast<long>(nn) * p.aff_stride + ch) : 1.f;
-                tab[2 * BN + j] = (MODE == EPI_FWD && p.aff_s && in) ? __ldg(p.aff_s + static_cast<long>(nn) * p.aff_stride + ch) : 0.f;
+                sts32f(tab + j * 4, (MODE == EPI_FWD && p.bias && in) ? __ldg(p.bias + ch) : 0.f);
+                sts32f(tab + (BN + j) * 4, (p.aff_a && in) ? __ldg(p.aff_a + static_cast<long>(nn) * p.aff_stride + ch) : 1.f);
+                sts32f(tab + (2 * BN + j) * 4, (MODE == EPI_FWD && p.aff_s && in) ? __ldg(p.aff_s + static_cast<long>(nn) * p.aff_stride + ch) : 0.f);
             }
             bar_epilogue(grp);  // table[it & 1] was last read by this group's previous tile (or two tiles ago): every warp has passed a barrier since
         }
@@ -335,7 +337,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 if (use_tab) {
 #pragma unroll
                     for (int q = 0; q < CH / 4; ++q) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(tab + c + q * 4);
+                        const float4 b4 = lds128f(tab + (c + q * 4) * 4);
                         v[q * 4 + 0] = fmaf(alpha, v[q * 4 + 0], b4.x); v[q * 4 + 1] = fmaf(alpha, v[q * 4 + 1], b4.y);
                         v[q * 4 + 2] = fmaf(alpha, v[q * 4 + 2], b4.z); v[q * 4 + 3] = fmaf(alpha, v[q * 4 + 3], b4.w);
                     }
@@ -388,8 +390,8 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     if (p.aff_a && use_tab) {
 #pragma unroll
                         for (int q = 0; q < CH / 4; ++q) {
-                            const float4 a4 = *reinterpret_cast<const float4*>(tab + BN + c + q * 4);
-                            const float4 s4 = *reinterpret_cast<const float4*>(tab + 2 * BN + c + q * 4);
+                            const float4 a4 = lds128f(tab + (BN + c + q * 4) * 4);
+                            const float4 s4 = lds128f(tab + (2 * BN + c + q * 4) * 4);
                             v[q * 4 + 0] = fmaf(a4.x, v[q * 4 + 0], s4.x);
                             v[q * 4 + 1] = fmaf(a4.y, v[q * 4 + 1], s4.y);
                             v[q * 4 + 2] = fmaf(a4.z, v[q * 4 + 2], s4.z);
@@ -499,7 +501,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 if (p.aff_a && use_tab) {
 #pragma unroll
                     for (int q = 0; q < CH / 4; ++q) {
-                        const float4 a4 = *reinterpret_cast<const float4*>(tab + BN + c + q * 4);
+                        const float4 a4 = lds128f(tab + (BN + c + q * 4) * 4);
                         v[q * 4 + 0] *= a4.x; v[q * 4 + 1] *= a4.y; v[q * 4 + 2] *= a4.z; v[q * 4 + 3] *= a4.w;
                     }
                 } else if (p.aff_a) {

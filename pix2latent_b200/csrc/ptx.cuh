@@ -106,6 +106,25 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // named barrier over the 128 threads of epilogue group `grp` (ids 1, 2; id 0 is __syncthreads)
 __device__ __forceinline__ void bar_epilogue(int grp = 0) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
+// explicit shared-space accesses by 32-bit address: pointers derived from the dynamic shared array are
+// generic to the compiler, which then emits LD.E / ST.E (address-space resolution, long-scoreboard latency)
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32f(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one 32-byte sector per lane and instruction —
 // half the LSU transactions of 128-bit accesses for the row-per-thread epilogue pattern
 __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {

@@ -16,6 +16,8 @@ z = torch.fmod(torch.randn(n, 128), 2.0).cuda()
 for halo in halos:
     if halo > 100:
         _lib.set_option("tma_kmax", halo); halo = 0
+    _lib.set_option("halo_rgb", 1 if halo == 3 else 0)
+    if halo == 3: halo = 0
     _lib.set_option("halo_mode", halo)
     model = BigGAN(seed=0).cuda()          # plans are built lazily with the current options
     loss_fn = ProjectionLoss()

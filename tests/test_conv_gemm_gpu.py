@@ -151,17 +151,24 @@ def test_conv3x3_paths_agree(mode, N, H, W, C, BN):
     assert rel_err(st1, (dpre * saved.float()).sum((2, 3))) < 2e-3
 
 
-def test_conv_fwd_rgb_tanh():
+@pytest.mark.parametrize("halo_rgb", [0, 1])
+@pytest.mark.parametrize("N,H,W", [(2, 64, 64), (3, 256, 256)])
+def test_conv_fwd_rgb_tanh(halo_rgb, N, H, W):
+    from pix2latent_b200 import _lib as L
     torch.manual_seed(2)
     dev = "cuda"
-    N, H, W, Cin = 2, 64, 64, 128
+    Cin = 128
     x = torch.randn(N, Cin, H, W, device=dev).to(ACT())
     w = (torch.randn(3, Cin, 3, 3, device=dev) / (Cin * 9) ** 0.5).to(ACT())
     bias = torch.randn(3, device=dev) * 0.1
     ref = torch.tanh(F.conv2d(x.float(), w.float(), bias, padding=1))
     img = torch.zeros(N, 3, H, W, device=dev)
-    run_conv(A=nhwc(x), A_N=N, A_H=H, A_W=W, A_C=Cin, Cin=Cin, B=pack_w(w), Cout=3, kh=3, kw=3, pad_h=1, pad_w=1,
-             NI=N, H=H, W=W, BN=16, mode=0, bias=bias, img_nchw=img)
+    L.set_option("halo_rgb", halo_rgb)
+    try:
+        run_conv(A=nhwc(x), A_N=N, A_H=H, A_W=W, A_C=Cin, Cin=Cin, B=pack_w(w), Cout=3, kh=3, kw=3, pad_h=1, pad_w=1,
+                 NI=N, H=H, W=W, BN=16, mode=0, bias=bias, img_nchw=img)
+    finally:
+        L.set_option("halo_rgb", 0)
     assert (img - ref).abs().max().item() < 5e-3
 
 
