@@ -106,7 +106,7 @@ struct GemmCfg {
     static constexpr int kInSlots = TMA_OUT ? 4 : 0;
     static constexpr int kOutBytes = TMA_OUT ? (4 + kInSlots) * kATileBytes : 0;  // 2 x {raw, act} + inputs
     static constexpr int kEpiGroups = TMA_OUT ? 2 : 1;
-    static constexpr int kThreads = 64 + 128 * kEpiGroups + (TMA_OUT ? 32 : 0);
+    static constexpr int kThreads = 64 + 128 * kEpiGroups + (TMA_OUT ? 32 * kEpiGroups : 0);  // + one input-loader warp per group
     static constexpr int kMaxStages = ((kOcc == 2 ? 104 : 208) * 1024 - kOutBytes) / kStageBytes;
     static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
     static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -704,8 +704,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_commit(&tfull_bar[as]);
             }
         }
-    } else if (warp == 2 + 4 * Cfg::kEpiGroups) {
-        // ------------------------------------------------------------------ epilogue-input loader
+    } else if (warp >= 2 + 4 * Cfg::kEpiGroups) {
+        // ------------------------------------------------------------------ epilogue-input loaders (one warp per group:
+        // a single in-order loader would stall group 1's ring behind group 0's full one)
         if constexpr (TMA_OUT) {
             if (lane == 0) {
                 uint8_t* inbuf = obuf + 4 * kATileBytes;
@@ -713,11 +714,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int sh = (MODE == EPI_FWD) ? p.resid_shift : 0;
                 const uint32_t bytes0 = kATileBytes >> (2 * sh);
                 constexpr int RING = NIN / Cfg::kEpiGroups;  // one ring per epilogue group
-                int cnts[2] = {0, 0};
-                int it = 0;
-                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                    const int g = it & 1;
-                    int& cnt = cnts[g];
+                const int g = warp - (2 + 4 * Cfg::kEpiGroups);
+                int cnt = 0;
+                for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += Cfg::kEpiGroups * gridDim.x) {
                     const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
                     const int w0 = (m_tile % p.tiles_w) * p.tw;
                     const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
