@@ -129,23 +129,28 @@ def cpu_reference(steps, warmup, budget_s=150.0, cand=None):
         }
         return oc.initialize(spec, n, "cpu")
 
+    # Bounded: one candidate-step costs seconds on the host, so the sample is sized to a wall-clock
+    # budget — candidates per step first, then (if even 1 candidate x K steps is too long) the step count.
+    v = make_vars(1)
+    t0 = time.time()
+    oc.step(model, v, loss_fn, optimize=True, max_batch_size=CHUNK)   # also warms the thread pool / allocator
+    per_cand = time.time() - t0
     if cand is None:
-        v = make_vars(2)
-        t0 = time.time()
-        oc.step(model, v, loss_fn, optimize=True, max_batch_size=CHUNK)
-        per_cand = (time.time() - t0) / 2
         cand = int(max(1, min(CHUNK, budget_s / max(1e-6, (steps + warmup) * per_cand))))
+    warmup_run = max(0, min(warmup, int(0.2 * budget_s / (cand * per_cand))))
+    steps_run = max(1, min(steps, int(0.8 * budget_s / (cand * per_cand))))
     v = make_vars(cand)
-    for _ in range(warmup):
+    for _ in range(warmup_run):
         oc.step(model, v, loss_fn, optimize=True, max_batch_size=CHUNK)
     t0 = time.time()
-    for _ in range(steps):
+    for _ in range(steps_run):
         oc.step(model, v, loss_fn, optimize=True, max_batch_size=CHUNK)
     dt = time.time() - t0
-    return {"value": cand * steps / dt, "unit": "candidates/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "%d candidates x %d optimise-steps (+%d warm-up) of the BigGAN-deep-256 / alex-LPIPS step, "
-                      "torch fp32, %d threads" % (cand, steps, warmup, os.cpu_count()),
-            "ms_per_step": 1e3 * dt / steps, "candidates": cand}
+    return {"value": cand * steps_run / dt, "unit": "candidates/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d candidates x %d optimise-steps (+%d warm-up after one 1-candidate sizing step) of the "
+                      "BigGAN-deep-256 / alex-LPIPS step, torch fp32, %d threads"
+                      % (cand, steps_run, warmup_run, os.cpu_count()),
+            "ms_per_step": 1e3 * dt / steps_run, "candidates": cand, "steps_run": steps_run, "warmup_run": warmup_run}
 
 
 def run_reference(args, rank, world):
@@ -154,7 +159,8 @@ def run_reference(args, rank, world):
     r = cpu_reference(args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "candidates/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "steps": r["steps_run"], "warmup": r["warmup_run"], "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BigGAN-deep-256 BasinCMA inner step, CPU sample of %d candidates (chunk<=9)" % r["candidates"],
                    "resolution": 256, "lpips_net": "alex"},
@@ -297,7 +303,7 @@ def run_native(args, rank, world, local_rank):
         "final_loss_mean": float(loss.mean().item()),
     }
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(2, 1, cand=CHUNK)
+        r = cpu_reference(1, 0, budget_s=30.0, cand=3)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -39,6 +39,7 @@ struct BigGANPlan {
     ConvOp f_rgb, d_rgb;
     act_t* col_rgb = nullptr;
     float* img = nullptr;  // internal copy target when the caller passes none
+    float* rgbT = nullptr; // tap-expanded rgb head output [b, 27, R, R]
     // gradient ping-pong
     act_t *dhA = nullptr, *dhB = nullptr, *g1 = nullptr, *g2 = nullptr, *g3 = nullptr, *dh_pool = nullptr;
     double flops_fwd = 0, flops_bwd = 0;
@@ -224,7 +225,17 @@ int BigGAN::finalize() {
         const auto* w = stage.get("generator.conv_to_rgb.weight", (long)C_last * C_last * 9);
         const auto* bsv = stage.get("generator.conv_to_rgb.bias", C_last);
         if (!w || !bsv) return -1;
-        wrgb = upload(weights, pack_conv_fwd(*w, C_last, C_last, 3, 3, 3));
+        // The 3-channel 3x3 head as a 1x1 GEMM with N = 27 = (tap, channel) outputs + a 9-tap gather:
+        // a tcgen05.mma costs the same ~100 cycles for N = 16 as for N = 64, so nine K=128 taps with
+        // N = 3 (72 MMAs per tile) are replaced by one K = 128 pass with N = 27 (8 MMAs per tile).
+        {
+            std::vector<act_t> t((size_t)27 * C_last);
+            for (int tap = 0; tap < 9; ++tap)
+                for (int o = 0; o < 3; ++o)
+                    for (int c = 0; c < C_last; ++c)
+                        t[((size_t)tap * 3 + o) * C_last + c] = host_f2bf((*w)[(((size_t)o * C_last + c) * 3 + tap / 3) * 3 + tap % 3]);
+            wrgb = upload(weights, t);
+        }
         std::vector<float> b3(bsv->begin(), bsv->begin() + 3);
         brgb = upload(weights, b3);
         // dgrad operand for the im2col'd gradient: [C_last][64], k = (r*3+s)*3 + o -> W[o, c, r, s]
@@ -326,6 +337,7 @@ BigGANPlan* BigGAN::plan(int b) {
     const int R = H_out;
     P.col_rgb = ar.alloc<bf>((size_t)b * R * R * 64);
     P.img = ar.alloc<float>((size_t)b * 3 * R * R);
+    P.rgbT = ar.alloc<float>((size_t)b * 27 * R * R);
     if (ar.failed) return nullptr;
 
     auto build = [&](ConvOp* op, OpB& ob, double* flops, int* launches) -> int {
@@ -525,10 +537,11 @@ BigGANPlan* BigGAN::plan(int b) {
     // ---- rgb
     {
         const BigGANPlan::BB& Bl = P.bb[nL - 1];
-        OpB o(Bl.out_act, b, R, R, C_last, 0, C_last, wrgb, 3, 3, EPI_FWD);
-        o.d.epi.bias = brgb;
-        o.d.epi.img_nchw = P.img;  // patched per call
+        OpB o(Bl.out_act, b, R, R, C_last, 0, C_last, wrgb, 27, 1, EPI_FWD);
+        o.d.epi.img_nchw = P.rgbT;  // planar fp32 [b, 27, R, R]; k_rgb_gather adds bias, sums the taps, tanh
+        o.d.epi.img_linear = 1;
         if (build(&P.f_rgb, o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
+        P.launches_fwd += 1;
     }
     {
         const BigGANPlan::BB& Bl = P.bb[nL - 1];
@@ -576,9 +589,8 @@ int BigGAN::forward(int b, const float* z, const float* c, float* img, cudaStrea
         for (int k = 0; k < 4; ++k)
             if (conv_op_launch(P.bb[i].f[k], st)) return -1;
     }
-    ConvOp rgb = P.f_rgb;
-    rgb.p.img_nchw = img ? img : P.img;
-    if (conv_op_launch(rgb, st)) return -1;
+    if (conv_op_launch(P.f_rgb, st)) return -1;
+    k_rgb_gather(P.rgbT, brgb, img ? img : P.img, b, H_out, H_out, st);
     if (img && img != P.img) {
         // keep a private copy for the backward pass (tanh')
         P2L_CUDA_CHECK(cudaMemcpyAsync(P.img, img, (size_t)b * 3 * H_out * H_out * sizeof(float),

@@ -43,7 +43,7 @@ struct BigGAN {
     } attn;
     int final_bn = -1;
     int C_last = 0, H_out = 0;
-    act_t *wrgb = nullptr, *wrgb_t = nullptr;
+    act_t *wrgb = nullptr, *wrgb_t = nullptr;  // wrgb: tap-expanded head [27 = tap*3 + o][C_last]
     float* brgb = nullptr;
 
     std::map<int, std::shared_ptr<BigGANPlan>> plans;

@@ -73,6 +73,7 @@ struct ConvGemmParams {
     int act_up;             // write act to the 2x nearest-upsampled grid [NI, 2H, 2W, act_C]
     act_t* act_lo;  // with act_up: also keep the low-res copy (needed by backward)
     float* img_nchw;        // tanh(v) for c < Cout written as fp32 NCHW [NI, Cout, H, W]
+    int img_linear;         // ... without the tanh (planar fp32 output of a tap-expanded head)
     // ---- epilogue, backward
     const act_t* saved;  // forward activation of the layer being differentiated
     int saved_C;
@@ -373,7 +374,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 #pragma unroll
                         for (int j = 0; j < CH; ++j) {
                             if (cbase + j < p.Cout) {
-                                p.img_nchw[((static_cast<long>(n) * p.Cout + cbase + j) * p.H + h) * p.W + w] = tanhf(v[j]);
+                                p.img_nchw[((static_cast<long>(n) * p.Cout + cbase + j) * p.H + h) * p.W + w] = p.img_linear ? v[j] : tanhf(v[j]);
                             }
                         }
                     }

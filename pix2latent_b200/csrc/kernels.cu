@@ -288,6 +288,34 @@ __global__ void fill_kernel(float* p, float v, long n) {
 void k_fill_f32(float* p, float v, long n, cudaStream_t st) { fill_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, v, n); count_launch(); }
 
 // ============================================================================= BigGAN glue
+__global__ void rgb_gather_kernel(const float* __restrict__ T, const float* __restrict__ bias, float* __restrict__ img,
+                                  int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+    if (x >= W) return;
+    const long plane = (long)H * W;
+    const float* Tn = T + (long)n * 27 * plane;
+    float acc[3] = {__ldg(bias), __ldg(bias + 1), __ldg(bias + 2)};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int yy = y + r - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int xx = x + s - 1;
+            if (xx < 0 || xx >= W) continue;
+            const float* t = Tn + (long)((r * 3 + s) * 3) * plane + (long)yy * W + xx;
+            acc[0] += __ldg(t);
+            acc[1] += __ldg(t + plane);
+            acc[2] += __ldg(t + 2 * plane);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 3; ++o) img[((long)n * 3 + o) * plane + (long)y * W + x] = tanhf(acc[o]);
+}
+void k_rgb_gather(const float* T, const float* bias, float* img, int b, int H, int W, cudaStream_t st) {
+    rgb_gather_kernel<<<dim3(cdiv(W, 128), H, b), 128, 0, st>>>(T, bias, img, H, W); count_launch();
+}
+
 // thread = 8 channels (one uint4) of one low-res pixel; block = 8 channel-groups x 32 pixels
 __device__ __forceinline__ void unpack8(const uint4 t, float (&f)[8]) {
     f[0] = act_lo(t.x); f[1] = act_hi(t.x); f[2] = act_lo(t.y); f[3] = act_hi(t.y);

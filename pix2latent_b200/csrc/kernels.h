@@ -44,6 +44,9 @@ void k_split_dcond(const float* dcond, float* dz, float* dc, int b, int zd, int 
                    const float* row_scale, cudaStream_t st);
 
 // ---- BigGAN glue ---------------------------------------------------------------------------
+// rgb head, second half: T[n, tap*3+o, y, x] holds every pixel's contribution to its 3x3 neighbours
+// (x[n,y,x,:] . W[o,:,tap]); img[n,o,y,x] = tanh(bias[o] + sum_tap T[n, tap*3+o, y+r-1, x+s-1]) with zero padding
+void k_rgb_gather(const float* T, const float* bias, float* img, int b, int H, int W, cudaStream_t st);
 // backward through nearest-x2 + relu + BN affine of an up block's conv_0 output:
 //   g = sum2x2(g_up) ; dpre = g*[y>0] ; S0 += dpre ; S1 += dpre*y ; dx = a*dpre
 void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int aff_stride,

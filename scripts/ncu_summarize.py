@@ -50,7 +50,7 @@ def traffic(path, out):
             continue
         b = sum(m[x][0] * unit[m[x][1]] for x in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         tot_b += b
-        tot_t += m["gpu__time_duration.sum"][0]
+        tot_t += m.get("gpu__time_duration.sum", (0.0, "ns"))[0]
         n += 1
     res = {"kernel": "conv_gemm_kernel (all tensor-core launches of one step)", "launches": n,
            "dram_bytes_total": tot_b, "dram_bytes_per_launch": tot_b / max(n, 1),
