@@ -110,7 +110,6 @@ def cpu_reference(steps, warmup, budget_s=150.0, cand=None):
     import pix2latent_b200.distribution as dist
     import pix2latent_b200.utils.function_hooks as hook
     import torch.optim as optim
-    torch.set_num_threads(os.cpu_count())
     model = obg.make_biggan(obg.BigGANConfig.deep256(), seed=0, calibrate=False)
     loss_fn = olp.ProjectionLoss(lpips_module=olp.make_lpips("alex", seed=0))
     target, weight = synthetic_target(256, "cpu")
@@ -131,10 +130,24 @@ def cpu_reference(steps, warmup, budget_s=150.0, cand=None):
 
     # Bounded: one candidate-step costs seconds on the host, so the sample is sized to a wall-clock
     # budget — candidates per step first, then (if even 1 candidate x K steps is too long) the step count.
-    v = make_vars(1)
-    t0 = time.time()
-    oc.step(model, v, loss_fn, optimize=True, max_batch_size=CHUNK)   # also warms the thread pool / allocator
-    per_cand = time.time() - t0
+    # thread count: "all host cores" is often NOT the fastest setting for torch's CPU convolutions on
+    # a many-core box (oversubscription), so a 1-candidate step is timed at a few settings and the best
+    # one is used and reported as `cores`
+    ncpu = os.cpu_count()
+    per_cand, threads = None, ncpu
+    for t in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16)}, reverse=True):
+        torch.set_num_threads(t)
+        v = make_vars(1)
+        if per_cand is None:
+            oc.step(model, v, loss_fn, optimize=True, max_batch_size=CHUNK)   # warms the thread pool / allocator
+        t0 = time.time()
+        oc.step(model, v, loss_fn, optimize=True, max_batch_size=CHUNK)
+        dt1 = time.time() - t0
+        if per_cand is None or dt1 < per_cand:
+            per_cand, threads = dt1, t
+        if dt1 > 0.25 * budget_s:
+            break   # too slow to keep probing
+    torch.set_num_threads(threads)
     if cand is None:
         cand = int(max(1, min(CHUNK, budget_s / max(1e-6, (steps + warmup) * per_cand))))
     warmup_run = max(0, min(warmup, int(0.2 * budget_s / (cand * per_cand))))
@@ -146,10 +159,10 @@ def cpu_reference(steps, warmup, budget_s=150.0, cand=None):
     for _ in range(steps_run):
         oc.step(model, v, loss_fn, optimize=True, max_batch_size=CHUNK)
     dt = time.time() - t0
-    return {"value": cand * steps_run / dt, "unit": "candidates/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": cand * steps_run / dt, "unit": "candidates/s", "cores": threads, "kind": "port",
             "sample": "%d candidates x %d optimise-steps (+%d warm-up after one 1-candidate sizing step) of the "
-                      "BigGAN-deep-256 / alex-LPIPS step, torch fp32, %d threads"
-                      % (cand, steps_run, warmup_run, os.cpu_count()),
+                      "BigGAN-deep-256 / alex-LPIPS step, torch fp32, %d threads (best of a probe over thread counts; %d cores on the box)"
+                      % (cand, steps_run, warmup_run, threads, ncpu),
             "ms_per_step": 1e3 * dt / steps_run, "candidates": cand, "steps_run": steps_run, "warmup_run": warmup_run}
 
 

@@ -106,7 +106,7 @@ struct GemmCfg {
     static constexpr int kOcc = TMA_OUT ? 1 : ((BN <= 128) ? P2L_OCC : 1);
     static constexpr int kInSlots = TMA_OUT ? 4 : 0;
     static constexpr int kOutBytes = TMA_OUT ? (4 + kInSlots) * kATileBytes : 0;  // 2 x {raw, act} + inputs
-    static constexpr int kEpiGroups = TMA_OUT ? 2 : 1;
+    static constexpr int kEpiGroups = (TMA_OUT || kOcc == 1) ? 2 : 1;  // one CTA per SM: two groups drain the two TMEM stages
     static constexpr int kThreads = 64 + 128 * kEpiGroups + (TMA_OUT ? 32 * kEpiGroups : 0);  // + one input-loader warp per group
     static constexpr int kMaxStages = ((kOcc == 2 ? 104 : 208) * 1024 - kOutBytes) / kStageBytes;
     static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
