@@ -135,7 +135,7 @@ def cpu_reference(steps, warmup, budget_s=150.0, cand=None):
     # one is used and reported as `cores`
     ncpu = os.cpu_count()
     per_cand, threads = None, ncpu
-    for t in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16)}, reverse=True):
+    for t in sorted({min(ncpu, 16), min(ncpu, 32), min(ncpu, 64), ncpu}):   # ascending: the small settings are the cheap ones
         torch.set_num_threads(t)
         v = make_vars(1)
         if per_cand is None:
@@ -145,8 +145,8 @@ def cpu_reference(steps, warmup, budget_s=150.0, cand=None):
         dt1 = time.time() - t0
         if per_cand is None or dt1 < per_cand:
             per_cand, threads = dt1, t
-        if dt1 > 0.25 * budget_s:
-            break   # too slow to keep probing
+        if dt1 > 1.2 * per_cand or dt1 > 0.15 * budget_s:
+            break   # getting worse (oversubscription), or too slow to keep probing
     torch.set_num_threads(threads)
     if cand is None:
         cand = int(max(1, min(CHUNK, budget_s / max(1e-6, (steps + warmup) * per_cand))))
