@@ -115,6 +115,37 @@ int p2l_biggan_step(p2l_biggan* g, p2l_lpips* l, p2l_target* t, int b, const flo
                     const float* c_dev, int want_grad, float grad_scale, const float* dloss_dev,
                     float* loss_dev, float* dz_dev, float* dc_dev, float* img_dev, void* stream);
 
+/* ---- device-resident inner loop: `steps` repetitions of closure.py:38-71 for one
+ * population of b candidates without a host round trip —
+ *     hooks: function_hooks.py:10-27 Clamp (clamp_z / clamp_c > 0: clamp to [-x, x] before every forward)
+ *     out = model(z, c); loss = loss_fn(out, target...); loss.mean().backward()     closure.py:51-58
+ *     optimizer.step(): torch.optim.Adam, one param group per latent tensor           closure.py:65,
+ *                                                                            variable_manager.py:231-238
+ * z_dev[b,z_dim] / c_dev[b,class_embed_dim] are updated IN PLACE. adam_mv_dev: [2][b*(z_dim+class_embed_dim)]
+ * first/second moments laid out as (z rows | c rows), zero for a fresh optimizer; counters_dev: int[2],
+ * [0] = Adam step count so far (carried across calls; 0 for a fresh optimizer), [1] = scratch.
+ * loss_hist_dev[steps,b] receives every step's per-candidate losses (the values closure.step returns,
+ * i.e. of the forward BEFORE that step's update). z_hist_dev / c_hist_dev (optional, [steps,b,dim]) record the
+ * inputs as base_optimizer.py:105-106 tracks them (before the hooks of that step). img_dev (optional,
+ * [b,3,R,R]) = output of the last forward. The upstream gradient of sample i is
+ * grad_scale * (dloss_dev ? dloss_dev[i] : 1) as in p2l_biggan_step. use_graph: capture one step into a CUDA
+ * graph and replay it (falls back to plain launches if capture is refused). Asynchronous, stream-ordered. */
+typedef struct p2l_adam_config {
+    float lr_z, lr_c;     /* learning rate of the z / c param groups (0 = frozen) */
+    float beta1, beta2, eps;
+    float clamp_z, clamp_c; /* Clamp hook bounds; <= 0: no hook */
+} p2l_adam_config;
+int p2l_biggan_optimize(p2l_biggan* g, p2l_lpips* l, p2l_target* t, int b, int steps, float* z_dev, float* c_dev,
+                        const float* dloss_dev, float grad_scale, const p2l_adam_config* cfg, float* adam_mv_dev,
+                        int* counters_dev, float* loss_hist_dev, float* z_hist_dev, float* c_hist_dev, float* img_dev,
+                        int use_graph, void* stream);
+/* 1 if the last p2l_biggan_optimize on this generator replayed a CUDA graph, 0 if it launched step by step */
+int p2l_biggan_optimize_used_graph(p2l_biggan* g);
+/* One Adam update alone (replaces `opt.step()` closure.py:65 for the latent leaves): same state layout as above;
+ * loss_dev / loss_hist_dev may be NULL. */
+int p2l_adam_update(int b, int z_dim, int c_dim, float* z_dev, float* c_dev, const float* dz_dev, const float* dc_dev,
+                    const p2l_adam_config* cfg, float* adam_mv_dev, int* counters_dev, void* stream);
+
 /* ---- StyleGAN2 generator: replaces StyleGAN2.__init__ / forward_z
  *      (pix2latent/model/stylegan2.py:66-119: rosinality Generator(size, 512, 8, channel_multiplier=2),
  *      `model([z], truncation=1.0)[0].clamp_(-1, 1)`) */

@@ -4,13 +4,14 @@
 #include "biggan.h"
 #include "lpips.h"
 #include "sg2.h"
+#include "optim.h"
 
 #define P2L_EXPORT extern "C" __attribute__((visibility("default")))
 
 using namespace p2l;
 
 struct p2l_ctx { Ctx c; };
-struct p2l_biggan { BigGAN g; };
+struct p2l_biggan { BigGAN g; InnerLoop loop; };
 struct p2l_lpips { Lpips l; };
 struct p2l_target { Target* t; };
 struct p2l_sg2 { SG2 g; };
@@ -185,6 +186,38 @@ P2L_EXPORT int p2l_biggan_step(p2l_biggan* g, p2l_lpips* l, p2l_target* t, int b
     float* dimg = l->l.unit_grad(*t->t, b);
     if (!dimg) return -1;
     if (g->g.backward(b, dimg, dz, dc, st, grad_scale, dloss)) return -1;
+    return 0;
+    P2L_TRY_END
+}
+
+// ----------------------------------------------------------------------------- device-resident inner loop
+P2L_EXPORT int p2l_biggan_optimize(p2l_biggan* g, p2l_lpips* l, p2l_target* t, int b, int steps, float* z, float* c,
+                                   const float* dloss, float grad_scale, const p2l_adam_config* cfg, float* mv, int* counters,
+                                   float* loss_hist, float* z_hist, float* c_hist, float* img, int use_graph, void* stream) {
+    if (!g || !l || !t || b <= 0 || steps < 0 || !z || !c || !cfg || !mv || !counters) {
+        set_error("p2l_biggan_optimize: bad argument");
+        return -1;
+    }
+    if (!(cfg->beta1 >= 0.f && cfg->beta1 < 1.f && cfg->beta2 >= 0.f && cfg->beta2 < 1.f && cfg->eps >= 0.f)) {
+        set_error("p2l_biggan_optimize: bad Adam hyper-parameters (beta1 %g beta2 %g eps %g)", cfg->beta1, cfg->beta2, cfg->eps);
+        return -1;
+    }
+    P2L_TRY_BEGIN
+    return biggan_optimize(g->g, l->l, *t->t, g->loop, b, steps, z, c, dloss, grad_scale, *cfg, mv, counters, loss_hist, z_hist,
+                           c_hist, img, use_graph, static_cast<cudaStream_t>(stream));
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_biggan_optimize_used_graph(p2l_biggan* g) { return g ? g->loop.graph_used : 0; }
+P2L_EXPORT int p2l_adam_update(int b, int z_dim, int c_dim, float* z, float* c, const float* dz, const float* dc,
+                               const p2l_adam_config* cfg, float* mv, int* counters, void* stream) {
+    if (b <= 0 || z_dim < 0 || c_dim < 0 || !cfg || !mv || !counters || (z_dim > 0 && (!z || !dz)) || (c_dim > 0 && (!c || !dc))) {
+        set_error("p2l_adam_update: bad argument");
+        return -1;
+    }
+    P2L_TRY_BEGIN
+    const int nz = b * z_dim, nc = b * c_dim;
+    k_adam(z, c, dz, dc, mv, mv + nz + nc, nz, nc, *cfg, counters, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream));
+    P2L_CUDA_CHECK(cudaGetLastError());
     return 0;
     P2L_TRY_END
 }

@@ -22,6 +22,7 @@ const char* get_error() { return g_err; }
 
 static long g_launches = 0;
 void count_launch() { ++g_launches; }
+void add_launches(long n) { g_launches += n; }
 long launch_count() { return g_launches; }
 
 static int g_tma_out = 1, g_tma_kmax = 512;

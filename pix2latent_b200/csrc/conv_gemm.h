@@ -45,6 +45,7 @@ const char* get_error();
 int num_sms();
 void count_launch();  // every kernel launch of the library is counted (bench.py gpu_launches)
 long launch_count();
+void add_launches(long n);  // graph replays: the captured sequence's launches per replay
 // tuning / experiment switches: "halo" (patch pitch 10 | 16), "halo_mode" (0 off, 1 resident-weight layers, 2 all 3x3), "halo_bo" (0/1), "tma_out", "tma_kmax", "grad_scale"
 // Static loss scale carried by 16-bit gradients (act_type.h); default kGradScale, option "grad_scale".
 float grad_scale();

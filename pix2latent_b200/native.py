@@ -26,6 +26,12 @@ class BigGANConfigC(C.Structure):
     ]
 
 
+class AdamConfigC(C.Structure):
+    """Mirror of ``p2l_adam_config``."""
+    _fields_ = [("lr_z", C.c_float), ("lr_c", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("clamp_z", C.c_float), ("clamp_c", C.c_float)]
+
+
 class SG2ConfigC(C.Structure):
     """Mirror of ``p2l_sg2_config``."""
     _fields_ = [("size", C.c_int), ("style_dim", C.c_int), ("n_mlp", C.c_int), ("channels", C.c_int * 9)]
@@ -60,6 +66,10 @@ def declare(L):
         "p2l_lpips_flops": (C.c_double, [vp, ci, ci, ci, ci]),
         "p2l_lpips_launches": (ci, [vp, ci]),
         "p2l_biggan_step": (ci, [vp, vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]),
+        "p2l_biggan_optimize": (ci, [vp, vp, vp, ci, ci, vp, vp, vp, cf, C.POINTER(AdamConfigC), vp, vp, vp, vp, vp, vp,
+                                    ci, vp]),
+        "p2l_biggan_optimize_used_graph": (ci, [vp]),
+        "p2l_adam_update": (ci, [ci, ci, ci, vp, vp, vp, vp, C.POINTER(AdamConfigC), vp, vp, vp]),
         "p2l_sg2_create": (ci, [vp, C.POINTER(SG2ConfigC), pp]),
         "p2l_sg2_set_tensor": (ci, [vp, C.c_char_p, vp, cl]),
         "p2l_sg2_finalize": (ci, [vp]),
@@ -84,6 +94,7 @@ EXPORTED_SYMBOLS = [
     "p2l_biggan_launches", "p2l_lpips_create", "p2l_lpips_set_tensor", "p2l_lpips_finalize",
     "p2l_lpips_destroy", "p2l_target_create", "p2l_target_destroy", "p2l_loss_forward",
     "p2l_loss_backward", "p2l_lpips_flops", "p2l_lpips_launches", "p2l_biggan_step",
+    "p2l_biggan_optimize", "p2l_biggan_optimize_used_graph", "p2l_adam_update",
     "p2l_profile_enable", "p2l_profile_read", "p2l_sg2_create", "p2l_sg2_set_tensor", "p2l_sg2_finalize",
     "p2l_sg2_destroy", "p2l_sg2_num_noise_layers", "p2l_sg2_forward", "p2l_sg2_backward", "p2l_sg2_step",
     "p2l_debug_conv", "p2l_debug_set_option", "p2l_debug_get_option", "p2l_debug_profile_get",
@@ -348,3 +359,66 @@ def biggan_step(gen, lp, tgt, z, c, want_grad, grad_scale, want_img=True, dloss=
                                           _lib.ptr(loss), _lib.ptr(dz), _lib.ptr(dc),
                                           _lib.ptr(img), _lib.current_stream()))
     return loss, dz, dc, img
+
+
+def adam_config(lr_z, lr_c, betas=(0.9, 0.999), eps=1e-8, clamp_z=0.0, clamp_c=0.0):
+    return AdamConfigC(float(lr_z), float(lr_c), float(betas[0]), float(betas[1]), float(eps),
+                       float(clamp_z or 0.0), float(clamp_c or 0.0))
+
+
+class AdamState:
+    """Device-side state of the per-candidate Adam of ``biggan_optimize`` / ``adam_update``:
+    ``mv`` [2, b*(zd+cd)] first/second moments laid out (z rows | c rows), ``counters`` int32[2]
+    (step count, scratch). Fresh = zeros, like a new torch.optim.Adam (variable_manager.py:238)."""
+
+    def __init__(self, b, zd, cd, device, step=0):
+        self.b, self.zd, self.cd = b, zd, cd
+        self.mv = torch.zeros(2, b * (zd + cd), device=device, dtype=torch.float32)
+        self.counters = torch.tensor([int(step), 0], device=device, dtype=torch.int32)
+
+    def moments(self):
+        """(m_z [b,zd], v_z, m_c [b,cd], v_c) views."""
+        nz = self.b * self.zd
+        m, v = self.mv[0], self.mv[1]
+        return (m[:nz].view(self.b, self.zd), v[:nz].view(self.b, self.zd),
+                m[nz:].view(self.b, self.cd), v[nz:].view(self.b, self.cd))
+
+    def step_count(self):
+        return int(self.counters[0].item())
+
+
+def adam_update(z, c, dz, dc, cfg, state):
+    """In-place Adam update of z [b,zd] and c [b,cd] (closure.py:65 for the latent leaves)."""
+    for t in (z, c, dz, dc):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    b = z.shape[0]
+    _lib.check(_lib.lib().p2l_adam_update(b, z.shape[1], c.shape[1], _lib.ptr(z), _lib.ptr(c), _lib.ptr(dz), _lib.ptr(dc),
+                                          C.byref(cfg), _lib.ptr(state.mv), _lib.ptr(state.counters),
+                                          _lib.current_stream()))
+
+
+def biggan_optimize(gen, lp, tgt, z, c, steps, cfg, state=None, dloss=None, grad_scale=1.0, track=False,
+                    want_img=True, use_graph=True):
+    """``steps`` fused inner steps (Clamp hook -> generator -> loss -> backward -> Adam) on the device.
+    z [b,zd], c [b,cd]: contiguous fp32 CUDA tensors, updated IN PLACE. Returns a dict with
+    ``loss`` [steps,b] (per-step losses as closure.step reports them), ``z_hist``/``c_hist`` [steps,b,dim]
+    (when ``track``), ``img`` [b,3,R,R] of the last forward, ``state`` (AdamState), ``graph`` (bool)."""
+    for t in (z, c):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "z/c must be contiguous fp32 CUDA tensors"
+    b, zd, cd = z.shape[0], z.shape[1], c.shape[1]
+    dev = z.device
+    if state is None:
+        state = AdamState(b, zd, cd, dev)
+    assert (state.b, state.zd, state.cd) == (b, zd, cd)
+    loss = torch.empty(steps, b, device=dev, dtype=torch.float32)
+    zh = torch.empty(steps, b, zd, device=dev, dtype=torch.float32) if track else None
+    ch = torch.empty(steps, b, cd, device=dev, dtype=torch.float32) if track else None
+    img = torch.empty(b, 3, gen.out_res, gen.out_res, device=dev, dtype=torch.float32) if want_img else None
+    dl = None if dloss is None else _f32c(dloss)
+    _lib.check(_lib.lib().p2l_biggan_optimize(gen.h, lp.h, tgt.h, b, int(steps), _lib.ptr(z), _lib.ptr(c), _lib.ptr(dl),
+                                              float(grad_scale), C.byref(cfg), _lib.ptr(state.mv), _lib.ptr(state.counters),
+                                              _lib.ptr(loss), _lib.ptr(zh), _lib.ptr(ch), _lib.ptr(img), int(use_graph),
+                                              _lib.current_stream()))
+    # the library ran on an internal stream ordered before the current one; keep the buffers alive until here
+    graph = bool(_lib.lib().p2l_biggan_optimize_used_graph(gen.h))
+    return {"loss": loss, "z_hist": zh, "c_hist": ch, "img": img, "state": state, "graph": graph, "_keep": dl}

@@ -1,6 +1,7 @@
 """Shared host loop machinery of all optimizers (reference: pix2latent/optimizer/base_optimizer.py
 :9-141): holds model / loss / variable manager, runs the optional target transforms, tracks the
 per-step inputs on the CPU and delegates the evaluation to ``closure.step``."""
+import os
 import time
 
 import numpy as np
@@ -10,6 +11,27 @@ from .. import parallel
 from ..utils.image import to_grid, to_image
 from ..utils.misc import progress_print
 from .closure import step
+
+
+# Device-resident inner loop: runs of gradient steps go through ONE C-ABI call
+# (p2l_biggan_optimize: Clamp hook + fused step + per-candidate Adam, CUDA-graph replayed) when the
+# run is expressible there — see _BaseOptimizer._fusable. P2L_FUSE_INNER_LOOP=0 turns it off.
+FUSE_INNER_LOOP = os.environ.get("P2L_FUSE_INNER_LOOP", "1") != "0"
+
+
+def _clamp_of(hook_fn):
+    """Bound of a hook that is None / Clamp / Compose of Clamps; False when it is anything else."""
+    from ..utils import function_hooks as hk
+    if hook_fn is None:
+        return 0.0
+    if type(hook_fn) is hk.Clamp:
+        return float(hook_fn.trunc) if hook_fn.trunc > 0 else False
+    if type(hook_fn) is hk.Compose and len(hook_fn.hook_fns) > 0:
+        bounds = [_clamp_of(h) for h in hook_fn.hook_fns]
+        if any(b is False or b == 0.0 for b in bounds):
+            return False
+        return min(bounds)
+    return False
 
 
 class _BaseOptimizer():
@@ -34,6 +56,8 @@ class _BaseOptimizer():
         self.log_resize_factor = None
         self.track_variables = track_variables
         self.tracked = {}
+        self.fuse_inner_loop = FUSE_INNER_LOOP
+        self.fused_calls = 0  # runs of gradient steps that went through the device-resident loop
 
     def register_benchmark(self, benchmark):
         self.bm = benchmark
@@ -65,6 +89,151 @@ class _BaseOptimizer():
             self.model, local, loss_fn=self.loss_fn, optimize=optimize, max_batch_size=self.max_batch_size)
         self._n_total = variables.num_samples
         return self.out, self.loss, self.other
+
+    # ---- runs of gradient steps --------------------------------------------------------------
+    def grad_steps(self, variables, n_steps, on_step=None):
+        """``n_steps`` gradient updates of ``variables`` — the loop body every optimizer of the reference
+        repeats (`self.step(variables, optimize=True, transform=(j == 0))`, e.g. basincma_optimizer.py:60-66);
+        ``on_step(j)`` runs after update j (logging / progress). Uses the device-resident loop when the
+        run is expressible there, the per-step path otherwise; both produce the same trajectory."""
+        plan = self._fusable(variables, n_steps)
+        if plan is not None:
+            self._fused_steps(variables, n_steps, plan)
+            for j in range(n_steps):
+                if on_step is not None:
+                    on_step(j)
+            return
+        for j in range(n_steps):
+            self.step(variables, optimize=True, transform=(j == 0))
+            if on_step is not None:
+                on_step(j)
+
+    def _fusable(self, variables, n_steps):
+        """Hyper-parameters of the fused run, or None when this run must go step by step: needs the
+        library's own BigGAN + loss, plain torch.optim.Adam over the z / c leaves (one lr per variable, no
+        weight decay / amsgrad), hooks that are None or Clamp, no per-step logging and no transform."""
+        from .closure import _native_pair
+        if not self.fuse_inner_loop or n_steps < 2 or self.log or len(self.transform_fns) > 0:
+            return None
+        if not _native_pair(self.model, variables, self.loss_fn):
+            return None
+        opt = variables.opt
+        if type(opt) is not torch.optim.Adam:
+            return None
+        z_list, c_list = variables.input.z.data, variables.input.c.data
+        group_of = {}
+        for g in opt.param_groups:
+            if (g.get("weight_decay", 0) != 0 or g.get("amsgrad", False) or g.get("maximize", False)
+                    or g.get("capturable", False) or g.get("differentiable", False) or g.get("fused", None)):
+                return None
+            if g.get("decoupled_weight_decay", False):
+                return None
+            for p in g["params"]:
+                group_of[id(p)] = g
+        hp = None
+        lrs = []
+        for lst in (z_list, c_list):
+            lr = None
+            for t in lst:
+                g = group_of.get(id(t))
+                if g is None:
+                    if t.requires_grad:
+                        return None  # a trainable leaf the optimizer does not know
+                    this = 0.0
+                else:
+                    if not t.requires_grad:
+                        return None
+                    this = float(g["lr"])
+                    key = (tuple(float(x) for x in g["betas"]), float(g["eps"]))
+                    if hp is None:
+                        hp = key
+                    elif hp != key:
+                        return None
+                if lr is None:
+                    lr = this
+                elif lr != this:
+                    return None
+            lrs.append(lr)
+        if len(group_of) != sum(1 for lst in (z_list, c_list) for t in lst if id(t) in group_of):
+            return None  # the optimizer also owns parameters other than z / c
+        if hp is None:
+            return None
+        clamps = [_clamp_of(variables.input.z.hook_fn), _clamp_of(variables.input.c.hook_fn)]
+        if any(c is False for c in clamps):
+            return None
+        # optimizer state: fresh everywhere, or stepped the same number of times everywhere
+        steps = set()
+        for lst in (z_list, c_list):
+            for t in lst:
+                if id(t) in group_of:
+                    st = opt.state.get(t, None)
+                    steps.add(int(st["step"]) if st else 0)
+        if len(steps) > 1:
+            return None
+        return dict(lr_z=lrs[0], lr_c=lrs[1], betas=hp[0], eps=hp[1], clamp_z=clamps[0], clamp_c=clamps[1],
+                    step0=steps.pop() if steps else 0, stateful=set(group_of.keys()))
+
+    @torch.no_grad()
+    def _fused_steps(self, variables, n_steps, plan):
+        from .. import native
+        from .closure import _unwrap
+        from ..variable_manager import split_vars
+        rank, size = parallel.world()
+        local = parallel.shard_vars(variables, rank, size) if size > 1 else variables
+        m = _unwrap(self.model)
+        z_list, c_list = local.input.z.data, local.input.c.data
+        n = len(z_list)
+        z = torch.stack(z_list).float().contiguous()
+        c = torch.stack(c_list).float().contiguous()
+        dev = z.device
+        first = {k: v.data[0] for k, v in local.output.items()}
+        tgt = self.loss_fn.prepared_target(first["target"], first.get("weight"), first.get("loss_mask"))
+        # d(mean over the chunk)/d loss_i = 1 / chunk size (closure.py:58), per sample
+        dloss = torch.cat([torch.full((ch.num_samples,), 1.0 / ch.num_samples)
+                           for ch in split_vars(local, size=self.max_batch_size)]).to(dev)
+        opt = variables.opt
+        state = native.AdamState(n, z.shape[1], c.shape[1], dev, step=plan["step0"])
+        if plan["step0"] > 0:
+            mz, vz, mc, vc = state.moments()
+            for i in range(n):
+                for t, mm, vv in ((z_list[i], mz, vz), (c_list[i], mc, vc)):
+                    st = opt.state.get(t, None)
+                    if st:
+                        mm[i].copy_(st["exp_avg"])
+                        vv[i].copy_(st["exp_avg_sq"])
+        cfg = native.adam_config(plan["lr_z"], plan["lr_c"], plan["betas"], plan["eps"], plan["clamp_z"], plan["clamp_c"])
+        res = native.biggan_optimize(m.native, self.loss_fn.native_lpips(), tgt, z, c, n_steps, cfg, state=state,
+                                     dloss=dloss, grad_scale=1.0, track=self.track_variables)
+        # back into the per-sample leaves and the torch optimizer (so per-step calls can follow)
+        mz, vz, mc, vc = state.moments()
+        t_now = plan["step0"] + n_steps
+        for i in range(n):
+            z_list[i].data.copy_(z[i])
+            c_list[i].data.copy_(c[i])
+            for t, mm, vv in ((z_list[i], mz, vz), (c_list[i], mc, vc)):
+                if id(t) in plan["stateful"]:
+                    opt.state[t] = {"step": torch.tensor(float(t_now)), "exp_avg": mm[i].clone(),
+                                    "exp_avg_sq": vv[i].clone()}
+        if self.track_variables:
+            lo, hi = parallel.shard_bounds(variables.num_samples, rank, size) if size > 1 else (0, n)
+            for name, hist in (("z", res["z_hist"]), ("c", res["c_hist"])):
+                hist = hist.cpu()
+                if size > 1:
+                    base = torch.stack(variables.input[name].data).cpu()
+                for j in range(n_steps):
+                    if size > 1:
+                        full = base.clone()
+                        full[lo:hi] = hist[j]
+                    else:
+                        full = hist[j].clone()
+                    self.tracked.setdefault(name, []).append(full)
+        self.out = res["img"]
+        self.loss = list(res["loss"][-1].cpu().numpy())
+        self.loss_history = res["loss"]  # [n_steps, n_local] device tensor of every step's losses
+        self.other = {}
+        self._n_total = variables.num_samples
+        self.fused_calls += 1
+        self.fused_graph = res["graph"]
 
     def gathered_loss(self):
         """Per-candidate losses of the whole population (one all_gather of scalars when sharded)."""

@@ -17,8 +17,7 @@ class GradientOptimizer(_BaseOptimizer):
         """
         self._start_run()
         variables = self._variables = self.var_manager.initialize(num_samples=num_samples)
-        for i in range(grad_steps):
-            self.step(variables, optimize=True, transform=(i == 0))
-            # the reference reports progress i/grad_steps before incrementing
-            self._after_step(i, grad_steps, log_at=i + 1, log_last=grad_steps, pbar=pbar)
+        # the reference reports progress i/grad_steps before incrementing
+        self.grad_steps(variables, grad_steps,
+                        lambda i: self._after_step(i, grad_steps, log_at=i + 1, log_last=grad_steps, pbar=pbar))
         return self._finish(variables, grad_steps)

@@ -26,10 +26,13 @@ class HybridNevergradOptimizer(_BaseOptimizer, _BaseNevergradOptimizer):
         for meta_iter in range(meta_steps + 1):
             last = meta_iter == meta_steps
             variables = self._variables = self.ng_init(self.var_manager, num_samples)
-            for j in range(last_grad_steps if last else grad_steps):
-                self.step(variables, optimize=True, transform=(j == 0))
-                i += 1
-                self._after_step(i, total_steps, log_at=i + 1, log_last=grad_steps, pbar=pbar)
+            n_inner = last_grad_steps if last else grad_steps
+
+            def on_step(j, i0=i):
+                self._after_step(i0 + j + 1, total_steps, log_at=i0 + j + 2, log_last=grad_steps, pbar=pbar)
+
+            self.grad_steps(variables, n_inner, on_step)
+            i += n_inner
             if not last:
                 self.ng_update(variables, inverted_loss=True)
         return self._finish(variables, total_steps)
