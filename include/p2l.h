@@ -115,6 +115,21 @@ int p2l_biggan_step(p2l_biggan* g, p2l_lpips* l, p2l_target* t, int b, const flo
                     const float* c_dev, int want_grad, float grad_scale, const float* dloss_dev,
                     float* loss_dev, float* dz_dev, float* dc_dev, float* img_dev, void* stream);
 
+/* ---- transform search: per-candidate targets
+ * p2l_affine_resample replaces SpatialTransform.transform / invert_transform
+ * (pix2latent/transform/spatial_transform.py:69-104): dst[b,C,H,W] = F.grid_sample(src, F.affine_grid(theta,
+ * src.size())) with torch's defaults (bilinear, zero padding, align_corners=False). theta_dev[b,2,3];
+ * src_batch = b, or 1 when every row resamples the same source image. */
+int p2l_affine_resample(const float* src_dev, int src_batch, const float* theta_dev, float* dst_dev, int b, int C,
+                        int H, int W, void* stream);
+/* p2l_biggan_step with one target per candidate (targets: HOST array of b handles created by
+ * p2l_target_create with the same resolution / loss configuration; consecutive equal handles are batched):
+ * what closure.py:51-58 computes when the 'target' / 'weight' variables were replaced per sample by
+ * base_optimizer.py:61-79 (apply_transform). */
+int p2l_biggan_step_targets(p2l_biggan* g, p2l_lpips* l, p2l_target* const* targets, int b, const float* z_dev,
+                            const float* c_dev, int want_grad, float grad_scale, const float* dloss_dev,
+                            float* loss_dev, float* dz_dev, float* dc_dev, float* img_dev, void* stream);
+
 /* ---- device-resident inner loop: `steps` repetitions of closure.py:38-71 for one
  * population of b candidates without a host round trip —
  *     hooks: function_hooks.py:10-27 Clamp (clamp_z / clamp_c > 0: clamp to [-x, x] before every forward)

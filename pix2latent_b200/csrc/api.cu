@@ -190,6 +190,42 @@ P2L_EXPORT int p2l_biggan_step(p2l_biggan* g, p2l_lpips* l, p2l_target* t, int b
     P2L_TRY_END
 }
 
+// ----------------------------------------------------------------------------- transform search
+P2L_EXPORT int p2l_affine_resample(const float* src, int src_batch, const float* theta, float* dst, int b, int C, int H, int W,
+                                   void* stream) {
+    if (!src || !theta || !dst || b <= 0 || C <= 0 || H <= 0 || W <= 0 || (src_batch != 1 && src_batch != b)) {
+        set_error("p2l_affine_resample: bad argument");
+        return -1;
+    }
+    P2L_TRY_BEGIN
+    k_affine_resample(src, src_batch, theta, dst, b, C, H, W, static_cast<cudaStream_t>(stream));
+    P2L_CUDA_CHECK(cudaGetLastError());
+    return 0;
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_biggan_step_targets(p2l_biggan* g, p2l_lpips* l, p2l_target* const* targets, int b, const float* z,
+                                       const float* c, int want_grad, float grad_scale, const float* dloss, float* loss,
+                                       float* dz, float* dc, float* img, void* stream) {
+    if (!g || !l || !targets || b <= 0 || !z || !c || !loss) { set_error("p2l_biggan_step_targets: bad argument"); return -1; }
+    if (want_grad && (!dz || !dc)) { set_error("p2l_biggan_step_targets: want_grad needs dz and dc"); return -1; }
+    P2L_TRY_BEGIN
+    std::vector<Target*> Ts((size_t)b);
+    for (int i = 0; i < b; ++i) {
+        if (!targets[i] || !targets[i]->t) { set_error("p2l_biggan_step_targets: target %d is NULL", i); return -1; }
+        Ts[i] = targets[i]->t;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g->g.forward(b, z, c, img, st)) return -1;
+    const float* im = img ? img : g->g.last_image(b);
+    if (l->l.loss_forward_multi(Ts.data(), b, im, loss, want_grad, st)) return -1;
+    if (!want_grad) return 0;
+    float* dimg = l->l.unit_grad(*Ts[0], b);
+    if (!dimg) return -1;
+    if (g->g.backward(b, dimg, dz, dc, st, grad_scale, dloss)) return -1;
+    return 0;
+    P2L_TRY_END
+}
+
 // ----------------------------------------------------------------------------- device-resident inner loop
 P2L_EXPORT int p2l_biggan_optimize(p2l_biggan* g, p2l_lpips* l, p2l_target* t, int b, int steps, float* z, float* c,
                                    const float* dloss, float grad_scale, const p2l_adam_config* cfg, float* mv, int* counters,

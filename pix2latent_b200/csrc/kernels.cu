@@ -935,4 +935,43 @@ void k_nhwc_to_dimg_scaled(const bf16* dx, int Cp, float* dimg, int b, int H, in
     nhwc_to_dimg_scaled_kernel<<<cdiv(total, 256), 256, 0, st>>>(dx, Cp, dimg, b, H, W, accumulate, unscale); count_launch();
 }
 
+// ============================================================================= transform search
+// F.affine_grid(theta, size) (align_corners=False): x_j = (2j + 1)/W - 1, y_i = (2i + 1)/H - 1,
+//   (gx, gy) = theta[n] . (x_j, y_i, 1)
+// F.grid_sample(src, grid) (bilinear, padding zeros, align_corners=False):
+//   ix = ((gx + 1) * W - 1) / 2, iy likewise; out = sum over the four neighbours inside the image of
+//   src * (1 - |ix - x0|)(1 - |iy - y0|)
+__global__ void affine_resample_kernel(const float* __restrict__ src, int src_batch, const float* __restrict__ theta,
+                                       float* __restrict__ dst, int b, int C, int H, int W) {
+    const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)b * H * W;
+    if (q >= total) return;
+    const int j = q % W, i = (q / W) % H, n = q / ((long)W * H);
+    const float* th = theta + (long)n * 6;
+    const float x = (2.f * j + 1.f) / W - 1.f, y = (2.f * i + 1.f) / H - 1.f;
+    const float gx = th[0] * x + th[1] * y + th[2];
+    const float gy = th[3] * x + th[4] * y + th[5];
+    const float ix = ((gx + 1.f) * W - 1.f) * 0.5f, iy = ((gy + 1.f) * H - 1.f) * 0.5f;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    const float ax = ix - fx0, ay = iy - fy0;
+    const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
+    const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
+    const bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
+    const float* s0 = src + (src_batch == 1 ? 0 : (long)n * C * H * W);
+    for (int c = 0; c < C; ++c) {
+        const float* sp = s0 + (long)c * H * W;
+        float v = 0.f;
+        if (vy0 && vx0) v += w00 * __ldg(sp + (long)y0 * W + x0);
+        if (vy0 && vx1) v += w01 * __ldg(sp + (long)y0 * W + x0 + 1);
+        if (vy1 && vx0) v += w10 * __ldg(sp + (long)(y0 + 1) * W + x0);
+        if (vy1 && vx1) v += w11 * __ldg(sp + (long)(y0 + 1) * W + x0 + 1);
+        dst[((long)n * C + c) * H * W + (long)i * W + j] = v;
+    }
+}
+void k_affine_resample(const float* src, int src_batch, const float* theta, float* dst, int b, int C, int H, int W,
+                       cudaStream_t st) {
+    affine_resample_kernel<<<cdiv((long)b * H * W, 256), 256, 0, st>>>(src, src_batch, theta, dst, b, C, H, W); count_launch();
+}
+
 }  // namespace p2l

@@ -108,4 +108,10 @@ void k_im2col_rgb_bwd(const float* dimg, const float* img, bf16* col, int b, int
 
 void k_fill_f32(float* p, float v, long n, cudaStream_t st);
 
+// ---- transform search (pix2latent/transform/spatial_transform.py:69-104) ---------------------
+// dst[b,C,H,W] = grid_sample(src, affine_grid(theta[b,2,3], src.size())) with torch's defaults (bilinear,
+// zeros padding, align_corners=False); src_batch 1: every output row samples the same source image
+void k_affine_resample(const float* src, int src_batch, const float* theta, float* dst, int b, int C, int H, int W,
+                       cudaStream_t st);
+
 }  // namespace p2l

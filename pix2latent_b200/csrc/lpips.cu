@@ -305,16 +305,43 @@ Target* Lpips::make_target(const float* target, const float* weight, const float
 
 // ----------------------------------------------------------------------------- loss
 int Lpips::loss_forward(Target& T, int b, const float* img, float* loss, int want_grad, cudaStream_t st) {
+    std::vector<Target*> Ts((size_t)b, &T);
+    return loss_forward_multi(Ts.data(), b, img, loss, want_grad, st);
+}
+
+// One target PER CANDIDATE (transform search, pix2latent/transform/transform_optimizer.py:165-255: every
+// candidate's target / weight is its own affine resample): the generator-side work (features, dgrad) is
+// batched as before; only the target-dependent kernels (pixel term, layer distances) run once per run of
+// consecutive identical targets. All targets must share the resolution and the loss configuration.
+int Lpips::loss_forward_multi(Target* const* Ts, int b, const float* img, float* loss, int want_grad, cudaStream_t st) {
+    Target& T = *Ts[0];
+    for (int i = 1; i < b; ++i) {
+        const Target& U = *Ts[i];
+        if (U.H != T.H || U.W != T.W || U.rec_type != T.rec_type || U.rec_w != T.rec_w || U.per_w != T.per_w || U.m != T.m) {
+            set_error("lpips: per-candidate targets must share resolution and loss configuration");
+            return -1;
+        }
+    }
     LpipsPlan* Pp = plan(b, T.H, T.W);
     if (!Pp) return -1;
     LpipsPlan& P = *Pp;
     const int n = (int)convs.size();
     const int HW = T.H * T.W;
+    // runs of consecutive identical targets: [r0[k], r0[k+1])
+    std::vector<int> r0;
+    for (int i = 0; i < b; ++i)
+        if (i == 0 || Ts[i] != Ts[i - 1]) r0.push_back(i);
+    r0.push_back(b);
+    const int nr = (int)r0.size() - 1;
     P2L_CUDA_CHECK(cudaMemsetAsync(loss, 0, (size_t)b * sizeof(float), st));
     // pixel term (also initialises dimg)
     if (T.rec_w != 0.f) {
-        k_l1_loss(img, T.target, T.weight, T.mask, T.total + 1, loss, want_grad ? P.dimg : nullptr, b, 3 * HW, HW,
-                  T.rec_type == 2, st);
+        for (int k = 0; k < nr; ++k) {
+            const Target& U = *Ts[r0[k]];
+            const int i0 = r0[k], nb = r0[k + 1] - r0[k];
+            k_l1_loss(img + (size_t)i0 * 3 * HW, U.target, U.weight, U.mask, U.total + 1, loss + i0,
+                      want_grad ? P.dimg + (size_t)i0 * 3 * HW : nullptr, nb, 3 * HW, HW, U.rec_type == 2, st);
+        }
     } else if (want_grad) {
         P2L_CUDA_CHECK(cudaMemsetAsync(P.dimg, 0, (size_t)b * 3 * HW * sizeof(float), st));
     }
@@ -324,8 +351,13 @@ int Lpips::loss_forward(Target& T, int b, const float* img, float* loss, int wan
     for (int j = 0; j < n; ++j) {
         const int f = convs[j].feat;
         if (f < 0) continue;
-        k_lpips_dist(P.L[j].F, T.tfeat[f], lin[f], T.wadj[f], loss, want_grad ? P.L[j].g : nullptr, b, T.fh[f] * T.fw[f],
-                     chns[f], grad_scale(), st);
+        const size_t per = (size_t)T.fh[f] * T.fw[f] * chns[f];
+        for (int k = 0; k < nr; ++k) {
+            const Target& U = *Ts[r0[k]];
+            const int i0 = r0[k], nb = r0[k + 1] - r0[k];
+            k_lpips_dist(P.L[j].F + i0 * per, U.tfeat[f], lin[f], U.wadj[f], loss + i0, want_grad ? P.L[j].g + i0 * per : nullptr,
+                         nb, T.fh[f] * T.fw[f], chns[f], grad_scale(), st);
+        }
     }
     if (!want_grad) return 0;
     // ---- backward through the backbone (dgrad only)

@@ -49,6 +49,7 @@ struct Lpips {
     Target* make_target(const float* target, const float* weight, const float* mask, int H, int W, int rec_type,
                         float rec_weight, float per_weight, cudaStream_t st);
     int loss_forward(Target& T, int b, const float* img, float* loss, int want_grad, cudaStream_t st);
+    int loss_forward_multi(Target* const* Ts, int b, const float* img, float* loss, int want_grad, cudaStream_t st);
     int loss_backward(Target& T, int b, const float* dloss, float* dimg, cudaStream_t st);
     float* unit_grad(Target& T, int b);
     double flops(int b, int H, int W, int backward);

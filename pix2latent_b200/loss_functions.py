@@ -114,7 +114,9 @@ class _TargetCache:
             if k == key:
                 return tgt
         tgt = self.lp.make_target(target, weight, mask, self.rec_type, self.rec_weight, self.per_weight)
-        self.entries.append((key, tgt, (target, weight, mask)))
+        # detached aliases pin the STORAGE the key's pointers refer to (a leaf whose `.data` is rebound later,
+        # base_optimizer.py apply_transform, would otherwise let the allocator reuse the address under a live key)
+        self.entries.append((key, tgt, tuple(None if t is None else t.detach() for t in (target, weight, mask))))
         if len(self.entries) > self.capacity:
             self.entries.pop(0)
         return tgt
@@ -157,6 +159,16 @@ class _NativeLoss(nn.Module):
     def prepared_target(self, target, weight=None, loss_mask=None):
         """target/weight/loss_mask: single [3,H,W] tensors -> cached NativeTarget."""
         return self.target_cache().get(target, weight, loss_mask)
+
+    def prepared_targets(self, targets, weights=None, loss_masks=None):
+        """Per-candidate targets (lists of [3,H,W] tensors; transform search): one cached NativeTarget per
+        row, rows with identical storage share one."""
+        if getattr(self, "_row_cache", None) is None:
+            self._row_cache = _TargetCache(self.native_lpips(), self._rec_type, self._rec_weight, self._per_weight,
+                                           capacity=96)
+        n = len(targets)
+        return [self._row_cache.get(targets[i], None if weights is None else weights[i],
+                                    None if loss_masks is None else loss_masks[i]) for i in range(n)]
 
     def __call__(self, output, target, weight=None, loss_mask=None):
         if not output.is_cuda:

@@ -66,6 +66,8 @@ def declare(L):
         "p2l_lpips_flops": (C.c_double, [vp, ci, ci, ci, ci]),
         "p2l_lpips_launches": (ci, [vp, ci]),
         "p2l_biggan_step": (ci, [vp, vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]),
+        "p2l_affine_resample": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, vp]),
+        "p2l_biggan_step_targets": (ci, [vp, vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]),
         "p2l_biggan_optimize": (ci, [vp, vp, vp, ci, ci, vp, vp, vp, cf, C.POINTER(AdamConfigC), vp, vp, vp, vp, vp, vp,
                                     ci, vp]),
         "p2l_biggan_optimize_used_graph": (ci, [vp]),
@@ -95,6 +97,7 @@ EXPORTED_SYMBOLS = [
     "p2l_lpips_destroy", "p2l_target_create", "p2l_target_destroy", "p2l_loss_forward",
     "p2l_loss_backward", "p2l_lpips_flops", "p2l_lpips_launches", "p2l_biggan_step",
     "p2l_biggan_optimize", "p2l_biggan_optimize_used_graph", "p2l_adam_update",
+    "p2l_affine_resample", "p2l_biggan_step_targets",
     "p2l_profile_enable", "p2l_profile_read", "p2l_sg2_create", "p2l_sg2_set_tensor", "p2l_sg2_finalize",
     "p2l_sg2_destroy", "p2l_sg2_num_noise_layers", "p2l_sg2_forward", "p2l_sg2_backward", "p2l_sg2_step",
     "p2l_debug_conv", "p2l_debug_set_option", "p2l_debug_get_option", "p2l_debug_profile_get",
@@ -422,3 +425,37 @@ def biggan_optimize(gen, lp, tgt, z, c, steps, cfg, state=None, dloss=None, grad
     # the library ran on an internal stream ordered before the current one; keep the buffers alive until here
     graph = bool(_lib.lib().p2l_biggan_optimize_used_graph(gen.h))
     return {"loss": loss, "z_hist": zh, "c_hist": ch, "img": img, "state": state, "graph": graph, "_keep": dl}
+
+
+def affine_resample(src, theta):
+    """``F.grid_sample(src, F.affine_grid(theta, size))`` with torch's defaults (bilinear, zero padding,
+    align_corners=False) — SpatialTransform.transform (pix2latent/transform/spatial_transform.py:69-85).
+    src [b,C,H,W] or [1,C,H,W] (shared source), theta [b,2,3] -> [b,C,H,W]."""
+    src, theta = _f32c(src), _f32c(theta)
+    assert src.dim() == 4 and theta.dim() == 3 and tuple(theta.shape[1:]) == (2, 3)
+    b = theta.shape[0]
+    assert src.shape[0] in (1, b), "source batch must be 1 or match theta"
+    C_, H, W = int(src.shape[1]), int(src.shape[2]), int(src.shape[3])
+    dst = torch.empty(b, C_, H, W, device=src.device, dtype=torch.float32)
+    _lib.check(_lib.lib().p2l_affine_resample(_lib.ptr(src), int(src.shape[0]), _lib.ptr(theta), _lib.ptr(dst), b, C_, H, W,
+                                              _lib.current_stream()))
+    return dst
+
+
+def biggan_step_targets(gen, lp, tgts, z, c, want_grad, grad_scale, want_img=True, dloss=None):
+    """``biggan_step`` with one NativeTarget per candidate (transform search: every candidate's target and
+    weight are their own resample). Returns (loss[b], dz, dc, img)."""
+    z, c = _f32c(z), _f32c(c)
+    b = z.shape[0]
+    assert len(tgts) == b, "one target per candidate"
+    dev = z.device
+    loss = torch.empty(b, device=dev, dtype=torch.float32)
+    dz = torch.empty_like(z) if want_grad else None
+    dc = torch.empty_like(c) if want_grad else None
+    img = torch.empty(b, 3, gen.out_res, gen.out_res, device=dev, dtype=torch.float32) if want_img else None
+    arr = (C.c_void_p * b)(*[t.h for t in tgts])
+    _lib.check(_lib.lib().p2l_biggan_step_targets(gen.h, lp.h, arr, b, _lib.ptr(z), _lib.ptr(c), int(want_grad),
+                                                  float(grad_scale), _lib.ptr(None if dloss is None else _f32c(dloss)),
+                                                  _lib.ptr(loss), _lib.ptr(dz), _lib.ptr(dc), _lib.ptr(img),
+                                                  _lib.current_stream()))
+    return loss, dz, dc, img

@@ -40,6 +40,24 @@ def _native_pair(model, vars, loss_fn):
     return "target" in outs and outs <= {"target", "weight", "loss_mask"}
 
 
+def _native_targets_pair(model, vars, loss_fn):
+    """BigGAN + native loss with PER-CANDIDATE targets: a 'transform' variable group is present, i.e.
+    base_optimizer.apply_transform replaced every sample's target / weight (transform search)."""
+    from ..loss_functions import _NativeLoss
+    from ..model.biggan import BigGAN
+    m = _unwrap(model)
+    if not (isinstance(m, BigGAN) and isinstance(loss_fn, _NativeLoss) and m.native is not None):
+        return False
+    if "transform" not in vars.keys():
+        return False
+    if any(k not in ("input", "output", "transform", "opt", "num_samples") for k in vars.keys()):
+        return False
+    if set(vars.input.keys()) != {"z", "c"}:
+        return False
+    outs = set(vars.output.keys()) if "output" in vars else set()
+    return "target" in outs and outs <= {"target", "weight", "loss_mask"}
+
+
 def _run_hooks(group):
     for _, var in group.items():
         if var.hook_fn is not None:
@@ -108,6 +126,37 @@ def _step_native(model, vars, loss_fn, optimize, max_batch_size):
     return img, list(loss.cpu().numpy()), {}
 
 
+def _step_native_targets(model, vars, loss_fn, optimize, max_batch_size):
+    """As ``_step_native`` with one cached NativeTarget per candidate (p2l_biggan_step_targets)."""
+    from .. import native
+    m = _unwrap(model)
+    chunks = split_vars(vars, size=max_batch_size)
+    for chunk in chunks:
+        _run_hooks(chunk.input)
+    z_list, c_list = vars.input.z.data, vars.input.c.data
+    n = len(z_list)
+    with torch.no_grad():
+        z = torch.stack(z_list)
+        c = torch.stack(c_list)
+    o = vars.output
+    tgts = loss_fn.prepared_targets(o.target.data, o.weight.data if "weight" in o else None,
+                                    o.loss_mask.data if "loss_mask" in o else None)
+    dloss = torch.cat([torch.full((ch.num_samples,), 1.0 / ch.num_samples) for ch in chunks]).to(z.device)
+    loss, dz, dc, img = native.biggan_step_targets(m.native, loss_fn.native_lpips(), tgts, z, c, want_grad=optimize,
+                                                   grad_scale=1.0, dloss=dloss)
+    if optimize:
+        opt = vars.opt
+        opt.zero_grad()
+        for i in range(n):
+            if z_list[i].requires_grad:
+                z_list[i].grad = dz[i]
+            if c_list[i].requires_grad:
+                c_list[i].grad = dc[i]
+        opt.step()
+        opt.zero_grad()
+    return img, list(loss.cpu().numpy()), {}
+
+
 def _native_sg2_pair(model, vars, loss_fn):
     from ..loss_functions import _NativeLoss
     from ..model.stylegan2 import StyleGAN2
@@ -157,6 +206,8 @@ def step(model, vars, loss_fn, optimize=True, max_batch_size=9):
     Returns ``(outs [N,3,H,W], indiv_losses list[N], {})`` as the reference does."""
     if _native_pair(model, vars, loss_fn):
         return _step_native(model, vars, loss_fn, optimize, max_batch_size)
+    if _native_targets_pair(model, vars, loss_fn):
+        return _step_native_targets(model, vars, loss_fn, optimize, max_batch_size)
     if _native_sg2_pair(model, vars, loss_fn):
         return _step_native_sg2(model, vars, loss_fn, optimize, max_batch_size)
     return _step_autograd(model, vars, loss_fn, optimize, max_batch_size)
