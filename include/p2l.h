@@ -186,6 +186,23 @@ int p2l_sg2_step(p2l_sg2* g, p2l_lpips* l, p2l_target* t, int b, const float* z_
                  int want_grad, float grad_scale, const float* dloss_dev, float* loss_dev, float* dz_dev, float* img_dev,
                  void* stream);
 
+/* ---- StyleGAN2 w / w+ / noise search: replaces StyleGAN2.forward_w
+ *      (pix2latent/model/stylegan2.py:122-125: `model([w], input_is_latent=True, noise=noises)[0].clamp_(-1, 1)`)
+ * latent_dev[b, n_latent, style_dim], n_latent = 2*log2(size) - 2: StyledConv l reads row l, ToRGB t reads row
+ * 2t+1 (rosinality Generator.forward); a plain w is the same row repeated. The mapping network is skipped.
+ * Backward reaches the latent rows and — when dnoise_dev (HOST array of num_noise_layers DEVICE pointers, entries
+ * may be NULL) is given — every layer's noise image [b,1,r,r]. */
+int p2l_sg2_n_latent(p2l_sg2* m);
+/* w_dev[b, style_dim] = style(z) (PixelNorm + 8 EqualLinear): what stylegan2.py:97-104 samples 4096 times for
+ * latent_mean / latent_std */
+int p2l_sg2_style(p2l_sg2* m, int b, const float* z_dev, float* w_dev, void* stream);
+int p2l_sg2_forward_w(p2l_sg2* m, int b, const float* latent_dev, const float* const* noise_dev, float* img_dev, void* stream);
+int p2l_sg2_backward_w(p2l_sg2* m, int b, const float* dimg_dev, float* dlatent_dev, float* const* dnoise_dev, void* stream);
+/* fused step, as p2l_sg2_step */
+int p2l_sg2_step_w(p2l_sg2* g, p2l_lpips* l, p2l_target* t, int b, const float* latent_dev, const float* const* noise_dev,
+                   int want_grad, float grad_scale, const float* dloss_dev, float* loss_dev, float* dlatent_dev,
+                   float* const* dnoise_dev, float* img_dev, void* stream);
+
 /* ---- measurement hooks (bench.py): while enabled, every tensor-core launch is bracketed by
  * CUDA events on its stream; p2l_profile_read synchronises and returns the summed duration
  * (ms), the number of launches and their algorithmic FLOPs since the last enable. */

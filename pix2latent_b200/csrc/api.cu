@@ -311,3 +311,40 @@ P2L_EXPORT int p2l_sg2_step(p2l_sg2* g, p2l_lpips* l, p2l_target* t, int b, cons
     return g->g.backward(b, dimg, dz, st, grad_scale, dloss);
     P2L_TRY_END
 }
+
+// ----------------------------------------------------------------------------- StyleGAN2 w / w+ / noise search
+P2L_EXPORT int p2l_sg2_n_latent(p2l_sg2* m) { return (m && m->g.finalized) ? m->g.n_latent() : 0; }
+P2L_EXPORT int p2l_sg2_style(p2l_sg2* m, int b, const float* z, float* w, void* stream) {
+    if (!m || b <= 0 || !z || !w) { set_error("p2l_sg2_style: bad argument"); return -1; }
+    P2L_TRY_BEGIN
+    return m->g.style(b, z, w, static_cast<cudaStream_t>(stream));
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_sg2_forward_w(p2l_sg2* m, int b, const float* latent, const float* const* noise, float* img, void* stream) {
+    if (!m || b <= 0 || !latent) { set_error("p2l_sg2_forward_w: bad argument"); return -1; }
+    P2L_TRY_BEGIN
+    return m->g.forward_w(b, latent, noise, img, static_cast<cudaStream_t>(stream));
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_sg2_backward_w(p2l_sg2* m, int b, const float* dimg, float* dlatent, float* const* dnoise, void* stream) {
+    if (!m || b <= 0 || !dimg || !dlatent) { set_error("p2l_sg2_backward_w: bad argument"); return -1; }
+    P2L_TRY_BEGIN
+    return m->g.backward_w(b, dimg, dlatent, dnoise, static_cast<cudaStream_t>(stream));
+    P2L_TRY_END
+}
+P2L_EXPORT int p2l_sg2_step_w(p2l_sg2* g, p2l_lpips* l, p2l_target* t, int b, const float* latent, const float* const* noise,
+                              int want_grad, float grad_scale, const float* dloss, float* loss, float* dlatent,
+                              float* const* dnoise, float* img, void* stream) {
+    if (!g || !l || !t || b <= 0 || !latent || !loss) { set_error("p2l_sg2_step_w: bad argument"); return -1; }
+    if (want_grad && !dlatent) { set_error("p2l_sg2_step_w: want_grad needs dlatent"); return -1; }
+    P2L_TRY_BEGIN
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g->g.forward_w(b, latent, noise, img, st)) return -1;
+    const float* im = img ? img : g->g.last_image(b);
+    if (l->l.loss_forward(*t->t, b, im, loss, want_grad, st)) return -1;
+    if (!want_grad) return 0;
+    float* dimg = l->l.unit_grad(*t->t, b);
+    if (!dimg) return -1;
+    return g->g.backward_w(b, dimg, dlatent, dnoise, st, grad_scale, dloss);
+    P2L_TRY_END
+}

@@ -33,6 +33,7 @@ struct SG2Plan {
     float *drgbA = nullptr, *drgbB = nullptr, *img = nullptr;
     act_t *dx[2] = {nullptr, nullptr}, *G = nullptr, *dDp = nullptr, *dA = nullptr;
     bool forward_done = false;
+    int mode = 0;  // 0: z search (mapping network ran), 1: w / w+ search (styles from the latent rows)
 };
 
 SG2::~SG2() {}
@@ -252,20 +253,67 @@ SG2Plan* SG2::plan(int b) {
     return raw;
 }
 
+// mapping network: PixelNorm + n_mlp EqualLinear(fused_lrelu); h[0..n_mlp] are [b, sdim] buffers, h[n_mlp] = w
+int SG2::run_mapping(int b, const float* z, float* zbuf, float* const* h, cudaStream_t st) {
+    P2L_CUDA_CHECK(cudaMemcpyAsync(zbuf, z, (size_t)b * sdim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    k_pixelnorm_fwd(zbuf, h[0], b, sdim, st);
+    for (int k = 0; k < n_mlp; ++k)
+        k_fc_fwd(h[k], sdim, map_WT[k], map_b[k], map_scale, h[k + 1], sdim, b, sdim, sdim, 1, 0, st);
+    return 0;
+}
+
+int SG2::style(int b, const float* z, float* w, cudaStream_t st) {
+    if (!finalized) { set_error("sg2: style before finalize"); return -1; }
+    // own scratch (not a full per-batch plan: this is called with thousands of samples for the latent statistics)
+    auto it = style_scratch.find(b);
+    if (it == style_scratch.end()) {
+        float* p = style_ar.alloc<float>((size_t)(n_mlp + 2) * b * sdim);
+        if (!p) return -1;
+        it = style_scratch.emplace(b, p).first;
+    }
+    float* base = it->second;
+    float* h[16];
+    for (int k = 0; k <= n_mlp; ++k) h[k] = base + (size_t)(k + 1) * b * sdim;
+    if (run_mapping(b, z, base, h, st)) return -1;
+    P2L_CUDA_CHECK(cudaMemcpyAsync(w, h[n_mlp], (size_t)b * sdim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 int SG2::forward(int b, const float* z, const float* const* noise, float* img, cudaStream_t st) {
     if (!finalized) { set_error("sg2: forward before finalize"); return -1; }
     SG2Plan* Pp = plan(b);
     if (!Pp) return -1;
     SG2Plan& P = *Pp;
-    const int nL = (int)convs.size();
-    P2L_CUDA_CHECK(cudaMemcpyAsync(P.z, z, (size_t)b * sdim * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    // mapping network
-    k_pixelnorm_fwd(P.z, P.h[0], b, sdim, st);
-    for (int k = 0; k < n_mlp; ++k)
-        k_fc_fwd(P.h[k], sdim, map_WT[k], map_b[k], map_scale, P.h[k + 1], sdim, b, sdim, sdim, 1, 0, st);
+    if (run_mapping(b, z, P.z, P.h, st)) return -1;
     const float* w = P.h[n_mlp];
     // styles of every modulated conv / ToRGB (the same w feeds all of them in z search)
     k_fc_fwd(w, sdim, affT, aff_b, 1.f / std::sqrt((float)sdim), P.s_all, S, b, sdim, S, 0, 0, st);
+    P.mode = 0;
+    return synth(P, b, noise, img, st);
+}
+
+int SG2::forward_w(int b, const float* latent, const float* const* noise, float* img, cudaStream_t st) {
+    if (!finalized) { set_error("sg2: forward_w before finalize"); return -1; }
+    SG2Plan* Pp = plan(b);
+    if (!Pp) return -1;
+    SG2Plan& P = *Pp;
+    const int nlat = n_latent(), ldl = nlat * sdim;
+    const float sc = 1.f / std::sqrt((float)sdim);
+    // every modulation reads ITS row of the latent: one small GEMV per layer on a column block of affT
+    for (size_t l = 0; l < convs.size(); ++l) {
+        const Conv& c = convs[l];
+        k_fc_fwd_ld(latent + l * sdim, ldl, affT + c.s_off, S, aff_b + c.s_off, sc, P.s_all + c.s_off, S, b, sdim, c.Cin, 0, 0, st);
+    }
+    for (size_t t = 0; t < rgbs.size(); ++t) {
+        const Rgb& r = rgbs[t];
+        k_fc_fwd_ld(latent + (2 * t + 1) * sdim, ldl, affT + r.s_off, S, aff_b + r.s_off, sc, P.s_all + r.s_off, S, b, sdim, r.Cin, 0, 0, st);
+    }
+    P.mode = 1;
+    return synth(P, b, noise, img, st);
+}
+
+int SG2::synth(SG2Plan& P, int b, const float* const* noise, float* img, cudaStream_t st) {
+    const int nL = (int)convs.size();
     for (int l = 0; l < nL; ++l) {
         const Conv& c = convs[l];
         k_fc_fwd(P.s_all + c.s_off, S, c.wsqT, nullptr, 1.f, P.dm_all + c.dm_off, DM, b, c.Cin, c.Cout, 2, 1, st);
@@ -296,10 +344,8 @@ int SG2::forward(int b, const float* z, const float* const* noise, float* img, c
     return 0;
 }
 
-int SG2::backward(int b, const float* dimg, float* dz, cudaStream_t st, float scale, const float* row_scale) {
-    auto it = plans.find(b);
-    if (it == plans.end() || !it->second->forward_done) { set_error("sg2: backward(b=%d) without a matching forward", b); return -1; }
-    SG2Plan& P = *it->second;
+int SG2::synth_bwd(SG2Plan& P, int b, const float* dimg, float* const* dnoise, float out_scale, const float* row_scale,
+                   cudaStream_t st) {
     const int T = (int)rgbs.size();
     P2L_CUDA_CHECK(cudaMemsetAsync(P.ds_all, 0, (size_t)b * S * sizeof(float), st));
     P2L_CUDA_CHECK(cudaMemsetAsync(P.ddm_all, 0, (size_t)b * DM * sizeof(float), st));
@@ -309,6 +355,8 @@ int SG2::backward(int b, const float* dimg, float* dz, cudaStream_t st, float sc
     auto layer_bwd = [&](int l) -> int {
         const Conv& c = convs[l];
         SG2Plan::Lay& q = P.L[l];
+        if (dnoise && dnoise[l])
+            k_sg_noise_bwd(P.dx[l & 1], q.x, c.noise_w, dnoise[l], b, c.Hout, c.Hout, c.Cout, out_scale, row_scale, st);
         k_sg_post_bwd(P.dx[l & 1], q.x, q.D, P.dm_all + c.dm_off, DM, P.G, P.ddm_all + c.dm_off, b, c.Hout, c.Hout, c.Cout, c.up, st);
         if (c.up) k_sg_blur_adjoint(P.G, P.dDp, b, c.Hout, c.Hout, c.Cout, st);
         if (conv_op_launch(q.d, st)) return -1;
@@ -330,6 +378,15 @@ int SG2::backward(int b, const float* dimg, float* dz, cudaStream_t st, float sc
         if (t > 0 && layer_bwd(l - 1)) return -1;
         std::swap(dcur, dprev);
     }
+    return 0;
+}
+
+int SG2::backward(int b, const float* dimg, float* dz, cudaStream_t st, float scale, const float* row_scale) {
+    auto it = plans.find(b);
+    if (it == plans.end() || !it->second->forward_done) { set_error("sg2: backward(b=%d) without a matching forward", b); return -1; }
+    SG2Plan& P = *it->second;
+    if (P.mode != 0) { set_error("sg2: backward (z search) after forward_w; use backward_w"); return -1; }
+    if (synth_bwd(P, b, dimg, nullptr, 1.f, nullptr, st)) return -1;
     // styles -> w -> mapping network -> z
     k_fc_bwd(P.ds_all, S, nullptr, 0, aff, 1.f / std::sqrt((float)sdim), P.dw, sdim, b, sdim, S, 0, 0, st);
     float *g = P.dw, *gn = P.g0;
@@ -339,6 +396,30 @@ int SG2::backward(int b, const float* dimg, float* dz, cudaStream_t st, float sc
         gn = (gn == P.g0) ? P.g1 : P.g0;
     }
     k_pixelnorm_bwd(P.z, g, dz, b, sdim, scale / grad_scale(), row_scale, st);
+    return 0;
+}
+
+int SG2::backward_w(int b, const float* dimg, float* dlatent, float* const* dnoise, cudaStream_t st, float scale,
+                    const float* row_scale) {
+    auto it = plans.find(b);
+    if (it == plans.end() || !it->second->forward_done) { set_error("sg2: backward_w(b=%d) without a matching forward_w", b); return -1; }
+    SG2Plan& P = *it->second;
+    if (P.mode != 1) { set_error("sg2: backward_w after a z-search forward; use backward"); return -1; }
+    const float out_scale = scale / grad_scale();
+    if (synth_bwd(P, b, dimg, dnoise, out_scale, row_scale, st)) return -1;
+    const int nlat = n_latent(), ldl = nlat * sdim;
+    const float sc = 1.f / std::sqrt((float)sdim);
+    P2L_CUDA_CHECK(cudaMemsetAsync(dlatent, 0, (size_t)b * ldl * sizeof(float), st));
+    // styles -> their latent rows (row 2t+1 is shared by StyledConv 2t+1 and ToRGB t: accumulate)
+    for (size_t l = 0; l < convs.size(); ++l) {
+        const Conv& c = convs[l];
+        k_fc_bwd(P.ds_all + c.s_off, S, nullptr, 0, aff + (size_t)c.s_off * sdim, sc, dlatent + l * sdim, ldl, b, sdim, c.Cin, 0, 1, st);
+    }
+    for (size_t t = 0; t < rgbs.size(); ++t) {
+        const Rgb& r = rgbs[t];
+        k_fc_bwd(P.ds_all + r.s_off, S, nullptr, 0, aff + (size_t)r.s_off * sdim, sc, dlatent + (2 * t + 1) * sdim, ldl, b, sdim, r.Cin, 0, 1, st);
+    }
+    k_sg_scale_out(dlatent, b, (long)ldl, out_scale, row_scale, st);
     return 0;
 }
 

@@ -44,6 +44,20 @@ struct SG2 {
     SG2Plan* plan(int b);
     int forward(int b, const float* z, const float* const* noise, float* img, cudaStream_t st);
     int backward(int b, const float* dimg, float* dz, cudaStream_t st, float scale = 1.f, const float* row_scale = nullptr);
+    // w / w+ search (pix2latent/model/stylegan2.py:122-125 forward_w: Generator([w], input_is_latent=True, noise=noises)):
+    // latent [b, n_latent, sdim] (layer l reads row l, ToRGB t reads row 2t+1); backward to the latent rows and,
+    // when dnoise != null, to every layer's noise image
+    int n_latent() const { return 2 * log_size - 2; }
+    int style(int b, const float* z, float* w, cudaStream_t st);  // mapping network alone: w = style(z)
+    int run_mapping(int b, const float* z, float* zbuf, float* const* h, cudaStream_t st);
+    Arena style_ar;
+    std::map<int, float*> style_scratch;
+    int forward_w(int b, const float* latent, const float* const* noise, float* img, cudaStream_t st);
+    int backward_w(int b, const float* dimg, float* dlatent, float* const* dnoise, cudaStream_t st, float scale = 1.f,
+                   const float* row_scale = nullptr);
+    int synth(SG2Plan& P, int b, const float* const* noise, float* img, cudaStream_t st);
+    int synth_bwd(SG2Plan& P, int b, const float* dimg, float* const* dnoise, float out_scale, const float* row_scale,
+                  cudaStream_t st);
     const float* last_image(int b);
     ~SG2();
 };

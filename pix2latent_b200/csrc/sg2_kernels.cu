@@ -31,7 +31,7 @@ constexpr float kSqrt2 = 1.41421356237309515f;
 
 // ----------------------------------------------------------------------------- dense latent-side layers
 // y[b, j] = act(wscale * sum_k x[b,k] * WT[k][j] + bias[j]); thread per j, <= 24 samples per pass
-__global__ void fc_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ WT, const float* __restrict__ bias,
+__global__ void fc_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ WT, int ldw, const float* __restrict__ bias,
                               float wscale, float* y, int ldy, int b, int in, int out, int act, int square_in) {
     extern __shared__ float sx[];  // [b][in]
     for (int i = threadIdx.x; i < b * in; i += blockDim.x) {
@@ -48,7 +48,7 @@ __global__ void fc_fwd_kernel(const float* __restrict__ x, int ldx, const float*
         for (int k0 = 0; k0 < in; k0 += 8) {
             float w[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) w[u] = (k0 + u < in) ? __ldg(WT + (long)(k0 + u) * out + j) : 0.f;
+            for (int u = 0; u < 8; ++u) w[u] = (k0 + u < in) ? __ldg(WT + (long)(k0 + u) * ldw + j) : 0.f;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int k = min(k0 + u, in - 1);
@@ -68,14 +68,18 @@ __global__ void fc_fwd_kernel(const float* __restrict__ x, int ldx, const float*
         }
     }
 }
-void k_fc_fwd(const float* x, int ldx, const float* WT, const float* bias, float wscale, float* y, int ldy, int b, int in,
-              int out, int act, int square_in, cudaStream_t st) {
+void k_fc_fwd_ld(const float* x, int ldx, const float* WT, int ldw, const float* bias, float wscale, float* y, int ldy, int b,
+                 int in, int out, int act, int square_in, cudaStream_t st) {
     for (int b0 = 0; b0 < b; b0 += 16) {  // <= 16 samples per launch keeps the staged inputs under 48 KB
         const int nb = b - b0 < 16 ? b - b0 : 16;
-        fc_fwd_kernel<<<cdiv(out, 64), 64, (size_t)nb * in * sizeof(float), st>>>(x + (long)b0 * ldx, ldx, WT, bias, wscale,
+        fc_fwd_kernel<<<cdiv(out, 64), 64, (size_t)nb * in * sizeof(float), st>>>(x + (long)b0 * ldx, ldx, WT, ldw, bias, wscale,
                                                                                   y + (long)b0 * ldy, ldy, nb, in, out, act, square_in);
         count_launch();
     }
+}
+void k_fc_fwd(const float* x, int ldx, const float* WT, const float* bias, float wscale, float* y, int ldy, int b, int in,
+              int out, int act, int square_in, cudaStream_t st) {
+    k_fc_fwd_ld(x, ldx, WT, out, bias, wscale, y, ldy, b, in, out, act, square_in, st);
 }
 
 // dx[b, k] (+)= wscale * sum_j g[b,j] * W[j][k], g = dy * act'(y); thread per k
@@ -559,6 +563,40 @@ __global__ void clamp_bwd_kernel(const float* rgb, const float* dimg, float* drg
 }
 void k_sg_clamp_bwd(const float* rgb, const float* dimg, float* drgb, long n, float scale, cudaStream_t st) {
     clamp_bwd_kernel<<<cdiv(n, 256), 256, 0, st>>>(rgb, dimg, drgb, n, scale); count_launch();
+}
+
+// ----------------------------------------------------------------------------- w+ / noise search (stylegan2.py:122-125)
+// NoiseInjection backward: x = lrelu(dm*u + nw*noise + bias)*sqrt2  =>  dnoise[b,p] = nw * sum_c dx[b,p,c]*sqrt2*lrelu'(x[b,p,c]);
+// one warp per pixel; `scale` (and row_scale[b]) remove the 16-bit gradient scale / apply the upstream factor
+__global__ void noise_bwd_kernel(const bf16* __restrict__ dx, const bf16* __restrict__ x, const float* __restrict__ nw,
+                                 float* __restrict__ dnoise, long npix, int HW, int C, float scale, const float* __restrict__ row_scale) {
+    const long p = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= npix) return;
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    for (int c = lane * 8; c < C; c += 256) {
+        float g[8], xv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dx + p * C + c)), g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * C + c)), xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc += g[e] * (xv[e] > 0.f ? 1.f : 0.2f);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) dnoise[p] = acc * kSqrt2 * nw[0] * scale * (row_scale ? row_scale[p / HW] : 1.f);
+}
+void k_sg_noise_bwd(const bf16* dx, const bf16* x, const float* nw, float* dnoise, int b, int H, int W, int C, float scale,
+                    const float* row_scale, cudaStream_t st) {
+    const long npix = (long)b * H * W;
+    noise_bwd_kernel<<<cdiv(npix, 8), 256, 0, st>>>(dx, x, nw, dnoise, npix, H * W, C, scale, row_scale); count_launch();
+}
+// x[b, n] *= scale * (row_scale ? row_scale[b] : 1)
+__global__ void scale_out_kernel(float* x, long n, float scale, const float* row_scale) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[(long)blockIdx.y * n + i] *= scale * (row_scale ? row_scale[blockIdx.y] : 1.f);
+}
+void k_sg_scale_out(float* x, int b, long n, float scale, const float* row_scale, cudaStream_t st) {
+    dim3 grid(cdiv(n, 256), b);
+    scale_out_kernel<<<grid, 256, 0, st>>>(x, n, scale, row_scale); count_launch();
 }
 
 }  // namespace p2l

@@ -10,6 +10,9 @@ typedef act_t bf16;
 // square_in squares x first (demodulation)
 void k_fc_fwd(const float* x, int ldx, const float* WT, const float* bias, float wscale, float* y, int ldy, int b, int in,
               int out, int act, int square_in, cudaStream_t st);
+// same with an explicit row pitch of WT (a column block of a wider matrix)
+void k_fc_fwd_ld(const float* x, int ldx, const float* WT, int ldw, const float* bias, float wscale, float* y, int ldy, int b,
+                 int in, int out, int act, int square_in, cudaStream_t st);
 // dx (+)= wscale * (dy * act'(y)) W, W is [out][in]
 void k_fc_bwd(const float* dy, int lddy, const float* y, int ldy, const float* W, float wscale, float* dx, int lddx, int b,
               int in, int out, int act, int accumulate, cudaStream_t st);
@@ -33,5 +36,9 @@ void k_sg_torgb_bwd(const float* drgb, const bf16* x, const float* weff, bf16* d
 void k_sg_weff_bwd(const float* dweff, const float* Wr, float scale, float* ds, int ldds, int b, int C, cudaStream_t st);
 void k_sg_rgb_up_adjoint(const float* drgb, float* dprev, int b, int h, int w, cudaStream_t st);
 void k_sg_clamp(const float* rgb, float* img, long n, cudaStream_t st);
+// NoiseInjection backward: dnoise[b,1,H,W] = nw * sum_c dx * sqrt2 * lrelu'(x), times scale (* row_scale[b])
+void k_sg_noise_bwd(const bf16* dx, const bf16* x, const float* nw, float* dnoise, int b, int H, int W, int C, float scale,
+                    const float* row_scale, cudaStream_t st);
+void k_sg_scale_out(float* x, int b, long n, float scale, const float* row_scale, cudaStream_t st);
 void k_sg_clamp_bwd(const float* rgb, const float* dimg, float* drgb, long n, float scale, cudaStream_t st);
 }  // namespace p2l

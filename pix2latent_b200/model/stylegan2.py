@@ -8,8 +8,12 @@ across processes instead, pix2latent_b200/parallel.py).
 
 Per-layer noise: rosinality draws fresh N(0,1) per layer per forward; this wrapper draws it with
 torch's CUDA generator in the same layer order and hands the tensors to the library, so a run can
-be replayed with explicit ``noises``. ``search='w+'`` (forward_w) is not built yet
-(SURVEY.md §8f N3).
+be replayed with explicit ``noises``.
+
+``search='w+'`` (stylegan2.py:97-104, 122-138): ``__call__(z, noises)`` takes the latent in W ([b,512]) or W+
+([b,n_latent,512]) and the per-layer noise as ONE flat tensor [b, sum(r*r)] (``reshape_noise`` splits it); both
+are differentiable inputs (p2l_sg2_forward_w / p2l_sg2_backward_w); ``latent_mean`` / ``latent_std`` are the
+statistics of style(N(0,I)) over 4096 samples as the reference computes them.
 """
 import warnings
 
@@ -78,11 +82,30 @@ class _SG2Fn(torch.autograd.Function):
         return ctx.model.native.backward(ctx.b, dimg.contiguous()), None, None
 
 
+class _SG2WFn(torch.autograd.Function):
+    """image = G(w | w+, noise) with the mapping network skipped; backward to the latent and the flat noise."""
+
+    @staticmethod
+    def forward(ctx, w, noise_flat, model):
+        b = w.shape[0]
+        noises = None if noise_flat is None else model.reshape_noise(noise_flat)
+        ctx.model, ctx.b, ctx.w_dim, ctx.has_noise = model, b, w.dim(), noise_flat is not None
+        return native.sg2_forward_w(model.native, w, noises)
+
+    @staticmethod
+    def backward(ctx, dimg):
+        want_noise = ctx.has_noise and ctx.needs_input_grad[1]
+        dlat, dn = native.sg2_backward_w(ctx.model.native, ctx.b, dimg.contiguous(), want_noise_grad=want_noise)
+        dw = dlat.sum(1) if ctx.w_dim == 2 else dlat  # a plain w feeds every row
+        dnoise = torch.cat([t.reshape(ctx.b, -1) for t in dn], 1) if want_noise else None
+        return dw, dnoise, None
+
+
 class StyleGAN2(nn.Module):
     def __init__(self, model="cars", search="z", state_dict=None, size=None, channels=None, seed=0):
         super().__init__()
-        if search != "z":
-            raise NotImplementedError("StyleGAN2(search=%r): only the z search of the reference examples is built" % search)
+        if search not in ("z", "w+"):
+            raise ValueError("StyleGAN2(search=%r): expected 'z' or 'w+'" % search)
         self.im_res = int(size or IM_DIM[model])
         self.channels = dict(channels or CHANNELS)
         if state_dict is None:
@@ -102,6 +125,17 @@ class StyleGAN2(nn.Module):
     def _build(self):
         sd = {k: v.cuda() for k, v in self._state.items()}
         self.native = native.NativeStyleGAN2(self.im_res, self.channels, sd)
+        self.n_latent = self.native.n_latent
+        if self.search == "w+":
+            self._latent_statistics()
+
+    @torch.no_grad()
+    def _latent_statistics(self, n_mean_latent=4096):
+        """stylegan2.py:99-104: mean and (scalar) std of style(z), z ~ N(0, I), 4096 samples."""
+        z = torch.randn(n_mean_latent, 512, device="cuda")
+        w = torch.cat([native.sg2_style(self.native, z[i:i + 512]) for i in range(0, n_mean_latent, 512)])
+        self.latent_mean = w.mean(0)
+        self.latent_std = ((w - self.latent_mean).pow(2).sum() / n_mean_latent) ** 0.5
 
     def cuda(self, device=None):
         if self.native is None:
@@ -123,11 +157,22 @@ class StyleGAN2(nn.Module):
     def forward(self, z, noises=None, truncation=1.0):
         if self.native is None:
             raise RuntimeError("StyleGAN2: native sm_100a model not built (no CUDA device). There is no CPU fallback.")
+        if self.search == "w+":
+            return self.forward_w(z, noises)
         if noises is None:
             noises = self.draw_noise(z.shape[0], z.device)
         if torch.is_grad_enabled() and z.requires_grad:
             return _SG2Fn.apply(z, self, noises)
         return self.native.forward(z, noises)
+
+    def forward_w(self, z, noises, truncation=1.0):  # stylegan2.py:122-125
+        """z: latent in W [b,512] or W+ [b,n_latent,512]; noises: flat [b, sum(r*r)] (``reshape_noise`` layout).
+        ``noises=None`` draws fresh per-layer noise (the reference requires the tensor)."""
+        if noises is None:
+            noises = torch.cat([n.reshape(z.shape[0], -1) for n in self.draw_noise(z.shape[0], z.device)], 1)
+        if torch.is_grad_enabled() and (z.requires_grad or noises.requires_grad):
+            return _SG2WFn.apply(z, noises, self)
+        return native.sg2_forward_w(self.native, z, self.reshape_noise(noises))
 
     def reshape_noise(self, z):  # stylegan2.py:128-138
         st, out = 0, []

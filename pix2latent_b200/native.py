@@ -80,6 +80,11 @@ def declare(L):
         "p2l_sg2_forward": (ci, [vp, ci, vp, vp, vp, vp]),
         "p2l_sg2_backward": (ci, [vp, ci, vp, vp, vp]),
         "p2l_sg2_step": (ci, [vp, vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp]),
+        "p2l_sg2_n_latent": (ci, [vp]),
+        "p2l_sg2_style": (ci, [vp, ci, vp, vp, vp]),
+        "p2l_sg2_forward_w": (ci, [vp, ci, vp, vp, vp, vp]),
+        "p2l_sg2_backward_w": (ci, [vp, ci, vp, vp, vp, vp]),
+        "p2l_sg2_step_w": (ci, [vp, vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]),
         "p2l_profile_enable": (None, [ci]),
         "p2l_profile_read": (ci, [C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_double)]),
     }
@@ -98,6 +103,7 @@ EXPORTED_SYMBOLS = [
     "p2l_loss_backward", "p2l_lpips_flops", "p2l_lpips_launches", "p2l_biggan_step",
     "p2l_biggan_optimize", "p2l_biggan_optimize_used_graph", "p2l_adam_update",
     "p2l_affine_resample", "p2l_biggan_step_targets",
+    "p2l_sg2_n_latent", "p2l_sg2_style", "p2l_sg2_forward_w", "p2l_sg2_backward_w", "p2l_sg2_step_w",
     "p2l_profile_enable", "p2l_profile_read", "p2l_sg2_create", "p2l_sg2_set_tensor", "p2l_sg2_finalize",
     "p2l_sg2_destroy", "p2l_sg2_num_noise_layers", "p2l_sg2_forward", "p2l_sg2_backward", "p2l_sg2_step",
     "p2l_debug_conv", "p2l_debug_set_option", "p2l_debug_get_option", "p2l_debug_profile_get",
@@ -219,6 +225,7 @@ class NativeStyleGAN2:
                 _lib.check(L.p2l_sg2_set_tensor(self.h, k.encode(), C.c_void_p(t.data_ptr()), t.numel()))
             _lib.check(L.p2l_sg2_finalize(self.h))
         self.num_layers = int(L.p2l_sg2_num_noise_layers(self.h))
+        self.n_latent = int(L.p2l_sg2_n_latent(self.h))
 
     def __del__(self):
         try:
@@ -254,6 +261,60 @@ class NativeStyleGAN2:
         dz = torch.empty(b, 512, device=dimg.device, dtype=torch.float32)
         _lib.check(_lib.lib().p2l_sg2_backward(self.h, b, _lib.ptr(dimg), _lib.ptr(dz), _lib.current_stream()))
         return dz
+
+
+def _sg2_latent(gen, w):
+    """[b,512] (w) or [b,n_latent,512] (w+) -> contiguous [b,n_latent,512]."""
+    w = _f32c(w)
+    if w.dim() == 2:
+        w = w.unsqueeze(1).repeat(1, gen.n_latent, 1)
+    assert w.dim() == 3 and tuple(w.shape[1:]) == (gen.n_latent, 512), "latent must be [b,512] or [b,%d,512]" % gen.n_latent
+    return w.contiguous()
+
+
+def sg2_style(gen, z):
+    """w = style(z): the mapping network alone (stylegan2.py:99-101)."""
+    z = _f32c(z)
+    w = torch.empty_like(z)
+    _lib.check(_lib.lib().p2l_sg2_style(gen.h, z.shape[0], _lib.ptr(z), _lib.ptr(w), _lib.current_stream()))
+    return w
+
+
+def sg2_forward_w(gen, w, noises=None):
+    lat = _sg2_latent(gen, w)
+    b = lat.shape[0]
+    img = torch.empty(b, 3, gen.size, gen.size, device=lat.device, dtype=torch.float32)
+    arr, keep = gen._noise_ptrs(noises, b)
+    _lib.check(_lib.lib().p2l_sg2_forward_w(gen.h, b, _lib.ptr(lat), arr, _lib.ptr(img), _lib.current_stream()))
+    return img
+
+
+def sg2_backward_w(gen, b, dimg, want_noise_grad=True):
+    """(dlatent [b,n_latent,512], [dnoise_l [b,1,r,r]] or None) of the last sg2_forward_w with this b."""
+    dimg = _f32c(dimg)
+    dlat = torch.empty(b, gen.n_latent, 512, device=dimg.device, dtype=torch.float32)
+    dn = [torch.empty(s, device=dimg.device, dtype=torch.float32) for s in gen.noise_shapes(b)] if want_noise_grad else None
+    arr = (C.c_void_p * gen.num_layers)(*[t.data_ptr() for t in dn]) if dn is not None else None
+    _lib.check(_lib.lib().p2l_sg2_backward_w(gen.h, b, _lib.ptr(dimg), _lib.ptr(dlat), arr, _lib.current_stream()))
+    return dlat, dn
+
+
+def sg2_step_w(gen, lp, tgt, w, noises, want_grad, grad_scale, want_img=True, dloss=None, want_noise_grad=True):
+    """Fused StyleGAN2 w/w+ step: returns (loss[b], dlatent [b,n_latent,512], [dnoise_l], img)."""
+    lat = _sg2_latent(gen, w)
+    b = lat.shape[0]
+    dev = lat.device
+    loss = torch.empty(b, device=dev, dtype=torch.float32)
+    dlat = torch.empty_like(lat) if want_grad else None
+    dn = ([torch.empty(s, device=dev, dtype=torch.float32) for s in gen.noise_shapes(b)]
+          if (want_grad and want_noise_grad and noises is not None) else None)
+    darr = (C.c_void_p * gen.num_layers)(*[t.data_ptr() for t in dn]) if dn is not None else None
+    img = torch.empty(b, 3, gen.size, gen.size, device=dev, dtype=torch.float32) if want_img else None
+    arr, keep = gen._noise_ptrs(noises, b)
+    _lib.check(_lib.lib().p2l_sg2_step_w(gen.h, lp.h, tgt.h, b, _lib.ptr(lat), arr, int(want_grad), float(grad_scale),
+                                         _lib.ptr(None if dloss is None else _f32c(dloss)), _lib.ptr(loss), _lib.ptr(dlat),
+                                         darr, _lib.ptr(img), _lib.current_stream()))
+    return loss, dlat, dn, img
 
 
 def sg2_step(gen, lp, tgt, z, noises, want_grad, grad_scale, want_img=True, dloss=None):

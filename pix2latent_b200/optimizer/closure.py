@@ -161,8 +161,8 @@ def _native_sg2_pair(model, vars, loss_fn):
     from ..loss_functions import _NativeLoss
     from ..model.stylegan2 import StyleGAN2
     m = _unwrap(model)
-    if not (isinstance(m, StyleGAN2) and isinstance(loss_fn, _NativeLoss) and m.native is not None):
-        return False
+    if not (isinstance(m, StyleGAN2) and isinstance(loss_fn, _NativeLoss) and m.native is not None and m.search == "z"):
+        return False  # w / w+ search: the differentiable model / loss calls of the autograd path
     if any(k not in ("input", "output", "opt", "num_samples") for k in vars.keys()):
         return False
     if set(vars.input.keys()) != {"z"}:
