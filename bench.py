@@ -320,6 +320,25 @@ def run_native(args, rank, world, local_rank):
                 inner["graph_used"] = bool(r["graph"])
                 inner["final_loss_mean"] = float(hist[-1].mean())
                 inner["first_loss_mean"] = float(hist[0].mean())
+        # the same K steps through the product's per-step public API (closure.step: hooks in Python, one C-ABI
+        # step, torch.optim.Adam over 2n per-candidate param groups, one D2H of the losses per step)
+        from pix2latent_b200 import VariableManager
+        from pix2latent_b200.optimizer.closure import step as api_step
+        import pix2latent_b200.utils.function_hooks as hook
+        vm = VariableManager(device=dev)
+        vm.register("z", (128,), "input", learning_rate=0.05, hook_fn=hook.Clamp(2.0))
+        vm.register("c", (128,), "input", default=model.get_class_embedding(153)[0], learning_rate=0.01)
+        vm.register("target", (3, 256, 256), "output", requires_grad=False, default=target)
+        vm.register("weight", (3, 256, 256), "output", requires_grad=False, default=weight)
+        variables = vm.initialize(n)
+        for _ in range(3):
+            api_step(model, variables, loss_fn, optimize=True, max_batch_size=CHUNK)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(k_inner):
+            api_step(model, variables, loss_fn, optimize=True, max_batch_size=CHUNK)
+        sync_all()
+        inner["api_per_step"] = world * n * k_inner / (time.perf_counter() - t0)
     except Exception as e:  # the headline numbers above do not depend on this leg
         inner = {"error": "%s: %s" % (type(e).__name__, e)}
 

@@ -26,6 +26,7 @@ void add_launches(long n) { g_launches += n; }
 long launch_count() { return g_launches; }
 
 static int g_tma_out = 1, g_tma_kmax = 512;
+static int g_deep = 0, g_deep_kmin = 8;  // "deep": full-depth single-CTA pipeline for launches with <= #SM tiles and >= deep_kmin K blocks
 static int g_grad_scale = (int)kGradScale;
 float grad_scale() { return (float)g_grad_scale; }
 // halo patches for 3x3 convs: "halo" = patch pitch in pixels (10 | 16), "halo_mode" = 0 off, 1 only where the
@@ -41,6 +42,8 @@ void set_option(const char* key, int value) {
     else if (!std::strcmp(key, "halo_rgb")) g_halo_rgb = value;
     else if (!std::strcmp(key, "tma_out")) g_tma_out = value;
     else if (!std::strcmp(key, "tma_kmax")) g_tma_kmax = value;
+    else if (!std::strcmp(key, "deep")) g_deep = value;
+    else if (!std::strcmp(key, "deep_kmin")) g_deep_kmin = value;
 }
 int get_option(const char* key) {
     if (!std::strcmp(key, "halo")) return g_halo;
@@ -49,6 +52,8 @@ int get_option(const char* key) {
     if (!std::strcmp(key, "halo_mode")) return g_halo_mode;
     if (!std::strcmp(key, "tma_out")) return g_tma_out;
     if (!std::strcmp(key, "tma_kmax")) return g_tma_kmax;
+    if (!std::strcmp(key, "deep")) return g_deep;
+    if (!std::strcmp(key, "deep_kmin")) return g_deep_kmin;
     return -1;
 }
 
@@ -273,19 +278,21 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     op->mode = d.mode;
     op->halo = halo ? halo_p : 0;
     const long total = (long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
-    const long slots = (long)num_sms() * ((halo || d.BN > 128 || op->tma_out) ? 1 : P2L_OCC);
+    op->deep = (g_deep && !halo && !op->tma_out && (d.BN == 64 || d.BN == 128) && total <= num_sms() &&
+                (long)d.kh * d.kw * p.cin_chunks >= g_deep_kmin) ? 1 : 0;
+    const long slots = (long)num_sms() * ((halo || d.BN > 128 || op->tma_out || op->deep) ? 1 : P2L_OCC);
     op->grid = (int)(total < slots ? total : slots);
     op->flops = 2.0 * d.NI * d.H * d.W * (double)d.Cout * d.kh * d.kw * d.Cin;
     return 0;
 }
 
 // ----------------------------------------------------------------------------- launch
-template <int BN, int MODE, bool TMA_OUT>
+template <int BN, int MODE, bool TMA_OUT, bool DEEP = false>
 static int launch_t(const ConvOp& op, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, TMA_OUT>;
+    using Cfg = GemmCfg<BN, TMA_OUT, DEEP>;
     static bool attr_set = false;
     if (!attr_set) {
-        P2L_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE, TMA_OUT>,
+        P2L_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE, TMA_OUT, DEEP>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
@@ -304,7 +311,7 @@ static int launch_t(const ConvOp& op, cudaStream_t stream) {
                                op.p.taps_h * op.p.taps_w * op.p.cin_chunks * kBK});
         cudaEventRecord(e0, stream);
     }
-    conv_gemm_kernel<BN, MODE, TMA_OUT><<<op.grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(op.tmA, op.tmB, op.tmO, op.p);
+    conv_gemm_kernel<BN, MODE, TMA_OUT, DEEP><<<op.grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(op.tmA, op.tmB, op.tmO, op.p);
     if (g_prof) cudaEventRecord(e1, stream);
     count_launch();
     P2L_CUDA_CHECK(cudaGetLastError());
@@ -357,6 +364,10 @@ int conv_op_launch(const ConvOp& op, cudaStream_t stream) {
     if (op.tma_out) {
         if (op.BN == 64) return op.mode == EPI_FWD ? launch_t<64, EPI_FWD, true>(op, stream) : launch_t<64, EPI_BWD, true>(op, stream);
         if (op.BN == 128) return op.mode == EPI_FWD ? launch_t<128, EPI_FWD, true>(op, stream) : launch_t<128, EPI_BWD, true>(op, stream);
+    }
+    if (op.deep) {
+        if (op.BN == 64) return op.mode == EPI_FWD ? launch_t<64, EPI_FWD, false, true>(op, stream) : launch_t<64, EPI_BWD, false, true>(op, stream);
+        if (op.BN == 128) return op.mode == EPI_FWD ? launch_t<128, EPI_FWD, false, true>(op, stream) : launch_t<128, EPI_BWD, false, true>(op, stream);
     }
 #define P2L_DISPATCH(bn)                                                          \
     case bn:                                                                      \

@@ -88,7 +88,10 @@ struct ConvGemmParams {
     int dx_f32_C;
 };
 
-template <int BN, bool TMA_OUT = false>
+// DEEP: one CTA per SM with the full shared memory as pipeline (8 x 24 KB stages for BN = 64): for launches with
+// fewer tiles than SMs and a long K loop (the 4x4 .. 16x16 generator blocks: 24-144 tiles, K up to 4608), where
+// the main loop is bound by the bytes ONE CTA keeps in flight, not by the tensor pipe.
+template <int BN, bool TMA_OUT = false, bool DEEP = false>
 struct GemmCfg {
     static constexpr int kBTileBytes = BN * kBK * 2;
     static constexpr int kStageBytes = kATileBytes + kBTileBytes;
@@ -103,7 +106,7 @@ struct GemmCfg {
     // cp.async.bulk.tensor stores; the per-pixel epilogue inputs (saved activation, residual skip,
     // skip gradient) are prefetched by TMA into a ring of kInSlots slabs shared by both groups, so
     // no thread ever waits on a global load.
-    static constexpr int kOcc = TMA_OUT ? 1 : ((BN <= 128) ? P2L_OCC : 1);
+    static constexpr int kOcc = (TMA_OUT || DEEP) ? 1 : ((BN <= 128) ? P2L_OCC : 1);
     static constexpr int kInSlots = TMA_OUT ? 4 : 0;
     static constexpr int kOutBytes = TMA_OUT ? (4 + kInSlots) * kATileBytes : 0;  // 2 x {raw, act} + inputs
     static constexpr int kEpiGroups = (TMA_OUT || kOcc == 1) ? 2 : 1;  // one CTA per SM: two groups drain the two TMEM stages
@@ -587,11 +590,11 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 
 struct OutMaps { CUtensorMap m[6]; };  // [0..3] epilogue outputs, [4..5] epilogue inputs
 
-template <int BN, int MODE, bool TMA_OUT>
-__global__ void __launch_bounds__(GemmCfg<BN, TMA_OUT>::kThreads, GemmCfg<BN, TMA_OUT>::kOcc)
+template <int BN, int MODE, bool TMA_OUT, bool DEEP = false>
+__global__ void __launch_bounds__(GemmCfg<BN, TMA_OUT, DEEP>::kThreads, GemmCfg<BN, TMA_OUT, DEEP>::kOcc)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ OutMaps tmO, const ConvGemmParams p) {
-    using Cfg = GemmCfg<BN, TMA_OUT>;
+    using Cfg = GemmCfg<BN, TMA_OUT, DEEP>;
     constexpr int S = Cfg::kStages;
     constexpr int CH = (BN >= 32) ? 32 : 16;  // epilogue column chunk
 

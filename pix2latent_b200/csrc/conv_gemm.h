@@ -31,6 +31,7 @@ struct ConvOp {
     int tma_out;  // epilogue outputs through TMA bulk stores
     ConvGemmParams p;
     int BN, mode, grid;
+    int deep;  // one CTA per SM, full-depth pipeline (few tiles, long K)
     int halo;  // 0: per-tap A loads; 10 / 16: halo-patch kernel with that patch row pitch
     int halo_smem;  // dynamic shared memory of the halo kernel for this plan
     double flops;  // algorithmic 2*M*N*K of this launch
