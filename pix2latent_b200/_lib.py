@@ -26,6 +26,11 @@ def lib():
                 "(or __graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
         _lib = C.CDLL(LIB_PATH)
         _declare(_lib)
+        # experiment switches from the environment, e.g. P2L_OPTS="pdl=1,deep=1" (see conv_gemm.h set_option)
+        for kv in os.environ.get("P2L_OPTS", "").split(","):
+            if "=" in kv:
+                k, v = kv.split("=", 1)
+                _lib.p2l_debug_set_option(k.strip().encode(), int(v))
     return _lib
 
 

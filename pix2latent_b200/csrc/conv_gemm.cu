@@ -26,7 +26,8 @@ void add_launches(long n) { g_launches += n; }
 long launch_count() { return g_launches; }
 
 static int g_tma_out = 1, g_tma_kmax = 512;
-static int g_deep = 0, g_deep_kmin = 8;  // "deep": full-depth single-CTA pipeline for launches with <= #SM tiles and >= deep_kmin K blocks
+static int g_pdl = 1;  // "pdl": launch the tensor-core kernel with programmatic stream serialization (prologue overlaps the previous kernel's tail)
+static int g_deep = 1, g_deep_kmin = 8;  // "deep": full-depth single-CTA pipeline for launches with <= #SM tiles and >= deep_kmin K blocks
 static int g_grad_scale = (int)kGradScale;
 float grad_scale() { return (float)g_grad_scale; }
 // halo patches for 3x3 convs: "halo" = patch pitch in pixels (10 | 16), "halo_mode" = 0 off, 1 only where the
@@ -42,6 +43,7 @@ void set_option(const char* key, int value) {
     else if (!std::strcmp(key, "halo_rgb")) g_halo_rgb = value;
     else if (!std::strcmp(key, "tma_out")) g_tma_out = value;
     else if (!std::strcmp(key, "tma_kmax")) g_tma_kmax = value;
+    else if (!std::strcmp(key, "pdl")) g_pdl = value;
     else if (!std::strcmp(key, "deep")) g_deep = value;
     else if (!std::strcmp(key, "deep_kmin")) g_deep_kmin = value;
 }
@@ -52,6 +54,7 @@ int get_option(const char* key) {
     if (!std::strcmp(key, "halo_mode")) return g_halo_mode;
     if (!std::strcmp(key, "tma_out")) return g_tma_out;
     if (!std::strcmp(key, "tma_kmax")) return g_tma_kmax;
+    if (!std::strcmp(key, "pdl")) return g_pdl;
     if (!std::strcmp(key, "deep")) return g_deep;
     if (!std::strcmp(key, "deep_kmin")) return g_deep_kmin;
     return -1;
@@ -311,7 +314,19 @@ static int launch_t(const ConvOp& op, cudaStream_t stream) {
                                op.p.taps_h * op.p.taps_w * op.p.cin_chunks * kBK});
         cudaEventRecord(e0, stream);
     }
-    conv_gemm_kernel<BN, MODE, TMA_OUT, DEEP><<<op.grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(op.tmA, op.tmB, op.tmO, op.p);
+    {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(op.grid);
+        lc.blockDim = dim3(Cfg::kThreads);
+        lc.dynamicSmemBytes = Cfg::kSmemBytes;
+        lc.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = g_pdl ? 1 : 0;
+        P2L_CUDA_CHECK(cudaLaunchKernelEx(&lc, conv_gemm_kernel<BN, MODE, TMA_OUT, DEEP>, op.tmA, op.tmB, op.tmO, op.p));
+    }
     if (g_prof) cudaEventRecord(e1, stream);
     count_launch();
     P2L_CUDA_CHECK(cudaGetLastError());

@@ -637,6 +637,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch ("pdl" option): everything above (barrier init, TMEM allocation, descriptor
+    // prefetch) touches no global memory and may overlap the tail of the previous kernel in the stream; from here
+    // on the previous grid's writes are needed. No-ops when the launch carries no PDL attribute.
+    grid_dep_wait();
+    grid_dep_launch_dependents();
 
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     const int total_tiles = m_tiles * p.n_tiles;

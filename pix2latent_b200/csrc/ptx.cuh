@@ -243,4 +243,9 @@ __device__ __forceinline__ float bf16_lo(uint32_t u) { return act_lo(u); }  // (
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return act_hi(u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) { return pack_act(a, b); }
 
+// ---- programmatic dependent launch (griddepcontrol): wait for the prerequisite grid's completion + memory flush /
+// allow the dependent grid to start launching
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace p2l
