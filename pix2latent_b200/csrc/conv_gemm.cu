@@ -34,7 +34,7 @@ float grad_scale() { return (float)g_grad_scale; }
 // weight matrix stays resident in shared memory (the 64-channel layers, L2-bandwidth-bound otherwise), 2 every
 // eligible 3x3 conv
 static int g_halo_rgb = 0;
-static int g_halo = 10, g_halo_mode = 0, g_halo_bo = 0;  // measured: the per-tap path with 2 CTAs/SM is faster at every BigGAN shape (profiles/)
+static int g_halo = 10, g_halo_mode = 1, g_halo_bo = 0;  // mode 1: the 64-channel 3x3 layers (weights resident in shared memory) run on the halo-patch kernel: 121 -> 102 us at 256^2 (profiles/r1k)
 void set_option(const char* key, int value) {
     if (!std::strcmp(key, "halo")) g_halo = value;
     else if (!std::strcmp(key, "grad_scale")) g_grad_scale = value > 0 ? value : 1;

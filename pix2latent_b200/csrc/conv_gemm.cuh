@@ -235,7 +235,9 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
     // obuf = [2 output slabs][kInSlots input slabs]; input slabs arrive through in_full / in_empty
     constexpr int NIN = GemmCfg<BN, TMA_OUT>::kInSlots;
     const int grp = (NG == 2) ? ((warp - 2) >> 2) : 0;  // epilogue group = TMEM accumulator stage it drains
-    const bool storer = TMA_OUT && ((warp - 2) & 3) == 0 && lane == 0;
+    // the group's first warp issues the bulk stores: under elect.sync (deterministic leader, so the same thread
+    // commits and waits on the bulk groups), never from `if (lane == 0)` (see conv_gemm_kernel)
+    const bool store_warp = TMA_OUT && ((warp - 2) & 3) == 0;
     uint8_t* inbuf = nullptr;
     constexpr int RING = (NIN >= NG) ? NIN / NG : 1;
     if constexpr (TMA_OUT) {
@@ -303,9 +305,12 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     // both output slabs are about to be overwritten: their previous stores must have
                     // finished READING shared memory
                     // the pair written two slabs ago must have been READ by its bulk stores
-                    if (storer) {
-                        if (single_out) bulk_wait_read1();
-                        else bulk_wait_read0();
+                    if (store_warp) {
+                        if (elect_one()) {
+                            if (single_out) bulk_wait_read1();
+                            else bulk_wait_read0();
+                        }
+                        __syncwarp();
                     }
                     s_raw = single_out ? obuf + (slab_no & 1) * kATileBytes : obuf;
                     s_act = single_out ? s_raw : obuf + kATileBytes;
@@ -557,7 +562,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     }
                     fence_async_smem();
                     bar_epilogue(grp);
-                    if (storer) {
+                    if (store_warp && elect_one()) {
                         const int cs = n_tile * BN + (c & ~63);
                         const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.nb;
                         if constexpr (MODE == EPI_FWD) {
@@ -585,7 +590,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
-    if (storer) bulk_wait0();  // shared memory must outlive the last bulk store's reads
+    if (store_warp && elect_one()) bulk_wait0();  // shared memory must outlive the last bulk store's reads
 }
 
 struct OutMaps { CUtensorMap m[6]; };  // [0..3] epilogue outputs, [4..5] epilogue inputs
@@ -648,33 +653,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int k_blocks = p.taps_h * p.taps_w * p.cin_chunks;
     const int Cin = p.cin_chunks * kBK;
 
+    // The producer and MMA warps run their loops CONVERGED (all 32 lanes wait on the barriers and keep the loop
+    // state); only the asynchronous-instruction issue itself sits under elect.sync. Issuing from `if (lane == 0)`
+    // makes the compiler wrap every uniform-datapath instruction (UTCHMMA / UTMALDG / UTCBAR) in an
+    // ELECT + BRA.U.ANY "waterfall" loop — measured (ncu source page, profiles/r1i): the MMA warp then spends ~75 %
+    // of its time in issue overhead, ~160-195 cycles per MMA instruction.
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-                const int twi = m_tile % p.tiles_w;
-                const int thi = (m_tile / p.tiles_w) % p.tiles_h;
-                const int tni = m_tile / (p.tiles_w * p.tiles_h);
-                const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.nb;
-                for (int r = 0; r < p.taps_h; ++r) {
-                    for (int s = 0; s < p.taps_w; ++s) {
-                        const int kbase = (r * p.taps_w + s) * Cin;
-                        for (int cc = 0; cc < p.cin_chunks; ++cc) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
-                            uint8_t* sA = smem + stage * Cfg::kStageBytes;
-                            uint8_t* sB = sA + kATileBytes;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+            const int twi = m_tile % p.tiles_w;
+            const int thi = (m_tile / p.tiles_w) % p.tiles_h;
+            const int tni = m_tile / (p.tiles_w * p.tiles_h);
+            const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.nb;
+            for (int r = 0; r < p.taps_h; ++r) {
+                for (int s = 0; s < p.taps_w; ++s) {
+                    const int kbase = (r * p.taps_w + s) * Cin;
+                    for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sA = smem + stage * Cfg::kStageBytes;
+                        uint8_t* sB = sA + kATileBytes;
+                        if (elect_one()) {
                             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                             tma_load_4d(sA, &tmA, &full_bar[stage], p.a_c0 + cc * kBK,
                                         w0 + s - p.pad_w, h0 + r - p.pad_h, n0);
                             tma_load_3d(sB, &tmB, &full_bar[stage], kbase + cc * kBK, n_tile * BN,
                                         p.b_batched ? n0 : 0);
-                            if (++stage == S) {
-                                stage = 0;
-                                phase ^= 1;
-                            }
+                        }
+                        __syncwarp();
+                        if (++stage == S) {
+                            stage = 0;
+                            phase ^= 1;
                         }
                     }
                 }
@@ -682,71 +693,77 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[as], aphase ^ 1);
+        constexpr uint32_t idesc = umma_idesc_bf16(BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BN;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint64_t adesc = umma_desc_k128(sA);
-                    const uint64_t bdesc = umma_desc_k128(sA + kATileBytes);
+                const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
+                const uint64_t adesc = umma_desc_k128(sA);
+                const uint64_t bdesc = umma_desc_k128(sA + kATileBytes);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
                         // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in 16-B units
                         umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty_bar[stage]);
-                    if (++stage == S) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
                 }
-                umma_commit(&tfull_bar[as]);
+                __syncwarp();
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
+            if (elect_one()) umma_commit(&tfull_bar[as]);
+            __syncwarp();
         }
     } else if (warp >= 2 + 4 * Cfg::kEpiGroups) {
         // ------------------------------------------------------------------ epilogue-input loaders (one warp per group:
         // a single in-order loader would stall group 1's ring behind group 0's full one)
         if constexpr (TMA_OUT) {
-            if (lane == 0) {
-                uint8_t* inbuf = obuf + 4 * kATileBytes;
-                const bool has0 = (MODE == EPI_FWD) ? (p.resid != nullptr) : (p.saved != nullptr);
-                const int sh = (MODE == EPI_FWD) ? p.resid_shift : 0;
-                const uint32_t bytes0 = kATileBytes >> (2 * sh);
-                constexpr int RING = NIN / Cfg::kEpiGroups;  // one ring per epilogue group
-                const int g = warp - (2 + 4 * Cfg::kEpiGroups);
-                int cnt = 0;
-                for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += Cfg::kEpiGroups * gridDim.x) {
-                    const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-                    const int w0 = (m_tile % p.tiles_w) * p.tw;
-                    const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
-                    const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
-                    for (int c = 0; c < BN; c += 64) {
-                        const int cs = n_tile * BN + c;
-                        if (cs >= p.Cout) break;
-                        if (has0) {
-                            const int slot = g * RING + cnt % RING;
-                            mbar_wait(&in_empty[slot], ((cnt / RING) & 1) ^ 1);
+            uint8_t* inbuf = obuf + 4 * kATileBytes;
+            const bool has0 = (MODE == EPI_FWD) ? (p.resid != nullptr) : (p.saved != nullptr);
+            const int sh = (MODE == EPI_FWD) ? p.resid_shift : 0;
+            const uint32_t bytes0 = kATileBytes >> (2 * sh);
+            constexpr int RING = NIN / Cfg::kEpiGroups;  // one ring per epilogue group
+            const int g = warp - (2 + 4 * Cfg::kEpiGroups);
+            int cnt = 0;
+            for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += Cfg::kEpiGroups * gridDim.x) {
+                const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+                const int w0 = (m_tile % p.tiles_w) * p.tw;
+                const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+                const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
+                for (int c = 0; c < BN; c += 64) {
+                    const int cs = n_tile * BN + c;
+                    if (cs >= p.Cout) break;
+                    if (has0) {
+                        const int slot = g * RING + cnt % RING;
+                        mbar_wait(&in_empty[slot], ((cnt / RING) & 1) ^ 1);
+                        if (elect_one()) {
                             mbar_expect_tx(&in_full[slot], bytes0);
                             tma_load_4d(inbuf + slot * kATileBytes, &tmO.m[4], &in_full[slot], cs, w0 >> sh, h0 >> sh, n0);
-                            ++cnt;
                         }
-                        if (MODE == EPI_BWD && p.addin != nullptr && cs < p.addin_climit) {
-                            const int slot = g * RING + cnt % RING;
-                            mbar_wait(&in_empty[slot], ((cnt / RING) & 1) ^ 1);
+                        __syncwarp();
+                        ++cnt;
+                    }
+                    if (MODE == EPI_BWD && p.addin != nullptr && cs < p.addin_climit) {
+                        const int slot = g * RING + cnt % RING;
+                        mbar_wait(&in_empty[slot], ((cnt / RING) & 1) ^ 1);
+                        if (elect_one()) {
                             mbar_expect_tx(&in_full[slot], kATileBytes);
                             tma_load_4d(inbuf + slot * kATileBytes, &tmO.m[5], &in_full[slot], cs, w0, h0, n0);
-                            ++cnt;
                         }
+                        __syncwarp();
+                        ++cnt;
                     }
                 }
             }
@@ -832,81 +849,102 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int total_tiles = m_tiles * p.n_tiles;
     const int Cin = p.cin_chunks * kBK;
 
+    // producer / MMA warps converged, issue under elect.sync (see conv_gemm_kernel)
     if (warp == 0) {
-        if (lane == 0) {
-            int sa = 0, sb = 0;
-            uint32_t pa = 0, pb = 0;
-            if (resb && static_cast<int>(blockIdx.x) < total_tiles) {
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        if (resb && static_cast<int>(blockIdx.x) < total_tiles) {
+            if (elect_one()) {
                 mbar_expect_tx(&bfull[0], nB * Cfg::kBTileBytes);
                 for (int tap = 0; tap < 9; ++tap)
                     for (int cc = 0; cc < p.cin_chunks; ++cc)
                         tma_load_3d(smemB + (tap * p.cin_chunks + cc) * Cfg::kBTileBytes, &tmB, &bfull[0], tap * Cin + cc * kBK, 0, 0);
             }
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-                const int w0 = (m_tile % p.tiles_w) * Cfg::kTw;
-                const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * Cfg::kTh;
-                const int n0 = m_tile / (p.tiles_w * p.tiles_h);
-                for (int cc = 0; cc < p.cin_chunks; ++cc) {
-                    mbar_wait(&aempty[sa], pa ^ 1);
+            __syncwarp();
+        }
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+            const int w0 = (m_tile % p.tiles_w) * Cfg::kTw;
+            const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * Cfg::kTh;
+            const int n0 = m_tile / (p.tiles_w * p.tiles_h);
+            for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                mbar_wait(&aempty[sa], pa ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&afull[sa], Cfg::kPatchTx);
                     tma_load_4d(smem + sa * Cfg::kPatchBytes, &tmA, &afull[sa], p.a_c0 + cc * kBK, w0 - 1, h0 - 1, n0);
-                    if (++sa == SA) { sa = 0; pa ^= 1; }
-                    if (resb) continue;
-                    for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(&bempty[sb], pb ^ 1);
+                }
+                __syncwarp();
+                if (++sa == SA) { sa = 0; pa ^= 1; }
+                if (resb) continue;
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(&bempty[sb], pb ^ 1);
+                    if (elect_one()) {
                         mbar_expect_tx(&bfull[sb], Cfg::kBTileBytes);
                         tma_load_3d(smemB + sb * Cfg::kBTileBytes, &tmB, &bfull[sb], tap * Cin + cc * kBK, n_tile * BN, 0);
-                        if (++sb == SB) { sb = 0; pb ^= 1; }
                     }
+                    __syncwarp();
+                    if (++sb == SB) { sb = 0; pb ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BN);
-            int sa = 0, sb = 0;
-            uint32_t pa = 0, pb = 0;
-            int it = 0;
-            if (resb && static_cast<int>(blockIdx.x) < total_tiles) mbar_wait(&bfull[0], 0);
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[as], aphase ^ 1);
+        constexpr uint32_t idesc = umma_idesc_bf16(BN);
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        int it = 0;
+        if (resb && static_cast<int>(blockIdx.x) < total_tiles) mbar_wait(&bfull[0], 0);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BN;
+            for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                mbar_wait(&afull[sa], pa);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int cc = 0; cc < p.cin_chunks; ++cc) {
-                    mbar_wait(&afull[sa], pa);
-                    tc_fence_after();
-                    const uint32_t a_base = smem_u32(smem + sa * Cfg::kPatchBytes);
+                const uint32_t a_base = smem_u32(smem + sa * Cfg::kPatchBytes);
+                if (resb) {
+                    // weights resident: the nine taps of this channel chunk are 36 back-to-back MMAs
+                    if (elect_one()) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t b_addr = smem_u32(smemB + (tap * p.cin_chunks + cc) * Cfg::kBTileBytes);
+                            const uint32_t a_addr = a_base + ((tap / 3) * P + (tap % 3)) * 128;
+                            const uint64_t adesc = umma_desc_sw128(a_addr, P * 128, p.halo_bo ? (a_addr >> 7) : 0);
+                            const uint64_t bdesc = umma_desc_k128(b_addr);
+#pragma unroll
+                            for (int k = 0; k < kBK / 16; ++k)
+                                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cc | tap | k) != 0);
+                        }
+                        umma_commit(&aempty[sa]);
+                    }
+                    __syncwarp();
+                } else {
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
-                        uint32_t b_addr;
-                        if (resb) {
-                            b_addr = smem_u32(smemB + (tap * p.cin_chunks + cc) * Cfg::kBTileBytes);
-                        } else {
-                            mbar_wait(&bfull[sb], pb);
-                            tc_fence_after();
-                            b_addr = smem_u32(smemB + sb * Cfg::kBTileBytes);
-                        }
+                        mbar_wait(&bfull[sb], pb);
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(smemB + sb * Cfg::kBTileBytes);
                         const int r = tap / 3, s = tap - 3 * r;
                         const uint32_t a_addr = a_base + (r * P + s) * 128;
                         const uint64_t adesc = umma_desc_sw128(a_addr, P * 128, p.halo_bo ? (a_addr >> 7) : 0);
                         const uint64_t bdesc = umma_desc_k128(b_addr);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < kBK / 16; ++k) {
-                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cc | tap | k) != 0);
-                        }
-                        if (!resb) {
+                            for (int k = 0; k < kBK / 16; ++k)
+                                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cc | tap | k) != 0);
                             umma_commit(&bempty[sb]);
-                            if (++sb == SB) { sb = 0; pb ^= 1; }
                         }
+                        __syncwarp();
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
                     }
-                    umma_commit(&aempty[sa]);
-                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                    if (elect_one()) umma_commit(&aempty[sa]);
+                    __syncwarp();
                 }
-                umma_commit(&tfull_bar[as]);
+                if (++sa == SA) { sa = 0; pa ^= 1; }
             }
+            if (elect_one()) umma_commit(&tfull_bar[as]);
+            __syncwarp();
         }
     } else {
         epilogue_loop_direct<BN, MODE, CH, false, 2>(p, nullptr, nullptr, nullptr, nullptr, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane,
