@@ -59,8 +59,10 @@ def traffic(path, out):
     print(res)
 
 
-def rep(path, out):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def rep(path, out, index=None):
+    """index: which kernel of a multi-kernel report (default: the last one)"""
+    sel = [] if index is None else ["--launch-skip", str(index), "--launch-count", "1"]
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[-1]
     want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -68,13 +70,22 @@ def rep(path, out):
             "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "smsp__inst_executed.sum", "sm__inst_executed_pipe_uniform.sum"]
-    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
     srows = list(csv.reader(src.splitlines()))
     shdr, sdata = srows[1], srows[2:]
     ix = {h: i for i, h in enumerate(shdr)}
+    # a report with imported sources repeats the header per view: keep the SASS rows of the first view only
+    keep = []
+    for r in sdata:
+        if len(r) <= ix["# Samples"] or not r[ix["# Samples"]].strip().isdigit():
+            if keep:
+                break
+            continue
+        keep.append(r)
+    sdata = keep
     stalls = [h for h in shdr if h.startswith("stall_") and "Not Issued" not in h]
     agg = {s: sum(int(r[ix[s]] or 0) for r in sdata if len(r) > ix[s]) for s in stalls}
-    mn = {"UTCHMMA": 0, "UTMALDG": 0, "UTMASTG": 0, "LDTM": 0, "SYNCS": 0}
+    mn = {"UTCHMMA": 0, "UTMALDG": 0, "UTMASTG": 0, "LDTM": 0, "SYNCS": 0, "ELECT": 0, "BRA.U.ANY": 0}
     for r in sdata:
         for k in mn:
             if k in r[ix["Source"]]:
@@ -97,4 +108,4 @@ def rep(path, out):
 if __name__ == "__main__":
     {"launches": lambda: launches(sys.argv[2], int(sys.argv[3]), sys.argv[4]),
      "traffic": lambda: traffic(sys.argv[2], sys.argv[3]),
-     "rep": lambda: rep(sys.argv[2], sys.argv[3])}[sys.argv[1]]()
+     "rep": lambda: rep(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else None)}[sys.argv[1]]()
