@@ -12,10 +12,43 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(HERE, "golden"))
 
 
+def fused_toy(out_path, fused):
+    """BasinCMA on the toy problem of tests/test_fused_host_cpu.py with the native calls replaced by their CPU
+    stand-ins (device-resident loop -> oracle/inner_loop.py, per-step native path -> the autograd path)."""
+    sys.path.insert(0, HERE)
+    import test_fused_host_cpu as T
+    from _pytest.monkeypatch import MonkeyPatch
+    from pix2latent_b200.optimizer import BasinCMAOptimizer, closure
+    from pix2latent_b200.utils import function_hooks as hk
+    mp = MonkeyPatch()
+    model, loss_fn = T.ToyModel(), T.ToyLoss()
+    T._patch(mp, model, loss_fn)
+    mp.setattr(closure, "_step_native", closure._step_autograd)
+    vm = T._make(0, hk.Clamp(0.6))
+    vm.edit_variable("z", {"grad_free": True})
+    opt = BasinCMAOptimizer(model, vm, loss_fn, max_batch_size=3)
+    opt.cma_seed = 5
+    opt.fuse_inner_loop = fused
+    variables, outs, loss = opt.optimize(meta_steps=2, grad_steps=3, last_grad_steps=4)
+    res = dict(loss=np.array(loss[0][1]["loss"], dtype=np.float64), z=torch.stack(variables.input.z.data).detach().numpy(),
+               c=torch.stack(variables.input.c.data).detach().numpy(), fused_calls=np.array(opt.fused_calls),
+               n=np.array(opt.num_samples), tracked=torch.stack(opt.tracked["z"]).numpy(),
+               mean=np.array(list(opt.cma_optimizers.values())[0].mean()))
+    mp.undo()
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        np.savez(out_path, **res)
+    return res
+
+
 def main():
     out_path = sys.argv[1]
     dist.init_process_group("gloo")
     torch.set_num_threads(4)
+    if len(sys.argv) > 2 and sys.argv[2] == "fused":
+        fused_toy(out_path, True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     import make_golden as mg
     from oracle import lpips as olp
     from pix2latent_b200 import VariableManager

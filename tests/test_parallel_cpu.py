@@ -32,3 +32,27 @@ def test_basincma_two_ranks_equals_reference(tmp_path):
     # the CPU convolutions; Adam's normalised first updates amplify that to ~1e-3 on a few elements
     np.testing.assert_allclose(res["z"], GOLD["basin_z"], rtol=1e-2, atol=5e-3)
     np.testing.assert_allclose(res["mean"], GOLD["basin_cma_mean"], rtol=1e-2, atol=5e-3)
+
+
+def test_fused_inner_loop_two_ranks_equals_single_process(tmp_path):
+    """The device-resident inner loop under candidate sharding (each rank runs its shard's K steps in one call,
+    tracked inputs are assembled for the whole population, final latents / losses are gathered) against the
+    unsharded per-step run; native calls replaced by their CPU stand-ins (see _dist_worker.fused_toy)."""
+    import _dist_worker as W
+    ref = W.fused_toy(str(tmp_path / "ref.npz"), False)
+    assert int(ref["fused_calls"]) == 0 and int(ref["n"]) == 9  # CMA population for 6 dimensions
+    out = str(tmp_path / "fused.npz")
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29617", os.path.join(HERE, "_dist_worker.py"), out, "fused"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = np.load(out)
+    assert int(res["fused_calls"]) == 3
+    np.testing.assert_allclose(res["loss"], ref["loss"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(res["z"], ref["z"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(res["c"], ref["c"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(res["mean"], ref["mean"], rtol=1e-4, atol=2e-5)
+    # rank 0's tracked history: its own shard (rows 0..4) live, the other shard as of the last gather
+    assert res["tracked"].shape == ref["tracked"].shape
+    np.testing.assert_allclose(res["tracked"][:, :5], ref["tracked"][:, :5], rtol=1e-4, atol=2e-5)
