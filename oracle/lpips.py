@@ -5,11 +5,13 @@ pix2latent/loss_functions.py:131,142 and of the reference's loss algebra
 ``lpips>=0.1`` (requirements.txt:15) is a third-party package absent from /root/reference and this
 image; its published algorithm (lpips/lpips.py: LPIPS, ScalingLayer, NetLinLayer,
 normalize_tensor, upsample; lpips/pretrained_networks.py: alexnet / vgg16 slices) is restated
-here — SURVEY.md Appendix A.2. PARITY UNPINNED for that third-party arithmetic. The backbone layer
-structure is taken from the installed torchvision (alexnet/vgg16 ``features`` indices), which is
-what the real package wraps. The loss classes below it are checked against the real reference
-code (tests/golden/make_golden.py imports /root/reference with this module standing in for
-``lpips``).
+here — SURVEY.md Appendix A.2.
+PINNED (partially): the backbones — where the FLOPs are — are checked against the INSTALLED
+torchvision ``alexnet().features`` / ``vgg16().features`` on the same weights at the tap indices the real
+package uses (tests/test_oracle_backbones_cpu.py); the loss classes below are checked against the real
+reference code (tests/golden/make_golden.py imports /root/reference with this module standing in for
+``lpips``). PARITY UNPINNED for the small algebra in between, restated from the package's published
+source: ScalingLayer constants, unit-normalisation eps, the 1x1 ``lin`` layers, the bilinear up-sampling.
 """
 import torch
 import torch.nn as nn
