@@ -47,6 +47,13 @@ typedef struct p2l_conv_args {
     int dx_C;
     float* dx_f32;
     int dx_f32_C;
+    /* forward epilogue, row-wise softmax fusions (need a -DP2L_ROWFUSE=1 build) */
+    float* rowstat;
+    const float* rowstat_in;
+    int rowstat_nt;
+    const float* rowsub;
+    const void* mulin;
+    int mulin_C;
 } p2l_conv_args;
 
 /* returns 0 on success, <0 on error (see p2l_last_error) */

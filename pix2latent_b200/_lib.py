@@ -64,6 +64,8 @@ class ConvArgs(C.Structure):
         ("addin_pool", C.c_int),
         ("dx", C.c_void_p), ("dx_C", C.c_int),
         ("dx_f32", C.c_void_p), ("dx_f32_C", C.c_int),
+        ("rowstat", C.c_void_p), ("rowstat_in", C.c_void_p), ("rowstat_nt", C.c_int),
+        ("rowsub", C.c_void_p), ("mulin", C.c_void_p), ("mulin_C", C.c_int),
     ]
 
 

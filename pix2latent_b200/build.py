@@ -53,14 +53,25 @@ def _compile(src, force, hdr_m):
     return obj, True
 
 
-def build(force=False, verbose=True):
+def build(force=False, verbose=True, rowfuse=False):
+    """rowfuse: compile the prepared (not yet GPU-validated) row-wise softmax fusions in (-DP2L_ROWFUSE=1)"""
+    if rowfuse and "-DP2L_ROWFUSE=1" not in FLAGS:
+        FLAGS.append("-DP2L_ROWFUSE=1")
+        force = True
     os.makedirs(OBJ, exist_ok=True)
+    # objects built with other flags (e.g. a --rowfuse build) are stale whatever their timestamps say
+    stamp = os.path.join(OBJ, "flags.txt")
+    sig = " ".join(FLAGS)
+    if not os.path.exists(stamp) or open(stamp).read() != sig:
+        force = True
     hdr_m = _headers_mtime()
     srcs = _sources()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         res = list(ex.map(lambda s: _compile(s, force, hdr_m), srcs))
     objs = [o for o, _ in res]
     rebuilt = any(c for _, c in res)
+    with open(stamp, "w") as f:
+        f.write(sig)
     if rebuilt or not os.path.exists(LIB):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                      "-cudart", "static"]
@@ -75,4 +86,4 @@ def build(force=False, verbose=True):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    build(force="--force" in sys.argv, rowfuse="--rowfuse" in sys.argv)

@@ -35,6 +35,10 @@ struct BigGANPlan {
     act_t *dO = nullptr, *dOT = nullptr, *dS = nullptr, *dST = nullptr, *PT = nullptr, *thetaT = nullptr,
                   *dqkv = nullptr, *dphi_p = nullptr, *dg_p = nullptr;
     ConvOp a_qkv, a_s, a_o, a_out, ad_out, ad_p, ad_theta, ad_phi, ad_g, ad_qkv;
+    // "attn_fused" (prepared, unvalidated): two-pass softmax in the S GEMM's epilogue, dS in the dP GEMM's epilogue
+    bool attn_fused = false;
+    ConvOp a_s1, a_s2, ad_pf;
+    float *rowstat = nullptr, *Drow = nullptr;
     // image
     ConvOp f_rgb, d_rgb;
     act_t* col_rgb = nullptr;
@@ -479,6 +483,30 @@ BigGANPlan* BigGAN::plan(int b) {
             o.d.B_batch = b; o.d.epi.raw_f32 = P.S; o.d.epi.raw_f32_C = Nk;
             if (build(&P.a_s, o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
         }
+        P.attn_fused = get_option("attn_fused") != 0;
+        if (P.attn_fused) {
+            // pass 1: per-row (max, sum exp) of every N tile of S = theta phi_p^T; pass 2: P = exp(S - M) / L, 16-bit.
+            // The fp32 logits never reach HBM (2 x 302 MB per step at the bench shape) and k_softmax_fwd goes away.
+            OpB o1(P.qkv, b, H, H, nq, 0, dq, P.phi_p, Nk, 1, EPI_FWD);
+            o1.d.B_batch = b;
+            const int nt = (Nk + o1.d.BN - 1) / o1.d.BN;
+            P.rowstat = ar.alloc<float>(px * nt * 2);
+            P.Drow = ar.alloc<float>(px);
+            if (ar.failed) return nullptr;
+            o1.d.epi.rowstat = P.rowstat; o1.d.epi.rowstat_nt = nt;
+            if (build(&P.a_s1, o1, &P.flops_fwd, &P.launches_fwd)) return nullptr;
+            OpB o2(P.qkv, b, H, H, nq, 0, dq, P.phi_p, Nk, 1, EPI_FWD);
+            o2.d.B_batch = b; o2.d.BN = o1.d.BN;
+            o2.d.epi.rowstat_in = P.rowstat; o2.d.epi.rowstat_nt = nt;
+            o2.d.epi.raw = P.P; o2.d.epi.raw_C = Nk;
+            if (build(&P.a_s2, o2, &P.flops_fwd, &P.launches_fwd)) return nullptr;
+            // dS = P o (dO g_p^T - rowsum(dO o O)) straight out of the dP GEMM (k_softmax_bwd and the fp32 dP go away)
+            OpB o3(P.dO, b, H, H, dv, 0, dv, P.g_p, Nk, 1, EPI_FWD);
+            o3.d.B_batch = b;
+            o3.d.epi.rowsub = P.Drow; o3.d.epi.mulin = P.P; o3.d.epi.mulin_C = Nk;
+            o3.d.epi.raw = P.dS; o3.d.epi.raw_C = Nk;
+            if (build(&P.ad_pf, o3, &P.flops_bwd, &P.launches_bwd)) return nullptr;
+        }
         {   // O = P g_p
             OpB o(P.P, b, H, H, Nk, 0, Nk, P.gT, dv, 1, EPI_FWD);
             o.d.B_batch = b; o.d.epi.raw = P.O; o.d.epi.raw_C = dv;
@@ -581,8 +609,13 @@ int BigGAN::forward(int b, const float* z, const float* c, float* img, cudaStrea
             if (conv_op_launch(P.a_qkv, st)) return -1;
             k_maxpool2_fwd(P.qkv, nq, dq, dq, P.phi_p, P.phiT, P.idx_phi, b, H, H, st);
             k_maxpool2_fwd(P.qkv, nq, 2 * dq, dv, P.g_p, P.gT, P.idx_g, b, H, H, st);
-            if (conv_op_launch(P.a_s, st)) return -1;
-            k_softmax_fwd(P.S, P.P, (long)b * H * H, H * H / 4, st);
+            if (P.attn_fused) {
+                if (conv_op_launch(P.a_s1, st)) return -1;
+                if (conv_op_launch(P.a_s2, st)) return -1;
+            } else {
+                if (conv_op_launch(P.a_s, st)) return -1;
+                k_softmax_fwd(P.S, P.P, (long)b * H * H, H * H / 4, st);
+            }
             if (conv_op_launch(P.a_o, st)) return -1;
             if (conv_op_launch(P.a_out, st)) return -1;
         }
@@ -636,8 +669,13 @@ int BigGAN::backward(int b, const float* dimg, float* dz, float* dc, cudaStream_
             const int H = attn.H, dq = attn.dq, dv = attn.dv, nq = 2 * dq + dv;
             const int Nq = H * H, Nk = Nq / 4;
             if (conv_op_launch(P.ad_out, st)) return -1;              // dO
-            if (conv_op_launch(P.ad_p, st)) return -1;                // dP -> S
-            k_softmax_bwd(P.P, P.S, P.dS, (long)b * Nq, Nk, st);      // dS
+            if (P.attn_fused) {
+                k_rowdot(P.dO, P.O, P.Drow, (long)b * Nq, dv, st);    // rowsum(dP o P) = dO . O
+                if (conv_op_launch(P.ad_pf, st)) return -1;           // dS
+            } else {
+                if (conv_op_launch(P.ad_p, st)) return -1;            // dP -> S
+                k_softmax_bwd(P.P, P.S, P.dS, (long)b * Nq, Nk, st);  // dS
+            }
             if (conv_op_launch(P.ad_theta, st)) return -1;            // dtheta -> dqkv[:, :dq]
             k_transpose(P.dS, Nk, 0, P.dST, b, Nq, Nk, st);
             k_transpose(P.qkv, nq, 0, P.thetaT, b, Nq, dq, st);

@@ -26,6 +26,7 @@ void add_launches(long n) { g_launches += n; }
 long launch_count() { return g_launches; }
 
 static int g_tma_out = 1, g_tma_kmax = 512;
+static int g_attn_fused = 0;  // "attn_fused": two-pass softmax + fused dS in the attention GEMM epilogues (needs a -DP2L_ROWFUSE=1 build; unvalidated)
 static int g_pdl = 1;  // "pdl": launch the tensor-core kernel with programmatic stream serialization (prologue overlaps the previous kernel's tail)
 static int g_deep = 1, g_deep_kmin = 8;  // "deep": full-depth single-CTA pipeline for launches with <= #SM tiles and >= deep_kmin K blocks
 static int g_grad_scale = (int)kGradScale;
@@ -44,6 +45,7 @@ void set_option(const char* key, int value) {
     else if (!std::strcmp(key, "tma_out")) g_tma_out = value;
     else if (!std::strcmp(key, "tma_kmax")) g_tma_kmax = value;
     else if (!std::strcmp(key, "pdl")) g_pdl = value;
+    else if (!std::strcmp(key, "attn_fused")) g_attn_fused = value;
     else if (!std::strcmp(key, "deep")) g_deep = value;
     else if (!std::strcmp(key, "deep_kmin")) g_deep_kmin = value;
 }
@@ -55,6 +57,8 @@ int get_option(const char* key) {
     if (!std::strcmp(key, "tma_out")) return g_tma_out;
     if (!std::strcmp(key, "tma_kmax")) return g_tma_kmax;
     if (!std::strcmp(key, "pdl")) return g_pdl;
+    if (!std::strcmp(key, "attn_fused")) return g_attn_fused;
+    if (!std::strcmp(key, "rowfuse_built")) return P2L_ROWFUSE;
     if (!std::strcmp(key, "deep")) return g_deep;
     if (!std::strcmp(key, "deep_kmin")) return g_deep_kmin;
     return -1;
@@ -169,6 +173,10 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
         set_error("conv_op_build: unsupported BN=%d", d.BN);
         return -1;
     }
+    if (!P2L_ROWFUSE && (d.epi.rowstat || d.epi.rowstat_in || d.epi.mulin || d.epi.rowsub)) {
+        set_error("conv_op_build: row-wise softmax fusions need a library built with -DP2L_ROWFUSE=1");
+        return -1;
+    }
     std::memset(op, 0, sizeof(*op));
     ConvGemmParams p = d.epi;
     p.NI = d.NI; p.H = d.H; p.W = d.W;
@@ -239,7 +247,7 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     }
     // ---- epilogue outputs by TMA bulk store: worthwhile where the epilogue dominates (small K)
     const long Ktot = (long)d.kh * d.kw * d.Cin;
-    const bool any_out = d.epi.raw || d.epi.act || d.epi.dx;
+    const bool any_out = (d.epi.raw || d.epi.act || d.epi.dx) && !d.epi.rowstat && !d.epi.rowstat_in && !d.epi.mulin;  // row-wise fusions: direct epilogue only
     op->tma_out = (g_tma_out && !halo && any_out && (d.BN == 64 || d.BN == 128) && d.Cout % 64 == 0 && Ktot <= g_tma_kmax &&
                    !d.epi.img_nchw && !(d.epi.addin && d.epi.addin_pool) && (d.epi.resid_shift == 0 || (tw >= 2 && th >= 2)) &&
                    (!d.epi.addin || d.epi.addin_climit % 64 == 0)) ? 1 : 0;

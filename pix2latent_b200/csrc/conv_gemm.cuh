@@ -33,6 +33,13 @@ constexpr int kATileBytes = kBM * kBK * 2;
 #ifndef P2L_OCC
 #define P2L_OCC 2
 #endif
+// Row-wise softmax / softmax-gradient fusions in the forward epilogue (attention; see ConvGemmParams::rowstat ...).
+// PREPARED, NOT YET VALIDATED ON A GPU: compiled out by default so that the validated kernels stay byte-for-byte what
+// the round's tests and profiles ran; build with -DP2L_ROWFUSE=1 (python -m pix2latent_b200.build --rowfuse) and set
+// the "attn_fused" option to exercise it.
+#ifndef P2L_ROWFUSE
+#define P2L_ROWFUSE 0
+#endif
 
 enum { EPI_FWD = 0, EPI_BWD = 1 };
 
@@ -74,6 +81,15 @@ struct ConvGemmParams {
     act_t* act_lo;  // with act_up: also keep the low-res copy (needed by backward)
     float* img_nchw;        // tanh(v) for c < Cout written as fp32 NCHW [NI, Cout, H, W]
     int img_linear;         // ... without the tanh (planar fp32 output of a tap-expanded head)
+    // ---- epilogue, forward: row-wise softmax / softmax-gradient fusions (attention, "attn_fused" option;
+    //      direct-epilogue path only). A thread owns one accumulator row, so row reductions are thread-local.
+    float* rowstat;          // pass 1 of a two-pass softmax: (max, sum exp(v - max)) of this tile's columns per row,
+                             // [pixel][n_tiles][2]; nothing else is written
+    const float* rowstat_in; // pass 2: v <- exp(v - M) / L with (M, L) combined from the row's n_tiles partials
+    int rowstat_nt;          // n_tiles of the pass-1 launch
+    const float* rowsub;     // v <- (v - rowsub[pixel]) * mulin[pixel, c]   (dS = P o (dP - rowsum(dO o O)))
+    const act_t* mulin;
+    int mulin_C;
     // ---- epilogue, backward
     const act_t* saved;  // forward activation of the layer being differentiated
     int saved_C;
@@ -295,6 +311,22 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+        // row-wise softmax fusions (forward mode, direct path): running (max, sum) of pass 1 / (M, 1/L) of pass 2
+#if P2L_ROWFUSE
+        float rs_max = -INFINITY, rs_sum = 0.f, rs_M = 0.f, rs_invL = 1.f, rs_sub = 0.f;
+        if constexpr (MODE == EPI_FWD && !TMA_OUT) {
+            if (p.rowstat_in && valid) {
+                const float* rp = p.rowstat_in + pix * p.rowstat_nt * 2;
+                float M = -INFINITY;
+                for (int t = 0; t < p.rowstat_nt; ++t) M = fmaxf(M, __ldg(rp + 2 * t));
+                float L = 0.f;
+                for (int t = 0; t < p.rowstat_nt; ++t) L += __ldg(rp + 2 * t + 1) * __expf(__ldg(rp + 2 * t) - M);
+                rs_M = M;
+                rs_invL = 1.f / L;
+            }
+            if (p.rowsub && valid) rs_sub = __ldg(p.rowsub + pix);
+        }
+#endif
 
 #pragma unroll 1
         for (int c = 0; c < BN; c += CH) {
@@ -377,6 +409,34 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     const long rp = (static_cast<long>(n) * Hs + (h >> p.resid_shift)) * Ws + (w >> p.resid_shift);
                     row_load_add<CH>(p.resid + rp * p.resid_C + cbase, v, wide_ok(p.resid, p.resid_C * 2));
                 }
+#if P2L_ROWFUSE
+                if constexpr (!TMA_OUT) {
+                    if (p.rowstat) {  // pass 1: online (max, sum exp) over this tile's columns; no stores
+                        float cm = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) cm = (cbase + j < p.Cout) ? fmaxf(cm, v[j]) : cm;
+                        const float nm = fmaxf(rs_max, cm);
+                        float acc = 0.f;
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) acc += (cbase + j < p.Cout) ? __expf(v[j] - nm) : 0.f;
+                        rs_sum = rs_sum * __expf(rs_max - nm) + acc;
+                        rs_max = nm;
+                        continue;
+                    }
+                    if (p.rowstat_in) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = __expf(v[j] - rs_M) * rs_invL;
+                    }
+                    if (p.mulin) {
+                        float mv[CH];
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) mv[j] = 0.f;
+                        if (valid) row_load_add<CH>(p.mulin + pix * p.mulin_C + cbase, mv, wide_ok(p.mulin, p.mulin_C * 2));
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = (v[j] - rs_sub) * mv[j];
+                    }
+                }
+#endif
                 if (p.img_nchw) {
                     if (valid) {
 #pragma unroll
@@ -585,6 +645,15 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 }
             }
         }
+#if P2L_ROWFUSE
+        if constexpr (MODE == EPI_FWD && !TMA_OUT) {
+            if (p.rowstat && valid) {
+                float* rp = p.rowstat + (pix * p.rowstat_nt + n_tile) * 2;
+                rp[0] = rs_max;
+                rp[1] = rs_sum;
+            }
+        }
+#endif
         // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above)
         tc_fence_before();
         __syncwarp();

@@ -499,6 +499,25 @@ void k_softmax_bwd(const bf16* P, const float* dP, bf16* dS, long rows, int n, c
     softmax_bwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(P, dP, dS, rows, n); count_launch();
 }
 
+// one warp per row, 16-byte loads
+__global__ void rowdot_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, float* __restrict__ D, long rows, int C) {
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float acc = 0.f;
+    for (int c = lane * 8; c < C; c += 256) {
+        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(a + row * C + c));
+        const uint4 ub = __ldg(reinterpret_cast<const uint4*>(b + row * C + c));
+        acc += act_lo(ua.x) * act_lo(ub.x) + act_hi(ua.x) * act_hi(ub.x) + act_lo(ua.y) * act_lo(ub.y) + act_hi(ua.y) * act_hi(ub.y) +
+               act_lo(ua.z) * act_lo(ub.z) + act_hi(ua.z) * act_hi(ub.z) + act_lo(ua.w) * act_lo(ub.w) + act_hi(ua.w) * act_hi(ub.w);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) D[row] = acc;
+}
+void k_rowdot(const bf16* a, const bf16* b, float* D, long rows, int C, cudaStream_t st) {
+    rowdot_kernel<<<cdiv(rows, 8), 256, 0, st>>>(a, b, D, rows, C); count_launch();
+}
+
 __global__ void transpose_kernel(const bf16* __restrict__ in, int ldin, int in_c0, bf16* __restrict__ out, int R, int C) {
     // 64 x 64 tile; rows padded to 72 elements so column reads spread over the banks
     __shared__ __align__(16) bf16 tile[64][72];

@@ -69,6 +69,8 @@ void k_maxpool2_bwd(const bf16* d_out, const unsigned char* idx, bf16* dx, int x
 void k_softmax_fwd(const float* S, bf16* P, long rows, int n, cudaStream_t st);
 // dS = P * (dP - sum_k dP*P)
 void k_softmax_bwd(const bf16* P, const float* dP, bf16* dS, long rows, int n, cudaStream_t st);
+// D[p] = sum_c a[p, c] * b[p, c]  (softmax backward: rowsum(dP o P) = dO . O per query row)
+void k_rowdot(const bf16* a, const bf16* b, float* D, long rows, int C, cudaStream_t st);
 // out[b, c, r] = in[b, r, in_c0 + c], in row stride ldin
 void k_transpose(const bf16* in, int ldin, int in_c0, bf16* out, int b, int R, int C, cudaStream_t st);
 
