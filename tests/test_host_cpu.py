@@ -103,3 +103,48 @@ def test_cma_wrapper_scalar_hack():
     assert x.shape[1] == 1 and c.is_scalar
     c.tell(x, list(np.abs(x[:, 0])))
     assert np.asarray(c.mean()).shape == (1,)
+
+
+def test_c1_plumbing_shape_on_cpu():
+    """BASELINE.json configs[0]: invert_biggan_adam.py, num_samples=1, 256x256 — the reference's own CPU-runnable
+    case (shortened to 2 gradient steps): the product's GradientOptimizer driving the full-size oracle generator and
+    oracle ProjectionLoss on CPU reproduces the oracle closure's trajectory (oracle/closure.py, itself pinned to the
+    real reference's closure.step by tests/test_golden_cpu.py)."""
+    import torch.optim as optim
+    from oracle import biggan as obg, closure as oc, lpips as olp
+    from pix2latent_b200 import VariableManager
+    from pix2latent_b200.optimizer import GradientOptimizer
+    import pix2latent_b200.distribution as dist
+    import pix2latent_b200.utils.function_hooks as hook
+    model = obg.make_biggan(obg.BigGANConfig.deep256(), seed=0, calibrate=False)
+    for p in model.parameters():
+        p.requires_grad_(False)
+    loss_fn = olp.ProjectionLoss(lpips_module=olp.make_lpips("alex", seed=0))
+    g = torch.Generator().manual_seed(3)
+    target = torch.tanh(0.5 * torch.randn(3, 256, 256, generator=g))
+    weight = torch.full((3, 256, 256), 0.3)
+    weight[:, 64:192, 64:192] = 1.0
+    c0 = model.get_class_embedding(153)[0]
+
+    def vm():
+        m = VariableManager(device="cpu")
+        m.register("z", (128,), "input", distribution=dist.TruncatedNormalModulo(sigma=1.0, trunc=2.0), learning_rate=0.05,
+                   hook_fn=hook.Clamp(2.0))
+        m.register("c", (128,), "input", default=c0, learning_rate=0.01)
+        m.register("target", (3, 256, 256), "output", requires_grad=False, default=target)
+        m.register("weight", (3, 256, 256), "output", requires_grad=False, default=weight)
+        return m
+
+    torch.manual_seed(7)
+    opt = GradientOptimizer(model, vm(), loss_fn, max_batch_size=9)
+    variables, outs, loss = opt.optimize(num_samples=1, grad_steps=2)
+    assert outs[0].shape == (3, 256, 256) and loss[0][0] == 2 and len(loss[0][1]["loss"]) == 1
+    # the same two steps through the oracle's restatement of closure.step
+    torch.manual_seed(7)
+    spec = {k: dict(v) for k, v in vm().variable_info.items()}
+    ref_vars = oc.initialize(spec, 1)
+    for _ in range(2):
+        _, l_ref, _ = oc.step(model, ref_vars, loss_fn, optimize=True, max_batch_size=9)
+    np.testing.assert_allclose(np.array(loss[0][1]["loss"]), np.array(l_ref), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(torch.stack(variables.input.z.data).detach().numpy(),
+                               torch.stack(ref_vars.input.z.data).detach().numpy(), rtol=1e-4, atol=1e-5)
