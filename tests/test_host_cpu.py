@@ -148,3 +148,21 @@ def test_c1_plumbing_shape_on_cpu():
     np.testing.assert_allclose(np.array(loss[0][1]["loss"]), np.array(l_ref), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(torch.stack(variables.input.z.data).detach().numpy(),
                                torch.stack(ref_vars.input.z.data).detach().numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("script", ["invert_biggan_basincma.py", "invert_biggan_with_transform.py",
+                                    "invert_stylegan2_cars_basincma.py"])
+def test_reference_examples_import_through_the_alias(script):
+    """The reference's own example scripts resolve every `pix2latent.*` import against this package (argument
+    parsing happens after the imports, so `--help` exercises exactly the import block). Needs the reference checkout."""
+    import os
+    import subprocess
+    import sys
+    path = os.path.join("/root/reference/examples", script)
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root)
+    r = subprocess.run([sys.executable, path, "--help"], capture_output=True, text=True, timeout=300, env=env, cwd="/tmp")
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "usage:" in r.stdout
