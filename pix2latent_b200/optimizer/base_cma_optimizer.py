@@ -115,8 +115,14 @@ class _BaseCMAOptimizer():
                 target = info["target"]["default"].unsqueeze(0).type_as(out)
                 weight = info["weight"]["default"].unsqueeze(0).type_as(out)
                 t_fn = self.transform_fns["target"]["fn"]
-                out = t_fn(out, torch.stack(variables.transform.t.data), invert=True)
+                # (candidate sharding: `out` holds this rank's candidates only)
+                rank, size = parallel.world()
+                n_all = variables.num_samples
+                lo, hi = parallel.shard_bounds(n_all, rank, size) if size > 1 else (0, n_all)
+                out = t_fn(out, torch.stack(variables.transform.t.data[lo:hi]), invert=True)
                 loss = self.loss_fn(out, target, binarize(weight)).cpu().detach().numpy()
+                if size > 1:
+                    loss = np.array(parallel.allgather_losses(loss, n_all))
             if parallel.world()[0] == 0:
                 opt.tell(asked, loss)
         return loss

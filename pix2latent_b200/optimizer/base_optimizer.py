@@ -281,17 +281,26 @@ class _BaseOptimizer():
         self._maybe_log(self._variables, log_at, log_last)
         self._progress(i, total_steps, log_at, pbar)
 
+    def sync_inputs(self, variables):
+        """Candidate sharding: every rank refines only its shard; bring the current latents of ALL candidates to every
+        rank (an all_gather of N x dim floats — KBs). No-op in a single process."""
+        rank, size = parallel.world()
+        if size <= 1:
+            return
+        n = variables.num_samples
+        lo, hi = parallel.shard_bounds(n, rank, size)
+        with torch.no_grad():
+            for var in variables.input.values():
+                full = parallel.allgather_rows(torch.stack(var.data[lo:hi]), n)
+                for i, t in enumerate(var.data):
+                    t.data.copy_(full[i])
+
     def _finish(self, variables, total_steps):
         rank, size = parallel.world()
         if size > 1:
             # final state of every shard to every rank: latents (KBs), losses, images
             n = variables.num_samples
-            lo, hi = parallel.shard_bounds(n, rank, size)
-            with torch.no_grad():
-                for var in variables.input.values():
-                    full = parallel.allgather_rows(torch.stack(var.data[lo:hi]), n)
-                    for i, t in enumerate(var.data):
-                        t.data.copy_(full[i])
+            self.sync_inputs(variables)
             self.loss = self.gathered_loss()
             self.out = parallel.allgather_rows(self.out, n)
         if self.log:

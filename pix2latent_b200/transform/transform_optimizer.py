@@ -62,8 +62,14 @@ class TransformBasinCMAOptimizer(_BaseOptimizer, _BaseCMAOptimizer):
     @torch.no_grad()
     def update_propagation_variable_statistic(self, variables, ema_beta=0.5):
         """moving average towards the seed that currently performs best (ema_beta = 1 forgets the past)"""
+        from .. import parallel
+        losses = self.loss
+        if parallel.world()[1] > 1:
+            # candidates are sharded: the best seed may live on another rank
+            self.sync_inputs(variables)
+            losses = self.gathered_loss()
         for name, entry in self._propagated(variables):
-            best = entry.data[int(np.argmin(self.loss))]
+            best = entry.data[int(np.argmin(losses))]
             self.vp_means[name] = (1.0 - ema_beta) * self.vp_means[name] + ema_beta * best
 
     @torch.no_grad()
@@ -128,6 +134,11 @@ class TransformBasinCMAOptimizer(_BaseOptimizer, _BaseCMAOptimizer):
         candidate_out = variables.output.target.data[int(np.argmin(loss))]
         if self.log:
             return variables, (self.outs, self.transform_outs, candidate_out), self.losses
+        from .. import parallel
+        if parallel.world()[1] > 1:
+            self.sync_inputs(variables)
+            self.loss = self.gathered_loss()
+            self.out = parallel.allgather_rows(self.out, variables.num_samples)
         transform_target = to_grid(torch.stack(variables.output.target.data).cpu())
         transform_out = to_grid(torch.stack(list(self.out.cpu().detach())))
         return variables, ([transform_out], [transform_target], candidate_out), self.loss

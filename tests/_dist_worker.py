@@ -40,10 +40,42 @@ def fused_toy(out_path, fused):
     return res
 
 
+def transform_search(out_path):
+    """TransformBasinCMAOptimizer on the tiny problem of tests/golden/make_golden_transform.py with the torch resampler."""
+    import make_golden as mg
+    import make_golden_transform as mgt
+    from oracle import lpips as olp
+    from oracle import transform as otf
+    from pix2latent_b200 import VariableManager
+    from pix2latent_b200.transform import TransformBasinCMAOptimizer
+    import pix2latent_b200.distribution as dst
+    import pix2latent_b200.utils.function_hooks as hook
+    cfg, model, target, weight = mg.problem()
+    loss_fn = olp.ProjectionLoss(lpips_module=olp.make_lpips("alex", seed=0))
+    torch.manual_seed(31)
+    vm = VariableManager(device="cpu")
+    mgt.register_transform_problem(vm, hook, dst, model, target, weight)
+    opt = TransformBasinCMAOptimizer(model, vm, loss_fn, max_batch_size=4)
+    opt.cma_seed = mg.CMA_SEED
+    opt.register_transform(otf.TorchSpatialTransform(t=[1.0, 0.0, 0.0]), "t", "target")
+    opt.register_transform(otf.TorchSpatialTransform(t=[1.0, 0.0, 0.0]), "t", "weight")
+    opt.set_variable_propagation("z")
+    variables, (t_out, t_target, t_cand), loss = opt.optimize(meta_steps=3, grad_steps=2)
+    if dist.get_rank() == 0:
+        np.savez(out_path, loss=np.array(loss, dtype=np.float64), z=torch.stack(variables.input.z.data).detach().numpy(),
+                 tracked=torch.stack(opt.transform_tracked).numpy(), cand=opt.get_candidate().numpy(),
+                 vp=opt.vp_means["z"].numpy())
+
+
 def main():
     out_path = sys.argv[1]
     dist.init_process_group("gloo")
     torch.set_num_threads(4)
+    if len(sys.argv) > 2 and sys.argv[2] == "transform":
+        transform_search(out_path)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if len(sys.argv) > 2 and sys.argv[2] == "fused":
         fused_toy(out_path, True)
         dist.barrier()
