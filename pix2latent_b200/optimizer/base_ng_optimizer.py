@@ -17,9 +17,10 @@ def _ng():
     try:
         import nevergrad as ng
         return ng
-    except ImportError as e:
-        raise ImportError("HybridNevergradOptimizer / NevergradOptimizer need the `nevergrad` package "
-                          "(reference requirements.txt:3); it is not installed in this environment") from e
+    except ImportError:
+        # offline image: the minimal ask / tell stand-in (CMA, RandomSearch); production uses the real package
+        from . import _mining
+        return _mining
 
 
 class _BaseNevergradOptimizer():
