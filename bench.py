@@ -342,6 +342,27 @@ def run_native(args, rank, world, local_rank):
     except Exception as e:  # the headline numbers above do not depend on this leg
         inner = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    # ---- eval-only units (generator fwd + loss, no backward): what CMAOptimizer's meta-iterations run
+    # (cma_optimizer.py:46-72; SURVEY.md section 8d asks for them separately). Informational.
+    eval_only = None
+    try:
+        for _ in range(3):
+            native.biggan_step(gen, lp, tgt, z, c, False, scale, want_img=False)
+        sync_all()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            native.biggan_step(gen, lp, tgt, z, c, False, scale, want_img=False)
+        f1.record()
+        sync_all()
+        t = torch.tensor([f0.elapsed_time(f1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        eval_only = {"value": world * n * args.steps / (float(t.item()) / 1e3), "unit": "candidates/s",
+                     "what": "generator forward + L1+10*LPIPS loss only (no backward), inputs resident in HBM"}
+    except Exception as e:
+        eval_only = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -361,6 +382,7 @@ def run_native(args, rank, world, local_rank):
         "roofline": roof,
         "final_loss_mean": float(loss.mean().item()),
         "inner_loop": inner,
+        "eval_only": eval_only,
     }
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(1, 0, budget_s=30.0, cand=3)
