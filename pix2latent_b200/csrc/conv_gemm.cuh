@@ -40,6 +40,14 @@ constexpr int kATileBytes = kBM * kBK * 2;
 #ifndef P2L_ROWFUSE
 #define P2L_ROWFUSE 0
 #endif
+// Backward epilogue, direct path, one-CTA-per-SM kernels with N = 64 (halo-patch 3x3, DEEP): fetch the tile's rows of the
+// saved activation BEFORE waiting for the accumulator, so that their global-load latency (exposed once per 32-column chunk
+// today: block 11's dgrad conv_2 takes 179 us against 97 us for the same contraction without a saved activation,
+// profiles/r1d_per_layer_roofline.md) overlaps the tile's main loop. 32 more registers per thread, hence only where the
+// register budget is 204. PREPARED, NOT YET VALIDATED ON A GPU: compiled out by default (-DP2L_PREFETCH_SAVED=1 to try).
+#ifndef P2L_PREFETCH_SAVED
+#define P2L_PREFETCH_SAVED 0
+#endif
 
 enum { EPI_FWD = 0, EPI_BWD = 1 };
 
@@ -308,6 +316,20 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
             }
             bar_epilogue(grp);  // table[it & 1] was last read by this group's previous tile (or two tiles ago): every warp has passed a barrier since
         }
+#if P2L_PREFETCH_SAVED
+        constexpr bool kPre = (MODE == EPI_BWD) && !TMA_OUT && NG == 2 && BN == 64 && CH == 32;
+        // eight named registers rather than an array: the compiler keeps an indexed array (partly) in local memory
+        uint4 pa0 = make_uint4(0, 0, 0, 0), pa1 = pa0, pa2 = pa0, pa3 = pa0, pb0 = pa0, pb1 = pa0, pb2 = pa0, pb3 = pa0;
+        bool pre_ok = false;
+        if constexpr (kPre) {
+            pre_ok = p.saved != nullptr && valid && (n_tile * BN + BN <= p.Cout) && (p.saved_C % 8 == 0);
+            if (pre_ok) {
+                const uint4* sp = reinterpret_cast<const uint4*>(p.saved + pix * p.saved_C + n_tile * BN);
+                pa0 = __ldg(sp + 0); pa1 = __ldg(sp + 1); pa2 = __ldg(sp + 2); pa3 = __ldg(sp + 3);
+                pb0 = __ldg(sp + 4); pb1 = __ldg(sp + 5); pb2 = __ldg(sp + 6); pb3 = __ldg(sp + 7);
+            }
+        }
+#endif
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
@@ -520,6 +542,15 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 #pragma unroll
                     for (int j = 0; j < CH; ++j) v[j] = (valid && y[j] > 0.f) ? v[j] : 0.f;
                 } else if (p.saved) {
+#if P2L_PREFETCH_SAVED
+                    if (kPre && pre_ok) {
+                        if (c == 0) {
+                            acc8_act(pa0, y); acc8_act(pa1, y + 8); acc8_act(pa2, y + 16); acc8_act(pa3, y + 24);
+                        } else {
+                            acc8_act(pb0, y); acc8_act(pb1, y + 8); acc8_act(pb2, y + 16); acc8_act(pb3, y + 24);
+                        }
+                    } else
+#endif
                     if (valid) {
                         row_load_add<CH>(p.saved + pix * p.saved_C + cbase, y, wide_ok(p.saved, p.saved_C * 2));  // y starts at 0
                     } else {
