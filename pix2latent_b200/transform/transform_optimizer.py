@@ -87,50 +87,64 @@ class TransformBasinCMAOptimizer(_BaseOptimizer, _BaseCMAOptimizer):
     def get_candidate(self):
         return self._candidate
 
-    def optimize(self, meta_steps, grad_steps, last_grad_steps=None, pbar=None):
-        """
-        Args
-            meta_steps (int): CMA updates
-            grad_steps (int): gradient updates per CMA update
-            last_grad_steps (int): gradient updates of the last meta-iteration (default: grad_steps)
-        Returns (variables, (outs, transformed targets, best candidate's target), losses)
-        """
-        self.setup_cma(self.var_manager)
+    # ---- the search ---------------------------------------------------------------------------------------------
+    def _reset(self):
         self.losses, self.outs, self.transform_outs = [], [], []
         self._best_loss, self._candidate = 999, None
         self.vp_means = {}
         self.transform_tracked = []
-        if last_grad_steps is None:
-            last_grad_steps = grad_steps
+
+    def _refine(self, variables, n_steps, done, total_steps, grad_steps, pbar, t_mark):
+        """n_steps gradient updates of (z, c) against this meta-iteration's transformed targets; returns (steps done, t_mark)"""
+        for j in range(n_steps):
+            self.step(variables, optimize=True, transform=(j == 0))   # j == 0: every candidate's target / weight is resampled
+            done += 1
+            if self.log:
+                if j == 0:
+                    self.vis_transform(variables)
+                if done % self.log_iter == 0 or done == grad_steps:
+                    self.log_result(variables, done)
+            if pbar is not None:
+                pbar.progress(done / total_steps)
+            elif done % self.show_iter == 0:
+                progress_print("optimize", done, total_steps, "c", (time.time() - t_mark) / self.show_iter)
+                t_mark = time.time()
+        return done, t_mark
+
+    def _remember_best(self, variables, loss):
+        best = int(np.argmin(loss))
+        if loss[best] < self._best_loss:
+            self._candidate = variables.transform.t.data[best].cpu().detach()
+            self._best_loss = loss[best]
+
+    def optimize(self, meta_steps, grad_steps, last_grad_steps=None, pbar=None):
+        """
+        Args
+            meta_steps (int): CMA updates of the transformation parameter
+            grad_steps (int): gradient updates of the latents per CMA update
+            last_grad_steps (int): gradient updates of the last meta-iteration (default: grad_steps)
+        Returns (variables, (outs, transformed targets, best candidate's target), losses)
+        """
+        self.setup_cma(self.var_manager)
+        self._reset()
+        last_grad_steps = grad_steps if last_grad_steps is None else last_grad_steps
         total_steps = (meta_steps - 1) * grad_steps + last_grad_steps
-        i, t_mark, loss = 0, time.time(), None
+        done, t_mark, loss = 0, time.time(), None
         for meta_iter in range(meta_steps):
-            last = meta_iter + 1 == meta_steps
+            final = meta_iter == meta_steps - 1
             variables = self._variables = self.cma_init(self.var_manager)
             if meta_iter > 0:
                 self.propagate_variable(variables, meta_iter, meta_steps)
             self.transform_tracked.append(torch.stack(variables.transform.t.data).cpu().detach().clone())
-            for j in range(last_grad_steps if last else grad_steps):
-                self.step(variables, optimize=True, transform=(j == 0))
-                i += 1
-                if self.log and j == 0:
-                    self.vis_transform(variables)
-                if self.log and ((i % self.log_iter == 0) or (i == grad_steps)):
-                    self.log_result(variables, i)
-                if pbar is not None:
-                    pbar.progress(i / total_steps)
-                elif i % self.show_iter == 0:
-                    progress_print("optimize", i, total_steps, "c", (time.time() - t_mark) / self.show_iter)
-                    t_mark = time.time()
-            if not last:
-                loss = self.cma_update(variables, inverted_loss=True)
+            done, t_mark = self._refine(variables, last_grad_steps if final else grad_steps, done, total_steps, grad_steps,
+                                        pbar, t_mark)
+            if not final:
+                loss = np.asarray(self.cma_update(variables, inverted_loss=True))
             elif loss is None:
-                loss = np.array(self.loss)  # single meta-iteration: the reference would fail on an unbound name
+                loss = np.asarray(self.loss)  # a single meta-iteration: the reference would stop on an unbound name here
+            # (after the last meta-iteration `loss` still holds the previous CMA update's losses, as in the reference)
             self.update_propagation_variable_statistic(variables)
-            # (on the last meta-iteration `loss` still holds the previous CMA update's losses, as in the reference)
-            if np.min(loss) < self._best_loss:
-                self._candidate = variables.transform.t.data[int(np.argmin(loss))].cpu().detach()
-                self._best_loss = np.min(loss)
+            self._remember_best(variables, loss)
         candidate_out = variables.output.target.data[int(np.argmin(loss))]
         if self.log:
             return variables, (self.outs, self.transform_outs, candidate_out), self.losses

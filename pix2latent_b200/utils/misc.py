@@ -38,27 +38,19 @@ class HiddenPrints:
         sys.stdout = self._stdout
 
 
-class bcolors:
-    HEADER = '\033[95m'
-    b = blue = OKBLUE = '\033[94m'
-    g = green = OKGREEN = '\033[92m'
-    y = yellow = WARNING = '\033[93m'
-    r = red = FAIL = '\033[91m'
-    c = cyan = '\033[36m'
-    lb = lightblue = '\033[94m'
-    p = pink = '\033[95m'
-    o = orange = '\033[33m'
-    lc = lightcyan = '\033[96m'
-    end = ENDC = '\033[0m'
-    BOLD = '\033[1m'
-    UNDERLINE = '\033[4m'
+_ANSI = {"HEADER": 95, "OKBLUE": 94, "OKGREEN": 92, "WARNING": 93, "FAIL": 91, "ENDC": 0, "BOLD": 1, "UNDERLINE": 4,
+         "b": 94, "blue": 94, "g": 92, "green": 92, "y": 93, "yellow": 93, "r": 91, "red": 91, "c": 36, "cyan": 36,
+         "lb": 94, "lightblue": 94, "p": 95, "pink": 95, "o": 33, "orange": 33, "lc": 96, "lightcyan": 96, "end": 0}
+# attribute access (bcolors.red, bcolors.ENDC, ...) as the reference's scripts use it
+bcolors = type("bcolors", (), {k: "\033[%dm" % v for k, v in _ANSI.items()})
 
 
 def color_str(string, color):
-    if not hasattr(bcolors, color):
+    code = getattr(bcolors, color, None)
+    if code is None:
         warnings.warn("Unknown color {}".format(color))
         return string
-    return "{}{}{}".format(getattr(bcolors, color), string, bcolors.end)
+    return code + str(string) + bcolors.end
 
 
 def cprint(print_str, color):
@@ -66,14 +58,11 @@ def cprint(print_str, color):
 
 
 def color_loss(loss):
-    c = "red"
-    if loss < 0.5:
-        c = "yellow"
-    if loss < 0.1:
-        c = "green"
-    if loss < 0.01:
-        c = "cyan"
-    return "{}{:.5f}{}".format(getattr(bcolors, c), loss, bcolors.end)
+    """loss as a 5-decimal string, coloured by magnitude (red >= 0.5 > yellow >= 0.1 > green >= 0.01 > cyan)"""
+    for bound, name in ((0.01, "cyan"), (0.1, "green"), (0.5, "yellow")):
+        if loss < bound:
+            return color_str("{:.5f}".format(loss), name)
+    return color_str("{:.5f}".format(loss), "red")
 
 
 def progress_print(phase, i, j, color="c", t=None):
