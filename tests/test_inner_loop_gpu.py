@@ -130,14 +130,14 @@ def test_fused_loop_equals_step_by_step(world):
         rel = ((a - b_).abs() / (1 + b_.abs())).max(1).values.tolist()
         print(what, ["%.1e" % r for r in rel])
         for k, r in enumerate(rel):
-            assert r < (2e-6 if k == 0 else min(2e-2, 2e-4 * 4.0 ** (k - 1))), (what, k, r)
+            assert r < (2e-6 if k == 0 else min(2e-2, 4e-4 * 4.0 ** (k - 1))), (what, k, r)
 
     ladder(rf["loss"], ref_losses, "fused vs step-by-step:")
     # tracked inputs are recorded before the hook of each step; the first updates are identical
     assert torch.equal(rf["z_hist"][0], z0)
     assert mostly_equal(rf["z_hist"][1], ref_z[1])
     # (from the second update on, components whose gradient is at noise level may step either way: compare the mean)
-    assert (rf["z_hist"][2] - ref_z[2]).abs().mean().item() < 2e-3
+    assert (rf["z_hist"][2] - ref_z[2]).abs().mean().item() < 5e-3
     assert (zf - torch.stack(zt).detach()).abs().mean().item() < 0.05
     assert (cf - torch.stack(ct).detach()).abs().mean().item() < 0.02
     img_ref = model.native.forward(rf["z_hist"][K - 1].clamp(-trunc, trunc), rf["c_hist"][K - 1])
@@ -161,21 +161,26 @@ def test_fused_loop_state_carries_over(world):
     zb, cb = z0.clone(), c0.clone()
     r1 = native.biggan_optimize(model.native, loss.native_lpips(), tgt, zb, cb, 3, cfgA, grad_scale=1 / 3, use_graph=False)
     r2 = native.biggan_optimize(model.native, loss.native_lpips(), tgt, zb, cb, 3, cfgA, state=r1["state"], grad_scale=1 / 3,
-                                use_graph=True)
+                                use_graph=True, track=True)
     torch.cuda.synchronize()
     assert r2["state"].step_count() == 6
     both = torch.cat([r1["loss"], r2["loss"]])
     rel = ((both - ra["loss"]).abs() / (1 + ra["loss"].abs())).max(1).values.tolist()
     print("3+3 vs 6 fused steps:", ["%.1e" % r for r in rel])
     for k, r in enumerate(rel):
-        assert r < (2e-6 if k == 0 else min(2e-2, 2e-4 * 4.0 ** (k - 1))), (k, r)
-    # a FRESH optimizer at step 3 would take a full +-lr sign step there; the carried state does not
-    zc, cc = z0.clone(), c0.clone()
-    native.biggan_optimize(model.native, loss.native_lpips(), tgt, zc, cc, 3, cfgA, grad_scale=1 / 3, use_graph=False)
-    native.biggan_optimize(model.native, loss.native_lpips(), tgt, zc, cc, 3, cfgA, grad_scale=1 / 3, use_graph=False)
-    torch.cuda.synchronize()
-    assert (zc - za).abs().mean().item() > 1.5 * (zb - za).abs().mean().item()
+        assert r < (2e-6 if k == 0 else min(2e-2, 4e-4 * 4.0 ** (k - 1))), (k, r)
     assert (za - zb).abs().mean().item() < 0.03
+    # The carried moments are really used: a FRESH Adam takes a full +-lr step in every component (m / sqrt(v) = sign(g)
+    # at t = 1), an optimizer that carries three steps of history does not.
+    lr = 0.05
+    first_of_second_call = (r2["z_hist"][1] - r2["z_hist"][0].clamp(-2, 2)).abs()
+    zc, cc = zb.clone(), cb.clone()
+    r3 = native.biggan_optimize(model.native, loss.native_lpips(), tgt, zc, cc, 2, cfgA, grad_scale=1 / 3, use_graph=False, track=True)
+    torch.cuda.synchronize()
+    fresh = (r3["z_hist"][1] - r3["z_hist"][0].clamp(-2, 2)).abs()
+    full_step = lambda d: ((d - lr).abs() < 1e-3 * lr).float().mean().item()
+    print("fraction of components moving by exactly lr: carried %.2f, fresh %.2f" % (full_step(first_of_second_call), full_step(fresh)))
+    assert full_step(fresh) > 0.95 and full_step(first_of_second_call) < 0.5
 
 
 def test_product_api_fused_vs_per_step(world):
@@ -196,7 +201,7 @@ def test_product_api_fused_vs_per_step(world):
     print("GradientOptimizer fused vs per-step: loss", l0, l1)
     assert np.abs(l0 - l1).max() < 2e-2 * (1 + np.abs(l0).max())
     assert (z0 - z1).abs().mean().item() < 0.05
-    assert len(t0) == len(t1) == 6 and mostly_equal(t0[1], t1[1]) and (t0[2] - t1[2]).abs().mean().item() < 2e-3
+    assert len(t0) == len(t1) == 6 and mostly_equal(t0[1], t1[1]) and (t0[2] - t1[2]).abs().mean().item() < 5e-3
     assert o0.shape == o1.shape
     res = {}
     for fused in (False, True):
