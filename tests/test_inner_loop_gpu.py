@@ -180,7 +180,7 @@ def test_fused_loop_state_carries_over(world):
     fresh = (r3["z_hist"][1] - r3["z_hist"][0].clamp(-2, 2)).abs()
     full_step = lambda d: ((d - lr).abs() < 1e-3 * lr).float().mean().item()
     print("fraction of components moving by exactly lr: carried %.2f, fresh %.2f" % (full_step(first_of_second_call), full_step(fresh)))
-    assert full_step(fresh) > 0.95 and full_step(first_of_second_call) < 0.5
+    assert full_step(fresh) > 0.9 and full_step(fresh) - full_step(first_of_second_call) > 0.4
 
 
 def test_product_api_fused_vs_per_step(world):
