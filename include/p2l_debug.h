@@ -54,6 +54,9 @@ typedef struct p2l_conv_args {
     const float* rowsub;
     const void* mulin;
     int mulin_C;
+    /* split-K workspace (needs a -DP2L_SPLITK=1 build and the "splitk" option) */
+    float* splitk_ws;
+    long splitk_ws_floats;
 } p2l_conv_args;
 
 /* returns 0 on success, <0 on error (see p2l_last_error) */

@@ -53,10 +53,10 @@ def _compile(src, force, hdr_m):
     return obj, True
 
 
-def build(force=False, verbose=True, rowfuse=False, prefetch_saved=False):
+def build(force=False, verbose=True, rowfuse=False, prefetch_saved=False, splitk=False):
     """rowfuse / prefetch_saved: compile the prepared (not yet GPU-validated) row-wise softmax fusions
     (-DP2L_ROWFUSE=1) / saved-activation prefetch of the backward epilogue (-DP2L_PREFETCH_SAVED=1) in"""
-    for on, flag in ((rowfuse, "-DP2L_ROWFUSE=1"), (prefetch_saved, "-DP2L_PREFETCH_SAVED=1")):
+    for on, flag in ((rowfuse, "-DP2L_ROWFUSE=1"), (prefetch_saved, "-DP2L_PREFETCH_SAVED=1"), (splitk, "-DP2L_SPLITK=1")):
         if on and flag not in FLAGS:
             FLAGS.append(flag)
             force = True
@@ -88,4 +88,5 @@ def build(force=False, verbose=True, rowfuse=False, prefetch_saved=False):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, rowfuse="--rowfuse" in sys.argv, prefetch_saved="--prefetch-saved" in sys.argv)
+    build(force="--force" in sys.argv, rowfuse="--rowfuse" in sys.argv, prefetch_saved="--prefetch-saved" in sys.argv,
+          splitk="--splitk" in sys.argv)

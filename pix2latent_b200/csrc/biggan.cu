@@ -36,6 +36,8 @@ struct BigGANPlan {
                   *dqkv = nullptr, *dphi_p = nullptr, *dg_p = nullptr;
     ConvOp a_qkv, a_s, a_o, a_out, ad_out, ad_p, ad_theta, ad_phi, ad_g, ad_qkv;
     // "attn_fused" (prepared, unvalidated): two-pass softmax in the S GEMM's epilogue, dS in the dP GEMM's epilogue
+    float* ks_ws = nullptr;  // split-K workspace ("splitk" option, P2L_SPLITK builds)
+    long ks_ws_floats = 0;
     bool attn_fused = false;
     ConvOp a_s1, a_s2, ad_pf;
     float *rowstat = nullptr, *Drow = nullptr;
@@ -344,7 +346,14 @@ BigGANPlan* BigGAN::plan(int b) {
     P.rgbT = ar.alloc<float>((size_t)b * 27 * R * R);
     if (ar.failed) return nullptr;
 
+    if (get_option("splitk") > 0 && get_option("splitk_built") > 0) {
+        P.ks_ws_floats = 16L << 20;  // 64 MB: 8 splits of the largest eligible launch (M = 1152, N = 2048)
+        P.ks_ws = ar.alloc<float>((size_t)P.ks_ws_floats);
+        if (ar.failed) return nullptr;
+    }
     auto build = [&](ConvOp* op, OpB& ob, double* flops, int* launches) -> int {
+        ob.d.splitk_ws = P.ks_ws;
+        ob.d.splitk_ws_floats = P.ks_ws_floats;
         if (conv_op_build(op, ob.d)) return -1;
         *flops += op->flops;
         *launches += 1;

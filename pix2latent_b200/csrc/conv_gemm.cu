@@ -26,6 +26,7 @@ void add_launches(long n) { g_launches += n; }
 long launch_count() { return g_launches; }
 
 static int g_tma_out = 1, g_tma_kmax = 512;
+static int g_splitk = 0;  // "splitk": split-K over idle SMs for few-tile / long-K launches (needs a -DP2L_SPLITK=1 build; unvalidated)
 static int g_attn_fused = 0;  // "attn_fused": two-pass softmax + fused dS in the attention GEMM epilogues (needs a -DP2L_ROWFUSE=1 build; unvalidated)
 static int g_pdl = 1;  // "pdl": launch the tensor-core kernel with programmatic stream serialization (prologue overlaps the previous kernel's tail)
 static int g_deep = 1, g_deep_kmin = 8;  // "deep": full-depth single-CTA pipeline for launches with <= #SM tiles and >= deep_kmin K blocks
@@ -46,6 +47,7 @@ void set_option(const char* key, int value) {
     else if (!std::strcmp(key, "tma_kmax")) g_tma_kmax = value;
     else if (!std::strcmp(key, "pdl")) g_pdl = value;
     else if (!std::strcmp(key, "attn_fused")) g_attn_fused = value;
+    else if (!std::strcmp(key, "splitk")) g_splitk = value;
     else if (!std::strcmp(key, "deep")) g_deep = value;
     else if (!std::strcmp(key, "deep_kmin")) g_deep_kmin = value;
 }
@@ -59,6 +61,8 @@ int get_option(const char* key) {
     if (!std::strcmp(key, "pdl")) return g_pdl;
     if (!std::strcmp(key, "attn_fused")) return g_attn_fused;
     if (!std::strcmp(key, "rowfuse_built")) return P2L_ROWFUSE;
+    if (!std::strcmp(key, "splitk")) return g_splitk;
+    if (!std::strcmp(key, "splitk_built")) return P2L_SPLITK;
     if (!std::strcmp(key, "deep")) return g_deep;
     if (!std::strcmp(key, "deep_kmin")) return g_deep_kmin;
     return -1;
@@ -296,6 +300,28 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
                 (long)d.kh * d.kw * p.cin_chunks >= g_deep_kmin) ? 1 : 0;
     const long slots = (long)num_sms() * ((halo || d.BN > 128 || op->tma_out || op->deep) ? 1 : P2L_OCC);
     op->grid = (int)(total < slots ? total : slots);
+#if P2L_SPLITK
+    if (g_splitk && d.splitk_ws && !op->tma_out && !halo && !d.epi.img_nchw && d.Cout % 32 == 0 && total * 2 <= num_sms()) {
+        const long kblocks = (long)d.kh * d.kw * p.cin_chunks;
+        long target = num_sms() / total;                 // splits that still fit one wave
+        if (target > 8) target = 8;
+        if (kblocks / target < 4) target = kblocks / 4;  // at least four K blocks per split
+        if (target >= 2) {
+            const long kbs = (kblocks + target - 1) / target;
+            const long KS = (kblocks + kbs - 1) / kbs;    // every split non-empty
+            const long stride = (long)d.NI * d.H * d.W * d.Cout;
+            if (KS >= 2 && KS * stride <= d.splitk_ws_floats) {
+                p.ksplit = (int)KS; p.ks_blocks = (int)kbs; p.ks_finish = 0;
+                p.ks_partial = d.splitk_ws; p.ks_stride = stride;
+                op->p = p;
+                op->ksplit = (int)KS;
+                op->grid_finish = op->grid;
+                const long work = total * KS;
+                op->grid = (int)(work < slots ? work : slots);
+            }
+        }
+    }
+#endif
     op->flops = 2.0 * d.NI * d.H * d.W * (double)d.Cout * d.kh * d.kw * d.Cin;
     return 0;
 }
@@ -375,7 +401,23 @@ static int launch_halo_t(const ConvOp& op, cudaStream_t stream) {
     return 0;
 }
 
+static int conv_op_launch_one(const ConvOp& op, cudaStream_t stream);
+
 int conv_op_launch(const ConvOp& op, cudaStream_t stream) {
+#if P2L_SPLITK
+    if (op.ksplit > 1) {
+        // partial pass over (tile, K split) work items, then the finish pass (epilogue warps only) of the same kernel
+        if (conv_op_launch_one(op, stream)) return -1;
+        ConvOp fin = op;
+        fin.p.ks_finish = 1;
+        fin.grid = op.grid_finish;
+        return conv_op_launch_one(fin, stream);
+    }
+#endif
+    return conv_op_launch_one(op, stream);
+}
+
+static int conv_op_launch_one(const ConvOp& op, cudaStream_t stream) {
     if (op.halo) {
 #define P2L_HALO(bn, pp)                                                                   \
     if (op.BN == bn && op.halo == pp)                                                      \

@@ -48,6 +48,14 @@ constexpr int kATileBytes = kBM * kBK * 2;
 #ifndef P2L_PREFETCH_SAVED
 #define P2L_PREFETCH_SAVED 0
 #endif
+// Split-K over idle SMs for launches with fewer tiles than SMs and a long K loop (the 4x4 / 8x8 generator blocks: one SM's
+// L2->shared-memory port, ~40-64 B/clk, bounds them — profiles/r1d_ncu_lo3_before.md): work item = (tile, K split); a split
+// writes its fp32 partial accumulators to a workspace; a second launch of the SAME kernel in "finish" mode runs only the
+// epilogue warps, which sum the partials instead of reading TMEM and then apply the layer's normal epilogue.
+// PREPARED, NOT YET VALIDATED ON A GPU: compiled out by default (-DP2L_SPLITK=1 and the "splitk" option to try).
+#ifndef P2L_SPLITK
+#define P2L_SPLITK 0
+#endif
 
 enum { EPI_FWD = 0, EPI_BWD = 1 };
 
@@ -110,6 +118,10 @@ struct ConvGemmParams {
     int dx_C;
     float* dx_f32;  // optional fp32 copy (used for the latent-side tensors)
     int dx_f32_C;
+    // ---- split-K (P2L_SPLITK): ksplit > 1: K is cut into ksplit ranges of ks_blocks K blocks; partials [split][pixel][Cout] fp32
+    int ksplit, ks_blocks, ks_finish;
+    float* ks_partial;
+    long ks_stride;  // floats between two splits' partials
 };
 
 // DEEP: one CTA per SM with the full shared memory as pipeline (8 x 24 KB stages for BN = 64): for launches with
@@ -289,7 +301,19 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
     float alpha = p.alpha;
     if (p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
     int it = grp;  // index of the tile in this CTA's sequence
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += NG * gridDim.x, it += NG) {
+#if P2L_SPLITK
+    const bool ks_finish = !TMA_OUT && p.ks_finish != 0;
+    const int KS = (!TMA_OUT && p.ksplit > 1 && !ks_finish) ? p.ksplit : 1;  // work item = (tile, split) in the partial pass
+    const int loop_tiles = total_tiles * KS;
+#else
+    const int loop_tiles = total_tiles;
+#endif
+    for (int wt = blockIdx.x + grp * gridDim.x; wt < loop_tiles; wt += NG * gridDim.x, it += NG) {
+#if P2L_SPLITK
+        const int tile = wt / KS, split = wt - tile * KS;
+#else
+        const int tile = wt;
+#endif
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
@@ -330,8 +354,13 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
             }
         }
 #endif
-        mbar_wait(&tfull_bar[as], aphase);
-        tc_fence_after();
+#if P2L_SPLITK
+        if (!ks_finish)
+#endif
+        {
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+        }
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
         // row-wise softmax fusions (forward mode, direct path): running (max, sum) of pass 1 / (M, 1/L) of pass 2
 #if P2L_ROWFUSE
@@ -385,6 +414,23 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 }
             }
             float v[CH];
+#if P2L_SPLITK
+            if (ks_finish) {
+                // finish pass: the accumulator is the sum of the splits' partials (fp32, L2-resident)
+#pragma unroll
+                for (int j = 0; j < CH; ++j) v[j] = 0.f;
+                if (valid) {
+                    for (int sp = 0; sp < p.ksplit; ++sp) {
+                        const float4* src = reinterpret_cast<const float4*>(p.ks_partial + sp * p.ks_stride + pix * p.Cout + cbase);
+#pragma unroll
+                        for (int q = 0; q < CH / 4; ++q) {
+                            const float4 t4 = __ldg(src + q);
+                            v[q * 4 + 0] += t4.x; v[q * 4 + 1] += t4.y; v[q * 4 + 2] += t4.z; v[q * 4 + 3] += t4.w;
+                        }
+                    }
+                }
+            } else
+#endif
             {
                 uint32_t u[CH];
                 if constexpr (CH == 32) tmem_ld32(t_addr + c, u);
@@ -393,6 +439,14 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 #pragma unroll
                 for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(u[j]);
             }
+#if P2L_SPLITK
+            if constexpr (!TMA_OUT) {
+                if (KS > 1) {  // partial pass: the raw accumulator goes to this split's slice of the workspace
+                    if (valid) row_store_f32<CH>(p.ks_partial + split * p.ks_stride + pix * p.Cout + cbase, v, false);
+                    continue;
+                }
+            }
+#endif
             const bool full_chunk = (cbase + CH <= p.Cout);
 
             if constexpr (MODE == EPI_FWD) {
@@ -688,7 +742,11 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
         // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above)
         tc_fence_before();
         __syncwarp();
+#if P2L_SPLITK
+        if (lane == 0 && !ks_finish) mbar_arrive(&tempty_bar[as]);
+#else
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
+#endif
     }
     if (store_warp && elect_one()) bulk_wait0();  // shared memory must outlive the last bulk store's reads
 }
@@ -758,6 +816,68 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // makes the compiler wrap every uniform-datapath instruction (UTCHMMA / UTMALDG / UTCBAR) in an
     // ELECT + BRA.U.ANY "waterfall" loop — measured (ncu source page, profiles/r1i): the MMA warp then spends ~75 %
     // of its time in issue overhead, ~160-195 cycles per MMA instruction.
+#if P2L_SPLITK
+    const int KS = (!TMA_OUT && p.ksplit > 1) ? p.ksplit : 1;
+    const int kbs = KS > 1 ? p.ks_blocks : k_blocks;                                  // K blocks per split
+    const int work_tiles = (!TMA_OUT && p.ks_finish) ? 0 : total_tiles * KS;          // finish pass: epilogue warps only
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer, work item = (tile, K split)
+        int stage = 0;
+        uint32_t phase = 0;
+        const int tapc = p.taps_w * p.cin_chunks;
+        for (int wt = blockIdx.x; wt < work_tiles; wt += gridDim.x) {
+            const int tile = wt / KS, split = wt - tile * KS;
+            const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+            const int w0 = (m_tile % p.tiles_w) * p.tw, h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+            const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
+            const int kb0 = split * kbs, kb1 = min(k_blocks, kb0 + kbs);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int r = kb / tapc, rem = kb - r * tapc, sx = rem / p.cin_chunks, cc = rem - sx * p.cin_chunks;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + stage * Cfg::kStageBytes;
+                if (elect_one()) {
+                    mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_4d(sA, &tmA, &full_bar[stage], p.a_c0 + cc * kBK, w0 + sx - p.pad_w, h0 + r - p.pad_h, n0);
+                    tma_load_3d(sA + kATileBytes, &tmB, &full_bar[stage], (r * p.taps_w + sx) * Cin + cc * kBK, n_tile * BN,
+                                p.b_batched ? n0 : 0);
+                }
+                __syncwarp();
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_bf16(BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int wt = blockIdx.x; wt < work_tiles; wt += gridDim.x, ++it) {
+            const int split = wt % KS;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BN;
+            const int kb0 = split * kbs, kb1 = min(k_blocks, kb0 + kbs);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
+                const uint64_t adesc = umma_desc_k128(sA);
+                const uint64_t bdesc = umma_desc_k128(sA + kATileBytes);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+                    umma_commit(&empty_bar[stage]);
+                }
+                __syncwarp();
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) umma_commit(&tfull_bar[as]);
+            __syncwarp();
+        }
+    } else
+#else
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         int stage = 0;
@@ -826,7 +946,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (elect_one()) umma_commit(&tfull_bar[as]);
             __syncwarp();
         }
-    } else if (warp >= 2 + 4 * Cfg::kEpiGroups) {
+    } else
+#endif
+    if (warp >= 2 + 4 * Cfg::kEpiGroups) {
         // ------------------------------------------------------------------ epilogue-input loaders (one warp per group:
         // a single in-order loader would stall group 1's ring behind group 0's full one)
         if constexpr (TMA_OUT) {

@@ -23,6 +23,9 @@ struct ConvDesc {
     int BN = 128;
     int mode = EPI_FWD;
     ConvGemmParams epi{};  // only the epilogue fields are read from here
+    // split-K workspace (P2L_SPLITK builds with the "splitk" option): fp32 partials of launches with few tiles and long K
+    float* splitk_ws = nullptr;
+    long splitk_ws_floats = 0;
 };
 
 struct ConvOp {
@@ -32,6 +35,7 @@ struct ConvOp {
     ConvGemmParams p;
     int BN, mode, grid;
     int deep;  // one CTA per SM, full-depth pipeline (few tiles, long K)
+    int ksplit, grid_finish;  // split-K: number of K ranges (0 / 1: off), grid of the finish pass
     int halo;  // 0: per-tap A loads; 10 / 16: halo-patch kernel with that patch row pitch
     int halo_smem;  // dynamic shared memory of the halo kernel for this plan
     double flops;  // algorithmic 2*M*N*K of this launch

@@ -18,7 +18,7 @@ from pix2latent_b200 import _lib, native  # noqa: E402
 from pix2latent_b200.loss_functions import ProjectionLoss  # noqa: E402
 from pix2latent_b200.model import BigGAN, synth  # noqa: E402
 
-DEFAULTS = {"attn_fused": 0, "pdl": 1, "deep": 1, "deep_kmin": 8, "tma_out": 1, "tma_kmax": 512, "halo_mode": 1, "halo": 10}
+DEFAULTS = {"splitk": 0, "attn_fused": 0, "pdl": 1, "deep": 1, "deep_kmin": 8, "tma_out": 1, "tma_kmax": 512, "halo_mode": 1, "halo": 10}
 
 
 def run(cfg, sd, lp_sd, steps=20):
