@@ -38,7 +38,7 @@ typedef struct p2l_conv_args {
     /* backward epilogue */
     const void* saved;
     int saved_C;
-    float* stat0;
+    float* stat0; /* [NI, stat_stride]: sum_pix dpre, sum_pix dpre*saved (overwritten; summed in a fixed order) */
     float* stat1;
     int stat_stride;
     const void* addin;
@@ -47,16 +47,19 @@ typedef struct p2l_conv_args {
     int dx_C;
     float* dx_f32;
     int dx_f32_C;
-    /* forward epilogue, row-wise softmax fusions (need a -DP2L_ROWFUSE=1 build) */
+    /* forward epilogue, row-wise softmax fusions (attention) */
     float* rowstat;
     const float* rowstat_in;
     int rowstat_nt;
     const float* rowsub;
     const void* mulin;
     int mulin_C;
-    /* split-K workspace (needs a -DP2L_SPLITK=1 build and the "splitk" option) */
+    /* split-K workspace (used when the "splitk" option is on) */
     float* splitk_ws;
     long splitk_ws_floats;
+    /* transposed 16-bit copy of the main output (fwd: raw, bwd: dx), channels [outT_c0, outT_c1): [NI][c][H*W] */
+    void* outT;
+    int outT_c0, outT_c1;
 } p2l_conv_args;
 
 /* returns 0 on success, <0 on error (see p2l_last_error) */

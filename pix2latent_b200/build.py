@@ -53,13 +53,7 @@ def _compile(src, force, hdr_m):
     return obj, True
 
 
-def build(force=False, verbose=True, rowfuse=False, prefetch_saved=False, splitk=False):
-    """rowfuse / prefetch_saved: compile the prepared (not yet GPU-validated) row-wise softmax fusions
-    (-DP2L_ROWFUSE=1) / saved-activation prefetch of the backward epilogue (-DP2L_PREFETCH_SAVED=1) in"""
-    for on, flag in ((rowfuse, "-DP2L_ROWFUSE=1"), (prefetch_saved, "-DP2L_PREFETCH_SAVED=1"), (splitk, "-DP2L_SPLITK=1")):
-        if on and flag not in FLAGS:
-            FLAGS.append(flag)
-            force = True
+def build(force=False, verbose=True):
     os.makedirs(OBJ, exist_ok=True)
     # objects built with other flags (e.g. a --rowfuse build) are stale whatever their timestamps say
     stamp = os.path.join(OBJ, "flags.txt")
@@ -88,5 +82,4 @@ def build(force=False, verbose=True, rowfuse=False, prefetch_saved=False, splitk
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, rowfuse="--rowfuse" in sys.argv, prefetch_saved="--prefetch-saved" in sys.argv,
-          splitk="--splitk" in sys.argv)
+    build(force="--force" in sys.argv)

@@ -2,6 +2,9 @@
 #include "p2l_debug.h"
 
 #include "conv_gemm.h"
+#include "kernels.h"
+
+#include <vector>
 
 #define P2L_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -23,7 +26,16 @@ P2L_EXPORT int p2l_debug_conv(const p2l_conv_args* a, void* cuda_stream) {
     e.act = static_cast<act_t*>(a->act); e.act_C = a->act_C; e.act_up = a->act_up;
     e.act_lo = static_cast<act_t*>(a->act_lo); e.img_nchw = a->img_nchw;
     e.saved = static_cast<const act_t*>(a->saved); e.saved_C = a->saved_C;
-    e.stat0 = a->stat0; e.stat1 = a->stat1; e.stat_stride = a->stat_stride;
+    // BN-gradient sums: the kernel fills per-tile partial slots (ConvGemmParams::statp); this entry point keeps the
+    // (stat0, stat1, stat_stride) view of the result by running the fixed-order reduction itself
+    float* statp = nullptr;
+    StatSeg* dsegs = nullptr;
+    const int parts = conv_stat_parts_max(a->H, a->W);
+    if (a->stat0 && a->stat1) {
+        if (cudaMalloc(&statp, (size_t)a->NI * parts * 2 * a->Cout * sizeof(float)) != cudaSuccess) { set_error("debug_conv: cudaMalloc failed"); return -1; }
+        e.statp = statp; e.statp_parts = parts; e.statp_C = a->Cout;
+    }
+    e.outT = static_cast<act_t*>(a->outT); e.outT_c0 = a->outT_c0; e.outT_c1 = a->outT_c1;
     e.addin = static_cast<const act_t*>(a->addin); e.addin_C = a->addin_C;
     e.addin_climit = a->addin_climit; e.addin_pool = a->addin_pool;
     e.dx = static_cast<act_t*>(a->dx); e.dx_C = a->dx_C;
@@ -32,8 +44,27 @@ P2L_EXPORT int p2l_debug_conv(const p2l_conv_args* a, void* cuda_stream) {
     e.rowsub = a->rowsub; e.mulin = static_cast<const act_t*>(a->mulin); e.mulin_C = a->mulin_C;
     d.splitk_ws = a->splitk_ws; d.splitk_ws_floats = a->splitk_ws_floats;
     ConvOp op;
-    if (conv_op_build(&op, d)) return -1;
-    return conv_op_launch(op, static_cast<cudaStream_t>(cuda_stream));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int rc = conv_op_build(&op, d);
+    if (rc == 0) rc = conv_op_launch(op, st);
+    if (rc == 0 && statp) {
+        if (a->Cout % 32) { set_error("debug_conv: statistics need Cout %% 32 == 0"); rc = -1; }
+        else {
+            std::vector<StatSeg> segs;
+            for (int c0 = 0; c0 < a->Cout; c0 += 32) segs.push_back({statp, op.stat_parts, parts, a->Cout, 0, c0});
+            if (cudaMalloc(&dsegs, segs.size() * sizeof(StatSeg)) != cudaSuccess) { set_error("debug_conv: cudaMalloc failed"); rc = -1; }
+            else {
+                cudaMemcpyAsync(dsegs, segs.data(), segs.size() * sizeof(StatSeg), cudaMemcpyHostToDevice, st);
+                k_stat_reduce(dsegs, (int)segs.size(), a->stat0, a->stat1, a->stat_stride, a->NI, st);
+            }
+        }
+    }
+    if (statp || dsegs) {
+        cudaStreamSynchronize(st);
+        cudaFree(statp);
+        cudaFree(dsegs);
+    }
+    return rc;
 }
 
 P2L_EXPORT const char* p2l_last_error(void) { return get_error(); }

@@ -22,11 +22,20 @@ struct BigGANPlan {
     // latent side
     float *cond = nullptr, *a = nullptr, *s = nullptr, *S0 = nullptr, *S1 = nullptr, *G = nullptr, *dcond = nullptr,
           *dh0 = nullptr, *ones = nullptr;
+    struct Sub { int n0, ns; };  // candidates [n0, n0 + ns) of the batch
     struct BB {
         act_t *in_raw, *in_act, *t1_lo, *t1, *t2, *t3, *out_raw, *out_act;
-        ConvOp f[4], d[4];
+        // L2-resident sub-batching ("sub_mb" option): the block's launches run sub-batch by sub-batch, so that what
+        // one convolution writes is still in the 126 MB L2 when the next one reads it
+        std::vector<Sub> subs;
+        std::vector<ConvOp> f[4], d[4];  // [conv][sub-batch]
+        // BN-affine gradient partial sums of bn_0..bn_3 ([n][part][2][C], ConvGemmParams::statp)
+        float* sp[4] = {nullptr, nullptr, nullptr, nullptr};
+        int sp_parts[4] = {0, 0, 0, 0};
     };
     std::vector<BB> bb;
+    StatSeg* segs = nullptr;  // device table for k_stat_reduce
+    int nsegs = 0;
     // attention
     act_t *qkv = nullptr, *phi_p = nullptr, *phiT = nullptr, *g_p = nullptr, *gT = nullptr, *P = nullptr,
                   *O = nullptr, *attn_raw = nullptr, *attn_act = nullptr;
@@ -35,10 +44,11 @@ struct BigGANPlan {
     act_t *dO = nullptr, *dOT = nullptr, *dS = nullptr, *dST = nullptr, *PT = nullptr, *thetaT = nullptr,
                   *dqkv = nullptr, *dphi_p = nullptr, *dg_p = nullptr;
     ConvOp a_qkv, a_s, a_o, a_out, ad_out, ad_p, ad_theta, ad_phi, ad_g, ad_qkv;
-    // "attn_fused" (prepared, unvalidated): two-pass softmax in the S GEMM's epilogue, dS in the dP GEMM's epilogue
-    float* ks_ws = nullptr;  // split-K workspace ("splitk" option, P2L_SPLITK builds)
+    float* ks_ws = nullptr;  // split-K workspace ("splitk" option)
     long ks_ws_floats = 0;
-    bool attn_fused = false;
+    // "attn_fused": two-pass softmax in the S GEMM's epilogue, dS in the dP GEMM's epilogue (no fp32 logits in HBM);
+    // "attn_emit_t" (needs attn_fused): theta^T, P^T, dO^T, dS^T come out of the producing epilogues (no transposes)
+    bool attn_fused = false, attn_emit_t = false;
     ConvOp a_s1, a_s2, ad_pf;
     float *rowstat = nullptr, *Drow = nullptr;
     // image
@@ -288,6 +298,34 @@ struct OpB {  // small builder
     }
 };
 
+// Sub-batches of one block: sized so that the largest working set of its four convolutions (operand + outputs + skip,
+// per candidate) fits `sub_mb` MB of L2, but never so small that a launch has fewer than `min_tiles` 128-pixel tiles
+// (a partial last wave would cost more than the HBM traffic saved). Near-even split.
+static std::vector<BigGANPlan::Sub> pick_subs(int b, int in, int mid, int out, int Hin, int Hout, bool up, int sub_mb, int min_tiles) {
+    std::vector<BigGANPlan::Sub> v;
+    int nsub = 1;
+    if (sub_mb > 0) {
+        const double pin = (double)Hin * Hin, pout = (double)Hout * Hout;
+        const double w0 = pin * in + pout * mid + (up ? pin * mid : 0.0);
+        const double w1 = 2.0 * pout * mid;
+        const double w3 = pout * mid + pin * out + 2.0 * pout * out;
+        const double ws = 2.0 * std::max(w0, std::max(w1, w3));  // bytes per candidate
+        long sub = (long)(sub_mb * 1048576.0 / ws);
+        const long tiles_per = ((long)Hout * Hout + 127) / 128;
+        const long min_sub = (min_tiles + tiles_per - 1) / tiles_per;
+        if (sub < min_sub) sub = min_sub;
+        if (sub < 1) sub = 1;
+        if (sub < b) nsub = (int)((b + sub - 1) / sub);
+    }
+    int n0 = 0;
+    for (int k = 0; k < nsub; ++k) {
+        const int ns = b / nsub + (k < b % nsub ? 1 : 0);
+        v.push_back({n0, ns});
+        n0 += ns;
+    }
+    return v;
+}
+
 BigGANPlan* BigGAN::plan(int b) {
     auto it = plans.find(b);
     if (it != plans.end()) return it->second.get();
@@ -307,6 +345,7 @@ BigGANPlan* BigGAN::plan(int b) {
     const int nL = (int)blocks.size();
     P.bb.resize(nL);
     size_t max_dh = 0, max_g = 0;
+    const int sub_mb = get_option("sub_mb"), sub_min_tiles = get_option("sub_min_tiles");
     // activations
     act_t *cur_raw = ar.alloc<bf>((size_t)b * genz_J), *cur_act = ar.alloc<bf>((size_t)b * genz_J);
     for (int i = 0; i < nL; ++i) {
@@ -333,6 +372,14 @@ BigGANPlan* BigGAN::plan(int b) {
         cur_act = B.out_act;
         max_dh = std::max(max_dh, std::max(pout * bl.out, pin * bl.in));
         max_g = std::max(max_g, pout * bl.mid);
+        B.subs = pick_subs(b, bl.in, bl.mid, bl.out, bl.Hin, bl.Hout, bl.up, sub_mb, sub_min_tiles);
+        // BN-gradient partial buffers: bn_0 is filled by d0 (input grid), bn_1 by d1 (or the pooling kernel of an up
+        // block, input grid), bn_2 / bn_3 by d2 / d3 (output grid)
+        const int cs[4] = {bl.in, bl.mid, bl.mid, bl.mid};
+        B.sp_parts[0] = conv_stat_parts_max(bl.Hin, bl.Hin);
+        B.sp_parts[1] = bl.up ? k_pool_bnrelu_parts(bl.Hin, bl.Hin) : conv_stat_parts_max(bl.Hout, bl.Hout);
+        B.sp_parts[2] = B.sp_parts[3] = conv_stat_parts_max(bl.Hout, bl.Hout);
+        for (int k = 0; k < 4; ++k) B.sp[k] = ar.alloc<float>((size_t)b * B.sp_parts[k] * 2 * cs[k]);
     }
     P.dhA = ar.alloc<bf>(max_dh);
     P.dhB = ar.alloc<bf>(max_dh);
@@ -346,7 +393,7 @@ BigGANPlan* BigGAN::plan(int b) {
     P.rgbT = ar.alloc<float>((size_t)b * 27 * R * R);
     if (ar.failed) return nullptr;
 
-    if (get_option("splitk") > 0 && get_option("splitk_built") > 0) {
+    if (get_option("splitk") > 0) {
         P.ks_ws_floats = 16L << 20;  // 64 MB: 8 splits of the largest eligible launch (M = 1152, N = 2048)
         P.ks_ws = ar.alloc<float>((size_t)P.ks_ws_floats);
         if (ar.failed) return nullptr;
@@ -359,99 +406,124 @@ BigGANPlan* BigGAN::plan(int b) {
         *launches += 1;
         return 0;
     };
-    // ---- per-block ops
+    std::vector<StatSeg> segs;
+    // ---- per-block ops, one set per sub-batch (every pointer below is offset to the sub-batch's first candidate)
     for (int i = 0; i < nL; ++i) {
         const Block& bl = blocks[i];
         BigGANPlan::BB& B = P.bb[i];
         const int Hi = bl.Hin, Ho = bl.Hout;
+        const size_t pi = (size_t)Hi * Hi, po = (size_t)Ho * Ho;  // pixels per candidate
         const bool attn_next = attn.C && (i + 1 == cfg.attention_pos);
         const int next_bn = (i + 1 < nL) ? blocks[i + 1].bn[0] : final_bn;
-        {   // f0: 1x1 in->mid on in_act; epilogue bn_1+relu (+x2 replicate)
-            OpB o(B.in_act, b, Hi, Hi, bl.in, 0, bl.in, bl.w[0], bl.mid, 1, EPI_FWD);
-            ConvGemmParams& e = o.d.epi;
-            e.bias = bl.bias[0];
-            e.aff_a = P.a + bns[bl.bn[1]].off; e.aff_s = P.s + bns[bl.bn[1]].off; e.aff_stride = C_all; e.relu = 1;
-            e.act = B.t1; e.act_C = bl.mid; e.act_up = bl.up ? 1 : 0; e.act_lo = bl.up ? B.t1_lo : nullptr;
-            if (build(&B.f[0], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
-        }
-        {   // f1: 3x3 mid->mid
-            OpB o(B.t1, b, Ho, Ho, bl.mid, 0, bl.mid, bl.w[1], bl.mid, 3, EPI_FWD);
-            ConvGemmParams& e = o.d.epi;
-            e.bias = bl.bias[1];
-            e.aff_a = P.a + bns[bl.bn[2]].off; e.aff_s = P.s + bns[bl.bn[2]].off; e.aff_stride = C_all; e.relu = 1;
-            e.act = B.t2; e.act_C = bl.mid;
-            if (build(&B.f[1], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
-        }
-        {   // f2
-            OpB o(B.t2, b, Ho, Ho, bl.mid, 0, bl.mid, bl.w[2], bl.mid, 3, EPI_FWD);
-            ConvGemmParams& e = o.d.epi;
-            e.bias = bl.bias[2];
-            e.aff_a = P.a + bns[bl.bn[3]].off; e.aff_s = P.s + bns[bl.bn[3]].off; e.aff_stride = C_all; e.relu = 1;
-            e.act = B.t3; e.act_C = bl.mid;
-            if (build(&B.f[2], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
-        }
-        {   // f3: 1x1 mid->out + skip; raw; next BN + relu
-            OpB o(B.t3, b, Ho, Ho, bl.mid, 0, bl.mid, bl.w[3], bl.out, 1, EPI_FWD);
-            ConvGemmParams& e = o.d.epi;
-            e.bias = bl.bias[3];
-            e.resid = B.in_raw; e.resid_C = bl.in; e.resid_shift = bl.up ? 1 : 0;
-            // the raw (pre-BN) output feeds the next block's skip / the attention; after the last block
-            // nothing reads it
-            if (i + 1 < nL) { e.raw = B.out_raw; e.raw_C = bl.out; }
-            if (!attn_next) {
-                e.aff_a = P.a + bns[next_bn].off; e.aff_s = P.s + bns[next_bn].off; e.aff_stride = C_all; e.relu = 1;
-                e.act = B.out_act; e.act_C = bl.out;
-            }
-            if (build(&B.f[3], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
-        }
-        // ---- backward ops (dh_out lives in dhA when (nL-1-i) is even, dh_in goes to the other)
-        act_t* dh_out = ((nL - 1 - i) % 2 == 0) ? P.dhA : P.dhB;
+        act_t* dh_out = ((nL - 1 - i) % 2 == 0) ? P.dhA : P.dhB;  // dh_out lives in dhA when (nL-1-i) is even, dh_in goes to the other
         act_t* dh_in = ((nL - 1 - i) % 2 == 0) ? P.dhB : P.dhA;
-        {   // d3: dh_out -> g3 (through bn_3/relu)
-            OpB o(dh_out, b, Ho, Ho, bl.out, 0, bl.out, bl.wt[3], bl.mid, 1, EPI_BWD);
-            ConvGemmParams& e = o.d.epi;
-            e.saved = B.t3; e.saved_C = bl.mid;
-            e.stat0 = P.S0 + bns[bl.bn[3]].off; e.stat1 = P.S1 + bns[bl.bn[3]].off; e.stat_stride = C_all;
-            e.aff_a = P.a + bns[bl.bn[3]].off; e.aff_stride = C_all;
-            e.dx = P.g3; e.dx_C = bl.mid;
-            if (build(&B.d[3], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
-        }
-        {   // d2: g3 -> g2 (through bn_2/relu)
-            OpB o(P.g3, b, Ho, Ho, bl.mid, 0, bl.mid, bl.wt[2], bl.mid, 3, EPI_BWD);
-            ConvGemmParams& e = o.d.epi;
-            e.saved = B.t2; e.saved_C = bl.mid;
-            e.stat0 = P.S0 + bns[bl.bn[2]].off; e.stat1 = P.S1 + bns[bl.bn[2]].off; e.stat_stride = C_all;
-            e.aff_a = P.a + bns[bl.bn[2]].off; e.aff_stride = C_all;
-            e.dx = P.g2; e.dx_C = bl.mid;
-            if (build(&B.d[2], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
-        }
-        {   // d1: g2 -> g1 (bn_1/relu; through the x2 upsample when bl.up: plain dgrad into g3, pooled later)
-            OpB o(P.g2, b, Ho, Ho, bl.mid, 0, bl.mid, bl.wt[1], bl.mid, 3, EPI_BWD);
-            ConvGemmParams& e = o.d.epi;
-            if (!bl.up) {
-                e.saved = B.t1_lo; e.saved_C = bl.mid;
-                e.stat0 = P.S0 + bns[bl.bn[1]].off; e.stat1 = P.S1 + bns[bl.bn[1]].off; e.stat_stride = C_all;
-                e.aff_a = P.a + bns[bl.bn[1]].off; e.aff_stride = C_all;
-                e.dx = P.g1; e.dx_C = bl.mid;
-            } else {
-                e.dx = P.g3; e.dx_C = bl.mid;  // g3 is free again: holds the hi-res gradient
-                P.launches_bwd += 1;           // + k_pool_bnrelu_bwd
+        const int nsub = (int)B.subs.size();
+        for (int k = 0; k < 4; ++k) { B.f[k].resize(nsub); B.d[k].resize(nsub); }
+        int parts_used[4] = {0, 0, 0, 0};
+        for (int si = 0; si < nsub; ++si) {
+            const int n0 = B.subs[si].n0, ns = B.subs[si].ns;
+            const float* aff_a = P.a + (size_t)n0 * C_all;
+            const float* aff_s = P.s + (size_t)n0 * C_all;
+            auto stat = [&](ConvGemmParams& e, int k, int C) {
+                e.statp = B.sp[k] + (size_t)n0 * B.sp_parts[k] * 2 * C; e.statp_parts = B.sp_parts[k]; e.statp_C = C;
+            };
+            {   // f0: 1x1 in->mid on in_act; epilogue bn_1+relu (+x2 replicate)
+                OpB o(B.in_act + n0 * pi * bl.in, ns, Hi, Hi, bl.in, 0, bl.in, bl.w[0], bl.mid, 1, EPI_FWD);
+                ConvGemmParams& e = o.d.epi;
+                e.bias = bl.bias[0];
+                e.aff_a = aff_a + bns[bl.bn[1]].off; e.aff_s = aff_s + bns[bl.bn[1]].off; e.aff_stride = C_all; e.relu = 1;
+                e.act = B.t1 + n0 * po * bl.mid; e.act_C = bl.mid; e.act_up = bl.up ? 1 : 0;
+                e.act_lo = bl.up ? B.t1_lo + n0 * pi * bl.mid : nullptr;
+                if (build(&B.f[0][si], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
             }
-            if (build(&B.d[1], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
+            {   // f1: 3x3 mid->mid
+                OpB o(B.t1 + n0 * po * bl.mid, ns, Ho, Ho, bl.mid, 0, bl.mid, bl.w[1], bl.mid, 3, EPI_FWD);
+                ConvGemmParams& e = o.d.epi;
+                e.bias = bl.bias[1];
+                e.aff_a = aff_a + bns[bl.bn[2]].off; e.aff_s = aff_s + bns[bl.bn[2]].off; e.aff_stride = C_all; e.relu = 1;
+                e.act = B.t2 + n0 * po * bl.mid; e.act_C = bl.mid;
+                if (build(&B.f[1][si], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
+            }
+            {   // f2
+                OpB o(B.t2 + n0 * po * bl.mid, ns, Ho, Ho, bl.mid, 0, bl.mid, bl.w[2], bl.mid, 3, EPI_FWD);
+                ConvGemmParams& e = o.d.epi;
+                e.bias = bl.bias[2];
+                e.aff_a = aff_a + bns[bl.bn[3]].off; e.aff_s = aff_s + bns[bl.bn[3]].off; e.aff_stride = C_all; e.relu = 1;
+                e.act = B.t3 + n0 * po * bl.mid; e.act_C = bl.mid;
+                if (build(&B.f[2][si], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
+            }
+            {   // f3: 1x1 mid->out + skip; raw; next BN + relu
+                OpB o(B.t3 + n0 * po * bl.mid, ns, Ho, Ho, bl.mid, 0, bl.mid, bl.w[3], bl.out, 1, EPI_FWD);
+                ConvGemmParams& e = o.d.epi;
+                e.bias = bl.bias[3];
+                e.resid = B.in_raw + n0 * pi * bl.in; e.resid_C = bl.in; e.resid_shift = bl.up ? 1 : 0;
+                // the raw (pre-BN) output feeds the next block's skip / the attention; after the last block
+                // nothing reads it
+                if (i + 1 < nL) { e.raw = B.out_raw + n0 * po * bl.out; e.raw_C = bl.out; }
+                if (!attn_next) {
+                    e.aff_a = aff_a + bns[next_bn].off; e.aff_s = aff_s + bns[next_bn].off; e.aff_stride = C_all; e.relu = 1;
+                    e.act = B.out_act + n0 * po * bl.out; e.act_C = bl.out;
+                }
+                if (build(&B.f[3][si], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
+            }
+            // ---- backward ops
+            {   // d3: dh_out -> g3 (through bn_3/relu)
+                OpB o(dh_out + n0 * po * bl.out, ns, Ho, Ho, bl.out, 0, bl.out, bl.wt[3], bl.mid, 1, EPI_BWD);
+                ConvGemmParams& e = o.d.epi;
+                e.saved = B.t3 + n0 * po * bl.mid; e.saved_C = bl.mid;
+                stat(e, 3, bl.mid);
+                e.aff_a = aff_a + bns[bl.bn[3]].off; e.aff_stride = C_all;
+                e.dx = P.g3 + n0 * po * bl.mid; e.dx_C = bl.mid;
+                if (build(&B.d[3][si], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
+                parts_used[3] = B.d[3][si].stat_parts;
+            }
+            {   // d2: g3 -> g2 (through bn_2/relu)
+                OpB o(P.g3 + n0 * po * bl.mid, ns, Ho, Ho, bl.mid, 0, bl.mid, bl.wt[2], bl.mid, 3, EPI_BWD);
+                ConvGemmParams& e = o.d.epi;
+                e.saved = B.t2 + n0 * po * bl.mid; e.saved_C = bl.mid;
+                stat(e, 2, bl.mid);
+                e.aff_a = aff_a + bns[bl.bn[2]].off; e.aff_stride = C_all;
+                e.dx = P.g2 + n0 * po * bl.mid; e.dx_C = bl.mid;
+                if (build(&B.d[2][si], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
+                parts_used[2] = B.d[2][si].stat_parts;
+            }
+            {   // d1: g2 -> g1 (bn_1/relu; through the x2 upsample when bl.up: plain dgrad into g3, pooled later)
+                OpB o(P.g2 + n0 * po * bl.mid, ns, Ho, Ho, bl.mid, 0, bl.mid, bl.wt[1], bl.mid, 3, EPI_BWD);
+                ConvGemmParams& e = o.d.epi;
+                if (!bl.up) {
+                    e.saved = B.t1_lo + n0 * pi * bl.mid; e.saved_C = bl.mid;
+                    stat(e, 1, bl.mid);
+                    e.aff_a = aff_a + bns[bl.bn[1]].off; e.aff_stride = C_all;
+                    e.dx = P.g1 + n0 * pi * bl.mid; e.dx_C = bl.mid;
+                } else {
+                    e.dx = P.g3 + n0 * po * bl.mid; e.dx_C = bl.mid;  // g3 is free again: holds the hi-res gradient
+                    P.launches_bwd += 1;           // + k_pool_bnrelu_bwd
+                }
+                if (build(&B.d[1][si], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
+                parts_used[1] = bl.up ? B.sp_parts[1] : B.d[1][si].stat_parts;
+            }
+            {   // d0: g1 -> dh_in (bn_0/relu) + skip gradient
+                OpB o(P.g1 + n0 * pi * bl.mid, ns, Hi, Hi, bl.mid, 0, bl.mid, bl.wt[0], bl.in, 1, EPI_BWD);
+                ConvGemmParams& e = o.d.epi;
+                e.saved = B.in_act + n0 * pi * bl.in; e.saved_C = bl.in;
+                stat(e, 0, bl.in);
+                e.aff_a = aff_a + bns[bl.bn[0]].off; e.aff_stride = C_all;
+                // skip gradient: dh_out itself, or (up block) its 2x2-pooled copy written by k_pool2x2_sum
+                e.addin = bl.up ? P.dh_pool + n0 * pi * bl.out : dh_out + n0 * po * bl.out;
+                e.addin_C = bl.out; e.addin_climit = bl.out; e.addin_pool = 0;
+                e.dx = dh_in + n0 * pi * bl.in; e.dx_C = bl.in;
+                if (i == 0) { e.dx_f32 = P.dh0 + n0 * pi * bl.in; e.dx_f32_C = bl.in; }
+                if (build(&B.d[0][si], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
+                parts_used[0] = B.d[0][si].stat_parts;
+            }
         }
-        {   // d0: g1 -> dh_in (bn_0/relu) + skip gradient
-            OpB o(P.g1, b, Hi, Hi, bl.mid, 0, bl.mid, bl.wt[0], bl.in, 1, EPI_BWD);
-            ConvGemmParams& e = o.d.epi;
-            e.saved = B.in_act; e.saved_C = bl.in;
-            e.stat0 = P.S0 + bns[bl.bn[0]].off; e.stat1 = P.S1 + bns[bl.bn[0]].off; e.stat_stride = C_all;
-            e.aff_a = P.a + bns[bl.bn[0]].off; e.aff_stride = C_all;
-            // skip gradient: dh_out itself, or (up block) its 2x2-pooled copy written by k_pool2x2_sum
-            e.addin = bl.up ? P.dh_pool : dh_out; e.addin_C = bl.out; e.addin_climit = bl.out; e.addin_pool = 0;
-            e.dx = dh_in; e.dx_C = bl.in;
-            if (i == 0) { e.dx_f32 = P.dh0; e.dx_f32_C = bl.in; }
-            if (build(&B.d[0], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
-        }
+        const int cs[4] = {bl.in, bl.mid, bl.mid, bl.mid};
+        for (int k = 0; k < 4; ++k)
+            for (int c0 = 0; c0 < cs[k]; c0 += 32) segs.push_back({B.sp[k], parts_used[k], B.sp_parts[k], cs[k], bns[bl.bn[k]].off, c0});
     }
+    P.nsegs = (int)segs.size();
+    P.segs = upload(ar, segs);
+    if (ar.failed) return nullptr;
     // ---- attention ops
     if (attn.C) {
         const int ap = cfg.attention_pos;
@@ -482,9 +554,12 @@ BigGANPlan* BigGAN::plan(int b) {
         const int Hk = H / 2;
         P.launches_fwd += 3;  // 2 pools + softmax
         P.launches_bwd += 8;  // transposes x4, softmax bwd, pool bwd x2 ... (counted below as launched)
+        P.attn_fused = get_option("attn_fused") != 0;
+        P.attn_emit_t = P.attn_fused && get_option("attn_emit_t") != 0;
         {   // qkv = x W_qkv^T
             OpB o(x_raw, b, H, H, C, 0, C, attn.wqkv, nq, 1, EPI_FWD);
             o.d.epi.raw = P.qkv; o.d.epi.raw_C = nq;
+            if (P.attn_emit_t) { o.d.epi.outT = P.thetaT; o.d.epi.outT_c0 = 0; o.d.epi.outT_c1 = dq; }
             if (build(&P.a_qkv, o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
         }
         {   // S = theta phi_p^T (fp32)
@@ -492,7 +567,6 @@ BigGANPlan* BigGAN::plan(int b) {
             o.d.B_batch = b; o.d.epi.raw_f32 = P.S; o.d.epi.raw_f32_C = Nk;
             if (build(&P.a_s, o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
         }
-        P.attn_fused = get_option("attn_fused") != 0;
         if (P.attn_fused) {
             // pass 1: per-row (max, sum exp) of every N tile of S = theta phi_p^T; pass 2: P = exp(S - M) / L, 16-bit.
             // The fp32 logits never reach HBM (2 x 302 MB per step at the bench shape) and k_softmax_fwd goes away.
@@ -508,12 +582,14 @@ BigGANPlan* BigGAN::plan(int b) {
             o2.d.B_batch = b; o2.d.BN = o1.d.BN;
             o2.d.epi.rowstat_in = P.rowstat; o2.d.epi.rowstat_nt = nt;
             o2.d.epi.raw = P.P; o2.d.epi.raw_C = Nk;
+            if (P.attn_emit_t) { o2.d.epi.outT = P.PT; o2.d.epi.outT_c0 = 0; o2.d.epi.outT_c1 = Nk; }
             if (build(&P.a_s2, o2, &P.flops_fwd, &P.launches_fwd)) return nullptr;
             // dS = P o (dO g_p^T - rowsum(dO o O)) straight out of the dP GEMM (k_softmax_bwd and the fp32 dP go away)
             OpB o3(P.dO, b, H, H, dv, 0, dv, P.g_p, Nk, 1, EPI_FWD);
             o3.d.B_batch = b;
             o3.d.epi.rowsub = P.Drow; o3.d.epi.mulin = P.P; o3.d.epi.mulin_C = Nk;
             o3.d.epi.raw = P.dS; o3.d.epi.raw_C = Nk;
+            if (P.attn_emit_t) { o3.d.epi.outT = P.dST; o3.d.epi.outT_c0 = 0; o3.d.epi.outT_c1 = Nk; }
             if (build(&P.ad_pf, o3, &P.flops_bwd, &P.launches_bwd)) return nullptr;
         }
         {   // O = P g_p
@@ -541,6 +617,7 @@ BigGANPlan* BigGAN::plan(int b) {
         {   // dO = gamma * dh W_o
             OpB o(dh_attn_out, b, H, H, C, 0, C, attn.wo_t, dv, 1, EPI_BWD);
             o.d.epi.alpha_ptr = attn.gamma; o.d.epi.dx = P.dO; o.d.epi.dx_C = dv;
+            if (P.attn_emit_t) { o.d.epi.outT = P.dOT; o.d.epi.outT_c0 = 0; o.d.epi.outT_c1 = dv; }
             if (build(&P.ad_out, o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
         }
         {   // dP = dO g_p^T (fp32, reuses S)
@@ -628,8 +705,10 @@ int BigGAN::forward(int b, const float* z, const float* c, float* img, cudaStrea
             if (conv_op_launch(P.a_o, st)) return -1;
             if (conv_op_launch(P.a_out, st)) return -1;
         }
-        for (int k = 0; k < 4; ++k)
-            if (conv_op_launch(P.bb[i].f[k], st)) return -1;
+        const BigGANPlan::BB& B = P.bb[i];
+        for (size_t si = 0; si < B.subs.size(); ++si)
+            for (int k = 0; k < 4; ++k)
+                if (conv_op_launch(B.f[k][si], st)) return -1;
     }
     if (conv_op_launch(P.f_rgb, st)) return -1;
     k_rgb_gather(P.rgbT, brgb, img ? img : P.img, b, H_out, H_out, st);
@@ -653,27 +732,28 @@ int BigGAN::backward(int b, const float* dimg, float* dz, float* dc, cudaStream_
     BigGANPlan& P = *it->second;
     const int nL = (int)blocks.size();
     const int R = H_out;
-    P2L_CUDA_CHECK(cudaMemsetAsync(P.S0, 0, (size_t)b * C_all * sizeof(float), st));
-    P2L_CUDA_CHECK(cudaMemsetAsync(P.S1, 0, (size_t)b * C_all * sizeof(float), st));
     // image -> last block output
     k_im2col_rgb_bwd(dimg, P.img, P.col_rgb, b, R, R, 64, grad_scale(), st);  // 16-bit gradients carry grad_scale() from here ...
     if (conv_op_launch(P.d_rgb, st)) return -1;
     for (int i = nL - 1; i >= 0; --i) {
         const Block& bl = blocks[i];
         BigGANPlan::BB& B = P.bb[i];
-        if (conv_op_launch(B.d[3], st)) return -1;
-        if (conv_op_launch(B.d[2], st)) return -1;
-        if (conv_op_launch(B.d[1], st)) return -1;
-        if (bl.up) {
-            const BN& bn1 = bns[bl.bn[1]];
-            k_pool_bnrelu_bwd(P.g3, B.t1_lo, P.a + bn1.off, C_all, P.S0 + bn1.off, P.S1 + bn1.off, C_all, P.g1, b, bl.Hin,
-                              bl.Hin, bl.mid, st);
+        const size_t pi = (size_t)bl.Hin * bl.Hin, po = (size_t)bl.Hout * bl.Hout;
+        for (size_t si = 0; si < B.subs.size(); ++si) {
+            const int n0 = B.subs[si].n0, ns = B.subs[si].ns;
+            if (conv_op_launch(B.d[3][si], st)) return -1;
+            if (conv_op_launch(B.d[2][si], st)) return -1;
+            if (conv_op_launch(B.d[1][si], st)) return -1;
+            if (bl.up) {
+                const BN& bn1 = bns[bl.bn[1]];
+                k_pool_bnrelu_bwd(P.g3 + n0 * po * bl.mid, B.t1_lo + n0 * pi * bl.mid, P.a + (size_t)n0 * C_all + bn1.off, C_all,
+                                  B.sp[1] + (size_t)n0 * B.sp_parts[1] * 2 * bl.mid, P.g1 + n0 * pi * bl.mid, ns, bl.Hin, bl.Hin,
+                                  bl.mid, st);
+                act_t* dh_out = ((nL - 1 - i) % 2 == 0) ? P.dhA : P.dhB;
+                k_pool2x2_sum(dh_out + n0 * po * bl.out, bl.out, P.dh_pool + n0 * pi * bl.out, ns, bl.Hin, bl.Hin, bl.out, st);
+            }
+            if (conv_op_launch(B.d[0][si], st)) return -1;
         }
-        if (bl.up) {
-            act_t* dh_out = ((nL - 1 - i) % 2 == 0) ? P.dhA : P.dhB;
-            k_pool2x2_sum(dh_out, bl.out, P.dh_pool, b, bl.Hin, bl.Hin, bl.out, st);
-        }
-        if (conv_op_launch(B.d[0], st)) return -1;
         if (attn.C && i == cfg.attention_pos) {
             const int H = attn.H, dq = attn.dq, dv = attn.dv, nq = 2 * dq + dv;
             const int Nq = H * H, Nk = Nq / 4;
@@ -686,18 +766,23 @@ int BigGAN::backward(int b, const float* dimg, float* dz, float* dc, cudaStream_
                 k_softmax_bwd(P.P, P.S, P.dS, (long)b * Nq, Nk, st);  // dS
             }
             if (conv_op_launch(P.ad_theta, st)) return -1;            // dtheta -> dqkv[:, :dq]
-            k_transpose(P.dS, Nk, 0, P.dST, b, Nq, Nk, st);
-            k_transpose(P.qkv, nq, 0, P.thetaT, b, Nq, dq, st);
+            if (!P.attn_emit_t) {
+                k_transpose(P.dS, Nk, 0, P.dST, b, Nq, Nk, st);
+                k_transpose(P.qkv, nq, 0, P.thetaT, b, Nq, dq, st);
+            }
             if (conv_op_launch(P.ad_phi, st)) return -1;              // dphi_p
-            k_transpose(P.P, Nk, 0, P.PT, b, Nq, Nk, st);
-            k_transpose(P.dO, dv, 0, P.dOT, b, Nq, dv, st);
+            if (!P.attn_emit_t) {
+                k_transpose(P.P, Nk, 0, P.PT, b, Nq, Nk, st);
+                k_transpose(P.dO, dv, 0, P.dOT, b, Nq, dv, st);
+            }
             if (conv_op_launch(P.ad_g, st)) return -1;                // dg_p
             k_maxpool2_bwd(P.dphi_p, P.idx_phi, P.dqkv, nq, dq, dq, b, H, H, st);
             k_maxpool2_bwd(P.dg_p, P.idx_g, P.dqkv, nq, 2 * dq, dv, b, H, H, st);
             if (conv_op_launch(P.ad_qkv, st)) return -1;              // -> dh of block ap-1
         }
     }
-    // BN-affine gradients -> d cond
+    // BN-affine gradients -> d cond: fixed-order sums of the per-tile partials, then the finalisation
+    k_stat_reduce(P.segs, P.nsegs, P.S0, P.S1, C_all, b, st);
     k_bn_grad_finalize(P.S0, P.S1, P.a, P.s, mean, inv_std, P.G, b, C_cond, C_all, st);
     const int nb_g = k_dcond_blocks(2 * C_cond), nb_z = k_dcond_blocks(genz_J);
     k_dcond_partial(P.G, 2 * C_cond, Wcat, P.dcond, b, 2 * C_cond, cdim, st);

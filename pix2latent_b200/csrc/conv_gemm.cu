@@ -26,8 +26,12 @@ void add_launches(long n) { g_launches += n; }
 long launch_count() { return g_launches; }
 
 static int g_tma_out = 1, g_tma_kmax = 512;
-static int g_splitk = 0;  // "splitk": split-K over idle SMs for few-tile / long-K launches (needs a -DP2L_SPLITK=1 build; unvalidated)
-static int g_attn_fused = 0;  // "attn_fused": two-pass softmax + fused dS in the attention GEMM epilogues (needs a -DP2L_ROWFUSE=1 build; unvalidated)
+static int g_splitk = 0;      // "splitk": split-K over idle SMs for few-tile / long-K launches
+static int g_attn_fused = 0;  // "attn_fused": two-pass softmax + fused dS in the attention GEMM epilogues
+static int g_attn_emit_t = 0; // "attn_emit_t": the attention backward's transposed operands come out of the producing epilogues
+static int g_prefetch_saved = 0;  // "prefetch_saved": backward epilogue of the N = 64 one-CTA-per-SM kernels fetches the saved rows early
+static int g_sub_mb = 0;      // "sub_mb": L2 budget (MB) for sub-batching the high-resolution generator blocks (0: off)
+static int g_sub_min_tiles = 592;  // "sub_min_tiles": a sub-batch keeps at least this many 128-pixel tiles per launch
 static int g_pdl = 1;  // "pdl": launch the tensor-core kernel with programmatic stream serialization (prologue overlaps the previous kernel's tail)
 static int g_deep = 1, g_deep_kmin = 8;  // "deep": full-depth single-CTA pipeline for launches with <= #SM tiles and >= deep_kmin K blocks
 static int g_grad_scale = (int)kGradScale;
@@ -48,6 +52,10 @@ void set_option(const char* key, int value) {
     else if (!std::strcmp(key, "pdl")) g_pdl = value;
     else if (!std::strcmp(key, "attn_fused")) g_attn_fused = value;
     else if (!std::strcmp(key, "splitk")) g_splitk = value;
+    else if (!std::strcmp(key, "attn_emit_t")) g_attn_emit_t = value;
+    else if (!std::strcmp(key, "prefetch_saved")) g_prefetch_saved = value;
+    else if (!std::strcmp(key, "sub_mb")) g_sub_mb = value;
+    else if (!std::strcmp(key, "sub_min_tiles")) g_sub_min_tiles = value;
     else if (!std::strcmp(key, "deep")) g_deep = value;
     else if (!std::strcmp(key, "deep_kmin")) g_deep_kmin = value;
 }
@@ -60,9 +68,13 @@ int get_option(const char* key) {
     if (!std::strcmp(key, "tma_kmax")) return g_tma_kmax;
     if (!std::strcmp(key, "pdl")) return g_pdl;
     if (!std::strcmp(key, "attn_fused")) return g_attn_fused;
-    if (!std::strcmp(key, "rowfuse_built")) return P2L_ROWFUSE;
+    if (!std::strcmp(key, "rowfuse_built")) return 1;
     if (!std::strcmp(key, "splitk")) return g_splitk;
-    if (!std::strcmp(key, "splitk_built")) return P2L_SPLITK;
+    if (!std::strcmp(key, "splitk_built")) return 1;
+    if (!std::strcmp(key, "attn_emit_t")) return g_attn_emit_t;
+    if (!std::strcmp(key, "prefetch_saved")) return g_prefetch_saved;
+    if (!std::strcmp(key, "sub_mb")) return g_sub_mb;
+    if (!std::strcmp(key, "sub_min_tiles")) return g_sub_min_tiles;
     if (!std::strcmp(key, "deep")) return g_deep;
     if (!std::strcmp(key, "deep_kmin")) return g_deep_kmin;
     return -1;
@@ -163,6 +175,15 @@ static int pow2_ceil(int x) {
     return p;
 }
 
+int conv_stat_parts_max(int H, int W) {
+    int tw = pow2_ceil(W); if (tw > 16) tw = 16;
+    int th = pow2_ceil(H); if (th > kBM / tw) th = kBM / tw;
+    if (tw * th < kBM) return tw * th >= 32 ? (tw * th) / 32 : 1;
+    const int a = ((W + tw - 1) / tw) * ((H + th - 1) / th);
+    const int b = ((W + 7) / 8) * ((H + 15) / 16);   // halo-patch kernel tiling
+    return a > b ? a : b;
+}
+
 // ----------------------------------------------------------------------------- build
 int conv_op_build(ConvOp* op, const ConvDesc& d) {
     if (d.Cin <= 0 || d.Cin % kBK != 0) {
@@ -175,10 +196,6 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     }
     if (d.BN != 16 && d.BN != 64 && d.BN != 128 && d.BN != 256) {
         set_error("conv_op_build: unsupported BN=%d", d.BN);
-        return -1;
-    }
-    if (!P2L_ROWFUSE && (d.epi.rowstat || d.epi.rowstat_in || d.epi.mulin || d.epi.rowsub)) {
-        set_error("conv_op_build: row-wise softmax fusions need a library built with -DP2L_ROWFUSE=1");
         return -1;
     }
     std::memset(op, 0, sizeof(*op));
@@ -222,7 +239,7 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     if (halo) {
         // shared-memory plan: [patch ring][B tiles (resident matrix | ring)][barriers][coefficient tables]
         const long patch = (((long)halo_p * 18 * 128 + 1023) / 1024) * 1024, btile = (long)d.BN * kBK * 2;
-        const long fixed = 1024 + 64 * 8 + 6L * d.BN * 4, budget = 227 * 1024 - fixed;
+        const long fixed = 1024 + 64 * 8 + 6L * d.BN * 4 + kStatRedBytes, budget = 227 * 1024 - fixed;
         if (p.halo_resb) {
             p.halo_sa = (int)((budget - resb_bytes) / patch);
         } else {
@@ -234,6 +251,13 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
         op->halo_smem = (int)(p.halo_sa * patch + (p.halo_resb ? resb_bytes : p.halo_sb * btile) + fixed);
     }
     if (p.alpha == 0.f) p.alpha = 1.f;
+    p.prefetch_saved = g_prefetch_saved;
+    // partial slots per image of the BN-gradient sums this launch fills (see ConvGemmParams::statp)
+    op->stat_parts = (nb == 1) ? p.tiles_w * p.tiles_h : ((tw * th >= 32) ? (tw * th) / 32 : 1);
+    if (d.epi.statp && op->stat_parts > d.epi.statp_parts) {
+        set_error("conv_op_build: BN-gradient partial buffer holds %d slots per image, the launch needs %d", d.epi.statp_parts, op->stat_parts);
+        return -1;
+    }
 
     {   // A: {C, W, H, N}
         cuuint64_t dims[4] = {(cuuint64_t)d.A_C, (cuuint64_t)d.A_W, (cuuint64_t)d.A_H, (cuuint64_t)d.A_N};
@@ -300,7 +324,6 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
                 (long)d.kh * d.kw * p.cin_chunks >= g_deep_kmin) ? 1 : 0;
     const long slots = (long)num_sms() * ((halo || d.BN > 128 || op->tma_out || op->deep) ? 1 : P2L_OCC);
     op->grid = (int)(total < slots ? total : slots);
-#if P2L_SPLITK
     if (g_splitk && d.splitk_ws && !op->tma_out && !halo && !d.epi.img_nchw && d.Cout % 32 == 0 && total * 2 <= num_sms()) {
         const long kblocks = (long)d.kh * d.kw * p.cin_chunks;
         long target = num_sms() / total;                 // splits that still fit one wave
@@ -321,7 +344,6 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
             }
         }
     }
-#endif
     op->flops = 2.0 * d.NI * d.H * d.W * (double)d.Cout * d.kh * d.kw * d.Cin;
     return 0;
 }
@@ -404,7 +426,6 @@ static int launch_halo_t(const ConvOp& op, cudaStream_t stream) {
 static int conv_op_launch_one(const ConvOp& op, cudaStream_t stream);
 
 int conv_op_launch(const ConvOp& op, cudaStream_t stream) {
-#if P2L_SPLITK
     if (op.ksplit > 1) {
         // partial pass over (tile, K split) work items, then the finish pass (epilogue warps only) of the same kernel
         if (conv_op_launch_one(op, stream)) return -1;
@@ -413,7 +434,6 @@ int conv_op_launch(const ConvOp& op, cudaStream_t stream) {
         fin.grid = op.grid_finish;
         return conv_op_launch_one(fin, stream);
     }
-#endif
     return conv_op_launch_one(op, stream);
 }
 

@@ -30,33 +30,10 @@ constexpr int kBM = 128;  // pixels per tile
 constexpr int kBK = 64;   // bf16 per K chunk = one 128-byte swizzle row
 constexpr int kGemmThreads = 192;
 constexpr int kATileBytes = kBM * kBK * 2;
+constexpr int kStatRedBytes = 4096;  // cross-warp staging of the BN-gradient sums: 2 groups x 2 parities x [4][2][32] floats
 #ifndef P2L_OCC
 #define P2L_OCC 2
 #endif
-// Row-wise softmax / softmax-gradient fusions in the forward epilogue (attention; see ConvGemmParams::rowstat ...).
-// PREPARED, NOT YET VALIDATED ON A GPU: compiled out by default so that the validated kernels stay byte-for-byte what
-// the round's tests and profiles ran; build with -DP2L_ROWFUSE=1 (python -m pix2latent_b200.build --rowfuse) and set
-// the "attn_fused" option to exercise it.
-#ifndef P2L_ROWFUSE
-#define P2L_ROWFUSE 0
-#endif
-// Backward epilogue, direct path, one-CTA-per-SM kernels with N = 64 (halo-patch 3x3, DEEP): fetch the tile's rows of the
-// saved activation BEFORE waiting for the accumulator, so that their global-load latency (exposed once per 32-column chunk
-// today: block 11's dgrad conv_2 takes 179 us against 97 us for the same contraction without a saved activation,
-// profiles/r1d_per_layer_roofline.md) overlaps the tile's main loop. 32 more registers per thread, hence only where the
-// register budget is 204. PREPARED, NOT YET VALIDATED ON A GPU: compiled out by default (-DP2L_PREFETCH_SAVED=1 to try).
-#ifndef P2L_PREFETCH_SAVED
-#define P2L_PREFETCH_SAVED 0
-#endif
-// Split-K over idle SMs for launches with fewer tiles than SMs and a long K loop (the 4x4 / 8x8 generator blocks: one SM's
-// L2->shared-memory port, ~40-64 B/clk, bounds them — profiles/r1d_ncu_lo3_before.md): work item = (tile, K split); a split
-// writes its fp32 partial accumulators to a workspace; a second launch of the SAME kernel in "finish" mode runs only the
-// epilogue warps, which sum the partials instead of reading TMEM and then apply the layer's normal epilogue.
-// PREPARED, NOT YET VALIDATED ON A GPU: compiled out by default (-DP2L_SPLITK=1 and the "splitk" option to try).
-#ifndef P2L_SPLITK
-#define P2L_SPLITK 0
-#endif
-
 enum { EPI_FWD = 0, EPI_BWD = 1 };
 
 struct ConvGemmParams {
@@ -106,19 +83,29 @@ struct ConvGemmParams {
     const float* rowsub;     // v <- (v - rowsub[pixel]) * mulin[pixel, c]   (dS = P o (dP - rowsum(dO o O)))
     const act_t* mulin;
     int mulin_C;
+    // ---- both modes: transposed 16-bit copy of the main output (FWD: the raw value, BWD: dx) for channels
+    //      [outT_c0, outT_c1): outT[(n * (outT_c1 - outT_c0) + c - outT_c0) * H * W + h * W + w]. The attention
+    //      backward consumes P^T, dS^T, theta^T and dO^T as K-major operands; emitting them here replaces four
+    //      transpose passes (a warp's 32 lanes are 32 consecutive pixels: two full 32-byte sectors per store).
+    act_t* outT;
+    int outT_c0, outT_c1;
     // ---- epilogue, backward
     const act_t* saved;  // forward activation of the layer being differentiated
     int saved_C;
-    float* stat0;  // += sum_pix dpre          [NI, stat_stride]
-    float* stat1;  // += sum_pix dpre * saved  [NI, stat_stride]
-    int stat_stride;
+    // BN-affine gradient sums, deterministic: every (image, partial, channel) slot is written by exactly one warp,
+    // statp[((n * statp_parts + part) * 2 + {0: sum_pix dpre, 1: sum_pix dpre * saved}) * statp_C + c]; a fixed-order
+    // reduction over `part` follows (stat_reduce_kernel). part = tile index inside the image (128-pixel tiles: the four
+    // epilogue warps are summed in shared memory first) or the 32-row quarter of a small image.
+    float* statp;
+    int statp_parts, statp_C;
+    int prefetch_saved;  // backward, direct path, N = 64 one-CTA-per-SM kernels: fetch the saved rows before the accumulator wait
     const act_t* addin;  // gradient arriving through the skip connection
     int addin_C, addin_climit, addin_pool;  // pool: sum the 2x2 block of a [NI,2H,2W,addin_C] map
     act_t* dx;
     int dx_C;
     float* dx_f32;  // optional fp32 copy (used for the latent-side tensors)
     int dx_f32_C;
-    // ---- split-K (P2L_SPLITK): ksplit > 1: K is cut into ksplit ranges of ks_blocks K blocks; partials [split][pixel][Cout] fp32
+    // ---- split-K: ksplit > 1: K is cut into ksplit ranges of ks_blocks K blocks; partials [split][pixel][Cout] fp32
     int ksplit, ks_blocks, ks_finish;
     float* ks_partial;
     long ks_stride;  // floats between two splits' partials
@@ -150,7 +137,7 @@ struct GemmCfg {
     static constexpr int kMaxStages = ((kOcc == 2 ? 104 : 208) * 1024 - kOutBytes) / kStageBytes;
     static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
     static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 6 * BN * 4 /*coefficient tables*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 6 * BN * 4 /*coefficient tables*/ + kStatRedBytes;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
 };
 
@@ -257,12 +244,25 @@ __device__ __forceinline__ void row_store_f32(float* dst, const float (&v)[CH], 
     }
 }
 
+// transposed 16-bit copy of a chunk of the thread's output row (ConvGemmParams::outT)
+template <int CH>
+__device__ __forceinline__ void row_store_transposed(const ConvGemmParams& p, int n, int h, int w, int cbase, const float (&v)[CH]) {
+    const long hw = static_cast<long>(p.H) * p.W;
+    act_t* dst = p.outT + (static_cast<long>(n) * (p.outT_c1 - p.outT_c0) + (cbase - p.outT_c0)) * hw + static_cast<long>(h) * p.W + w;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+        if (cbase + j >= p.outT_c0 && cbase + j < p.outT_c1) dst[j * hw] = f2a(v[j]);
+}
+
 // Direct epilogue: every thread reads / writes the global rows of its own accumulator row.
 template <int BN, int MODE, int CH, bool TMA_OUT, int NG>
 __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, const CUtensorMap* tmo, uint8_t* obuf,
                                                      uint64_t* in_full, uint64_t* in_empty, uint64_t* tfull_bar,
                                                      uint64_t* tempty_bar, uint32_t tmem_base, int total_tiles, int warp,
                                                      int lane, float* ctab) {
+    // the 4 KB behind the tables: cross-warp staging of the BN-gradient column sums, [group][parity][quad][2][32]
+    float* stat_red = ctab + 6 * BN;
+    int stat_it = 0;
     // ctab: 2 x 3 x BN floats in shared memory — per-tile copies of bias / affine gain / affine offset
     // (they depend on (image, channel) only; staging them once per tile, before the accumulator is
     // ready, takes their global-load latency off the per-chunk critical path)
@@ -301,19 +301,11 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
     float alpha = p.alpha;
     if (p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
     int it = grp;  // index of the tile in this CTA's sequence
-#if P2L_SPLITK
     const bool ks_finish = !TMA_OUT && p.ks_finish != 0;
     const int KS = (!TMA_OUT && p.ksplit > 1 && !ks_finish) ? p.ksplit : 1;  // work item = (tile, split) in the partial pass
     const int loop_tiles = total_tiles * KS;
-#else
-    const int loop_tiles = total_tiles;
-#endif
     for (int wt = blockIdx.x + grp * gridDim.x; wt < loop_tiles; wt += NG * gridDim.x, it += NG) {
-#if P2L_SPLITK
         const int tile = wt / KS, split = wt - tile * KS;
-#else
-        const int tile = wt;
-#endif
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
@@ -340,30 +332,25 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
             }
             bar_epilogue(grp);  // table[it & 1] was last read by this group's previous tile (or two tiles ago): every warp has passed a barrier since
         }
-#if P2L_PREFETCH_SAVED
         constexpr bool kPre = (MODE == EPI_BWD) && !TMA_OUT && NG == 2 && BN == 64 && CH == 32;
         // eight named registers rather than an array: the compiler keeps an indexed array (partly) in local memory
         uint4 pa0 = make_uint4(0, 0, 0, 0), pa1 = pa0, pa2 = pa0, pa3 = pa0, pb0 = pa0, pb1 = pa0, pb2 = pa0, pb3 = pa0;
         bool pre_ok = false;
         if constexpr (kPre) {
-            pre_ok = p.saved != nullptr && valid && (n_tile * BN + BN <= p.Cout) && (p.saved_C % 8 == 0);
+            pre_ok = p.prefetch_saved && p.saved != nullptr && valid && (n_tile * BN + BN <= p.Cout) && (p.saved_C % 8 == 0);
             if (pre_ok) {
                 const uint4* sp = reinterpret_cast<const uint4*>(p.saved + pix * p.saved_C + n_tile * BN);
                 pa0 = __ldg(sp + 0); pa1 = __ldg(sp + 1); pa2 = __ldg(sp + 2); pa3 = __ldg(sp + 3);
                 pb0 = __ldg(sp + 4); pb1 = __ldg(sp + 5); pb2 = __ldg(sp + 6); pb3 = __ldg(sp + 7);
             }
         }
-#endif
-#if P2L_SPLITK
         if (!ks_finish)
-#endif
         {
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
         }
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
         // row-wise softmax fusions (forward mode, direct path): running (max, sum) of pass 1 / (M, 1/L) of pass 2
-#if P2L_ROWFUSE
         float rs_max = -INFINITY, rs_sum = 0.f, rs_M = 0.f, rs_invL = 1.f, rs_sub = 0.f;
         if constexpr (MODE == EPI_FWD && !TMA_OUT) {
             if (p.rowstat_in && valid) {
@@ -377,7 +364,6 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
             }
             if (p.rowsub && valid) rs_sub = __ldg(p.rowsub + pix);
         }
-#endif
 
 #pragma unroll 1
         for (int c = 0; c < BN; c += CH) {
@@ -414,7 +400,6 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 }
             }
             float v[CH];
-#if P2L_SPLITK
             if (ks_finish) {
                 // finish pass: the accumulator is the sum of the splits' partials (fp32, L2-resident)
 #pragma unroll
@@ -430,7 +415,6 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     }
                 }
             } else
-#endif
             {
                 uint32_t u[CH];
                 if constexpr (CH == 32) tmem_ld32(t_addr + c, u);
@@ -439,14 +423,12 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 #pragma unroll
                 for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(u[j]);
             }
-#if P2L_SPLITK
             if constexpr (!TMA_OUT) {
                 if (KS > 1) {  // partial pass: the raw accumulator goes to this split's slice of the workspace
                     if (valid) row_store_f32<CH>(p.ks_partial + split * p.ks_stride + pix * p.Cout + cbase, v, false);
                     continue;
                 }
             }
-#endif
             const bool full_chunk = (cbase + CH <= p.Cout);
 
             if constexpr (MODE == EPI_FWD) {
@@ -485,7 +467,6 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     const long rp = (static_cast<long>(n) * Hs + (h >> p.resid_shift)) * Ws + (w >> p.resid_shift);
                     row_load_add<CH>(p.resid + rp * p.resid_C + cbase, v, wide_ok(p.resid, p.resid_C * 2));
                 }
-#if P2L_ROWFUSE
                 if constexpr (!TMA_OUT) {
                     if (p.rowstat) {  // pass 1: online (max, sum exp) over this tile's columns; no stores
                         float cm = -INFINITY;
@@ -512,7 +493,6 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                         for (int j = 0; j < CH; ++j) v[j] = (v[j] - rs_sub) * mv[j];
                     }
                 }
-#endif
                 if (p.img_nchw) {
                     if (valid) {
 #pragma unroll
@@ -526,6 +506,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 if (p.raw_f32 && valid) {
                     row_store_f32<CH>(p.raw_f32 + pix * p.raw_f32_C + cbase, v, wide_ok(p.raw_f32, p.raw_f32_C * 4));
                 }
+                if (p.outT && valid && cbase < p.outT_c1 && cbase + CH > p.outT_c0) row_store_transposed<CH>(p, n, h, w, cbase, v);
                 if constexpr (TMA_OUT) {
                     if (p.raw) slab_put_row(s_raw, row, (c & 32) >> 3, v);
                 } else if (p.raw && valid) {
@@ -596,7 +577,6 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 #pragma unroll
                     for (int j = 0; j < CH; ++j) v[j] = (valid && y[j] > 0.f) ? v[j] : 0.f;
                 } else if (p.saved) {
-#if P2L_PREFETCH_SAVED
                     if (kPre && pre_ok) {
                         if (c == 0) {
                             acc8_act(pa0, y); acc8_act(pa1, y + 8); acc8_act(pa2, y + 16); acc8_act(pa3, y + 24);
@@ -604,7 +584,6 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                             acc8_act(pb0, y); acc8_act(pb1, y + 8); acc8_act(pb2, y + 16); acc8_act(pb3, y + 24);
                         }
                     } else
-#endif
                     if (valid) {
                         row_load_add<CH>(p.saved + pix * p.saved_C + cbase, y, wide_ok(p.saved, p.saved_C * 2));  // y starts at 0
                     } else {
@@ -617,25 +596,45 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 #pragma unroll
                     for (int j = 0; j < CH; ++j) v[j] = 0.f;
                 }
-                if (p.stat0) {
-                    // BN-affine gradients: reduce over the pixels (lanes) of one image.
-                    if (rows_per_img >= 32) {
-                        float t0[32], t1[32];
-                        static_assert(CH == 32 || CH == 16, "chunk");
-                        if constexpr (CH == 32) {
+                if (p.statp) {
+                    // BN-affine gradients: reduce over the pixels (lanes) of one image; no atomics — every slot of the
+                    // partial buffer has exactly one writer, so the step is bitwise reproducible
+                    static_assert(CH == 32 || CH == 16, "chunk");
+                    if constexpr (CH == 32) {
+                        if (rows_per_img >= 32) {
+                            float t0[32], t1[32];
 #pragma unroll
                             for (int j = 0; j < 32; ++j) { t0[j] = v[j]; t1[j] = v[j] * y[j]; }
-                            const float s0 = colsum_group<32>(t0, lane);
-                            const float s1 = colsum_group<32>(t1, lane);
-                            const int nn = tni * p.nb + (quad * 32) / rows_per_img;
-                            if (nn < p.NI) {
-                                atomicAdd(p.stat0 + static_cast<long>(nn) * p.stat_stride + cbase + lane, s0);
-                                atomicAdd(p.stat1 + static_cast<long>(nn) * p.stat_stride + cbase + lane, s1);
+                            float s0 = colsum_group<32>(t0, lane);
+                            float s1 = colsum_group<32>(t1, lane);
+                            if (p.nb == 1) {
+                                // the group's four warps hold the four 32-row quarters of ONE image's tile: sum them in
+                                // shared memory in a fixed order (double-buffered by chunk parity: one barrier per chunk)
+                                const uint32_t red = smem_u32(stat_red) + ((grp * 2 + (stat_it & 1)) * 256) * 4;
+                                ++stat_it;
+                                sts32f(red + (quad * 64 + lane) * 4, s0);
+                                sts32f(red + (quad * 64 + 32 + lane) * 4, s1);
+                                bar_epilogue(grp);
+                                if (quad == 0 && tni < p.NI && cbase + lane < p.Cout) {
+                                    s0 = (lds32f(red + lane * 4) + lds32f(red + (64 + lane) * 4)) + (lds32f(red + (128 + lane) * 4) + lds32f(red + (192 + lane) * 4));
+                                    s1 = (lds32f(red + (32 + lane) * 4) + lds32f(red + (96 + lane) * 4)) + (lds32f(red + (160 + lane) * 4) + lds32f(red + (224 + lane) * 4));
+                                    const int part = thi * p.tiles_w + twi;
+                                    float* dst = p.statp + (static_cast<long>(tni) * p.statp_parts + part) * 2 * p.statp_C + cbase + lane;
+                                    dst[0] = s0;
+                                    dst[p.statp_C] = s1;
+                                }
+                            } else {
+                                // small images (32 or 64 pixels): the warp's 32 rows are one quarter / half of one image
+                                const int nn = tni * p.nb + (quad * 32) / rows_per_img;
+                                const int part = ((quad * 32) % rows_per_img) >> 5;
+                                if (nn < p.NI && cbase + lane < p.Cout) {
+                                    float* dst = p.statp + (static_cast<long>(nn) * p.statp_parts + part) * 2 * p.statp_C + cbase + lane;
+                                    dst[0] = s0;
+                                    dst[p.statp_C] = s1;
+                                }
                             }
-                        }
-                    } else {
-                        // 16 pixels per image (4x4 maps): half-warp groups.
-                        if constexpr (CH == 32) {
+                        } else {
+                            // 16 pixels per image (4x4 maps): half-warp groups, one partial per image
 #pragma unroll
                             for (int half = 0; half < 2; ++half) {
                                 float t0[16], t1[16];
@@ -644,9 +643,11 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                                 const float s0 = colsum_group<16>(t0, lane);
                                 const float s1 = colsum_group<16>(t1, lane);
                                 const int nn = tni * p.nb + (quad * 32 + (lane & 16)) / rows_per_img;
-                                if (nn < p.NI) {
-                                    atomicAdd(p.stat0 + static_cast<long>(nn) * p.stat_stride + cbase + half * 16 + (lane & 15), s0);
-                                    atomicAdd(p.stat1 + static_cast<long>(nn) * p.stat_stride + cbase + half * 16 + (lane & 15), s1);
+                                const int ch = cbase + half * 16 + (lane & 15);
+                                if (nn < p.NI && ch < p.Cout) {
+                                    float* dst = p.statp + static_cast<long>(nn) * p.statp_parts * 2 * p.statp_C + ch;
+                                    dst[0] = s0;
+                                    dst[p.statp_C] = s1;
                                 }
                             }
                         }
@@ -687,6 +688,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 if constexpr (TMA_OUT) {
                     if (p.dx) slab_put_row(s_raw, row, (c & 32) >> 3, v);
                 }
+                if (p.outT && valid && cbase < p.outT_c1 && cbase + CH > p.outT_c0) row_store_transposed<CH>(p, n, h, w, cbase, v);
                 if (valid) {
                     if (!TMA_OUT && p.dx) {
                         row_store<CH>(p.dx + pix * p.dx_C + cbase, v, wide_ok(p.dx, p.dx_C * 2));
@@ -730,7 +732,6 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 }
             }
         }
-#if P2L_ROWFUSE
         if constexpr (MODE == EPI_FWD && !TMA_OUT) {
             if (p.rowstat && valid) {
                 float* rp = p.rowstat + (pix * p.rowstat_nt + n_tile) * 2;
@@ -738,15 +739,10 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 rp[1] = rs_sum;
             }
         }
-#endif
         // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above)
         tc_fence_before();
         __syncwarp();
-#if P2L_SPLITK
         if (lane == 0 && !ks_finish) mbar_arrive(&tempty_bar[as]);
-#else
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
-#endif
     }
     if (store_warp && elect_one()) bulk_wait0();  // shared memory must outlive the last bulk store's reads
 }
@@ -816,7 +812,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // makes the compiler wrap every uniform-datapath instruction (UTCHMMA / UTMALDG / UTCBAR) in an
     // ELECT + BRA.U.ANY "waterfall" loop — measured (ncu source page, profiles/r1i): the MMA warp then spends ~75 %
     // of its time in issue overhead, ~160-195 cycles per MMA instruction.
-#if P2L_SPLITK
     const int KS = (!TMA_OUT && p.ksplit > 1) ? p.ksplit : 1;
     const int kbs = KS > 1 ? p.ks_blocks : k_blocks;                                  // K blocks per split
     const int work_tiles = (!TMA_OUT && p.ks_finish) ? 0 : total_tiles * KS;          // finish pass: epilogue warps only
@@ -877,77 +872,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
         }
     } else
-#else
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-            const int twi = m_tile % p.tiles_w;
-            const int thi = (m_tile / p.tiles_w) % p.tiles_h;
-            const int tni = m_tile / (p.tiles_w * p.tiles_h);
-            const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.nb;
-            for (int r = 0; r < p.taps_h; ++r) {
-                for (int s = 0; s < p.taps_w; ++s) {
-                    const int kbase = (r * p.taps_w + s) * Cin;
-                    for (int cc = 0; cc < p.cin_chunks; ++cc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* sA = smem + stage * Cfg::kStageBytes;
-                        uint8_t* sB = sA + kATileBytes;
-                        if (elect_one()) {
-                            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                            tma_load_4d(sA, &tmA, &full_bar[stage], p.a_c0 + cc * kBK,
-                                        w0 + s - p.pad_w, h0 + r - p.pad_h, n0);
-                            tma_load_3d(sB, &tmB, &full_bar[stage], kbase + cc * kBK, n_tile * BN,
-                                        p.b_batched ? n0 : 0);
-                        }
-                        __syncwarp();
-                        if (++stage == S) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_bf16(BN);
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            mbar_wait(&tempty_bar[as], aphase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * BN;
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
-                const uint64_t adesc = umma_desc_k128(sA);
-                const uint64_t bdesc = umma_desc_k128(sA + kATileBytes);
-                if (elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k) {
-                        // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in 16-B units
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    }
-                    umma_commit(&empty_bar[stage]);
-                }
-                __syncwarp();
-                if (++stage == S) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-            if (elect_one()) umma_commit(&tfull_bar[as]);
-            __syncwarp();
-        }
-    } else
-#endif
     if (warp >= 2 + 4 * Cfg::kEpiGroups) {
         // ------------------------------------------------------------------ epilogue-input loaders (one warp per group:
         // a single in-order loader would stall group 1's ring behind group 0's full one)
@@ -1019,7 +943,7 @@ struct HaloCfg {
     static constexpr int kThreads = 64 + 2 * 128;   // TMA, MMA, two epilogue groups (one per TMEM stage)
     static constexpr int kMaxBars = 64;             // 8-byte slots reserved for barriers
     static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kFixedBytes = 1024 /*align slack*/ + kMaxBars * 8 + 6 * BN * 4 /*coefficient tables*/;
+    static constexpr int kFixedBytes = 1024 /*align slack*/ + kMaxBars * 8 + 6 * BN * 4 /*coefficient tables*/ + kStatRedBytes;
     static constexpr int kMaxSmem = 227 * 1024;
 };
 

@@ -23,7 +23,7 @@ struct ConvDesc {
     int BN = 128;
     int mode = EPI_FWD;
     ConvGemmParams epi{};  // only the epilogue fields are read from here
-    // split-K workspace (P2L_SPLITK builds with the "splitk" option): fp32 partials of launches with few tiles and long K
+    // split-K workspace ("splitk" option): fp32 partials of launches with few tiles and long K
     float* splitk_ws = nullptr;
     long splitk_ws_floats = 0;
 };
@@ -38,12 +38,15 @@ struct ConvOp {
     int ksplit, grid_finish;  // split-K: number of K ranges (0 / 1: off), grid of the finish pass
     int halo;  // 0: per-tap A loads; 10 / 16: halo-patch kernel with that patch row pitch
     int halo_smem;  // dynamic shared memory of the halo kernel for this plan
+    int stat_parts; // partial slots per image of the BN-gradient sums this launch fills
     double flops;  // algorithmic 2*M*N*K of this launch
 };
 
 // returns 0 on success; on failure sets the thread-local error string
 int conv_op_build(ConvOp* op, const ConvDesc& d);
 int conv_op_launch(const ConvOp& op, cudaStream_t stream);
+// upper bound of ConvOp::stat_parts for an H x W output grid (either tiling: 16x8 or the halo kernel's 8x16)
+int conv_stat_parts_max(int H, int W);
 
 void set_error(const char* fmt, ...);
 const char* get_error();

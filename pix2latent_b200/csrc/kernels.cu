@@ -326,8 +326,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return make_uint4(pk2(f[0], f[1]), pk2(f[2], f[3]), pk2(f[4], f[5]), pk2(f[6], f[7]));
 }
 __global__ void pool_bnrelu_bwd_kernel(const bf16* __restrict__ g_up, const bf16* __restrict__ y_lo,
-                                       const float* __restrict__ a, int aff_stride, float* S0, float* S1,
-                                       int stat_stride, bf16* dx, int H, int W, int C) {
+                                       const float* __restrict__ a, int aff_stride, float* __restrict__ statp,
+                                       int parts, bf16* dx, int H, int W, int C) {
     __shared__ float r0[32][65], r1[32][65];
     const int cg = threadIdx.x, py = threadIdx.y;  // 8 x 32
     const int c = blockIdx.y * 64 + cg * 8;
@@ -371,14 +371,45 @@ __global__ void pool_bnrelu_bwd_kernel(const bf16* __restrict__ g_up, const bf16
         float t0 = 0.f, t1 = 0.f;
 #pragma unroll 8
         for (int k = 0; k < 32; ++k) { t0 += r0[k][tid]; t1 += r1[k][tid]; }
-        atomicAdd(S0 + (long)bi * stat_stride + blockIdx.y * 64 + tid, t0);
-        atomicAdd(S1 + (long)bi * stat_stride + blockIdx.y * 64 + tid, t1);
+        // one writer per (image, pixel block, channel): the fixed-order sum over the blocks follows in stat_reduce_kernel
+        float* dst = statp + ((long)bi * parts + blockIdx.x) * 2 * C + blockIdx.y * 64 + tid;
+        dst[0] = t0;
+        dst[C] = t1;
     }
 }
-void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int aff_stride, float* S0,
-                       float* S1, int stat_stride, bf16* dx, int b, int H, int W, int C, cudaStream_t st) {
+int k_pool_bnrelu_parts(int H, int W) { return cdiv((long)H * W, 256); }
+void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int aff_stride, float* statp,
+                       bf16* dx, int b, int H, int W, int C, cudaStream_t st) {
     dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
-    pool_bnrelu_bwd_kernel<<<grid, block, 0, st>>>(g_up, y_lo, a, aff_stride, S0, S1, stat_stride, dx, H, W, C); count_launch();
+    pool_bnrelu_bwd_kernel<<<grid, block, 0, st>>>(g_up, y_lo, a, aff_stride, statp, (int)grid.x, dx, H, W, C); count_launch();
+}
+
+// BN-gradient sums: S0/S1[n][off + c] = sum over the layer's partial slots, in slot order (8 interleaved running sums
+// per (n, c), then a fixed tree) — the same order whatever the launch geometry of the producers was
+__global__ void __launch_bounds__(256) stat_reduce_kernel(const StatSeg* __restrict__ segs, float* __restrict__ S0,
+                                                          float* __restrict__ S1, int stride) {
+    __shared__ float r0[8][33], r1[8][33];
+    const StatSeg sg = segs[blockIdx.x];
+    const int n = blockIdx.y, lane = threadIdx.x, sl = threadIdx.y;
+    const float* base = sg.p + (long)n * sg.pstride * 2 * sg.C + sg.c0 + lane;
+    float a0 = 0.f, a1 = 0.f;
+    for (int q = sl; q < sg.parts; q += 8) {
+        a0 += __ldg(base + (long)q * 2 * sg.C);
+        a1 += __ldg(base + (long)q * 2 * sg.C + sg.C);
+    }
+    r0[sl][lane] = a0;
+    r1[sl][lane] = a1;
+    __syncthreads();
+    if (sl == 0) {
+        a0 = ((r0[0][lane] + r0[1][lane]) + (r0[2][lane] + r0[3][lane])) + ((r0[4][lane] + r0[5][lane]) + (r0[6][lane] + r0[7][lane]));
+        a1 = ((r1[0][lane] + r1[1][lane]) + (r1[2][lane] + r1[3][lane])) + ((r1[4][lane] + r1[5][lane]) + (r1[6][lane] + r1[7][lane]));
+        S0[(long)n * stride + sg.off + sg.c0 + lane] = a0;
+        S1[(long)n * stride + sg.off + sg.c0 + lane] = a1;
+    }
+}
+void k_stat_reduce(const StatSeg* segs, int nsegs, float* S0, float* S1, int stride, int b, cudaStream_t st) {
+    if (nsegs <= 0) return;
+    stat_reduce_kernel<<<dim3(nsegs, b), dim3(32, 8), 0, st>>>(segs, S0, S1, stride); count_launch();
 }
 
 __global__ void pool2x2_sum_kernel(const bf16* __restrict__ in, int inC, bf16* __restrict__ out, int b, int H, int W, int C) {
@@ -704,8 +735,8 @@ void k_maxpool_bwd(const bf16* dout, const unsigned char* idx, const bf16* x, co
 
 // one warp per feature pixel; block = 8 warps; one atomic per block for the loss
 __global__ void lpips_dist_kernel(const bf16* __restrict__ f, const float* __restrict__ t,
-                                  const float* __restrict__ lin, const float* __restrict__ wadj, float* loss,
-                                  bf16* __restrict__ g, int HW, int C, float gscale) {
+                                  const float* __restrict__ lin, const float* __restrict__ wadj, float* __restrict__ lossp,
+                                  int lp_stride, bf16* __restrict__ g, int HW, int C, float gscale) {
     __shared__ float part[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bi = blockIdx.y;
@@ -752,13 +783,33 @@ __global__ void lpips_dist_kernel(const bf16* __restrict__ f, const float* __res
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += part[i];
-        atomicAdd(loss + bi, s);
+        lossp[(long)bi * lp_stride + blockIdx.x] = s;   // one slot per block: summed in slot order by loss_reduce_kernel
     }
 }
-void k_lpips_dist(const bf16* f, const float* t, const float* lin, const float* wadj, float* loss, bf16* g, int b,
-                  int HW, int C, float gscale, cudaStream_t st) {
+int k_lpips_dist_slots(int HW) { return cdiv(HW, 8); }
+void k_lpips_dist(const bf16* f, const float* t, const float* lin, const float* wadj, float* lossp, int lp_stride, bf16* g,
+                  int b, int HW, int C, float gscale, cudaStream_t st) {
     dim3 grid(cdiv(HW, 8), b);
-    lpips_dist_kernel<<<grid, 256, 0, st>>>(f, t, lin, wadj, loss, g, HW, C, gscale); count_launch();
+    lpips_dist_kernel<<<grid, 256, 0, st>>>(f, t, lin, wadj, lossp, lp_stride, g, HW, C, gscale); count_launch();
+}
+
+// loss[bi] = sum of the sample's partial slots (pixel term blocks, then every layer's distance blocks), fixed order
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ lossp, int nslots, int lp_stride,
+                                                          float* __restrict__ loss) {
+    __shared__ float red[256];
+    const int bi = blockIdx.x, t = threadIdx.x;
+    float a = 0.f;
+    for (int k = t; k < nslots; k += 256) a += lossp[(long)bi * lp_stride + k];
+    red[t] = a;
+    __syncthreads();
+    for (int h = 128; h >= 1; h >>= 1) {
+        if (t < h) red[t] += red[t + h];
+        __syncthreads();
+    }
+    if (t == 0) loss[bi] = red[0];
+}
+void k_loss_reduce(const float* lossp, int nslots, int lp_stride, float* loss, int b, cudaStream_t st) {
+    loss_reduce_kernel<<<b, 256, 0, st>>>(lossp, nslots, lp_stride, loss); count_launch();
 }
 
 __global__ void lpips_normalize_kernel(const bf16* __restrict__ f, float* __restrict__ t, int HW, int C) {
@@ -787,32 +838,49 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, 
     i1 = i0 < in_size - 1 ? i0 + 1 : i0;
     l1 = src - i0;
 }
-__global__ void upsample_adjoint_kernel(const float* __restrict__ wsum, float* wadj, int H, int W, int h, int w,
+// adjoint of the bilinear up-sampling as a GATHER (one thread per low-res pixel sums, in raster order, the hi-res
+// pixels whose footprint touches it): no atomics, so two targets built from the same data are bitwise identical
+__global__ void upsample_adjoint_kernel(const float* __restrict__ wsum, float* __restrict__ wadj, int H, int W, int h, int w,
                                         float coef) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= H * W) return;
-    const int Y = i / W, X = i % W;
-    int y0, y1, x0, x1;
-    float ly, lx;
-    bilinear_src(Y, (float)h / H, h, y0, y1, ly);
-    bilinear_src(X, (float)w / W, w, x0, x1, lx);
-    const float v = wsum[i] * coef;
-    atomicAdd(wadj + y0 * w + x0, v * (1.f - ly) * (1.f - lx));
-    atomicAdd(wadj + y0 * w + x1, v * (1.f - ly) * lx);
-    atomicAdd(wadj + y1 * w + x0, v * ly * (1.f - lx));
-    atomicAdd(wadj + y1 * w + x1, v * ly * lx);
+    if (i >= h * w) return;
+    const int y = i / w, x = i % w;
+    // hi-res rows whose source coordinate lies in (y - 1, y + 1): src = (h/H)(Y + .5) - .5
+    const float sy = (float)H / h, sx = (float)W / w;
+    const int Y0 = max(0, (int)floorf((y - 1 + 0.5f) * sy - 0.5f) - 1), Y1 = min(H - 1, (int)ceilf((y + 1 + 0.5f) * sy - 0.5f) + 1);
+    const int X0 = max(0, (int)floorf((x - 1 + 0.5f) * sx - 0.5f) - 1), X1 = min(W - 1, (int)ceilf((x + 1 + 0.5f) * sx - 0.5f) + 1);
+    float acc = 0.f;
+    for (int Y = Y0; Y <= Y1; ++Y) {
+        int y0, y1;
+        float ly;
+        bilinear_src(Y, (float)h / H, h, y0, y1, ly);
+        float wy = 0.f;
+        if (y0 == y) wy += 1.f - ly;
+        if (y1 == y) wy += ly;
+        if (wy == 0.f) continue;
+        for (int X = X0; X <= X1; ++X) {
+            int x0, x1;
+            float lx;
+            bilinear_src(X, (float)w / W, w, x0, x1, lx);
+            float wx = 0.f;
+            if (x0 == x) wx += 1.f - lx;
+            if (x1 == x) wx += lx;
+            if (wx != 0.f) acc += wsum[Y * W + X] * coef * wy * wx;
+        }
+    }
+    wadj[i] = acc;
 }
 void k_upsample_adjoint(const float* wsum, float* wadj, int H, int W, int h, int w, float coef, cudaStream_t st) {
-    cudaMemsetAsync(wadj, 0, (size_t)h * w * sizeof(float), st);
-    upsample_adjoint_kernel<<<cdiv((long)H * W, 256), 256, 0, st>>>(wsum, wadj, H, W, h, w, coef); count_launch();
+    upsample_adjoint_kernel<<<cdiv((long)h * w, 64), 64, 0, st>>>(wsum, wadj, H, W, h, w, coef); count_launch();
 }
 
-__global__ void weight_sum_kernel(const float* __restrict__ weight, const float* __restrict__ mask, float* wsum,
-                                  float* total, int HW) {
-    __shared__ float part[8];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float v = 0.f;
-    if (i < HW) {
+__global__ void __launch_bounds__(1024) weight_sum_kernel(const float* __restrict__ weight, const float* __restrict__ mask,
+                                                          float* wsum, float* total, int HW) {
+    // ONE block (runs once per target): strided running sums, then a fixed tree — deterministic
+    __shared__ float red[1024];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < HW; i += 1024) {
+        float v = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float wv = weight ? weight[c * HW + i] : 1.f;
@@ -820,25 +888,24 @@ __global__ void weight_sum_kernel(const float* __restrict__ weight, const float*
             v += wv;
         }
         wsum[i] = v;
+        acc += v;
     }
-    v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+    red[threadIdx.x] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int k = 0; k < (blockDim.x >> 5); ++k) s += part[k];
-        atomicAdd(total, s);
+    for (int h = 512; h >= 1; h >>= 1) {
+        if ((int)threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+        __syncthreads();
     }
+    if (threadIdx.x == 0) total[0] = red[0];
 }
 void k_weight_sum(const float* weight, const float* mask, float* wsum, float* total, int HW, cudaStream_t st) {
-    cudaMemsetAsync(total, 0, sizeof(float), st);
-    weight_sum_kernel<<<cdiv(HW, 256), 256, 0, st>>>(weight, mask, wsum, total, HW); count_launch();
+    weight_sum_kernel<<<1, 1024, 0, st>>>(weight, mask, wsum, total, HW); count_launch();
 }
 
 __global__ void l1_loss_kernel(const float* __restrict__ img, const float* __restrict__ target,
                                const float* __restrict__ weight, const float* __restrict__ mask,
-                               const float* __restrict__ total, float* loss, float* __restrict__ dimg, int HW3,
-                               int l2) {
+                               const float* __restrict__ total, float* __restrict__ lossp, int lp_stride,
+                               float* __restrict__ dimg, int HW3, int l2) {
     __shared__ float part[8];
     const int bi = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -865,14 +932,15 @@ __global__ void l1_loss_kernel(const float* __restrict__ img, const float* __res
     if (threadIdx.x == 0) {
         float s = 0.f;
         for (int k = 0; k < (blockDim.x >> 5); ++k) s += part[k];
-        atomicAdd(loss + bi, s);
+        lossp[(long)bi * lp_stride + blockIdx.x] = s;
     }
 }
+int k_l1_loss_slots(int HW3) { return cdiv(HW3, 256); }
 void k_l1_loss(const float* img, const float* target, const float* weight, const float* mask, const float* total,
-               float* loss, float* dimg, int b, int HW3, int HW, int l2, cudaStream_t st) {
+               float* lossp, int lp_stride, float* dimg, int b, int HW3, int HW, int l2, cudaStream_t st) {
     (void)HW;
     dim3 grid(cdiv(HW3, 256), b);
-    l1_loss_kernel<<<grid, 256, 0, st>>>(img, target, weight, mask, total, loss, dimg, HW3, l2); count_launch();
+    l1_loss_kernel<<<grid, 256, 0, st>>>(img, target, weight, mask, total, lossp, lp_stride, dimg, HW3, l2); count_launch();
 }
 
 __global__ void scale_rows_kernel(float* x, const float* scale, long n) {

@@ -48,10 +48,15 @@ void k_split_dcond(const float* dcond, float* dz, float* dc, int b, int zd, int 
 // (x[n,y,x,:] . W[o,:,tap]); img[n,o,y,x] = tanh(bias[o] + sum_tap T[n, tap*3+o, y+r-1, x+s-1]) with zero padding
 void k_rgb_gather(const float* T, const float* bias, float* img, int b, int H, int W, cudaStream_t st);
 // backward through nearest-x2 + relu + BN affine of an up block's conv_0 output:
-//   g = sum2x2(g_up) ; dpre = g*[y>0] ; S0 += dpre ; S1 += dpre*y ; dx = a*dpre
+//   g = sum2x2(g_up) ; dpre = g*[y>0] ; dx = a*dpre ; the sums of dpre and dpre*y over each 256-pixel block go to
+//   statp[((n * parts + block) * 2 + {0,1}) * C + c], parts = k_pool_bnrelu_parts(H, W) (no atomics; k_stat_reduce sums them)
+int k_pool_bnrelu_parts(int H, int W);
 void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int aff_stride,
-                       float* S0, float* S1, int stat_stride, bf16* dx, int b, int H, int W, int C,
-                       cudaStream_t st);
+                       float* statp, bf16* dx, int b, int H, int W, int C, cudaStream_t st);
+// One 32-channel chunk of one BN layer's partial sums (ConvGemmParams::statp layout): S0/S1[n][off + c0 + lane] =
+// sum over `parts` slots, in slot order
+struct StatSeg { const float* p; int parts, pstride, C, off, c0; };  // parts filled of pstride allocated per image
+void k_stat_reduce(const StatSeg* segs, int nsegs, float* S0, float* S1, int stride, int b, cudaStream_t st);
 
 // out[b,H,W,C] = sum of the 2x2 block of in[b,2H,2W,inC] (first C channels): the skip gradient of an
 // up block at the block's input resolution
@@ -90,18 +95,24 @@ void k_maxpool_bwd(const bf16* dout, const unsigned char* idx, const bf16* x, co
                    int b, int H, int W, int C, int Ho, int Wo, int k, int s, cudaStream_t st);
 // LPIPS layer distance + its gradient: f[b,HW,C] bf16 (post-relu), t[HW,C] fp32 (unit-normalised
 // target features), lin[C], wadj[HW] (adjoint-upsampled weight map / sumW * beta).
-//   loss[b] += sum_p wadj[p] * sum_c lin_c (f_c/(|f|+eps) - t_c)^2 ; g = d/df (masked by f>0), or null
-void k_lpips_dist(const bf16* f, const float* t, const float* lin, const float* wadj, float* loss,
+//   sum_p wadj[p] * sum_c lin_c (f_c/(|f|+eps) - t_c)^2 ; g = d/df (masked by f>0), or null.
+// Deterministic reduction: block k of sample bi writes its part to lossp[bi * lp_stride + k] (k_lpips_dist_slots(HW)
+// slots); k_loss_reduce sums a sample's slots in slot order.
+int k_lpips_dist_slots(int HW);
+void k_lpips_dist(const bf16* f, const float* t, const float* lin, const float* wadj, float* lossp, int lp_stride,
                   bf16* g, int b, int HW, int C, float gscale, cudaStream_t st);
+void k_loss_reduce(const float* lossp, int nslots, int lp_stride, float* loss, int b, cudaStream_t st);
 // t[p, c] = f_c/(|f|+eps)  (target features, b = 1)
 void k_lpips_normalize(const bf16* f, float* t, int HW, int C, cudaStream_t st);
 // wadj_k = U_k^T (sum_c W[c]) * coef   for a feature map h x w (bilinear, align_corners=False)
 void k_upsample_adjoint(const float* wsum, float* wadj, int H, int W, int h, int w, float coef, cudaStream_t st);
 // wsum[p] = sum_c W[c,p] (* mask) ; total = sum
 void k_weight_sum(const float* weight, const float* mask, float* wsum, float* total, int HW, cudaStream_t st);
-// L1 term: loss[b] += sum |t-o| * W / sumW ; dimg[b,c,p] = -sign(t-o) * W / sumW   (dimg overwritten)
+// L1 term: sum |t-o| * W / sumW into k_l1_loss_slots(HW3) partial slots per sample (see k_lpips_dist) ;
+// dimg[b,c,p] = -sign(t-o) * W / sumW   (dimg overwritten)
+int k_l1_loss_slots(int HW3);
 void k_l1_loss(const float* img, const float* target, const float* weight, const float* mask,
-               const float* total, float* loss, float* dimg, int b, int HW3, int HW, int l2, cudaStream_t st);
+               const float* total, float* lossp, int lp_stride, float* dimg, int b, int HW3, int HW, int l2, cudaStream_t st);
 // dimg[b] *= dloss[b]
 void k_scale_rows(float* x, const float* scale, int b, long n, cudaStream_t st);
 // rgb conv backward input: A[b,H,W,Kp] bf16 with k = (r*3+s)*3 + c of dpre = dimg*(1-img^2)

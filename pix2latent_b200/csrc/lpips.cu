@@ -31,6 +31,8 @@ struct LpipsPlan {
     };
     std::vector<Lay> L;
     float* dimg = nullptr;  // unit-upstream d loss_i / d img_i
+    float* lossp = nullptr; // [b][nslots] per-block partial sums of the loss (pixel term, then each feature layer)
+    int nslots = 0, slot_l1 = 0, slot_feat[8] = {0};
     bool grad_ready = false;
 };
 
@@ -185,6 +187,15 @@ LpipsPlan* Lpips::plan(int b, int H, int W) {
     }
     // the last conv's pre-relu gradient IS its (relu-masked) distance gradient
     P.L[n - 1].D = P.L[n - 1].g;
+    // loss partial slots: every block of the pixel-term / distance kernels owns one (no atomics: reproducible sums)
+    P.slot_l1 = 0;
+    P.nslots = k_l1_loss_slots(3 * H * W);
+    for (int j = 0; j < n; ++j) {
+        if (convs[j].feat < 0) continue;
+        P.slot_feat[convs[j].feat] = P.nslots;
+        P.nslots += k_lpips_dist_slots(P.L[j].Hout * P.L[j].Wout);
+    }
+    P.lossp = ar.alloc<float>((size_t)b * P.nslots);
     if (ar.failed) return nullptr;
     auto m_tiles = [&](int hh, int ww) {
         int tw = 1; while (tw < ww) tw <<= 1; if (tw > 16) tw = 16;
@@ -333,20 +344,24 @@ int Lpips::loss_forward_multi(Target* const* Ts, int b, const float* img, float*
         if (i == 0 || Ts[i] != Ts[i - 1]) r0.push_back(i);
     r0.push_back(b);
     const int nr = (int)r0.size() - 1;
-    P2L_CUDA_CHECK(cudaMemsetAsync(loss, 0, (size_t)b * sizeof(float), st));
+    P2L_CUDA_CHECK(cudaMemsetAsync(P.lossp, 0, (size_t)b * P.nslots * sizeof(float), st));
     // pixel term (also initialises dimg)
     if (T.rec_w != 0.f) {
         for (int k = 0; k < nr; ++k) {
             const Target& U = *Ts[r0[k]];
             const int i0 = r0[k], nb = r0[k + 1] - r0[k];
-            k_l1_loss(img + (size_t)i0 * 3 * HW, U.target, U.weight, U.mask, U.total + 1, loss + i0,
-                      want_grad ? P.dimg + (size_t)i0 * 3 * HW : nullptr, nb, 3 * HW, HW, U.rec_type == 2, st);
+            k_l1_loss(img + (size_t)i0 * 3 * HW, U.target, U.weight, U.mask, U.total + 1, P.lossp + (size_t)i0 * P.nslots + P.slot_l1,
+                      P.nslots, want_grad ? P.dimg + (size_t)i0 * 3 * HW : nullptr, nb, 3 * HW, HW, U.rec_type == 2, st);
         }
     } else if (want_grad) {
         P2L_CUDA_CHECK(cudaMemsetAsync(P.dimg, 0, (size_t)b * 3 * HW * sizeof(float), st));
     }
     P.grad_ready = false;
-    if (T.per_w == 0.f) { P.grad_ready = want_grad; return 0; }
+    if (T.per_w == 0.f) {
+        k_loss_reduce(P.lossp, P.nslots, P.nslots, loss, b, st);
+        P.grad_ready = want_grad;
+        return 0;
+    }
     if (features(P, img, st)) return -1;
     for (int j = 0; j < n; ++j) {
         const int f = convs[j].feat;
@@ -355,10 +370,11 @@ int Lpips::loss_forward_multi(Target* const* Ts, int b, const float* img, float*
         for (int k = 0; k < nr; ++k) {
             const Target& U = *Ts[r0[k]];
             const int i0 = r0[k], nb = r0[k + 1] - r0[k];
-            k_lpips_dist(P.L[j].F + i0 * per, U.tfeat[f], lin[f], U.wadj[f], loss + i0, want_grad ? P.L[j].g + i0 * per : nullptr,
-                         nb, T.fh[f] * T.fw[f], chns[f], grad_scale(), st);
+            k_lpips_dist(P.L[j].F + i0 * per, U.tfeat[f], lin[f], U.wadj[f], P.lossp + (size_t)i0 * P.nslots + P.slot_feat[f], P.nslots,
+                         want_grad ? P.L[j].g + i0 * per : nullptr, nb, T.fh[f] * T.fw[f], chns[f], grad_scale(), st);
         }
     }
+    k_loss_reduce(P.lossp, P.nslots, P.nslots, loss, b, st);
     if (!want_grad) return 0;
     // ---- backward through the backbone (dgrad only)
     // last conv's pre-relu gradient is its (already relu-masked) distance gradient

@@ -32,6 +32,7 @@ struct SG2Plan {
     std::vector<float*> rgb, weff, dweff;
     float *drgbA = nullptr, *drgbB = nullptr, *img = nullptr;
     act_t *dx[2] = {nullptr, nullptr}, *G = nullptr, *dDp = nullptr, *dA = nullptr;
+    float* scratch = nullptr;  // block partials of the per-(sample, channel) reductions (sg2_kernels.h)
     bool forward_done = false;
     int mode = 0;  // 0: z search (mapping network ran), 1: w / w+ search (styles from the latent rows)
 };
@@ -210,6 +211,14 @@ SG2Plan* SG2::plan(int b) {
     P.G = ar.alloc<bf>(max_x);
     P.dDp = ar.alloc<bf>(max_a);
     P.dA = ar.alloc<bf>(max_a);
+    {
+        long ms = 0;
+        for (int l = 0; l < nL; ++l) {
+            const Conv& c = convs[l];
+            ms = std::max(ms, std::max(k_sg_scratch_floats(b, c.Hout, c.Hout, c.Cout), k_sg_scratch_floats(b, c.Hin, c.Hin, c.Cin)));
+        }
+        P.scratch = ar.alloc<float>((size_t)ms);
+    }
     const int R = cfg.size;
     for (size_t t = 0; t < rgbs.size(); ++t) {
         P.rgb.push_back(ar.alloc<float>((size_t)b * 3 * rgbs[t].H * rgbs[t].H));
@@ -357,12 +366,12 @@ int SG2::synth_bwd(SG2Plan& P, int b, const float* dimg, float* const* dnoise, f
         SG2Plan::Lay& q = P.L[l];
         if (dnoise && dnoise[l])
             k_sg_noise_bwd(P.dx[l & 1], q.x, c.noise_w, dnoise[l], b, c.Hout, c.Hout, c.Cout, out_scale, row_scale, st);
-        k_sg_post_bwd(P.dx[l & 1], q.x, q.D, P.dm_all + c.dm_off, DM, P.G, P.ddm_all + c.dm_off, b, c.Hout, c.Hout, c.Cout, c.up, st);
+        k_sg_post_bwd(P.dx[l & 1], q.x, q.D, P.dm_all + c.dm_off, DM, P.G, P.ddm_all + c.dm_off, P.scratch, b, c.Hout, c.Hout, c.Cout, c.up, st);
         if (c.up) k_sg_blur_adjoint(P.G, P.dDp, b, c.Hout, c.Hout, c.Cout, st);
         if (conv_op_launch(q.d, st)) return -1;
         const act_t* xp = l == 0 ? const_in : P.L[l - 1].x;
         const long xbs = l == 0 ? 0 : (long)c.Hin * c.Hin * c.Cin;
-        k_sg_modulate_bwd(P.dA, xp, xbs, P.s_all + c.s_off, S, l == 0 ? nullptr : P.dx[(l - 1) & 1], P.ds_all + c.s_off, S, b, c.Hin,
+        k_sg_modulate_bwd(P.dA, xp, xbs, P.s_all + c.s_off, S, l == 0 ? nullptr : P.dx[(l - 1) & 1], P.ds_all + c.s_off, S, P.scratch, b, c.Hin,
                           c.Hin, c.Cin, c.up, st);
         k_demod_bwd(P.ddm_all + c.dm_off, P.dm_all + c.dm_off, DM, P.s_all + c.s_off, S, c.wsq, P.ds_all + c.s_off, S, b, c.Cin,
                     c.Cout, st);
@@ -371,7 +380,7 @@ int SG2::synth_bwd(SG2Plan& P, int b, const float* dimg, float* const* dnoise, f
     for (int t = T - 1; t >= 0; --t) {
         const Rgb& r = rgbs[t];
         const int l = (t == 0) ? 0 : 2 * t;
-        k_sg_torgb_bwd(dcur, P.L[l].x, P.weff[t], P.dx[l & 1], P.dweff[t], b, r.H, r.H, r.Cin, t < T - 1 ? 1 : 0, st);
+        k_sg_torgb_bwd(dcur, P.L[l].x, P.weff[t], P.dx[l & 1], P.dweff[t], P.scratch, b, r.H, r.H, r.Cin, t < T - 1 ? 1 : 0, st);
         k_sg_weff_bwd(P.dweff[t], r.Wr, r.scale, P.ds_all + r.s_off, S, b, r.Cin, st);
         if (t > 0) k_sg_rgb_up_adjoint(dcur, dprev, b, r.H / 2, r.H / 2, st);
         if (layer_bwd(l)) return -1;

@@ -225,7 +225,7 @@ void k_sg_modulate(const bf16* x, long x_bstride, const float* s, int lds, bf16*
 // backward: dA (sampled at odd positions when up) -> ds[b,c] += sum_p dA*x ; dx = s*dA
 // block = 8 channel groups x 32 pixels, one image; 64 channels per blockIdx.y
 __global__ void modulate_bwd_kernel(const bf16* __restrict__ dA, const bf16* __restrict__ x, long x_bstride, const float* __restrict__ s,
-                                    int lds, bf16* __restrict__ dx, float* ds, int ldds, int H, int W, int C, int up) {
+                                    int lds, bf16* __restrict__ dx, float* __restrict__ part, int H, int W, int C, int up) {
     __shared__ float red[32][65];
     const int cg = threadIdx.x, py = threadIdx.y;
     const int c = blockIdx.y * 64 + cg * 8;
@@ -254,13 +254,27 @@ __global__ void modulate_bwd_kernel(const bf16* __restrict__ dA, const bf16* __r
         float t = 0.f;
 #pragma unroll 8
         for (int k = 0; k < 32; ++k) t += red[k][tid];
-        atomicAdd(ds + (long)bi * ldds + blockIdx.y * 64 + tid, t);
+        part[((long)bi * gridDim.x + blockIdx.x) * C + blockIdx.y * 64 + tid] = t;  // one writer per slot (no atomics)
     }
 }
+// dst[bi][j] += sum over the `parts` pixel blocks of part[bi][p][j], in block order: the reproducible second stage of the
+// per-(sample, channel) reductions below
+__global__ void partial_reduce_add_kernel(const float* __restrict__ part, int parts, int n, float* __restrict__ dst, int ld) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, bi = blockIdx.y;
+    if (j >= n) return;
+    float t = 0.f;
+    for (int q = 0; q < parts; ++q) t += part[((long)bi * parts + q) * n + j];
+    dst[(long)bi * ld + j] += t;
+}
+static void partial_reduce_add(const float* part, int parts, int b, int n, float* dst, int ld, cudaStream_t st) {
+    partial_reduce_add_kernel<<<dim3(cdiv(n, 128), b), 128, 0, st>>>(part, parts, n, dst, ld); count_launch();
+}
+long k_sg_scratch_floats(int b, int H, int W, int C) { return (long)b * cdiv((long)H * W, 256) * C * 3; }
 void k_sg_modulate_bwd(const bf16* dA, const bf16* x, long x_bstride, const float* s, int lds, bf16* dx, float* ds, int ldds,
-                       int b, int H, int W, int C, int up, cudaStream_t st) {
+                       float* scratch, int b, int H, int W, int C, int up, cudaStream_t st) {
     dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
-    modulate_bwd_kernel<<<grid, block, 0, st>>>(dA, x, x_bstride, s, lds, dx, ds, ldds, H, W, C, up); count_launch();
+    modulate_bwd_kernel<<<grid, block, 0, st>>>(dA, x, x_bstride, s, lds, dx, scratch, H, W, C, up); count_launch();
+    partial_reduce_add(scratch, (int)grid.x, b, C, ds, ldds, st);
 }
 
 // ----------------------------------------------------------------------------- demod + noise + bias + lrelu (+ blur)
@@ -322,7 +336,7 @@ void k_sg_post_fwd(const float* D, const float* dm, int lddm, const float* noise
 
 // backward pass 1: g = dx * sqrt2 * lrelu'(x) ; ddm[b,c] += sum_p g * u (u = [blurred] D) ; G = dm * g (bf16)
 __global__ void post_bwd_kernel(const bf16* __restrict__ dx, const bf16* __restrict__ x, const float* __restrict__ D,
-                                const float* __restrict__ dm, int lddm, bf16* __restrict__ G, float* ddm, int H, int W, int C, int up) {
+                                const float* __restrict__ dm, int lddm, bf16* __restrict__ G, float* __restrict__ part, int H, int W, int C, int up) {
     __shared__ float red[32][65];
     const int cg = threadIdx.x, py = threadIdx.y;
     const int c = blockIdx.y * 64 + cg * 8;
@@ -360,13 +374,14 @@ __global__ void post_bwd_kernel(const bf16* __restrict__ dx, const bf16* __restr
         float t = 0.f;
 #pragma unroll 8
         for (int k = 0; k < 32; ++k) t += red[k][tid];
-        atomicAdd(ddm + (long)bi * lddm + blockIdx.y * 64 + tid, t);
+        part[((long)bi * gridDim.x + blockIdx.x) * C + blockIdx.y * 64 + tid] = t;
     }
 }
-void k_sg_post_bwd(const bf16* dx, const bf16* x, const float* D, const float* dm, int lddm, bf16* G, float* ddm, int b, int H,
-                   int W, int C, int up, cudaStream_t st) {
+void k_sg_post_bwd(const bf16* dx, const bf16* x, const float* D, const float* dm, int lddm, bf16* G, float* ddm, float* scratch,
+                   int b, int H, int W, int C, int up, cudaStream_t st) {
     dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
-    post_bwd_kernel<<<grid, block, 0, st>>>(dx, x, D, dm, lddm, G, ddm, H, W, C, up); count_launch();
+    post_bwd_kernel<<<grid, block, 0, st>>>(dx, x, D, dm, lddm, G, scratch, H, W, C, up); count_launch();
+    partial_reduce_add(scratch, (int)grid.x, b, C, ddm, lddm, st);
 }
 
 // backward pass 2 (up layers): adjoint of the blur: dD'[m, n] = sum_{t,v} G[m - t + 1, n - v + 1] k[t] k[v]
@@ -467,7 +482,7 @@ void k_sg_torgb_fwd(const bf16* x, const float* weff, const float* bias, const f
 // backward: dx[b,p,i] (+)= sum_c drgb[b,c,p] weff[b,c,i] ; dweff[b,c,i] += sum_p drgb[b,c,p] x[b,p,i]
 // block = 8 channel groups x 32 pixels
 __global__ void torgb_bwd_kernel(const float* __restrict__ drgb, const bf16* __restrict__ x, const float* __restrict__ weff,
-                                 bf16* __restrict__ dx, float* dweff, int H, int W, int C, int accumulate) {
+                                 bf16* __restrict__ dx, float* __restrict__ part, int H, int W, int C, int accumulate) {
     __shared__ float red[3][32][65];
     const int cg = threadIdx.x, py = threadIdx.y;
     const int c = blockIdx.y * 64 + cg * 8;
@@ -505,13 +520,14 @@ __global__ void torgb_bwd_kernel(const float* __restrict__ drgb, const bf16* __r
         float t = 0.f;
 #pragma unroll 8
         for (int j = 0; j < 32; ++j) t += red[cc][j][k];
-        atomicAdd(dweff + ((long)bi * 3 + cc) * C + blockIdx.y * 64 + k, t);
+        part[(((long)bi * gridDim.x + blockIdx.x) * 3 + cc) * C + blockIdx.y * 64 + k] = t;
     }
 }
-void k_sg_torgb_bwd(const float* drgb, const bf16* x, const float* weff, bf16* dx, float* dweff, int b, int H, int W, int C,
-                    int accumulate, cudaStream_t st) {
+void k_sg_torgb_bwd(const float* drgb, const bf16* x, const float* weff, bf16* dx, float* dweff, float* scratch, int b, int H, int W,
+                    int C, int accumulate, cudaStream_t st) {
     dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
-    torgb_bwd_kernel<<<grid, block, 0, st>>>(drgb, x, weff, dx, dweff, H, W, C, accumulate); count_launch();
+    torgb_bwd_kernel<<<grid, block, 0, st>>>(drgb, x, weff, dx, scratch, H, W, C, accumulate); count_launch();
+    partial_reduce_add(scratch, (int)grid.x, b, 3 * C, dweff, 3 * C, st);
 }
 // ds[b, i] += scale * sum_c dweff[b,c,i] * Wr[c,i]
 __global__ void weff_bwd_kernel(const float* dweff, const float* Wr, float scale, float* ds, int ldds, int b, int C) {

@@ -21,18 +21,22 @@ void k_pixelnorm_bwd(const float* x, const float* dy, float* dx, int b, int n, f
 void k_demod_bwd(const float* ddm, const float* dm, int lddm, const float* s, int lds, const float* Wsq, float* ds, int ldds,
                  int b, int Cin, int Cout, cudaStream_t st);
 void k_sg_modulate(const bf16* x, long x_bstride, const float* s, int lds, bf16* A, int b, int H, int W, int C, int up, cudaStream_t st);
+// The three per-(sample, channel) reductions of the backward pass (modulate_bwd -> ds, post_bwd -> ddm, torgb_bwd -> dweff)
+// are two-stage and atomic-free: every 256-pixel block writes its partial sums to `scratch` (>= k_sg_scratch_floats
+// floats), a second kernel adds them to the destination in block order.
+long k_sg_scratch_floats(int b, int H, int W, int C);
 void k_sg_modulate_bwd(const bf16* dA, const bf16* x, long x_bstride, const float* s, int lds, bf16* dx, float* ds, int ldds,
-                       int b, int H, int W, int C, int up, cudaStream_t st);
+                       float* scratch, int b, int H, int W, int C, int up, cudaStream_t st);
 void k_sg_post_fwd(const float* D, const float* dm, int lddm, const float* noise, const float* nw, const float* bias, bf16* x,
                    int b, int H, int W, int C, int up, cudaStream_t st);
-void k_sg_post_bwd(const bf16* dx, const bf16* x, const float* D, const float* dm, int lddm, bf16* G, float* ddm, int b, int H,
-                   int W, int C, int up, cudaStream_t st);
+void k_sg_post_bwd(const bf16* dx, const bf16* x, const float* D, const float* dm, int lddm, bf16* G, float* ddm, float* scratch,
+                   int b, int H, int W, int C, int up, cudaStream_t st);
 void k_sg_blur_adjoint(const bf16* G, bf16* dD, int b, int H, int W, int C, cudaStream_t st);
 void k_sg_weff(const float* Wr, const float* s, int lds, float scale, float* weff, int b, int C, cudaStream_t st);
 void k_sg_torgb_fwd(const bf16* x, const float* weff, const float* bias, const float* prev, float* rgb, int b, int H, int W, int C,
                     cudaStream_t st);
-void k_sg_torgb_bwd(const float* drgb, const bf16* x, const float* weff, bf16* dx, float* dweff, int b, int H, int W, int C,
-                    int accumulate, cudaStream_t st);
+void k_sg_torgb_bwd(const float* drgb, const bf16* x, const float* weff, bf16* dx, float* dweff, float* scratch, int b, int H, int W,
+                    int C, int accumulate, cudaStream_t st);
 void k_sg_weff_bwd(const float* dweff, const float* Wr, float scale, float* ds, int ldds, int b, int C, cudaStream_t st);
 void k_sg_rgb_up_adjoint(const float* drgb, float* dprev, int b, int h, int w, cudaStream_t st);
 void k_sg_clamp(const float* rgb, float* img, long n, cudaStream_t st);

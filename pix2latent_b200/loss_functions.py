@@ -156,6 +156,14 @@ class _NativeLoss(nn.Module):
             self._cache = _TargetCache(self.native_lpips(), self._rec_type, self._rec_weight, self._per_weight)
         return self._cache
 
+    def invalidate_targets(self):
+        """Drop every cached prepared target. The caches are keyed by (storage pointer, version counter, shape); a
+        buffer rewritten through ``.data`` (``t.data.copy_(...)``) keeps all three, so whoever edits a registered
+        target / weight / loss_mask IN PLACE calls this (``_BaseOptimizer.apply_transform`` does)."""
+        self._cache = None
+        self._row_cache = None
+        self.__dict__.pop("_uniform_cache", None)
+
     def prepared_target(self, target, weight=None, loss_mask=None):
         """target/weight/loss_mask: single [3,H,W] tensors -> cached NativeTarget."""
         return self.target_cache().get(target, weight, loss_mask)

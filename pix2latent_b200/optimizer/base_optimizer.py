@@ -75,6 +75,8 @@ class _BaseOptimizer():
         new = list(transform_dict["fn"](torch.stack(dst_list), src_data))
         for i, t in enumerate(new):
             dst_list[i].data = t.data
+        if hasattr(self.loss_fn, "invalidate_targets"):
+            self.loss_fn.invalidate_targets()  # prepared targets are keyed by storage: drop what the old tensors cached
 
     def step(self, variables, optimize=True, transform=False):
         if transform and len(self.transform_fns) > 0:
@@ -117,67 +119,26 @@ class _BaseOptimizer():
             return None
         if not _native_pair(self.model, variables, self.loss_fn):
             return None
-        opt = variables.opt
-        if type(opt) is not torch.optim.Adam:
-            return None
+        from .closure import _uniform_outputs
+        if not _uniform_outputs(self.loss_fn, variables.output):
+            return None  # per-sample targets / weights: the per-step path with one target per candidate
+        from .closure import adam_plan
         z_list, c_list = variables.input.z.data, variables.input.c.data
-        group_of = {}
-        for g in opt.param_groups:
-            if (g.get("weight_decay", 0) != 0 or g.get("amsgrad", False) or g.get("maximize", False)
-                    or g.get("capturable", False) or g.get("differentiable", False) or g.get("fused", None)):
-                return None
-            if g.get("decoupled_weight_decay", False):
-                return None
-            for p in g["params"]:
-                group_of[id(p)] = g
-        hp = None
-        lrs = []
-        for lst in (z_list, c_list):
-            lr = None
-            for t in lst:
-                g = group_of.get(id(t))
-                if g is None:
-                    if t.requires_grad:
-                        return None  # a trainable leaf the optimizer does not know
-                    this = 0.0
-                else:
-                    if not t.requires_grad:
-                        return None
-                    this = float(g["lr"])
-                    key = (tuple(float(x) for x in g["betas"]), float(g["eps"]))
-                    if hp is None:
-                        hp = key
-                    elif hp != key:
-                        return None
-                if lr is None:
-                    lr = this
-                elif lr != this:
-                    return None
-            lrs.append(lr)
-        if len(group_of) != sum(1 for lst in (z_list, c_list) for t in lst if id(t) in group_of):
-            return None  # the optimizer also owns parameters other than z / c
-        if hp is None:
+        plan = adam_plan(variables.opt, z_list, c_list)
+        if plan is None:
             return None
+        if plan["n_owned"] != sum(1 for lst in (z_list, c_list) for t in lst if id(t) in plan["stateful"]):
+            return None  # the optimizer also owns parameters other than z / c
         clamps = [_clamp_of(variables.input.z.hook_fn), _clamp_of(variables.input.c.hook_fn)]
         if any(c is False for c in clamps):
             return None
-        # optimizer state: fresh everywhere, or stepped the same number of times everywhere
-        steps = set()
-        for lst in (z_list, c_list):
-            for t in lst:
-                if id(t) in group_of:
-                    st = opt.state.get(t, None)
-                    steps.add(int(st["step"]) if st else 0)
-        if len(steps) > 1:
-            return None
-        return dict(lr_z=lrs[0], lr_c=lrs[1], betas=hp[0], eps=hp[1], clamp_z=clamps[0], clamp_c=clamps[1],
-                    step0=steps.pop() if steps else 0, stateful=set(group_of.keys()))
+        plan["clamp_z"], plan["clamp_c"] = clamps
+        return plan
 
     @torch.no_grad()
     def _fused_steps(self, variables, n_steps, plan):
         from .. import native
-        from .closure import _unwrap
-        from ..variable_manager import split_vars
+        from .closure import LazyLosses, _unwrap, chunk_scales, native_adam
         rank, size = parallel.world()
         local = parallel.shard_vars(variables, rank, size) if size > 1 else variables
         m = _unwrap(self.model)
@@ -188,32 +149,15 @@ class _BaseOptimizer():
         dev = z.device
         first = {k: v.data[0] for k, v in local.output.items()}
         tgt = self.loss_fn.prepared_target(first["target"], first.get("weight"), first.get("loss_mask"))
-        # d(mean over the chunk)/d loss_i = 1 / chunk size (closure.py:58), per sample
-        dloss = torch.cat([torch.full((ch.num_samples,), 1.0 / ch.num_samples)
-                           for ch in split_vars(local, size=self.max_batch_size)]).to(dev)
-        opt = variables.opt
-        state = native.AdamState(n, z.shape[1], c.shape[1], dev, step=plan["step0"])
-        if plan["step0"] > 0:
-            mz, vz, mc, vc = state.moments()
-            for i in range(n):
-                for t, mm, vv in ((z_list[i], mz, vz), (c_list[i], mc, vc)):
-                    st = opt.state.get(t, None)
-                    if st:
-                        mm[i].copy_(st["exp_avg"])
-                        vv[i].copy_(st["exp_avg_sq"])
+        dloss = chunk_scales(local, self.max_batch_size, dev)
+        # the Adam state (moments [n, dim], step count) lives on the device and is shared with the per-step path
+        ad = native_adam(variables.opt, z_list, c_list)
         cfg = native.adam_config(plan["lr_z"], plan["lr_c"], plan["betas"], plan["eps"], plan["clamp_z"], plan["clamp_c"])
-        res = native.biggan_optimize(m.native, self.loss_fn.native_lpips(), tgt, z, c, n_steps, cfg, state=state,
+        res = native.biggan_optimize(m.native, self.loss_fn.native_lpips(), tgt, z, c, n_steps, cfg, state=ad["state"],
                                      dloss=dloss, grad_scale=1.0, track=self.track_variables)
-        # back into the per-sample leaves and the torch optimizer (so per-step calls can follow)
-        mz, vz, mc, vc = state.moments()
-        t_now = plan["step0"] + n_steps
-        for i in range(n):
-            z_list[i].data.copy_(z[i])
-            c_list[i].data.copy_(c[i])
-            for t, mm, vv in ((z_list[i], mz, vz), (c_list[i], mc, vc)):
-                if id(t) in plan["stateful"]:
-                    opt.state[t] = {"step": torch.tensor(float(t_now)), "exp_avg": mm[i].clone(),
-                                    "exp_avg_sq": vv[i].clone()}
+        ad["steps"] += n_steps
+        torch._foreach_copy_([t.data.view(-1) for t in z_list], list(z.unbind(0)))
+        torch._foreach_copy_([t.data.view(-1) for t in c_list], list(c.unbind(0)))
         if self.track_variables:
             lo, hi = parallel.shard_bounds(variables.num_samples, rank, size) if size > 1 else (0, n)
             for name, hist in (("z", res["z_hist"]), ("c", res["c_hist"])):
@@ -228,7 +172,7 @@ class _BaseOptimizer():
                         full = hist[j].clone()
                     self.tracked.setdefault(name, []).append(full)
         self.out = res["img"]
-        self.loss = list(res["loss"][-1].cpu().numpy())
+        self.loss = LazyLosses(res["loss"][-1])
         self.loss_history = res["loss"]  # [n_steps, n_local] device tensor of every step's losses
         self.other = {}
         self._n_total = variables.num_samples
@@ -296,6 +240,8 @@ class _BaseOptimizer():
                     t.data.copy_(full[i])
 
     def _finish(self, variables, total_steps):
+        from .closure import flush_native_adam
+        flush_native_adam(variables.opt)  # torch's optimizer state is current again when optimize() returns
         rank, size = parallel.world()
         if size > 1:
             # final state of every shard to every rank: latents (KBs), losses, images
@@ -306,4 +252,4 @@ class _BaseOptimizer():
         if self.log:
             return variables, self.outs, self.losses
         grid = to_grid(torch.stack(list(self.out.cpu().detach())))
-        return variables, [grid], [[total_steps, {"loss": self.loss}]]
+        return variables, [grid], [[total_steps, {"loss": list(self.loss)}]]

@@ -38,7 +38,7 @@ def shard_vars(vars, rank, size):
     lo, hi = shard_bounds(vars.num_samples, rank, size)
     out = {}
     for var_type, group in vars.items():
-        if var_type in ("opt", "num_samples"):
+        if var_type in ("opt", "num_samples", "shard"):
             continue
         out[var_type] = {}
         for name, entry in group.items():
@@ -47,6 +47,7 @@ def shard_vars(vars, rank, size):
             out[var_type][name] = e
     out["opt"] = vars.opt
     out["num_samples"] = hi - lo
+    out["shard"] = (lo, hi, vars.num_samples)  # closure.chunk_scales: the 1/b_chunk scales follow the GLOBAL chunking
     return AttrDict(out)
 
 
@@ -77,21 +78,33 @@ def broadcast_array(arr, shape=None, dtype=np.float64):
 
 def allgather_losses(local, n_total):
     """Concatenate per-candidate losses of all ranks in candidate order -> list of n_total floats.
-    The single data-path collective of the search loop (a few hundred bytes)."""
+    The single data-path collective of the search loop (a few hundred bytes). On NCCL the losses stay on the device:
+    the step's loss tensor (closure.LazyLosses) is the send buffer, ONE all_gather, ONE device -> host copy."""
     rank, size = world()
     if size == 1:
         return list(local)
     dev = _comm_device()
     counts = [shard_bounds(n_total, r, size) for r in range(size)]
     width = max(hi - lo for lo, hi in counts)
-    buf = torch.zeros(width, dtype=torch.float32, device=dev)
-    loc = torch.as_tensor(np.asarray(local, dtype=np.float32))
-    buf[: loc.numel()] = loc.to(dev)
-    out = [torch.empty_like(buf) for _ in range(size)]
-    dist.all_gather(out, buf)
+    src = local.device_tensor() if hasattr(local, "device_tensor") else None
+    if src is not None and src.device == dev:
+        loc = src.detach().float()
+    else:
+        loc = torch.as_tensor(np.asarray(local, dtype=np.float32)).to(dev)
+    if loc.numel() == width:
+        buf = loc.contiguous()
+    else:
+        buf = torch.zeros(width, dtype=torch.float32, device=dev)
+        buf[: loc.numel()] = loc
+    out = torch.empty(size * width, dtype=torch.float32, device=dev)
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(out, buf)
+    else:
+        dist.all_gather(list(out.view(size, width).unbind(0)), buf)
+    host = out.view(size, width).cpu().numpy()
     res = []
     for r, (lo, hi) in enumerate(counts):
-        res.extend(out[r][: hi - lo].cpu().numpy().tolist())
+        res.extend(host[r, : hi - lo].tolist())
     return [np.float32(x) for x in res]
 
 

@@ -54,7 +54,7 @@ class AttrDict(dict):
         del self[k]
 
 
-_META_KEYS = ("opt", "num_samples")
+_META_KEYS = ("opt", "num_samples", "shard")  # "shard": (lo, hi, N) of a candidate-sharded view (parallel.shard_vars)
 
 
 def split_vars(vars, size):
@@ -74,6 +74,8 @@ def split_vars(vars, size):
                 part[var_type][name] = {"data": piece, "hook_fn": entry.hook_fn}
         part["opt"] = vars.opt
         part["num_samples"] = count
+        if "shard" in vars:
+            part["shard"] = vars["shard"]
         chunks.append(AttrDict(part))
     return chunks
 
