@@ -197,8 +197,8 @@ def run_native(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = POP_PER_GPU
-    model = BigGAN(seed=0).cuda()
-    loss_fn = ProjectionLoss()
+    model = BigGAN(seed=0, allow_synthetic=True).cuda()   # no network here: seeded random-init weights of the named architecture
+    loss_fn = ProjectionLoss(allow_synthetic=True)
     target, weight = synthetic_target(256, dev)
     tgt = loss_fn.prepared_target(target, weight)
     gen, lp = model.native, loss_fn.native_lpips()

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libp2l.so")
+LIB_PATH = os.environ.get("P2L_LIB") or os.path.join(_HERE, "libp2l.so")
 
 _lib = None
 

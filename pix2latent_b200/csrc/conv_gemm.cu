@@ -210,10 +210,11 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     const int halo_p = g_halo;
     const long resb_bytes = 9L * d.Cin * d.BN * 2;
     const bool resb = d.Cout <= d.BN && resb_bytes <= 80 * 1024;
-    // mode 1: resident-weight layers with enough tiles per CTA to amortise the one-off weight load (measured: 256^2 gains
-    // 15-20 %, 128^2 loses 4 %)
+    // mode 1: resident-weight layers on large images (measured: 256^2 gains 15-20 %, 128^2 loses 4 %). The choice depends
+    // on the image size only, never on the batch: the tiling decides how the BN-gradient partial sums are grouped, and a
+    // candidate's result must not depend on which other candidates share its launch (sub-batches, candidate sharding).
     const bool halo_on = (d.BN == 16) ? (g_halo_rgb != 0)
-                                      : (g_halo_mode != 0 && (g_halo_mode == 2 || (resb && (long)d.NI * d.H * d.W >= (1L << 19))));
+                                      : (g_halo_mode != 0 && (g_halo_mode == 2 || (resb && (long)d.H * d.W >= (1L << 16))));
     const bool halo = halo_p != 0 && halo_on && d.kh == 3 && d.kw == 3 &&
                       d.pad_h == 1 && d.pad_w == 1 && d.B_batch == 0 && d.H >= 12 && d.W >= 8;
     if (halo) { tw = 8; th = 16; nb = 1; }

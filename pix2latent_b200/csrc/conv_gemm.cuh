@@ -332,7 +332,10 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
             }
             bar_epilogue(grp);  // table[it & 1] was last read by this group's previous tile (or two tiles ago): every warp has passed a barrier since
         }
-        constexpr bool kPre = (MODE == EPI_BWD) && !TMA_OUT && NG == 2 && BN == 64 && CH == 32;
+#ifndef P2L_KPRE   // (A/B build switch while the early fetch is being measured; removed once decided)
+#define P2L_KPRE 1
+#endif
+        constexpr bool kPre = P2L_KPRE && (MODE == EPI_BWD) && !TMA_OUT && NG == 2 && BN == 64 && CH == 32;
         // eight named registers rather than an array: the compiler keeps an indexed array (partly) in local memory
         uint4 pa0 = make_uint4(0, 0, 0, 0), pa1 = pa0, pa2 = pa0, pa3 = pa0, pb0 = pa0, pb1 = pa0, pb2 = pa0, pb3 = pa0;
         bool pre_ok = false;

@@ -76,21 +76,29 @@ def weight_regularization(orig_model, curr_model, reg="l1", weight_dict=None):
 _lpips_cache = {}
 
 
-def get_native_lpips(net="alex", state_dict=None, seed=0):
-    """One NativeLPIPS per (net, device, weights id). Official weights through the ``lpips``
-    package when importable, else seeded synthetic weights (warned)."""
+def _lpips_from_package(net):
+    try:
+        import lpips  # noqa: F401
+    except ImportError:
+        return None
+    from .utils.misc import HiddenPrints
+    with HiddenPrints():
+        return synth.lpips_state_from_package(lpips.LPIPS(net=net, spatial=True).state_dict())
+
+
+def get_native_lpips(net="alex", state_dict=None, seed=0, allow_synthetic=False):
+    """One NativeLPIPS per (net, device, weights id). Weights (model/weights.py): ``state_dict`` if given; else a
+    ``torch.save``d LPIPS state dict at ``$P2L_LPIPS_CKPT``; else the ``lpips`` package when importable; else — ONLY with
+    ``allow_synthetic`` / ``P2L_ALLOW_SYNTHETIC=1`` — seeded synthetic weights; otherwise ``MissingWeights``."""
+    import os
+    from .model import weights
     dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
-    key = (net, dev, id(state_dict) if state_dict is not None else ("synthetic", seed))
+    key = (net, dev, id(state_dict) if state_dict is not None else ("default", seed))
     if key not in _lpips_cache:
         if state_dict is None:
-            try:
-                import lpips  # noqa: F401
-                from .utils.misc import HiddenPrints
-                with HiddenPrints():
-                    state_dict = synth.lpips_state_from_package(lpips.LPIPS(net=net, spatial=True).state_dict())
-            except ImportError:
-                warnings.warn("lpips package not importable; using seeded random-init %s-LPIPS weights" % net)
-                state_dict = synth.lpips_state_dict(net, seed)
+            state_dict, _ = weights.resolve("LPIPS(%s)" % net, None, [os.environ.get("P2L_LPIPS_CKPT")],
+                                            lambda: _lpips_from_package(net), lambda: synth.lpips_state_dict(net, seed),
+                                            allow_synthetic, post=synth.lpips_state_from_package)
         sd = {k: v.cuda() for k, v in state_dict.items()}
         _lpips_cache[key] = native.NativeLPIPS(net, sd)
     return _lpips_cache[key]
@@ -141,15 +149,17 @@ def _same_rows(t):
 class _NativeLoss(nn.Module):
     """Common machinery: rec_weight * pixel term + per_weight * LPIPS term, natively."""
 
-    def __init__(self, net, rec_type, rec_weight, per_weight, lpips_state_dict=None):
+    def __init__(self, net, rec_type, rec_weight, per_weight, lpips_state_dict=None, allow_synthetic=False):
         super().__init__()
         self._net, self._rec_type = net, rec_type
         self._rec_weight, self._per_weight = rec_weight, per_weight
         self._lpips_state = lpips_state_dict
+        # a pure pixel loss never runs the perceptual net: its (unused) weights may be anything
+        self._allow_synthetic = allow_synthetic or per_weight == 0.0
         self._cache = None
 
     def native_lpips(self):
-        return get_native_lpips(self._net, self._lpips_state)
+        return get_native_lpips(self._net, self._lpips_state, allow_synthetic=self._allow_synthetic)
 
     def target_cache(self):
         if self._cache is None:
@@ -227,13 +237,13 @@ class ReconstructionLoss(_NativeLoss):
 class PerceptualLoss(_NativeLoss):
     """LPIPS(net, spatial=True) with spatial weighting: sum(map * W) / sum(W) per sample."""
 
-    def __init__(self, net="vgg", use_gpu=True, lpips_state_dict=None):
-        super().__init__(net, 1, 0.0, 1.0, lpips_state_dict)
+    def __init__(self, net="vgg", use_gpu=True, lpips_state_dict=None, allow_synthetic=False):
+        super().__init__(net, 1, 0.0, 1.0, lpips_state_dict, allow_synthetic)
 
 
 class ProjectionLoss(_NativeLoss):
     """The paper's default: weighted L1 + beta * weighted LPIPS."""
 
-    def __init__(self, lpips_net="alex", beta=10, lpips_state_dict=None):
-        super().__init__(lpips_net, 1, 1.0, float(beta), lpips_state_dict)
+    def __init__(self, lpips_net="alex", beta=10, lpips_state_dict=None, allow_synthetic=False):
+        super().__init__(lpips_net, 1, 1.0, float(beta), lpips_state_dict, allow_synthetic)
         self.beta = beta

@@ -6,7 +6,7 @@ Same surface as /root/reference pix2latent/model/biggan.py:15-58: ``BigGAN(model
 pytorch_pretrained_biggan Generator) runs in libp2l; backward reaches z and c only — the frozen
 generator's weight gradients the reference accumulates are never formed.
 """
-import warnings
+import os
 
 import torch
 import torch.nn as nn
@@ -40,21 +40,22 @@ class _GeneratorFn(torch.autograd.Function):
 class BigGAN(nn.Module):
     """Drop-in for pix2latent.model.BigGAN.
 
-    Weights: ``state_dict`` (pix2latent/HF key names) if given; else the official checkpoint via
-    ``pytorch_pretrained_biggan`` when that package is importable; else seeded synthetic weights
-    of the same architecture (with a warning) — the build environment has no network."""
+    Weights (model/weights.py): ``state_dict`` (pix2latent / HF key names) if given; else a checkpoint file
+    (``checkpoint=`` or ``$P2L_BIGGAN_CKPT``: a ``torch.save``d HF state dict); else the official checkpoint through
+    ``pytorch_pretrained_biggan`` when that package is importable; else — ONLY with ``allow_synthetic=True`` /
+    ``P2L_ALLOW_SYNTHETIC=1`` — seeded synthetic weights of the same architecture; otherwise ``MissingWeights``."""
 
-    def __init__(self, model_version="biggan-deep-256", state_dict=None, config=None, seed=0, truncation=1.0):
+    def __init__(self, model_version="biggan-deep-256", state_dict=None, config=None, seed=0, truncation=1.0,
+                 checkpoint=None, allow_synthetic=False):
         super().__init__()
         assert model_version == "biggan-deep-256" or config is not None, \
             "only biggan-deep-256 (or an explicit config) is supported"
         self.config = config or synth.BigGANConfig()
-        if state_dict is None:
-            state_dict = self._load_pretrained(model_version) if config is None else None
-        if state_dict is None:
-            warnings.warn("BigGAN: no pretrained checkpoint reachable; using seeded random-init weights "
-                          "(seed=%d) of the %s architecture" % (seed, model_version))
-            state_dict = synth.biggan_state_dict(self.config, seed)
+        from . import weights
+        state_dict, self.weights_source = weights.resolve(
+            "BigGAN(%s)" % model_version, state_dict, [checkpoint, os.environ.get("P2L_BIGGAN_CKPT")],
+            (lambda: self._load_pretrained(model_version)) if config is None else None,
+            lambda: synth.biggan_state_dict(self.config, seed), allow_synthetic, post=weights.strip_spectral_norm)
         self.register_buffer("embeddings_weight", state_dict["embeddings.weight"].detach().clone().float())
         self._state = {k: v for k, v in state_dict.items() if k.startswith("generator.")}
         self._truncation = float(truncation)

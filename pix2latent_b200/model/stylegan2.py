@@ -15,7 +15,7 @@ be replayed with explicit ``noises``.
 are differentiable inputs (p2l_sg2_forward_w / p2l_sg2_backward_w); ``latent_mean`` / ``latent_std`` are the
 statistics of style(N(0,I)) over 4096 samples as the reference computes them.
 """
-import warnings
+import os
 
 import torch
 import torch.nn as nn
@@ -101,16 +101,31 @@ class _SG2WFn(torch.autograd.Function):
         return dw, dnoise, None
 
 
+CKPT_FILES = {"cars": "stylegan2-car-config-f.pt", "ffhq": "stylegan2-ffhq-config-f.pt"}  # stylegan2.py:53-61
+
+
 class StyleGAN2(nn.Module):
-    def __init__(self, model="cars", search="z", state_dict=None, size=None, channels=None, seed=0):
+    """Weights (model/weights.py): ``state_dict`` (rosinality ``g_ema`` keys) if given; else the rosinality checkpoint
+    file — ``checkpoint=``, ``$P2L_STYLEGAN2_CKPT`` (a file, or a directory holding the reference's file names), or
+    ``stylegan2-pytorch/<file>`` next to this module (where the reference keeps it, stylegan2.py:9,53-61); else — ONLY
+    with ``allow_synthetic=True`` / ``P2L_ALLOW_SYNTHETIC=1`` — seeded synthetic weights; otherwise ``MissingWeights``."""
+
+    def __init__(self, model="cars", search="z", state_dict=None, size=None, channels=None, seed=0, checkpoint=None,
+                 allow_synthetic=False):
         super().__init__()
         if search not in ("z", "w+"):
             raise ValueError("StyleGAN2(search=%r): expected 'z' or 'w+'" % search)
         self.im_res = int(size or IM_DIM[model])
         self.channels = dict(channels or CHANNELS)
-        if state_dict is None:
-            warnings.warn("StyleGAN2: no checkpoint reachable offline; using seeded random-init weights (seed=%d)" % seed)
-            state_dict = synth.stylegan2_state_dict(self.im_res, self.channels, seed)
+        from . import weights
+        env = os.environ.get("P2L_STYLEGAN2_CKPT")
+        fname = CKPT_FILES.get(model)
+        cands = [checkpoint, env if env and os.path.isfile(env) else None,
+                 os.path.join(env, fname) if env and fname and os.path.isdir(env) else None,
+                 os.path.join(os.path.dirname(os.path.abspath(__file__)), "stylegan2-pytorch", fname) if fname else None]
+        state_dict, self.weights_source = weights.resolve(
+            "StyleGAN2(%s)" % model, state_dict, cands, None,
+            lambda: synth.stylegan2_state_dict(self.im_res, self.channels, seed), allow_synthetic)
         # the tcgen05 path tiles channels by 64: narrower levels (ffhq-1024's 32-channel top level) are
         # zero-padded to 64 — functionally exact, the padded channels have zero weights on both sides
         self._state, self.channels = pad_channels_to_64(state_dict, self.im_res, self.channels)

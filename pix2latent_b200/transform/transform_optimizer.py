@@ -155,4 +155,4 @@ class TransformBasinCMAOptimizer(_BaseOptimizer, _BaseCMAOptimizer):
             self.out = parallel.allgather_rows(self.out, variables.num_samples)
         transform_target = to_grid(torch.stack(variables.output.target.data).cpu())
         transform_out = to_grid(torch.stack(list(self.out.cpu().detach())))
-        return variables, ([transform_out], [transform_target], candidate_out), self.loss
+        return variables, ([transform_out], [transform_target], candidate_out), list(self.loss)

@@ -7,8 +7,8 @@ import torch
 from pix2latent_b200 import native
 from pix2latent_b200.loss_functions import ProjectionLoss
 from pix2latent_b200.model.stylegan2 import StyleGAN2
-model = StyleGAN2("cars")
-loss_fn = ProjectionLoss()
+model = StyleGAN2("cars", allow_synthetic=True)
+loss_fn = ProjectionLoss(allow_synthetic=True)
 g = torch.Generator().manual_seed(1)
 target = torch.tanh(0.5 * torch.randn(3, 512, 512, generator=g)).cuda()
 weight = torch.zeros(3, 512, 512).cuda(); weight[:, 64:-64, :] = 1

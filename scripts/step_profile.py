@@ -19,8 +19,8 @@ for halo in halos:
     _lib.set_option("halo_rgb", 1 if halo == 3 else 0)
     if halo == 3: halo = 0
     _lib.set_option("halo_mode", halo)
-    model = BigGAN(seed=0).cuda()          # plans are built lazily with the current options
-    loss_fn = ProjectionLoss()
+    model = BigGAN(seed=0, allow_synthetic=True).cuda()          # plans are built lazily with the current options
+    loss_fn = ProjectionLoss(allow_synthetic=True)
     tgt = loss_fn.prepared_target(target, weight)
     c = model.get_class_embedding(153).repeat(n, 1).contiguous()
     f = lambda: native.biggan_step(model.native, loss_fn.native_lpips(), tgt, z, c, True, 1 / 9, want_img=False)

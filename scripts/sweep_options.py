@@ -18,10 +18,15 @@ from pix2latent_b200 import _lib, native  # noqa: E402
 from pix2latent_b200.loss_functions import ProjectionLoss  # noqa: E402
 from pix2latent_b200.model import BigGAN, synth  # noqa: E402
 
-DEFAULTS = {"splitk": 0, "attn_fused": 0, "pdl": 1, "deep": 1, "deep_kmin": 8, "tma_out": 1, "tma_kmax": 512, "halo_mode": 1, "halo": 10}
+# the library's defaults at import time are the baseline every config starts from
+OPTION_KEYS = ["splitk", "attn_fused", "attn_emit_t", "prefetch_saved", "sub_mb", "sub_min_tiles", "pdl", "deep", "deep_kmin",
+               "tma_out", "tma_kmax", "halo_mode", "halo"]
+DEFAULTS = {}
 
 
 def run(cfg, sd, lp_sd, steps=20):
+    if not DEFAULTS:
+        DEFAULTS.update({k: _lib.get_option(k) for k in OPTION_KEYS})
     for k, v in DEFAULTS.items():
         _lib.set_option(k, v)
     for k, v in cfg.items():

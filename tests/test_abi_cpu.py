@@ -60,7 +60,11 @@ def test_fails_loudly_without_gpu():
         from pix2latent_b200.model import synth
         cfg = synth.BigGANConfig(output_dim=128, num_classes=16, attention_layer_position=3,
                                  layers=[(True, 4, 4), (True, 4, 4), (True, 4, 4), (False, 4, 4), (True, 4, 2), (True, 2, 1)])
-        m = BigGAN(config=cfg)
+        from pix2latent_b200.model.weights import MissingWeights
+        with pytest.raises(MissingWeights):
+            BigGAN(config=cfg)              # no checkpoint, no opt-in: refuse to build a meaningless generator
+        m = BigGAN(config=cfg, allow_synthetic=True)
+        assert m.weights_source == "synthetic"
     with pytest.raises(RuntimeError):
         m(z=torch.zeros(1, 128), c=torch.zeros(1, 128))
     with pytest.raises(RuntimeError):

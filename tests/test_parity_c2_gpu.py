@@ -1,0 +1,233 @@
+"""The parity run of the benchmarked configuration (SURVEY.md §8(d) "Parity run", BASELINE.json configs[1]):
+BigGAN-deep-256, 18 candidates in chunks of 9 + 9, the BasinCMA inner loop of
+/root/reference examples/invert_biggan_basincma.py:108-109 (Adam lr 0.05 / 0.01, Clamp(2) hook, ProjectionLoss = L1 +
+10 * alex-LPIPS) as /root/reference pix2latent/optimizer/closure.py:51-58 runs it.
+
+  * teacher-forced replay: the ORACLE (oracle/closure.py + oracle generator / LPIPS, fp32 on the GPU, TF32 off) produces
+    a 30-step trajectory (z_k, c_k); the native fused step is evaluated at the SAME (z_k, c_k) every step and compared:
+    per-step per-candidate loss, latent gradients at step 0, the final image, the final LPIPS term alone;
+  * fp64 truth: the oracle in float64 is the reference both the fp32 oracle and the 16-bit-operand native path are
+    measured against (SURVEY.md §8(c) numerics policy) — this is what the tolerances below are set from;
+  * free run: 30 steps of the product's own GradientOptimizer against 30 oracle steps from the same start.
+
+Tolerances (16-bit tensor-core operands, fp32 accumulation; oracle arithmetic for the third-party generator / LPIPS is a
+restatement — "parity unpinned"): per-step |dloss| <= 2e-3 * (1 + |loss|); dz / dc cosine >= 0.99 at step 0
+(calibrated weights); final image max-abs <= 2e-2 on >= 99.9 % of the pixels; final LPIPS |delta| <= 1e-3."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+N, CHUNK, STEPS = 18, 9, 30
+
+
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return (a @ b / (a.norm() * b.norm() + 1e-300)).item()
+
+
+def synthetic_target(res, device):
+    """bench.py's target: low-passed tanh(0.5 randn), weight 0.3 with a centred box of 1."""
+    g = torch.Generator().manual_seed(1)
+    t = torch.tanh(0.5 * torch.randn(1, 3, res, res, generator=g))
+    t = torch.nn.functional.avg_pool2d(t, 8)
+    t = torch.nn.functional.interpolate(t, size=(res, res), mode="bilinear", align_corners=False)[0]
+    w = torch.full((3, res, res), 0.3)
+    q = res // 4
+    w[:, q:res - q, q:res - q] = 1.0
+    return t.to(device), w.to(device)
+
+
+class World:
+    def __init__(self, weights):
+        from oracle import biggan as obg, lpips as olp
+        from pix2latent_b200.loss_functions import ProjectionLoss, PerceptualLoss
+        from pix2latent_b200.model import BigGAN, synth
+        import test_step_gpu as ts
+        _setup()
+        cfg = obg.BigGANConfig.deep256()
+        if weights == "calibrated":
+            # BN statistics set from a forward pass: every BN sees O(1) inputs, the regime of a trained network
+            self.orc = obg.make_biggan(cfg, seed=0, calibrate=True).cuda()
+        else:
+            # the bench's weights (pix2latent_b200.model.synth, seed 0) loaded into the oracle module
+            self.orc = obg.make_biggan(cfg, seed=0, calibrate=False)
+            missing = self.orc.load_state_dict(synth.biggan_state_dict(synth.BigGANConfig(), 0), strict=False)
+            assert not missing.missing_keys, missing.missing_keys
+            self.orc = self.orc.cuda()
+        for p in self.orc.parameters():
+            p.requires_grad_(False)  # weight gradients do not change dz / dc; keeps the oracle run short
+        self.lp = olp.make_lpips("alex", seed=0).cuda()
+        self.ref_loss = olp.ProjectionLoss(lpips_module=self.lp)
+        self.ref_per = olp.PerceptualLoss(lpips_module=self.lp)
+        sd = ts._lpips_state(self.lp)
+        self.model = BigGAN(config=ts._product_cfg(cfg), state_dict=self.orc.state_dict())
+        self.loss = ProjectionLoss(lpips_state_dict=sd)
+        self.per = PerceptualLoss(net="alex", lpips_state_dict=sd)
+        self.target, self.weight = synthetic_target(256, "cuda")
+        self.cfg = cfg
+
+    def vm(self, model):
+        from pix2latent_b200 import VariableManager
+        import pix2latent_b200.distribution as dist
+        import pix2latent_b200.utils.function_hooks as hook
+        vm = VariableManager(device="cuda")
+        vm.register(variable_name="z", shape=(128,), distribution=dist.TruncatedNormalModulo(sigma=1.0, trunc=2.0),
+                    var_type="input", learning_rate=0.05, hook_fn=hook.Clamp(2.0))
+        vm.register(variable_name="c", shape=(128,), default=model.get_class_embedding(153)[0], var_type="input",
+                    learning_rate=0.01)
+        vm.register(variable_name="target", shape=(3, 256, 256), requires_grad=False, default=self.target, var_type="output")
+        vm.register(variable_name="weight", shape=(3, 256, 256), requires_grad=False, default=self.weight, var_type="output")
+        return vm
+
+
+_worlds = {}
+
+
+def world(weights):
+    if weights not in _worlds:
+        _worlds.clear()  # one 256x256 world on the device at a time
+        torch.cuda.empty_cache()
+        _worlds[weights] = World(weights)
+    return _worlds[weights]
+
+
+@pytest.mark.parametrize("weights", ["calibrated", "bench_synth"])
+def test_replay_30_steps_c2(weights):
+    from oracle import closure as oc
+    from pix2latent_b200 import native
+    W = world(weights)
+    torch.manual_seed(2)
+    variables = W.vm(W.orc).initialize(N)
+    tgt = W.loss.prepared_target(W.target, W.weight)
+    tgt_per = W.per.prepared_target(W.target, W.weight)
+    dloss = torch.full((N,), 1.0 / CHUNK, device="cuda")
+    T = W.target[None].expand(N, -1, -1, -1)
+    Wt = W.weight[None].expand(N, -1, -1, -1)
+    worst, rows = 0.0, []
+    for k in range(STEPS + 1):
+        z = torch.stack(variables.input.z.data).detach().clamp(-2, 2)  # the Clamp hook runs first in the step
+        c = torch.stack(variables.input.c.data).detach()
+        l_nat, dz, dc, img = native.biggan_step(W.model.native, W.loss.native_lpips(), tgt, z, c, True, 1.0, dloss=dloss)
+        if k == 0:
+            zz, cc = z.clone().requires_grad_(True), c.clone().requires_grad_(True)
+            l0 = torch.cat([W.ref_loss(W.orc(z=zz[i:i + CHUNK], c=cc[i:i + CHUNK]), T[:CHUNK], Wt[:CHUNK]) for i in (0, CHUNK)])
+            (l0.sum() / CHUNK).backward()
+            cz, cc_ = cos(dz, zz.grad), cos(dc, cc.grad)
+            per_cand = min(cos(dz[i], zz.grad[i]) for i in range(N))
+            print("[%s] step 0: cos dz %.5f  cos dc %.5f  worst per-candidate cos dz %.5f  |dz| ratio %.4f"
+                  % (weights, cz, cc_, per_cand, (dz.norm() / zz.grad.norm()).item()))
+            assert cz >= (0.99 if weights == "calibrated" else 0.95) and cc_ >= (0.99 if weights == "calibrated" else 0.95)
+        if k == STEPS:
+            break
+        # advance the ORACLE trajectory; its per-candidate losses are those of the state the native step just saw
+        _, l_ref, _ = oc.step(W.orc, variables, W.ref_loss, optimize=True, max_batch_size=CHUNK)
+        l_ref = torch.tensor(np.array(l_ref), device="cuda")
+        err = ((l_nat - l_ref).abs() / (1 + l_ref.abs())).max().item()
+        rows.append(err)
+        worst = max(worst, err)
+    print("[%s] per-step max |dloss|/(1+|loss|):" % weights, " ".join("%.1e" % e for e in rows))
+    assert worst <= 2e-3, worst
+    # ---- final state (z_30, c_30): image, total loss, LPIPS term alone
+    with torch.no_grad():
+        ref_img = torch.cat([W.orc(z=z[i:i + CHUNK], c=c[i:i + CHUNK]) for i in (0, CHUNK)])
+        ref_l = W.ref_loss(ref_img, T, Wt)
+        ref_p = W.ref_per(ref_img, T, Wt)
+    nat_p = tgt_per.loss_forward(img, False)
+    d = (img - ref_img).abs()
+    frac_bad = (d > 2e-2).float().mean().item()
+    print("[%s] final image: max-abs %.3e, mean-abs %.3e, pixels beyond 2e-2: %.2e; final loss max |d| %.2e; "
+          "final LPIPS max |d| %.2e (values %.4f .. %.4f)"
+          % (weights, d.max().item(), d.mean().item(), frac_bad, (l_nat - ref_l).abs().max().item(),
+             (nat_p - ref_p).abs().max().item(), ref_p.min().item(), ref_p.max().item()))
+    assert (nat_p - ref_p).abs().max().item() <= 1e-3
+    assert frac_bad <= 1e-3 and d.max().item() <= 6e-2
+
+
+def test_fp64_truth_sets_the_tolerance():
+    """fp64 oracle = truth; error of the fp32 oracle and of the native path against it (2 candidates, step 0)."""
+    from oracle import biggan as obg, lpips as olp
+    from pix2latent_b200 import native
+    W = world("calibrated")
+    b = 2
+    torch.manual_seed(7)
+    z = torch.fmod(torch.randn(b, 128), 2.0).cuda()
+    c = W.orc.get_class_embedding(153).repeat(b, 1).clone()
+    orc64 = obg.make_biggan(W.cfg, seed=0, calibrate=True).double().cuda()
+    orc64.load_state_dict({k: v.double() for k, v in W.orc.state_dict().items()})
+    lp64 = olp.make_lpips("alex", seed=0, dtype=torch.float64).cuda()
+    loss64 = olp.ProjectionLoss(lpips_module=lp64)
+    res = {}
+    for name, orc, lossf, dt in (("fp64", orc64, loss64, torch.float64), ("fp32", W.orc, W.ref_loss, torch.float32)):
+        zz, cc = z.to(dt).requires_grad_(True), c.to(dt).requires_grad_(True)
+        img = orc(z=zz, c=cc)
+        l = lossf(img, W.target.to(dt)[None].expand(b, -1, -1, -1), W.weight.to(dt)[None].expand(b, -1, -1, -1))
+        l.sum().backward()
+        res[name] = (img.detach().double(), l.detach().double(), zz.grad.double(), cc.grad.double())
+    tgt = W.loss.prepared_target(W.target, W.weight)
+    l_nat, dz, dc, img = native.biggan_step(W.model.native, W.loss.native_lpips(), tgt, z, c, True, 1.0)
+    res["native"] = (img.double(), l_nat.double(), dz.double(), dc.double())
+    t = res["fp64"]
+    for name in ("fp32", "native"):
+        r = res[name]
+        print("%-6s vs fp64: image rel %.2e max-abs %.2e | loss |d| %.2e | dz rel %.2e cos %.6f | dc rel %.2e cos %.6f"
+              % (name, ((r[0] - t[0]).norm() / t[0].norm()).item(), (r[0] - t[0]).abs().max().item(),
+                 (r[1] - t[1]).abs().max().item(), ((r[2] - t[2]).norm() / t[2].norm()).item(), cos(r[2], t[2]),
+                 ((r[3] - t[3]).norm() / t[3].norm()).item(), cos(r[3], t[3])))
+    r = res["native"]
+    assert ((r[0] - t[0]).norm() / t[0].norm()).item() < 2e-2
+    assert (r[1] - t[1]).abs().max().item() < 2e-3 * (1 + t[1].abs().max().item())
+    assert cos(r[2], t[2]) > 0.99 and cos(r[3], t[3]) > 0.99
+
+
+def test_free_run_30_steps_c2():
+    """The product's own loop (GradientOptimizer: device-resident Adam, CUDA graph) against the oracle's, free-running
+    from the same start. Round-off is amplified along a 30-step trajectory on a random-init generator, so this bounds
+    the OUTCOME (what an inversion returns): the final losses and the final LPIPS of the population."""
+    from oracle import closure as oc
+    from pix2latent_b200.optimizer import GradientOptimizer
+    W = world("calibrated")
+    T = W.target[None].expand(N, -1, -1, -1)
+    Wt = W.weight[None].expand(N, -1, -1, -1)
+    torch.manual_seed(2)
+    v_ref = W.vm(W.orc).initialize(N)
+    z0 = torch.stack(v_ref.input.z.data).clone()
+    for _ in range(STEPS):
+        oc.step(W.orc, v_ref, W.ref_loss, optimize=True, max_batch_size=CHUNK)
+    with torch.no_grad():
+        z = torch.stack(v_ref.input.z.data).clamp(-2, 2)
+        c = torch.stack(v_ref.input.c.data)
+        ref_img = torch.cat([W.orc(z=z[i:i + CHUNK], c=c[i:i + CHUNK]) for i in (0, CHUNK)])
+        ref_l, ref_p = W.ref_loss(ref_img, T, Wt), W.ref_per(ref_img, T, Wt)
+    torch.manual_seed(2)
+    opt = GradientOptimizer(W.model, W.vm(W.model), W.loss, max_batch_size=CHUNK)
+    v_nat, outs, losses = opt.optimize(num_samples=N, grad_steps=STEPS)
+    assert opt.fused_calls == 1
+    assert torch.equal(opt.tracked["z"][0].cuda(), z0), "both runs start from the same latents"
+    with torch.no_grad():
+        zn = torch.stack(v_nat.input.z.data).clamp(-2, 2)
+        cn = torch.stack(v_nat.input.c.data)
+        nat_img = W.model.native.forward(zn, cn)
+        nat_l = W.loss(nat_img, T, Wt).view(-1)
+        nat_p = W.per(nat_img, T, Wt).view(-1)
+    print("free run, %d steps: final loss  oracle mean %.4f best %.4f | native mean %.4f best %.4f | per-candidate |d| max %.3e mean %.3e"
+          % (STEPS, ref_l.mean().item(), ref_l.min().item(), nat_l.mean().item(), nat_l.min().item(),
+             (nat_l - ref_l).abs().max().item(), (nat_l - ref_l).abs().mean().item()))
+    print("free run: final LPIPS oracle mean %.5f best %.5f | native mean %.5f best %.5f | per-candidate |d| max %.3e mean %.3e; z drift mean %.3e"
+          % (ref_p.mean().item(), ref_p.min().item(), nat_p.mean().item(), nat_p.min().item(),
+             (nat_p - ref_p).abs().max().item(), (nat_p - ref_p).abs().mean().item(), (zn - z).abs().mean().item()))
+    assert abs(nat_p.mean().item() - ref_p.mean().item()) <= 1e-3
+    assert abs(nat_l.mean().item() - ref_l.mean().item()) <= 2e-2 * (1 + abs(ref_l.mean().item()))
