@@ -54,12 +54,11 @@ typedef struct p2l_conv_args {
     const float* rowsub;
     const void* mulin;
     int mulin_C;
-    /* split-K workspace (used when the "splitk" option is on) */
-    float* splitk_ws;
-    long splitk_ws_floats;
     /* transposed 16-bit copy of the main output (fwd: raw, bwd: dx), channels [outT_c0, outT_c1): [NI][c][H*W] */
     void* outT;
     int outT_c0, outT_c1;
+    /* walk the tiles from the last to the first (same result) */
+    int tile_reverse;
 } p2l_conv_args;
 
 /* returns 0 on success, <0 on error (see p2l_last_error) */

@@ -66,8 +66,7 @@ class ConvArgs(C.Structure):
         ("dx_f32", C.c_void_p), ("dx_f32_C", C.c_int),
         ("rowstat", C.c_void_p), ("rowstat_in", C.c_void_p), ("rowstat_nt", C.c_int),
         ("rowsub", C.c_void_p), ("mulin", C.c_void_p), ("mulin_C", C.c_int),
-        ("splitk_ws", C.c_void_p), ("splitk_ws_floats", C.c_long),
-        ("outT", C.c_void_p), ("outT_c0", C.c_int), ("outT_c1", C.c_int),
+        ("outT", C.c_void_p), ("outT_c0", C.c_int), ("outT_c1", C.c_int), ("tile_reverse", C.c_int),
     ]
 
 

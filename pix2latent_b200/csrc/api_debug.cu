@@ -42,7 +42,7 @@ P2L_EXPORT int p2l_debug_conv(const p2l_conv_args* a, void* cuda_stream) {
     e.dx_f32 = a->dx_f32; e.dx_f32_C = a->dx_f32_C;
     e.rowstat = a->rowstat; e.rowstat_in = a->rowstat_in; e.rowstat_nt = a->rowstat_nt;
     e.rowsub = a->rowsub; e.mulin = static_cast<const act_t*>(a->mulin); e.mulin_C = a->mulin_C;
-    d.splitk_ws = a->splitk_ws; d.splitk_ws_floats = a->splitk_ws_floats;
+    e.tile_reverse = a->tile_reverse;
     ConvOp op;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     int rc = conv_op_build(&op, d);

@@ -22,13 +22,9 @@ struct BigGANPlan {
     // latent side
     float *cond = nullptr, *a = nullptr, *s = nullptr, *S0 = nullptr, *S1 = nullptr, *G = nullptr, *dcond = nullptr,
           *dh0 = nullptr, *ones = nullptr;
-    struct Sub { int n0, ns; };  // candidates [n0, n0 + ns) of the batch
     struct BB {
         act_t *in_raw, *in_act, *t1_lo, *t1, *t2, *t3, *out_raw, *out_act;
-        // L2-resident sub-batching ("sub_mb" option): the block's launches run sub-batch by sub-batch, so that what
-        // one convolution writes is still in the 126 MB L2 when the next one reads it
-        std::vector<Sub> subs;
-        std::vector<ConvOp> f[4], d[4];  // [conv][sub-batch]
+        ConvOp f[4], d[4];
         // BN-affine gradient partial sums of bn_0..bn_3 ([n][part][2][C], ConvGemmParams::statp)
         float* sp[4] = {nullptr, nullptr, nullptr, nullptr};
         int sp_parts[4] = {0, 0, 0, 0};
@@ -44,8 +40,6 @@ struct BigGANPlan {
     act_t *dO = nullptr, *dOT = nullptr, *dS = nullptr, *dST = nullptr, *PT = nullptr, *thetaT = nullptr,
                   *dqkv = nullptr, *dphi_p = nullptr, *dg_p = nullptr;
     ConvOp a_qkv, a_s, a_o, a_out, ad_out, ad_p, ad_theta, ad_phi, ad_g, ad_qkv;
-    float* ks_ws = nullptr;  // split-K workspace ("splitk" option)
-    long ks_ws_floats = 0;
     // "attn_fused": two-pass softmax in the S GEMM's epilogue, dS in the dP GEMM's epilogue (no fp32 logits in HBM);
     // "attn_emit_t" (needs attn_fused): theta^T, P^T, dO^T, dS^T come out of the producing epilogues (no transposes)
     bool attn_fused = false, attn_emit_t = false;
@@ -298,34 +292,6 @@ struct OpB {  // small builder
     }
 };
 
-// Sub-batches of one block: sized so that the largest working set of its four convolutions (operand + outputs + skip,
-// per candidate) fits `sub_mb` MB of L2, but never so small that a launch has fewer than `min_tiles` 128-pixel tiles
-// (a partial last wave would cost more than the HBM traffic saved). Near-even split.
-static std::vector<BigGANPlan::Sub> pick_subs(int b, int in, int mid, int out, int Hin, int Hout, bool up, int sub_mb, int min_tiles) {
-    std::vector<BigGANPlan::Sub> v;
-    int nsub = 1;
-    if (sub_mb > 0) {
-        const double pin = (double)Hin * Hin, pout = (double)Hout * Hout;
-        const double w0 = pin * in + pout * mid + (up ? pin * mid : 0.0);
-        const double w1 = 2.0 * pout * mid;
-        const double w3 = pout * mid + pin * out + 2.0 * pout * out;
-        const double ws = 2.0 * std::max(w0, std::max(w1, w3));  // bytes per candidate
-        long sub = (long)(sub_mb * 1048576.0 / ws);
-        const long tiles_per = ((long)Hout * Hout + 127) / 128;
-        const long min_sub = (min_tiles + tiles_per - 1) / tiles_per;
-        if (sub < min_sub) sub = min_sub;
-        if (sub < 1) sub = 1;
-        if (sub < b) nsub = (int)((b + sub - 1) / sub);
-    }
-    int n0 = 0;
-    for (int k = 0; k < nsub; ++k) {
-        const int ns = b / nsub + (k < b % nsub ? 1 : 0);
-        v.push_back({n0, ns});
-        n0 += ns;
-    }
-    return v;
-}
-
 BigGANPlan* BigGAN::plan(int b) {
     auto it = plans.find(b);
     if (it != plans.end()) return it->second.get();
@@ -345,7 +311,6 @@ BigGANPlan* BigGAN::plan(int b) {
     const int nL = (int)blocks.size();
     P.bb.resize(nL);
     size_t max_dh = 0, max_g = 0;
-    const int sub_mb = get_option("sub_mb"), sub_min_tiles = get_option("sub_min_tiles");
     // activations
     act_t *cur_raw = ar.alloc<bf>((size_t)b * genz_J), *cur_act = ar.alloc<bf>((size_t)b * genz_J);
     for (int i = 0; i < nL; ++i) {
@@ -372,7 +337,6 @@ BigGANPlan* BigGAN::plan(int b) {
         cur_act = B.out_act;
         max_dh = std::max(max_dh, std::max(pout * bl.out, pin * bl.in));
         max_g = std::max(max_g, pout * bl.mid);
-        B.subs = pick_subs(b, bl.in, bl.mid, bl.out, bl.Hin, bl.Hout, bl.up, sub_mb, sub_min_tiles);
         // BN-gradient partial buffers: bn_0 is filled by d0 (input grid), bn_1 by d1 (or the pooling kernel of an up
         // block, input grid), bn_2 / bn_3 by d2 / d3 (output grid)
         const int cs[4] = {bl.in, bl.mid, bl.mid, bl.mid};
@@ -393,129 +357,115 @@ BigGANPlan* BigGAN::plan(int b) {
     P.rgbT = ar.alloc<float>((size_t)b * 27 * R * R);
     if (ar.failed) return nullptr;
 
-    if (get_option("splitk") > 0) {
-        P.ks_ws_floats = 16L << 20;  // 64 MB: 8 splits of the largest eligible launch (M = 1152, N = 2048)
-        P.ks_ws = ar.alloc<float>((size_t)P.ks_ws_floats);
-        if (ar.failed) return nullptr;
-    }
     auto build = [&](ConvOp* op, OpB& ob, double* flops, int* launches) -> int {
-        ob.d.splitk_ws = P.ks_ws;
-        ob.d.splitk_ws_floats = P.ks_ws_floats;
         if (conv_op_build(op, ob.d)) return -1;
         *flops += op->flops;
         *launches += 1;
         return 0;
     };
     std::vector<StatSeg> segs;
-    // ---- per-block ops, one set per sub-batch (every pointer below is offset to the sub-batch's first candidate)
+    // ---- per-block ops
     for (int i = 0; i < nL; ++i) {
         const Block& bl = blocks[i];
         BigGANPlan::BB& B = P.bb[i];
         const int Hi = bl.Hin, Ho = bl.Hout;
-        const size_t pi = (size_t)Hi * Hi, po = (size_t)Ho * Ho;  // pixels per candidate
         const bool attn_next = attn.C && (i + 1 == cfg.attention_pos);
         const int next_bn = (i + 1 < nL) ? blocks[i + 1].bn[0] : final_bn;
         act_t* dh_out = ((nL - 1 - i) % 2 == 0) ? P.dhA : P.dhB;  // dh_out lives in dhA when (nL-1-i) is even, dh_in goes to the other
         act_t* dh_in = ((nL - 1 - i) % 2 == 0) ? P.dhB : P.dhA;
-        const int nsub = (int)B.subs.size();
-        for (int k = 0; k < 4; ++k) { B.f[k].resize(nsub); B.d[k].resize(nsub); }
         int parts_used[4] = {0, 0, 0, 0};
-        for (int si = 0; si < nsub; ++si) {
-            const int n0 = B.subs[si].n0, ns = B.subs[si].ns;
-            const float* aff_a = P.a + (size_t)n0 * C_all;
-            const float* aff_s = P.s + (size_t)n0 * C_all;
-            auto stat = [&](ConvGemmParams& e, int k, int C) {
-                e.statp = B.sp[k] + (size_t)n0 * B.sp_parts[k] * 2 * C; e.statp_parts = B.sp_parts[k]; e.statp_C = C;
-            };
-            {   // f0: 1x1 in->mid on in_act; epilogue bn_1+relu (+x2 replicate)
-                OpB o(B.in_act + n0 * pi * bl.in, ns, Hi, Hi, bl.in, 0, bl.in, bl.w[0], bl.mid, 1, EPI_FWD);
-                ConvGemmParams& e = o.d.epi;
-                e.bias = bl.bias[0];
-                e.aff_a = aff_a + bns[bl.bn[1]].off; e.aff_s = aff_s + bns[bl.bn[1]].off; e.aff_stride = C_all; e.relu = 1;
-                e.act = B.t1 + n0 * po * bl.mid; e.act_C = bl.mid; e.act_up = bl.up ? 1 : 0;
-                e.act_lo = bl.up ? B.t1_lo + n0 * pi * bl.mid : nullptr;
-                if (build(&B.f[0][si], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
+        const float *aff_a = P.a, *aff_s = P.s;
+        auto stat = [&](ConvGemmParams& e, int k, int C) {
+            e.statp = B.sp[k]; e.statp_parts = B.sp_parts[k]; e.statp_C = C;
+        };
+        {   // f0: 1x1 in->mid on in_act; epilogue bn_1+relu (+x2 replicate)
+            OpB o(B.in_act, b, Hi, Hi, bl.in, 0, bl.in, bl.w[0], bl.mid, 1, EPI_FWD);
+            ConvGemmParams& e = o.d.epi;
+            e.bias = bl.bias[0];
+            e.aff_a = aff_a + bns[bl.bn[1]].off; e.aff_s = aff_s + bns[bl.bn[1]].off; e.aff_stride = C_all; e.relu = 1;
+            e.act = B.t1; e.act_C = bl.mid; e.act_up = bl.up ? 1 : 0;
+            e.act_lo = bl.up ? B.t1_lo : nullptr;
+            if (build(&B.f[0], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
+        }
+        {   // f1: 3x3 mid->mid
+            OpB o(B.t1, b, Ho, Ho, bl.mid, 0, bl.mid, bl.w[1], bl.mid, 3, EPI_FWD);
+            ConvGemmParams& e = o.d.epi;
+            e.bias = bl.bias[1];
+            e.aff_a = aff_a + bns[bl.bn[2]].off; e.aff_s = aff_s + bns[bl.bn[2]].off; e.aff_stride = C_all; e.relu = 1;
+            e.act = B.t2; e.act_C = bl.mid;
+            if (build(&B.f[1], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
+        }
+        {   // f2
+            OpB o(B.t2, b, Ho, Ho, bl.mid, 0, bl.mid, bl.w[2], bl.mid, 3, EPI_FWD);
+            ConvGemmParams& e = o.d.epi;
+            e.bias = bl.bias[2];
+            e.aff_a = aff_a + bns[bl.bn[3]].off; e.aff_s = aff_s + bns[bl.bn[3]].off; e.aff_stride = C_all; e.relu = 1;
+            e.act = B.t3; e.act_C = bl.mid;
+            if (build(&B.f[2], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
+        }
+        {   // f3: 1x1 mid->out + skip; raw; next BN + relu
+            OpB o(B.t3, b, Ho, Ho, bl.mid, 0, bl.mid, bl.w[3], bl.out, 1, EPI_FWD);
+            ConvGemmParams& e = o.d.epi;
+            e.bias = bl.bias[3];
+            e.resid = B.in_raw; e.resid_C = bl.in; e.resid_shift = bl.up ? 1 : 0;
+            // the raw (pre-BN) output feeds the next block's skip / the attention; after the last block
+            // nothing reads it
+            if (i + 1 < nL) { e.raw = B.out_raw; e.raw_C = bl.out; }
+            if (!attn_next) {
+                e.aff_a = aff_a + bns[next_bn].off; e.aff_s = aff_s + bns[next_bn].off; e.aff_stride = C_all; e.relu = 1;
+                e.act = B.out_act; e.act_C = bl.out;
             }
-            {   // f1: 3x3 mid->mid
-                OpB o(B.t1 + n0 * po * bl.mid, ns, Ho, Ho, bl.mid, 0, bl.mid, bl.w[1], bl.mid, 3, EPI_FWD);
-                ConvGemmParams& e = o.d.epi;
-                e.bias = bl.bias[1];
-                e.aff_a = aff_a + bns[bl.bn[2]].off; e.aff_s = aff_s + bns[bl.bn[2]].off; e.aff_stride = C_all; e.relu = 1;
-                e.act = B.t2 + n0 * po * bl.mid; e.act_C = bl.mid;
-                if (build(&B.f[1][si], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
+            if (build(&B.f[3], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
+        }
+        // ---- backward ops
+        {   // d3: dh_out -> g3 (through bn_3/relu)
+            OpB o(dh_out, b, Ho, Ho, bl.out, 0, bl.out, bl.wt[3], bl.mid, 1, EPI_BWD);
+            ConvGemmParams& e = o.d.epi;
+            e.saved = B.t3; e.saved_C = bl.mid;
+            stat(e, 3, bl.mid);
+            e.aff_a = aff_a + bns[bl.bn[3]].off; e.aff_stride = C_all;
+            e.dx = P.g3; e.dx_C = bl.mid;
+            if (build(&B.d[3], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
+            parts_used[3] = B.d[3].stat_parts;
+        }
+        {   // d2: g3 -> g2 (through bn_2/relu)
+            OpB o(P.g3, b, Ho, Ho, bl.mid, 0, bl.mid, bl.wt[2], bl.mid, 3, EPI_BWD);
+            ConvGemmParams& e = o.d.epi;
+            e.saved = B.t2; e.saved_C = bl.mid;
+            stat(e, 2, bl.mid);
+            e.aff_a = aff_a + bns[bl.bn[2]].off; e.aff_stride = C_all;
+            e.dx = P.g2; e.dx_C = bl.mid;
+            if (build(&B.d[2], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
+            parts_used[2] = B.d[2].stat_parts;
+        }
+        {   // d1: g2 -> g1 (bn_1/relu; through the x2 upsample when bl.up: plain dgrad into g3, pooled later)
+            OpB o(P.g2, b, Ho, Ho, bl.mid, 0, bl.mid, bl.wt[1], bl.mid, 3, EPI_BWD);
+            ConvGemmParams& e = o.d.epi;
+            if (!bl.up) {
+                e.saved = B.t1_lo; e.saved_C = bl.mid;
+                stat(e, 1, bl.mid);
+                e.aff_a = aff_a + bns[bl.bn[1]].off; e.aff_stride = C_all;
+                e.dx = P.g1; e.dx_C = bl.mid;
+            } else {
+                e.dx = P.g3; e.dx_C = bl.mid;  // g3 is free again: holds the hi-res gradient
+                P.launches_bwd += 1;           // + k_pool_bnrelu_bwd
             }
-            {   // f2
-                OpB o(B.t2 + n0 * po * bl.mid, ns, Ho, Ho, bl.mid, 0, bl.mid, bl.w[2], bl.mid, 3, EPI_FWD);
-                ConvGemmParams& e = o.d.epi;
-                e.bias = bl.bias[2];
-                e.aff_a = aff_a + bns[bl.bn[3]].off; e.aff_s = aff_s + bns[bl.bn[3]].off; e.aff_stride = C_all; e.relu = 1;
-                e.act = B.t3 + n0 * po * bl.mid; e.act_C = bl.mid;
-                if (build(&B.f[2][si], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
-            }
-            {   // f3: 1x1 mid->out + skip; raw; next BN + relu
-                OpB o(B.t3 + n0 * po * bl.mid, ns, Ho, Ho, bl.mid, 0, bl.mid, bl.w[3], bl.out, 1, EPI_FWD);
-                ConvGemmParams& e = o.d.epi;
-                e.bias = bl.bias[3];
-                e.resid = B.in_raw + n0 * pi * bl.in; e.resid_C = bl.in; e.resid_shift = bl.up ? 1 : 0;
-                // the raw (pre-BN) output feeds the next block's skip / the attention; after the last block
-                // nothing reads it
-                if (i + 1 < nL) { e.raw = B.out_raw + n0 * po * bl.out; e.raw_C = bl.out; }
-                if (!attn_next) {
-                    e.aff_a = aff_a + bns[next_bn].off; e.aff_s = aff_s + bns[next_bn].off; e.aff_stride = C_all; e.relu = 1;
-                    e.act = B.out_act + n0 * po * bl.out; e.act_C = bl.out;
-                }
-                if (build(&B.f[3][si], o, &P.flops_fwd, &P.launches_fwd)) return nullptr;
-            }
-            // ---- backward ops
-            {   // d3: dh_out -> g3 (through bn_3/relu)
-                OpB o(dh_out + n0 * po * bl.out, ns, Ho, Ho, bl.out, 0, bl.out, bl.wt[3], bl.mid, 1, EPI_BWD);
-                ConvGemmParams& e = o.d.epi;
-                e.saved = B.t3 + n0 * po * bl.mid; e.saved_C = bl.mid;
-                stat(e, 3, bl.mid);
-                e.aff_a = aff_a + bns[bl.bn[3]].off; e.aff_stride = C_all;
-                e.dx = P.g3 + n0 * po * bl.mid; e.dx_C = bl.mid;
-                if (build(&B.d[3][si], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
-                parts_used[3] = B.d[3][si].stat_parts;
-            }
-            {   // d2: g3 -> g2 (through bn_2/relu)
-                OpB o(P.g3 + n0 * po * bl.mid, ns, Ho, Ho, bl.mid, 0, bl.mid, bl.wt[2], bl.mid, 3, EPI_BWD);
-                ConvGemmParams& e = o.d.epi;
-                e.saved = B.t2 + n0 * po * bl.mid; e.saved_C = bl.mid;
-                stat(e, 2, bl.mid);
-                e.aff_a = aff_a + bns[bl.bn[2]].off; e.aff_stride = C_all;
-                e.dx = P.g2 + n0 * po * bl.mid; e.dx_C = bl.mid;
-                if (build(&B.d[2][si], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
-                parts_used[2] = B.d[2][si].stat_parts;
-            }
-            {   // d1: g2 -> g1 (bn_1/relu; through the x2 upsample when bl.up: plain dgrad into g3, pooled later)
-                OpB o(P.g2 + n0 * po * bl.mid, ns, Ho, Ho, bl.mid, 0, bl.mid, bl.wt[1], bl.mid, 3, EPI_BWD);
-                ConvGemmParams& e = o.d.epi;
-                if (!bl.up) {
-                    e.saved = B.t1_lo + n0 * pi * bl.mid; e.saved_C = bl.mid;
-                    stat(e, 1, bl.mid);
-                    e.aff_a = aff_a + bns[bl.bn[1]].off; e.aff_stride = C_all;
-                    e.dx = P.g1 + n0 * pi * bl.mid; e.dx_C = bl.mid;
-                } else {
-                    e.dx = P.g3 + n0 * po * bl.mid; e.dx_C = bl.mid;  // g3 is free again: holds the hi-res gradient
-                    P.launches_bwd += 1;           // + k_pool_bnrelu_bwd
-                }
-                if (build(&B.d[1][si], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
-                parts_used[1] = bl.up ? B.sp_parts[1] : B.d[1][si].stat_parts;
-            }
-            {   // d0: g1 -> dh_in (bn_0/relu) + skip gradient
-                OpB o(P.g1 + n0 * pi * bl.mid, ns, Hi, Hi, bl.mid, 0, bl.mid, bl.wt[0], bl.in, 1, EPI_BWD);
-                ConvGemmParams& e = o.d.epi;
-                e.saved = B.in_act + n0 * pi * bl.in; e.saved_C = bl.in;
-                stat(e, 0, bl.in);
-                e.aff_a = aff_a + bns[bl.bn[0]].off; e.aff_stride = C_all;
-                // skip gradient: dh_out itself, or (up block) its 2x2-pooled copy written by k_pool2x2_sum
-                e.addin = bl.up ? P.dh_pool + n0 * pi * bl.out : dh_out + n0 * po * bl.out;
-                e.addin_C = bl.out; e.addin_climit = bl.out; e.addin_pool = 0;
-                e.dx = dh_in + n0 * pi * bl.in; e.dx_C = bl.in;
-                if (i == 0) { e.dx_f32 = P.dh0 + n0 * pi * bl.in; e.dx_f32_C = bl.in; }
-                if (build(&B.d[0][si], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
-                parts_used[0] = B.d[0][si].stat_parts;
-            }
+            if (build(&B.d[1], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
+            parts_used[1] = bl.up ? B.sp_parts[1] : B.d[1].stat_parts;
+        }
+        {   // d0: g1 -> dh_in (bn_0/relu) + skip gradient
+            OpB o(P.g1, b, Hi, Hi, bl.mid, 0, bl.mid, bl.wt[0], bl.in, 1, EPI_BWD);
+            ConvGemmParams& e = o.d.epi;
+            e.saved = B.in_act; e.saved_C = bl.in;
+            stat(e, 0, bl.in);
+            e.aff_a = aff_a + bns[bl.bn[0]].off; e.aff_stride = C_all;
+            // skip gradient: dh_out itself, or (up block) its 2x2-pooled copy written by k_pool2x2_sum
+            e.addin = bl.up ? P.dh_pool : dh_out;
+            e.addin_C = bl.out; e.addin_climit = bl.out; e.addin_pool = 0;
+            e.dx = dh_in; e.dx_C = bl.in;
+            if (i == 0) { e.dx_f32 = P.dh0; e.dx_f32_C = bl.in; }
+            if (build(&B.d[0], o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
+            parts_used[0] = B.d[0].stat_parts;
         }
         const int cs[4] = {bl.in, bl.mid, bl.mid, bl.mid};
         for (int k = 0; k < 4; ++k)
@@ -555,7 +505,9 @@ BigGANPlan* BigGAN::plan(int b) {
         P.launches_fwd += 3;  // 2 pools + softmax
         P.launches_bwd += 8;  // transposes x4, softmax bwd, pool bwd x2 ... (counted below as launched)
         P.attn_fused = get_option("attn_fused") != 0;
-        P.attn_emit_t = P.attn_fused && get_option("attn_emit_t") != 0;
+        // the transposed operands come out of the TMA-I/O (qkv, dO) and row-fusion (P, dS) kernels: K <= tma_kmax there
+        P.attn_emit_t = P.attn_fused && get_option("attn_emit_t") != 0 && get_option("tma_out") != 0 &&
+                        C <= get_option("tma_kmax") && nq % 64 == 0 && dv % 64 == 0;
         {   // qkv = x W_qkv^T
             OpB o(x_raw, b, H, H, C, 0, C, attn.wqkv, nq, 1, EPI_FWD);
             o.d.epi.raw = P.qkv; o.d.epi.raw_C = nq;
@@ -667,6 +619,33 @@ BigGANPlan* BigGAN::plan(int b) {
         if (build(&P.d_rgb, o, &P.flops_bwd, &P.launches_bwd)) return nullptr;
         P.launches_bwd += 1;  // im2col
     }
+    // ---- serpentine tile order: the k-th tensor-core launch of a pass walks its tiles backwards when k is odd, so that
+    // every layer starts on the tiles its producer wrote last (still in L2) — same results, the BN-gradient partial
+    // slots are indexed by tile, not by arrival order
+    if (get_option("serpentine") != 0) {
+        std::vector<ConvOp*> fs, bs;
+        for (int i = 0; i < nL; ++i) {
+            if (attn.C && i == cfg.attention_pos) {
+                fs.push_back(&P.a_qkv);
+                if (P.attn_fused) { fs.push_back(&P.a_s1); fs.push_back(&P.a_s2); } else fs.push_back(&P.a_s);
+                fs.push_back(&P.a_o);
+                fs.push_back(&P.a_out);
+            }
+            for (int k = 0; k < 4; ++k) fs.push_back(&P.bb[i].f[k]);
+        }
+        fs.push_back(&P.f_rgb);
+        bs.push_back(&P.d_rgb);
+        for (int i = nL - 1; i >= 0; --i) {
+            for (int k = 3; k >= 0; --k) bs.push_back(&P.bb[i].d[k]);
+            if (attn.C && i == cfg.attention_pos) {
+                bs.push_back(&P.ad_out);
+                bs.push_back(P.attn_fused ? &P.ad_pf : &P.ad_p);
+                bs.push_back(&P.ad_theta); bs.push_back(&P.ad_phi); bs.push_back(&P.ad_g); bs.push_back(&P.ad_qkv);
+            }
+        }
+        for (size_t k = 0; k < fs.size(); ++k) fs[k]->p.tile_reverse = (int)(k & 1);
+        for (size_t k = 0; k < bs.size(); ++k) bs[k]->p.tile_reverse = (int)(k & 1);
+    }
     P.launches_fwd += 4;  // concat, cond_affine, uncond_affine, gen_z
     P.launches_bwd += 6;  // memsets + finalize + dcond x2 + convert + split
     BigGANPlan* raw = pp.get();
@@ -705,10 +684,8 @@ int BigGAN::forward(int b, const float* z, const float* c, float* img, cudaStrea
             if (conv_op_launch(P.a_o, st)) return -1;
             if (conv_op_launch(P.a_out, st)) return -1;
         }
-        const BigGANPlan::BB& B = P.bb[i];
-        for (size_t si = 0; si < B.subs.size(); ++si)
-            for (int k = 0; k < 4; ++k)
-                if (conv_op_launch(B.f[k][si], st)) return -1;
+        for (int k = 0; k < 4; ++k)
+            if (conv_op_launch(P.bb[i].f[k], st)) return -1;
     }
     if (conv_op_launch(P.f_rgb, st)) return -1;
     k_rgb_gather(P.rgbT, brgb, img ? img : P.img, b, H_out, H_out, st);
@@ -738,22 +715,16 @@ int BigGAN::backward(int b, const float* dimg, float* dz, float* dc, cudaStream_
     for (int i = nL - 1; i >= 0; --i) {
         const Block& bl = blocks[i];
         BigGANPlan::BB& B = P.bb[i];
-        const size_t pi = (size_t)bl.Hin * bl.Hin, po = (size_t)bl.Hout * bl.Hout;
-        for (size_t si = 0; si < B.subs.size(); ++si) {
-            const int n0 = B.subs[si].n0, ns = B.subs[si].ns;
-            if (conv_op_launch(B.d[3][si], st)) return -1;
-            if (conv_op_launch(B.d[2][si], st)) return -1;
-            if (conv_op_launch(B.d[1][si], st)) return -1;
-            if (bl.up) {
-                const BN& bn1 = bns[bl.bn[1]];
-                k_pool_bnrelu_bwd(P.g3 + n0 * po * bl.mid, B.t1_lo + n0 * pi * bl.mid, P.a + (size_t)n0 * C_all + bn1.off, C_all,
-                                  B.sp[1] + (size_t)n0 * B.sp_parts[1] * 2 * bl.mid, P.g1 + n0 * pi * bl.mid, ns, bl.Hin, bl.Hin,
-                                  bl.mid, st);
-                act_t* dh_out = ((nL - 1 - i) % 2 == 0) ? P.dhA : P.dhB;
-                k_pool2x2_sum(dh_out + n0 * po * bl.out, bl.out, P.dh_pool + n0 * pi * bl.out, ns, bl.Hin, bl.Hin, bl.out, st);
-            }
-            if (conv_op_launch(B.d[0][si], st)) return -1;
+        if (conv_op_launch(B.d[3], st)) return -1;
+        if (conv_op_launch(B.d[2], st)) return -1;
+        if (conv_op_launch(B.d[1], st)) return -1;
+        if (bl.up) {
+            const BN& bn1 = bns[bl.bn[1]];
+            k_pool_bnrelu_bwd(P.g3, B.t1_lo, P.a + bn1.off, C_all, B.sp[1], P.g1, b, bl.Hin, bl.Hin, bl.mid, st);
+            act_t* dh_out = ((nL - 1 - i) % 2 == 0) ? P.dhA : P.dhB;
+            k_pool2x2_sum(dh_out, bl.out, P.dh_pool, b, bl.Hin, bl.Hin, bl.out, st);
         }
+        if (conv_op_launch(B.d[0], st)) return -1;
         if (attn.C && i == cfg.attention_pos) {
             const int H = attn.H, dq = attn.dq, dv = attn.dv, nq = 2 * dq + dv;
             const int Nq = H * H, Nk = Nq / 4;

@@ -26,12 +26,9 @@ void add_launches(long n) { g_launches += n; }
 long launch_count() { return g_launches; }
 
 static int g_tma_out = 1, g_tma_kmax = 512;
-static int g_splitk = 0;      // "splitk": split-K over idle SMs for few-tile / long-K launches
 static int g_attn_fused = 0;  // "attn_fused": two-pass softmax + fused dS in the attention GEMM epilogues
 static int g_attn_emit_t = 0; // "attn_emit_t": the attention backward's transposed operands come out of the producing epilogues
-static int g_prefetch_saved = 0;  // "prefetch_saved": backward epilogue of the N = 64 one-CTA-per-SM kernels fetches the saved rows early
-static int g_sub_mb = 0;      // "sub_mb": L2 budget (MB) for sub-batching the high-resolution generator blocks (0: off)
-static int g_sub_min_tiles = 592;  // "sub_min_tiles": a sub-batch keeps at least this many 128-pixel tiles per launch
+static int g_serpentine = 1;  // "serpentine": consecutive layers walk their tiles in opposite directions (L2 reuse of the producer's last writes)
 static int g_pdl = 1;  // "pdl": launch the tensor-core kernel with programmatic stream serialization (prologue overlaps the previous kernel's tail)
 static int g_deep = 1, g_deep_kmin = 8;  // "deep": full-depth single-CTA pipeline for launches with <= #SM tiles and >= deep_kmin K blocks
 static int g_grad_scale = (int)kGradScale;
@@ -51,11 +48,8 @@ void set_option(const char* key, int value) {
     else if (!std::strcmp(key, "tma_kmax")) g_tma_kmax = value;
     else if (!std::strcmp(key, "pdl")) g_pdl = value;
     else if (!std::strcmp(key, "attn_fused")) g_attn_fused = value;
-    else if (!std::strcmp(key, "splitk")) g_splitk = value;
     else if (!std::strcmp(key, "attn_emit_t")) g_attn_emit_t = value;
-    else if (!std::strcmp(key, "prefetch_saved")) g_prefetch_saved = value;
-    else if (!std::strcmp(key, "sub_mb")) g_sub_mb = value;
-    else if (!std::strcmp(key, "sub_min_tiles")) g_sub_min_tiles = value;
+    else if (!std::strcmp(key, "serpentine")) g_serpentine = value;
     else if (!std::strcmp(key, "deep")) g_deep = value;
     else if (!std::strcmp(key, "deep_kmin")) g_deep_kmin = value;
 }
@@ -68,13 +62,8 @@ int get_option(const char* key) {
     if (!std::strcmp(key, "tma_kmax")) return g_tma_kmax;
     if (!std::strcmp(key, "pdl")) return g_pdl;
     if (!std::strcmp(key, "attn_fused")) return g_attn_fused;
-    if (!std::strcmp(key, "rowfuse_built")) return 1;
-    if (!std::strcmp(key, "splitk")) return g_splitk;
-    if (!std::strcmp(key, "splitk_built")) return 1;
     if (!std::strcmp(key, "attn_emit_t")) return g_attn_emit_t;
-    if (!std::strcmp(key, "prefetch_saved")) return g_prefetch_saved;
-    if (!std::strcmp(key, "sub_mb")) return g_sub_mb;
-    if (!std::strcmp(key, "sub_min_tiles")) return g_sub_min_tiles;
+    if (!std::strcmp(key, "serpentine")) return g_serpentine;
     if (!std::strcmp(key, "deep")) return g_deep;
     if (!std::strcmp(key, "deep_kmin")) return g_deep_kmin;
     return -1;
@@ -252,7 +241,6 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
         op->halo_smem = (int)(p.halo_sa * patch + (p.halo_resb ? resb_bytes : p.halo_sb * btile) + fixed);
     }
     if (p.alpha == 0.f) p.alpha = 1.f;
-    p.prefetch_saved = g_prefetch_saved;
     // partial slots per image of the BN-gradient sums this launch fills (see ConvGemmParams::statp)
     op->stat_parts = (nb == 1) ? p.tiles_w * p.tiles_h : ((tw * th >= 32) ? (tw * th) / 32 : 1);
     if (d.epi.statp && op->stat_parts > d.epi.statp_parts) {
@@ -316,46 +304,36 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
             }
         }
     }
+    const bool rowfuse = d.epi.rowstat || d.epi.rowstat_in || d.epi.mulin || d.epi.rowsub;
+    if (rowfuse && (d.mode != EPI_FWD || halo || (d.BN != 64 && d.BN != 128))) {
+        set_error("conv_op_build: row-wise softmax fusions run in the forward 1x1 kernels with BN 64 / 128");
+        return -1;
+    }
+    if (d.epi.outT && !op->tma_out && !rowfuse) {
+        set_error("conv_op_build: a transposed output needs the TMA-I/O or the row-fusion kernel (K <= tma_kmax, BN 64 / 128)");
+        return -1;
+    }
+    op->rowfuse = rowfuse ? 1 : 0;
     op->p = p;
     op->BN = d.BN;
     op->mode = d.mode;
     op->halo = halo ? halo_p : 0;
     const long total = (long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
-    op->deep = (g_deep && !halo && !op->tma_out && (d.BN == 64 || d.BN == 128) && total <= num_sms() &&
+    op->deep = (g_deep && !halo && !op->tma_out && !rowfuse && (d.BN == 64 || d.BN == 128) && total <= num_sms() &&
                 (long)d.kh * d.kw * p.cin_chunks >= g_deep_kmin) ? 1 : 0;
     const long slots = (long)num_sms() * ((halo || d.BN > 128 || op->tma_out || op->deep) ? 1 : P2L_OCC);
     op->grid = (int)(total < slots ? total : slots);
-    if (g_splitk && d.splitk_ws && !op->tma_out && !halo && !d.epi.img_nchw && d.Cout % 32 == 0 && total * 2 <= num_sms()) {
-        const long kblocks = (long)d.kh * d.kw * p.cin_chunks;
-        long target = num_sms() / total;                 // splits that still fit one wave
-        if (target > 8) target = 8;
-        if (kblocks / target < 4) target = kblocks / 4;  // at least four K blocks per split
-        if (target >= 2) {
-            const long kbs = (kblocks + target - 1) / target;
-            const long KS = (kblocks + kbs - 1) / kbs;    // every split non-empty
-            const long stride = (long)d.NI * d.H * d.W * d.Cout;
-            if (KS >= 2 && KS * stride <= d.splitk_ws_floats) {
-                p.ksplit = (int)KS; p.ks_blocks = (int)kbs; p.ks_finish = 0;
-                p.ks_partial = d.splitk_ws; p.ks_stride = stride;
-                op->p = p;
-                op->ksplit = (int)KS;
-                op->grid_finish = op->grid;
-                const long work = total * KS;
-                op->grid = (int)(work < slots ? work : slots);
-            }
-        }
-    }
     op->flops = 2.0 * d.NI * d.H * d.W * (double)d.Cout * d.kh * d.kw * d.Cin;
     return 0;
 }
 
 // ----------------------------------------------------------------------------- launch
-template <int BN, int MODE, bool TMA_OUT, bool DEEP = false>
+template <int BN, int MODE, bool TMA_OUT, bool DEEP = false, bool ROWFUSE = false>
 static int launch_t(const ConvOp& op, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, TMA_OUT, DEEP>;
     static bool attr_set = false;
     if (!attr_set) {
-        P2L_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE, TMA_OUT, DEEP>,
+        P2L_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE, TMA_OUT, DEEP, ROWFUSE>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
@@ -385,7 +363,7 @@ static int launch_t(const ConvOp& op, cudaStream_t stream) {
         at[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = at;
         lc.numAttrs = g_pdl ? 1 : 0;
-        P2L_CUDA_CHECK(cudaLaunchKernelEx(&lc, conv_gemm_kernel<BN, MODE, TMA_OUT, DEEP>, op.tmA, op.tmB, op.tmO, op.p));
+        P2L_CUDA_CHECK(cudaLaunchKernelEx(&lc, conv_gemm_kernel<BN, MODE, TMA_OUT, DEEP, ROWFUSE>, op.tmA, op.tmB, op.tmO, op.p));
     }
     if (g_prof) cudaEventRecord(e1, stream);
     count_launch();
@@ -424,21 +402,7 @@ static int launch_halo_t(const ConvOp& op, cudaStream_t stream) {
     return 0;
 }
 
-static int conv_op_launch_one(const ConvOp& op, cudaStream_t stream);
-
 int conv_op_launch(const ConvOp& op, cudaStream_t stream) {
-    if (op.ksplit > 1) {
-        // partial pass over (tile, K split) work items, then the finish pass (epilogue warps only) of the same kernel
-        if (conv_op_launch_one(op, stream)) return -1;
-        ConvOp fin = op;
-        fin.p.ks_finish = 1;
-        fin.grid = op.grid_finish;
-        return conv_op_launch_one(fin, stream);
-    }
-    return conv_op_launch_one(op, stream);
-}
-
-static int conv_op_launch_one(const ConvOp& op, cudaStream_t stream) {
     if (op.halo) {
 #define P2L_HALO(bn, pp)                                                                   \
     if (op.BN == bn && op.halo == pp)                                                      \
@@ -448,6 +412,12 @@ static int conv_op_launch_one(const ConvOp& op, cudaStream_t stream) {
         P2L_HALO(64, 16) P2L_HALO(128, 16) P2L_HALO(256, 16)
 #undef P2L_HALO
         set_error("conv_op_launch: unsupported halo config BN=%d P=%d", op.BN, op.halo);
+        return -1;
+    }
+    if (op.rowfuse) {
+        if (op.BN == 64) return launch_t<64, EPI_FWD, false, false, true>(op, stream);
+        if (op.BN == 128) return launch_t<128, EPI_FWD, false, false, true>(op, stream);
+        set_error("conv_op_launch: row-fusion epilogues exist for BN 64 / 128 (got %d)", op.BN);
         return -1;
     }
     if (op.tma_out) {

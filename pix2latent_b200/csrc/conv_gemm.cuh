@@ -74,8 +74,8 @@ struct ConvGemmParams {
     act_t* act_lo;  // with act_up: also keep the low-res copy (needed by backward)
     float* img_nchw;        // tanh(v) for c < Cout written as fp32 NCHW [NI, Cout, H, W]
     int img_linear;         // ... without the tanh (planar fp32 output of a tap-expanded head)
-    // ---- epilogue, forward: row-wise softmax / softmax-gradient fusions (attention, "attn_fused" option;
-    //      direct-epilogue path only). A thread owns one accumulator row, so row reductions are thread-local.
+    // ---- epilogue, forward: row-wise softmax / softmax-gradient fusions (attention, "attn_fused" option; ROWFUSE
+    //      instantiations of the direct-epilogue kernel only). A thread owns one accumulator row, so row reductions are thread-local.
     float* rowstat;          // pass 1 of a two-pass softmax: (max, sum exp(v - max)) of this tile's columns per row,
                              // [pixel][n_tiles][2]; nothing else is written
     const float* rowstat_in; // pass 2: v <- exp(v - M) / L with (M, L) combined from the row's n_tiles partials
@@ -83,10 +83,10 @@ struct ConvGemmParams {
     const float* rowsub;     // v <- (v - rowsub[pixel]) * mulin[pixel, c]   (dS = P o (dP - rowsum(dO o O)))
     const act_t* mulin;
     int mulin_C;
-    // ---- both modes: transposed 16-bit copy of the main output (FWD: the raw value, BWD: dx) for channels
-    //      [outT_c0, outT_c1): outT[(n * (outT_c1 - outT_c0) + c - outT_c0) * H * W + h * W + w]. The attention
-    //      backward consumes P^T, dS^T, theta^T and dO^T as K-major operands; emitting them here replaces four
-    //      transpose passes (a warp's 32 lanes are 32 consecutive pixels: two full 32-byte sectors per store).
+    // ---- both modes (TMA-I/O and row-fusion kernels): transposed 16-bit copy of the main output (FWD: the raw value,
+    //      BWD: dx) for channels [outT_c0, outT_c1): outT[(n * (outT_c1 - outT_c0) + c - outT_c0) * H * W + h * W + w].
+    //      The attention backward consumes P^T, dS^T, theta^T and dO^T as K-major operands; emitting them here replaces
+    //      four transpose passes (a warp's 32 lanes are 32 consecutive pixels: two full 32-byte sectors per store).
     act_t* outT;
     int outT_c0, outT_c1;
     // ---- epilogue, backward
@@ -98,17 +98,15 @@ struct ConvGemmParams {
     // epilogue warps are summed in shared memory first) or the 32-row quarter of a small image.
     float* statp;
     int statp_parts, statp_C;
-    int prefetch_saved;  // backward, direct path, N = 64 one-CTA-per-SM kernels: fetch the saved rows before the accumulator wait
     const act_t* addin;  // gradient arriving through the skip connection
     int addin_C, addin_climit, addin_pool;  // pool: sum the 2x2 block of a [NI,2H,2W,addin_C] map
     act_t* dx;
     int dx_C;
     float* dx_f32;  // optional fp32 copy (used for the latent-side tensors)
     int dx_f32_C;
-    // ---- split-K: ksplit > 1: K is cut into ksplit ranges of ks_blocks K blocks; partials [split][pixel][Cout] fp32
-    int ksplit, ks_blocks, ks_finish;
-    float* ks_partial;
-    long ks_stride;  // floats between two splits' partials
+    // ---- tile order: walk the tiles from the last to the first. Consecutive layers alternate the direction
+    //      ("serpentine"): a layer starts on the tiles its producer wrote LAST, which are still in the 126 MB L2.
+    int tile_reverse;
 };
 
 // DEEP: one CTA per SM with the full shared memory as pipeline (8 x 24 KB stages for BN = 64): for launches with
@@ -254,8 +252,15 @@ __device__ __forceinline__ void row_store_transposed(const ConvGemmParams& p, in
         if (cbase + j >= p.outT_c0 && cbase + j < p.outT_c1) dst[j * hw] = f2a(v[j]);
 }
 
+// tile index of the i-th work item (ConvGemmParams::tile_reverse)
+__device__ __forceinline__ int tile_of(const ConvGemmParams& p, int i, int total_tiles) {
+    return p.tile_reverse ? total_tiles - 1 - i : i;
+}
+
 // Direct epilogue: every thread reads / writes the global rows of its own accumulator row.
-template <int BN, int MODE, int CH, bool TMA_OUT, int NG>
+// ROWFUSE: the attention instantiations (row-wise softmax statistics / normalisation / softmax gradient); kept out of
+// every other kernel — the epilogue body is the hot loop of 8 warps per SM and its size is what the instruction cache sees.
+template <int BN, int MODE, int CH, bool TMA_OUT, int NG, bool ROWFUSE = false>
 __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, const CUtensorMap* tmo, uint8_t* obuf,
                                                      uint64_t* in_full, uint64_t* in_empty, uint64_t* tfull_bar,
                                                      uint64_t* tempty_bar, uint32_t tmem_base, int total_tiles, int warp,
@@ -301,11 +306,8 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
     float alpha = p.alpha;
     if (p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
     int it = grp;  // index of the tile in this CTA's sequence
-    const bool ks_finish = !TMA_OUT && p.ks_finish != 0;
-    const int KS = (!TMA_OUT && p.ksplit > 1 && !ks_finish) ? p.ksplit : 1;  // work item = (tile, split) in the partial pass
-    const int loop_tiles = total_tiles * KS;
-    for (int wt = blockIdx.x + grp * gridDim.x; wt < loop_tiles; wt += NG * gridDim.x, it += NG) {
-        const int tile = wt / KS, split = wt - tile * KS;
+    for (int wt = blockIdx.x + grp * gridDim.x; wt < total_tiles; wt += NG * gridDim.x, it += NG) {
+        const int tile = tile_of(p, wt, total_tiles);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
@@ -332,30 +334,14 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
             }
             bar_epilogue(grp);  // table[it & 1] was last read by this group's previous tile (or two tiles ago): every warp has passed a barrier since
         }
-#ifndef P2L_KPRE   // (A/B build switch while the early fetch is being measured; removed once decided)
-#define P2L_KPRE 1
-#endif
-        constexpr bool kPre = P2L_KPRE && (MODE == EPI_BWD) && !TMA_OUT && NG == 2 && BN == 64 && CH == 32;
-        // eight named registers rather than an array: the compiler keeps an indexed array (partly) in local memory
-        uint4 pa0 = make_uint4(0, 0, 0, 0), pa1 = pa0, pa2 = pa0, pa3 = pa0, pb0 = pa0, pb1 = pa0, pb2 = pa0, pb3 = pa0;
-        bool pre_ok = false;
-        if constexpr (kPre) {
-            pre_ok = p.prefetch_saved && p.saved != nullptr && valid && (n_tile * BN + BN <= p.Cout) && (p.saved_C % 8 == 0);
-            if (pre_ok) {
-                const uint4* sp = reinterpret_cast<const uint4*>(p.saved + pix * p.saved_C + n_tile * BN);
-                pa0 = __ldg(sp + 0); pa1 = __ldg(sp + 1); pa2 = __ldg(sp + 2); pa3 = __ldg(sp + 3);
-                pb0 = __ldg(sp + 4); pb1 = __ldg(sp + 5); pb2 = __ldg(sp + 6); pb3 = __ldg(sp + 7);
-            }
-        }
-        if (!ks_finish)
         {
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
         }
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
         // row-wise softmax fusions (forward mode, direct path): running (max, sum) of pass 1 / (M, 1/L) of pass 2
-        float rs_max = -INFINITY, rs_sum = 0.f, rs_M = 0.f, rs_invL = 1.f, rs_sub = 0.f;
-        if constexpr (MODE == EPI_FWD && !TMA_OUT) {
+        [[maybe_unused]] float rs_max = -INFINITY, rs_sum = 0.f, rs_M = 0.f, rs_invL = 1.f, rs_sub = 0.f;
+        if constexpr (ROWFUSE && MODE == EPI_FWD && !TMA_OUT) {
             if (p.rowstat_in && valid) {
                 const float* rp = p.rowstat_in + pix * p.rowstat_nt * 2;
                 float M = -INFINITY;
@@ -403,21 +389,6 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 }
             }
             float v[CH];
-            if (ks_finish) {
-                // finish pass: the accumulator is the sum of the splits' partials (fp32, L2-resident)
-#pragma unroll
-                for (int j = 0; j < CH; ++j) v[j] = 0.f;
-                if (valid) {
-                    for (int sp = 0; sp < p.ksplit; ++sp) {
-                        const float4* src = reinterpret_cast<const float4*>(p.ks_partial + sp * p.ks_stride + pix * p.Cout + cbase);
-#pragma unroll
-                        for (int q = 0; q < CH / 4; ++q) {
-                            const float4 t4 = __ldg(src + q);
-                            v[q * 4 + 0] += t4.x; v[q * 4 + 1] += t4.y; v[q * 4 + 2] += t4.z; v[q * 4 + 3] += t4.w;
-                        }
-                    }
-                }
-            } else
             {
                 uint32_t u[CH];
                 if constexpr (CH == 32) tmem_ld32(t_addr + c, u);
@@ -425,12 +396,6 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(u[j]);
-            }
-            if constexpr (!TMA_OUT) {
-                if (KS > 1) {  // partial pass: the raw accumulator goes to this split's slice of the workspace
-                    if (valid) row_store_f32<CH>(p.ks_partial + split * p.ks_stride + pix * p.Cout + cbase, v, false);
-                    continue;
-                }
             }
             const bool full_chunk = (cbase + CH <= p.Cout);
 
@@ -470,7 +435,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     const long rp = (static_cast<long>(n) * Hs + (h >> p.resid_shift)) * Ws + (w >> p.resid_shift);
                     row_load_add<CH>(p.resid + rp * p.resid_C + cbase, v, wide_ok(p.resid, p.resid_C * 2));
                 }
-                if constexpr (!TMA_OUT) {
+                if constexpr (ROWFUSE && !TMA_OUT) {
                     if (p.rowstat) {  // pass 1: online (max, sum exp) over this tile's columns; no stores
                         float cm = -INFINITY;
 #pragma unroll
@@ -509,7 +474,9 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 if (p.raw_f32 && valid) {
                     row_store_f32<CH>(p.raw_f32 + pix * p.raw_f32_C + cbase, v, wide_ok(p.raw_f32, p.raw_f32_C * 4));
                 }
-                if (p.outT && valid && cbase < p.outT_c1 && cbase + CH > p.outT_c0) row_store_transposed<CH>(p, n, h, w, cbase, v);
+                if constexpr (TMA_OUT || ROWFUSE) {
+                    if (p.outT && valid && cbase < p.outT_c1 && cbase + CH > p.outT_c0) row_store_transposed<CH>(p, n, h, w, cbase, v);
+                }
                 if constexpr (TMA_OUT) {
                     if (p.raw) slab_put_row(s_raw, row, (c & 32) >> 3, v);
                 } else if (p.raw && valid) {
@@ -580,13 +547,6 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
 #pragma unroll
                     for (int j = 0; j < CH; ++j) v[j] = (valid && y[j] > 0.f) ? v[j] : 0.f;
                 } else if (p.saved) {
-                    if (kPre && pre_ok) {
-                        if (c == 0) {
-                            acc8_act(pa0, y); acc8_act(pa1, y + 8); acc8_act(pa2, y + 16); acc8_act(pa3, y + 24);
-                        } else {
-                            acc8_act(pb0, y); acc8_act(pb1, y + 8); acc8_act(pb2, y + 16); acc8_act(pb3, y + 24);
-                        }
-                    } else
                     if (valid) {
                         row_load_add<CH>(p.saved + pix * p.saved_C + cbase, y, wide_ok(p.saved, p.saved_C * 2));  // y starts at 0
                     } else {
@@ -691,7 +651,9 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 if constexpr (TMA_OUT) {
                     if (p.dx) slab_put_row(s_raw, row, (c & 32) >> 3, v);
                 }
-                if (p.outT && valid && cbase < p.outT_c1 && cbase + CH > p.outT_c0) row_store_transposed<CH>(p, n, h, w, cbase, v);
+                if constexpr (TMA_OUT) {
+                    if (p.outT && valid && cbase < p.outT_c1 && cbase + CH > p.outT_c0) row_store_transposed<CH>(p, n, h, w, cbase, v);
+                }
                 if (valid) {
                     if (!TMA_OUT && p.dx) {
                         row_store<CH>(p.dx + pix * p.dx_C + cbase, v, wide_ok(p.dx, p.dx_C * 2));
@@ -735,7 +697,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 }
             }
         }
-        if constexpr (MODE == EPI_FWD && !TMA_OUT) {
+        if constexpr (ROWFUSE && MODE == EPI_FWD && !TMA_OUT) {
             if (p.rowstat && valid) {
                 float* rp = p.rowstat + (pix * p.rowstat_nt + n_tile) * 2;
                 rp[0] = rs_max;
@@ -745,14 +707,14 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
         // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0 && !ks_finish) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
     if (store_warp && elect_one()) bulk_wait0();  // shared memory must outlive the last bulk store's reads
 }
 
 struct OutMaps { CUtensorMap m[6]; };  // [0..3] epilogue outputs, [4..5] epilogue inputs
 
-template <int BN, int MODE, bool TMA_OUT, bool DEEP = false>
+template <int BN, int MODE, bool TMA_OUT, bool DEEP = false, bool ROWFUSE = false>
 __global__ void __launch_bounds__(GemmCfg<BN, TMA_OUT, DEEP>::kThreads, GemmCfg<BN, TMA_OUT, DEEP>::kOcc)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ OutMaps tmO, const ConvGemmParams p) {
@@ -815,32 +777,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // makes the compiler wrap every uniform-datapath instruction (UTCHMMA / UTMALDG / UTCBAR) in an
     // ELECT + BRA.U.ANY "waterfall" loop — measured (ncu source page, profiles/r1i): the MMA warp then spends ~75 %
     // of its time in issue overhead, ~160-195 cycles per MMA instruction.
-    const int KS = (!TMA_OUT && p.ksplit > 1) ? p.ksplit : 1;
-    const int kbs = KS > 1 ? p.ks_blocks : k_blocks;                                  // K blocks per split
-    const int work_tiles = (!TMA_OUT && p.ks_finish) ? 0 : total_tiles * KS;          // finish pass: epilogue warps only
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer, work item = (tile, K split)
+        // ------------------------------------------------------------------ TMA producer
         int stage = 0;
         uint32_t phase = 0;
-        const int tapc = p.taps_w * p.cin_chunks;
-        for (int wt = blockIdx.x; wt < work_tiles; wt += gridDim.x) {
-            const int tile = wt / KS, split = wt - tile * KS;
+        for (int wt = blockIdx.x; wt < total_tiles; wt += gridDim.x) {
+            const int tile = tile_of(p, wt, total_tiles);
             const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-            const int w0 = (m_tile % p.tiles_w) * p.tw, h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
-            const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
-            const int kb0 = split * kbs, kb1 = min(k_blocks, kb0 + kbs);
-            for (int kb = kb0; kb < kb1; ++kb) {
-                const int r = kb / tapc, rem = kb - r * tapc, sx = rem / p.cin_chunks, cc = rem - sx * p.cin_chunks;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sA = smem + stage * Cfg::kStageBytes;
-                if (elect_one()) {
-                    mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    tma_load_4d(sA, &tmA, &full_bar[stage], p.a_c0 + cc * kBK, w0 + sx - p.pad_w, h0 + r - p.pad_h, n0);
-                    tma_load_3d(sA + kATileBytes, &tmB, &full_bar[stage], (r * p.taps_w + sx) * Cin + cc * kBK, n_tile * BN,
-                                p.b_batched ? n0 : 0);
+            const int twi = m_tile % p.tiles_w;
+            const int thi = (m_tile / p.tiles_w) % p.tiles_h;
+            const int tni = m_tile / (p.tiles_w * p.tiles_h);
+            const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.nb;
+            for (int r = 0; r < p.taps_h; ++r) {
+                for (int s = 0; s < p.taps_w; ++s) {
+                    const int kbase = (r * p.taps_w + s) * Cin;
+                    for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sA = smem + stage * Cfg::kStageBytes;
+                        uint8_t* sB = sA + kATileBytes;
+                        if (elect_one()) {
+                            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                            tma_load_4d(sA, &tmA, &full_bar[stage], p.a_c0 + cc * kBK,
+                                        w0 + s - p.pad_w, h0 + r - p.pad_h, n0);
+                            tma_load_3d(sB, &tmB, &full_bar[stage], kbase + cc * kBK, n_tile * BN,
+                                        p.b_batched ? n0 : 0);
+                        }
+                        __syncwarp();
+                        if (++stage == S) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
                 }
-                __syncwarp();
-                if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -849,15 +817,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int wt = blockIdx.x; wt < work_tiles; wt += gridDim.x, ++it) {
-            const int split = wt % KS;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tempty_bar[as], aphase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * BN;
-            const int kb0 = split * kbs, kb1 = min(k_blocks, kb0 + kbs);
-            for (int kb = kb0; kb < kb1; ++kb) {
+            for (int kb = 0; kb < k_blocks; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -865,11 +831,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint64_t bdesc = umma_desc_k128(sA + kATileBytes);
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in 16-B units
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty_bar[stage]);
                 }
                 __syncwarp();
-                if (++stage == S) { stage = 0; phase ^= 1; }
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
             if (elect_one()) umma_commit(&tfull_bar[as]);
             __syncwarp();
@@ -886,7 +858,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr int RING = NIN / Cfg::kEpiGroups;  // one ring per epilogue group
             const int g = warp - (2 + 4 * Cfg::kEpiGroups);
             int cnt = 0;
-            for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += Cfg::kEpiGroups * gridDim.x) {
+            for (int wt = blockIdx.x + g * gridDim.x; wt < total_tiles; wt += Cfg::kEpiGroups * gridDim.x) {
+                const int tile = tile_of(p, wt, total_tiles);
                 const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
                 const int w0 = (m_tile % p.tiles_w) * p.tw;
                 const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
@@ -918,7 +891,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        epilogue_loop_direct<BN, MODE, CH, TMA_OUT, Cfg::kEpiGroups>(p, tmO.m, obuf, in_full, in_empty, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane,
+        epilogue_loop_direct<BN, MODE, CH, TMA_OUT, Cfg::kEpiGroups, ROWFUSE>(p, tmO.m, obuf, in_full, in_empty, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane,
                                                     reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + Cfg::kOutBytes + 256));
     }
 
@@ -1011,7 +984,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             __syncwarp();
         }
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int wt = blockIdx.x; wt < total_tiles; wt += gridDim.x) {
+            const int tile = tile_of(p, wt, total_tiles);
             const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
             const int w0 = (m_tile % p.tiles_w) * Cfg::kTw;
             const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * Cfg::kTh;

@@ -23,9 +23,6 @@ struct ConvDesc {
     int BN = 128;
     int mode = EPI_FWD;
     ConvGemmParams epi{};  // only the epilogue fields are read from here
-    // split-K workspace ("splitk" option): fp32 partials of launches with few tiles and long K
-    float* splitk_ws = nullptr;
-    long splitk_ws_floats = 0;
 };
 
 struct ConvOp {
@@ -35,7 +32,7 @@ struct ConvOp {
     ConvGemmParams p;
     int BN, mode, grid;
     int deep;  // one CTA per SM, full-depth pipeline (few tiles, long K)
-    int ksplit, grid_finish;  // split-K: number of K ranges (0 / 1: off), grid of the finish pass
+    int rowfuse;  // attention instantiation: row-wise softmax fusions in the epilogue
     int halo;  // 0: per-tap A loads; 10 / 16: halo-patch kernel with that patch row pitch
     int halo_smem;  // dynamic shared memory of the halo kernel for this plan
     int stat_parts; // partial slots per image of the BN-gradient sums this launch fills

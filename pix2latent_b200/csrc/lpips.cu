@@ -221,6 +221,7 @@ LpipsPlan* Lpips::plan(int b, int H, int W) {
             d.BN = pick_bn_l(c.Cout, m_tiles(l.Hout, l.Wout));
             d.epi.bias = c.bias; d.epi.relu = 1; d.epi.act = l.F; d.epi.act_C = c.Cout;
             if (conv_op_build(&l.f, d)) return nullptr;
+            l.f.p.tile_reverse = (get_option("serpentine") != 0) ? ((j + 1) & 1) : 0;  // the rgb head before conv 0 walked backwards
         }
         {   // backward: gradient wrt the conv input
             ConvDesc d;
@@ -246,6 +247,7 @@ LpipsPlan* Lpips::plan(int b, int H, int W) {
                 d.epi.dx = P.L[j - 1].D; d.epi.dx_C = cin_eff;
             }
             if (conv_op_build(&l.d, d)) return nullptr;
+            l.d.p.tile_reverse = (get_option("serpentine") != 0) ? ((n - 1 - j) & 1) : 0;
         }
     }
     LpipsPlan* raw = pp.get();

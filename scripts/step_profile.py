@@ -1,43 +1,54 @@
-"""Per-launch timing of the tensor-core kernels inside one real step (CUDA events), for a few
-kernel-option settings. Usage: python scripts/step_profile.py [halo values...]"""
-import sys, warnings
+"""Per-launch timing of the tensor-core kernels inside one real bench step (CUDA events around every launch), as JSON
+lines: one header {"ms_per_step", "conv_ms", "launches"} and one record per launch. Options are taken from P2L_OPTS;
+P2L_LIB selects another build of the library (A/B of two builds on the same box).
+    python scripts/step_profile.py > gpurun_out/profile.jsonl"""
+import json
+import sys
+import warnings
+
 sys.path.insert(0, ".")
 warnings.filterwarnings("ignore")
-import torch
-from pix2latent_b200 import native, _lib
-from pix2latent_b200.loss_functions import ProjectionLoss
-from pix2latent_b200.model import BigGAN
-from bench import synthetic_target
+import torch  # noqa: E402
+from bench import synthetic_target  # noqa: E402
+from pix2latent_b200 import _lib, native  # noqa: E402
+from pix2latent_b200.loss_functions import ProjectionLoss  # noqa: E402
+from pix2latent_b200.model import BigGAN  # noqa: E402
 
-halos = [int(x) for x in sys.argv[1:]] or [0, 1]  # halo_mode values (0 off, 1 resident-weight layers, 2 all 3x3); values > 100 set the TMA-I/O K limit instead
 n = 18
 target, weight = synthetic_target(256, "cuda")
-z = torch.fmod(torch.randn(n, 128), 2.0).cuda()
-for halo in halos:
-    if halo > 100:
-        _lib.set_option("tma_kmax", halo); halo = 0
-    _lib.set_option("halo_rgb", 1 if halo == 3 else 0)
-    if halo == 3: halo = 0
-    _lib.set_option("halo_mode", halo)
-    model = BigGAN(seed=0, allow_synthetic=True).cuda()          # plans are built lazily with the current options
-    loss_fn = ProjectionLoss(allow_synthetic=True)
-    tgt = loss_fn.prepared_target(target, weight)
-    c = model.get_class_embedding(153).repeat(n, 1).contiguous()
-    f = lambda: native.biggan_step(model.native, loss_fn.native_lpips(), tgt, z, c, True, 1 / 9, want_img=False)
-    for _ in range(3): f()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10): f()
-    e1.record(); torch.cuda.synchronize()
-    print("halo=%d: %.3f ms/step" % (halo, e0.elapsed_time(e1) / 10), flush=True)
+g = torch.Generator().manual_seed(2)
+z = torch.fmod(torch.randn(n, 128, generator=g), 2.0).cuda()
+model = BigGAN(seed=0, allow_synthetic=True).cuda()
+loss_fn = ProjectionLoss(allow_synthetic=True)
+tgt = loss_fn.prepared_target(target, weight)
+c = model.get_class_embedding(153).repeat(n, 1).contiguous()
+
+
+def f():
+    return native.biggan_step(model.native, loss_fn.native_lpips(), tgt, z, c, True, 1 / 9, want_img=False)
+
+
+for _ in range(3):
+    f()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    f()
+e1.record()
+torch.cuda.synchronize()
+ms_step = e0.elapsed_time(e1) / 20
+# three instrumented passes, per-launch minimum (the events serialise the launches: PDL overlap is lost, tails are exposed)
+best = None
+for _ in range(3):
     native.profile_enable(1)
-    f(); torch.cuda.synchronize()
+    f()
+    torch.cuda.synchronize()
     recs = _lib.profile_records()
-    native.profile_read(); native.profile_enable(0)
-    tot = sum(r[0] for r in recs)
-    print("  conv launches %d, sum %.3f ms" % (len(recs), tot))
-    for i, (ms, fl, BN, mode, hl, grid, M, N, K) in enumerate(recs):
-        if ms > 0.04:
-            print("  #%3d %s BN%3d halo%2d grid%3d M%8d N%5d K%5d  %7.1f us  %6.0f TF/s" % (i, "bwd" if mode else "fwd", BN, hl, grid, M, N, K, ms * 1e3, fl / ms / 1e9))
-    del model, loss_fn, tgt
+    native.profile_read()
+    native.profile_enable(0)
+    best = recs if best is None else [r if r[0] < b[0] else b for r, b in zip(recs, best)]
+print(json.dumps({"ms_per_step": ms_step, "conv_ms": sum(r[0] for r in best), "launches": len(best)}))
+for i, (ms, fl, BN, mode, hl, grid, M, N, K) in enumerate(best):
+    print(json.dumps({"i": i, "mode": "bwd" if mode else "fwd", "BN": BN, "halo": hl, "grid": grid, "M": M, "N": N, "K": K,
+                      "us": round(ms * 1e3, 2), "tflops": round(fl / ms / 1e9, 1)}))

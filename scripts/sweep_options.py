@@ -19,8 +19,7 @@ from pix2latent_b200.loss_functions import ProjectionLoss  # noqa: E402
 from pix2latent_b200.model import BigGAN, synth  # noqa: E402
 
 # the library's defaults at import time are the baseline every config starts from
-OPTION_KEYS = ["splitk", "attn_fused", "attn_emit_t", "prefetch_saved", "sub_mb", "sub_min_tiles", "pdl", "deep", "deep_kmin",
-               "tma_out", "tma_kmax", "halo_mode", "halo"]
+OPTION_KEYS = ["attn_fused", "attn_emit_t", "serpentine", "pdl", "deep", "deep_kmin", "tma_out", "tma_kmax", "halo_mode", "halo"]
 DEFAULTS = {}
 
 

@@ -1,9 +1,9 @@
-"""Kernel-selection options of the tensor-core path, each against the default path on the same inputs (all through the
+"""Kernel-selection options of the tensor-core path, each against the other setting on the same inputs (all through the
 C-ABI): the row-wise softmax fusions of the attention GEMM epilogues ("attn_fused"), the transposed epilogue outputs
-that replace the attention backward's transposes ("attn_emit_t"), split-K over idle SMs ("splitk"), the early fetch of
-the saved activation in the backward epilogue ("prefetch_saved"), and L2-resident sub-batching of the generator blocks
-("sub_mb"). Kernel level (p2l_debug_conv) against torch fp32, then model level: image and latent gradients of the
-reduced generator with the option on / off."""
+that replace the attention backward's transposes ("attn_emit_t"), and the serpentine tile order ("serpentine": every
+other launch walks its tiles backwards so that it starts on what its producer left in L2). Kernel level
+(p2l_debug_conv) against torch fp32, then model level: image and latent gradients of the reduced generator with the
+option on / off."""
 import contextlib
 import os
 import sys
@@ -141,8 +141,11 @@ def test_generator_fused_attention(problem):
         assert torch.equal(u, v), "transposed epilogue outputs changed the result"
 
 
-@pytest.mark.parametrize("N,H,Cin,Cout,k", [(18, 4, 512, 512, 3), (18, 4, 2048, 512, 1), (18, 8, 512, 512, 3), (5, 8, 256, 128, 3)])
-def test_conv_splitk_matches_unsplit(N, H, Cin, Cout, k):
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("N,H,Cin,Cout,k,BN", [(3, 64, 64, 128, 1, 128), (2, 256, 64, 64, 3, 64), (18, 4, 512, 512, 3, 64), (5, 40, 128, 192, 3, 64)])
+def test_reverse_tile_order_is_exact(mode, N, H, Cin, Cout, k, BN):
+    """tile_reverse changes the order in which a launch visits its tiles, not what a tile computes: outputs and the
+    (per-tile, fixed-order) BN-gradient sums are bit-identical."""
     from pix2latent_b200 import native
     from test_conv_gemm_gpu import run_conv, pack_w
     dt = native.act_dtype()
@@ -154,65 +157,31 @@ def test_conv_splitk_matches_unsplit(N, H, Cin, Cout, k):
     s = torch.randn(N, Cout, device=dev) * 0.1
     bias = torch.randn(Cout, device=dev) * 0.1
     saved = torch.relu(torch.randn(N, H, H, Cout, device=dev)).to(dt)
-    ws = torch.zeros(16 << 20, device=dev)
     out = {}
-    for on in (0, 1):
-        with options(splitk=on):
-            extra = dict(splitk_ws=ws, splitk_ws_floats=ws.numel()) if on else {}
+    for rev in (0, 1):
+        common = dict(A=x, A_N=N, A_H=H, A_W=H, A_C=Cin, Cin=Cin, B=pack_w(w), Cout=Cout, kh=k, kw=k, pad_h=k // 2, pad_w=k // 2,
+                      NI=N, H=H, W=H, BN=BN, mode=mode, tile_reverse=rev)
+        if mode == 0:
             raw = torch.zeros(N, H, H, Cout, device=dev, dtype=dt)
             act = torch.zeros_like(raw)
-            run_conv(A=x, A_N=N, A_H=H, A_W=H, A_C=Cin, Cin=Cin, B=pack_w(w), Cout=Cout, kh=k, kw=k, pad_h=k // 2, pad_w=k // 2, NI=N,
-                     H=H, W=H, BN=64, mode=0, bias=bias, aff_a=a, aff_s=s, aff_stride=Cout, relu=1, raw=raw, raw_C=Cout, act=act,
-                     act_C=Cout, **extra)
+            run_conv(bias=bias, aff_a=a, aff_s=s, aff_stride=Cout, relu=1, raw=raw, raw_C=Cout, act=act, act_C=Cout, **common)
+            out[rev] = (raw, act)
+        else:
             dx = torch.zeros(N, H, H, Cout, device=dev, dtype=dt)
-            st0 = torch.zeros(N, Cout, device=dev)
-            st1 = torch.zeros(N, Cout, device=dev)
-            wt = w.transpose(0, 1).flip(2, 3).contiguous() if Cin == Cout else None
-            if wt is not None:  # dgrad-shaped launch (Cin == Cout keeps the packed layout simple)
-                run_conv(A=x, A_N=N, A_H=H, A_W=H, A_C=Cin, Cin=Cin, B=pack_w(wt), Cout=Cout, kh=k, kw=k, pad_h=k // 2, pad_w=k // 2,
-                         NI=N, H=H, W=H, BN=64, mode=1, saved=saved, saved_C=Cout, stat0=st0, stat1=st1, stat_stride=Cout, aff_a=a,
-                         aff_stride=Cout, dx=dx, dx_C=Cout, **extra)
-            out[on] = (raw.float(), act.float(), dx.float(), st0.clone(), st1.clone())
-    for name, u, v in zip(("raw", "act", "dx", "stat0", "stat1"), out[0], out[1]):
-        denom = u.abs().max().item() + 1e-6
-        err = (u - v).abs().max().item() / denom
-        print("%s: max rel diff split vs unsplit %.2e" % (name, err))
-        assert err < 5e-3, name  # fp32 summation order of the K ranges + one 16-bit rounding of the outputs
-
-
-def test_generator_splitk(problem):
-    cfg, orc = problem
-    io = _model_io(cfg, orc)
-    with options(splitk=0):
-        base = _run_model(cfg, orc, *io)
-    with options(splitk=1):
-        split = _run_model(cfg, orc, *io)
-    rel, cz, cc = _cmp("split-K", base, split)
-    assert rel < 2e-3 and cz > 0.999 and cc > 0.999
-
-
-def test_generator_prefetch_saved_is_exact(problem):
-    """the early fetch moves loads, not arithmetic: identical bits"""
-    cfg, orc = problem
-    io = _model_io(cfg, orc)
-    with options(prefetch_saved=0, halo_mode=2):
-        base = _run_model(cfg, orc, *io)
-    with options(prefetch_saved=1, halo_mode=2):
-        pre = _run_model(cfg, orc, *io)
-    for u, v in zip(base, pre):
+            st0, st1 = torch.zeros(N, Cout, device=dev), torch.zeros(N, Cout, device=dev)
+            run_conv(saved=saved, saved_C=Cout, stat0=st0, stat1=st1, stat_stride=Cout, aff_a=a, aff_stride=Cout, dx=dx, dx_C=Cout,
+                     **common)
+            out[rev] = (dx, st0, st1)
+    for u, v in zip(out[0], out[1]):
         assert torch.equal(u, v)
 
 
-@pytest.mark.parametrize("sub_mb,min_tiles", [(1, 1), (4, 1), (8, 64)])
-def test_generator_sub_batching_is_exact(problem, sub_mb, min_tiles):
-    """Sub-batching changes WHEN a candidate's tiles run, not what they compute: every candidate's image and gradients
-    are bit-identical to the whole-batch run (this is also what makes a sharded run equal the unsharded one)."""
+def test_generator_serpentine_is_exact(problem):
     cfg, orc = problem
     io = _model_io(cfg, orc, b=5)
-    with options(sub_mb=0):
+    with options(serpentine=0):
         base = _run_model(cfg, orc, *io)
-    with options(sub_mb=sub_mb, sub_min_tiles=min_tiles):
-        sub = _run_model(cfg, orc, *io)
-    _cmp("sub-batched (sub_mb=%d)" % sub_mb, base, sub)
-    for u, v in zip(base, sub):
+    with options(serpentine=1):
+        serp = _run_model(cfg, orc, *io)
+    for u, v in zip(base, serp):
         assert torch.equal(u, v)
