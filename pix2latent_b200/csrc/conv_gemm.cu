@@ -26,8 +26,8 @@ void add_launches(long n) { g_launches += n; }
 long launch_count() { return g_launches; }
 
 static int g_tma_out = 1, g_tma_kmax = 512;
-static int g_attn_fused = 0;  // "attn_fused": two-pass softmax + fused dS in the attention GEMM epilogues
-static int g_attn_emit_t = 0; // "attn_emit_t": the attention backward's transposed operands come out of the producing epilogues
+static int g_attn_fused = 1;  // "attn_fused": two-pass softmax + fused dS in the attention GEMM epilogues (no fp32 logits in HBM)
+static int g_attn_emit_t = 1; // "attn_emit_t": the attention backward's transposed operands come out of the producing epilogues
 static int g_serpentine = 1;  // "serpentine": consecutive layers walk their tiles in opposite directions (L2 reuse of the producer's last writes)
 static int g_pdl = 1;  // "pdl": launch the tensor-core kernel with programmatic stream serialization (prologue overlaps the previous kernel's tail)
 static int g_deep = 1, g_deep_kmin = 8;  // "deep": full-depth single-CTA pipeline for launches with <= #SM tiles and >= deep_kmin K blocks
