@@ -30,111 +30,120 @@ __device__ __constant__ float kFir[4] = {0.25f, 0.75f, 0.75f, 0.25f};  // [1,3,3
 constexpr float kSqrt2 = 1.41421356237309515f;
 
 // ----------------------------------------------------------------------------- dense latent-side layers
-// y[b, j] = act(wscale * sum_k x[b,k] * WT[k][j] + bias[j]); thread per j, <= 24 samples per pass
-__global__ void fc_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ WT, int ldw, const float* __restrict__ bias,
-                              float wscale, float* y, int ldy, int b, int in, int out, int act, int square_in) {
-    extern __shared__ float sx[];  // [b][in]
-    for (int i = threadIdx.x; i < b * in; i += blockDim.x) {
-        const float v = x[(long)(i / in) * ldx + (i % in)];
-        sx[i] = square_in ? v * v : v;
-    }
-    __syncthreads();
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= out) return;
-    for (int b0 = 0; b0 < b; b0 += 24) {
-        float acc[24];
+// One small-batch GEMM kernel for every latent-side contraction (mapping network, style affines, demodulation and their
+// backward passes):  y[bi][j] = epi( wscale * sum_k pro(x)[bi][k] * M[k * ldm + j] ),  bi < b <= NB.
+// Block = 32 outputs j x 8 warps; warp w owns every 8th run of 16 k's, lane = j (coalesced 128-byte rows of M), the
+// (transformed) inputs of a 256-wide K chunk sit in shared memory (broadcast reads); the eight partial sums meet in
+// shared memory and are added in warp order (no atomics: reproducible).
+enum { SG_PRO_ID = 0, SG_PRO_SQUARE = 1, SG_PRO_ACTGRAD = 2, SG_PRO_DEMOD = 3 };
+enum { SG_EPI_BIAS_ACT = 0, SG_EPI_STORE = 1, SG_EPI_ACCUM = 2, SG_EPI_SUB_SCALED = 3 };
+struct SgGemm {
+    const float* x; int ldx;        // inputs [b][K]
+    const float* x2; int ldx2;      // PRO_ACTGRAD: y of the forward pass (act' = y > 0 ? 1 : 0.2, * sqrt2); PRO_DEMOD: dm
+    const float* M; int ldm;        // [K][ldm]
+    const float* bias; float wscale;
+    float* y; int ldy;
+    const float* s; int lds;        // EPI_SUB_SCALED: y -= s * acc
+    int b, K, J, act;
+};
+template <int NB>
+__global__ void __launch_bounds__(256) sg_gemm_kernel(const SgGemm a, int pro, int epi) {
+    constexpr int KC = 128, KW = KC / 8;   // K chunk staged per pass; k's per warp and chunk
+    __shared__ float xs[NB][KC];
+    __shared__ float red[8][NB][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 32 + lane;
+    float acc[NB];
 #pragma unroll
-        for (int i = 0; i < 24; ++i) acc[i] = 0.f;
-        for (int k0 = 0; k0 < in; k0 += 8) {
-            float w[8];
+    for (int i = 0; i < NB; ++i) acc[i] = 0.f;
+    for (int k0 = 0; k0 < a.K; k0 += KC) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < NB * KC; t += 256) {
+            const int bi = t / KC, kk = t - bi * KC, k = k0 + kk;
+            float v = 0.f;
+            if (bi < a.b && k < a.K) {
+                v = a.x[(long)bi * a.ldx + k];
+                if (pro == SG_PRO_SQUARE) v *= v;
+                else if (pro == SG_PRO_ACTGRAD) v *= (a.x2[(long)bi * a.ldx2 + k] > 0.f ? 1.f : 0.2f) * kSqrt2;
+                else if (pro == SG_PRO_DEMOD) { const float d = a.x2[(long)bi * a.ldx2 + k]; v *= d * d * d; }
+            }
+            xs[bi][kk] = v;
+        }
+        __syncthreads();
+        if (j < a.J) {
+            const int kend = min(KC, a.K - k0);
+            const int kk = warp * KW;   // warp w: k = w*KW .. w*KW+KW-1 of this chunk
+            if (kk < kend) {
+                const int n = min(KW, kend - kk);
+                const float* mp = a.M + (long)(k0 + kk) * a.ldm + j;
+#pragma unroll 8
+                for (int u = 0; u < n; ++u) {
+                    const float w = __ldg(mp + (long)u * a.ldm);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) w[u] = (k0 + u < in) ? __ldg(WT + (long)(k0 + u) * ldw + j) : 0.f;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int k = min(k0 + u, in - 1);
-#pragma unroll
-                for (int i = 0; i < 24; ++i) acc[i] = fmaf(sx[min(b0 + i, b - 1) * in + k], w[u], acc[i]);
+                    for (int i = 0; i < NB; ++i) acc[i] = fmaf(xs[i][kk + u], w, acc[i]);
+                }
             }
         }
-        const float bj = bias ? bias[j] : 0.f;
+    }
 #pragma unroll
-        for (int i = 0; i < 24; ++i) {
-            if (b0 + i < b) {
-                float v = acc[i] * wscale + bj;
-                if (act == 1) v = (v > 0.f ? v : 0.2f * v) * kSqrt2;      // fused_leaky_relu
-                else if (act == 2) v = rsqrtf(v + 1e-8f);                   // demodulation (bias = 0)
-                y[(long)(b0 + i) * ldy + j] = v;
-            }
+    for (int i = 0; i < NB; ++i) red[warp][i][lane] = acc[i];
+    __syncthreads();
+    for (int t = threadIdx.x; t < NB * 32; t += 256) {
+        const int bi = t >> 5, jj = t & 31, jo = blockIdx.x * 32 + jj;
+        if (bi >= a.b || jo >= a.J) continue;
+        float v = ((red[0][bi][jj] + red[1][bi][jj]) + (red[2][bi][jj] + red[3][bi][jj])) +
+                  ((red[4][bi][jj] + red[5][bi][jj]) + (red[6][bi][jj] + red[7][bi][jj]));
+        v *= a.wscale;
+        float* yp = a.y + (long)bi * a.ldy + jo;
+        if (epi == SG_EPI_BIAS_ACT) {
+            v += a.bias ? a.bias[jo] : 0.f;
+            if (a.act == 1) v = (v > 0.f ? v : 0.2f * v) * kSqrt2;      // fused_leaky_relu
+            else if (a.act == 2) v = rsqrtf(v + 1e-8f);                   // demodulation (bias = 0)
+            *yp = v;
+        } else if (epi == SG_EPI_STORE) {
+            *yp = v;
+        } else if (epi == SG_EPI_ACCUM) {
+            *yp += v;
+        } else {
+            *yp -= a.s[(long)bi * a.lds + jo] * v;
         }
     }
 }
-void k_fc_fwd_ld(const float* x, int ldx, const float* WT, int ldw, const float* bias, float wscale, float* y, int ldy, int b,
-                 int in, int out, int act, int square_in, cudaStream_t st) {
-    for (int b0 = 0; b0 < b; b0 += 16) {  // <= 16 samples per launch keeps the staged inputs under 48 KB
-        const int nb = b - b0 < 16 ? b - b0 : 16;
-        fc_fwd_kernel<<<cdiv(out, 64), 64, (size_t)nb * in * sizeof(float), st>>>(x + (long)b0 * ldx, ldx, WT, ldw, bias, wscale,
-                                                                                  y + (long)b0 * ldy, ldy, nb, in, out, act, square_in);
+static void sg_gemm(SgGemm a, int pro, int epi, cudaStream_t st) {
+    const int b_all = a.b;
+    for (int b0 = 0; b0 < b_all; b0 += 24) {   // <= 24 samples per launch
+        SgGemm c = a;
+        c.b = b_all - b0 < 24 ? b_all - b0 : 24;
+        c.x = a.x + (long)b0 * a.ldx;
+        c.x2 = a.x2 ? a.x2 + (long)b0 * a.ldx2 : nullptr;
+        c.y = a.y + (long)b0 * a.ldy;
+        c.s = a.s ? a.s + (long)b0 * a.lds : nullptr;
+        const int grid = cdiv(a.J, 32);
+        if (c.b <= 8) sg_gemm_kernel<8><<<grid, 256, 0, st>>>(c, pro, epi);
+        else if (c.b <= 16) sg_gemm_kernel<16><<<grid, 256, 0, st>>>(c, pro, epi);
+        else sg_gemm_kernel<24><<<grid, 256, 0, st>>>(c, pro, epi);
         count_launch();
     }
+}
+// y[b, j] = act(wscale * sum_k x[b,k] * WT[k][j] + bias[j]); WT row pitch ldw
+void k_fc_fwd_ld(const float* x, int ldx, const float* WT, int ldw, const float* bias, float wscale, float* y, int ldy, int b,
+                 int in, int out, int act, int square_in, cudaStream_t st) {
+    SgGemm a{};
+    a.x = x; a.ldx = ldx; a.M = WT; a.ldm = ldw; a.bias = bias; a.wscale = wscale; a.y = y; a.ldy = ldy; a.b = b; a.K = in; a.J = out;
+    a.act = act;
+    sg_gemm(a, square_in ? SG_PRO_SQUARE : SG_PRO_ID, SG_EPI_BIAS_ACT, st);
 }
 void k_fc_fwd(const float* x, int ldx, const float* WT, const float* bias, float wscale, float* y, int ldy, int b, int in,
               int out, int act, int square_in, cudaStream_t st) {
     k_fc_fwd_ld(x, ldx, WT, out, bias, wscale, y, ldy, b, in, out, act, square_in, st);
 }
-
-// dx[b, k] (+)= wscale * sum_j g[b,j] * W[j][k], g = dy * act'(y); thread per k
-__global__ void fc_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
-                              const float* __restrict__ W, float wscale, float* dx, int lddx, int b, int in, int out, int act,
-                              int accumulate) {
-    constexpr int JC = 256;          // rows of W per shared-memory chunk
-    extern __shared__ float sg[];    // [b <= 16][JC]
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    float acc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-    for (int jc = 0; jc < out; jc += JC) {
-        const int nj = min(JC, out - jc);
-        __syncthreads();
-        for (int i = threadIdx.x; i < b * JC; i += blockDim.x) {
-            const int bi = i / JC, jj = i % JC;
-            float g = 0.f;
-            if (jj < nj) {
-                g = dy[(long)bi * lddy + jc + jj];
-                if (act == 1) g *= (y[(long)bi * ldy + jc + jj] > 0.f ? 1.f : 0.2f) * kSqrt2;
-            }
-            sg[i] = g;
-        }
-        __syncthreads();
-        if (k < in) {
-            for (int j0 = 0; j0 < nj; j0 += 8) {
-                float w[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) w[u] = (j0 + u < nj) ? __ldg(W + (long)(jc + j0 + u) * in + k) : 0.f;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) acc[i] = fmaf(sg[min(i, b - 1) * JC + min(j0 + u, JC - 1)], w[u], acc[i]);
-                }
-            }
-        }
-    }
-    if (k >= in) return;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        if (i < b) {
-            float* d = dx + (long)i * lddx + k;
-            *d = (accumulate ? *d : 0.f) + acc[i] * wscale;
-        }
-    }
-}
+// dx[b, k] (+)= wscale * sum_j g[b,j] * W[j][k], g = dy * act'(y); W is [out][in]
 void k_fc_bwd(const float* dy, int lddy, const float* y, int ldy, const float* W, float wscale, float* dx, int lddx, int b,
               int in, int out, int act, int accumulate, cudaStream_t st) {
-    for (int b0 = 0; b0 < b; b0 += 16) {
-        const int nb = b - b0 < 16 ? b - b0 : 16;
-        fc_bwd_kernel<<<cdiv(in, 64), 64, (size_t)nb * 256 * sizeof(float), st>>>(
-            dy + (long)b0 * lddy, lddy, y ? y + (long)b0 * ldy : nullptr, ldy, W, wscale, dx + (long)b0 * lddx, lddx, nb, in, out, act, accumulate);
-        count_launch();
-    }
+    SgGemm a{};
+    a.x = dy; a.ldx = lddy; a.x2 = y; a.ldx2 = ldy; a.M = W; a.ldm = in; a.wscale = wscale; a.y = dx; a.ldy = lddx; a.b = b;
+    a.K = out; a.J = in;
+    sg_gemm(a, (act == 1 && y) ? SG_PRO_ACTGRAD : SG_PRO_ID, accumulate ? SG_EPI_ACCUM : SG_EPI_STORE, st);
 }
 
 // PixelNorm: y = x * rsqrt(mean(x^2) + 1e-8); one warp per sample
@@ -168,32 +177,12 @@ void k_pixelnorm_bwd(const float* x, const float* dy, float* dx, int b, int n, f
 }
 
 // ds[b,i] += -s[b,i] * sum_o (ddm*dm^3)[b,o] * Wsq[o][i]   (gradient through the demodulation)
-__global__ void demod_bwd_kernel(const float* __restrict__ ddm, const float* __restrict__ dm, int lddm,
-                                 const float* __restrict__ s, int lds, const float* __restrict__ Wsq, float* ds, int ldds,
-                                 int b, int Cin, int Cout) {
-    extern __shared__ float sg[];  // [b][Cout]
-    for (int i = threadIdx.x; i < b * Cout; i += blockDim.x) {
-        const int bi = i / Cout, o = i % Cout;
-        const float d = dm[(long)bi * lddm + o];
-        sg[i] = ddm[(long)bi * lddm + o] * d * d * d;
-    }
-    __syncthreads();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= Cin) return;
-    for (int bi = 0; bi < b; ++bi) {
-        float acc = 0.f;
-        for (int o = 0; o < Cout; ++o) acc = fmaf(sg[bi * Cout + o], __ldg(Wsq + (long)o * Cin + k), acc);
-        ds[(long)bi * ldds + k] -= s[(long)bi * lds + k] * acc;
-    }
-}
 void k_demod_bwd(const float* ddm, const float* dm, int lddm, const float* s, int lds, const float* Wsq, float* ds, int ldds,
                  int b, int Cin, int Cout, cudaStream_t st) {
-    for (int b0 = 0; b0 < b; b0 += 16) {
-        const int nb = b - b0 < 16 ? b - b0 : 16;
-        demod_bwd_kernel<<<cdiv(Cin, 64), 64, (size_t)nb * Cout * sizeof(float), st>>>(
-            ddm + (long)b0 * lddm, dm + (long)b0 * lddm, lddm, s + (long)b0 * lds, lds, Wsq, ds + (long)b0 * ldds, ldds, nb, Cin, Cout);
-        count_launch();
-    }
+    SgGemm a{};
+    a.x = ddm; a.ldx = lddm; a.x2 = dm; a.ldx2 = lddm; a.M = Wsq; a.ldm = Cin; a.wscale = 1.f; a.y = ds; a.ldy = ldds;
+    a.s = s; a.lds = lds; a.b = b; a.K = Cout; a.J = Cin;
+    sg_gemm(a, SG_PRO_DEMOD, SG_EPI_SUB_SCALED, st);
 }
 
 // ----------------------------------------------------------------------------- modulation
@@ -447,37 +436,45 @@ __device__ __forceinline__ float up_gather(const float* __restrict__ prev, int h
     }
     return acc;
 }
-// rgb[b,c,p] = sum_i weff[b,c,i] x[b,p,i] + bias[c] (+ upsampled previous rgb); one warp per pixel
-__global__ void torgb_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ weff, const float* __restrict__ bias,
-                                 const float* __restrict__ prev, float* __restrict__ rgb, int H, int W, int C) {
+// rgb[b,c,p] = sum_i weff[b,c,i] x[b,p,i] + bias[c] (+ upsampled previous rgb); thread per pixel: the pixel's C channels
+// are one contiguous run (16-byte loads), the three weight rows sit in shared memory (broadcast reads), stores are
+// coalesced along the pixels of a plane
+__global__ void __launch_bounds__(128) torgb_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ weff,
+                                                        const float* __restrict__ bias, const float* __restrict__ prev,
+                                                        float* __restrict__ rgb, int H, int W, int C) {
     extern __shared__ float sw[];  // [3][C]
     const int bi = blockIdx.y;
     for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sw[i] = weff[(long)bi * 3 * C + i];
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (p >= H * W) return;
-    const bf16* xp = x + ((long)bi * H * W + p) * C;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int k = lane * 2; k < C; k += 64) {
-        const uint32_t v2 = *reinterpret_cast<const uint32_t*>(xp + k);
-        const float v0 = act_lo(v2), v1 = act_hi(v2);
-        a0 = fmaf(v0, sw[k], a0); a0 = fmaf(v1, sw[k + 1], a0);
-        a1 = fmaf(v0, sw[C + k], a1); a1 = fmaf(v1, sw[C + k + 1], a1);
-        a2 = fmaf(v0, sw[2 * C + k], a2); a2 = fmaf(v1, sw[2 * C + k + 1], a2);
-    }
-    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-    if (lane < 3) {
+    const int HW = H * W;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+        const uint4* xp = reinterpret_cast<const uint4*>(x + ((long)bi * HW + p) * C);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int k = 0; k < C; k += 8) {
+            float v[8];
+            unpack8(__ldg(xp + (k >> 3)), v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                a0 = fmaf(v[e], sw[k + e], a0);
+                a1 = fmaf(v[e], sw[C + k + e], a1);
+                a2 = fmaf(v[e], sw[2 * C + k + e], a2);
+            }
+        }
         const int y = p / W, xx = p % W;
-        float v = (lane == 0 ? a0 : lane == 1 ? a1 : a2) + bias[lane];
-        if (prev) v += up_gather(prev + ((long)bi * 3 + lane) * (H / 2) * (W / 2), H / 2, W / 2, y, xx);
-        rgb[((long)bi * 3 + lane) * H * W + p] = v;
+        const float acc[3] = {a0, a1, a2};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = acc[c] + bias[c];
+            if (prev) v += up_gather(prev + ((long)bi * 3 + c) * (H / 2) * (W / 2), H / 2, W / 2, y, xx);
+            rgb[((long)bi * 3 + c) * HW + p] = v;
+        }
     }
 }
 void k_sg_torgb_fwd(const bf16* x, const float* weff, const float* bias, const float* prev, float* rgb, int b, int H, int W, int C,
                     cudaStream_t st) {
-    dim3 grid(cdiv((long)H * W, 8), b);
-    torgb_fwd_kernel<<<grid, 256, (size_t)3 * C * sizeof(float), st>>>(x, weff, bias, prev, rgb, H, W, C); count_launch();
+    int gx = cdiv((long)H * W, 128);
+    if (gx > 1024) gx = 1024;
+    torgb_fwd_kernel<<<dim3(gx, b), 128, (size_t)3 * C * sizeof(float), st>>>(x, weff, bias, prev, rgb, H, W, C); count_launch();
 }
 // backward: dx[b,p,i] (+)= sum_c drgb[b,c,p] weff[b,c,i] ; dweff[b,c,i] += sum_p drgb[b,c,p] x[b,p,i]
 // block = 8 channel groups x 32 pixels
