@@ -51,7 +51,7 @@ P2L_EXPORT int p2l_debug_conv(const p2l_conv_args* a, void* cuda_stream) {
         if (a->Cout % 32) { set_error("debug_conv: statistics need Cout %% 32 == 0"); rc = -1; }
         else {
             std::vector<StatSeg> segs;
-            for (int c0 = 0; c0 < a->Cout; c0 += 32) segs.push_back({statp, op.stat_parts, parts, a->Cout, 0, c0});
+            for (int c0 = 0; c0 < a->Cout; c0 += 32) segs.push_back({statp, op.stat_parts, parts, a->Cout, 0, c0, 0});
             if (cudaMalloc(&dsegs, segs.size() * sizeof(StatSeg)) != cudaSuccess) { set_error("debug_conv: cudaMalloc failed"); rc = -1; }
             else {
                 cudaMemcpyAsync(dsegs, segs.data(), segs.size() * sizeof(StatSeg), cudaMemcpyHostToDevice, st);

@@ -469,7 +469,7 @@ BigGANPlan* BigGAN::plan(int b) {
         }
         const int cs[4] = {bl.in, bl.mid, bl.mid, bl.mid};
         for (int k = 0; k < 4; ++k)
-            for (int c0 = 0; c0 < cs[k]; c0 += 32) segs.push_back({B.sp[k], parts_used[k], B.sp_parts[k], cs[k], bns[bl.bn[k]].off, c0});
+            for (int c0 = 0; c0 < cs[k]; c0 += 32) segs.push_back({B.sp[k], parts_used[k], B.sp_parts[k], cs[k], bns[bl.bn[k]].off, c0, bns[bl.bn[k]].off});
     }
     P.nsegs = (int)segs.size();
     P.segs = upload(ar, segs);

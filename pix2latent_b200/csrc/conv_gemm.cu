@@ -204,7 +204,7 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     // candidate's result must not depend on which other candidates share its launch (sub-batches, candidate sharding).
     const bool halo_on = (d.BN == 16) ? (g_halo_rgb != 0)
                                       : (g_halo_mode != 0 && (g_halo_mode == 2 || (resb && (long)d.H * d.W >= (1L << 16))));
-    const bool halo = halo_p != 0 && halo_on && d.kh == 3 && d.kw == 3 &&
+    const bool halo = halo_p != 0 && halo_on && (!d.sg || (d.BN == 64 && halo_p == 10)) && d.kh == 3 && d.kw == 3 &&
                       d.pad_h == 1 && d.pad_w == 1 && d.B_batch == 0 && d.H >= 12 && d.W >= 8;
     if (halo) { tw = 8; th = 16; nb = 1; }
     if (d.B_batch > 0 && nb != 1) {
@@ -265,7 +265,7 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
     // ---- epilogue outputs by TMA bulk store: worthwhile where the epilogue dominates (small K)
     const long Ktot = (long)d.kh * d.kw * d.Cin;
     const bool any_out = (d.epi.raw || d.epi.act || d.epi.dx) && !d.epi.rowstat && !d.epi.rowstat_in && !d.epi.mulin;  // row-wise fusions: direct epilogue only
-    op->tma_out = (g_tma_out && !halo && any_out && (d.BN == 64 || d.BN == 128) && d.Cout % 64 == 0 && Ktot <= g_tma_kmax &&
+    op->tma_out = (g_tma_out && !halo && !d.sg && any_out && (d.BN == 64 || d.BN == 128) && d.Cout % 64 == 0 && Ktot <= g_tma_kmax &&
                    !d.epi.img_nchw && !(d.epi.addin && d.epi.addin_pool) && (d.epi.resid_shift == 0 || (tw >= 2 && th >= 2)) &&
                    (!d.epi.addin || d.epi.addin_climit % 64 == 0)) ? 1 : 0;
     if (op->tma_out) {
@@ -313,7 +313,11 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
         set_error("conv_op_build: a transposed output needs the TMA-I/O or the row-fusion kernel (K <= tma_kmax, BN 64 / 128)");
         return -1;
     }
-    op->rowfuse = rowfuse ? 1 : 0;
+    if (d.sg && (rowfuse || op->tma_out || (d.BN != 64 && d.BN != 128 && d.BN != 256) || (halo && (d.BN != 64 || halo_p != 10)))) {
+        set_error("conv_op_build: StyleGAN2 epilogues run in the direct-epilogue kernels with BN 64 / 128 / 256");
+        return -1;
+    }
+    op->flavor = d.sg ? FLAVOR_SG : (rowfuse ? FLAVOR_ROWFUSE : FLAVOR_PLAIN);
     op->p = p;
     op->BN = d.BN;
     op->mode = d.mode;
@@ -328,12 +332,12 @@ int conv_op_build(ConvOp* op, const ConvDesc& d) {
 }
 
 // ----------------------------------------------------------------------------- launch
-template <int BN, int MODE, bool TMA_OUT, bool DEEP = false, bool ROWFUSE = false>
+template <int BN, int MODE, bool TMA_OUT, bool DEEP = false, int FLAVOR = FLAVOR_PLAIN>
 static int launch_t(const ConvOp& op, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, TMA_OUT, DEEP>;
     static bool attr_set = false;
     if (!attr_set) {
-        P2L_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE, TMA_OUT, DEEP, ROWFUSE>,
+        P2L_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE, TMA_OUT, DEEP, FLAVOR>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
@@ -363,7 +367,7 @@ static int launch_t(const ConvOp& op, cudaStream_t stream) {
         at[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = at;
         lc.numAttrs = g_pdl ? 1 : 0;
-        P2L_CUDA_CHECK(cudaLaunchKernelEx(&lc, conv_gemm_kernel<BN, MODE, TMA_OUT, DEEP, ROWFUSE>, op.tmA, op.tmB, op.tmO, op.p));
+        P2L_CUDA_CHECK(cudaLaunchKernelEx(&lc, conv_gemm_kernel<BN, MODE, TMA_OUT, DEEP, FLAVOR>, op.tmA, op.tmB, op.tmO, op.p));
     }
     if (g_prof) cudaEventRecord(e1, stream);
     count_launch();
@@ -371,12 +375,12 @@ static int launch_t(const ConvOp& op, cudaStream_t stream) {
     return 0;
 }
 
-template <int BN, int MODE, int P>
+template <int BN, int MODE, int P, int FLAVOR = FLAVOR_PLAIN>
 static int launch_halo_t(const ConvOp& op, cudaStream_t stream) {
     using Cfg = HaloCfg<BN, P>;
     static bool attr_set = false;
     if (!attr_set) {
-        P2L_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, MODE, P>,
+        P2L_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, MODE, P, FLAVOR>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
         attr_set = true;
     }
@@ -395,7 +399,7 @@ static int launch_halo_t(const ConvOp& op, cudaStream_t stream) {
                                op.p.taps_h * op.p.taps_w * op.p.cin_chunks * kBK});
         cudaEventRecord(e0, stream);
     }
-    conv3x3_halo_kernel<BN, MODE, P><<<op.grid, Cfg::kThreads, op.halo_smem, stream>>>(op.tmA, op.tmB, op.p);
+    conv3x3_halo_kernel<BN, MODE, P, FLAVOR><<<op.grid, Cfg::kThreads, op.halo_smem, stream>>>(op.tmA, op.tmB, op.p);
     if (g_prof) cudaEventRecord(e1, stream);
     count_launch();
     P2L_CUDA_CHECK(cudaGetLastError());
@@ -403,6 +407,23 @@ static int launch_halo_t(const ConvOp& op, cudaStream_t stream) {
 }
 
 int conv_op_launch(const ConvOp& op, cudaStream_t stream) {
+    if (op.flavor == FLAVOR_SG) {
+        const bool f = op.mode == EPI_FWD;
+        if (op.halo) {
+            if (op.BN == 64 && op.halo == 10) return f ? launch_halo_t<64, EPI_FWD, 10, FLAVOR_SG>(op, stream) : launch_halo_t<64, EPI_BWD, 10, FLAVOR_SG>(op, stream);
+            set_error("conv_op_launch: StyleGAN2 halo kernels exist for BN 64, pitch 10");
+            return -1;
+        }
+        if (op.deep) {
+            if (op.BN == 64) return f ? launch_t<64, EPI_FWD, false, true, FLAVOR_SG>(op, stream) : launch_t<64, EPI_BWD, false, true, FLAVOR_SG>(op, stream);
+            if (op.BN == 128) return f ? launch_t<128, EPI_FWD, false, true, FLAVOR_SG>(op, stream) : launch_t<128, EPI_BWD, false, true, FLAVOR_SG>(op, stream);
+        }
+        if (op.BN == 64) return f ? launch_t<64, EPI_FWD, false, false, FLAVOR_SG>(op, stream) : launch_t<64, EPI_BWD, false, false, FLAVOR_SG>(op, stream);
+        if (op.BN == 128) return f ? launch_t<128, EPI_FWD, false, false, FLAVOR_SG>(op, stream) : launch_t<128, EPI_BWD, false, false, FLAVOR_SG>(op, stream);
+        if (op.BN == 256) return f ? launch_t<256, EPI_FWD, false, false, FLAVOR_SG>(op, stream) : launch_t<256, EPI_BWD, false, false, FLAVOR_SG>(op, stream);
+        set_error("conv_op_launch: StyleGAN2 epilogues exist for BN 64 / 128 / 256 (got %d)", op.BN);
+        return -1;
+    }
     if (op.halo) {
 #define P2L_HALO(bn, pp)                                                                   \
     if (op.BN == bn && op.halo == pp)                                                      \
@@ -414,9 +435,9 @@ int conv_op_launch(const ConvOp& op, cudaStream_t stream) {
         set_error("conv_op_launch: unsupported halo config BN=%d P=%d", op.BN, op.halo);
         return -1;
     }
-    if (op.rowfuse) {
-        if (op.BN == 64) return launch_t<64, EPI_FWD, false, false, true>(op, stream);
-        if (op.BN == 128) return launch_t<128, EPI_FWD, false, false, true>(op, stream);
+    if (op.flavor == FLAVOR_ROWFUSE) {
+        if (op.BN == 64) return launch_t<64, EPI_FWD, false, false, FLAVOR_ROWFUSE>(op, stream);
+        if (op.BN == 128) return launch_t<128, EPI_FWD, false, false, FLAVOR_ROWFUSE>(op, stream);
         set_error("conv_op_launch: row-fusion epilogues exist for BN 64 / 128 (got %d)", op.BN);
         return -1;
     }

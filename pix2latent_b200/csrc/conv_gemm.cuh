@@ -35,6 +35,9 @@ constexpr int kStatRedBytes = 4096;  // cross-warp staging of the BN-gradient su
 #define P2L_OCC 2
 #endif
 enum { EPI_FWD = 0, EPI_BWD = 1 };
+// epilogue flavours: every flavour is its own kernel instantiation, so that no kernel carries another one's epilogue code
+// (the epilogue body is the hot loop of 8 warps per SM; its size is what the instruction cache sees)
+enum { FLAVOR_PLAIN = 0, FLAVOR_ROWFUSE = 1, FLAVOR_SG = 2 };
 
 struct ConvGemmParams {
     // ---- M: output pixel grid [NI, H, W], tile box (nb, th, tw), tw*th*nb == 128
@@ -104,6 +107,15 @@ struct ConvGemmParams {
     int dx_C;
     float* dx_f32;  // optional fp32 copy (used for the latent-side tensors)
     int dx_f32_C;
+    // ---- StyleGAN2 modulated-convolution epilogues (FLAVOR_SG instantiations, sg_epilogue.cuh)
+    const float* sg_dm;      // [NI, sg_ld] demodulation: of this layer (FWD) / of the layer that produced `saved` (BWD)
+    int sg_ld;
+    const float* sg_noise;   // [NI, H', W'] noise image at the OUTPUT resolution (FWD) / at this grid (BWD), or null
+    const float* sg_nw;      // device scalar: noise strength
+    const float* sg_bias;    // BWD: bias of the layer that produced `saved`
+    int d2s_C;               // FWD: columns are (phase, channel), depth-to-space stores, d2s_C channels per phase (0: off)
+    int s2d;                 // BWD: dx leaves in space-to-depth layout [NI, H/2, W/2, 4 * dx_C]
+    act_t* dx2;              // BWD: optional copy of the gradient wrt `saved` before its activation's derivative
     // ---- tile order: walk the tiles from the last to the first. Consecutive layers alternate the direction
     //      ("serpentine"): a layer starts on the tiles its producer wrote LAST, which are still in the 126 MB L2.
     int tile_reverse;
@@ -260,11 +272,12 @@ __device__ __forceinline__ int tile_of(const ConvGemmParams& p, int i, int total
 // Direct epilogue: every thread reads / writes the global rows of its own accumulator row.
 // ROWFUSE: the attention instantiations (row-wise softmax statistics / normalisation / softmax gradient); kept out of
 // every other kernel — the epilogue body is the hot loop of 8 warps per SM and its size is what the instruction cache sees.
-template <int BN, int MODE, int CH, bool TMA_OUT, int NG, bool ROWFUSE = false>
+template <int BN, int MODE, int CH, bool TMA_OUT, int NG, int FLAVOR = FLAVOR_PLAIN>
 __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, const CUtensorMap* tmo, uint8_t* obuf,
                                                      uint64_t* in_full, uint64_t* in_empty, uint64_t* tfull_bar,
                                                      uint64_t* tempty_bar, uint32_t tmem_base, int total_tiles, int warp,
                                                      int lane, float* ctab) {
+    constexpr bool ROWFUSE = (FLAVOR == FLAVOR_ROWFUSE);
     // the 4 KB behind the tables: cross-warp staging of the BN-gradient column sums, [group][parity][quad][2][32]
     float* stat_red = ctab + 6 * BN;
     int stat_it = 0;
@@ -712,9 +725,13 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
     if (store_warp && elect_one()) bulk_wait0();  // shared memory must outlive the last bulk store's reads
 }
 
+}  // namespace p2l
+#include "sg_epilogue.cuh"
+namespace p2l {
+
 struct OutMaps { CUtensorMap m[6]; };  // [0..3] epilogue outputs, [4..5] epilogue inputs
 
-template <int BN, int MODE, bool TMA_OUT, bool DEEP = false, bool ROWFUSE = false>
+template <int BN, int MODE, bool TMA_OUT, bool DEEP = false, int FLAVOR = FLAVOR_PLAIN>
 __global__ void __launch_bounds__(GemmCfg<BN, TMA_OUT, DEEP>::kThreads, GemmCfg<BN, TMA_OUT, DEEP>::kOcc)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ OutMaps tmO, const ConvGemmParams p) {
@@ -891,8 +908,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        epilogue_loop_direct<BN, MODE, CH, TMA_OUT, Cfg::kEpiGroups, ROWFUSE>(p, tmO.m, obuf, in_full, in_empty, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane,
-                                                    reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + Cfg::kOutBytes + 256));
+        float* ctab = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + Cfg::kOutBytes + 256);
+        if constexpr (FLAVOR == FLAVOR_SG) {
+            epilogue_loop_sg<BN, MODE, Cfg::kEpiGroups>(p, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane, ctab);
+        } else {
+            epilogue_loop_direct<BN, MODE, CH, TMA_OUT, Cfg::kEpiGroups, FLAVOR>(p, tmO.m, obuf, in_full, in_empty, tfull_bar, tempty_bar,
+                                                                                tmem_base, total_tiles, warp, lane, ctab);
+        }
     }
 
     tc_fence_before();
@@ -925,7 +947,7 @@ struct HaloCfg {
 
 // Weights: when the whole [BN x 9*Cin] matrix fits next to the patch ring (p.halo_resb; the 64-channel
 // layers), it is loaded ONCE per persistent CTA and stays resident — per tile only the patch moves.
-template <int BN, int MODE, int P>
+template <int BN, int MODE, int P, int FLAVOR = FLAVOR_PLAIN>
 __global__ void __launch_bounds__(HaloCfg<BN, P>::kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const ConvGemmParams p) {
@@ -1070,8 +1092,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
         }
     } else {
-        epilogue_loop_direct<BN, MODE, CH, false, 2>(p, nullptr, nullptr, nullptr, nullptr, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane,
-                                                     reinterpret_cast<float*>(tail + Cfg::kMaxBars * 8));
+        float* ctab = reinterpret_cast<float*>(tail + Cfg::kMaxBars * 8);
+        if constexpr (FLAVOR == FLAVOR_SG) {
+            epilogue_loop_sg<BN, MODE, 2>(p, tfull_bar, tempty_bar, tmem_base, total_tiles, warp, lane, ctab);
+        } else {
+            epilogue_loop_direct<BN, MODE, CH, false, 2>(p, nullptr, nullptr, nullptr, nullptr, tfull_bar, tempty_bar, tmem_base, total_tiles,
+                                                         warp, lane, ctab);
+        }
     }
     tc_fence_before();
     __syncthreads();

@@ -23,6 +23,7 @@ struct ConvDesc {
     int BN = 128;
     int mode = EPI_FWD;
     ConvGemmParams epi{};  // only the epilogue fields are read from here
+    int sg = 0;            // StyleGAN2 modulated-convolution epilogue (FLAVOR_SG kernels, sg_epilogue.cuh)
 };
 
 struct ConvOp {
@@ -32,7 +33,7 @@ struct ConvOp {
     ConvGemmParams p;
     int BN, mode, grid;
     int deep;  // one CTA per SM, full-depth pipeline (few tiles, long K)
-    int rowfuse;  // attention instantiation: row-wise softmax fusions in the epilogue
+    int flavor;   // FLAVOR_PLAIN | FLAVOR_ROWFUSE (attention: row-wise softmax fusions) | FLAVOR_SG (StyleGAN2 epilogues)
     int halo;  // 0: per-tap A loads; 10 / 16: halo-patch kernel with that patch row pitch
     int halo_smem;  // dynamic shared memory of the halo kernel for this plan
     int stat_parts; // partial slots per image of the BN-gradient sums this launch fills

@@ -387,7 +387,7 @@ void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int a
 // BN-gradient sums: S0/S1[n][off + c] = sum over the layer's partial slots, in slot order (8 interleaved running sums
 // per (n, c), then a fixed tree) — the same order whatever the launch geometry of the producers was
 __global__ void __launch_bounds__(256) stat_reduce_kernel(const StatSeg* __restrict__ segs, float* __restrict__ S0,
-                                                          float* __restrict__ S1, int stride) {
+                                                          float* __restrict__ S1, int stride, int stride1) {
     __shared__ float r0[8][33], r1[8][33];
     const StatSeg sg = segs[blockIdx.x];
     const int n = blockIdx.y, lane = threadIdx.x, sl = threadIdx.y;
@@ -404,12 +404,16 @@ __global__ void __launch_bounds__(256) stat_reduce_kernel(const StatSeg* __restr
         a0 = ((r0[0][lane] + r0[1][lane]) + (r0[2][lane] + r0[3][lane])) + ((r0[4][lane] + r0[5][lane]) + (r0[6][lane] + r0[7][lane]));
         a1 = ((r1[0][lane] + r1[1][lane]) + (r1[2][lane] + r1[3][lane])) + ((r1[4][lane] + r1[5][lane]) + (r1[6][lane] + r1[7][lane]));
         S0[(long)n * stride + sg.off + sg.c0 + lane] = a0;
-        S1[(long)n * stride + sg.off + sg.c0 + lane] = a1;
+        S1[(long)n * stride1 + sg.off1 + sg.c0 + lane] = a1;
     }
 }
 void k_stat_reduce(const StatSeg* segs, int nsegs, float* S0, float* S1, int stride, int b, cudaStream_t st) {
     if (nsegs <= 0) return;
-    stat_reduce_kernel<<<dim3(nsegs, b), dim3(32, 8), 0, st>>>(segs, S0, S1, stride); count_launch();
+    stat_reduce_kernel<<<dim3(nsegs, b), dim3(32, 8), 0, st>>>(segs, S0, S1, stride, stride); count_launch();
+}
+void k_stat_reduce2(const StatSeg* segs, int nsegs, float* S0, int stride0, float* S1, int stride1, int b, cudaStream_t st) {
+    if (nsegs <= 0) return;
+    stat_reduce_kernel<<<dim3(nsegs, b), dim3(32, 8), 0, st>>>(segs, S0, S1, stride0, stride1); count_launch();
 }
 
 __global__ void pool2x2_sum_kernel(const bf16* __restrict__ in, int inC, bf16* __restrict__ out, int b, int H, int W, int C) {

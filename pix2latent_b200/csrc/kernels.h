@@ -55,8 +55,11 @@ void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int a
                        float* statp, bf16* dx, int b, int H, int W, int C, cudaStream_t st);
 // One 32-channel chunk of one BN layer's partial sums (ConvGemmParams::statp layout): S0/S1[n][off + c0 + lane] =
 // sum over `parts` slots, in slot order
-struct StatSeg { const float* p; int parts, pstride, C, off, c0; };  // parts filled of pstride allocated per image
+struct StatSeg { const float* p; int parts, pstride, C, off, c0, off1; };  // parts filled of pstride allocated per image;
+                                                                           // off / off1: column offsets into S0 / S1
 void k_stat_reduce(const StatSeg* segs, int nsegs, float* S0, float* S1, int stride, int b, cudaStream_t st);
+// the two sums go to different tables: S0[n * stride0 + off + c], S1[n * stride1 + off1 + c] (StyleGAN2: ds, ddm)
+void k_stat_reduce2(const StatSeg* segs, int nsegs, float* S0, int stride0, float* S1, int stride1, int b, cudaStream_t st);
 
 // out[b,H,W,C] = sum of the 2x2 block of in[b,2H,2W,inC] (first C channels): the skip gradient of an
 // up block at the block's input resolution

@@ -1,15 +1,18 @@
 // Native StyleGAN2 generator (see sg2.h). Layer algebra follows oracle/stylegan2.py, which restates
 // rosinality/stylegan2-pytorch model.py as reached via pix2latent/model/stylegan2.py:116-119.
 //
-// Execution map (reference op -> here):
-//   ModulatedConv2d (grouped conv with b*Cout per-sample filters)
-//        -> k_sg_modulate (x * s[b,cin]) -> conv_gemm_kernel with SHARED weights -> dm[b,cout] in k_sg_post_fwd
+// Execution map (reference op -> here; sg_epilogue.cuh has the arithmetic):
+//   ModulatedConv2d (grouped conv with b*Cout per-sample filters) + NoiseInjection + FusedLeakyReLU
+//        -> ONE tcgen05 convolution with SHARED weights per layer: the per-sample modulation is applied by the PREVIOUS
+//           layer's epilogue (it writes x_l and A_{l+1} = x_l * s_{l+1}), demodulation + noise + bias + leaky-ReLU are
+//           this layer's epilogue
 //   conv_transpose2d(stride 2) + Blur (upfirdn2d)
-//        -> the same 3x3 kernel (taps flipped) on the zero-inserted (2H+1)^2 grid, 4x4 FIR in k_sg_post_fwd
-//   NoiseInjection + FusedLeakyReLU (rosinality's fused_bias_act CUDA op) -> k_sg_post_fwd
-//   ToRGB (1x1 modulated conv, no demod) + Upsample skip (upfirdn2d CUDA op) -> k_sg_torgb_fwd
-// This round's StyleGAN2 path is correctness-first (separate elementwise passes, 4x zero-work in the
-// up-sampling convs); DESIGN.md lists the fusion / polyphase work that remains.
+//        -> the two linear maps composed into ONE 3x3 filter per output phase (py, px): a plain 3x3 convolution on the
+//           LOW-resolution grid with 4*Cout columns whose stores go depth-to-space; its gradient arrives
+//           space-to-depth, so the dgrad is a plain 3x3 convolution too. No zero-inserted grid, no FIR pass.
+//   backward: layer l's dgrad epilogue = modulation-backward of layer l + activation / noise / demodulation-backward of
+//           layer l-1 (two per-(sample, channel) sums in the deterministic partial slots)
+//   ToRGB (1x1 modulated conv, no demod) + Upsample skip (upfirdn2d CUDA op) -> k_sg_torgb_fwd / _bwd
 #include "sg2.h"
 
 #include <cmath>
@@ -23,16 +26,21 @@ struct SG2Plan {
     float *z = nullptr, *h[9] = {nullptr}, *g0 = nullptr, *g1 = nullptr;
     float *s_all = nullptr, *ds_all = nullptr, *dm_all = nullptr, *ddm_all = nullptr, *dw = nullptr;
     struct Lay {
-        act_t *A = nullptr, *x = nullptr;
-        float* D = nullptr;
-        int Ha = 0;  // grid the convolution runs on (2*Hin+1 for up layers)
+        act_t* x = nullptr;      // x_l: the layer's output (saved for the backward pass and read by ToRGB)
+        float* sp = nullptr;     // partial slots of (ds_l, ddm_{l-1}) filled by this layer's dgrad epilogue
+        int sp_parts = 0;
         ConvOp f, d;
     };
     std::vector<Lay> L;
-    std::vector<float*> rgb, weff, dweff;
-    float *drgbA = nullptr, *drgbB = nullptr, *img = nullptr;
-    act_t *dx[2] = {nullptr, nullptr}, *G = nullptr, *dDp = nullptr, *dA = nullptr;
+    act_t* A[2] = {nullptr, nullptr};   // modulated conv inputs A_l = x_{l-1} * s_l (ping-pong: A_l is read by layer l only)
+    act_t* G[2] = {nullptr, nullptr};   // dgrad inputs G_l (ping-pong)
+    act_t *dxrgb = nullptr, *dx2 = nullptr, *dA0 = nullptr;
+    StatSeg* segs = nullptr;
+    int nsegs = 0;
+    std::vector<float*> rgb, weff, dweff, drgb;
+    float* img = nullptr;
     float* scratch = nullptr;  // block partials of the per-(sample, channel) reductions (sg2_kernels.h)
+    std::vector<const float*> noise_ptrs;   // the last forward's noise images (read again by the backward epilogues)
     bool forward_done = false;
     int mode = 0;  // 0: z search (mapping network ran), 1: w / w+ search (styles from the latent rows)
 };
@@ -124,23 +132,51 @@ int SG2::finalize() {
         const auto* bsv = stage.get(pre + ".activate.bias", c.Cout);
         if (!w || !nw || !bsv) return -1;
         const float scale = 1.f / std::sqrt((float)c.Cin * 9.f);
-        std::vector<float> ws(w->size()), wsq((size_t)c.Cout * c.Cin), wsqT((size_t)c.Cout * c.Cin);
+        std::vector<float> wsq((size_t)c.Cout * c.Cin), wsqT((size_t)c.Cout * c.Cin);
         for (int o = 0; o < c.Cout; ++o)
             for (int i = 0; i < c.Cin; ++i) {
                 double q = 0;
-                for (int r = 0; r < 3; ++r)
-                    for (int s2 = 0; s2 < 3; ++s2) {
-                        const float v = (*w)[(((size_t)o * c.Cin + i) * 3 + r) * 3 + s2] * scale;
-                        q += (double)v * v;
-                        // up layers: conv_transpose == same-conv with flipped taps on the zero-inserted grid
-                        const int rr = c.up ? 2 - r : r, ss = c.up ? 2 - s2 : s2;
-                        ws[(((size_t)o * c.Cin + i) * 3 + rr) * 3 + ss] = v;
-                    }
+                for (int t = 0; t < 9; ++t) {
+                    const double v = (double)(*w)[((size_t)o * c.Cin + i) * 9 + t] * scale;
+                    q += v * v;   // demodulation uses the 3x3 weights themselves (before the transposed conv / blur)
+                }
                 wsq[(size_t)o * c.Cin + i] = (float)q;
                 wsqT[(size_t)i * c.Cout + o] = (float)q;
             }
-        c.w = upload(weights, pack_conv_fwd(ws, c.Cout, c.Cin, 3, 3));
-        c.wt = upload(weights, pack_conv_dgrad(ws, c.Cout, c.Cin, 3, 3));
+        if (!c.up) {
+            std::vector<float> ws(w->size());
+            for (size_t t = 0; t < w->size(); ++t) ws[t] = (*w)[t] * scale;
+            c.w = upload(weights, pack_conv_fwd(ws, c.Cout, c.Cin, 3, 3));
+            c.wt = upload(weights, pack_conv_dgrad(ws, c.Cout, c.Cin, 3, 3));
+        } else {
+            // conv_transpose2d(stride 2): D'[2i + ky] += W[ky] in[i]; Blur (upfirdn2d, 4-tap FIR kf, pad (1, 1)):
+            // out[Y] = sum_u kf[u] D'[Y + u - 1]. Composed, per axis and output phase py = Y & 1 (Y = 2i + py):
+            //   out[2i + py] = sum_{d in -1..1} Wc_py[d] in[i + d],   Wc_py[d] = sum_{u, ky : py + u - 1 - ky = 2d} kf[u] W[ky]
+            // i.e. four plain 3x3 filters on the low-resolution grid, one per phase (py, px): a conv with 4*Cout outputs.
+            const double kf[4] = {0.25, 0.75, 0.75, 0.25};   // [1,3,3,1] / 8 * 2 per axis (upsample_factor 2)
+            std::vector<float> wc((size_t)4 * c.Cout * c.Cin * 9, 0.f);
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px)
+                    for (int u = 0; u < 4; ++u)
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int ey = py + u - 1 - ky;
+                            if (ey & 1) continue;
+                            const int dy = ey / 2;   // -1, 0, 1
+                            for (int v = 0; v < 4; ++v)
+                                for (int kx = 0; kx < 3; ++kx) {
+                                    const int ex = px + v - 1 - kx;
+                                    if (ex & 1) continue;
+                                    const int dx = ex / 2;
+                                    const double kk = kf[u] * kf[v] * scale;
+                                    for (int o = 0; o < c.Cout; ++o)
+                                        for (int i = 0; i < c.Cin; ++i)
+                                            wc[((((size_t)(py * 2 + px) * c.Cout + o) * c.Cin + i) * 3 + (dy + 1)) * 3 + (dx + 1)] +=
+                                                (float)(kk * (*w)[(((size_t)o * c.Cin + i) * 3 + ky) * 3 + kx]);
+                                }
+                        }
+            c.w = upload(weights, pack_conv_fwd(wc, 4 * c.Cout, c.Cin, 3, 3));
+            c.wt = upload(weights, pack_conv_dgrad(wc, 4 * c.Cout, c.Cin, 3, 3));
+        }
         c.wsq = upload(weights, wsq);
         c.wsqT = upload(weights, wsqT);
         c.noise_w = upload(weights, *nw);
@@ -175,6 +211,8 @@ int SG2::finalize() {
     return 0;
 }
 
+static bool has_rgb(int l) { return l == 0 || (l % 2 == 0); }   // ToRGB t reads x_0 (t = 0) or x_{2t}
+
 SG2Plan* SG2::plan(int b) {
     auto it = plans.find(b);
     if (it != plans.end()) return it->second.get();
@@ -195,38 +233,34 @@ SG2Plan* SG2::plan(int b) {
     const int nL = (int)convs.size();
     P.L.resize(nL);
     size_t max_x = 0, max_a = 0;
+    long ms = 0;
     for (int l = 0; l < nL; ++l) {
         const Conv& c = convs[l];
         SG2Plan::Lay& q = P.L[l];
-        q.Ha = c.up ? 2 * c.Hin + 1 : c.Hin;
-        const size_t pa = (size_t)b * q.Ha * q.Ha;
-        q.A = ar.alloc<bf>(pa * c.Cin, /*zero=*/true);  // up layers: even rows / columns stay zero forever
-        q.D = ar.alloc<float>(pa * c.Cout);
         q.x = ar.alloc<bf>((size_t)b * c.Hout * c.Hout * c.Cout);
         max_x = std::max(max_x, (size_t)b * c.Hout * c.Hout * c.Cout);
-        max_a = std::max(max_a, std::max(pa * c.Cin, pa * c.Cout));
-    }
-    P.dx[0] = ar.alloc<bf>(max_x);
-    P.dx[1] = ar.alloc<bf>(max_x);
-    P.G = ar.alloc<bf>(max_x);
-    P.dDp = ar.alloc<bf>(max_a);
-    P.dA = ar.alloc<bf>(max_a);
-    {
-        long ms = 0;
-        for (int l = 0; l < nL; ++l) {
-            const Conv& c = convs[l];
-            ms = std::max(ms, std::max(k_sg_scratch_floats(b, c.Hout, c.Hout, c.Cout), k_sg_scratch_floats(b, c.Hin, c.Hin, c.Cin)));
+        max_a = std::max(max_a, (size_t)b * c.Hin * c.Hin * c.Cin);
+        if (l > 0) {
+            q.sp_parts = conv_stat_parts_max(c.Hin, c.Hin);
+            q.sp = ar.alloc<float>((size_t)b * q.sp_parts * 2 * c.Cin);
         }
-        P.scratch = ar.alloc<float>((size_t)ms);
+        ms = std::max(ms, std::max(k_sg_scratch_floats(b, c.Hout, c.Hout, c.Cout), k_sg_scratch_floats(b, c.Hin, c.Hin, c.Cin)));
     }
+    for (int k = 0; k < 2; ++k) {
+        P.A[k] = ar.alloc<bf>(std::max(max_a, max_x));
+        P.G[k] = ar.alloc<bf>(max_x);
+    }
+    P.dxrgb = ar.alloc<bf>(max_x);
+    P.dx2 = ar.alloc<bf>(max_x);
+    P.dA0 = ar.alloc<bf>((size_t)b * convs[0].Hin * convs[0].Hin * convs[0].Cin);
+    P.scratch = ar.alloc<float>((size_t)ms);
     const int R = cfg.size;
     for (size_t t = 0; t < rgbs.size(); ++t) {
         P.rgb.push_back(ar.alloc<float>((size_t)b * 3 * rgbs[t].H * rgbs[t].H));
+        P.drgb.push_back(ar.alloc<float>((size_t)b * 3 * rgbs[t].H * rgbs[t].H));
         P.weff.push_back(ar.alloc<float>((size_t)b * 3 * rgbs[t].Cin));
         P.dweff.push_back(ar.alloc<float>((size_t)b * 3 * rgbs[t].Cin));
     }
-    P.drgbA = ar.alloc<float>((size_t)b * 3 * R * R);
-    P.drgbB = ar.alloc<float>((size_t)b * 3 * R * R);
     P.img = ar.alloc<float>((size_t)b * 3 * R * R);
     if (ar.failed) return nullptr;
     auto m_tiles = [&](int hh) {
@@ -235,28 +269,68 @@ SG2Plan* SG2::plan(int b) {
         const int nb = 128 / (tw * th);
         return (long)((hh + tw - 1) / tw) * ((hh + th - 1) / th) * ((b + nb - 1) / nb);
     };
+    std::vector<StatSeg> segs;
+    const int serp = get_option("serpentine") != 0 ? 1 : 0;
     for (int l = 0; l < nL; ++l) {
         const Conv& c = convs[l];
         SG2Plan::Lay& q = P.L[l];
-        {   // D = conv(A, W')   (fp32 out)
+        const int Nf = c.up ? 4 * c.Cout : c.Cout;   // GEMM columns: (phase, channel) for up-sampling layers
+        {   // forward: x_l = lrelu(dm * conv(A_l) + noise + bias) * sqrt2 ; A_{l+1} = s_{l+1} * x_l
             ConvDesc d;
-            d.A = q.A; d.A_N = b; d.A_H = q.Ha; d.A_W = q.Ha; d.A_C = c.Cin; d.Cin = c.Cin;
-            d.B = c.w; d.Cout = c.Cout; d.kh = d.kw = 3; d.pad_h = d.pad_w = 1;
-            d.NI = b; d.H = q.Ha; d.W = q.Ha; d.mode = EPI_FWD;
-            d.BN = pick_bn_sg(c.Cout, m_tiles(q.Ha), 9L * c.Cin);
-            d.epi.raw_f32 = q.D; d.epi.raw_f32_C = c.Cout;
+            d.A = P.A[l & 1]; d.A_N = b; d.A_H = c.Hin; d.A_W = c.Hin; d.A_C = c.Cin; d.Cin = c.Cin;
+            d.B = c.w; d.Cout = Nf; d.kh = d.kw = 3; d.pad_h = d.pad_w = 1;
+            d.NI = b; d.H = c.Hin; d.W = c.Hin; d.mode = EPI_FWD;
+            d.BN = pick_bn_sg(Nf, m_tiles(c.Hin), 9L * c.Cin);
+            d.sg = 1;
+            ConvGemmParams& e = d.epi;
+            e.bias = c.bias;
+            e.sg_dm = P.dm_all + c.dm_off; e.sg_ld = DM;
+            e.sg_nw = c.noise_w;                      // e.sg_noise: the caller's noise image, set per call
+            e.d2s_C = c.up ? c.Cout : 0;
+            e.raw = q.x; e.raw_C = c.Cout;
+            if (l + 1 < nL) {
+                e.aff_a = P.s_all + convs[l + 1].s_off; e.aff_stride = S;
+                e.act = P.A[(l + 1) & 1]; e.act_C = c.Cout;
+            }
+            e.tile_reverse = serp & l;
             if (conv_op_build(&q.f, d)) return nullptr;
         }
-        {   // dA = conv^T(dD, W')
+        if (l == 0) {
+            // layer 0 reads the learned constant: only ds_0 = sum dA * const is needed (k_sg_modulate_bwd)
             ConvDesc d;
-            d.A = c.up ? P.dDp : P.G; d.A_N = b; d.A_H = q.Ha; d.A_W = q.Ha; d.A_C = c.Cout; d.Cin = c.Cout;
+            d.A = P.G[l & 1]; d.A_N = b; d.A_H = c.Hout; d.A_W = c.Hout; d.A_C = c.Cout; d.Cin = c.Cout;
             d.B = c.wt; d.Cout = c.Cin; d.kh = d.kw = 3; d.pad_h = d.pad_w = 1;
-            d.NI = b; d.H = q.Ha; d.W = q.Ha; d.mode = EPI_BWD;
-            d.BN = pick_bn_sg(c.Cin, m_tiles(q.Ha), 9L * c.Cout);
-            d.epi.dx = P.dA; d.epi.dx_C = c.Cin;
+            d.NI = b; d.H = c.Hin; d.W = c.Hin; d.mode = EPI_BWD;
+            d.BN = pick_bn_sg(c.Cin, m_tiles(c.Hin), 9L * c.Cout);
+            d.epi.dx = P.dA0; d.epi.dx_C = c.Cin;
             if (conv_op_build(&q.d, d)) return nullptr;
+            continue;
+        }
+        {   // backward: dgrad of layer l; its epilogue also takes the gradient through layer l-1's activation / noise /
+            // demodulation and writes G_{l-1} (space-to-depth when layer l-1 up-samples)
+            const Conv& pv = convs[l - 1];
+            ConvDesc d;
+            d.A = P.G[l & 1]; d.A_N = b; d.A_H = c.Hin; d.A_W = c.Hin; d.A_C = Nf; d.Cin = Nf;   // up: G_l arrives space-to-depth
+            d.B = c.wt; d.Cout = c.Cin; d.kh = d.kw = 3; d.pad_h = d.pad_w = 1;
+            d.NI = b; d.H = c.Hin; d.W = c.Hin; d.mode = EPI_BWD;
+            d.BN = pick_bn_sg(c.Cin, m_tiles(c.Hin), 9L * Nf);
+            d.sg = 1;
+            ConvGemmParams& e = d.epi;
+            e.saved = P.L[l - 1].x; e.saved_C = c.Cin;
+            e.aff_a = P.s_all + c.s_off; e.aff_stride = S;
+            e.sg_dm = P.dm_all + pv.dm_off; e.sg_ld = DM;
+            e.sg_bias = pv.bias; e.sg_nw = pv.noise_w;   // e.sg_noise (layer l-1's noise), e.addin, e.dx2: set per call
+            e.statp = q.sp; e.statp_parts = q.sp_parts; e.statp_C = c.Cin;
+            e.dx = P.G[(l - 1) & 1]; e.dx_C = c.Cin; e.s2d = pv.up ? 1 : 0;
+            e.addin_C = c.Cin; e.addin_climit = c.Cin;
+            e.tile_reverse = serp & (l ^ 1) & 1;
+            if (conv_op_build(&q.d, d)) return nullptr;
+            for (int c0 = 0; c0 < c.Cin; c0 += 32) segs.push_back({q.sp, q.d.stat_parts, q.sp_parts, c.Cin, c.s_off, c0, pv.dm_off});
         }
     }
+    P.nsegs = (int)segs.size();
+    P.segs = upload(ar, segs);
+    if (ar.failed) return nullptr;
     SG2Plan* raw = pp.get();
     plans[b] = pp;
     return raw;
@@ -327,25 +401,24 @@ int SG2::synth(SG2Plan& P, int b, const float* const* noise, float* img, cudaStr
         const Conv& c = convs[l];
         k_fc_fwd(P.s_all + c.s_off, S, c.wsqT, nullptr, 1.f, P.dm_all + c.dm_off, DM, b, c.Cin, c.Cout, 2, 1, st);
     }
-    const act_t* xprev = const_in;
-    long xprev_bs = 0;
+    // A_0 = const * s_0; every later A_l comes out of layer l-1's epilogue
+    k_sg_modulate(const_in, 0, P.s_all + convs[0].s_off, S, P.A[0], b, convs[0].Hin, convs[0].Hin, convs[0].Cin, st);
     int t = 0;
     for (int l = 0; l < nL; ++l) {
-        const Conv& c = convs[l];
         SG2Plan::Lay& q = P.L[l];
-        k_sg_modulate(xprev, xprev_bs, P.s_all + c.s_off, S, q.A, b, c.Hin, c.Hin, c.Cin, c.up, st);
+        q.f.p.sg_noise = noise ? noise[l] : nullptr;
         if (conv_op_launch(q.f, st)) return -1;
-        k_sg_post_fwd(q.D, P.dm_all + c.dm_off, DM, noise ? noise[l] : nullptr, c.noise_w, c.bias, q.x, b, c.Hout, c.Hout, c.Cout,
-                      c.up, st);
-        xprev = q.x;
-        xprev_bs = (long)c.Hout * c.Hout * c.Cout;
-        if (l == 0 || (l % 2 == 0)) {
+        if (has_rgb(l)) {
             const Rgb& r = rgbs[t];
             k_sg_weff(r.Wr, P.s_all + r.s_off, S, r.scale, P.weff[t], b, r.Cin, st);
             k_sg_torgb_fwd(q.x, P.weff[t], r.bias, t > 0 ? P.rgb[t - 1] : nullptr, P.rgb[t], b, r.H, r.H, r.Cin, st);
             ++t;
         }
     }
+    // the noise images are needed again by the backward epilogues (they recompute the pre-activation from x)
+    P.noise_ptrs.assign(nL, nullptr);
+    if (noise)
+        for (int l = 0; l < nL; ++l) P.noise_ptrs[l] = noise[l];
     const long n = (long)b * 3 * cfg.size * cfg.size;
     k_sg_clamp(P.rgb.back(), P.img, n, st);
     if (img && img != P.img) P2L_CUDA_CHECK(cudaMemcpyAsync(img, P.img, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -355,37 +428,50 @@ int SG2::synth(SG2Plan& P, int b, const float* const* noise, float* img, cudaStr
 
 int SG2::synth_bwd(SG2Plan& P, int b, const float* dimg, float* const* dnoise, float out_scale, const float* row_scale,
                    cudaStream_t st) {
-    const int T = (int)rgbs.size();
+    const int T = (int)rgbs.size(), nL = (int)convs.size();
     P2L_CUDA_CHECK(cudaMemsetAsync(P.ds_all, 0, (size_t)b * S * sizeof(float), st));
     P2L_CUDA_CHECK(cudaMemsetAsync(P.ddm_all, 0, (size_t)b * DM * sizeof(float), st));
     for (int t = 0; t < T; ++t) P2L_CUDA_CHECK(cudaMemsetAsync(P.dweff[t], 0, (size_t)b * 3 * rgbs[t].Cin * sizeof(float), st));
-    float *dcur = P.drgbA, *dprev = P.drgbB;
-    k_sg_clamp_bwd(P.rgb.back(), dimg, dcur, (long)b * 3 * cfg.size * cfg.size, grad_scale(), st);
-    auto layer_bwd = [&](int l) -> int {
-        const Conv& c = convs[l];
-        SG2Plan::Lay& q = P.L[l];
-        if (dnoise && dnoise[l])
-            k_sg_noise_bwd(P.dx[l & 1], q.x, c.noise_w, dnoise[l], b, c.Hout, c.Hout, c.Cout, out_scale, row_scale, st);
-        k_sg_post_bwd(P.dx[l & 1], q.x, q.D, P.dm_all + c.dm_off, DM, P.G, P.ddm_all + c.dm_off, P.scratch, b, c.Hout, c.Hout, c.Cout, c.up, st);
-        if (c.up) k_sg_blur_adjoint(P.G, P.dDp, b, c.Hout, c.Hout, c.Cout, st);
-        if (conv_op_launch(q.d, st)) return -1;
-        const act_t* xp = l == 0 ? const_in : P.L[l - 1].x;
-        const long xbs = l == 0 ? 0 : (long)c.Hin * c.Hin * c.Cin;
-        k_sg_modulate_bwd(P.dA, xp, xbs, P.s_all + c.s_off, S, l == 0 ? nullptr : P.dx[(l - 1) & 1], P.ds_all + c.s_off, S, P.scratch, b, c.Hin,
-                          c.Hin, c.Cin, c.up, st);
-        k_demod_bwd(P.ddm_all + c.dm_off, P.dm_all + c.dm_off, DM, P.s_all + c.s_off, S, c.wsq, P.ds_all + c.s_off, S, b, c.Cin,
-                    c.Cout, st);
-        return 0;
-    };
-    for (int t = T - 1; t >= 0; --t) {
+    // gradient of every resolution's rgb image: d rgb_{t-1} = (adjoint of the FIR up-sampling)(d rgb_t)
+    k_sg_clamp_bwd(P.rgb.back(), dimg, P.drgb[T - 1], (long)b * 3 * cfg.size * cfg.size, grad_scale(), st);
+    for (int t = T - 1; t > 0; --t) k_sg_rgb_up_adjoint(P.drgb[t], P.drgb[t - 1], b, rgbs[t].H / 2, rgbs[t].H / 2, st);
+    // gradient wrt x_l through its ToRGB branch -> dxrgb; style gradient of that ToRGB
+    auto rgb_branch = [&](int l) {
+        const int t = l / 2;   // l == 0 -> 0, l == 2t -> t
         const Rgb& r = rgbs[t];
-        const int l = (t == 0) ? 0 : 2 * t;
-        k_sg_torgb_bwd(dcur, P.L[l].x, P.weff[t], P.dx[l & 1], P.dweff[t], P.scratch, b, r.H, r.H, r.Cin, t < T - 1 ? 1 : 0, st);
+        k_sg_torgb_bwd(P.drgb[t], P.L[l].x, P.weff[t], P.dxrgb, P.dweff[t], P.scratch, b, r.H, r.H, r.Cin, 0, st);
         k_sg_weff_bwd(P.dweff[t], r.Wr, r.scale, P.ds_all + r.s_off, S, b, r.Cin, st);
-        if (t > 0) k_sg_rgb_up_adjoint(dcur, dprev, b, r.H / 2, r.H / 2, st);
-        if (layer_bwd(l)) return -1;
-        if (t > 0 && layer_bwd(l - 1)) return -1;
-        std::swap(dcur, dprev);
+    };
+    {   // last layer: its output feeds the last ToRGB only
+        const int l = nL - 1;
+        const Conv& c = convs[l];
+        rgb_branch(l);
+        if (dnoise && dnoise[l]) k_sg_noise_bwd(P.dxrgb, P.L[l].x, c.noise_w, dnoise[l], b, c.Hout, c.Hout, c.Cout, out_scale, row_scale, st);
+        k_sg_post_bwd_x(P.dxrgb, P.L[l].x, P.dm_all + c.dm_off, DM, P.noise_ptrs[l], c.noise_w, c.bias, P.G[l & 1],
+                        P.ddm_all + c.dm_off, P.scratch, b, c.Hout, c.Hout, c.Cout, st);
+    }
+    for (int l = nL - 1; l >= 1; --l) {
+        const Conv& pv = convs[l - 1];
+        SG2Plan::Lay& q = P.L[l];
+        const bool rgb = has_rgb(l - 1);
+        if (rgb) rgb_branch(l - 1);
+        const bool want_dn = dnoise && dnoise[l - 1];
+        q.d.p.sg_noise = P.noise_ptrs[l - 1];
+        q.d.p.addin = rgb ? P.dxrgb : nullptr;
+        q.d.p.dx2 = want_dn ? P.dx2 : nullptr;
+        if (conv_op_launch(q.d, st)) return -1;
+        if (want_dn) k_sg_noise_bwd(P.dx2, P.L[l - 1].x, pv.noise_w, dnoise[l - 1], b, pv.Hout, pv.Hout, pv.Cout, out_scale, row_scale, st);
+    }
+    {   // layer 0: ds_0 = sum dA_0 * const
+        const Conv& c = convs[0];
+        if (conv_op_launch(P.L[0].d, st)) return -1;
+        k_sg_modulate_bwd(P.dA0, const_in, 0, P.s_all + c.s_off, S, nullptr, P.ds_all + c.s_off, S, P.scratch, b, c.Hin, c.Hin, c.Cin, st);
+    }
+    // (ds_l, ddm_{l-1}) from the dgrad epilogues' partial slots, then the gradient through every demodulation
+    k_stat_reduce2(P.segs, P.nsegs, P.ds_all, S, P.ddm_all, DM, b, st);
+    for (int l = 0; l < nL; ++l) {
+        const Conv& c = convs[l];
+        k_demod_bwd(P.ddm_all + c.dm_off, P.dm_all + c.dm_off, DM, P.s_all + c.s_off, S, c.wsq, P.ds_all + c.s_off, S, b, c.Cin, c.Cout, st);
     }
     return 0;
 }

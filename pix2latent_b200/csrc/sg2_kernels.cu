@@ -186,35 +186,34 @@ void k_demod_bwd(const float* ddm, const float* dm, int lddm, const float* s, in
 }
 
 // ----------------------------------------------------------------------------- modulation
-// A[b, p, c] = x[b or 0, p, c] * s[b, c]; up: written at (2y+1, 2x+1) of a zero-filled [2H+1, 2W+1] grid
+// A[b, p, c] = x[b or 0, p, c] * s[b, c] (layer 0: the learned constant times its style; every later layer's
+// modulated input comes out of the previous layer's convolution epilogue)
 __global__ void modulate_kernel(const bf16* __restrict__ x, long x_bstride, const float* __restrict__ s, int lds, bf16* __restrict__ A,
-                                int b, int H, int W, int C, int up) {
+                                int b, int H, int W, int C) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int CG = C / 8;
     const long total = (long)b * H * W * CG;
     if (i >= total) return;
     const int cg = i % CG;
     const long q = i / CG;
-    const int xx = q % W, y = (q / W) % H, bi = q / ((long)W * H);
+    const long pp = q % ((long)W * H);
+    const int bi = q / ((long)W * H);
     float v[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + bi * x_bstride + ((long)y * W + xx) * C + cg * 8)), v);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + bi * x_bstride + pp * C + cg * 8)), v);
     const float4 s0 = *reinterpret_cast<const float4*>(s + (long)bi * lds + cg * 8);
     const float4 s1 = *reinterpret_cast<const float4*>(s + (long)bi * lds + cg * 8 + 4);
     v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
-    long o;
-    if (up) o = (((long)bi * (2 * H + 1) + 2 * y + 1) * (2 * W + 1) + 2 * xx + 1) * C + cg * 8;
-    else o = q * C + cg * 8;
-    *reinterpret_cast<uint4*>(A + o) = pack8(v);
+    *reinterpret_cast<uint4*>(A + q * C + cg * 8) = pack8(v);
 }
-void k_sg_modulate(const bf16* x, long x_bstride, const float* s, int lds, bf16* A, int b, int H, int W, int C, int up, cudaStream_t st) {
+void k_sg_modulate(const bf16* x, long x_bstride, const float* s, int lds, bf16* A, int b, int H, int W, int C, cudaStream_t st) {
     const long total = (long)b * H * W * (C / 8);
-    modulate_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, x_bstride, s, lds, A, b, H, W, C, up); count_launch();
+    modulate_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, x_bstride, s, lds, A, b, H, W, C); count_launch();
 }
 
-// backward: dA (sampled at odd positions when up) -> ds[b,c] += sum_p dA*x ; dx = s*dA
+// backward: ds[b,c] += sum_p dA*x ; dx = s*dA (when dx != null)
 // block = 8 channel groups x 32 pixels, one image; 64 channels per blockIdx.y
 __global__ void modulate_bwd_kernel(const bf16* __restrict__ dA, const bf16* __restrict__ x, long x_bstride, const float* __restrict__ s,
-                                    int lds, bf16* __restrict__ dx, float* __restrict__ part, int H, int W, int C, int up) {
+                                    int lds, bf16* __restrict__ dx, float* __restrict__ part, int H, int W, int C) {
     __shared__ float red[32][65];
     const int cg = threadIdx.x, py = threadIdx.y;
     const int c = blockIdx.y * 64 + cg * 8;
@@ -224,10 +223,7 @@ __global__ void modulate_bwd_kernel(const bf16* __restrict__ dA, const bf16* __r
 #pragma unroll
     for (int e = 0; e < 8; ++e) { sv[e] = s[(long)bi * lds + c + e]; acc[e] = 0.f; }
     for (int p = blockIdx.x * 256 + py; p < min(HW, (int)(blockIdx.x + 1) * 256); p += 32) {
-        const int y = p / W, xx = p % W;
-        long ia;
-        if (up) ia = (((long)bi * (2 * H + 1) + 2 * y + 1) * (2 * W + 1) + 2 * xx + 1) * C + c;
-        else ia = ((long)bi * HW + p) * C + c;
+        const long ia = ((long)bi * HW + p) * C + c;
         float g[8], xv[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(dA + ia)), g);
         unpack8(__ldg(reinterpret_cast<const uint4*>(x + bi * x_bstride + (long)p * C + c)), xv);
@@ -260,97 +256,41 @@ static void partial_reduce_add(const float* part, int parts, int b, int n, float
 }
 long k_sg_scratch_floats(int b, int H, int W, int C) { return (long)b * cdiv((long)H * W, 256) * C * 3; }
 void k_sg_modulate_bwd(const bf16* dA, const bf16* x, long x_bstride, const float* s, int lds, bf16* dx, float* ds, int ldds,
-                       float* scratch, int b, int H, int W, int C, int up, cudaStream_t st) {
+                       float* scratch, int b, int H, int W, int C, cudaStream_t st) {
     dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
-    modulate_bwd_kernel<<<grid, block, 0, st>>>(dA, x, x_bstride, s, lds, dx, scratch, H, W, C, up); count_launch();
+    modulate_bwd_kernel<<<grid, block, 0, st>>>(dA, x, x_bstride, s, lds, dx, scratch, H, W, C); count_launch();
     partial_reduce_add(scratch, (int)grid.x, b, C, ds, ldds, st);
 }
 
-// ----------------------------------------------------------------------------- demod + noise + bias + lrelu (+ blur)
-// x = lrelu(dm * [blur](D) + nw * noise + bias) * sqrt2. up: D is [b, H+1, W+1, C] (conv_transpose grid),
-// blur = 4x4 FIR with pad (1,1): out[y] = sum_t D[y + t - 1] k[t]
-__device__ __forceinline__ void blur_gather(const float* __restrict__ D, int bi, int y, int xx, int H, int W, int C, int c, float (&u)[8]) {
-    const int Hd = H + 1, Wd = W + 1;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) u[e] = 0.f;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int yy = y + t - 1;
-        if (yy < 0 || yy >= Hd) continue;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const int xv = xx + v - 1;
-            if (xv < 0 || xv >= Wd) continue;
-            const float kw = kFir[t] * kFir[v];
-            const float* src = D + (((long)bi * Hd + yy) * Wd + xv) * C + c;
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-            const float4 bq = __ldg(reinterpret_cast<const float4*>(src) + 1);
-            u[0] = fmaf(kw, a.x, u[0]); u[1] = fmaf(kw, a.y, u[1]); u[2] = fmaf(kw, a.z, u[2]); u[3] = fmaf(kw, a.w, u[3]);
-            u[4] = fmaf(kw, bq.x, u[4]); u[5] = fmaf(kw, bq.y, u[5]); u[6] = fmaf(kw, bq.z, u[6]); u[7] = fmaf(kw, bq.w, u[7]);
-        }
-    }
-}
-__global__ void post_fwd_kernel(const float* __restrict__ D, const float* __restrict__ dm, int lddm, const float* __restrict__ noise,
-                                const float* __restrict__ nw, const float* __restrict__ bias, bf16* __restrict__ x, int b, int H, int W,
-                                int C, int up) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int CG = C / 8;
-    const long total = (long)b * H * W * CG;
-    if (i >= total) return;
-    const int cg = i % CG, c = cg * 8;
-    const long q = i / CG;
-    const int xx = q % W, y = (q / W) % H, bi = q / ((long)W * H);
-    float u[8];
-    if (up) {
-        blur_gather(D, bi, y, xx, H, W, C, c, u);
-    } else {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(D + q * C + c));
-        const float4 bq = __ldg(reinterpret_cast<const float4*>(D + q * C + c) + 1);
-        u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = bq.x; u[5] = bq.y; u[6] = bq.z; u[7] = bq.w;
-    }
-    const float nz = noise ? nw[0] * noise[q] : 0.f;
-    float o[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const float pre = dm[(long)bi * lddm + c + e] * u[e] + nz + bias[c + e];
-        o[e] = (pre > 0.f ? pre : 0.2f * pre) * kSqrt2;
-    }
-    *reinterpret_cast<uint4*>(x + q * C + c) = pack8(o);
-}
-void k_sg_post_fwd(const float* D, const float* dm, int lddm, const float* noise, const float* nw, const float* bias, bf16* x,
-                   int b, int H, int W, int C, int up, cudaStream_t st) {
-    const long total = (long)b * H * W * (C / 8);
-    post_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(D, dm, lddm, noise, nw, bias, x, b, H, W, C, up); count_launch();
-}
-
-// backward pass 1: g = dx * sqrt2 * lrelu'(x) ; ddm[b,c] += sum_p g * u (u = [blurred] D) ; G = dm * g (bf16)
-__global__ void post_bwd_kernel(const bf16* __restrict__ dx, const bf16* __restrict__ x, const float* __restrict__ D,
-                                const float* __restrict__ dm, int lddm, bf16* __restrict__ G, float* __restrict__ part, int H, int W, int C, int up) {
+// ----------------------------------------------------------------------------- last layer's activation backward
+// The gradient through layer l's leaky-ReLU / noise / bias / demodulation normally lives in the epilogue of layer l+1's
+// dgrad (sg_epilogue.cuh); the LAST layer has no successor, so it runs here as an element-wise pass with the same
+// arithmetic: g = dx * sqrt2 * lrelu'(x) ; u = (lrelu^-1(x / sqrt2) - nw * noise - bias) / dm ; ddm[b,c] += sum_p g * u ;
+// G = dm * g (16-bit). block = 8 channel groups x 32 pixels, 64 channels per blockIdx.y
+__global__ void post_bwd_x_kernel(const bf16* __restrict__ dx, const bf16* __restrict__ x, const float* __restrict__ dm, int lddm,
+                                  const float* __restrict__ noise, const float* __restrict__ nw, const float* __restrict__ bias,
+                                  bf16* __restrict__ G, float* __restrict__ part, int H, int W, int C) {
     __shared__ float red[32][65];
     const int cg = threadIdx.x, py = threadIdx.y;
     const int c = blockIdx.y * 64 + cg * 8;
     const int bi = blockIdx.z;
     const int HW = H * W;
-    float dmv[8], acc[8];
+    float dmv[8], bv[8], acc[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { dmv[e] = dm[(long)bi * lddm + c + e]; acc[e] = 0.f; }
+    for (int e = 0; e < 8; ++e) { dmv[e] = dm[(long)bi * lddm + c + e]; bv[e] = bias[c + e]; acc[e] = 0.f; }
+    const float nwv = noise ? nw[0] : 0.f;
     for (int p = blockIdx.x * 256 + py; p < min(HW, (int)(blockIdx.x + 1) * 256); p += 32) {
-        const int y = p / W, xx = p % W;
         const long o = ((long)bi * HW + p) * C + c;
-        float g[8], xv[8], u[8];
+        float g[8], xv[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(dx + o)), g);
         unpack8(__ldg(reinterpret_cast<const uint4*>(x + o)), xv);
-        if (up) {
-            blur_gather(D, bi, y, xx, H, W, C, c, u);
-        } else {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(D + o));
-            const float4 bq = __ldg(reinterpret_cast<const float4*>(D + o) + 1);
-            u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = bq.x; u[5] = bq.y; u[6] = bq.z; u[7] = bq.w;
-        }
+        const float nz = noise ? nwv * noise[(long)bi * HW + p] : 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            g[e] *= (xv[e] > 0.f ? 1.f : 0.2f) * kSqrt2;
-            acc[e] += g[e] * u[e];
+            const bool pos = xv[e] > 0.f;
+            g[e] *= pos ? kSqrt2 : 0.2f * kSqrt2;
+            const float pre = xv[e] * (pos ? (1.f / kSqrt2) : (1.f / (0.2f * kSqrt2)));
+            acc[e] += g[e] * ((pre - nz - bv[e]) / dmv[e]);
             g[e] *= dmv[e];
         }
         *reinterpret_cast<uint4*>(G + o) = pack8(g);
@@ -366,45 +306,11 @@ __global__ void post_bwd_kernel(const bf16* __restrict__ dx, const bf16* __restr
         part[((long)bi * gridDim.x + blockIdx.x) * C + blockIdx.y * 64 + tid] = t;
     }
 }
-void k_sg_post_bwd(const bf16* dx, const bf16* x, const float* D, const float* dm, int lddm, bf16* G, float* ddm, float* scratch,
-                   int b, int H, int W, int C, int up, cudaStream_t st) {
+void k_sg_post_bwd_x(const bf16* dx, const bf16* x, const float* dm, int lddm, const float* noise, const float* nw, const float* bias,
+                     bf16* G, float* ddm, float* scratch, int b, int H, int W, int C, cudaStream_t st) {
     dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
-    post_bwd_kernel<<<grid, block, 0, st>>>(dx, x, D, dm, lddm, G, scratch, H, W, C, up); count_launch();
+    post_bwd_x_kernel<<<grid, block, 0, st>>>(dx, x, dm, lddm, noise, nw, bias, G, scratch, H, W, C); count_launch();
     partial_reduce_add(scratch, (int)grid.x, b, C, ddm, lddm, st);
-}
-
-// backward pass 2 (up layers): adjoint of the blur: dD'[m, n] = sum_{t,v} G[m - t + 1, n - v + 1] k[t] k[v]
-__global__ void blur_adjoint_kernel(const bf16* __restrict__ G, bf16* __restrict__ dD, int b, int H, int W, int C) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int CG = C / 8, Hd = H + 1, Wd = W + 1;
-    const long total = (long)b * Hd * Wd * CG;
-    if (i >= total) return;
-    const int cg = i % CG, c = cg * 8;
-    const long q = i / CG;
-    const int n = q % Wd, m = (q / Wd) % Hd, bi = q / ((long)Wd * Hd);
-    float u[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) u[e] = 0.f;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int y = m - t + 1;
-        if (y < 0 || y >= H) continue;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const int xx = n - v + 1;
-            if (xx < 0 || xx >= W) continue;
-            float g[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(G + (((long)bi * H + y) * W + xx) * C + c)), g);
-            const float kw = kFir[t] * kFir[v];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) u[e] = fmaf(kw, g[e], u[e]);
-        }
-    }
-    *reinterpret_cast<uint4*>(dD + q * C + c) = pack8(u);
-}
-void k_sg_blur_adjoint(const bf16* G, bf16* dD, int b, int H, int W, int C, cudaStream_t st) {
-    const long total = (long)b * (H + 1) * (W + 1) * (C / 8);
-    blur_adjoint_kernel<<<cdiv(total, 256), 256, 0, st>>>(G, dD, b, H, W, C); count_launch();
 }
 
 // ----------------------------------------------------------------------------- ToRGB

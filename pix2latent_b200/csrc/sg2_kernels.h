@@ -20,18 +20,18 @@ void k_pixelnorm_fwd(const float* x, float* y, int b, int n, cudaStream_t st);
 void k_pixelnorm_bwd(const float* x, const float* dy, float* dx, int b, int n, float scale, const float* row_scale, cudaStream_t st);
 void k_demod_bwd(const float* ddm, const float* dm, int lddm, const float* s, int lds, const float* Wsq, float* ds, int ldds,
                  int b, int Cin, int Cout, cudaStream_t st);
-void k_sg_modulate(const bf16* x, long x_bstride, const float* s, int lds, bf16* A, int b, int H, int W, int C, int up, cudaStream_t st);
-// The three per-(sample, channel) reductions of the backward pass (modulate_bwd -> ds, post_bwd -> ddm, torgb_bwd -> dweff)
+// A[b, p, c] = x[b or 0 (x_bstride 0), p, c] * s[b, c]: layer 0's modulated input (the learned constant times its style)
+void k_sg_modulate(const bf16* x, long x_bstride, const float* s, int lds, bf16* A, int b, int H, int W, int C, cudaStream_t st);
+// The per-(sample, channel) reductions of the element-wise backward kernels (modulate_bwd -> ds, post_bwd_x -> ddm, torgb_bwd -> dweff)
 // are two-stage and atomic-free: every 256-pixel block writes its partial sums to `scratch` (>= k_sg_scratch_floats
 // floats), a second kernel adds them to the destination in block order.
 long k_sg_scratch_floats(int b, int H, int W, int C);
 void k_sg_modulate_bwd(const bf16* dA, const bf16* x, long x_bstride, const float* s, int lds, bf16* dx, float* ds, int ldds,
-                       float* scratch, int b, int H, int W, int C, int up, cudaStream_t st);
-void k_sg_post_fwd(const float* D, const float* dm, int lddm, const float* noise, const float* nw, const float* bias, bf16* x,
-                   int b, int H, int W, int C, int up, cudaStream_t st);
-void k_sg_post_bwd(const bf16* dx, const bf16* x, const float* D, const float* dm, int lddm, bf16* G, float* ddm, float* scratch,
-                   int b, int H, int W, int C, int up, cudaStream_t st);
-void k_sg_blur_adjoint(const bf16* G, bf16* dD, int b, int H, int W, int C, cudaStream_t st);
+                       float* scratch, int b, int H, int W, int C, cudaStream_t st);
+// The last layer's activation / noise / bias / demodulation backward (every other layer's lives in the next layer's
+// dgrad epilogue, sg_epilogue.cuh): G = dm * dx * sqrt2 * lrelu'(x) ; ddm += sum_p g * u, u recomputed from x
+void k_sg_post_bwd_x(const bf16* dx, const bf16* x, const float* dm, int lddm, const float* noise, const float* nw, const float* bias,
+                     bf16* G, float* ddm, float* scratch, int b, int H, int W, int C, cudaStream_t st);
 void k_sg_weff(const float* Wr, const float* s, int lds, float scale, float* weff, int b, int C, cudaStream_t st);
 void k_sg_torgb_fwd(const bf16* x, const float* weff, const float* bias, const float* prev, float* rgb, int b, int H, int W, int C,
                     cudaStream_t st);
