@@ -37,6 +37,8 @@ struct SG2Plan {
     act_t *dxrgb = nullptr, *dx2 = nullptr, *dA0 = nullptr;
     StatSeg* segs = nullptr;
     int nsegs = 0;
+    void *demod_tab = nullptr, *demod_bwd_tab = nullptr;   // batched per-layer demodulation GEMMs (b <= 24)
+    int demod_maxJ = 0, demod_bwd_maxJ = 0;
     std::vector<float*> rgb, weff, dweff, drgb;
     float* img = nullptr;
     float* scratch = nullptr;  // block partials of the per-(sample, channel) reductions (sg2_kernels.h)
@@ -253,6 +255,7 @@ SG2Plan* SG2::plan(int b) {
     P.dxrgb = ar.alloc<bf>(max_x);
     P.dx2 = ar.alloc<bf>(max_x);
     P.dA0 = ar.alloc<bf>((size_t)b * convs[0].Hin * convs[0].Hin * convs[0].Cin);
+    ms = std::max(ms, 8L * 24 * sdim);   // split-K partials of the style-gradient GEMM (k_fc_bwd)
     P.scratch = ar.alloc<float>((size_t)ms);
     const int R = cfg.size;
     for (size_t t = 0; t < rgbs.size(); ++t) {
@@ -330,6 +333,19 @@ SG2Plan* SG2::plan(int b) {
     }
     P.nsegs = (int)segs.size();
     P.segs = upload(ar, segs);
+    if (b <= 24) {
+        std::vector<unsigned char> h0(k_sg_batch_bytes(nL)), h1(k_sg_batch_bytes(nL));
+        for (int l = 0; l < nL; ++l) {
+            const Conv& c = convs[l];
+            k_sg_demod_desc(h0.data(), l, P.s_all + c.s_off, S, c.wsqT, P.dm_all + c.dm_off, DM, b, c.Cin, c.Cout);
+            k_sg_demod_bwd_desc(h1.data(), l, P.ddm_all + c.dm_off, P.dm_all + c.dm_off, DM, P.s_all + c.s_off, S, c.wsq,
+                                P.ds_all + c.s_off, S, b, c.Cin, c.Cout);
+            P.demod_maxJ = std::max(P.demod_maxJ, c.Cout);
+            P.demod_bwd_maxJ = std::max(P.demod_bwd_maxJ, c.Cin);
+        }
+        P.demod_tab = upload(ar, h0);
+        P.demod_bwd_tab = upload(ar, h1);
+    }
     if (ar.failed) return nullptr;
     SG2Plan* raw = pp.get();
     plans[b] = pp;
@@ -397,9 +413,13 @@ int SG2::forward_w(int b, const float* latent, const float* const* noise, float*
 
 int SG2::synth(SG2Plan& P, int b, const float* const* noise, float* img, cudaStream_t st) {
     const int nL = (int)convs.size();
-    for (int l = 0; l < nL; ++l) {
-        const Conv& c = convs[l];
-        k_fc_fwd(P.s_all + c.s_off, S, c.wsqT, nullptr, 1.f, P.dm_all + c.dm_off, DM, b, c.Cin, c.Cout, 2, 1, st);
+    if (P.demod_tab) {
+        k_sg_demod_batched(P.demod_tab, nL, b, P.demod_maxJ, st);
+    } else {
+        for (int l = 0; l < nL; ++l) {
+            const Conv& c = convs[l];
+            k_fc_fwd(P.s_all + c.s_off, S, c.wsqT, nullptr, 1.f, P.dm_all + c.dm_off, DM, b, c.Cin, c.Cout, 2, 1, st);
+        }
     }
     // A_0 = const * s_0; every later A_l comes out of layer l-1's epilogue
     k_sg_modulate(const_in, 0, P.s_all + convs[0].s_off, S, P.A[0], b, convs[0].Hin, convs[0].Hin, convs[0].Cin, st);
@@ -469,9 +489,13 @@ int SG2::synth_bwd(SG2Plan& P, int b, const float* dimg, float* const* dnoise, f
     }
     // (ds_l, ddm_{l-1}) from the dgrad epilogues' partial slots, then the gradient through every demodulation
     k_stat_reduce2(P.segs, P.nsegs, P.ds_all, S, P.ddm_all, DM, b, st);
-    for (int l = 0; l < nL; ++l) {
-        const Conv& c = convs[l];
-        k_demod_bwd(P.ddm_all + c.dm_off, P.dm_all + c.dm_off, DM, P.s_all + c.s_off, S, c.wsq, P.ds_all + c.s_off, S, b, c.Cin, c.Cout, st);
+    if (P.demod_bwd_tab) {
+        k_sg_demod_bwd_batched(P.demod_bwd_tab, nL, b, P.demod_bwd_maxJ, st);
+    } else {
+        for (int l = 0; l < nL; ++l) {
+            const Conv& c = convs[l];
+            k_demod_bwd(P.ddm_all + c.dm_off, P.dm_all + c.dm_off, DM, P.s_all + c.s_off, S, c.wsq, P.ds_all + c.s_off, S, b, c.Cin, c.Cout, st);
+        }
     }
     return 0;
 }
@@ -483,7 +507,7 @@ int SG2::backward(int b, const float* dimg, float* dz, cudaStream_t st, float sc
     if (P.mode != 0) { set_error("sg2: backward (z search) after forward_w; use backward_w"); return -1; }
     if (synth_bwd(P, b, dimg, nullptr, 1.f, nullptr, st)) return -1;
     // styles -> w -> mapping network -> z
-    k_fc_bwd(P.ds_all, S, nullptr, 0, aff, 1.f / std::sqrt((float)sdim), P.dw, sdim, b, sdim, S, 0, 0, st);
+    k_fc_bwd(P.ds_all, S, nullptr, 0, aff, 1.f / std::sqrt((float)sdim), P.dw, sdim, b, sdim, S, 0, 0, st, b <= 24 ? P.scratch : nullptr);
     float *g = P.dw, *gn = P.g0;
     for (int k = n_mlp - 1; k >= 0; --k) {
         k_fc_bwd(g, sdim, P.h[k + 1], sdim, map_W[k], map_scale, gn, sdim, b, sdim, sdim, 1, 0, st);

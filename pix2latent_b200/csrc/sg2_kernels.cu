@@ -45,9 +45,15 @@ struct SgGemm {
     float* y; int ldy;
     const float* s; int lds;        // EPI_SUB_SCALED: y -= s * acc
     int b, K, J, act;
+    float* part; int kper;          // split-K (non-batched launches): blockIdx.y owns k in [y * kper, (y+1) * kper) and writes its
+                                    // raw sums to part[(y * b + bi) * J + j]; sg_splitk_finish_kernel adds them in y order
 };
+// `tab` != null: a batch of independent GEMMs in one launch, blockIdx.y picks the descriptor (the per-layer demodulation
+// GEMMs and their backward: 15 launches of a few microseconds each become one)
 template <int NB>
-__global__ void __launch_bounds__(256) sg_gemm_kernel(const SgGemm a, int pro, int epi) {
+__global__ void __launch_bounds__(256) sg_gemm_kernel(const SgGemm a0, const SgGemm* __restrict__ tab, int pro, int epi) {
+    const SgGemm a = tab ? tab[blockIdx.y] : a0;
+    if (blockIdx.x * 32 >= a.J) return;
     constexpr int KC = 128, KW = KC / 8;   // K chunk staged per pass; k's per warp and chunk
     __shared__ float xs[NB][KC];
     __shared__ float red[8][NB][33];
@@ -56,22 +62,24 @@ __global__ void __launch_bounds__(256) sg_gemm_kernel(const SgGemm a, int pro, i
     float acc[NB];
 #pragma unroll
     for (int i = 0; i < NB; ++i) acc[i] = 0.f;
-    for (int k0 = 0; k0 < a.K; k0 += KC) {
+    const bool split = (tab == nullptr) && a.part != nullptr;
+    const int kbeg = split ? blockIdx.y * a.kper : 0, kstop = split ? min(a.K, kbeg + a.kper) : a.K;
+    for (int k0 = kbeg; k0 < kstop; k0 += KC) {
         __syncthreads();
         for (int t = threadIdx.x; t < NB * KC; t += 256) {
             const int bi = t / KC, kk = t - bi * KC, k = k0 + kk;
             float v = 0.f;
-            if (bi < a.b && k < a.K) {
+            if (bi < a.b && k < kstop) {
                 v = a.x[(long)bi * a.ldx + k];
                 if (pro == SG_PRO_SQUARE) v *= v;
                 else if (pro == SG_PRO_ACTGRAD) v *= (a.x2[(long)bi * a.ldx2 + k] > 0.f ? 1.f : 0.2f) * kSqrt2;
-                else if (pro == SG_PRO_DEMOD) { const float d = a.x2[(long)bi * a.ldx2 + k]; v *= d * d * d; }
+                else if (pro == SG_PRO_DEMOD) { const float d = a.x2[(long)bi * a.ldx2 + k]; v *= d * d; }   // x holds ddm * dm
             }
             xs[bi][kk] = v;
         }
         __syncthreads();
         if (j < a.J) {
-            const int kend = min(KC, a.K - k0);
+            const int kend = min(KC, kstop - k0);
             const int kk = warp * KW;   // warp w: k = w*KW .. w*KW+KW-1 of this chunk
             if (kk < kend) {
                 const int n = min(KW, kend - kk);
@@ -93,6 +101,10 @@ __global__ void __launch_bounds__(256) sg_gemm_kernel(const SgGemm a, int pro, i
         if (bi >= a.b || jo >= a.J) continue;
         float v = ((red[0][bi][jj] + red[1][bi][jj]) + (red[2][bi][jj] + red[3][bi][jj])) +
                   ((red[4][bi][jj] + red[5][bi][jj]) + (red[6][bi][jj] + red[7][bi][jj]));
+        if (split) {
+            a.part[((long)blockIdx.y * a.b + bi) * a.J + jo] = v;
+            continue;
+        }
         v *= a.wscale;
         float* yp = a.y + (long)bi * a.ldy + jo;
         if (epi == SG_EPI_BIAS_ACT) {
@@ -109,6 +121,16 @@ __global__ void __launch_bounds__(256) sg_gemm_kernel(const SgGemm a, int pro, i
         }
     }
 }
+// second stage of a split-K launch: y = epi(wscale * sum_y part[y]) for the store / accumulate epilogues
+__global__ void sg_splitk_finish_kernel(const SgGemm a, int ks, int epi) {
+    const int jo = blockIdx.x * blockDim.x + threadIdx.x, bi = blockIdx.y;
+    if (jo >= a.J) return;
+    float v = 0.f;
+    for (int y = 0; y < ks; ++y) v += a.part[((long)y * a.b + bi) * a.J + jo];
+    v *= a.wscale;
+    float* yp = a.y + (long)bi * a.ldy + jo;
+    *yp = (epi == SG_EPI_ACCUM) ? *yp + v : v;
+}
 static void sg_gemm(SgGemm a, int pro, int epi, cudaStream_t st) {
     const int b_all = a.b;
     for (int b0 = 0; b0 < b_all; b0 += 24) {   // <= 24 samples per launch
@@ -118,12 +140,54 @@ static void sg_gemm(SgGemm a, int pro, int epi, cudaStream_t st) {
         c.x2 = a.x2 ? a.x2 + (long)b0 * a.ldx2 : nullptr;
         c.y = a.y + (long)b0 * a.ldy;
         c.s = a.s ? a.s + (long)b0 * a.lds : nullptr;
-        const int grid = cdiv(a.J, 32);
-        if (c.b <= 8) sg_gemm_kernel<8><<<grid, 256, 0, st>>>(c, pro, epi);
-        else if (c.b <= 16) sg_gemm_kernel<16><<<grid, 256, 0, st>>>(c, pro, epi);
-        else sg_gemm_kernel<24><<<grid, 256, 0, st>>>(c, pro, epi);
+        // long K, few output columns (style gradients -> w: K ~ 6000, J = 512): spread K over blocks
+        int ks = 1;
+        if (c.part && (epi == SG_EPI_STORE || epi == SG_EPI_ACCUM) && a.K >= 2048 && cdiv(a.J, 32) < 64) {
+            ks = 8;
+            c.kper = ((cdiv(a.K, ks) + 127) / 128) * 128;
+            ks = cdiv(a.K, c.kper);
+        }
+        if (ks <= 1) c.part = nullptr;
+        const dim3 grid(cdiv(a.J, 32), ks);
+        if (c.b <= 8) sg_gemm_kernel<8><<<grid, 256, 0, st>>>(c, nullptr, pro, epi);
+        else if (c.b <= 16) sg_gemm_kernel<16><<<grid, 256, 0, st>>>(c, nullptr, pro, epi);
+        else sg_gemm_kernel<24><<<grid, 256, 0, st>>>(c, nullptr, pro, epi);
         count_launch();
+        if (ks > 1) {
+            sg_splitk_finish_kernel<<<dim3(cdiv(a.J, 128), c.b), 128, 0, st>>>(c, ks, epi);
+            count_launch();
+        }
     }
+}
+// ---- batched form: `n` descriptors in device memory (b <= 24 each, same prologue / epilogue mode), one launch
+static void sg_gemm_batched(const SgGemm* dtab, int n, int b, int max_J, int pro, int epi, cudaStream_t st) {
+    const dim3 grid(cdiv(max_J, 32), n);
+    SgGemm none{};
+    if (b <= 8) sg_gemm_kernel<8><<<grid, 256, 0, st>>>(none, dtab, pro, epi);
+    else if (b <= 16) sg_gemm_kernel<16><<<grid, 256, 0, st>>>(none, dtab, pro, epi);
+    else sg_gemm_kernel<24><<<grid, 256, 0, st>>>(none, dtab, pro, epi);
+    count_launch();
+}
+size_t k_sg_batch_bytes(int n) { return (size_t)n * sizeof(SgGemm); }
+// descriptor i of a demodulation batch: dm[b, Cout] = rsqrt(sum_i s[b,i]^2 * WsqT[i][o] + 1e-8)
+void k_sg_demod_desc(void* host_tab, int i, const float* s, int lds, const float* wsqT, float* dm, int lddm, int b, int Cin, int Cout) {
+    SgGemm a{};
+    a.x = s; a.ldx = lds; a.M = wsqT; a.ldm = Cout; a.wscale = 1.f; a.y = dm; a.ldy = lddm; a.b = b; a.K = Cin; a.J = Cout; a.act = 2;
+    static_cast<SgGemm*>(host_tab)[i] = a;
+}
+// descriptor i of the demodulation-backward batch (see k_demod_bwd)
+void k_sg_demod_bwd_desc(void* host_tab, int i, const float* ddm, const float* dm, int lddm, const float* s, int lds, const float* wsq,
+                         float* ds, int ldds, int b, int Cin, int Cout) {
+    SgGemm a{};
+    a.x = ddm; a.ldx = lddm; a.x2 = dm; a.ldx2 = lddm; a.M = wsq; a.ldm = Cin; a.wscale = 1.f; a.y = ds; a.ldy = ldds;
+    a.s = s; a.lds = lds; a.b = b; a.K = Cout; a.J = Cin;
+    static_cast<SgGemm*>(host_tab)[i] = a;
+}
+void k_sg_demod_batched(const void* dev_tab, int n, int b, int max_J, cudaStream_t st) {
+    sg_gemm_batched(static_cast<const SgGemm*>(dev_tab), n, b, max_J, SG_PRO_SQUARE, SG_EPI_BIAS_ACT, st);
+}
+void k_sg_demod_bwd_batched(const void* dev_tab, int n, int b, int max_J, cudaStream_t st) {
+    sg_gemm_batched(static_cast<const SgGemm*>(dev_tab), n, b, max_J, SG_PRO_DEMOD, SG_EPI_SUB_SCALED, st);
 }
 // y[b, j] = act(wscale * sum_k x[b,k] * WT[k][j] + bias[j]); WT row pitch ldw
 void k_fc_fwd_ld(const float* x, int ldx, const float* WT, int ldw, const float* bias, float wscale, float* y, int ldy, int b,
@@ -139,8 +203,9 @@ void k_fc_fwd(const float* x, int ldx, const float* WT, const float* bias, float
 }
 // dx[b, k] (+)= wscale * sum_j g[b,j] * W[j][k], g = dy * act'(y); W is [out][in]
 void k_fc_bwd(const float* dy, int lddy, const float* y, int ldy, const float* W, float wscale, float* dx, int lddx, int b,
-              int in, int out, int act, int accumulate, cudaStream_t st) {
+              int in, int out, int act, int accumulate, cudaStream_t st, float* splitk_scratch) {
     SgGemm a{};
+    a.part = splitk_scratch;
     a.x = dy; a.ldx = lddy; a.x2 = y; a.ldx2 = ldy; a.M = W; a.ldm = in; a.wscale = wscale; a.y = dx; a.ldy = lddx; a.b = b;
     a.K = out; a.J = in;
     sg_gemm(a, (act == 1 && y) ? SG_PRO_ACTGRAD : SG_PRO_ID, accumulate ? SG_EPI_ACCUM : SG_EPI_STORE, st);
@@ -176,7 +241,8 @@ void k_pixelnorm_bwd(const float* x, const float* dy, float* dx, int b, int n, f
     pixelnorm_bwd_kernel<<<b, 32, 0, st>>>(x, dy, dx, n, scale, row_scale); count_launch();
 }
 
-// ds[b,i] += -s[b,i] * sum_o (ddm*dm^3)[b,o] * Wsq[o][i]   (gradient through the demodulation)
+// ds[b,i] += -s[b,i] * sum_o (ddm*dm^3)[b,o] * Wsq[o][i]   (gradient through the demodulation dm = rsqrt(sum s^2 Wsq + eps));
+// `ddm` arrives MULTIPLIED by dm (the producers sum g * u * dm per column and leave the division to this kernel)
 void k_demod_bwd(const float* ddm, const float* dm, int lddm, const float* s, int lds, const float* Wsq, float* ds, int ldds,
                  int b, int Cin, int Cout, cudaStream_t st) {
     SgGemm a{};
@@ -265,7 +331,7 @@ void k_sg_modulate_bwd(const bf16* dA, const bf16* x, long x_bstride, const floa
 // ----------------------------------------------------------------------------- last layer's activation backward
 // The gradient through layer l's leaky-ReLU / noise / bias / demodulation normally lives in the epilogue of layer l+1's
 // dgrad (sg_epilogue.cuh); the LAST layer has no successor, so it runs here as an element-wise pass with the same
-// arithmetic: g = dx * sqrt2 * lrelu'(x) ; u = (lrelu^-1(x / sqrt2) - nw * noise - bias) / dm ; ddm[b,c] += sum_p g * u ;
+// arithmetic: g = dx * sqrt2 * lrelu'(x) ; u * dm = lrelu^-1(x / sqrt2) - nw * noise - bias ; (ddm * dm)[b,c] += sum_p g * u * dm ;
 // G = dm * g (16-bit). block = 8 channel groups x 32 pixels, 64 channels per blockIdx.y
 __global__ void post_bwd_x_kernel(const bf16* __restrict__ dx, const bf16* __restrict__ x, const float* __restrict__ dm, int lddm,
                                   const float* __restrict__ noise, const float* __restrict__ nw, const float* __restrict__ bias,
@@ -290,7 +356,7 @@ __global__ void post_bwd_x_kernel(const bf16* __restrict__ dx, const bf16* __res
             const bool pos = xv[e] > 0.f;
             g[e] *= pos ? kSqrt2 : 0.2f * kSqrt2;
             const float pre = xv[e] * (pos ? (1.f / kSqrt2) : (1.f / (0.2f * kSqrt2)));
-            acc[e] += g[e] * ((pre - nz - bv[e]) / dmv[e]);
+            acc[e] += g[e] * (pre - nz - bv[e]);   // ddm * dm (see k_demod_bwd)
             g[e] *= dmv[e];
         }
         *reinterpret_cast<uint4*>(G + o) = pack8(g);

@@ -14,13 +14,22 @@ void k_fc_fwd(const float* x, int ldx, const float* WT, const float* bias, float
 void k_fc_fwd_ld(const float* x, int ldx, const float* WT, int ldw, const float* bias, float wscale, float* y, int ldy, int b,
                  int in, int out, int act, int square_in, cudaStream_t st);
 // dx (+)= wscale * (dy * act'(y)) W, W is [out][in]
+// splitk_scratch (>= 8 * 24 * in floats, or null): long reductions (out >= 2048) with few outputs are split over blocks
 void k_fc_bwd(const float* dy, int lddy, const float* y, int ldy, const float* W, float wscale, float* dx, int lddx, int b,
-              int in, int out, int act, int accumulate, cudaStream_t st);
+              int in, int out, int act, int accumulate, cudaStream_t st, float* splitk_scratch = nullptr);
 void k_pixelnorm_fwd(const float* x, float* y, int b, int n, cudaStream_t st);
 void k_pixelnorm_bwd(const float* x, const float* dy, float* dx, int b, int n, float scale, const float* row_scale, cudaStream_t st);
 void k_demod_bwd(const float* ddm, const float* dm, int lddm, const float* s, int lds, const float* Wsq, float* ds, int ldds,
                  int b, int Cin, int Cout, cudaStream_t st);
 // A[b, p, c] = x[b or 0 (x_bstride 0), p, c] * s[b, c]: layer 0's modulated input (the learned constant times its style)
+// Batched small GEMMs (one launch for all layers, b <= 24): host-side descriptor tables are filled with the *_desc calls,
+// copied to the device once per plan, and launched with *_batched (max_J = the largest output width of the batch)
+size_t k_sg_batch_bytes(int n);
+void k_sg_demod_desc(void* host_tab, int i, const float* s, int lds, const float* wsqT, float* dm, int lddm, int b, int Cin, int Cout);
+void k_sg_demod_bwd_desc(void* host_tab, int i, const float* ddm, const float* dm, int lddm, const float* s, int lds, const float* wsq,
+                         float* ds, int ldds, int b, int Cin, int Cout);
+void k_sg_demod_batched(const void* dev_tab, int n, int b, int max_J, cudaStream_t st);
+void k_sg_demod_bwd_batched(const void* dev_tab, int n, int b, int max_J, cudaStream_t st);
 void k_sg_modulate(const bf16* x, long x_bstride, const float* s, int lds, bf16* A, int b, int H, int W, int C, cudaStream_t st);
 // The per-(sample, channel) reductions of the element-wise backward kernels (modulate_bwd -> ds, post_bwd_x -> ddm, torgb_bwd -> dweff)
 // are two-stage and atomic-free: every 256-pixel block writes its partial sums to `scratch` (>= k_sg_scratch_floats

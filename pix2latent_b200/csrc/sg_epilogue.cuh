@@ -15,8 +15,9 @@
 //             ds_l[n,c]    = sum_pix acc * x_{l-1}                      (gradient of the modulation, stat 0)
 //             dx           = s_l[n,c] * acc + addin                      (addin: gradient through the ToRGB branch)
 //             g            = dx * sqrt2 * lrelu'(x_{l-1})
-//             u            = (lrelu^-1(x_{l-1} / sqrt2) - nw * noise - bias) / dm_{l-1}   (the demodulated conv output, recomputed)
-//             ddm_{l-1}[n,c] = sum_pix g * u                             (gradient of the demodulation, stat 1)
+//             u * dm       = lrelu^-1(x_{l-1} / sqrt2) - nw * noise - bias   (the conv output before demodulation is u; recomputed)
+//             (ddm * dm)_{l-1}[n,c] = sum_pix g * u * dm                  (gradient of the demodulation TIMES dm: the per-column
+//                                                                          division is left to the consumer, k_demod_bwd; stat 1)
 //             G_{l-1}      = dm_{l-1}[n,c] * g                           -> dx (operand of layer l-1's dgrad; space-to-depth
 //                                                                          when layer l-1 is an up-sampling layer)
 // i.e. one epilogue = the reference's modulate-backward of layer l + noise/bias/activation/demodulation-backward of layer
@@ -178,7 +179,7 @@ __device__ __forceinline__ void epilogue_loop_sg(const ConvGemmParams& p, uint64
                             const bool pos = y[j] > 0.f;
                             const float g = v[j] * (pos ? kSgSqrt2 : 0.2f * kSgSqrt2);
                             const float pre = y[j] * (pos ? (1.f / kSgSqrt2) : (1.f / (0.2f * kSgSqrt2)));
-                            t[j] = valid ? g * __fdividef(pre - nz - bb[e], dd[e]) : 0.f;
+                            t[j] = valid ? g * (pre - nz - bb[e]) : 0.f;   // = g * u * dm: the division by dm[n,c] waits for the column sum
                             v[j] = dd[e] * g;
                         }
                     }
