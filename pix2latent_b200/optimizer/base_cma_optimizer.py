@@ -29,10 +29,12 @@ class CMA():
     """Wrapper over ``cma.CMAEvolutionStrategy`` (1-d problems are padded to 2-d with the
     covariance adaptation off, as the reference does, base_cma_optimizer.py:170-173)."""
 
-    def __init__(self, mu=128 * [0], sigma=1.0, seed=None):
+    def __init__(self, mu=128 * [0], sigma=1.0, seed=None, popsize=None):
         options = {}
         if seed is not None:
             options["seed"] = seed
+        if popsize is not None:
+            options["popsize"] = int(popsize)
         self.is_scalar = False
         if len(mu) == 1:
             mu = list(mu) * 2
@@ -71,6 +73,7 @@ class _BaseCMAOptimizer():
         self.cma_optimizers = {}
         self._sampled = {}
         self.cma_seed = None  # not in the reference (its CMA is never seeded); opt-in
+        self.cma_popsize = None  # opt-in: population size other than PyCMA's default (BASELINE configs[3]: 144 over 8 GPUs)
 
     @torch.no_grad()
     def setup_cma(self, var_manager):
@@ -81,7 +84,7 @@ class _BaseCMAOptimizer():
             mu, sigma = (gf if type(gf) == tuple else (None, None))
             mu = np.zeros(spec["shape"]) if mu is None else mu
             sigma = 1.0 if sigma is None else sigma
-            opt = CMA(mu, sigma=sigma, seed=self.cma_seed)
+            opt = CMA(mu, sigma=sigma, seed=self.cma_seed, popsize=self.cma_popsize)
             self.cma_optimizers[(spec["var_type"], name)] = opt
             self.num_samples = max(self.num_samples, opt.batch_size())
         cprint("(cma-es) number of samples: {}".format(self.num_samples), "y")

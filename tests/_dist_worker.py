@@ -67,8 +67,46 @@ def transform_search(out_path):
                  vp=opt.vp_means["z"].numpy())
 
 
+def native_basincma(out_path):
+    """BasinCMAOptimizer with the NATIVE BigGAN / loss (tiny128 config) — single process, or one rank per GPU under NCCL
+    (LOCAL_RANK picks the device). Every rank evaluates its shard; rank 0 writes final losses / latents."""
+    import make_golden as mg
+    import test_step_gpu as ts
+    from oracle import lpips as olp
+    from pix2latent_b200 import VariableManager
+    from pix2latent_b200.loss_functions import ProjectionLoss
+    from pix2latent_b200.model import BigGAN
+    from pix2latent_b200.optimizer import BasinCMAOptimizer
+    import pix2latent_b200.distribution as dst
+    import pix2latent_b200.utils.function_hooks as hook
+    ts._setup()
+    cfg, orc, target, weight = mg.problem()
+    lp = olp.make_lpips("alex", seed=0)
+    model = BigGAN(config=ts._product_cfg(cfg), state_dict=orc.state_dict())
+    loss_fn = ProjectionLoss(lpips_state_dict={k: v.cuda() for k, v in ts._lpips_state(lp).items()})
+    torch.manual_seed(23)
+    vm = VariableManager(device="cuda")
+    mg.register(vm, hook, dst, model, target.cuda(), weight.cuda(), True)
+    opt = BasinCMAOptimizer(model, vm, loss_fn, max_batch_size=9)
+    opt.cma_seed = mg.CMA_SEED
+    variables, outs, loss = opt.optimize(meta_steps=2, grad_steps=3, last_grad_steps=4)
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        np.savez(out_path, loss=np.array(loss[0][1]["loss"], dtype=np.float64), z=torch.stack(variables.input.z.data).detach().cpu().numpy(),
+                 c=torch.stack(variables.input.c.data).detach().cpu().numpy(), mean=np.array(list(opt.cma_optimizers.values())[0].mean()),
+                 fused_calls=np.array(opt.fused_calls), world=np.array(dist.get_world_size() if dist.is_initialized() else 1))
+
+
 def main():
     out_path = sys.argv[1]
+    if len(sys.argv) > 2 and sys.argv[2] == "native":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        if int(os.environ.get("WORLD_SIZE", 1)) > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+        native_basincma(out_path)
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     dist.init_process_group("gloo")
     torch.set_num_threads(4)
     if len(sys.argv) > 2 and sys.argv[2] == "transform":
