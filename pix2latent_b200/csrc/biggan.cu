@@ -524,6 +524,9 @@ BigGANPlan* BigGAN::plan(int b) {
             // The fp32 logits never reach HBM (2 x 302 MB per step at the bench shape) and k_softmax_fwd goes away.
             OpB o1(P.qkv, b, H, H, nq, 0, dq, P.phi_p, Nk, 1, EPI_FWD);
             o1.d.B_batch = b;
+            // the row statistics are combined from one (max, sum) pair per N tile: the tile width must not depend on the
+            // batch size, or a candidate's softmax would round differently in a smaller launch (sharded == unsharded)
+            o1.d.BN = (Nk % 128 == 0) ? 128 : 64;
             const int nt = (Nk + o1.d.BN - 1) / o1.d.BN;
             P.rowstat = ar.alloc<float>(px * nt * 2);
             P.Drow = ar.alloc<float>(px);

@@ -89,9 +89,24 @@ def native_basincma(out_path):
     mg.register(vm, hook, dst, model, target.cuda(), weight.cuda(), True)
     opt = BasinCMAOptimizer(model, vm, loss_fn, max_batch_size=9)
     opt.cma_seed = mg.CMA_SEED
+    trace = {"asked": [], "told": []}   # per meta-iteration: what CMA asked, which losses it was told
+    init0, upd0 = opt.cma_init, opt.cma_update
+
+    def init1(*a, **k):
+        v = init0(*a, **k)
+        trace["asked"].append(np.array(list(opt._sampled.values())[0], dtype=np.float64))
+        return v
+
+    def upd1(*a, **k):
+        l = upd0(*a, **k)
+        trace["told"].append(np.array(l, dtype=np.float64))
+        return l
+
+    opt.cma_init, opt.cma_update = init1, upd1
     variables, outs, loss = opt.optimize(meta_steps=2, grad_steps=3, last_grad_steps=4)
     if not dist.is_initialized() or dist.get_rank() == 0:
         np.savez(out_path, loss=np.array(loss[0][1]["loss"], dtype=np.float64), z=torch.stack(variables.input.z.data).detach().cpu().numpy(),
+                 asked=np.stack(trace["asked"]), told=np.stack(trace["told"]),
                  c=torch.stack(variables.input.c.data).detach().cpu().numpy(), mean=np.array(list(opt.cma_optimizers.values())[0].mean()),
                  fused_calls=np.array(opt.fused_calls), world=np.array(dist.get_world_size() if dist.is_initialized() else 1))
 
@@ -99,6 +114,7 @@ def native_basincma(out_path):
 def main():
     out_path = sys.argv[1]
     if len(sys.argv) > 2 and sys.argv[2] == "native":
+        torch.set_num_threads(4)
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         if int(os.environ.get("WORLD_SIZE", 1)) > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))

@@ -61,7 +61,7 @@ def test_same_step_twice_same_bits(world):
             assert torch.equal(u, v), name
 
 
-@pytest.mark.parametrize("split", [(2, 4), (1, 5), (3, 3)])
+@pytest.mark.parametrize("split", [(2, 4), (1, 5), (3, 3), (9, 9), (18, 2)])
 def test_candidate_does_not_depend_on_its_batch(world, split):
     from pix2latent_b200 import native
     orc = world[1]
