@@ -445,55 +445,84 @@ void k_pool2x2_sum(const bf16* in, int inC, bf16* out, int b, int H, int W, int 
 }
 
 // ============================================================================= attention glue
-__global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, int xC, int c0, int C, bf16* out, bf16* outT,
-                                    unsigned char* idx, int b, int H, int W) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int Ho = H / 2, Wo = W / 2;
-    const long total = (long)b * Ho * Wo * C;
-    if (i >= total) return;
-    const int c = i % C;
-    const long q = i / C;
-    const int ox = q % Wo, oy = (q / Wo) % Ho, bi = q / ((long)Wo * Ho);
-    float best = 0.f;
-    int bidx = 0;
+// 2x2 max-pool of a channel slice, vectorised: block = 32 pooled pixels x 64 channels (thread = 8 channels of one pooled
+// pixel: four 16-byte loads, one 16-byte store of `out`, 8 argmax bytes); the transposed copy leaves through a shared-memory
+// tile so that its rows (one channel, 32 consecutive pooled pixels) are written as contiguous 64-byte runs
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const bf16* __restrict__ x, int xC, int c0, int C, bf16* __restrict__ out,
+                                                           bf16* __restrict__ outT, unsigned char* __restrict__ idx, int H, int W) {
+    __shared__ bf16 tile[64][40];   // [channel][pooled pixel] (+8 padding: 80-byte rows keep 16-byte alignment)
+    const int Ho = H / 2, Wo = W / 2, nk = Ho * Wo;
+    const int bi = blockIdx.z, cb = blockIdx.y * 64, k0 = blockIdx.x * 32;
+    const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    const int kk = k0 + pl;
+    if (kk < nk) {
+        const int oy = kk / Wo, ox = kk - oy * Wo;
+        float best[8];
+        int bidx[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int y = 2 * oy + (k >> 1), xx = 2 * ox + (k & 1);
-        const float v = b2f(x[(((long)bi * H + y) * W + xx) * xC + c0 + c]);
-        if (k == 0 || v > best) { best = v; bidx = k; }
+        for (int k = 0; k < 4; ++k) {
+            const int y = 2 * oy + (k >> 1), xx = 2 * ox + (k & 1);
+            float v[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long)bi * H + y) * W + xx) * xC + c0 + cb + cg * 8)), v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (k == 0 || v[e] > best[e]) { best[e] = v[e]; bidx[e] = k; }
+        }
+        const long o = ((long)bi * nk + kk) * C + cb + cg * 8;
+        const uint4 pk = pack8(best);
+        if (out) *reinterpret_cast<uint4*>(out + o) = pk;
+        uint2 ib;
+        ib.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+        ib.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+        *reinterpret_cast<uint2*>(idx + o) = ib;
+        const bf16* h = reinterpret_cast<const bf16*>(&pk);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tile[cg * 8 + e][pl] = h[e];
     }
-    const int nk = Ho * Wo, kk = oy * Wo + ox;
-    if (out) out[((long)bi * nk + kk) * C + c] = f2b(best);
-    if (outT) outT[((long)bi * C + c) * nk + kk] = f2b(best);
-    idx[i] = (unsigned char)bidx;
+    __syncthreads();
+    if (outT) {
+        // thread = (channel, quarter of the 32 pixels): one 16-byte store
+        const int c = threadIdx.x >> 2, q = threadIdx.x & 3;
+        if (k0 + q * 8 < nk)
+            *reinterpret_cast<uint4*>(outT + ((long)bi * C + cb + c) * nk + k0 + q * 8) = *reinterpret_cast<const uint4*>(&tile[c][q * 8]);
+    }
 }
 void k_maxpool2_fwd(const bf16* x, int xC, int c0, int C, bf16* out, bf16* outT, unsigned char* idx, int b,
                     int H, int W, cudaStream_t st) {
-    const long total = (long)b * (H / 2) * (W / 2) * C;
-    maxpool2_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, xC, c0, C, out, outT, idx, b, H, W); count_launch();
+    // C % 64 == 0, (H/2 * W/2) % 8 == 0 (the attention shapes: 64 / 256 channels, >= 128 pooled pixels)
+    const int nk = (H / 2) * (W / 2);
+    maxpool2_fwd_kernel<<<dim3(cdiv(nk, 32), C / 64, b), 256, 0, st>>>(x, xC, c0, C, out, outT, idx, H, W); count_launch();
 }
 
+// thread = 8 channels of one pooled pixel: routes the gradient to the argmax position, zeros to the other three
 __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ d_out, const unsigned char* __restrict__ idx,
-                                    bf16* dx, int xC, int c0, int C, int b, int H, int W) {
+                                    bf16* __restrict__ dx, int xC, int c0, int C, int b, int H, int W) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int Ho = H / 2, Wo = W / 2;
-    const long total = (long)b * Ho * Wo * C;
+    const int Ho = H / 2, Wo = W / 2, CG = C / 8;
+    const long total = (long)b * Ho * Wo * CG;
     if (i >= total) return;
-    const int c = i % C;
-    const long q = i / C;
+    const int cg = i % CG;
+    const long q = i / CG;
     const int ox = q % Wo, oy = (q / Wo) % Ho, bi = q / ((long)Wo * Ho);
-    const bf16 g = d_out[i];
-    const int bidx = idx[i];
-    const bf16 zero = f2b(0.f);
+    const long o = q * C + cg * 8;
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(d_out + o));
+    const uint2 ib = __ldg(reinterpret_cast<const uint2*>(idx + o));
+    const unsigned short* gh = reinterpret_cast<const unsigned short*>(&g);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int y = 2 * oy + (k >> 1), xx = 2 * ox + (k & 1);
-        dx[(((long)bi * H + y) * W + xx) * xC + c0 + c] = (k == bidx) ? g : zero;
+        unsigned short r[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int id = ((e < 4 ? ib.x : ib.y) >> ((e & 3) * 8)) & 0xFF;
+            r[e] = (id == k) ? gh[e] : (unsigned short)0;
+        }
+        *reinterpret_cast<uint4*>(dx + (((long)bi * H + y) * W + xx) * xC + c0 + cg * 8) = *reinterpret_cast<const uint4*>(r);
     }
 }
 void k_maxpool2_bwd(const bf16* d_out, const unsigned char* idx, bf16* dx, int xC, int c0, int C, int b, int H,
                     int W, cudaStream_t st) {
-    const long total = (long)b * (H / 2) * (W / 2) * C;
+    const long total = (long)b * (H / 2) * (W / 2) * (C / 8);
     maxpool2_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(d_out, idx, dx, xC, c0, C, b, H, W); count_launch();
 }
 
@@ -737,10 +766,12 @@ void k_maxpool_bwd(const bf16* dout, const unsigned char* idx, const bf16* x, co
     maxpool_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(dout, idx, x, addin, dx, b, H, W, C, Ho, Wo, k, s); count_launch();
 }
 
-// one warp per feature pixel; block = 8 warps; one atomic per block for the loss
-__global__ void lpips_dist_kernel(const bf16* __restrict__ f, const float* __restrict__ t,
+// one warp per feature pixel, block = 8 warps; a lane keeps its <= 16 channels of the pixel (features, target, lin
+// weights) in registers, so HBM is read ONCE; block k of sample bi writes its part of the loss to slot k
+__global__ void __launch_bounds__(256) lpips_dist_kernel(const bf16* __restrict__ f, const float* __restrict__ t,
                                   const float* __restrict__ lin, const float* __restrict__ wadj, float* __restrict__ lossp,
                                   int lp_stride, bf16* __restrict__ g, int HW, int C, float gscale) {
+    constexpr int NC = 16;   // channels per lane: C <= 512 (alex: 64..384, vgg16: 64..512)
     __shared__ float part[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bi = blockIdx.y;
@@ -749,21 +780,26 @@ __global__ void lpips_dist_kernel(const bf16* __restrict__ f, const float* __res
     if (p < HW) {
         const bf16* fp = f + ((long)bi * HW + p) * C;
         const float* tp = t + (long)p * C;
+        float v[NC], tv[NC], lv[NC];
         float ss = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float v = b2f(fp[c]);
-            ss = fmaf(v, v, ss);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            const bool in = c < C;
+            v[i] = in ? b2f(fp[c]) : 0.f;
+            tv[i] = in ? __ldg(tp + c) : 0.f;
+            lv[i] = in ? __ldg(lin + c) : 0.f;
+            ss = fmaf(v[i], v[i], ss);
         }
         ss = warp_sum(ss);
         const float r = sqrtf(ss);
         const float inv = 1.f / (r + 1e-10f);
         float d = 0.f, q = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float v = b2f(fp[c]);
-            const float diff = v * inv - tp[c];
-            const float l = lin[c];
-            d = fmaf(l * diff, diff, d);
-            q = fmaf(2.f * l * diff, v, q);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const float diff = v[i] * inv - tv[i];
+            d = fmaf(lv[i] * diff, diff, d);
+            q = fmaf(2.f * lv[i] * diff, v[i], q);
         }
         d = warp_sum(d);
         q = warp_sum(q);
@@ -772,12 +808,15 @@ __global__ void lpips_dist_kernel(const bf16* __restrict__ f, const float* __res
         if (g) {
             bf16* gp = g + ((long)bi * HW + p) * C;
             const float k2 = r > 0.f ? q * inv * inv / r : 0.f;
-            for (int c = lane; c < C; c += 32) {
-                const float v = b2f(fp[c]);
-                const float diff = v * inv - tp[c];
-                const float e = 2.f * lin[c] * diff;
-                const float df = e * inv - k2 * v;
-                gp[c] = f2b(v > 0.f ? wv * gscale * df : 0.f);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const int c = lane + 32 * i;
+                if (c < C) {
+                    const float diff = v[i] * inv - tv[i];
+                    const float e = 2.f * lv[i] * diff;
+                    const float df = e * inv - k2 * v[i];
+                    gp[c] = f2b(v[i] > 0.f ? wv * gscale * df : 0.f);
+                }
             }
         }
     }
@@ -906,44 +945,68 @@ void k_weight_sum(const float* weight, const float* mask, float* wsum, float* to
     weight_sum_kernel<<<1, 1024, 0, st>>>(weight, mask, wsum, total, HW); count_launch();
 }
 
-__global__ void l1_loss_kernel(const float* __restrict__ img, const float* __restrict__ target,
+// block = 4096 consecutive elements of one sample (16 per thread as four float4); its part of the loss goes to slot
+// blockIdx.x of the sample (no atomics)
+constexpr int kL1PerBlock = 4096;
+__global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ img, const float* __restrict__ target,
                                const float* __restrict__ weight, const float* __restrict__ mask,
                                const float* __restrict__ total, float* __restrict__ lossp, int lp_stride,
                                float* __restrict__ dimg, int HW3, int l2) {
     __shared__ float part[8];
     const int bi = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const float inv_total = 1.f / total[0];
+    const float* im = img + (long)bi * HW3;
+    float* dg = dimg ? dimg + (long)bi * HW3 : nullptr;
     float v = 0.f;
-    if (i < HW3) {
-        float wv = weight ? weight[i] : 1.f;
-        if (mask) wv *= mask[i];
-        wv *= inv_total;
-        const float d = target[i] - img[(long)bi * HW3 + i];
-        float gi;
-        if (l2) {
-            v = d * d * wv;
-            gi = -2.f * d * wv;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = blockIdx.x * kL1PerBlock + (q * 256 + threadIdx.x) * 4;
+        if (((HW3 & 3) == 0) && i + 3 < HW3) {   // (odd-sized images: rows of later samples are not 16-byte aligned)
+            const float4 o4 = __ldg(reinterpret_cast<const float4*>(im + i));
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(target + i));
+            float4 w4 = weight ? __ldg(reinterpret_cast<const float4*>(weight + i)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            if (mask) {
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mask + i));
+                w4.x *= m4.x; w4.y *= m4.y; w4.z *= m4.z; w4.w *= m4.w;
+            }
+            const float o[4] = {o4.x, o4.y, o4.z, o4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+            const float ww[4] = {w4.x * inv_total, w4.y * inv_total, w4.z * inv_total, w4.w * inv_total};
+            float gi[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float d = tt[e] - o[e];
+                if (l2) { v += d * d * ww[e]; gi[e] = -2.f * d * ww[e]; }
+                else { v += fabsf(d) * ww[e]; gi[e] = d > 0.f ? -ww[e] : (d < 0.f ? ww[e] : 0.f); }
+            }
+            if (dg) *reinterpret_cast<float4*>(dg + i) = make_float4(gi[0], gi[1], gi[2], gi[3]);
         } else {
-            v = fabsf(d) * wv;
-            gi = d > 0.f ? -wv : (d < 0.f ? wv : 0.f);
+            for (int e = 0; e < 4 && i + e < HW3; ++e) {   // ragged tail (HW3 % 4 != 0)
+                float wv = weight ? weight[i + e] : 1.f;
+                if (mask) wv *= mask[i + e];
+                wv *= inv_total;
+                const float d = target[i + e] - im[i + e];
+                float gi;
+                if (l2) { v += d * d * wv; gi = -2.f * d * wv; }
+                else { v += fabsf(d) * wv; gi = d > 0.f ? -wv : (d < 0.f ? wv : 0.f); }
+                if (dg) dg[i + e] = gi;
+            }
         }
-        if (dimg) dimg[(long)bi * HW3 + i] = gi;
     }
     v = warp_sum(v);
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x == 0) {
         float s = 0.f;
-        for (int k = 0; k < (blockDim.x >> 5); ++k) s += part[k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += part[k];
         lossp[(long)bi * lp_stride + blockIdx.x] = s;
     }
 }
-int k_l1_loss_slots(int HW3) { return cdiv(HW3, 256); }
+int k_l1_loss_slots(int HW3) { return cdiv(HW3, kL1PerBlock); }
 void k_l1_loss(const float* img, const float* target, const float* weight, const float* mask, const float* total,
                float* lossp, int lp_stride, float* dimg, int b, int HW3, int HW, int l2, cudaStream_t st) {
     (void)HW;
-    dim3 grid(cdiv(HW3, 256), b);
+    dim3 grid(cdiv(HW3, kL1PerBlock), b);
     l1_loss_kernel<<<grid, 256, 0, st>>>(img, target, weight, mask, total, lossp, lp_stride, dimg, HW3, l2); count_launch();
 }
 
