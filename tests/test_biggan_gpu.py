@@ -72,9 +72,11 @@ def test_generator_forward_backward(tiny):
     print("native: img rel %.4f max %.4f dz rel %.3f cos %.4f dc rel %.3f cos %.4f | autocast-bf16 oracle: img %.4f dz %.3f dc %.3f"
           % (rel(img, ref), (img - ref).abs().max().item(), rel(dz, gz), cos(dz, gz), rel(dc, gc), cos(dc, gc),
              ac_img, ac_dz, ac_dc))
-    assert rel(img, ref) < max(1.25 * ac_img, 1e-2) and rel(img, ref) < 5e-2
-    assert rel(dz, gz) < max(1.25 * ac_dz, 5e-2) and rel(dc, gc) < max(1.25 * ac_dc, 5e-2)
-    assert cos(dz, gz) > 0.9 and cos(dc, gc) > 0.9
+    # measured (B200, fp16 operands): img rel 2.6e-3, dz / dc rel 0.125 / 0.120, cos 0.9923 / 0.9929; the bf16-autocast oracle sits
+    # at 3.3e-2 / 0.45 / 0.44. Bounds = 2x measured, and always well inside what autocast gives.
+    assert rel(img, ref) < 6e-3 and rel(img, ref) < 0.5 * ac_img
+    assert rel(dz, gz) < 0.25 and rel(dc, gc) < 0.25 and rel(dz, gz) < 0.75 * ac_dz and rel(dc, gc) < 0.75 * ac_dc
+    assert cos(dz, gz) > 0.985 and cos(dc, gc) > 0.985
 
 
 @pytest.mark.parametrize("net", ["alex", "vgg"])

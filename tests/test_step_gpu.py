@@ -89,7 +89,7 @@ def test_replay_step_parity(world):
         cz = torch.nn.functional.cosine_similarity(dz.flatten(), zz.grad.flatten(), dim=0).item()
         cc_ = torch.nn.functional.cosine_similarity(dc.flatten(), cc.grad.flatten(), dim=0).item()
         print("step %d: loss err %.2e cos dz %.4f cos dc %.4f" % (k, err, cz, cc_))
-        assert err < 3e-3 and cz > 0.9 and cc_ > 0.9
+        assert err < 1e-4 and cz > 0.987 and cc_ > 0.987   # measured: 2.9e-5, 0.9935, 0.9939 — bounds = 2x the deviation
         oc.step(orc, variables, ref_loss, optimize=True, max_batch_size=3)  # advance the ORACLE trajectory
 
 
@@ -106,11 +106,12 @@ def test_free_running_gradient_optimizer(world):
     assert _native_pair(model, v_nat, loss)
     lr, ln = np.array(l_ref[0][1]["loss"]), np.array(l_nat[0][1]["loss"])
     print("final loss oracle", lr, "native", ln)
-    assert np.abs(lr - ln).max() < 2e-2
+    assert np.abs(lr - ln).max() < 4e-3   # measured 1.5e-3
     zr, zn = torch.stack(v_ref.input.z.data), torch.stack(v_nat.input.z.data)
     # Adam's first updates are sign-like (|dz| = lr = 0.05 per step whatever the gradient's size), so
     # bf16-level gradient noise on near-zero components moves a free-running z by O(lr) there; the
     # teacher-forced test above is the parity statement, this one bounds the drift.
+    print("free-running mean |dz| drift %.4f" % (zr - zn).abs().mean().item())
     assert (zr - zn).abs().mean().item() < 0.08
     assert outs[0].shape[0] == 3
 
@@ -129,6 +130,7 @@ def test_autograd_path_uses_native_functions(world):
     o2 = orc(z=z2, c=c2)
     l2 = ref_loss(o2, target[None].expand(3, -1, -1, -1), weight[None].expand(3, -1, -1, -1))
     l2.mean().backward()
-    assert torch.allclose(l, l2, rtol=5e-3, atol=2e-3)
+    print("autograd path: max |dloss| %.2e" % (l - l2).abs().max().item())
+    assert torch.allclose(l, l2, rtol=0, atol=2e-4)
     cs = torch.nn.functional.cosine_similarity(z.grad.flatten(), z2.grad.flatten(), dim=0).item()
-    assert cs > 0.9
+    assert cs > 0.987
