@@ -384,36 +384,52 @@ void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int a
     pool_bnrelu_bwd_kernel<<<grid, block, 0, st>>>(g_up, y_lo, a, aff_stride, statp, (int)grid.x, dx, H, W, C); count_launch();
 }
 
-// BN-gradient sums: S0/S1[n][off + c] = sum over the layer's partial slots, in slot order (8 interleaved running sums
-// per (n, c), then a fixed tree) — the same order whatever the launch geometry of the producers was
-__global__ void __launch_bounds__(256) stat_reduce_kernel(const StatSeg* __restrict__ segs, float* __restrict__ S0,
-                                                          float* __restrict__ S1, int stride, int stride1) {
-    __shared__ float r0[8][33], r1[8][33];
+// BN-gradient sums: S0/S1[n][off + c] = sum over the layer's partial slots in a fixed order — 32 interleaved slices of the
+// slot sequence per (n, c), four independent running sums per slice (loads in flight), then a fixed tree — the same order
+// whatever the launch geometry of the producers was
+__global__ void __launch_bounds__(1024) stat_reduce_kernel(const StatSeg* __restrict__ segs, float* __restrict__ S0,
+                                                           float* __restrict__ S1, int stride, int stride1) {
+    __shared__ float r0[32][33], r1[32][33];
     const StatSeg sg = segs[blockIdx.x];
     const int n = blockIdx.y, lane = threadIdx.x, sl = threadIdx.y;
     const float* base = sg.p + (long)n * sg.pstride * 2 * sg.C + sg.c0 + lane;
-    float a0 = 0.f, a1 = 0.f;
-    for (int q = sl; q < sg.parts; q += 8) {
-        a0 += __ldg(base + (long)q * 2 * sg.C);
-        a1 += __ldg(base + (long)q * 2 * sg.C + sg.C);
+    const long step = 2L * sg.C;
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+    int q = sl;
+    for (; q + 96 < sg.parts; q += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a0[u] += __ldg(base + (q + 32 * u) * step);
+            a1[u] += __ldg(base + (q + 32 * u) * step + sg.C);
+        }
     }
-    r0[sl][lane] = a0;
-    r1[sl][lane] = a1;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        if (q + 32 * u < sg.parts) {
+            a0[u] += __ldg(base + (q + 32 * u) * step);
+            a1[u] += __ldg(base + (q + 32 * u) * step + sg.C);
+        }
+    }
+    r0[sl][lane] = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+    r1[sl][lane] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
     __syncthreads();
+    // fixed tree over the 32 slices
+    for (int h = 16; h > 0; h >>= 1) {
+        if (sl < h) { r0[sl][lane] += r0[sl + h][lane]; r1[sl][lane] += r1[sl + h][lane]; }
+        __syncthreads();
+    }
     if (sl == 0) {
-        a0 = ((r0[0][lane] + r0[1][lane]) + (r0[2][lane] + r0[3][lane])) + ((r0[4][lane] + r0[5][lane]) + (r0[6][lane] + r0[7][lane]));
-        a1 = ((r1[0][lane] + r1[1][lane]) + (r1[2][lane] + r1[3][lane])) + ((r1[4][lane] + r1[5][lane]) + (r1[6][lane] + r1[7][lane]));
-        S0[(long)n * stride + sg.off + sg.c0 + lane] = a0;
-        S1[(long)n * stride1 + sg.off1 + sg.c0 + lane] = a1;
+        S0[(long)n * stride + sg.off + sg.c0 + lane] = r0[0][lane];
+        S1[(long)n * stride1 + sg.off1 + sg.c0 + lane] = r1[0][lane];
     }
 }
 void k_stat_reduce(const StatSeg* segs, int nsegs, float* S0, float* S1, int stride, int b, cudaStream_t st) {
     if (nsegs <= 0) return;
-    stat_reduce_kernel<<<dim3(nsegs, b), dim3(32, 8), 0, st>>>(segs, S0, S1, stride, stride); count_launch();
+    stat_reduce_kernel<<<dim3(nsegs, b), dim3(32, 32), 0, st>>>(segs, S0, S1, stride, stride); count_launch();
 }
 void k_stat_reduce2(const StatSeg* segs, int nsegs, float* S0, int stride0, float* S1, int stride1, int b, cudaStream_t st) {
     if (nsegs <= 0) return;
-    stat_reduce_kernel<<<dim3(nsegs, b), dim3(32, 8), 0, st>>>(segs, S0, S1, stride0, stride1); count_launch();
+    stat_reduce_kernel<<<dim3(nsegs, b), dim3(32, 32), 0, st>>>(segs, S0, S1, stride0, stride1); count_launch();
 }
 
 __global__ void pool2x2_sum_kernel(const bf16* __restrict__ in, int inC, bf16* __restrict__ out, int b, int H, int W, int C) {

@@ -355,6 +355,10 @@ SG2Plan* SG2::plan(int b) {
 // mapping network: PixelNorm + n_mlp EqualLinear(fused_lrelu); h[0..n_mlp] are [b, sdim] buffers, h[n_mlp] = w
 int SG2::run_mapping(int b, const float* z, float* zbuf, float* const* h, cudaStream_t st) {
     P2L_CUDA_CHECK(cudaMemcpyAsync(zbuf, z, (size_t)b * sdim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (k_sg_mapping_fusable(b, sdim, n_mlp)) {   // one cluster launch for the whole network
+        k_sg_mapping_fwd(zbuf, map_WT.data(), map_b.data(), map_scale, h, b, n_mlp, st);
+        return 0;
+    }
     k_pixelnorm_fwd(zbuf, h[0], b, sdim, st);
     for (int k = 0; k < n_mlp; ++k)
         k_fc_fwd(h[k], sdim, map_WT[k], map_b[k], map_scale, h[k + 1], sdim, b, sdim, sdim, 1, 0, st);
@@ -465,10 +469,18 @@ int SG2::synth_bwd(SG2Plan& P, int b, const float* dimg, float* const* dnoise, f
     {   // last layer: its output feeds the last ToRGB only
         const int l = nL - 1;
         const Conv& c = convs[l];
-        rgb_branch(l);
-        if (dnoise && dnoise[l]) k_sg_noise_bwd(P.dxrgb, P.L[l].x, c.noise_w, dnoise[l], b, c.Hout, c.Hout, c.Cout, out_scale, row_scale, st);
-        k_sg_post_bwd_x(P.dxrgb, P.L[l].x, P.dm_all + c.dm_off, DM, P.noise_ptrs[l], c.noise_w, c.bias, P.G[l & 1],
-                        P.ddm_all + c.dm_off, P.scratch, b, c.Hout, c.Hout, c.Cout, st);
+        if (dnoise && dnoise[l]) {   // the noise gradient reads the gradient wrt x: keep it materialised
+            rgb_branch(l);
+            k_sg_noise_bwd(P.dxrgb, P.L[l].x, c.noise_w, dnoise[l], b, c.Hout, c.Hout, c.Cout, out_scale, row_scale, st);
+            k_sg_post_bwd_x(P.dxrgb, P.L[l].x, P.dm_all + c.dm_off, DM, P.noise_ptrs[l], c.noise_w, c.bias, P.G[l & 1],
+                            P.ddm_all + c.dm_off, P.scratch, b, c.Hout, c.Hout, c.Cout, st);
+        } else {                     // one pass over x: ToRGB backward + the activation backward of the layer
+            const int t = l / 2;
+            const Rgb& r = rgbs[t];
+            k_sg_torgb_post_bwd(P.drgb[t], P.L[l].x, P.weff[t], P.dweff[t], P.dm_all + c.dm_off, DM, P.noise_ptrs[l], c.noise_w, c.bias,
+                                P.G[l & 1], P.ddm_all + c.dm_off, P.scratch, b, r.H, r.H, r.Cin, st);
+            k_sg_weff_bwd(P.dweff[t], r.Wr, r.scale, P.ds_all + r.s_off, S, b, r.Cin, st);
+        }
     }
     for (int l = nL - 1; l >= 1; --l) {
         const Conv& pv = convs[l - 1];
@@ -508,6 +520,10 @@ int SG2::backward(int b, const float* dimg, float* dz, cudaStream_t st, float sc
     if (synth_bwd(P, b, dimg, nullptr, 1.f, nullptr, st)) return -1;
     // styles -> w -> mapping network -> z
     k_fc_bwd(P.ds_all, S, nullptr, 0, aff, 1.f / std::sqrt((float)sdim), P.dw, sdim, b, sdim, S, 0, 0, st, b <= 24 ? P.scratch : nullptr);
+    if (k_sg_mapping_fusable(b, sdim, n_mlp)) {
+        k_sg_mapping_bwd(P.dw, map_W.data(), map_scale, P.h, P.z, dz, scale / grad_scale(), row_scale, b, n_mlp, st);
+        return 0;
+    }
     float *g = P.dw, *gn = P.g0;
     for (int k = n_mlp - 1; k >= 0; --k) {
         k_fc_bwd(g, sdim, P.h[k + 1], sdim, map_W[k], map_scale, gn, sdim, b, sdim, sdim, 1, 0, st);

@@ -6,9 +6,12 @@
 // scale before and an output-channel scale after the convolution.
 #include "sg2_kernels.h"
 
+#include <cooperative_groups.h>
+
 #include "conv_gemm.h"
 
 namespace p2l {
+namespace cg = cooperative_groups;
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 __device__ __forceinline__ float b2f(bf16 x) { return a2f(x); }
@@ -211,6 +214,154 @@ void k_fc_bwd(const float* dy, int lddy, const float* y, int ldy, const float* W
     sg_gemm(a, (act == 1 && y) ? SG_PRO_ACTGRAD : SG_PRO_ID, accumulate ? SG_EPI_ACCUM : SG_EPI_STORE, st);
 }
 
+// ----------------------------------------------------------------------------- mapping network in ONE launch
+// PixelNorm + n_mlp x EqualLinear(512, 512, fused_lrelu) (forward), or the gradient back through them (backward), for
+// b <= NB samples: a cluster of 8 CTAs, CTA r owns output columns [64 r, 64 r + 64) of every layer. The layer input
+// [NB][512] sits in the shared memory of EVERY CTA; a layer = each warp contracts its 64-wide K slice against the CTA's
+// 64 columns of the weight matrix (256-byte coalesced rows, float2 per lane), the eight slices meet in shared memory in
+// warp order, and the finished 64 columns are written into the NEXT input buffer of all eight CTAs through distributed
+// shared memory; one cluster barrier per layer. 16 launches of ~19 us (latency-bound at 16 blocks) become two.
+struct SgMap {
+    const float* in;          // forward: z [b][512]; backward: dw [b][512]
+    const float* M[8];        // forward: W^T of layer k ([in][out]); backward: W of layer k ([out][in])
+    const float* bias[8];     // forward
+    float* h[9];              // forward: written (h[0] = pixelnorm(z) .. h[n] = w); backward: read (saved activations)
+    const float* z;           // backward: the raw latent (PixelNorm backward)
+    float* out;               // backward: dz [b][512]
+    const float* row_scale;   // backward: optional per-sample factor
+    float wscale, scale;
+    int b, n;
+};
+constexpr int kMapDim = 512, kMapCtas = 8, kMapCols = kMapDim / kMapCtas;
+template <int NB, bool BWD>
+__global__ void __cluster_dims__(kMapCtas, 1, 1) __launch_bounds__(256) sg_mapping_kernel(const SgMap a) {
+    extern __shared__ __align__(16) float map_sm[];
+    float(*xs)[NB][kMapDim] = reinterpret_cast<float(*)[NB][kMapDim]>(map_sm);                       // [2][NB][512]
+    float(*red)[NB][kMapCols] = reinterpret_cast<float(*)[NB][kMapCols]>(map_sm + 2 * NB * kMapDim);   // [8][NB][64]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- the first input, computed by every CTA for itself
+    for (int bi = warp; bi < NB; bi += 8) {
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = bi < a.b ? a.in[(long)bi * kMapDim + q * 32 + lane] : 0.f;
+        if constexpr (!BWD) {
+            float ss = 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) ss += v[q] * v[q];
+            ss = warp_sum(ss);
+            const float r = rsqrtf(ss / kMapDim + 1e-8f);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                v[q] *= r;
+                if (rank == 0 && bi < a.b) a.h[0][(long)bi * kMapDim + q * 32 + lane] = v[q];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (bi < a.b) v[q] *= (a.h[a.n][(long)bi * kMapDim + q * 32 + lane] > 0.f ? 1.f : 0.2f) * kSqrt2;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) xs[0][bi][q * 32 + lane] = v[q];
+    }
+    cluster.sync();   // every CTA of the cluster runs (remote shared memory may be written from here on) + local visibility
+    for (int L = 0; L < a.n; ++L) {
+        const int k = BWD ? a.n - 1 - L : L, cur = L & 1;
+        float acc[NB][2];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) acc[i][0] = acc[i][1] = 0.f;
+        const float* mp = a.M[k] + (long)(warp * 64) * kMapDim + rank * kMapCols + lane * 2;
+#pragma unroll 2
+        for (int u = 0; u < 64; u += 4) {
+            float2 w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[q] = __ldg(reinterpret_cast<const float2*>(mp + (long)(u + q) * kMapDim));
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const float4 x4 = *reinterpret_cast<const float4*>(&xs[cur][i][warp * 64 + u]);
+                acc[i][0] = fmaf(x4.x, w[0].x, acc[i][0]); acc[i][1] = fmaf(x4.x, w[0].y, acc[i][1]);
+                acc[i][0] = fmaf(x4.y, w[1].x, acc[i][0]); acc[i][1] = fmaf(x4.y, w[1].y, acc[i][1]);
+                acc[i][0] = fmaf(x4.z, w[2].x, acc[i][0]); acc[i][1] = fmaf(x4.z, w[2].y, acc[i][1]);
+                acc[i][0] = fmaf(x4.w, w[3].x, acc[i][0]); acc[i][1] = fmaf(x4.w, w[3].y, acc[i][1]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) *reinterpret_cast<float2*>(&red[warp][i][lane * 2]) = make_float2(acc[i][0], acc[i][1]);
+        __syncthreads();
+        for (int t = threadIdx.x; t < NB * kMapCols; t += 256) {
+            const int bi = t / kMapCols, jj = t % kMapCols, jo = rank * kMapCols + jj;
+            float v = ((red[0][bi][jj] + red[1][bi][jj]) + (red[2][bi][jj] + red[3][bi][jj])) +
+                      ((red[4][bi][jj] + red[5][bi][jj]) + (red[6][bi][jj] + red[7][bi][jj]));
+            v *= a.wscale;
+            if constexpr (!BWD) {
+                v += a.bias[k][jo];
+                v = (v > 0.f ? v : 0.2f * v) * kSqrt2;
+                if (bi < a.b) a.h[k + 1][(long)bi * kMapDim + jo] = v;
+            } else {
+                if (bi >= a.b) v = 0.f;
+                else if (k > 0) v *= (a.h[k][(long)bi * kMapDim + jo] > 0.f ? 1.f : 0.2f) * kSqrt2;
+            }
+            float* dst = &xs[cur ^ 1][bi][jo];
+#pragma unroll
+            for (int r = 0; r < kMapCtas; ++r) *cluster.map_shared_rank(dst, r) = v;
+        }
+        cluster.sync();   // the next input is complete everywhere; nobody still reads the current one or `red`
+    }
+    if constexpr (BWD) {
+        if (rank != 0) return;   // no remote access after the last barrier: leaving is safe
+        const float(*g)[kMapDim] = xs[a.n & 1];
+        for (int bi = warp; bi < a.b; bi += 8) {
+            float x[16], ss = 0.f, dot = 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                x[q] = a.z[(long)bi * kMapDim + q * 32 + lane];
+                ss += x[q] * x[q];
+                dot += x[q] * g[bi][q * 32 + lane];
+            }
+            ss = warp_sum(ss);
+            dot = warp_sum(dot);
+            const float r = rsqrtf(ss / kMapDim + 1e-8f);
+            const float sc = a.scale * (a.row_scale ? a.row_scale[bi] : 1.f);
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                a.out[(long)bi * kMapDim + q * 32 + lane] = sc * (r * g[bi][q * 32 + lane] - x[q] * dot * r * r * r / kMapDim);
+        }
+    }
+}
+template <int NB, bool BWD>
+static void launch_mapping(const SgMap& a, cudaStream_t st) {
+    constexpr size_t smem = (size_t)(2 * NB * kMapDim + 8 * NB * kMapCols) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(sg_mapping_kernel<NB, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    sg_mapping_kernel<NB, BWD><<<kMapCtas, 256, smem, st>>>(a);
+    count_launch();
+}
+bool k_sg_mapping_fusable(int b, int sdim, int n_mlp) { return sdim == kMapDim && b <= 24 && n_mlp >= 1 && n_mlp <= 8; }
+void k_sg_mapping_fwd(const float* z, const float* const* WT, const float* const* bias, float wscale, float* const* h, int b, int n_mlp,
+                      cudaStream_t st) {
+    SgMap a{};
+    a.in = z; a.wscale = wscale; a.b = b; a.n = n_mlp;
+    for (int k = 0; k < n_mlp; ++k) { a.M[k] = WT[k]; a.bias[k] = bias[k]; }
+    for (int k = 0; k <= n_mlp; ++k) a.h[k] = h[k];
+    if (b <= 8) launch_mapping<8, false>(a, st);
+    else if (b <= 16) launch_mapping<16, false>(a, st);
+    else launch_mapping<24, false>(a, st);
+}
+void k_sg_mapping_bwd(const float* dw, const float* const* W, float wscale, float* const* h, const float* z, float* dz, float scale,
+                      const float* row_scale, int b, int n_mlp, cudaStream_t st) {
+    SgMap a{};
+    a.in = dw; a.wscale = wscale; a.b = b; a.n = n_mlp; a.z = z; a.out = dz; a.scale = scale; a.row_scale = row_scale;
+    for (int k = 0; k < n_mlp; ++k) a.M[k] = W[k];
+    for (int k = 0; k <= n_mlp; ++k) a.h[k] = h[k];
+    if (b <= 8) launch_mapping<8, true>(a, st);
+    else if (b <= 16) launch_mapping<16, true>(a, st);
+    else launch_mapping<24, true>(a, st);
+}
+
 // PixelNorm: y = x * rsqrt(mean(x^2) + 1e-8); one warp per sample
 __global__ void pixelnorm_fwd_kernel(const float* x, float* y, int n) {
     const int bi = blockIdx.x, lane = threadIdx.x;
@@ -310,17 +461,34 @@ __global__ void modulate_bwd_kernel(const bf16* __restrict__ dA, const bf16* __r
 }
 // dst[bi][j] += sum over the `parts` pixel blocks of part[bi][p][j], in block order: the reproducible second stage of the
 // per-(sample, channel) reductions below
-__global__ void partial_reduce_add_kernel(const float* __restrict__ part, int parts, int n, float* __restrict__ dst, int ld) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, bi = blockIdx.y;
-    if (j >= n) return;
-    float t = 0.f;
-    for (int q = 0; q < parts; ++q) t += part[((long)bi * parts + q) * n + j];
-    dst[(long)bi * ld + j] += t;
+__global__ void __launch_bounds__(512) partial_reduce_add_kernel(const float* __restrict__ part, int parts, int n,
+                                                                 float* __restrict__ dst, int ld) {
+    __shared__ float r[16][33];
+    const int j = blockIdx.x * 32 + threadIdx.x, bi = blockIdx.y, sl = threadIdx.y;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    if (j < n) {
+        const float* base = part + (long)bi * parts * n + j;
+        int q = sl;
+        for (; q + 48 < parts; q += 64) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] += __ldg(base + (long)(q + 16 * u) * n);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+            if (q + 16 * u < parts) a[u] += __ldg(base + (long)(q + 16 * u) * n);
+    }
+    r[sl][threadIdx.x] = (a[0] + a[1]) + (a[2] + a[3]);
+    __syncthreads();
+    for (int h = 8; h > 0; h >>= 1) {
+        if (sl < h) r[sl][threadIdx.x] += r[sl + h][threadIdx.x];
+        __syncthreads();
+    }
+    if (sl == 0 && j < n) dst[(long)bi * ld + j] += r[0][threadIdx.x];
 }
 static void partial_reduce_add(const float* part, int parts, int b, int n, float* dst, int ld, cudaStream_t st) {
-    partial_reduce_add_kernel<<<dim3(cdiv(n, 128), b), 128, 0, st>>>(part, parts, n, dst, ld); count_launch();
+    partial_reduce_add_kernel<<<dim3(cdiv(n, 32), b), dim3(32, 16), 0, st>>>(part, parts, n, dst, ld); count_launch();
 }
-long k_sg_scratch_floats(int b, int H, int W, int C) { return (long)b * cdiv((long)H * W, 256) * C * 3; }
+long k_sg_scratch_floats(int b, int H, int W, int C) { return (long)b * cdiv((long)H * W, 256) * C * 4; }
 void k_sg_modulate_bwd(const bf16* dA, const bf16* x, long x_bstride, const float* s, int lds, bf16* dx, float* ds, int ldds,
                        float* scratch, int b, int H, int W, int C, cudaStream_t st) {
     dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
@@ -390,28 +558,99 @@ __global__ void weff_kernel(const float* Wr, const float* s, int lds, float scal
 void k_sg_weff(const float* Wr, const float* s, int lds, float scale, float* weff, int b, int C, cudaStream_t st) {
     weff_kernel<<<cdiv((long)b * 3 * C, 256), 256, 0, st>>>(Wr, s, lds, scale, weff, b, C); count_launch();
 }
-// FIR x2 up-sampling of the previous rgb (upfirdn2d up=2, pad (2,1)): out[y] = sum_{t: (y+t) even} prev[(y+t-2)/2] k[t]
+// FIR x2 up-sampling of the previous rgb (upfirdn2d up=2, pad (2,1)): out[y] = sum_{t: (y+t) even} prev[(y+t-2)/2] k[t].
+// Per axis that is two taps: rows ia = floor((y-1)/2) and ia+1 with weights (1/4, 3/4) for even y, (3/4, 1/4) for odd y.
 __device__ __forceinline__ float up_gather(const float* __restrict__ prev, int h, int w, int y, int xx) {
+    const int ia = (y - 1) >> 1, ja = (xx - 1) >> 1;
+    const float wya = (y & 1) ? 0.75f : 0.25f, wxa = (xx & 1) ? 0.75f : 0.25f;
+    const float wyb = 1.f - wya, wxb = 1.f - wxa;
+    const bool ra = ia >= 0, rb = ia + 1 < h, ca = ja >= 0, cb = ja + 1 < w;
+    const float* r0 = prev + (long)ia * w + ja;
+    const float* r1 = r0 + w;
     float acc = 0.f;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        if ((y + t) & 1) continue;
-        const int i = (y + t - 2) / 2;
-        if (y + t - 2 < 0 || i >= h) continue;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            if ((xx + v) & 1) continue;
-            const int j = (xx + v - 2) / 2;
-            if (xx + v - 2 < 0 || j >= w) continue;
-            acc = fmaf(kFir[t] * kFir[v], prev[i * w + j], acc);
-        }
+    // same association as the 4 x 4 tap loop: per row, then rows in order
+    if (ra) {
+        if (ca) acc = fmaf(wya * wxa, __ldg(r0), acc);
+        if (cb) acc = fmaf(wya * wxb, __ldg(r0 + 1), acc);
+    }
+    if (rb) {
+        if (ca) acc = fmaf(wyb * wxa, __ldg(r1), acc);
+        if (cb) acc = fmaf(wyb * wxb, __ldg(r1 + 1), acc);
     }
     return acc;
 }
-// rgb[b,c,p] = sum_i weff[b,c,i] x[b,p,i] + bias[c] (+ upsampled previous rgb); thread per pixel: the pixel's C channels
-// are one contiguous run (16-byte loads), the three weight rows sit in shared memory (broadcast reads), stores are
-// coalesced along the pixels of a plane
-__global__ void __launch_bounds__(128) torgb_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ weff,
+// rgb[b,c,p] = sum_i weff[b,c,i] x[b,p,i] + bias[c] (+ upsampled previous rgb). block = 256 consecutive pixels of one image,
+// 32 per warp. A warp load covers 512 contiguous bytes of x (32/lpp pixels, lpp = min(32, C/8) lanes per pixel, 8 channels per
+// lane; C = 512 takes two loads per pixel), the lane's 3 x 8 weights sit in registers, the three sums are reduced over the lanes
+// of a pixel by shuffles and leave through shared memory so that the planar stores are coalesced.
+template <int NK>
+__global__ void __launch_bounds__(256) torgb_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ weff,
+                                                        const float* __restrict__ bias, const float* __restrict__ prev,
+                                                        float* __restrict__ rgb, int H, int W, int C, int tiles_per_block) {
+    __shared__ float res[3][256];
+    const int bi = blockIdx.y, HW = H * W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lpp = min(32, C >> 3), ppl = 32 / lpp;
+    const int sub = lane % lpp, cl = sub * 8;
+    float w[NK][3][8];
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float4* wp = reinterpret_cast<const float4*>(weff + ((long)bi * 3 + c) * C + k * 256 + cl);
+            const float4 lo = __ldg(wp), hi = __ldg(wp + 1);
+            w[k][c][0] = lo.x; w[k][c][1] = lo.y; w[k][c][2] = lo.z; w[k][c][3] = lo.w;
+            w[k][c][4] = hi.x; w[k][c][5] = hi.y; w[k][c][6] = hi.z; w[k][c][7] = hi.w;
+        }
+    const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
+    const bf16* xb = x + (long)bi * HW * C + cl;
+    for (int tile = 0; tile < tiles_per_block; ++tile) {
+        const int p0 = (blockIdx.x * tiles_per_block + tile) * 256;
+        if (p0 >= HW) break;
+        const int pw = p0 + warp * 32 + lane / lpp;
+#pragma unroll 4
+        for (int q = 0; q < 32; q += ppl) {
+            const int p = pw + q;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            if (p < HW) {
+#pragma unroll
+                for (int k = 0; k < NK; ++k) {
+                    float v[8];
+                    unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (long)p * C + k * 256)), v);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        a0 = fmaf(v[e], w[k][0][e], a0);
+                        a1 = fmaf(v[e], w[k][1][e], a1);
+                        a2 = fmaf(v[e], w[k][2][e], a2);
+                    }
+                }
+            }
+            for (int h = lpp >> 1; h > 0; h >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, h);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, h);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, h);
+            }
+            if (sub == 0 && p < HW) { res[0][p - p0] = a0; res[1][p - p0] = a1; res[2][p - p0] = a2; }
+        }
+        __syncthreads();
+        const int p = p0 + threadIdx.x;   // thread = pixel: one division for the three planes
+        if (p < HW) {
+            float v0 = res[0][threadIdx.x] + b0, v1 = res[1][threadIdx.x] + b1, v2 = res[2][threadIdx.x] + b2;
+            if (prev) {
+                const int y = p / W, xx = p - y * W, h2 = H >> 1, w2 = W >> 1;
+                const float* pp = prev + (long)bi * 3 * h2 * w2;
+                v0 += up_gather(pp, h2, w2, y, xx);
+                v1 += up_gather(pp + h2 * w2, h2, w2, y, xx);
+                v2 += up_gather(pp + 2 * h2 * w2, h2, w2, y, xx);
+            }
+            float* o = rgb + (long)bi * 3 * HW + p;
+            o[0] = v0; o[HW] = v1; o[2L * HW] = v2;
+        }
+        __syncthreads();
+    }
+}
+// any other channel count (multiple of 8): thread per pixel, the three weight rows in shared memory
+__global__ void __launch_bounds__(128) torgb_fwd_generic_kernel(const bf16* __restrict__ x, const float* __restrict__ weff,
                                                         const float* __restrict__ bias, const float* __restrict__ prev,
                                                         float* __restrict__ rgb, int H, int W, int C) {
     extern __shared__ float sw[];  // [3][C]
@@ -444,59 +683,122 @@ __global__ void __launch_bounds__(128) torgb_fwd_kernel(const bf16* __restrict__
 }
 void k_sg_torgb_fwd(const bf16* x, const float* weff, const float* bias, const float* prev, float* rgb, int b, int H, int W, int C,
                     cudaStream_t st) {
-    int gx = cdiv((long)H * W, 128);
-    if (gx > 1024) gx = 1024;
-    torgb_fwd_kernel<<<dim3(gx, b), 128, (size_t)3 * C * sizeof(float), st>>>(x, weff, bias, prev, rgb, H, W, C); count_launch();
+    // several 256-pixel tiles per block at the large resolutions: the per-lane weights are fetched once per block
+    const int tiles = cdiv((long)H * W, 256), tpb = tiles >= 1024 ? 4 : (tiles >= 256 ? 2 : 1);
+    const dim3 grid(cdiv(tiles, tpb), b);
+    if (C < 64 || C > 512 || (C & (C - 1))) {
+        int gx = cdiv((long)H * W, 128);
+        if (gx > 1024) gx = 1024;
+        torgb_fwd_generic_kernel<<<dim3(gx, b), 128, (size_t)3 * C * sizeof(float), st>>>(x, weff, bias, prev, rgb, H, W, C);
+    } else if (C <= 256) torgb_fwd_kernel<1><<<grid, 256, 0, st>>>(x, weff, bias, prev, rgb, H, W, C, tpb);
+    else torgb_fwd_kernel<2><<<grid, 256, 0, st>>>(x, weff, bias, prev, rgb, H, W, C, tpb);
+    count_launch();
 }
 // backward: dx[b,p,i] (+)= sum_c drgb[b,c,p] weff[b,c,i] ; dweff[b,c,i] += sum_p drgb[b,c,p] x[b,p,i]
-// block = 8 channel groups x 32 pixels
-__global__ void torgb_bwd_kernel(const float* __restrict__ drgb, const bf16* __restrict__ x, const float* __restrict__ weff,
-                                 bf16* __restrict__ dx, float* __restrict__ part, int H, int W, int C, int accumulate) {
-    __shared__ float red[3][32][65];
+// block = 8 channel groups x 32 pixels, 256 pixels per block (eight independent iterations per thread: loads in flight).
+// POST (the LAST layer, whose output feeds only its ToRGB): the activation / noise / bias / demodulation backward of
+// post_bwd_x_kernel runs on the gradient while it is still in registers — G = dm * g is stored instead of dx, and the
+// (ddm * dm) sums leave through a fourth plane of partial slots.
+template <bool POST>
+__global__ void __launch_bounds__(256, 3) torgb_bwd_kernel(const float* __restrict__ drgb, const bf16* __restrict__ x,
+                                                           const float* __restrict__ weff, bf16* __restrict__ dx, float* __restrict__ part,
+                                                           int H, int W, int C, int accumulate, const float* __restrict__ dm, int lddm,
+                                                           const float* __restrict__ noise, const float* __restrict__ nw,
+                                                           const float* __restrict__ bias, float* __restrict__ part_dm) {
+    __shared__ float red[POST ? 4 : 3][32][65];
+    __shared__ __align__(16) float coef[5][64];   // the block's 64 channels: three weight rows, dm, bias (registers go to the sums)
     const int cg = threadIdx.x, py = threadIdx.y;
     const int c = blockIdx.y * 64 + cg * 8;
     const int bi = blockIdx.z;
     const int HW = H * W;
-    float w0[8], w1[8], w2[8], a0[8], a1[8], a2[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        w0[e] = weff[((long)bi * 3 + 0) * C + c + e]; w1[e] = weff[((long)bi * 3 + 1) * C + c + e]; w2[e] = weff[((long)bi * 3 + 2) * C + c + e];
-        a0[e] = a1[e] = a2[e] = 0.f;
+    const int tid = py * 8 + cg;
+    if (tid < 192) coef[tid >> 6][tid & 63] = weff[((long)bi * 3 + (tid >> 6)) * C + blockIdx.y * 64 + (tid & 63)];
+    else if (POST) {
+        coef[3][tid & 63] = dm[(long)bi * lddm + blockIdx.y * 64 + (tid & 63)];
+        coef[4][tid & 63] = bias[blockIdx.y * 64 + (tid & 63)];
     }
-    for (int p = blockIdx.x * 256 + py; p < min(HW, (int)(blockIdx.x + 1) * 256); p += 32) {
-        const float g0 = drgb[((long)bi * 3 + 0) * HW + p], g1 = drgb[((long)bi * 3 + 1) * HW + p], g2 = drgb[((long)bi * 3 + 2) * HW + p];
+    __syncthreads();
+    float a0[8], a1[8], a2[8], a3[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a0[e] = a1[e] = a2[e] = a3[e] = 0.f;
+    const float nwv = (POST && noise) ? nw[0] : 0.f;
+    auto row8 = [&](int r, float (&v)[8]) {
+        const float4 lo = *reinterpret_cast<const float4*>(&coef[r][cg * 8]), hi = *reinterpret_cast<const float4*>(&coef[r][cg * 8 + 4]);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    };
+#pragma unroll(POST ? 1 : 4)
+    for (int it = 0; it < 8; ++it) {
+        const int p = blockIdx.x * 256 + it * 32 + py;
+        if (p >= HW) break;
+        const float g0 = __ldg(drgb + ((long)bi * 3 + 0) * HW + p), g1 = __ldg(drgb + ((long)bi * 3 + 1) * HW + p),
+                    g2 = __ldg(drgb + ((long)bi * 3 + 2) * HW + p);
         const long o = ((long)bi * HW + p) * C + c;
-        float xv[8], d[8];
+        float xv[8], d[8], w[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(x + o)), xv);
-        if (accumulate) unpack8(*reinterpret_cast<const uint4*>(dx + o), d);
+        if (!POST && accumulate) unpack8(*reinterpret_cast<const uint4*>(dx + o), d);
         else {
 #pragma unroll
             for (int e = 0; e < 8; ++e) d[e] = 0.f;
         }
+        const float nz = (POST && noise) ? nwv * __ldg(noise + (long)bi * HW + p) : 0.f;
+        row8(0, w);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            d[e] += g0 * w0[e] + g1 * w1[e] + g2 * w2[e];
-            a0[e] = fmaf(g0, xv[e], a0[e]); a1[e] = fmaf(g1, xv[e], a1[e]); a2[e] = fmaf(g2, xv[e], a2[e]);
+        for (int e = 0; e < 8; ++e) { d[e] = fmaf(g0, w[e], d[e]); a0[e] = fmaf(g0, xv[e], a0[e]); }
+        row8(1, w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { d[e] = fmaf(g1, w[e], d[e]); a1[e] = fmaf(g1, xv[e], a1[e]); }
+        row8(2, w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { d[e] = fmaf(g2, w[e], d[e]); a2[e] = fmaf(g2, xv[e], a2[e]); }
+        if constexpr (POST) {
+            float bv[8];
+            row8(4, bv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const bool pos = xv[e] > 0.f;
+                d[e] *= pos ? kSqrt2 : 0.2f * kSqrt2;
+                const float pre = xv[e] * (pos ? (1.f / kSqrt2) : (1.f / (0.2f * kSqrt2)));
+                a3[e] += d[e] * (pre - nz - bv[e]);   // ddm * dm (see k_demod_bwd)
+            }
+            row8(3, w);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d[e] *= w[e];
         }
         *reinterpret_cast<uint4*>(dx + o) = pack8(d);
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { red[0][py][cg * 8 + e] = a0[e]; red[1][py][cg * 8 + e] = a1[e]; red[2][py][cg * 8 + e] = a2[e]; }
+    for (int e = 0; e < 8; ++e) {
+        red[0][py][cg * 8 + e] = a0[e]; red[1][py][cg * 8 + e] = a1[e]; red[2][py][cg * 8 + e] = a2[e];
+        if constexpr (POST) red[3][py][cg * 8 + e] = a3[e];
+    }
     __syncthreads();
-    const int tid = py * 8 + cg;
-    if (tid < 192) {
+    if (tid < (POST ? 256 : 192)) {
         const int cc = tid / 64, k = tid % 64;
         float t = 0.f;
 #pragma unroll 8
         for (int j = 0; j < 32; ++j) t += red[cc][j][k];
-        part[(((long)bi * gridDim.x + blockIdx.x) * 3 + cc) * C + blockIdx.y * 64 + k] = t;
+        if (cc < 3) part[(((long)bi * gridDim.x + blockIdx.x) * 3 + cc) * C + blockIdx.y * 64 + k] = t;
+        else part_dm[((long)bi * gridDim.x + blockIdx.x) * C + blockIdx.y * 64 + k] = t;
     }
 }
 void k_sg_torgb_bwd(const float* drgb, const bf16* x, const float* weff, bf16* dx, float* dweff, float* scratch, int b, int H, int W,
                     int C, int accumulate, cudaStream_t st) {
     dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
-    torgb_bwd_kernel<<<grid, block, 0, st>>>(drgb, x, weff, dx, scratch, H, W, C, accumulate); count_launch();
+    torgb_bwd_kernel<false><<<grid, block, 0, st>>>(drgb, x, weff, dx, scratch, H, W, C, accumulate, nullptr, 0, nullptr, nullptr,
+                                                    nullptr, nullptr);
+    count_launch();
     partial_reduce_add(scratch, (int)grid.x, b, 3 * C, dweff, 3 * C, st);
+}
+// the last layer: ToRGB backward + that layer's activation backward in one pass over x (see torgb_bwd_kernel<true>)
+void k_sg_torgb_post_bwd(const float* drgb, const bf16* x, const float* weff, float* dweff, const float* dm, int lddm, const float* noise,
+                         const float* nw, const float* bias, bf16* G, float* ddm, float* scratch, int b, int H, int W, int C,
+                         cudaStream_t st) {
+    dim3 grid(cdiv((long)H * W, 256), C / 64, b), block(8, 32);
+    float* scratch_dm = scratch + (long)b * grid.x * 3 * C;
+    torgb_bwd_kernel<true><<<grid, block, 0, st>>>(drgb, x, weff, G, scratch, H, W, C, 0, dm, lddm, noise, nw, bias, scratch_dm);
+    count_launch();
+    partial_reduce_add(scratch, (int)grid.x, b, 3 * C, dweff, 3 * C, st);
+    partial_reduce_add(scratch_dm, (int)grid.x, b, C, ddm, lddm, st);
 }
 // ds[b, i] += scale * sum_c dweff[b,c,i] * Wr[c,i]
 __global__ void weff_bwd_kernel(const float* dweff, const float* Wr, float scale, float* ds, int ldds, int b, int C) {

@@ -17,6 +17,13 @@ void k_fc_fwd_ld(const float* x, int ldx, const float* WT, int ldw, const float*
 // splitk_scratch (>= 8 * 24 * in floats, or null): long reductions (out >= 2048) with few outputs are split over blocks
 void k_fc_bwd(const float* dy, int lddy, const float* y, int ldy, const float* W, float wscale, float* dx, int lddx, int b,
               int in, int out, int act, int accumulate, cudaStream_t st, float* splitk_scratch = nullptr);
+// the whole mapping network (PixelNorm + n_mlp EqualLinear(512, 512, fused_lrelu)) and its gradient as ONE cluster launch
+// each (sdim == 512, b <= 24, n_mlp <= 8); h[0..n_mlp] are the [b, 512] activations, W^T / W as for k_fc_fwd / k_fc_bwd
+bool k_sg_mapping_fusable(int b, int sdim, int n_mlp);
+void k_sg_mapping_fwd(const float* z, const float* const* WT, const float* const* bias, float wscale, float* const* h, int b, int n_mlp,
+                      cudaStream_t st);
+void k_sg_mapping_bwd(const float* dw, const float* const* W, float wscale, float* const* h, const float* z, float* dz, float scale,
+                      const float* row_scale, int b, int n_mlp, cudaStream_t st);
 void k_pixelnorm_fwd(const float* x, float* y, int b, int n, cudaStream_t st);
 void k_pixelnorm_bwd(const float* x, const float* dy, float* dx, int b, int n, float scale, const float* row_scale, cudaStream_t st);
 void k_demod_bwd(const float* ddm, const float* dm, int lddm, const float* s, int lds, const float* Wsq, float* ds, int ldds,
@@ -46,6 +53,10 @@ void k_sg_torgb_fwd(const bf16* x, const float* weff, const float* bias, const f
                     cudaStream_t st);
 void k_sg_torgb_bwd(const float* drgb, const bf16* x, const float* weff, bf16* dx, float* dweff, float* scratch, int b, int H, int W,
                     int C, int accumulate, cudaStream_t st);
+// last layer: ToRGB backward fused with that layer's activation / noise / bias / demodulation backward (k_sg_post_bwd_x)
+void k_sg_torgb_post_bwd(const float* drgb, const bf16* x, const float* weff, float* dweff, const float* dm, int lddm, const float* noise,
+                         const float* nw, const float* bias, bf16* G, float* ddm, float* scratch, int b, int H, int W, int C,
+                         cudaStream_t st);
 void k_sg_weff_bwd(const float* dweff, const float* Wr, float scale, float* ds, int ldds, int b, int C, cudaStream_t st);
 void k_sg_rgb_up_adjoint(const float* drgb, float* dprev, int b, int h, int w, cudaStream_t st);
 void k_sg_clamp(const float* rgb, float* img, long n, cudaStream_t st);
