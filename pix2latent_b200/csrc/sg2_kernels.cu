@@ -232,17 +232,23 @@ struct SgMap {
     float wscale, scale;
     int b, n;
 };
-constexpr int kMapDim = 512, kMapCtas = 8, kMapCols = kMapDim / kMapCtas;
+constexpr int kMapDim = 512, kMapCtas = 8, kMapCols = kMapDim / kMapCtas, kMapWarps = 16, kMapKW = kMapDim / kMapWarps;
 template <int NB, bool BWD>
-__global__ void __cluster_dims__(kMapCtas, 1, 1) __launch_bounds__(256) sg_mapping_kernel(const SgMap a) {
+__global__ void __cluster_dims__(kMapCtas, 1, 1) __launch_bounds__(kMapWarps * 32) sg_mapping_kernel(const SgMap a) {
     extern __shared__ __align__(16) float map_sm[];
     float(*xs)[NB][kMapDim] = reinterpret_cast<float(*)[NB][kMapDim]>(map_sm);                       // [2][NB][512]
-    float(*red)[NB][kMapCols] = reinterpret_cast<float(*)[NB][kMapCols]>(map_sm + 2 * NB * kMapDim);   // [8][NB][64]
+    float(*red)[NB][kMapCols] = reinterpret_cast<float(*)[NB][kMapCols]>(map_sm + 2 * NB * kMapDim);   // [16][NB][64]
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // every layer's 128 KB weight slab of this CTA on its way into L2 (thread = one 256-byte row of each slab)
+    for (int k = 0; k < a.n; ++k) {
+        const float* row = a.M[k] + (long)threadIdx.x * kMapDim + rank * kMapCols;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 32));
+    }
     // ---- the first input, computed by every CTA for itself
-    for (int bi = warp; bi < NB; bi += 8) {
+    for (int bi = warp; bi < NB; bi += kMapWarps) {
         float v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = bi < a.b ? a.in[(long)bi * kMapDim + q * 32 + lane] : 0.f;
@@ -271,29 +277,34 @@ __global__ void __cluster_dims__(kMapCtas, 1, 1) __launch_bounds__(256) sg_mappi
         float acc[NB][2];
 #pragma unroll
         for (int i = 0; i < NB; ++i) acc[i][0] = acc[i][1] = 0.f;
-        const float* mp = a.M[k] + (long)(warp * 64) * kMapDim + rank * kMapCols + lane * 2;
-#pragma unroll 2
-        for (int u = 0; u < 64; u += 4) {
-            float2 w[4];
+        const float* mp = a.M[k] + (long)(warp * kMapKW) * kMapDim + rank * kMapCols + lane * 2;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) w[q] = __ldg(reinterpret_cast<const float2*>(mp + (long)(u + q) * kMapDim));
+        for (int u0 = 0; u0 < kMapKW; u0 += 16) {
+            float2 w[16];   // sixteen 256-byte rows in flight per warp
 #pragma unroll
-            for (int i = 0; i < NB; ++i) {
-                const float4 x4 = *reinterpret_cast<const float4*>(&xs[cur][i][warp * 64 + u]);
-                acc[i][0] = fmaf(x4.x, w[0].x, acc[i][0]); acc[i][1] = fmaf(x4.x, w[0].y, acc[i][1]);
-                acc[i][0] = fmaf(x4.y, w[1].x, acc[i][0]); acc[i][1] = fmaf(x4.y, w[1].y, acc[i][1]);
-                acc[i][0] = fmaf(x4.z, w[2].x, acc[i][0]); acc[i][1] = fmaf(x4.z, w[2].y, acc[i][1]);
-                acc[i][0] = fmaf(x4.w, w[3].x, acc[i][0]); acc[i][1] = fmaf(x4.w, w[3].y, acc[i][1]);
+            for (int q = 0; q < 16; ++q) w[q] = __ldg(reinterpret_cast<const float2*>(mp + (long)(u0 + q) * kMapDim));
+#pragma unroll
+            for (int u = 0; u < 16; u += 4) {
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const float4 x4 = *reinterpret_cast<const float4*>(&xs[cur][i][warp * kMapKW + u0 + u]);
+                    acc[i][0] = fmaf(x4.x, w[u].x, acc[i][0]); acc[i][1] = fmaf(x4.x, w[u].y, acc[i][1]);
+                    acc[i][0] = fmaf(x4.y, w[u + 1].x, acc[i][0]); acc[i][1] = fmaf(x4.y, w[u + 1].y, acc[i][1]);
+                    acc[i][0] = fmaf(x4.z, w[u + 2].x, acc[i][0]); acc[i][1] = fmaf(x4.z, w[u + 2].y, acc[i][1]);
+                    acc[i][0] = fmaf(x4.w, w[u + 3].x, acc[i][0]); acc[i][1] = fmaf(x4.w, w[u + 3].y, acc[i][1]);
+                }
             }
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i) *reinterpret_cast<float2*>(&red[warp][i][lane * 2]) = make_float2(acc[i][0], acc[i][1]);
         __syncthreads();
-        for (int t = threadIdx.x; t < NB * kMapCols; t += 256) {
+        for (int t = threadIdx.x; t < NB * kMapCols; t += kMapWarps * 32) {
             const int bi = t / kMapCols, jj = t % kMapCols, jo = rank * kMapCols + jj;
-            float v = ((red[0][bi][jj] + red[1][bi][jj]) + (red[2][bi][jj] + red[3][bi][jj])) +
-                      ((red[4][bi][jj] + red[5][bi][jj]) + (red[6][bi][jj] + red[7][bi][jj]));
-            v *= a.wscale;
+            float s4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                s4[q] = (red[4 * q][bi][jj] + red[4 * q + 1][bi][jj]) + (red[4 * q + 2][bi][jj] + red[4 * q + 3][bi][jj]);
+            float v = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * a.wscale;
             if constexpr (!BWD) {
                 v += a.bias[k][jo];
                 v = (v > 0.f ? v : 0.2f * v) * kSqrt2;
@@ -311,7 +322,7 @@ __global__ void __cluster_dims__(kMapCtas, 1, 1) __launch_bounds__(256) sg_mappi
     if constexpr (BWD) {
         if (rank != 0) return;   // no remote access after the last barrier: leaving is safe
         const float(*g)[kMapDim] = xs[a.n & 1];
-        for (int bi = warp; bi < a.b; bi += 8) {
+        for (int bi = warp; bi < a.b; bi += kMapWarps) {
             float x[16], ss = 0.f, dot = 0.f;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
@@ -331,13 +342,13 @@ __global__ void __cluster_dims__(kMapCtas, 1, 1) __launch_bounds__(256) sg_mappi
 }
 template <int NB, bool BWD>
 static void launch_mapping(const SgMap& a, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(2 * NB * kMapDim + 8 * NB * kMapCols) * sizeof(float);
+    constexpr size_t smem = (size_t)(2 * NB * kMapDim + kMapWarps * NB * kMapCols) * sizeof(float);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(sg_mapping_kernel<NB, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    sg_mapping_kernel<NB, BWD><<<kMapCtas, 256, smem, st>>>(a);
+    sg_mapping_kernel<NB, BWD><<<kMapCtas, kMapWarps * 32, smem, st>>>(a);
     count_launch();
 }
 bool k_sg_mapping_fusable(int b, int sdim, int n_mlp) { return sdim == kMapDim && b <= 24 && n_mlp >= 1 && n_mlp <= 8; }
@@ -562,21 +573,19 @@ void k_sg_weff(const float* Wr, const float* s, int lds, float scale, float* wef
 // Per axis that is two taps: rows ia = floor((y-1)/2) and ia+1 with weights (1/4, 3/4) for even y, (3/4, 1/4) for odd y.
 __device__ __forceinline__ float up_gather(const float* __restrict__ prev, int h, int w, int y, int xx) {
     const int ia = (y - 1) >> 1, ja = (xx - 1) >> 1;
-    const float wya = (y & 1) ? 0.75f : 0.25f, wxa = (xx & 1) ? 0.75f : 0.25f;
-    const float wyb = 1.f - wya, wxb = 1.f - wxa;
-    const bool ra = ia >= 0, rb = ia + 1 < h, ca = ja >= 0, cb = ja + 1 < w;
-    const float* r0 = prev + (long)ia * w + ja;
-    const float* r1 = r0 + w;
+    const float ya = (y & 1) ? 0.75f : 0.25f, xa = (xx & 1) ? 0.75f : 0.25f;
+    // out-of-range taps: clamped address, zero weight — four independent loads in flight, same sum order as the tap loop
+    const float wya = ia >= 0 ? ya : 0.f, wyb = ia + 1 < h ? 1.f - ya : 0.f;
+    const float wxa = ja >= 0 ? xa : 0.f, wxb = ja + 1 < w ? 1.f - xa : 0.f;
+    const float* r0 = prev + (long)max(ia, 0) * w;
+    const float* r1 = prev + (long)min(ia + 1, h - 1) * w;
+    const int j0 = max(ja, 0), j1 = min(ja + 1, w - 1);
+    const float v00 = __ldg(r0 + j0), v01 = __ldg(r0 + j1), v10 = __ldg(r1 + j0), v11 = __ldg(r1 + j1);
     float acc = 0.f;
-    // same association as the 4 x 4 tap loop: per row, then rows in order
-    if (ra) {
-        if (ca) acc = fmaf(wya * wxa, __ldg(r0), acc);
-        if (cb) acc = fmaf(wya * wxb, __ldg(r0 + 1), acc);
-    }
-    if (rb) {
-        if (ca) acc = fmaf(wyb * wxa, __ldg(r1), acc);
-        if (cb) acc = fmaf(wyb * wxb, __ldg(r1 + 1), acc);
-    }
+    acc = fmaf(wya * wxa, v00, acc);
+    acc = fmaf(wya * wxb, v01, acc);
+    acc = fmaf(wyb * wxa, v10, acc);
+    acc = fmaf(wyb * wxb, v11, acc);
     return acc;
 }
 // rgb[b,c,p] = sum_i weff[b,c,i] x[b,p,i] + bias[c] (+ upsampled previous rgb). block = 256 consecutive pixels of one image,
@@ -608,15 +617,23 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const bf16* __restrict__
         const int p0 = (blockIdx.x * tiles_per_block + tile) * 256;
         if (p0 >= HW) break;
         const int pw = p0 + warp * 32 + lane / lpp;
-#pragma unroll 4
-        for (int q = 0; q < 32; q += ppl) {
-            const int p = pw + q;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-            if (p < HW) {
+        for (int q0 = 0; q0 < 32; q0 += 8 * ppl) {
+            uint4 raw[8][NK];   // eight warp loads (x NK) in flight before the first use
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int p = pw + q0 + j * ppl;
+#pragma unroll
+                for (int k = 0; k < NK; ++k)
+                    raw[j][k] = p < HW ? __ldg(reinterpret_cast<const uint4*>(xb + (long)p * C + k * 256)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int p = pw + q0 + j * ppl;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
                     float v[8];
-                    unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (long)p * C + k * 256)), v);
+                    unpack8(raw[j][k], v);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         a0 = fmaf(v[e], w[k][0][e], a0);
@@ -624,13 +641,16 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const bf16* __restrict__
                         a2 = fmaf(v[e], w[k][2][e], a2);
                     }
                 }
+#pragma unroll
+                for (int h = 16; h > 0; h >>= 1) {
+                    if (h < lpp) {
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, h);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, h);
+                        a2 += __shfl_xor_sync(0xffffffffu, a2, h);
+                    }
+                }
+                if (sub == 0 && p < HW) { res[0][p - p0] = a0; res[1][p - p0] = a1; res[2][p - p0] = a2; }
             }
-            for (int h = lpp >> 1; h > 0; h >>= 1) {
-                a0 += __shfl_xor_sync(0xffffffffu, a0, h);
-                a1 += __shfl_xor_sync(0xffffffffu, a1, h);
-                a2 += __shfl_xor_sync(0xffffffffu, a2, h);
-            }
-            if (sub == 0 && p < HW) { res[0][p - p0] = a0; res[1][p - p0] = a1; res[2][p - p0] = a2; }
         }
         __syncthreads();
         const int p = p0 + threadIdx.x;   // thread = pixel: one division for the three planes
@@ -700,7 +720,7 @@ void k_sg_torgb_fwd(const bf16* x, const float* weff, const float* bias, const f
 // post_bwd_x_kernel runs on the gradient while it is still in registers — G = dm * g is stored instead of dx, and the
 // (ddm * dm) sums leave through a fourth plane of partial slots.
 template <bool POST>
-__global__ void __launch_bounds__(256, 3) torgb_bwd_kernel(const float* __restrict__ drgb, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) torgb_bwd_kernel(const float* __restrict__ drgb, const bf16* __restrict__ x,
                                                            const float* __restrict__ weff, bf16* __restrict__ dx, float* __restrict__ part,
                                                            int H, int W, int C, int accumulate, const float* __restrict__ dm, int lddm,
                                                            const float* __restrict__ noise, const float* __restrict__ nw,
@@ -726,45 +746,54 @@ __global__ void __launch_bounds__(256, 3) torgb_bwd_kernel(const float* __restri
         const float4 lo = *reinterpret_cast<const float4*>(&coef[r][cg * 8]), hi = *reinterpret_cast<const float4*>(&coef[r][cg * 8 + 4]);
         v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
     };
-#pragma unroll(POST ? 1 : 4)
-    for (int it = 0; it < 8; ++it) {
-        const int p = blockIdx.x * 256 + it * 32 + py;
-        if (p >= HW) break;
-        const float g0 = __ldg(drgb + ((long)bi * 3 + 0) * HW + p), g1 = __ldg(drgb + ((long)bi * 3 + 1) * HW + p),
-                    g2 = __ldg(drgb + ((long)bi * 3 + 2) * HW + p);
-        const long o = ((long)bi * HW + p) * C + c;
-        float xv[8], d[8], w[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(x + o)), xv);
-        if (!POST && accumulate) unpack8(*reinterpret_cast<const uint4*>(dx + o), d);
-        else {
+    constexpr int B = 4;   // iterations whose loads are issued together
+    for (int it0 = 0; it0 < 8; it0 += B) {
+        uint4 xr[B], dr[B];
+        float g[B][3], nzv[B];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) d[e] = 0.f;
+        for (int j = 0; j < B; ++j) {
+            const int p = blockIdx.x * 256 + (it0 + j) * 32 + py;
+            const bool ok = p < HW;
+            const long o = ((long)bi * HW + p) * C + c;
+            xr[j] = ok ? __ldg(reinterpret_cast<const uint4*>(x + o)) : make_uint4(0u, 0u, 0u, 0u);
+            dr[j] = (!POST && accumulate && ok) ? *reinterpret_cast<const uint4*>(dx + o) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) g[j][cc] = ok ? __ldg(drgb + ((long)bi * 3 + cc) * HW + p) : 0.f;
+            nzv[j] = (POST && noise && ok) ? nwv * __ldg(noise + (long)bi * HW + p) : 0.f;
         }
-        const float nz = (POST && noise) ? nwv * __ldg(noise + (long)bi * HW + p) : 0.f;
-        row8(0, w);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { d[e] = fmaf(g0, w[e], d[e]); a0[e] = fmaf(g0, xv[e], a0[e]); }
-        row8(1, w);
+        for (int j = 0; j < B; ++j) {
+            const int p = blockIdx.x * 256 + (it0 + j) * 32 + py;
+            const long o = ((long)bi * HW + p) * C + c;
+            float xv[8], d[8], w[8];
+            unpack8(xr[j], xv);
+            unpack8(dr[j], d);
+            const float g0 = g[j][0], g1 = g[j][1], g2 = g[j][2], nz = nzv[j];
+            row8(0, w);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { d[e] = fmaf(g1, w[e], d[e]); a1[e] = fmaf(g1, xv[e], a1[e]); }
-        row8(2, w);
+            for (int e = 0; e < 8; ++e) { d[e] = fmaf(g0, w[e], d[e]); a0[e] = fmaf(g0, xv[e], a0[e]); }
+            row8(1, w);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { d[e] = fmaf(g2, w[e], d[e]); a2[e] = fmaf(g2, xv[e], a2[e]); }
-        if constexpr (POST) {
-            float bv[8];
-            row8(4, bv);
+            for (int e = 0; e < 8; ++e) { d[e] = fmaf(g1, w[e], d[e]); a1[e] = fmaf(g1, xv[e], a1[e]); }
+            row8(2, w);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const bool pos = xv[e] > 0.f;
-                d[e] *= pos ? kSqrt2 : 0.2f * kSqrt2;
-                const float pre = xv[e] * (pos ? (1.f / kSqrt2) : (1.f / (0.2f * kSqrt2)));
-                a3[e] += d[e] * (pre - nz - bv[e]);   // ddm * dm (see k_demod_bwd)
+            for (int e = 0; e < 8; ++e) { d[e] = fmaf(g2, w[e], d[e]); a2[e] = fmaf(g2, xv[e], a2[e]); }
+            if constexpr (POST) {
+                float bv[8];
+                row8(4, bv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const bool pos = xv[e] > 0.f;
+                    d[e] *= pos ? kSqrt2 : 0.2f * kSqrt2;
+                    const float pre = xv[e] * (pos ? (1.f / kSqrt2) : (1.f / (0.2f * kSqrt2)));
+                    a3[e] += d[e] * (pre - nz - bv[e]);   // ddm * dm (see k_demod_bwd)
+                }
+                row8(3, w);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d[e] *= w[e];
             }
-            row8(3, w);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) d[e] *= w[e];
+            if (p < HW) *reinterpret_cast<uint4*>(dx + o) = pack8(d);
         }
-        *reinterpret_cast<uint4*>(dx + o) = pack8(d);
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
