@@ -5,6 +5,8 @@
 #include "conv_gemm.h"
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 
 namespace p2l {
 
@@ -384,52 +386,48 @@ void k_pool_bnrelu_bwd(const bf16* g_up, const bf16* y_lo, const float* a, int a
     pool_bnrelu_bwd_kernel<<<grid, block, 0, st>>>(g_up, y_lo, a, aff_stride, statp, (int)grid.x, dx, H, W, C); count_launch();
 }
 
-// BN-gradient sums: S0/S1[n][off + c] = sum over the layer's partial slots in a fixed order — 32 interleaved slices of the
-// slot sequence per (n, c), four independent running sums per slice (loads in flight), then a fixed tree — the same order
-// whatever the launch geometry of the producers was
-__global__ void __launch_bounds__(1024) stat_reduce_kernel(const StatSeg* __restrict__ segs, float* __restrict__ S0,
-                                                           float* __restrict__ S1, int stride, int stride1) {
+// BN-gradient sums: S0/S1[n][off + c] = sum over the layer's partial slots in a fixed order: 32 interleaved slices of the slot
+// sequence per (n, c) — warp w keeps the running sums of slices w, w+8, w+16, w+24, i.e. eight independent loads in flight per
+// thread — then a fixed tree over the 32 slice sums. The order depends on the number of slots only, never on the launch
+// geometry of the producers or of this kernel.
+__global__ void __launch_bounds__(256) stat_reduce_kernel(const StatSeg* __restrict__ segs, float* __restrict__ S0,
+                                                          float* __restrict__ S1, int stride, int stride1) {
     __shared__ float r0[32][33], r1[32][33];
     const StatSeg sg = segs[blockIdx.x];
-    const int n = blockIdx.y, lane = threadIdx.x, sl = threadIdx.y;
+    const int n = blockIdx.y, lane = threadIdx.x, w = threadIdx.y;
     const float* base = sg.p + (long)n * sg.pstride * 2 * sg.C + sg.c0 + lane;
     const long step = 2L * sg.C;
     float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
-    int q = sl;
-    for (; q + 96 < sg.parts; q += 128) {
+    for (int q = w; q < sg.parts; q += 32) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            a0[u] += __ldg(base + (q + 32 * u) * step);
-            a1[u] += __ldg(base + (q + 32 * u) * step + sg.C);
+            if (q + 8 * u < sg.parts) {
+                a0[u] += __ldg(base + (q + 8 * u) * step);
+                a1[u] += __ldg(base + (q + 8 * u) * step + sg.C);
+            }
         }
     }
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
-        if (q + 32 * u < sg.parts) {
-            a0[u] += __ldg(base + (q + 32 * u) * step);
-            a1[u] += __ldg(base + (q + 32 * u) * step + sg.C);
-        }
-    }
-    r0[sl][lane] = (a0[0] + a0[1]) + (a0[2] + a0[3]);
-    r1[sl][lane] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+    for (int u = 0; u < 4; ++u) { r0[w + 8 * u][lane] = a0[u]; r1[w + 8 * u][lane] = a1[u]; }
     __syncthreads();
-    // fixed tree over the 32 slices
-    for (int h = 16; h > 0; h >>= 1) {
-        if (sl < h) { r0[sl][lane] += r0[sl + h][lane]; r1[sl][lane] += r1[sl + h][lane]; }
-        __syncthreads();
-    }
-    if (sl == 0) {
-        S0[(long)n * stride + sg.off + sg.c0 + lane] = r0[0][lane];
-        S1[(long)n * stride1 + sg.off1 + sg.c0 + lane] = r1[0][lane];
+    if (w == 0) {
+        float t0[8], t1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            t0[k] = (r0[4 * k][lane] + r0[4 * k + 1][lane]) + (r0[4 * k + 2][lane] + r0[4 * k + 3][lane]);
+            t1[k] = (r1[4 * k][lane] + r1[4 * k + 1][lane]) + (r1[4 * k + 2][lane] + r1[4 * k + 3][lane]);
+        }
+        S0[(long)n * stride + sg.off + sg.c0 + lane] = ((t0[0] + t0[1]) + (t0[2] + t0[3])) + ((t0[4] + t0[5]) + (t0[6] + t0[7]));
+        S1[(long)n * stride1 + sg.off1 + sg.c0 + lane] = ((t1[0] + t1[1]) + (t1[2] + t1[3])) + ((t1[4] + t1[5]) + (t1[6] + t1[7]));
     }
 }
 void k_stat_reduce(const StatSeg* segs, int nsegs, float* S0, float* S1, int stride, int b, cudaStream_t st) {
     if (nsegs <= 0) return;
-    stat_reduce_kernel<<<dim3(nsegs, b), dim3(32, 32), 0, st>>>(segs, S0, S1, stride, stride); count_launch();
+    stat_reduce_kernel<<<dim3(nsegs, b), dim3(32, 8), 0, st>>>(segs, S0, S1, stride, stride); count_launch();
 }
 void k_stat_reduce2(const StatSeg* segs, int nsegs, float* S0, int stride0, float* S1, int stride1, int b, cudaStream_t st) {
     if (nsegs <= 0) return;
-    stat_reduce_kernel<<<dim3(nsegs, b), dim3(32, 32), 0, st>>>(segs, S0, S1, stride0, stride1); count_launch();
+    stat_reduce_kernel<<<dim3(nsegs, b), dim3(32, 8), 0, st>>>(segs, S0, S1, stride0, stride1); count_launch();
 }
 
 __global__ void pool2x2_sum_kernel(const bf16* __restrict__ in, int inC, bf16* __restrict__ out, int b, int H, int W, int C) {
@@ -637,34 +635,50 @@ void k_transpose(const bf16* in, int ldin, int in_c0, bf16* out, int b, int R, i
 __constant__ float kLpipsShift[3] = {-.030f, -.088f, -.188f};
 __constant__ float kLpipsScale[3] = {.458f, .448f, .450f};
 
-__global__ void im2col_alex1_kernel(const float* __restrict__ img, bf16* __restrict__ col, int b, int H, int W,
-                                    int Ho, int Wo, int Kp) {
-    // thread = 8 consecutive k of one output pixel -> one 16-byte store
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int groups = Kp / 8;
-    const long total = (long)b * Ho * Wo * groups;
-    if (i >= total) return;
-    const int kg = i % groups;
-    const long q = i / groups;
-    const int ox = q % Wo, oy = (q / Wo) % Ho, bi = q / ((long)Wo * Ho);
-    float v[8];
+// AlexNet conv1 (11x11, stride 4, pad 2) as a GEMM: col[(bi, oy, ox)][k], k = (c*11 + r)*11 + s (363 of Kp = 384 columns).
+// block = one output row oy x 32 consecutive ox of one image: the (3 x 11 x 135)-pixel input patch is read once, coalesced,
+// normalised (LPIPS ScalingLayer) into shared memory; thread (kg, pl) then owns the 8 columns k = 8 kg .. 8 kg + 7 — their
+// patch offsets are computed once and live in registers — and writes one 16-byte store per pixel (pixels pl, pl + 8, ...):
+// the 48 threads of a pixel cover its 768 contiguous bytes.
+constexpr int kA1Pix = 32, kA1PW = 4 * (kA1Pix - 1) + 11;   // 135 patch columns
+__global__ void __launch_bounds__(384) im2col_alex1_kernel(const float* __restrict__ img, bf16* __restrict__ col, int H, int W,
+                                                           int Ho, int Wo, int Kp) {
+    __shared__ float patch[33][kA1PW + 1];   // [(c, r)][column]
+    const int bi = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * kA1Pix;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x0 = 4 * ox0 - 2, y0 = 4 * oy - 2;
+    for (int cr = warp; cr < 33; cr += 12) {
+        const int c = cr / 11, r = cr - c * 11, y = y0 + r;
+        const float sh = kLpipsShift[c];
+        const float* row = img + (((long)bi * 3 + c) * H + y) * W;
+        for (int j = lane; j < kA1PW; j += 32) {
+            const int x = x0 + j;
+            // (v - shift) / scale as the per-element kernel computed it
+            patch[cr][j] = (y >= 0 && y < H && x >= 0 && x < W) ? (__ldg(row + x) - sh) / kLpipsScale[c] : 0.f;
+        }
+    }
+    __syncthreads();
+    const int kg = threadIdx.x % 48, pl = threadIdx.x / 48;   // 48 column groups x 8 pixel lanes
+    int off[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int k = kg * 8 + e;
-        float val = 0.f;
-        if (k < 363) {
-            const int c = k / 121, rem = k - c * 121, r = rem / 11, s = rem - r * 11;
-            const int y = 4 * oy - 2 + r, x = 4 * ox - 2 + s;
-            if (y >= 0 && y < H && x >= 0 && x < W)
-                val = (__ldg(img + (((long)bi * 3 + c) * H + y) * W + x) - kLpipsShift[c]) / kLpipsScale[c];
-        }
-        v[e] = val;
+        const int cr = k / 11, s = k - cr * 11;
+        off[e] = k < 363 ? cr * (kA1PW + 1) + s : -1;
     }
-    *reinterpret_cast<uint4*>(col + q * Kp + kg * 8) = pack8(v);
+    const float* pf = &patch[0][0];
+    for (int p = pl; p < kA1Pix; p += 8) {
+        const int ox = ox0 + p;
+        if (ox >= Wo) break;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? pf[off[e] + 4 * p] : 0.f;
+        *reinterpret_cast<uint4*>(col + (((long)bi * Ho + oy) * Wo + ox) * Kp + kg * 8) = pack8(v);
+    }
 }
 void k_im2col_alex1(const float* img, bf16* col, int b, int H, int W, int Ho, int Wo, int Kp, cudaStream_t st) {
-    const long total = (long)b * Ho * Wo * (Kp / 8);
-    im2col_alex1_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, col, b, H, W, Ho, Wo, Kp); count_launch();
+    if (Kp != 384) { fprintf(stderr, "[p2l] im2col_alex1: Kp = %d (expected 384)\n", Kp); abort(); }
+    im2col_alex1_kernel<<<dim3(cdiv(Wo, kA1Pix), Ho, b), 384, 0, st>>>(img, col, H, W, Ho, Wo, Kp); count_launch();
 }
 
 __global__ void col2im_alex1_kernel(const bf16* __restrict__ dcol, float* __restrict__ dimg, int b, int H, int W,
@@ -673,18 +687,29 @@ __global__ void col2im_alex1_kernel(const bf16* __restrict__ dcol, float* __rest
     const long total = (long)b * 3 * H * W;
     if (i >= total) return;
     const int x = i % W, y = (i / W) % H, c = (i / ((long)W * H)) % 3, bi = i / ((long)3 * W * H);
-    float acc = 0.f;
-    const int oy_lo = max(0, (y + 2 - 10 + 3) / 4), oy_hi = min(Ho - 1, (y + 2) / 4);
-    const int ox_lo = max(0, (x + 2 - 10 + 3) / 4), ox_hi = min(Wo - 1, (x + 2) / 4);
-    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-        const int r = y + 2 - 4 * oy;
-        if (r < 0 || r > 10) continue;
-        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-            const int s = x + 2 - 4 * ox;
-            if (s < 0 || s > 10) continue;
-            acc += b2f(dcol[(((long)bi * Ho + oy) * Wo + ox) * Kp + (c * 11 + r) * 11 + s]);
+    // the (up to) 3 x 3 output pixels whose 11 x 11 windows cover (y, x): oy = (y+2)/4 - {2,1,0} with r = (y+2)%4 + {8,4,0}.
+    // Branch-free (clamped address, contribution zeroed) so that the nine loads are in flight together; same sum order
+    // (oy ascending, then ox ascending) as the bounded loops.
+    const int yy = y + 2, xx = x + 2;
+    const int oyh = yy >> 2, r0 = yy & 3, oxh = xx >> 2, s0 = xx & 3;
+    float t[9];
+    bool ok[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int oy = oyh - 2 + a, r = r0 + 8 - 4 * a;
+        const bool vy = oy >= 0 && oy < Ho && r <= 10;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int ox = oxh - 2 + d, s2 = s0 + 8 - 4 * d;
+            const bool v = vy && ox >= 0 && ox < Wo && s2 <= 10;
+            const long idx = v ? ((((long)bi * Ho + oy) * Wo + ox) * Kp + (c * 11 + r) * 11 + s2) : 0;
+            ok[a * 3 + d] = v;
+            t[a * 3 + d] = b2f(dcol[idx]);
         }
     }
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc += ok[q] ? t[q] : 0.f;
     acc *= unscale / kLpipsScale[c];
     dimg[i] = accumulate ? dimg[i] + acc : acc;
 }
@@ -784,10 +809,12 @@ void k_maxpool_bwd(const bf16* dout, const unsigned char* idx, const bf16* x, co
 
 // one warp per feature pixel, block = 8 warps; a lane keeps its <= 16 channels of the pixel (features, target, lin
 // weights) in registers, so HBM is read ONCE; block k of sample bi writes its part of the loss to slot k
+// NC = channels per lane = ceil(C / 32): 2 .. 16 (alex: 64..384 channels, vgg16: 64..512) — an instantiation per width, so
+// that the 64-channel first layer (most pixels by far) does not issue sixteen predicated passes
+template <int NC>
 __global__ void __launch_bounds__(256) lpips_dist_kernel(const bf16* __restrict__ f, const float* __restrict__ t,
                                   const float* __restrict__ lin, const float* __restrict__ wadj, float* __restrict__ lossp,
                                   int lp_stride, bf16* __restrict__ g, int HW, int C, float gscale) {
-    constexpr int NC = 16;   // channels per lane: C <= 512 (alex: 64..384, vgg16: 64..512)
     __shared__ float part[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bi = blockIdx.y;
@@ -849,7 +876,14 @@ int k_lpips_dist_slots(int HW) { return cdiv(HW, 8); }
 void k_lpips_dist(const bf16* f, const float* t, const float* lin, const float* wadj, float* lossp, int lp_stride, bf16* g,
                   int b, int HW, int C, float gscale, cudaStream_t st) {
     dim3 grid(cdiv(HW, 8), b);
-    lpips_dist_kernel<<<grid, 256, 0, st>>>(f, t, lin, wadj, lossp, lp_stride, g, HW, C, gscale); count_launch();
+    const int nc = cdiv(C, 32);
+    if (nc <= 2) lpips_dist_kernel<2><<<grid, 256, 0, st>>>(f, t, lin, wadj, lossp, lp_stride, g, HW, C, gscale);
+    else if (nc <= 4) lpips_dist_kernel<4><<<grid, 256, 0, st>>>(f, t, lin, wadj, lossp, lp_stride, g, HW, C, gscale);
+    else if (nc <= 8) lpips_dist_kernel<8><<<grid, 256, 0, st>>>(f, t, lin, wadj, lossp, lp_stride, g, HW, C, gscale);
+    else if (nc <= 12) lpips_dist_kernel<12><<<grid, 256, 0, st>>>(f, t, lin, wadj, lossp, lp_stride, g, HW, C, gscale);
+    else if (nc <= 16) lpips_dist_kernel<16><<<grid, 256, 0, st>>>(f, t, lin, wadj, lossp, lp_stride, g, HW, C, gscale);
+    else { fprintf(stderr, "[p2l] lpips_dist: %d channels (max 512)\n", C); abort(); }
+    count_launch();
 }
 
 // loss[bi] = sum of the sample's partial slots (pixel term blocks, then every layer's distance blocks), fixed order

@@ -130,7 +130,8 @@ def test_replay_30_steps_c2(weights):
             per_cand = min(cos(dz[i], zz.grad[i]) for i in range(N))
             print("[%s] step 0: cos dz %.5f  cos dc %.5f  worst per-candidate cos dz %.5f  |dz| ratio %.4f"
                   % (weights, cz, cc_, per_cand, (dz.norm() / zz.grad.norm()).item()))
-            assert cz >= (0.99 if weights == "calibrated" else 0.95) and cc_ >= (0.99 if weights == "calibrated" else 0.95)
+            # measured 0.9953 (calibrated: deep, strongly conditioned), 0.99992 (bench weights); bounds = 2x the deviation
+            assert cz >= (0.99 if weights == "calibrated" else 0.9998) and cc_ >= (0.99 if weights == "calibrated" else 0.9998)
         if k == STEPS:
             break
         # advance the ORACLE trajectory; its per-candidate losses are those of the state the native step just saw
@@ -140,7 +141,7 @@ def test_replay_30_steps_c2(weights):
         rows.append(err)
         worst = max(worst, err)
     print("[%s] per-step max |dloss|/(1+|loss|):" % weights, " ".join("%.1e" % e for e in rows))
-    assert worst <= 2e-3, worst
+    assert worst <= 6e-4, worst   # measured 2.4e-4 .. 2.7e-4
     # ---- final state (z_30, c_30): image, total loss, LPIPS term alone
     with torch.no_grad():
         ref_img = torch.cat([W.orc(z=z[i:i + CHUNK], c=c[i:i + CHUNK]) for i in (0, CHUNK)])
@@ -153,7 +154,7 @@ def test_replay_30_steps_c2(weights):
           "final LPIPS max |d| %.2e (values %.4f .. %.4f)"
           % (weights, d.max().item(), d.mean().item(), frac_bad, (l_nat - ref_l).abs().max().item(),
              (nat_p - ref_p).abs().max().item(), ref_p.min().item(), ref_p.max().item()))
-    assert (nat_p - ref_p).abs().max().item() <= 1e-3
+    assert (nat_p - ref_p).abs().max().item() <= 1e-4   # north star: 1e-3; measured 1.5e-5 on LPIPS values of 5e-3 .. 1e-2
     assert frac_bad <= 1e-3 and d.max().item() <= 6e-2
 
 
@@ -229,5 +230,5 @@ def test_free_run_30_steps_c2():
     print("free run: final LPIPS oracle mean %.5f best %.5f | native mean %.5f best %.5f | per-candidate |d| max %.3e mean %.3e; z drift mean %.3e"
           % (ref_p.mean().item(), ref_p.min().item(), nat_p.mean().item(), nat_p.min().item(),
              (nat_p - ref_p).abs().max().item(), (nat_p - ref_p).abs().mean().item(), (zn - z).abs().mean().item()))
-    assert abs(nat_p.mean().item() - ref_p.mean().item()) <= 1e-3
-    assert abs(nat_l.mean().item() - ref_l.mean().item()) <= 2e-2 * (1 + abs(ref_l.mean().item()))
+    assert abs(nat_p.mean().item() - ref_p.mean().item()) <= 2e-4   # north star: 1e-3; measured 1e-5 .. 9e-5
+    assert abs(nat_l.mean().item() - ref_l.mean().item()) <= 2e-3 * (1 + abs(ref_l.mean().item()))   # measured 2e-4

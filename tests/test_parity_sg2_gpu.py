@@ -90,20 +90,20 @@ def test_cars512_replay_with_lpips():
         if k == 0:
             c0 = cos(dz, z.grad)
             print("cars-512 step 0: cos dz %.5f  |dz| ratio %.4f" % (c0, (dz.norm() / z.grad.norm()).item()))
-            assert c0 >= 0.99
+            assert c0 >= 0.9995   # measured 1.00000
         if k == steps:
             break
         opt.step()
     print("cars-512 per-step max |dloss|/(1+|loss|):", " ".join("%.1e" % e for e in errs))
-    assert max(errs) <= 2e-3
+    assert max(errs) <= 4e-4   # measured 1.7e-4
     with torch.no_grad():
         ref_p = ref_per(ref_img, T, Wt, Wt)
     nat_p = tgt_per.loss_forward(img, False)
     d = (img - ref_img.detach()).abs()
     print("cars-512 final image: max-abs %.3e mean-abs %.3e; final LPIPS max |d| %.2e (values %.4f .. %.4f)"
           % (d.max().item(), d.mean().item(), (nat_p - ref_p).abs().max().item(), ref_p.min().item(), ref_p.max().item()))
-    assert (nat_p - ref_p).abs().max().item() <= 1e-3
-    assert d.mean().item() <= 5e-3
+    assert (nat_p - ref_p).abs().max().item() <= 1e-4   # north star: 1e-3; measured 1.4e-5
+    assert d.mean().item() <= 6e-4   # measured 2.6e-4
 
 
 def test_ffhq1024_forward_backward():
@@ -125,5 +125,5 @@ def test_ffhq1024_forward_backward():
     d = (img - ref_img.detach()).abs()
     print("ffhq-1024: loss native %s oracle %s; image max-abs %.3e mean-abs %.3e; cos dz %.5f |dz| ratio %.4f"
           % (l_nat.tolist(), l_ref.tolist(), d.max().item(), d.mean().item(), cos(dz, z.grad), (dz.norm() / z.grad.norm()).item()))
-    assert ((l_nat - l_ref.detach()).abs() / (1 + l_ref.detach().abs())).max().item() <= 2e-3
-    assert cos(dz, z.grad) >= 0.99 and d.mean().item() <= 5e-3
+    assert ((l_nat - l_ref.detach()).abs() / (1 + l_ref.detach().abs())).max().item() <= 2e-4   # measured 5e-5
+    assert cos(dz, z.grad) >= 0.9995 and d.mean().item() <= 6e-4   # measured 0.99999, 2.8e-4
