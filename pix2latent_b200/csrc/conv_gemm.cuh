@@ -255,6 +255,13 @@ __device__ __forceinline__ void row_store_f32(float* dst, const float (&v)[CH], 
 }
 
 // transposed 16-bit copy of a chunk of the thread's output row (ConvGemmParams::outT)
+// L2 prefetch of NBYTES contiguous bytes (one request per 128-byte line)
+template <int NBYTES>
+__device__ __forceinline__ void prefetch_l2_row(const void* ptr) {
+#pragma unroll
+    for (int o = 0; o < NBYTES; o += 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const char*>(ptr) + o));
+}
 template <int CH>
 __device__ __forceinline__ void row_store_transposed(const ConvGemmParams& p, int n, int h, int w, int cbase, const float (&v)[CH]) {
     const long hw = static_cast<long>(p.H) * p.W;
@@ -330,6 +337,11 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
         const int w = twi * p.tw + wi, h = thi * p.th + hi, n = tni * p.nb + ni;
         const bool valid = (w < p.W) && (h < p.H) && (n < p.NI);
         const long pix = (static_cast<long>(n) * p.H + h) * p.W + w;
+        if constexpr (MODE == EPI_BWD && !TMA_OUT) {
+            // this thread's saved-activation row on its way into L2 while the tile's main loop still runs: the row load of
+            // the first chunk otherwise waits a full HBM round trip after the accumulator is ready
+            if (p.saved && valid) prefetch_l2_row<BN * 2>(p.saved + pix * p.saved_C + n_tile * BN);
+        }
 
         const uint32_t tab = smem_u32(ctab) + (it & 1) * 3 * BN * 4;  // shared-space byte address
         if (use_tab) {

@@ -59,6 +59,9 @@ __device__ __forceinline__ void epilogue_loop_sg(const ConvGemmParams& p, uint64
         const bool valid = (w < p.W) && (h < p.H) && (n < p.NI);
         const int nn = valid ? n : 0;
         const long pix = (static_cast<long>(n) * p.H + h) * p.W + w;
+        if constexpr (MODE == EPI_BWD) {
+            if (p.saved && valid) prefetch_l2_row<BN * 2>(p.saved + pix * p.saved_C + n_tile * BN);   // see epilogue_loop_direct
+        }
         // per-tile coefficient tables: [0] bias, [1] aff_a (FWD: next layer's modulation; BWD: this layer's), [2] dm
         const uint32_t tab = smem_u32(ctab) + (it & 1) * 3 * BN * 4;
         if (use_tab) {

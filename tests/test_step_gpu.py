@@ -112,7 +112,7 @@ def test_free_running_gradient_optimizer(world):
     # bf16-level gradient noise on near-zero components moves a free-running z by O(lr) there; the
     # teacher-forced test above is the parity statement, this one bounds the drift.
     print("free-running mean |dz| drift %.4f" % (zr - zn).abs().mean().item())
-    assert (zr - zn).abs().mean().item() < 0.08
+    assert (zr - zn).abs().mean().item() < 0.07   # measured 0.033
     assert outs[0].shape[0] == 3
 
 
@@ -131,6 +131,6 @@ def test_autograd_path_uses_native_functions(world):
     l2 = ref_loss(o2, target[None].expand(3, -1, -1, -1), weight[None].expand(3, -1, -1, -1))
     l2.mean().backward()
     print("autograd path: max |dloss| %.2e" % (l - l2).abs().max().item())
-    assert torch.allclose(l, l2, rtol=0, atol=2e-4)
+    assert torch.allclose(l, l2, rtol=0, atol=1.2e-4)   # measured 5.3e-5
     cs = torch.nn.functional.cosine_similarity(z.grad.flatten(), z2.grad.flatten(), dim=0).item()
     assert cs > 0.987
