@@ -269,13 +269,16 @@ class BigGANWork:
 
 
 class SG2Work:
-    """configs[2] / [4]: the population in the reference's chunks (closure.py:32: split_vars by max_batch_size = 9); every
-    chunk is one fused C-ABI call with fresh per-layer noise (rosinality draws N(0,1) noise per layer per forward)."""
+    """configs[2] / [4]: the population with the reference's chunking (closure.py:32: split_vars by max_batch_size = 9) as the
+    product runs it (closure._step_native_sg2): fresh per-layer noise drawn chunk by chunk (rosinality draws N(0,1) noise per
+    layer per forward), per-candidate gradient scales 1/b_chunk, and ONE fused C-ABI call per physical batch of up to 24
+    candidates — a candidate's result does not depend on the batch it is evaluated in (tests/test_determinism_gpu.py)."""
 
     def __init__(self, W, dev, rank):
         from pix2latent_b200 import native
         from pix2latent_b200.loss_functions import ProjectionLoss
         from pix2latent_b200.model.stylegan2 import StyleGAN2
+        from pix2latent_b200.optimizer.closure import SG2_PHYS_BATCH
         self.native, self.W, self.dev, self.n = native, W, dev, W["pop"]
         self.model = StyleGAN2(W["model"], allow_synthetic=True)
         self.loss_fn = ProjectionLoss(allow_synthetic=True)
@@ -284,31 +287,29 @@ class SG2Work:
         self.gen, self.lp = self.model.native, self.loss_fn.native_lpips()
         g = torch.Generator().manual_seed(2 + rank)
         self.z = torch.fmod(torch.randn(self.n, 512, generator=g), 2.0).to(dev)
-        self.bounds, lo = [], 0
-        for c in W["chunks"]:
-            self.bounds.append((lo, lo + c))
-            lo += c
+        self.dloss = torch.cat([torch.full((c,), 1.0 / c) for c in W["chunks"]]).to(dev)
+        self.phys = [(lo, min(self.n, lo + SG2_PHYS_BATCH)) for lo in range(0, self.n, SG2_PHYS_BATCH)]
         self.hz = self.z.cpu().pin_memory()
         self.hl, self.hdz = torch.empty(self.n).pin_memory(), torch.empty(self.n, 512).pin_memory()
         self.z_d = torch.empty(self.n, 512, device=dev)
         self.h2d = self.n * 512 * 4
         self.d2h = self.n * 4 + self.n * 512 * 4
 
-    def _chunks(self, z, grad):
-        out = []
-        for lo, hi in self.bounds:
-            noise = self.model.draw_noise(hi - lo, self.dev)
-            out.append(self.native.sg2_step(self.gen, self.lp, self.tgt, z[lo:hi], noise, grad, 1.0 / (hi - lo), want_img=False))
-        return out
+    def _batches(self, z, grad):
+        parts = [self.model.draw_noise(c, self.dev) for c in self.W["chunks"]]
+        noise = [torch.cat([p[l] for p in parts]) if len(parts) > 1 else parts[0][l] for l in range(len(parts[0]))]
+        return [self.native.sg2_step(self.gen, self.lp, self.tgt, z[lo:hi], [t[lo:hi] for t in noise], grad, 1.0,
+                                     want_img=False, dloss=self.dloss[lo:hi]) for lo, hi in self.phys]
 
     def step_dev(self, grad=True):
-        return torch.cat([o[0] for o in self._chunks(self.z, grad)])
+        out = self._batches(self.z, grad)
+        return out[0][0] if len(out) == 1 else torch.cat([o[0] for o in out])
 
     def step_e2e(self):
         self.z_d.copy_(self.hz, non_blocking=True)
-        out = self._chunks(self.z_d, True)
-        self.hl.copy_(torch.cat([o[0] for o in out]), non_blocking=True)
-        self.hdz.copy_(torch.cat([o[1] for o in out]), non_blocking=True)
+        out = self._batches(self.z_d, True)
+        self.hl.copy_(out[0][0] if len(out) == 1 else torch.cat([o[0] for o in out]), non_blocking=True)
+        self.hdz.copy_(out[0][1] if len(out) == 1 else torch.cat([o[1] for o in out]), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
 
@@ -580,6 +581,9 @@ def run_native(args, rank, world, local_rank):
         "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp16" if native.act_dtype() == torch.float16 else "bf16", "data": "synthetic",
         "config": {"workload": W["name"], "population_per_gpu": n, "global_population": n * world, "chunks": W["chunks"],
+                   "physical_batches": ([n] if W["kind"] == "biggan" else [hi - lo for lo, hi in work.phys]),
+                   "chunking": "the reference's chunks set the per-candidate 1/b_chunk gradient scales (and the RNG draw order); "
+                               "the candidates run in the physical batches listed — results are bitwise independent of the batching",
                    "resolution": W["res"], "lpips_net": "alex",
                    "parallelism": ("candidate-sharded x%d; the timed region ends with one NCCL all_gather of the per-candidate losses" % world)
                    if world > 1 else "single GPU",

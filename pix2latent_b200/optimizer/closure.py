@@ -17,6 +17,7 @@ Two executions of that contract:
     split into mini-batches on a 180 GB device (the reference's chunking is a memory workaround;
     results per candidate do not depend on it).
 """
+import os
 from collections.abc import Sequence
 
 import torch
@@ -367,33 +368,50 @@ def _native_sg2_pair(model, vars, loss_fn):
     return "target" in outs and outs <= {"target", "weight", "loss_mask"}
 
 
+# candidates per physical StyleGAN2 launch sequence (the reference's max_batch_size only sets the 1/b_chunk gradient scales
+# and the order of the RNG draws here; a candidate's result does not depend on the batch it is evaluated in)
+SG2_PHYS_BATCH = int(os.environ.get("P2L_SG2_PHYS_BATCH", "24"))
+
+
 def _step_native_sg2(model, vars, loss_fn, optimize, max_batch_size):
-    """StyleGAN2 (z search): chunk by chunk as the reference does, because hooks (NormalPerturb) and the
-    per-layer noise both draw from torch's RNG between chunks — the draw ORDER is part of the behaviour."""
+    """StyleGAN2 (z search). The reference works chunk by chunk (closure.py:32-66): hooks (NormalPerturb) and the per-layer
+    noise both draw from torch's RNG between chunks, and ``loss.mean().backward()`` scales a chunk's gradients by 1/b_chunk.
+    Here the hooks run and the noise is drawn chunk by chunk IN THAT ORDER, the per-candidate scales follow the reference's
+    chunking (``chunk_scales``), and the whole population goes through the native step in physical batches of up to
+    ``SG2_PHYS_BATCH`` candidates — bitwise the same per candidate (tests/test_determinism_gpu.py), fewer launches."""
     from .. import native
     m = _unwrap(model)
     first = {k: v.data[0] for k, v in vars.output.items()}
     tgt = loss_fn.prepared_target(first["target"], first.get("weight"), first.get("loss_mask"))
-    outs, losses = [], []
+    if optimize:
+        vars.opt.zero_grad()
+    z_list = vars.input.z.data
+    dev = z_list[0].device
+    parts = []
     for chunk in split_vars(vars, size=max_batch_size):
-        if optimize:
-            chunk.opt.zero_grad()
         _run_hooks(chunk.input)
-        z_list = chunk.input.z.data
-        with torch.no_grad():
-            z = torch.stack(z_list)
-        noises = m.draw_noise(z.shape[0], z.device)
-        loss, dz, img = native.sg2_step(m.native, loss_fn.native_lpips(), tgt, z, noises, want_grad=optimize,
-                                        grad_scale=1.0 / chunk.num_samples)
-        if optimize:
-            for i, t in enumerate(z_list):
-                if t.requires_grad:
-                    t.grad = dz[i]
-            chunk.opt.step()
-            chunk.opt.zero_grad()
-        outs.extend(img)
-        losses.extend(loss.cpu().numpy())
-    return torch.stack(outs), losses, {}
+        parts.append(m.draw_noise(chunk.num_samples, dev))
+    noises = [torch.cat([p[l] for p in parts]) if len(parts) > 1 else parts[0][l] for l in range(len(parts[0]))]
+    with torch.no_grad():
+        z = torch.stack(z_list)
+    dloss = chunk_scales(vars, max_batch_size, z.device)
+    n = z.shape[0]
+    outs, losses, grads = [], [], []
+    for lo in range(0, n, SG2_PHYS_BATCH):
+        hi = min(n, lo + SG2_PHYS_BATCH)
+        loss, dz, img = native.sg2_step(m.native, loss_fn.native_lpips(), tgt, z[lo:hi], [t[lo:hi] for t in noises],
+                                        want_grad=optimize, grad_scale=1.0, dloss=dloss[lo:hi])
+        outs.append(img)
+        losses.append(loss)
+        grads.append(dz)
+    if optimize:
+        dz = torch.cat(grads) if len(grads) > 1 else grads[0]
+        for i, t in enumerate(z_list):
+            if t.requires_grad:
+                t.grad = dz[i]
+        vars.opt.step()
+        vars.opt.zero_grad()
+    return (torch.cat(outs) if len(outs) > 1 else outs[0]), list((torch.cat(losses) if len(losses) > 1 else losses[0]).cpu().numpy()), {}
 
 
 def step(model, vars, loss_fn, optimize=True, max_batch_size=9):

@@ -94,3 +94,33 @@ def test_stylegan2_step_twice_same_bits():
     b_ = sg2_step(nat, nl, tgt, z, noise, True, 1.0 / b)
     for name, u, v in zip(("loss", "dz", "img"), a, b_):
         assert torch.equal(u, v), name
+
+
+@pytest.mark.parametrize("split", [(2, 3), (1, 4), (4, 1)])
+def test_stylegan2_candidate_does_not_depend_on_its_batch(split):
+    """What lets closure._step_native_sg2 run the reference's chunks (9/9/4, ...) as ONE physical batch with per-candidate
+    1/b_chunk scales: loss, dz and image of a candidate are the same bits whatever batch it is evaluated in."""
+    from oracle import lpips as olp, stylegan2 as osg
+    from pix2latent_b200.native import NativeLPIPS, NativeStyleGAN2, sg2_step
+    from test_biggan_gpu import lpips_native_state
+    ch = {4: 128, 8: 128, 16: 64, 32: 64, 64: 64}
+    orc = osg.make_stylegan2(64, ch, seed=0).cuda()
+    nat = NativeStyleGAN2(64, ch, orc.model.state_dict())
+    nl = NativeLPIPS("alex", lpips_native_state(olp.make_lpips("alex", seed=0).cuda()))
+    torch.manual_seed(4)
+    b = sum(split)
+    z = torch.randn(b, 512, device="cuda")
+    noise = [torch.randn(s, device="cuda") for s in orc.model.noise_shapes(b)]
+    dloss = torch.tensor([1.0 / split[0]] * split[0] + [1.0 / split[1]] * split[1], device="cuda")
+    tgt = nl.make_target(torch.tanh(torch.randn(3, 64, 64, device="cuda")), None, None, 1, 1.0, 10.0)
+    whole = [t.clone() for t in sg2_step(nat, nl, tgt, z, noise, True, 1.0, dloss=dloss)]
+    lo = 0
+    for n in split:
+        part = sg2_step(nat, nl, tgt, z[lo:lo + n].contiguous(), [t[lo:lo + n].contiguous() for t in noise], True, 1.0,
+                        dloss=dloss[lo:lo + n].contiguous())
+        for name, u, v in zip(("loss", "dz", "img"), whole, part):
+            assert torch.equal(u[lo:lo + n], v), "%s of candidates [%d, %d)" % (name, lo, lo + n)
+        # and the reference's form of the same chunk: scalar 1/b_chunk scale
+        ref = sg2_step(nat, nl, tgt, z[lo:lo + n].contiguous(), [t[lo:lo + n].contiguous() for t in noise], True, 1.0 / n)
+        assert torch.equal(ref[1], part[1]) and torch.equal(ref[0], part[0])
+        lo += n
