@@ -79,8 +79,8 @@ struct ConvGemmParams {
     int img_linear;         // ... without the tanh (planar fp32 output of a tap-expanded head)
     // ---- epilogue, forward: row-wise softmax / softmax-gradient fusions (attention, "attn_fused" option; ROWFUSE
     //      instantiations of the direct-epilogue kernel only). A thread owns one accumulator row, so row reductions are thread-local.
-    float* rowstat;          // pass 1 of a two-pass softmax: (max, sum exp(v - max)) of this tile's columns per row,
-                             // [pixel][n_tiles][2]; nothing else is written
+    float* rowstat;          // pass 1 of a two-pass softmax: (log2e * max, sum exp(v - max)) of this tile's columns per row,
+                             // [pixel][n_tiles][2] (the maximum in the log2 domain: the kernels use ex2); nothing else is written
     const float* rowstat_in; // pass 2: v <- exp(v - M) / L with (M, L) combined from the row's n_tiles partials
     int rowstat_nt;          // n_tiles of the pass-1 launch
     const float* rowsub;     // v <- (v - rowsub[pixel]) * mulin[pixel, c]   (dS = P o (dP - rowsum(dO o O)))
@@ -266,6 +266,11 @@ template <int CH>
 __device__ __forceinline__ void row_store_transposed(const ConvGemmParams& p, int n, int h, int w, int cbase, const float (&v)[CH]) {
     const long hw = static_cast<long>(p.H) * p.W;
     act_t* dst = p.outT + (static_cast<long>(n) * (p.outT_c1 - p.outT_c0) + (cbase - p.outT_c0)) * hw + static_cast<long>(h) * p.W + w;
+    if (cbase >= p.outT_c0 && cbase + CH <= p.outT_c1) {   // the whole chunk lies inside the slice: no per-element tests
+#pragma unroll
+        for (int j = 0; j < CH; ++j) dst[j * hw] = f2a(v[j]);
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < CH; ++j)
         if (cbase + j >= p.outT_c0 && cbase + j < p.outT_c1) dst[j * hw] = f2a(v[j]);
@@ -372,7 +377,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                 float M = -INFINITY;
                 for (int t = 0; t < p.rowstat_nt; ++t) M = fmaxf(M, __ldg(rp + 2 * t));
                 float L = 0.f;
-                for (int t = 0; t < p.rowstat_nt; ++t) L += __ldg(rp + 2 * t + 1) * __expf(__ldg(rp + 2 * t) - M);
+                for (int t = 0; t < p.rowstat_nt; ++t) L += __ldg(rp + 2 * t + 1) * exp2f(__ldg(rp + 2 * t) - M);   // maxima in the log2 domain
                 rs_M = M;
                 rs_invL = 1.f / L;
             }
@@ -440,7 +445,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                         v[q * 4 + 0] = fmaf(alpha, v[q * 4 + 0], b4.x); v[q * 4 + 1] = fmaf(alpha, v[q * 4 + 1], b4.y);
                         v[q * 4 + 2] = fmaf(alpha, v[q * 4 + 2], b4.z); v[q * 4 + 3] = fmaf(alpha, v[q * 4 + 3], b4.w);
                     }
-                } else {
+                } else if (!ROWFUSE || p.bias || alpha != 1.f) {   // the attention GEMMs have neither bias nor gain
 #pragma unroll
                     for (int j = 0; j < CH; ++j) {
                         float b = 0.f;
@@ -461,21 +466,34 @@ __device__ __forceinline__ void epilogue_loop_direct(const ConvGemmParams& p, co
                     row_load_add<CH>(p.resid + rp * p.resid_C + cbase, v, wide_ok(p.resid, p.resid_C * 2));
                 }
                 if constexpr (ROWFUSE && !TMA_OUT) {
+                    // exponentials as ex2(v * log2e - m * log2e): one FFMA + one MUFU per element; the running maximum is
+                    // kept in the log2 domain (rs_max = log2e * max)
+                    constexpr float kLog2e = 1.4426950408889634f;
                     if (p.rowstat) {  // pass 1: online (max, sum exp) over this tile's columns; no stores
                         float cm = -INFINITY;
+                        if (full_chunk) {
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) cm = (cbase + j < p.Cout) ? fmaxf(cm, v[j]) : cm;
-                        const float nm = fmaxf(rs_max, cm);
+                            for (int j = 0; j < CH; ++j) cm = fmaxf(cm, v[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) cm = (cbase + j < p.Cout) ? fmaxf(cm, v[j]) : cm;
+                        }
+                        const float nm = fmaxf(rs_max, cm * kLog2e);
                         float acc = 0.f;
+                        if (full_chunk) {
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) acc += (cbase + j < p.Cout) ? __expf(v[j] - nm) : 0.f;
-                        rs_sum = rs_sum * __expf(rs_max - nm) + acc;
+                            for (int j = 0; j < CH; ++j) acc += exp2f(fmaf(v[j], kLog2e, -nm));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) acc += (cbase + j < p.Cout) ? exp2f(fmaf(v[j], kLog2e, -nm)) : 0.f;
+                        }
+                        rs_sum = rs_sum * exp2f(rs_max - nm) + acc;
                         rs_max = nm;
                         continue;
                     }
                     if (p.rowstat_in) {
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) v[j] = __expf(v[j] - rs_M) * rs_invL;
+                        for (int j = 0; j < CH; ++j) v[j] = exp2f(fmaf(v[j], kLog2e, -rs_M)) * rs_invL;
                     }
                     if (p.mulin) {
                         float mv[CH];

@@ -1,8 +1,8 @@
-"""Per-launch roofline of one bench step: the ncu launch list (profiles/*_launches_bench_ncu.csv, last 162 launches) joined with
+"""Per-launch roofline of one bench step: the ncu launch list (profiles/r2_launches_bench_c2.csv, last 160 launches) joined with
 the analytic FLOPs and minimum HBM bytes of every launch of BigGAN-deep-256 forward + alex-LPIPS + backward for 18 candidates
 (the launch order of pix2latent_b200/csrc/biggan.cu / lpips.cu).
 
-    python scripts/per_layer_roofline.py profiles/r1d_launches_bench_ncu.csv profiles/r1d_per_layer_roofline.md
+    python scripts/per_layer_roofline.py profiles/r2_launches_bench_c2.csv profiles/r2_per_layer_roofline.md
 
 roofline time of a launch = max(FLOPs / tensor peak, bytes / HBM peak) with the MEASURED peaks (MEASURED_PEAKS.json, else
 the values below); `frac` = roofline time / measured duration. Durations under ncu are serialised and cold-cache."""
@@ -69,11 +69,11 @@ def sequence():
         fwd_block(i, blocks[i], False)
     C, Hh, dq, dv = 512, 64, 64, 256
     px, Nk, nq = B * Hh * Hh, Hh * Hh // 4, 2 * 64 + 256
-    conv("attn qkv 1x1", px, nq, C, px * C * E, px * nq * E)
+    conv("attn qkv 1x1 (+ theta^T)", px, nq, C, px * C * E, px * nq * E + px * dq * E)
     glue("attn maxpool phi", px * dq * E * 1.5)
     glue("attn maxpool g", px * dv * E * 1.5)
-    conv("attn S = theta phi^T (fp32 out)", px, Nk, dq, px * dq * E + B * Nk * dq * E, px * Nk * 4)
-    glue("attn softmax", px * Nk * 6)
+    conv("attn softmax pass 1: S = theta phi^T -> (max, sum) per row and N tile", px, Nk, dq, px * dq * E + B * Nk * dq * E, px * (Nk // 128) * 8)
+    conv("attn softmax pass 2: P = exp(S - M) / L, + P^T", px, Nk, dq, px * dq * E + B * Nk * dq * E, 2 * px * Nk * E)
     conv("attn O = P g", px, dv, Nk, px * Nk * E + B * Nk * dv * E, px * dv * E)
     conv("attn out 1x1 +x", px, C, dv, px * dv * E + px * C * E, 2 * px * C * E)
     for i in range(8, 12):
@@ -93,6 +93,7 @@ def sequence():
     for j in range(5):
         h, co = alex[j][2], alex[j][1]
         glue("lpips distance %d" % j, B * h * h * co * E * 2)
+    glue("loss slots -> loss", 0)
     for j in (4, 3, 2, 1, 0):
         ci, co, h, taps, name = alex[j]
         hin = {0: 63, 1: 31, 2: 15, 3: 15, 4: 15}[j]
@@ -106,21 +107,18 @@ def sequence():
     conv("rgb head dgrad", B * R * R, 128, 64, B * R * R * (64 + 128) * E, B * R * R * 128 * E)
     for i in (11, 10, 9, 8):
         bwd_block(i, blocks[i])
-    conv("attn dO = dh Wo", px, dv, C, px * C * E, px * dv * E)
-    conv("attn dP = dO g^T (fp32 out)", px, Nk, dv, px * dv * E + B * Nk * dv * E, px * Nk * 4)
-    glue("attn softmax bwd", px * Nk * (4 + 2 + 2))
+    conv("attn dO = dh Wo (+ dO^T)", px, dv, C, px * C * E, 2 * px * dv * E)
+    glue("attn rowsum(dO o O)", 2 * px * dv * E)
+    conv("attn dS = P o (dO g^T - rowsum), + dS^T", px, Nk, dv, px * dv * E + B * Nk * dv * E + px * Nk * E, 2 * px * Nk * E)
     conv("attn dtheta = dS phi", px, dq, Nk, px * Nk * E, px * dq * E)
-    glue("transpose dS", 2 * px * Nk * E)
-    glue("transpose theta", 2 * px * dq * E)
     conv("attn dphi = dS^T theta", B * Nk, dq, Hh * Hh, px * Nk * E, B * Nk * dq * E)
-    glue("transpose P", 2 * px * Nk * E)
-    glue("transpose dO", 2 * px * dv * E)
     conv("attn dg = P^T dO", B * Nk, dv, Hh * Hh, px * Nk * E, B * Nk * dv * E)
     glue("attn maxpool bwd phi", px * dq * E * 1.5)
     glue("attn maxpool bwd g", px * dv * E * 1.5)
     conv("attn dx = dqkv Wqkv + dh", px, C, nq, px * nq * E + px * C * E, px * C * E)
     for i in range(7, -1, -1):
         bwd_block(i, blocks[i])
+    glue("BN-gradient slots -> sums", 0)
     glue("BN-gradient finalise", 0)
     glue("dcond GEMV (BN tables)", 2 * 24192 * 256 * 4)
     glue("dcond GEMV (gen_z)", 32768 * 256 * 4)
