@@ -207,6 +207,10 @@ class _BaseOptimizer():
     # ---- helpers shared by the concrete loops ------------------------------------------------
     def _start_run(self):
         self.losses, self.outs = [], []
+        if hasattr(self.loss_fn, "invalidate_targets"):
+            # a new run: targets / weights may have been rewritten in place through .data since the last one (such writes do
+            # not bump the tensor version the cache is keyed on); re-preparing the target costs one LPIPS forward
+            self.loss_fn.invalidate_targets()
         self._t_mark = time.time()
 
     def _maybe_log(self, variables, log_at, log_last):
