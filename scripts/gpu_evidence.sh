@@ -24,7 +24,7 @@ timeout -k 5 400 ncu --set full --clock-control none --import-source on -k regex
     -o gpurun_out/${tag}_kernels -f python scripts/one_conv.py "$modes" 2 > gpurun_out/${tag}_ncu_kernels.log 2>&1
 echo "ncu one_conv rc=$?"; ls -la gpurun_out/${tag}_kernels.ncu-rep
 # every tensor-core launch of one BigGAN step (119) and the kernels of one StyleGAN2 chunk: metrics only, exported here
-timeout -k 5 900 ncu --set full --clock-control none -k regex:"conv_gemm|conv3x3" --launch-skip 130 --launch-count 119 \
+timeout -k 5 1500 ncu --set full --clock-control none -k regex:"conv_gemm|conv3x3" --launch-skip 130 --launch-count 119 \
     -o /tmp/${tag}_c2_step -f python bench.py --workload c2 --steps 2 --warmup 1 --ncu > gpurun_out/${tag}_ncu_c2_step.log 2>&1
 echo "ncu c2 step rc=$?"
 ncu -i /tmp/${tag}_c2_step.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_c2_step_raw.csv 2>/dev/null; wc -c gpurun_out/${tag}_ncu_c2_step_raw.csv
