@@ -55,7 +55,7 @@ def _compile(src, force, hdr_m):
 
 def build(force=False, verbose=True):
     os.makedirs(OBJ, exist_ok=True)
-    # objects built with other flags (e.g. a --rowfuse build) are stale whatever their timestamps say
+    # objects built with other flags are stale whatever their timestamps say
     stamp = os.path.join(OBJ, "flags.txt")
     sig = " ".join(FLAGS)
     if not os.path.exists(stamp) or open(stamp).read() != sig:
